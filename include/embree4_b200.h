@@ -1,0 +1,318 @@
+/* embree4_b200.h -- the C-ABI of the B200-native ray tracing kernel library.
+ *
+ * This is the drop-in boundary: a caller compiled against Embree 4.4.1's own
+ * include/embree4/rtcore.h links against libembree4_b200.so unchanged for the
+ * triangle-mesh hot path (device/scene/geometry/buffer objects, rtcCommitScene,
+ * rtcIntersect1/4/8/16, rtcOccluded1/4/8/16).  Every declaration below is
+ * binary compatible with -- and cites -- the reference interface it replaces
+ * (paths relative to the reference tree; configuration of kernels/rtcore_config.h.in:
+ * RTC_MAX_INSTANCE_LEVEL_COUNT=1, EMBREE_GEOMETRY_INSTANCE_ARRAY defined, EMBREE_MIN_WIDTH=0).
+ *
+ * Only plain C types cross this boundary: no C++ classes, no torch types.
+ * Section B is the batched / device-pointer extension ("rtcb200*") that the
+ * throughput configurations use; Embree 4 dropped its stream API
+ * (CHANGELOG.md:101) so there is no reference symbol for it.
+ */
+#ifndef EMBREE4_B200_H
+#define EMBREE4_B200_H
+
+#include <stddef.h>
+#include <stdbool.h>
+#include <sys/types.h> /* ssize_t, as include/embree4/rtcore_common.h:8 */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RTCB200_ALIGN(n) __attribute__((aligned(n)))
+#define RTCB200_API __attribute__((visibility("default")))
+#else
+#define RTCB200_ALIGN(n)
+#define RTCB200_API
+#endif
+
+/* ---- version / constants (kernels/rtcore_config.h.in:10-16, rtcore_common.h:51-54) ---- */
+#define RTC_VERSION_MAJOR 4
+#define RTC_VERSION_MINOR 4
+#define RTC_VERSION_PATCH 1
+#define RTC_VERSION 40401
+#define RTC_VERSION_STRING "4.4.1"
+#define RTC_MAX_INSTANCE_LEVEL_COUNT 1
+#define RTC_GEOMETRY_INSTANCE_ARRAY 1
+#define RTC_INVALID_GEOMETRY_ID ((unsigned int)-1)
+
+/* ---- opaque handles (rtcore_device.h:10-11, rtcore_scene.h:12-15, rtcore_buffer.h:36) ---- */
+typedef struct RTCDeviceTy* RTCDevice;
+typedef struct RTCSceneTy* RTCScene;
+typedef struct RTCGeometryTy* RTCGeometry;
+typedef struct RTCBufferTy* RTCBuffer;
+typedef struct RTCTraversableTy* RTCTraversable; /* on this back-end == the scene, as scene.cpp:928-935 */
+
+/* ---- enums: only the enumerators the triangle path can legally receive are named; values are the
+ *      reference's (rtcore_common.h:57-197, rtcore_device.h:49-100, rtcore_geometry.h:18-51,
+ *      rtcore_buffer.h:11-33, rtcore_scene.h:24-32) ---- */
+enum RTCFormat {
+  RTC_FORMAT_UNDEFINED = 0,
+  RTC_FORMAT_UINT = 0x5001, RTC_FORMAT_UINT2, RTC_FORMAT_UINT3, RTC_FORMAT_UINT4,
+  RTC_FORMAT_FLOAT = 0x9001, RTC_FORMAT_FLOAT2, RTC_FORMAT_FLOAT3, RTC_FORMAT_FLOAT4
+};
+enum RTCBuildQuality {
+  RTC_BUILD_QUALITY_LOW = 0,    /* -> device LBVH (Morton) build      */
+  RTC_BUILD_QUALITY_MEDIUM = 1, /* -> device binned-SAH build         */
+  RTC_BUILD_QUALITY_HIGH = 2,   /* accepted; built as MEDIUM          */
+  RTC_BUILD_QUALITY_REFIT = 3   /* accepted; built as LOW (full rebuild beats refit on this device) */
+};
+enum RTCSceneFlags {
+  RTC_SCENE_FLAG_NONE = 0,
+  RTC_SCENE_FLAG_DYNAMIC = 1 << 0,
+  RTC_SCENE_FLAG_COMPACT = 1 << 1,
+  RTC_SCENE_FLAG_ROBUST = 1 << 2,
+  RTC_SCENE_FLAG_FILTER_FUNCTION_IN_ARGUMENTS = 1 << 3,
+  RTC_SCENE_FLAG_PREFETCH_USM_SHARED_ON_GPU = 1 << 4
+};
+enum RTCRayQueryFlags {
+  RTC_RAY_QUERY_FLAG_NONE = 0,
+  RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER = 1 << 1,
+  RTC_RAY_QUERY_FLAG_INCOHERENT = 0 << 16,
+  RTC_RAY_QUERY_FLAG_COHERENT = 1 << 16
+};
+enum RTCFeatureFlags {
+  RTC_FEATURE_FLAG_NONE = 0,
+  RTC_FEATURE_FLAG_TRIANGLE = 1 << 1,
+  RTC_FEATURE_FLAG_ALL = 0xffffffff
+};
+enum RTCGeometryType { RTC_GEOMETRY_TYPE_TRIANGLE = 0 /* the only type this library accepts */ };
+enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2 };
+enum RTCError {
+  RTC_ERROR_NONE = 0, RTC_ERROR_UNKNOWN = 1, RTC_ERROR_INVALID_ARGUMENT = 2, RTC_ERROR_INVALID_OPERATION = 3,
+  RTC_ERROR_OUT_OF_MEMORY = 4, RTC_ERROR_UNSUPPORTED_CPU = 5, RTC_ERROR_CANCELLED = 6,
+  RTC_ERROR_LEVEL_ZERO_RAYTRACING_SUPPORT_MISSING = 7
+};
+enum RTCDeviceProperty {
+  RTC_DEVICE_PROPERTY_VERSION = 0, RTC_DEVICE_PROPERTY_VERSION_MAJOR = 1, RTC_DEVICE_PROPERTY_VERSION_MINOR = 2,
+  RTC_DEVICE_PROPERTY_VERSION_PATCH = 3,
+  RTC_DEVICE_PROPERTY_NATIVE_RAY4_SUPPORTED = 32, RTC_DEVICE_PROPERTY_NATIVE_RAY8_SUPPORTED = 33,
+  RTC_DEVICE_PROPERTY_NATIVE_RAY16_SUPPORTED = 34,
+  RTC_DEVICE_PROPERTY_BACKFACE_CULLING_SPHERES_ENABLED = 62, RTC_DEVICE_PROPERTY_BACKFACE_CULLING_CURVES_ENABLED = 63,
+  RTC_DEVICE_PROPERTY_RAY_MASK_SUPPORTED = 64, RTC_DEVICE_PROPERTY_BACKFACE_CULLING_ENABLED = 65,
+  RTC_DEVICE_PROPERTY_FILTER_FUNCTION_SUPPORTED = 66, RTC_DEVICE_PROPERTY_IGNORE_INVALID_RAYS_ENABLED = 67,
+  RTC_DEVICE_PROPERTY_COMPACT_POLYS_ENABLED = 68,
+  RTC_DEVICE_PROPERTY_TRIANGLE_GEOMETRY_SUPPORTED = 96, RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED = 97,
+  RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED = 98, RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED = 99,
+  RTC_DEVICE_PROPERTY_USER_GEOMETRY_SUPPORTED = 100, RTC_DEVICE_PROPERTY_POINT_GEOMETRY_SUPPORTED = 101,
+  RTC_DEVICE_PROPERTY_TASKING_SYSTEM = 128, RTC_DEVICE_PROPERTY_JOIN_COMMIT_SUPPORTED = 129,
+  RTC_DEVICE_PROPERTY_PARALLEL_COMMIT_SUPPORTED = 130,
+  RTC_DEVICE_PROPERTY_CPU_DEVICE = 140, RTC_DEVICE_PROPERTY_SYCL_DEVICE = 141
+};
+
+/* ---- I/O records.  Layouts of rtcore_ray.h:11-52 (single) and :55-184 (packets):
+ *      sizeof(RTCRay)=48, sizeof(RTCHit)=48, sizeof(RTCRayHit)=96, sizeof(RTCRayHit16)=1344. ---- */
+struct RTCB200_ALIGN(16) RTCRay {
+  float org_x, org_y, org_z, tnear;
+  float dir_x, dir_y, dir_z, time;
+  float tfar; unsigned int mask, id, flags;
+};
+struct RTCB200_ALIGN(16) RTCHit {
+  float Ng_x, Ng_y, Ng_z, u, v;
+  unsigned int primID, geomID, instID[RTC_MAX_INSTANCE_LEVEL_COUNT], instPrimID[RTC_MAX_INSTANCE_LEVEL_COUNT];
+};
+struct RTCRayHit { struct RTCRay ray; struct RTCHit hit; };
+
+#define RTCB200_PACKET(K, A)                                                                             \
+  struct RTCB200_ALIGN(A) RTCRay##K {                                                                    \
+    float org_x[K], org_y[K], org_z[K], tnear[K], dir_x[K], dir_y[K], dir_z[K], time[K], tfar[K];       \
+    unsigned int mask[K], id[K], flags[K];                                                               \
+  };                                                                                                     \
+  struct RTCB200_ALIGN(A) RTCHit##K {                                                                    \
+    float Ng_x[K], Ng_y[K], Ng_z[K], u[K], v[K];                                                         \
+    unsigned int primID[K], geomID[K], instID[RTC_MAX_INSTANCE_LEVEL_COUNT][K],                          \
+        instPrimID[RTC_MAX_INSTANCE_LEVEL_COUNT][K];                                                     \
+  };                                                                                                     \
+  struct RTCRayHit##K { struct RTCRay##K ray; struct RTCHit##K hit; };
+RTCB200_PACKET(4, 16)
+RTCB200_PACKET(8, 32)
+RTCB200_PACKET(16, 64)
+
+struct RTCB200_ALIGN(16) RTCBounds { /* rtcore_common.h:163-167 */
+  float lower_x, lower_y, lower_z, align0, upper_x, upper_y, upper_z, align1;
+};
+struct RTCB200_ALIGN(16) RTCLinearBounds { struct RTCBounds bounds0, bounds1; };
+
+/* per-query context and arguments (rtcore_common.h:335-361, rtcore_scene.h:34-86).  Host callbacks cannot run
+ * inside a device traversal: `filter`/`intersect`/`occluded` must be NULL, otherwise the call records
+ * RTC_ERROR_INVALID_OPERATION on the device and returns without tracing. */
+struct RTCRayQueryContext {
+  unsigned int instID[RTC_MAX_INSTANCE_LEVEL_COUNT];
+  unsigned int instPrimID[RTC_MAX_INSTANCE_LEVEL_COUNT];
+};
+typedef void (*RTCFilterFunctionN)(const void* args);
+typedef void (*RTCIntersectFunctionN)(const void* args);
+typedef void (*RTCOccludedFunctionN)(const void* args);
+struct RTCIntersectArguments {
+  enum RTCRayQueryFlags flags; enum RTCFeatureFlags feature_mask; struct RTCRayQueryContext* context;
+  RTCFilterFunctionN filter; RTCIntersectFunctionN intersect;
+};
+struct RTCOccludedArguments {
+  enum RTCRayQueryFlags flags; enum RTCFeatureFlags feature_mask; struct RTCRayQueryContext* context;
+  RTCFilterFunctionN filter; RTCOccludedFunctionN occluded;
+};
+static inline void rtcInitRayQueryContext(struct RTCRayQueryContext* c) {
+  c->instID[0] = RTC_INVALID_GEOMETRY_ID; c->instPrimID[0] = RTC_INVALID_GEOMETRY_ID;
+}
+static inline void rtcInitIntersectArguments(struct RTCIntersectArguments* a) {
+  a->flags = RTC_RAY_QUERY_FLAG_INCOHERENT; a->feature_mask = RTC_FEATURE_FLAG_ALL; a->context = NULL;
+  a->filter = NULL; a->intersect = NULL;
+}
+static inline void rtcInitOccludedArguments(struct RTCOccludedArguments* a) {
+  a->flags = RTC_RAY_QUERY_FLAG_INCOHERENT; a->feature_mask = RTC_FEATURE_FLAG_ALL; a->context = NULL;
+  a->filter = NULL; a->occluded = NULL;
+}
+
+typedef void (*RTCErrorFunction)(void* userPtr, enum RTCError code, const char* str);
+typedef bool (*RTCMemoryMonitorFunction)(void* ptr, ssize_t bytes, bool post);
+typedef bool (*RTCProgressMonitorFunction)(void* ptr, double n);
+
+/* =====================================================================================================
+ * Section A -- Embree 4 entry points (same names, argument meaning and error behaviour).
+ * Error convention (kernels/common/rtcore.h:23-49, device.cpp:263-330): no return codes; the FIRST failure is
+ * latched per device (per thread when the device is NULL) until read by rtcGetDeviceError; the optional
+ * error callback sees every failure.  Query functions do no argument checks (rtcore.cpp:604-608).
+ * ===================================================================================================== */
+
+/* device -- rtcore_device.h:15-125 / rtcore.cpp:19-140.  config keys: "verbose=N", "gpu=N" (CUDA ordinal, default:
+ * current device); all other reference keys ("threads", "isa", "tri_accel", ...) are accepted and ignored. */
+RTCB200_API RTCDevice rtcNewDevice(const char* config);
+RTCB200_API void rtcRetainDevice(RTCDevice device);
+RTCB200_API void rtcReleaseDevice(RTCDevice device);
+RTCB200_API ssize_t rtcGetDeviceProperty(RTCDevice device, enum RTCDeviceProperty prop);
+RTCB200_API void rtcSetDeviceProperty(RTCDevice device, enum RTCDeviceProperty prop, ssize_t value);
+RTCB200_API const char* rtcGetErrorString(enum RTCError error);
+RTCB200_API enum RTCError rtcGetDeviceError(RTCDevice device);
+RTCB200_API const char* rtcGetDeviceLastErrorMessage(RTCDevice device);
+RTCB200_API void rtcSetDeviceErrorFunction(RTCDevice device, RTCErrorFunction error, void* userPtr);
+RTCB200_API void rtcSetDeviceMemoryMonitorFunction(RTCDevice device, RTCMemoryMonitorFunction fn, void* userPtr);
+
+/* buffers -- rtcore_buffer.h:39-71 / kernels/common/buffer.h:16-97.  Host memory; uploaded at rtcCommitScene. */
+RTCB200_API RTCBuffer rtcNewBuffer(RTCDevice device, size_t byteSize);
+RTCB200_API RTCBuffer rtcNewSharedBuffer(RTCDevice device, void* ptr, size_t byteSize);
+RTCB200_API RTCBuffer rtcNewBufferHostDevice(RTCDevice device, size_t byteSize);
+RTCB200_API RTCBuffer rtcNewSharedBufferHostDevice(RTCDevice device, void* ptr, size_t byteSize);
+RTCB200_API void* rtcGetBufferData(RTCBuffer buffer);
+RTCB200_API void* rtcGetBufferDataDevice(RTCBuffer buffer);
+RTCB200_API void rtcCommitBuffer(RTCBuffer buffer);
+RTCB200_API void rtcRetainBuffer(RTCBuffer buffer);
+RTCB200_API void rtcReleaseBuffer(RTCBuffer buffer);
+
+/* geometry -- rtcore_geometry.h:130-207 / kernels/common/geometry.cpp:97-135, scene_triangle_mesh.cpp:35-147.
+ * VERTEX slot 0 must be RTC_FORMAT_FLOAT3 (stride >= 12, 4-byte aligned), INDEX must be RTC_FORMAT_UINT3. */
+RTCB200_API RTCGeometry rtcNewGeometry(RTCDevice device, enum RTCGeometryType type);
+RTCB200_API void rtcRetainGeometry(RTCGeometry geometry);
+RTCB200_API void rtcReleaseGeometry(RTCGeometry geometry);
+RTCB200_API void rtcCommitGeometry(RTCGeometry geometry);
+RTCB200_API void rtcEnableGeometry(RTCGeometry geometry);
+RTCB200_API void rtcDisableGeometry(RTCGeometry geometry);
+RTCB200_API void rtcSetGeometryTimeStepCount(RTCGeometry geometry, unsigned int timeStepCount); /* only 1 */
+RTCB200_API void rtcSetGeometryVertexAttributeCount(RTCGeometry geometry, unsigned int n);
+RTCB200_API void rtcSetGeometryMask(RTCGeometry geometry, unsigned int mask);
+RTCB200_API void rtcSetGeometryBuildQuality(RTCGeometry geometry, enum RTCBuildQuality quality);
+RTCB200_API void rtcSetGeometryBuffer(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot,
+                                      enum RTCFormat format, RTCBuffer buffer, size_t byteOffset, size_t byteStride,
+                                      size_t itemCount);
+RTCB200_API void rtcSetSharedGeometryBuffer(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot,
+                                            enum RTCFormat format, const void* ptr, size_t byteOffset,
+                                            size_t byteStride, size_t itemCount);
+RTCB200_API void* rtcSetNewGeometryBuffer(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot,
+                                          enum RTCFormat format, size_t byteStride, size_t itemCount);
+RTCB200_API void* rtcGetGeometryBufferData(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot);
+RTCB200_API void rtcUpdateGeometryBuffer(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot);
+RTCB200_API void rtcSetGeometryUserData(RTCGeometry geometry, void* ptr);
+RTCB200_API void* rtcGetGeometryUserData(RTCGeometry geometry);
+RTCB200_API void rtcSetGeometryEnableFilterFunctionFromArguments(RTCGeometry geometry, bool enable);
+/* host callbacks: a non-NULL function raises RTC_ERROR_INVALID_OPERATION (cannot run on the device) */
+RTCB200_API void rtcSetGeometryIntersectFilterFunction(RTCGeometry geometry, RTCFilterFunctionN filter);
+RTCB200_API void rtcSetGeometryOccludedFilterFunction(RTCGeometry geometry, RTCFilterFunctionN filter);
+
+/* scene -- rtcore_scene.h:89-140 / kernels/common/scene.cpp:152-235,762-1040, rtcore.cpp:293-416 */
+RTCB200_API RTCScene rtcNewScene(RTCDevice device);
+RTCB200_API RTCDevice rtcGetSceneDevice(RTCScene scene); /* returns an extra reference (rtcore.cpp:305) */
+RTCB200_API void rtcRetainScene(RTCScene scene);
+RTCB200_API void rtcReleaseScene(RTCScene scene);
+RTCB200_API RTCTraversable rtcGetSceneTraversable(RTCScene scene);
+RTCB200_API unsigned int rtcAttachGeometry(RTCScene scene, RTCGeometry geometry);
+RTCB200_API void rtcAttachGeometryByID(RTCScene scene, RTCGeometry geometry, unsigned int geomID);
+RTCB200_API void rtcDetachGeometry(RTCScene scene, unsigned int geomID);
+RTCB200_API RTCGeometry rtcGetGeometry(RTCScene scene, unsigned int geomID);
+RTCB200_API RTCGeometry rtcGetGeometryThreadSafe(RTCScene scene, unsigned int geomID);
+RTCB200_API void* rtcGetGeometryUserDataFromScene(RTCScene scene, unsigned int geomID);
+RTCB200_API void rtcCommitScene(RTCScene scene);     /* upload + device BVH build; blocking like the reference */
+RTCB200_API void rtcJoinCommitScene(RTCScene scene); /* == rtcCommitScene, serialised per scene */
+RTCB200_API void rtcSetSceneProgressMonitorFunction(RTCScene scene, RTCProgressMonitorFunction fn, void* ptr);
+RTCB200_API void rtcSetSceneBuildQuality(RTCScene scene, enum RTCBuildQuality quality);
+RTCB200_API void rtcSetSceneFlags(RTCScene scene, enum RTCSceneFlags flags);
+RTCB200_API enum RTCSceneFlags rtcGetSceneFlags(RTCScene scene);
+RTCB200_API void rtcGetSceneBounds(RTCScene scene, struct RTCBounds* bounds_o);
+RTCB200_API void rtcGetSceneLinearBounds(RTCScene scene, struct RTCLinearBounds* bounds_o);
+
+/* ray queries -- rtcore_scene.h:152-215 / rtcore.cpp:599-630 (1), 670-713 (4), 797-841 (8), 858-901 (16),
+ * 918-946 (occluded1), 987-1200 (occluded4/8/16).  Synchronous: the record is updated on return.
+ * `valid[i] == -1` marks an active lane, 0 an inactive one; inactive lanes come back bit-identical.
+ * Closest hit writes ray.tfar, hit.Ng/u/v/primID/geomID/instID[0]/instPrimID[0]; a miss writes nothing.
+ * Occluded writes ray.tfar = -inf on any hit, nothing otherwise. */
+RTCB200_API void rtcIntersect1(RTCScene scene, struct RTCRayHit* rayhit, struct RTCIntersectArguments* args);
+RTCB200_API void rtcIntersect4(const int* valid, RTCScene scene, struct RTCRayHit4* rayhit, struct RTCIntersectArguments* args);
+RTCB200_API void rtcIntersect8(const int* valid, RTCScene scene, struct RTCRayHit8* rayhit, struct RTCIntersectArguments* args);
+RTCB200_API void rtcIntersect16(const int* valid, RTCScene scene, struct RTCRayHit16* rayhit, struct RTCIntersectArguments* args);
+RTCB200_API void rtcOccluded1(RTCScene scene, struct RTCRay* ray, struct RTCOccludedArguments* args);
+RTCB200_API void rtcOccluded4(const int* valid, RTCScene scene, struct RTCRay4* ray, struct RTCOccludedArguments* args);
+RTCB200_API void rtcOccluded8(const int* valid, RTCScene scene, struct RTCRay8* ray, struct RTCOccludedArguments* args);
+RTCB200_API void rtcOccluded16(const int* valid, RTCScene scene, struct RTCRay16* ray, struct RTCOccludedArguments* args);
+RTCB200_API void rtcTraversableIntersect1(RTCTraversable t, struct RTCRayHit* rayhit, struct RTCIntersectArguments* args);
+RTCB200_API void rtcTraversableIntersect4(const int* valid, RTCTraversable t, struct RTCRayHit4* rayhit, struct RTCIntersectArguments* args);
+RTCB200_API void rtcTraversableIntersect8(const int* valid, RTCTraversable t, struct RTCRayHit8* rayhit, struct RTCIntersectArguments* args);
+RTCB200_API void rtcTraversableIntersect16(const int* valid, RTCTraversable t, struct RTCRayHit16* rayhit, struct RTCIntersectArguments* args);
+RTCB200_API void rtcTraversableOccluded1(RTCTraversable t, struct RTCRay* ray, struct RTCOccludedArguments* args);
+RTCB200_API void rtcTraversableOccluded4(const int* valid, RTCTraversable t, struct RTCRay4* ray, struct RTCOccludedArguments* args);
+RTCB200_API void rtcTraversableOccluded8(const int* valid, RTCTraversable t, struct RTCRay8* ray, struct RTCOccludedArguments* args);
+RTCB200_API void rtcTraversableOccluded16(const int* valid, RTCTraversable t, struct RTCRay16* ray, struct RTCOccludedArguments* args);
+
+/* =====================================================================================================
+ * Section B -- batched extension.  One call traces M records; semantics per record are exactly those of the
+ * single-record entry points above.  "Host" variants take host pointers (pageable or pinned) and pipeline
+ * H2D copy / trace / D2H copy in chunks; "Device" variants take device pointers on the scene's GPU and enqueue
+ * on `cuda_stream` (a cudaStream_t passed as void*; NULL = the legacy default stream) without synchronising.
+ * ===================================================================================================== */
+RTCB200_API void rtcb200Intersect1M(RTCScene scene, struct RTCRayHit* rayhits, size_t M, struct RTCIntersectArguments* args);
+RTCB200_API void rtcb200Occluded1M(RTCScene scene, struct RTCRay* rays, size_t M, struct RTCOccludedArguments* args);
+/* M packets of K = 4, 8 or 16 lanes; valid = M*K ints (or NULL = all active) */
+RTCB200_API void rtcb200IntersectNM(const int* valid, RTCScene scene, void* rayhitK, unsigned int K, size_t M, struct RTCIntersectArguments* args);
+RTCB200_API void rtcb200OccludedNM(const int* valid, RTCScene scene, void* rayK, unsigned int K, size_t M, struct RTCOccludedArguments* args);
+RTCB200_API void rtcb200Intersect1MDevice(RTCScene scene, struct RTCRayHit* d_rayhits, size_t M, struct RTCIntersectArguments* args, void* cuda_stream);
+RTCB200_API void rtcb200Occluded1MDevice(RTCScene scene, struct RTCRay* d_rays, size_t M, struct RTCOccludedArguments* args, void* cuda_stream);
+RTCB200_API void rtcb200IntersectNMDevice(const int* d_valid, RTCScene scene, void* d_rayhitK, unsigned int K, size_t M, struct RTCIntersectArguments* args, void* cuda_stream);
+RTCB200_API void rtcb200OccludedNMDevice(const int* d_valid, RTCScene scene, void* d_rayK, unsigned int K, size_t M, struct RTCOccludedArguments* args, void* cuda_stream);
+
+/* Build / traversal statistics of the last commit and, when enabled, of traced rays
+ * (device analogue of EMBREE_STAT_COUNTERS, kernels/common/stat.h:82-90). */
+struct RTCB200SceneStats {
+  unsigned long long num_triangles;      /* valid triangles in the BVH (after the validity filter) */
+  unsigned long long num_nodes;          /* 80-byte BVH8 nodes */
+  unsigned long long node_bytes, tri_bytes;
+  double build_ms;                       /* device time of the last rtcCommitScene build */
+  double sah_cost;                       /* SAH cost of the committed BVH8 (area-weighted, c_trav=1, c_tri=1) */
+  unsigned long long trav_rays, trav_nodes, trav_tris; /* accumulated while counting is enabled */
+  unsigned int builder;                  /* 0 = LBVH, 1 = binned SAH */
+  unsigned int max_depth;
+};
+RTCB200_API void rtcb200GetSceneStats(RTCScene scene, struct RTCB200SceneStats* out);
+RTCB200_API void rtcb200SetSceneStatCounters(RTCScene scene, int enable); /* routes queries to the counting kernel */
+RTCB200_API void rtcb200ResetSceneStatCounters(RTCScene scene);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+RTCB200_API unsigned long long rtcb200GetLaunchCount(void);
+/* device time (ms) of the most recent batched Device trace launch, measured with events on its stream; -1 if none */
+RTCB200_API double rtcb200GetLastTraceMs(RTCScene scene);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMBREE4_B200_H */
