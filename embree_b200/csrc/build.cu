@@ -1,0 +1,507 @@
+// build.cu -- device-wide BVH construction for sm_100a.
+//
+// Replaces (reference paths): kernels/builders/primrefgen.cpp:14-60 + scene_triangle_mesh.h:194-215,293-305
+// (PrimRef generation with the validity filter), kernels/builders/bvh_builder_morton.h:71-102,312-432
+// (Morton codes, split at the highest differing bit), common/algorithms/parallel_sort.h:254-454 (8-bit LSD radix
+// sort), kernels/builders/bvh_builder_sah.h:216-313 + heuristic_binning.h:17-393 (binned SAH, see build_sah.cu),
+// kernels/geometry/triangle.h:98-120 (leaf fill) and kernels/bvh/bvh_node_aabb.h:33-116 (node emission).
+//
+// Pipeline (all on one stream, counts stay on the device except two scalar read-backs):
+//   primref_gen -> morton_keys -> radix sort (8-bit digits, warp-match ranking) ->
+//   { lbvh_hierarchy + refit | binned SAH top-down (build_sah.cu) } -> collapse to 80-byte BVH8 nodes
+//   (level-synchronous, greedy largest-area opening) -> leaf_pack (48-byte triangle records).
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+#include "rtk_device.h"
+
+namespace rtk {
+
+static std::atomic<unsigned long long> g_launches{0};
+unsigned long long launch_count() { return g_launches.load(); }
+void count_launch(unsigned n) { g_launches.fetch_add(n); }
+
+#define CK(x)                                                                                        \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess) {                                                                         \
+      snprintf(errmsg, 256, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return (int)e_;                                                                                \
+    }                                                                                                \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+__host__ inline float ord2f_host(int i) { int j = i >= 0 ? i : i ^ 0x7FFFFFFF; float f; memcpy(&f, &j, 4); return f; }
+
+struct BuildInfo {        // device-resident scalars of one build
+  int geom_lo[3], geom_hi[3];   // ordered-int encoded bounds of all valid triangles
+  int cent_lo[3], cent_hi[3];   // bounds of (lower + upper) -- "center2" as in primref.h:60-62
+  uint32_t num_valid;
+  uint32_t node_tail;           // BVH8 nodes allocated so far (== collapse queue tail)
+  uint32_t tri_tail;            // triangle records allocated so far
+  uint32_t pad;
+  double sah;                   // accumulated SAH cost numerator
+};
+
+__device__ __forceinline__ int find_geom(const uint32_t* __restrict__ offs, int ngeoms, uint32_t p) {
+  int lo = 0, hi = ngeoms;  // offs has ngeoms+1 entries, offs[g] <= p < offs[g+1]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (offs[mid] <= p) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void load_tri_verts(const GeomDesc& g, uint32_t lp, float v[9], bool& ok) {
+  const uint32_t* ip = reinterpret_cast<const uint32_t*>(g.idx + (uint64_t)lp * g.istride);
+  const uint32_t i0 = ip[0], i1 = ip[1], i2 = ip[2];
+  ok = (i0 < g.nverts) & (i1 < g.nverts) & (i2 < g.nverts);          // scene_triangle_mesh.h:197-199
+  if (!ok) return;
+  const float* p0 = reinterpret_cast<const float*>(g.verts + (uint64_t)i0 * g.vstride);
+  const float* p1 = reinterpret_cast<const float*>(g.verts + (uint64_t)i1 * g.vstride);
+  const float* p2 = reinterpret_cast<const float*>(g.verts + (uint64_t)i2 * g.vstride);
+  v[0] = p0[0]; v[1] = p0[1]; v[2] = p0[2];
+  v[3] = p1[0]; v[4] = p1[1]; v[5] = p1[2];
+  v[6] = p2[0]; v[7] = p2[1]; v[8] = p2[2];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) ok &= (v[k] > -kFltLarge) & (v[k] < kFltLarge);  // isvalid(), vec3fa.h:304 (NaN fails)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 1. PrimRef generation + scene / centroid bounds
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ offs,
+                                                   int ngeoms, uint32_t ntot, PrimRef* __restrict__ out,
+                                                   BuildInfo* __restrict__ info) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool ok = false;
+  if (p < ntot) {
+    const int g = find_geom(offs, ngeoms, p);
+    float v[9];
+    load_tri_verts(geoms[g], p - offs[g], v, ok);
+    if (ok) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = fminf(fminf(v[a], v[3 + a]), v[6 + a]);
+        hi[a] = fmaxf(fmaxf(v[a], v[3 + a]), v[6 + a]);
+      }
+    }
+    PrimRef pr;
+    pr.lox = lo[0]; pr.loy = lo[1]; pr.loz = lo[2]; pr.prim = p;
+    pr.hix = hi[0]; pr.hiy = hi[1]; pr.hiz = hi[2]; pr.valid = ok ? 1u : 0u;
+    out[p] = pr;
+  }
+  // warp reduce, then one set of atomics per warp
+  float c_lo[3], c_hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { c_lo[a] = ok ? lo[a] + hi[a] : INFINITY; c_hi[a] = ok ? lo[a] + hi[a] : -INFINITY; }
+  unsigned cnt = ok ? 1u : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
+      c_lo[a] = fminf(c_lo[a], __shfl_xor_sync(0xFFFFFFFFu, c_lo[a], o));
+      c_hi[a] = fmaxf(c_hi[a], __shfl_xor_sync(0xFFFFFFFFu, c_hi[a], o));
+    }
+    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&info->geom_lo[a], f2ord(lo[a]));
+      atomicMax(&info->geom_hi[a], f2ord(hi[a]));
+      atomicMin(&info->cent_lo[a], f2ord(c_lo[a]));
+      atomicMax(&info->cent_hi[a], f2ord(c_hi[a]));
+    }
+    atomicAdd(&info->num_valid, cnt);
+  }
+}
+
+__global__ void init_info(BuildInfo* info) {
+  for (int a = 0; a < 3; ++a) {
+    info->geom_lo[a] = info->cent_lo[a] = f2ord(INFINITY);
+    info->geom_hi[a] = info->cent_hi[a] = f2ord(-INFINITY);
+  }
+  info->num_valid = 0; info->node_tail = 1; info->tri_tail = 0; info->pad = 0; info->sah = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 2. Morton keys: 21 bits per axis of the box centre, invalid primitives get the maximum key
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t expand21(uint32_t v) {
+  uint64_t x = v & 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void __launch_bounds__(256) morton_keys(const PrimRef* __restrict__ prims, uint32_t ntot,
+                                                   const BuildInfo* __restrict__ info, uint64_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ vals) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ntot) return;
+  const PrimRef pr = prims[p];
+  uint64_t key = ~0ull;
+  if (pr.valid) {
+    const float c[3] = {pr.lox + pr.hix, pr.loy + pr.hiy, pr.loz + pr.hiz};
+    uint32_t q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float lo = ord2f(info->cent_lo[a]), hi = ord2f(info->cent_hi[a]);
+      const float ext = hi - lo;
+      float f = ext > 0.0f ? (c[a] - lo) / ext : 0.0f;
+      f = fminf(fmaxf(f * 2097152.0f, 0.0f), 2097151.0f);
+      q[a] = (uint32_t)f;
+    }
+    key = (expand21(q[2]) << 2) | (expand21(q[1]) << 1) | expand21(q[0]);  // < 2^63, so never collides with ~0
+  }
+  keys[p] = key;
+  vals[p] = p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 3. LSD radix sort of (u64 key, u32 value), 8-bit digits.  Per pass: tile histograms -> scan -> stable scatter
+//    with warp-level multi-split ranking (__match_any_sync).
+// ---------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per block
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist(const uint64_t* __restrict__ keys, uint32_t n, int shift,
+                                                         uint32_t* __restrict__ block_hist, uint32_t nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t idx = base + i * RS_THREADS + threadIdx.x;
+    if (idx < n) atomicAdd(&h[(uint32_t)(keys[idx] >> shift) & 0xFFu], 1u);
+  }
+  __syncthreads();
+  block_hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major
+}
+
+// one block per digit: exclusive scan of that digit's row (over tiles); row total -> digit_total[d]
+__global__ void __launch_bounds__(256) radix_scan_rows(uint32_t* __restrict__ block_hist, uint32_t nblocks,
+                                                       uint32_t* __restrict__ digit_total) {
+  __shared__ uint32_t wsum[8];
+  __shared__ uint32_t carry;
+  uint32_t* row = block_hist + (size_t)blockIdx.x * nblocks;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nblocks; base += 256) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nblocks ? row[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+    const uint32_t incl = x + woff + carry;
+    if (i < nblocks) row[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(256) radix_scan_digits(const uint32_t* __restrict__ digit_total,
+                                                         uint32_t* __restrict__ digit_base) {
+  __shared__ uint32_t s[256];
+  s[threadIdx.x] = digit_total[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int d = 0; d < 256; ++d) { const uint32_t c = s[d]; s[d] = run; run += c; }
+  }
+  __syncthreads();
+  digit_base[threadIdx.x] = s[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                            uint64_t* __restrict__ kout, uint32_t* __restrict__ vout,
+                                                            uint32_t n, int shift, const uint32_t* __restrict__ row_prefix,
+                                                            const uint32_t* __restrict__ digit_base, uint32_t nblocks) {
+  __shared__ uint32_t wcnt[RS_THREADS / 32][256];
+  __shared__ uint32_t gbase[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  // warp w owns the contiguous slice [w*32*ITEMS, (w+1)*32*ITEMS) of the tile: stable order = (warp, item, lane)
+  const uint32_t wbase = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+  uint64_t k[RS_ITEMS];
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t idx = wbase + i * 32 + lane;
+    k[i] = idx < n ? kin[idx] : ~0ull;  // out-of-range slots sit at the very end of the last tile: harmless
+  }
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t d = (uint32_t)(k[i] >> shift) & 0xFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+    if (lane == __ffs(peers) - 1) wcnt[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;  // RS_THREADS == 256 digits
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; ++w) { const uint32_t c = wcnt[w][d]; wcnt[w][d] = run; run += c; }
+    gbase[d] = digit_base[d] + row_prefix[(size_t)d * nblocks + blockIdx.x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t idx = wbase + i * 32 + lane;
+    const uint32_t d = (uint32_t)(k[i] >> shift) & 0xFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (lane == leader) { old = wcnt[warp][d]; wcnt[warp][d] = old + __popc(peers); }
+    old = __shfl_sync(0xFFFFFFFFu, old, leader);
+    __syncwarp();
+    if (idx < n) {
+      const uint32_t pos = gbase[d] + old + __popc(peers & ((1u << lane) - 1u));
+      kout[pos] = k[i];
+      vout[pos] = vin[idx];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 4. LBVH hierarchy (parallel radix tree over the sorted keys, duplicates split by index) + bottom-up refit
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lbvh_hierarchy(const uint64_t* __restrict__ keys, int n, Node2* __restrict__ nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  lbvh_node(keys, n, i, nodes);
+}
+
+__global__ void __launch_bounds__(256) lbvh_leaves_refit(const PrimRef* __restrict__ prims, const uint32_t* __restrict__ sorted,
+                                                         int n, Node2* nodes, uint32_t* __restrict__ flags) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const PrimRef pr = prims[sorted[j]];
+  Node2& lf = nodes[n - 1 + j];
+  lf.lox = pr.lox; lf.loy = pr.loy; lf.loz = pr.loz; lf.left = j;
+  lf.hix = pr.hix; lf.hiy = pr.hiy; lf.hiz = pr.hiz; lf.right = -1;
+  lf.first = (uint32_t)j; lf.count = 1;
+  if (n == 1) { lf.parent = 0xFFFFFFFFu; return; }
+  uint32_t cur = lf.parent;
+  __threadfence();
+  while (cur != 0xFFFFFFFFu) {
+    if (atomicAdd(&flags[cur], 1u) == 0) return;  // first arrival: the sibling subtree is not finished yet
+    __threadfence();
+    Node2& nd = nodes[cur];
+    const float4* L = reinterpret_cast<const float4*>(&nodes[nd.left]);
+    const float4* R = reinterpret_cast<const float4*>(&nodes[nd.right]);
+    const float4 l0 = __ldcg(L), l1 = __ldcg(L + 1), r0 = __ldcg(R), r1 = __ldcg(R + 1);
+    nd.lox = fminf(l0.x, r0.x); nd.loy = fminf(l0.y, r0.y); nd.loz = fminf(l0.z, r0.z);
+    nd.hix = fmaxf(l1.x, r1.x); nd.hiy = fmaxf(l1.y, r1.y); nd.hiz = fmaxf(l1.z, r1.z);
+    __threadfence();
+    cur = nd.parent;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 5. Collapse the binary tree into BVH8 nodes, one tree level per launch.  Queue slot q == BVH8 node id q.
+// ---------------------------------------------------------------------------------------------------
+struct DeviceAlloc {  // allocation callbacks of collapse_node() on the device: global atomic bump counters
+  BuildInfo* info;
+  __device__ __forceinline__ uint32_t nodes(uint32_t k) const { return atomicAdd(&info->node_tail, k); }
+  __device__ __forceinline__ uint32_t tris(uint32_t k) const { return atomicAdd(&info->tri_tail, k); }
+  __device__ __forceinline__ void sah(double x) const { atomicAdd(&info->sah, x); }
+};
+
+__global__ void __launch_bounds__(128) collapse_level(const Node2* __restrict__ n2, uint32_t* __restrict__ src,
+                                                      uint32_t begin, uint32_t end, Node8* __restrict__ n8,
+                                                      uint32_t* __restrict__ tri_src, const uint32_t* __restrict__ sorted,
+                                                      BuildInfo* info, float inv_root_area) {
+  const uint32_t q = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= end) return;
+  collapse_node(n2, src, q, n8, tri_src, sorted, inv_root_area, DeviceAlloc{info});
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 6. leaf_pack: gather vertices through the index buffer, store v0, e1 = v0 - v1, e2 = v2 - v0 (triangle.h:98-120)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ offs, int ngeoms,
+                                                 const uint32_t* __restrict__ tri_src, uint32_t ntris, TriRec* __restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntris) return;
+  const uint32_t p = tri_src[t];
+  const int g = find_geom(offs, ngeoms, p);
+  const GeomDesc gd = geoms[g];
+  float v[9];
+  bool ok;
+  load_tri_verts(gd, p - offs[g], v, ok);
+  float4 a, b, c;
+  a.x = v[0]; a.y = v[1]; a.z = v[2]; a.w = __uint_as_float(p - offs[g]);
+  b.x = __fsub_rn(v[0], v[3]); b.y = __fsub_rn(v[1], v[4]); b.z = __fsub_rn(v[2], v[5]); b.w = __uint_as_float(gd.geomID);
+  c.x = __fsub_rn(v[6], v[0]); c.y = __fsub_rn(v[7], v[1]); c.z = __fsub_rn(v[8], v[2]); c.w = __uint_as_float(gd.mask);
+  float4* dst = reinterpret_cast<float4*>(&out[t]);
+  dst[0] = a; dst[1] = b; dst[2] = c;
+}
+
+// binned-SAH top-down build of the binary tree (build_sah.cu)
+int build_sah_tree(const PrimRef* prims, uint32_t* sorted, uint32_t n, Node2* nodes, const float* cent_bounds,
+                   cudaStream_t stream, char* errmsg);
+
+// ---------------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+
+void free_scene(SceneGPU& s) {
+  if (s.nodes) cudaFree(s.nodes);
+  if (s.tris) cudaFree(s.tris);
+  if (s.d_stat) cudaFree(s.d_stat);
+  s.nodes = nullptr; s.tris = nullptr; s.d_stat = nullptr;
+  s.num_nodes = s.num_tris = 0; s.root_valid = 0;
+}
+
+int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind, cudaStream_t st, char* errmsg) {
+  errmsg[0] = 0;
+  if (s.nodes) { cudaFree(s.nodes); s.nodes = nullptr; }
+  if (s.tris) { cudaFree(s.tris); s.tris = nullptr; }
+  s.num_nodes = s.num_tris = 0; s.root_valid = 0; s.max_depth = 0; s.sah_cost = 0; s.builder = kind;
+  for (int a = 0; a < 3; ++a) { s.bounds[a] = INFINITY; s.bounds[3 + a] = -INFINITY; }
+  if (!s.d_stat) { CK(cudaMalloc(&s.d_stat, 3 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s.d_stat, 0, 24, st)); }
+
+  std::vector<uint32_t> offs(ngeoms + 1, 0);
+  uint64_t tot64 = 0;
+  for (int g = 0; g < ngeoms; ++g) { offs[g] = (uint32_t)tot64; tot64 += geoms[g].ntris; }
+  if (tot64 >= 0x7FFFFFFFull) { snprintf(errmsg, 256, "too many triangles (%llu)", (unsigned long long)tot64); return -1; }
+  offs[ngeoms] = (uint32_t)tot64;
+  const uint32_t ntot = (uint32_t)tot64;
+  if (ntot == 0) return 0;  // empty scene: queries return immediately (bvh_intersector1.cpp:39)
+
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  CK(cudaEventRecord(ev0, st));
+
+  DevBuf<GeomDesc> d_geoms; DevBuf<uint32_t> d_offs; DevBuf<BuildInfo> d_info; DevBuf<PrimRef> d_prims;
+  DevBuf<uint64_t> d_k0, d_k1; DevBuf<uint32_t> d_v0, d_v1, d_hist, d_dtot, d_dbase;
+  CK(d_geoms.alloc(ngeoms)); CK(d_offs.alloc(ngeoms + 1)); CK(d_info.alloc(1)); CK(d_prims.alloc(ntot));
+  CK(d_k0.alloc(ntot)); CK(d_k1.alloc(ntot)); CK(d_v0.alloc(ntot)); CK(d_v1.alloc(ntot));
+  const uint32_t nb = (ntot + RS_TILE - 1) / RS_TILE;
+  CK(d_hist.alloc((size_t)256 * nb)); CK(d_dtot.alloc(256)); CK(d_dbase.alloc(256));
+  CK(cudaMemcpyAsync(d_geoms.p, geoms, sizeof(GeomDesc) * ngeoms, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_offs.p, offs.data(), 4 * (ngeoms + 1), cudaMemcpyHostToDevice, st));
+
+  const uint32_t g256 = (ntot + 255) / 256;
+  init_info<<<1, 1, 0, st>>>(d_info.p);
+  primref_gen<<<g256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, ntot, d_prims.p, d_info.p);
+  morton_keys<<<g256, 256, 0, st>>>(d_prims.p, ntot, d_info.p, d_k0.p, d_v0.p);
+  count_launch(3);
+  uint64_t *kin = d_k0.p, *kout = d_k1.p;
+  uint32_t *vin = d_v0.p, *vout = d_v1.p;
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 8 * pass;
+    radix_hist<<<nb, RS_THREADS, 0, st>>>(kin, ntot, shift, d_hist.p, nb);
+    radix_scan_rows<<<256, 256, 0, st>>>(d_hist.p, nb, d_dtot.p);
+    radix_scan_digits<<<1, 256, 0, st>>>(d_dtot.p, d_dbase.p);
+    radix_scatter<<<nb, RS_THREADS, 0, st>>>(kin, vin, kout, vout, ntot, shift, d_hist.p, d_dbase.p, nb);
+    count_launch(4);
+    std::swap(kin, kout); std::swap(vin, vout);
+  }
+  CK(cudaGetLastError());
+  BuildInfo hinfo;
+  CK(cudaMemcpyAsync(&hinfo, d_info.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint32_t n = hinfo.num_valid;  // valid primitives are sorted[0..n); invalid ones carry key ~0 at the end
+  if (n == 0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return 0; }
+  for (int a = 0; a < 3; ++a) { s.bounds[a] = ord2f_host(hinfo.geom_lo[a]); s.bounds[3 + a] = ord2f_host(hinfo.geom_hi[a]); }
+
+  // ---- binary tree
+  DevBuf<Node2> d_n2; DevBuf<uint32_t> d_flags;
+  CK(d_n2.alloc((size_t)2 * n)); CK(d_flags.alloc(n));
+  uint32_t root2 = 0;
+  if (kind == BUILDER_SAH && n > 1) {
+    float cb[6];
+    for (int a = 0; a < 3; ++a) { cb[a] = ord2f_host(hinfo.cent_lo[a]); cb[3 + a] = ord2f_host(hinfo.cent_hi[a]); }
+    int r = build_sah_tree(d_prims.p, vin, n, d_n2.p, cb, st, errmsg);
+    if (r) return r;
+    root2 = 0;
+  } else {
+    CK(cudaMemsetAsync(d_flags.p, 0, 4 * (size_t)n, st));
+    const uint32_t gn = (n + 255) / 256;
+    if (n > 1) { lbvh_hierarchy<<<gn, 256, 0, st>>>(kin, (int)n, d_n2.p); count_launch(); }
+    lbvh_leaves_refit<<<gn, 256, 0, st>>>(d_prims.p, vin, (int)n, d_n2.p, d_flags.p);
+    count_launch();
+    root2 = (n == 1) ? 0u : 0u;  // n == 1: the only node is leaf id n-1+0 == 0
+  }
+
+  // ---- collapse into BVH8, level by level
+  DevBuf<uint32_t> d_src, d_trisrc;
+  s.node_capacity = (size_t)n + 1; s.tri_capacity = n;
+  CK(d_src.alloc(s.node_capacity)); CK(d_trisrc.alloc(n));
+  Node8* n8 = nullptr;
+  CK(cudaMalloc(&n8, s.node_capacity * sizeof(Node8)));
+  CK(cudaMemcpyAsync(d_src.p, &root2, 4, cudaMemcpyHostToDevice, st));
+  const float ex = s.bounds[3] - s.bounds[0], ey = s.bounds[4] - s.bounds[1], ez = s.bounds[5] - s.bounds[2];
+  const float ra = ex * (ey + ez) + ey * ez;
+  const float inv_ra = ra > 0.0f ? 1.0f / ra : 0.0f;
+  uint32_t begin = 0, end = 1, depth = 0;
+  while (begin < end) {
+    collapse_level<<<(end - begin + 127) / 128, 128, 0, st>>>(d_n2.p, d_src.p, begin, end, n8, d_trisrc.p, vin, d_info.p, inv_ra);
+    count_launch();
+    uint32_t tail;
+    CK(cudaMemcpyAsync(&tail, &d_info.p->node_tail, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    begin = end; end = tail; ++depth;
+    if (depth > 4096) { snprintf(errmsg, 256, "collapse did not terminate"); cudaFree(n8); return -1; }
+  }
+  CK(cudaMemcpyAsync(&hinfo, d_info.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (hinfo.tri_tail != n) { snprintf(errmsg, 256, "internal: packed %u of %u triangles", hinfo.tri_tail, n); cudaFree(n8); return -1; }
+  if (depth >= (uint32_t)kStackSize) { snprintf(errmsg, 256, "BVH too deep for the traversal stack (%u)", depth); cudaFree(n8); return -1; }
+
+  // ---- triangle records, then shrink the node array to its final size
+  TriRec* tris = nullptr;
+  CK(cudaMalloc(&tris, (size_t)n * sizeof(TriRec)));
+  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, tris);
+  count_launch();
+  Node8* n8_final = nullptr;
+  CK(cudaMalloc(&n8_final, (size_t)end * sizeof(Node8)));
+  CK(cudaMemcpyAsync(n8_final, n8, (size_t)end * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
+  CK(cudaEventRecord(ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  cudaFree(n8);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  s.nodes = n8_final; s.tris = tris; s.num_nodes = end; s.num_tris = n; s.root_valid = 1;
+  s.build_ms = ms; s.sah_cost = hinfo.sah; s.max_depth = depth;
+  return 0;
+}
+
+}  // namespace rtk

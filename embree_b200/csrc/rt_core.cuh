@@ -1,0 +1,546 @@
+// rt_core.cuh -- data layout and per-ray / per-node core routines of the B200 ray tracing kernels.
+//
+// Everything here is `RT_HD` (__host__ __device__) on purpose: the CUDA kernels in build.cu / trace.cu call
+// these routines per thread, and tests/emu/ compiles the very same header with g++ so the node encoding,
+// the traversal loop and the triangle test can be debugged in a container without a GPU.  The host build is
+// a TEST tool only; the product library contains just the device instantiations.
+//
+// Reference semantics restated here (paths relative to the reference tree):
+//   ray setup        kernels/bvh/node_intersector1.h:34-57, common/math/vec3fa.h:167-172 (rcp_safe)
+//   slab test        kernels/bvh/node_intersector1.h:484-531  (we test 8 children of a *quantised* node)
+//   traversal loop   kernels/bvh/bvh_intersector1.cpp:31-114 (closest), :116-197 (any hit)
+//   triangle test    kernels/geometry/triangle_intersector_moeller.h:69-111 (+ :29-36 finalize)
+//   hit commit       kernels/geometry/intersector_epilog.h:220-302 (closest), :304-369 (occluded)
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define RT_HD __host__ __device__ __forceinline__
+#define RT_D __device__ __forceinline__
+#else
+#define RT_HD inline
+#endif
+
+namespace rtk {
+
+// ------------------------------------------------------------------------------------------------
+// HBM layout
+// ------------------------------------------------------------------------------------------------
+// BVH8 node, 80 bytes = 5 x 16 B (compressed wide BVH: 8-bit child boxes on a per-node power-of-two grid).
+//   w0 : px, py, pz (float bits)                | ex | ey<<8 | ez<<16 | imask<<24
+//   w1 : child_base | tri_base | meta[0..3] | meta[4..7]
+//   w2 : qlo_x[0..3] qlo_x[4..7] qlo_y[0..3] qlo_y[4..7]
+//   w3 : qlo_z[0..3] qlo_z[4..7] qhi_x[0..3] qhi_x[4..7]
+//   w4 : qhi_y[0..3] qhi_y[4..7] qhi_z[0..3] qhi_z[4..7]
+// meta[i]: 0 = empty slot; internal child: 0b001'sssss with sssss = 24 + i; leaf: high 3 bits = triangle count
+// in unary (1 -> 001, 2 -> 011, 3 -> 111), low 5 bits = offset of its first triangle from tri_base (0..23).
+// imask bit i is set when slot i holds an internal child; internal children of a node are stored consecutively
+// from child_base in slot order, triangles of its leaf slots consecutively from tri_base.
+struct alignas(16) Node8 {
+  uint32_t w[20];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+
+// Triangle record, 48 bytes = 3 x 16 B; what the reference keeps per lane of a Triangle4 block
+// (kernels/geometry/triangle.h:98-120: v0, e1 = v0 - v1, e2 = v2 - v0) plus ids and the geometry mask.
+struct alignas(16) TriRec {
+  float v0x, v0y, v0z; uint32_t primID;
+  float e1x, e1y, e1z; uint32_t geomID;
+  float e2x, e2y, e2z; uint32_t mask;
+};
+static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
+
+// Binary build tree (LBVH or binned SAH) that is collapsed into Node8s.  ids: [0, n-1) internal, [n-1, 2n-1) leaves.
+struct alignas(16) Node2 {
+  float lox, loy, loz; int32_t left;    // child id (internal); for a leaf: index into the sorted primitive list
+  float hix, hiy, hiz; int32_t right;   // child id (internal); for a leaf: -1
+  uint32_t first, count;                // range [first, first+count) of sorted primitives below this node
+  uint32_t parent, pad;
+};
+static_assert(sizeof(Node2) == 48, "Node2 must be 48 bytes");
+
+struct alignas(16) PrimRef {  // kernels/builders/primref.h:24-28 (lower, geomID | upper, primID) -> ours keeps a global prim index
+  float lox, loy, loz; uint32_t prim;   // global triangle index (geometry found by prefix search)
+  float hix, hiy, hiz; uint32_t valid;
+};
+
+struct Ray {  // RTCRay, include/embree4/rtcore_ray.h:11-28
+  float ox, oy, oz, tnear, dx, dy, dz, time, tfar;
+  uint32_t mask, id, flags;
+};
+struct Hit {  // what a closest-hit query commits (intersector_epilog.h:285-299)
+  float t, u, v, ngx, ngy, ngz;
+  uint32_t primID, geomID;
+};
+
+constexpr float kMinRcpInput = 1e-18f;   // common/math/constants.h:18
+constexpr float kFltLarge = 1.844E18f;   // common/math/constants.h:21
+constexpr uint32_t kInvalidID = 0xFFFFFFFFu;
+constexpr int kMaxLeafTris = 3;
+constexpr int kStackSize = 64;           // entries of 8 B; each BVH8 level pushes at most one node group
+
+// ------------------------------------------------------------------------------------------------
+// small portable helpers
+// ------------------------------------------------------------------------------------------------
+RT_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+RT_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+RT_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+RT_HD int popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+// fused multiply-add / explicitly rounded mul: the reference's AVX2/AVX-512 paths contract madd/msub
+// (common/math/vec3.h:204,209), so bit-equal Ng needs the same contraction and NO other.
+RT_HD float fma_rn(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+RT_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  volatile float r = a * b; return r;  // volatile: forbid host-side contraction
+#endif
+}
+RT_HD float sub_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  volatile float r = a - b; return r;
+#endif
+}
+RT_HD float msub(float a, float b, float c) { return fma_rn(a, b, -c); }            // a*b - c
+RT_HD float dot3(float ax, float ay, float az, float bx, float by, float bz) {      // vec3.h:204
+  return fma_rn(ax, bx, fma_rn(ay, by, mul_rn(az, bz)));
+}
+RT_HD float rcp_safe(float d) { return 1.0f / (fabsf(d) < kMinRcpInput ? kMinRcpInput : d); }
+
+// ------------------------------------------------------------------------------------------------
+// triangle test: MoellerTrumboreIntersector1<M>::intersect restated for one lane
+// returns true when the triangle is hit inside (tnear, tfar]; outputs T,U,V scaled by absDen and Ng.
+// ------------------------------------------------------------------------------------------------
+struct TriHit { float T, U, V, absDen, ngx, ngy, ngz; };
+
+RT_HD bool tri_test(const Ray& r, float tfar, float v0x, float v0y, float v0z, float e1x, float e1y, float e1z,
+                    float e2x, float e2y, float e2z, TriHit& h) {
+  const float cx = sub_rn(v0x, r.ox), cy = sub_rn(v0y, r.oy), cz = sub_rn(v0z, r.oz);          // C = v0 - O
+  const float rx = msub(cy, r.dz, mul_rn(cz, r.dy));                                           // R = cross(C, D)
+  const float ry = msub(cz, r.dx, mul_rn(cx, r.dz));
+  const float rz = msub(cx, r.dy, mul_rn(cy, r.dx));
+  const float ngx = msub(e2y, e1z, mul_rn(e2z, e1y));                                          // Ng = cross(e2, e1)
+  const float ngy = msub(e2z, e1x, mul_rn(e2x, e1z));
+  const float ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
+  const float den = dot3(ngx, ngy, ngz, r.dx, r.dy, r.dz);
+  const float absDen = fabsf(den);
+  const uint32_t sgn = f2u(den) & 0x80000000u;
+  const float U = u2f(f2u(dot3(rx, ry, rz, e2x, e2y, e2z)) ^ sgn);
+  const float V = u2f(f2u(dot3(rx, ry, rz, e1x, e1y, e1z)) ^ sgn);
+  if (!((den != 0.0f) & (U >= 0.0f) & (V >= 0.0f) & (U + V <= absDen))) return false;
+  const float T = u2f(f2u(dot3(ngx, ngy, ngz, cx, cy, cz)) ^ sgn);
+  if (!((mul_rn(absDen, r.tnear) < T) & (T <= mul_rn(absDen, tfar)))) return false;
+  h.T = T; h.U = U; h.V = V; h.absDen = absDen; h.ngx = ngx; h.ngy = ngy; h.ngz = ngz;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Node8 encoding (build side)
+// ------------------------------------------------------------------------------------------------
+struct ChildBox { float lo[3], hi[3]; };
+
+// smallest biased exponent e such that (extent / 2^(e-127)) <= 255
+RT_HD uint32_t grid_exponent(float extent) {
+  if (!(extent > 0.0f)) return 1;                     // degenerate axis: any tiny scale works, q = 0
+  // 2^k >= extent/255  ->  start from the exponent of extent/255 and bump while 255 * 2^k < extent
+  float s = extent / 255.0f;
+  uint32_t e = (f2u(s) >> 23) & 0xFF;
+  if ((f2u(s) & 0x7FFFFF) != 0) e += 1;               // round the scale up to a power of two
+  if (e < 1) e = 1;
+  if (e > 254) e = 254;
+  while (e < 254 && u2f(e << 23) * 255.0f < extent) e += 1;
+  return e;
+}
+
+RT_HD float round_down_add(float p, float q, float s) {  // p + q*s rounded towards -inf
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rd(q, s, p);
+#else
+  double d = (double)p + (double)q * (double)s; float f = (float)d; if ((double)f > d) f = nextafterf(f, -INFINITY); return f;
+#endif
+}
+RT_HD float round_up_add(float p, float q, float s) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_ru(q, s, p);
+#else
+  double d = (double)p + (double)q * (double)s; float f = (float)d; if ((double)f < d) f = nextafterf(f, INFINITY); return f;
+#endif
+}
+
+// Quantise n child boxes against the node box [plo, phi] and write the geometric part of the node.
+// Conservative by construction: decoded lo <= true lo and decoded hi >= true hi (checked with directed rounding).
+RT_HD void encode_node_boxes(Node8& nd, const float plo[3], const float phi[3], const ChildBox* cb, const uint8_t* slot_of,
+                             int n) {
+  uint32_t e[3];
+  float scale[3], inv[3];
+  for (int a = 0; a < 3; ++a) {
+    e[a] = grid_exponent(phi[a] - plo[a]);
+    // the subtraction above may round down: make sure the top grid line still covers phi
+    while (e[a] < 254 && round_up_add(plo[a], 255.0f, u2f(e[a] << 23)) < phi[a]) e[a] += 1;
+    scale[a] = u2f(e[a] << 23);
+    inv[a] = 1.0f / scale[a];
+  }
+  nd.w[0] = f2u(plo[0]); nd.w[1] = f2u(plo[1]); nd.w[2] = f2u(plo[2]);
+  nd.w[3] = (nd.w[3] & 0xFF000000u) | e[0] | (e[1] << 8) | (e[2] << 16);
+  uint8_t q[6][8];
+  for (int a = 0; a < 6; ++a) for (int s = 0; s < 8; ++s) q[a][s] = 0;
+  for (int c = 0; c < n; ++c) {
+    const int s = slot_of[c];
+    for (int a = 0; a < 3; ++a) {
+      int lo = (int)floorf((cb[c].lo[a] - plo[a]) * inv[a]);
+      int hi = (int)ceilf((cb[c].hi[a] - plo[a]) * inv[a]);
+      lo = lo < 0 ? 0 : (lo > 255 ? 255 : lo);
+      hi = hi < 0 ? 0 : (hi > 255 ? 255 : hi);
+      while (lo > 0 && round_up_add(plo[a], (float)lo, scale[a]) > cb[c].lo[a]) --lo;
+      while (hi < 255 && round_down_add(plo[a], (float)hi, scale[a]) < cb[c].hi[a]) ++hi;
+      q[a][s] = (uint8_t)lo;
+      q[3 + a][s] = (uint8_t)hi;
+    }
+  }
+  for (int a = 0; a < 6; ++a) {
+    const uint32_t lo4 = q[a][0] | (q[a][1] << 8) | (q[a][2] << 16) | ((uint32_t)q[a][3] << 24);
+    const uint32_t hi4 = q[a][4] | (q[a][5] << 8) | (q[a][6] << 16) | ((uint32_t)q[a][7] << 24);
+    nd.w[8 + 2 * a] = lo4;
+    nd.w[8 + 2 * a + 1] = hi4;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LBVH: internal node i of the binary radix tree over n sorted 64-bit keys (duplicates are split by index), after
+// Karras 2012; the reference's Morton builder splits at the highest differing bit the same way
+// (kernels/builders/bvh_builder_morton.h:312-353).
+// ------------------------------------------------------------------------------------------------
+RT_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return x ? __builtin_clzll(x) : 64;
+#endif
+}
+RT_HD int lbvh_delta(const uint64_t* keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint64_t x = keys[i] ^ keys[j];
+  return x ? clz64(x) : 64 + clz32((uint32_t)(i ^ j));
+}
+RT_HD void lbvh_node(const uint64_t* keys, int n, int i, Node2* nodes) {
+  const int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = lbvh_delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = lbvh_delta(keys, n, i, j);
+  int s = 0;
+  for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+    if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t == 1) break;
+  }
+  const int gamma = i + s * d + (d < 0 ? d : 0);
+  const int first = i < j ? i : j, last = i < j ? j : i;
+  const int left = (first == gamma) ? (n - 1 + gamma) : gamma;
+  const int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+  Node2& nd = nodes[i];
+  nd.left = left; nd.right = right;
+  nd.first = (uint32_t)first; nd.count = (uint32_t)(last - first + 1);
+  nodes[left].parent = (uint32_t)i;
+  nodes[right].parent = (uint32_t)i;
+  if (i == 0) nd.parent = 0xFFFFFFFFu;
+}
+
+// Choose which BVH2 nodes become the (<= 8) children of one BVH8 node: start from the node's two children and
+// repeatedly open the candidate with the largest surface area (the reference's heuristic for N-wide nodes,
+// kernels/builders/bvh_builder_sah.h:252-279 "split the largest-area child until N children").
+// A candidate with <= kMaxLeafTris primitives may stay closed and becomes a leaf slot.
+RT_HD float half_area(const Node2& n) {
+  const float dx = n.hix - n.lox, dy = n.hiy - n.loy, dz = n.hiz - n.loz;
+  return dx * (dy + dz) + dy * dz;
+}
+
+RT_HD int select_children(const Node2* nodes, uint32_t root, uint32_t* cand /*[8]*/) {
+  int n = 0;
+  const Node2& r = nodes[root];
+  if (r.right < 0) { cand[0] = root; return 1; }        // the build tree is a single leaf
+  cand[n++] = (uint32_t)r.left;
+  cand[n++] = (uint32_t)r.right;
+  while (n < 8) {
+    int best = -1;
+    float bestA = -1.0f;
+    for (int i = 0; i < n; ++i) {
+      const Node2& c = nodes[cand[i]];
+      if (c.right < 0) continue;                         // a single primitive cannot be opened
+      const float a = half_area(c);
+      if (a > bestA) { bestA = a; best = i; }
+    }
+    if (best < 0) break;
+    const Node2& c = nodes[cand[best]];
+    cand[best] = (uint32_t)c.left;
+    cand[n++] = (uint32_t)c.right;
+  }
+  return n;
+}
+
+// Assign children to slots so that (slot ^ octant-mask) orders them front-to-back for every ray octant:
+// greedy maximisation of dot(child centre - node centre, slot direction) (slot bit a set = +axis a).
+RT_HD void assign_slots(const ChildBox* cb, int n, const float plo[3], const float phi[3], uint8_t* slot_of) {
+  float cost[8][8];
+  const float cx = 0.5f * (plo[0] + phi[0]), cy = 0.5f * (plo[1] + phi[1]), cz = 0.5f * (plo[2] + phi[2]);
+  for (int c = 0; c < n; ++c) {
+    const float dx = 0.5f * (cb[c].lo[0] + cb[c].hi[0]) - cx;
+    const float dy = 0.5f * (cb[c].lo[1] + cb[c].hi[1]) - cy;
+    const float dz = 0.5f * (cb[c].lo[2] + cb[c].hi[2]) - cz;
+    for (int s = 0; s < 8; ++s)
+      cost[c][s] = ((s & 1) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 4) ? dz : -dz);
+  }
+  uint32_t used_slots = 0, done = 0;
+  for (int it = 0; it < n; ++it) {
+    int bc = -1, bs = -1;
+    float best = -INFINITY;
+    for (int c = 0; c < n; ++c) {
+      if (done & (1u << c)) continue;
+      for (int s = 0; s < 8; ++s) {
+        if (used_slots & (1u << s)) continue;
+        if (cost[c][s] > best || bc < 0) { best = cost[c][s]; bc = c; bs = s; }
+      }
+    }
+    slot_of[bc] = (uint8_t)bs;
+    used_slots |= 1u << bs;
+    done |= 1u << bc;
+  }
+}
+
+// Emit BVH8 node q from the binary subtree src[q]: choose <= 8 children, give them octant-ordered slots, quantise
+// their boxes, reserve the node ids of internal children / the triangle slots of leaf children through `alloc`
+// (atomic bump counters on the device), and queue the internal children (src[child id] = binary node).
+template <typename Alloc>
+RT_HD void collapse_node(const Node2* n2, uint32_t* src, uint32_t q, Node8* n8, uint32_t* tri_src, const uint32_t* sorted,
+                         float inv_root_area, const Alloc& alloc) {
+  const uint32_t root = src[q];
+  uint32_t cand[8];
+  const int n = select_children(n2, root, cand);
+  const Node2 self = n2[root];
+  const float plo[3] = {self.lox, self.loy, self.loz}, phi[3] = {self.hix, self.hiy, self.hiz};
+  ChildBox cb[8];
+  uint32_t cnt[8], first[8];
+  for (int c = 0; c < n; ++c) {
+    const Node2 ch = n2[cand[c]];
+    cb[c].lo[0] = ch.lox; cb[c].lo[1] = ch.loy; cb[c].lo[2] = ch.loz;
+    cb[c].hi[0] = ch.hix; cb[c].hi[1] = ch.hiy; cb[c].hi[2] = ch.hiz;
+    cnt[c] = ch.count; first[c] = ch.first;
+  }
+  uint8_t slot_of[8];
+  assign_slots(cb, n, plo, phi, slot_of);
+  // order children by slot; internal children and leaf triangles are numbered in slot order
+  int child_at[8];
+  for (int s = 0; s < 8; ++s) child_at[s] = -1;
+  for (int c = 0; c < n; ++c) child_at[slot_of[c]] = c;
+  uint32_t n_inner = 0, n_tris = 0, imask = 0;
+  for (int s = 0; s < 8; ++s) {
+    const int c = child_at[s];
+    if (c < 0) continue;
+    if (cnt[c] > (uint32_t)kMaxLeafTris) { imask |= 1u << s; ++n_inner; } else n_tris += cnt[c];
+  }
+  const uint32_t child_base = n_inner ? alloc.nodes(n_inner) : 0;
+  const uint32_t tri_base = n_tris ? alloc.tris(n_tris) : 0;
+  Node8 nd;
+  for (int k = 0; k < 20; ++k) nd.w[k] = 0;
+  encode_node_boxes(nd, plo, phi, cb, slot_of, n);
+  nd.w[3] = (nd.w[3] & 0x00FFFFFFu) | (imask << 24);
+  nd.w[4] = child_base; nd.w[5] = tri_base;
+  uint32_t meta[8];
+  uint32_t ir = 0, toff = 0;
+  double sah = 0.0;
+  for (int s = 0; s < 8; ++s) {
+    meta[s] = 0;
+    const int c = child_at[s];
+    if (c < 0) continue;
+    if (imask & (1u << s)) {
+      meta[s] = (1u << 5) | (24u + (uint32_t)s);
+      src[child_base + ir] = cand[c];
+      ++ir;
+    } else {
+      const uint32_t k = cnt[c];
+      meta[s] = (((1u << k) - 1u) << 5) | toff;
+      for (uint32_t t = 0; t < k; ++t) tri_src[tri_base + toff + t] = sorted[first[c] + t];
+      toff += k;
+      const float dx = cb[c].hi[0] - cb[c].lo[0], dy = cb[c].hi[1] - cb[c].lo[1], dz = cb[c].hi[2] - cb[c].lo[2];
+      sah += (double)((dx * (dy + dz) + dy * dz) * inv_root_area) * k;
+    }
+  }
+  nd.w[6] = meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24);
+  nd.w[7] = meta[4] | (meta[5] << 8) | (meta[6] << 16) | (meta[7] << 24);
+  n8[q] = nd;
+  sah += (double)(half_area(self) * inv_root_area);
+  alloc.sah(sah);
+}
+
+// ------------------------------------------------------------------------------------------------
+// traversal (per ray).  `NodeLoad` / `TriLoad` abstract the 16-byte loads so the host emulation can use plain
+// pointers and the device can use the read-only / cache-hinted path.
+// ------------------------------------------------------------------------------------------------
+struct u32x4 { uint32_t x, y, z, w; };
+struct TravStats { uint32_t nodes, tris; };
+
+RT_HD uint32_t sign_extend_s8x4(uint32_t x) {  // each byte: bit7 set -> 0xFF else 0x00
+  return ((x >> 7) & 0x01010101u) * 0xFFu;
+}
+
+// Slab test of the 8 quantised children of one node; returns the hit mask in the layout
+// [31:24] internal children ordered by traversal priority, [23:0] one bit per triangle of the node's leaf slots.
+template <bool ANYHIT>
+RT_HD uint32_t node_hitmask(const u32x4& n0, const u32x4& n1, const u32x4& n2, const u32x4& n3, const u32x4& n4,
+                            float ox, float oy, float oz, float idx, float idy, float idz, bool negx, bool negy,
+                            bool negz, float tnear, float tfar, uint32_t oct_inv4) {
+  const uint32_t e = n0.w;
+  // per-axis: t = q * (2^e * idir) + (p - org) * idir
+  const float sx = u2f((e & 0xFFu) << 23) * idx;
+  const float sy = u2f(((e >> 8) & 0xFFu) << 23) * idy;
+  const float sz = u2f(((e >> 16) & 0xFFu) << 23) * idz;
+  const float bx = (u2f(n0.x) - ox) * idx;
+  const float by = (u2f(n0.y) - oy) * idy;
+  const float bz = (u2f(n0.z) - oz) * idz;
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t meta4 = half ? n1.w : n1.z;
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    // near / far planes per axis picked by the ray's direction sign
+    const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+    const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+    const uint32_t nx = negx ? qhix : qlox, fx = negx ? qlox : qhix;
+    const uint32_t ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
+    const uint32_t nz = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sh = 8 * j;
+      const float tnx = fma_rn((float)((nx >> sh) & 0xFFu), sx, bx);
+      const float tny = fma_rn((float)((ny >> sh) & 0xFFu), sy, by);
+      const float tnz = fma_rn((float)((nz >> sh) & 0xFFu), sz, bz);
+      const float tfx = fma_rn((float)((fx >> sh) & 0xFFu), sx, bx);
+      const float tfy = fma_rn((float)((fy >> sh) & 0xFFu), sy, by);
+      const float tfz = fma_rn((float)((fz >> sh) & 0xFFu), sz, bz);
+      const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tnear));
+      // pad the exit distance by 2 ulp so rounding in the FMAs can never cull a box that exact arithmetic
+      // accepts (the reference's robust mode pads by 3 ulp, node_intersector1.h:106-110)
+      const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar)) * 1.0000003f;
+      if (tmin <= tmax) {
+        const uint32_t bits = (child_bits4 >> sh) & 0xFFu;
+        const uint32_t idx = (bit_index4 >> sh) & 0xFFu;
+        hitmask |= bits << idx;
+      }
+    }
+  }
+  (void)ANYHIT;
+  return hitmask;
+}
+
+// One closest-hit (ANYHIT=false) or any-hit (ANYHIT=true) query.  On a closest hit `hit` is filled and
+// r.tfar shrunk; for any-hit the function returns true as soon as one triangle is accepted.
+template <bool ANYHIT, bool STATS, typename NodeLoad, typename TriLoad>
+RT_HD bool traverse(Ray& r, Hit& hit, const NodeLoad& ldn, const TriLoad& ldt, uint32_t root_valid, TravStats* st) {
+  if (!root_valid) return false;                                         // empty scene (bvh_intersector1.cpp:39)
+  if (ANYHIT && r.tfar < 0.0f) return false;                             // already occluded (:128-129)
+  const float idx = rcp_safe(r.dx), idy = rcp_safe(r.dy), idz = rcp_safe(r.dz);
+  const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;    // near/far plane selectors (node_intersector1.h:47-52)
+  const uint32_t oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
+  const uint32_t oct_inv4 = (7u - oct) * 0x01010101u;
+  const float tnear_c = fmaxf(r.tnear, 0.0f);                            // TravRay clamps (bvh_intersector1.cpp:65)
+  float tfar_c = fmaxf(r.tfar, 0.0f);
+  float tfar_tri = r.tfar;                                               // the triangle test sees the raw value
+  bool found = false;
+
+  uint32_t stack_x[kStackSize], stack_y[kStackSize];
+  int sp = 0;
+  // node group: x = child_base, y = hits[31:24] | imask[7:0]; triangle group: x = tri_base, y = hits[23:0]
+  // The root is entered as "child_base 0, imask 0, one pending internal child": slot decoding then yields node 0.
+  uint32_t ngx = 0, ngy = 0x80000000u;
+  uint32_t tgx = 0, tgy = 0;
+
+  while (true) {
+    if (ngy & 0xFF000000u) {
+      const int bit = 31 - clz32(ngy);                                   // highest priority pending child
+      ngy &= ~(1u << bit);
+      if (ngy & 0xFF000000u) { stack_x[sp] = ngx; stack_y[sp] = ngy; ++sp; }
+      const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
+      const uint32_t node_index = ngx + (uint32_t)popc32(ngy & 0xFFu & ((1u << slot) - 1u));
+      const u32x4 n0 = ldn(node_index, 0), n1 = ldn(node_index, 1), n2 = ldn(node_index, 2), n3 = ldn(node_index, 3),
+                  n4 = ldn(node_index, 4);
+      if (STATS) st->nodes++;
+      const uint32_t hm = node_hitmask<ANYHIT>(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz,
+                                               tnear_c, tfar_c, oct_inv4);
+      ngx = n1.x;
+      ngy = (hm & 0xFF000000u) | (n0.w >> 24);
+      tgx = n1.y;
+      tgy = hm & 0x00FFFFFFu;
+    } else {
+      tgx = ngx; tgy = ngy; ngx = 0; ngy = 0;                            // popped entry was a triangle group
+    }
+    while (tgy) {
+      const int tb = 31 - clz32(tgy);
+      tgy &= ~(1u << tb);
+      const uint32_t ti = tgx + (uint32_t)tb;
+      const u32x4 a = ldt(ti, 0), b = ldt(ti, 1), c = ldt(ti, 2);
+      if (STATS) st->tris++;
+      TriHit th;
+      if (tri_test(r, tfar_tri, u2f(a.x), u2f(a.y), u2f(a.z), u2f(b.x), u2f(b.y), u2f(b.z), u2f(c.x), u2f(c.y),
+                   u2f(c.z), th)) {
+        if ((c.w & r.mask) == 0) continue;                               // ray mask (intersector_epilog.h:256-262)
+        if (ANYHIT) return true;
+        const float rcpAbsDen = 1.0f / th.absDen;                        // finalize(): t,u,v = T,U,V * rcp(absDen)
+        hit.t = th.T * rcpAbsDen; hit.u = th.U * rcpAbsDen; hit.v = th.V * rcpAbsDen;
+        hit.ngx = th.ngx; hit.ngy = th.ngy; hit.ngz = th.ngz;
+        hit.primID = a.w; hit.geomID = b.w;
+        tfar_tri = hit.t;                                                // ray.tfar = hit.vt[i]
+        tfar_c = fmaxf(hit.t, 0.0f);                                     // tray.tfar = ray.tfar (bvh_intersector1.cpp:105)
+        found = true;
+      }
+    }
+    if ((ngy & 0xFF000000u) == 0) {
+      if (sp == 0) break;
+      --sp;
+      ngx = stack_x[sp]; ngy = stack_y[sp];
+    }
+  }
+  if (found) r.tfar = tfar_tri;
+  return found;
+}
+
+}  // namespace rtk

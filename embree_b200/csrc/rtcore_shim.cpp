@@ -1,0 +1,801 @@
+// rtcore_shim.cpp -- host side of the drop-in boundary: the Embree 4 object model (device / buffer / geometry /
+// scene handles, reference counts, the sticky-first-error convention, the geometry commit state machine) and the
+// extern "C" rtc* entry points declared in include/embree4_b200.h, in front of the CUDA code in build.cu / trace.cu.
+//
+// Mirrors (reference paths): kernels/common/rtcore.cpp (entry points), rtcore.h:23-74 (error funnel),
+// device.cpp:263-330 (error slots), geometry.cpp:97-135 (modCounter / MODIFIED / COMMITTED),
+// scene_triangle_mesh.cpp:35-147 (buffer validation), scene.cpp:762-1040 + scene_verify.cpp:11-22 (commit),
+// buffer.h:16-97 (shared vs owned memory).  There is NO CPU traversal or build in this file or anywhere in the
+// library: if CUDA is unavailable, rtcNewDevice fails with RTC_ERROR_UNKNOWN and returns NULL.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/embree4_b200.h"
+#include "rtk_device.h"
+
+namespace {
+
+struct ApiError {
+  RTCError code;
+  std::string msg;
+};
+[[noreturn]] void fail(RTCError c, const char* m) { throw ApiError{c, m}; }
+
+struct ErrSlot {
+  RTCError code = RTC_ERROR_NONE;
+  std::string msg;
+};
+
+struct DeviceImpl;
+thread_local ErrSlot t_noDeviceError;                               // errors with no device (device.cpp:288-310)
+thread_local std::unordered_map<const DeviceImpl*, ErrSlot> t_err;  // per device, per thread (device.cpp:263-286)
+
+struct RefCounted {
+  std::atomic<long> rc{1};
+  virtual ~RefCounted() {}
+  void retain() { rc.fetch_add(1); }
+  void release() { if (rc.fetch_sub(1) == 1) delete this; }
+};
+
+std::mutex g_deviceMutex;  // device create/retain/release take a global lock (rtcore.cpp:17,23)
+
+struct DeviceImpl : RefCounted {
+  int gpu = 0;
+  int verbose = 0;
+  RTCErrorFunction errFn = nullptr;
+  void* errPtr = nullptr;
+  RTCMemoryMonitorFunction memFn = nullptr;
+  void* memPtr = nullptr;
+  cudaDeviceProp prop{};
+  void report(RTCError code, const char* msg) {
+    if (verbose >= 1) fprintf(stderr, "Embree(b200): %s, (%s)\n", rtcGetErrorString(code), msg ? msg : "");
+    if (errFn) errFn(errPtr, code, msg);
+    ErrSlot& s = t_err[this];
+    if (s.code == RTC_ERROR_NONE) { s.code = code; if (msg && *msg) s.msg = msg; }
+  }
+  void use() const { cudaSetDevice(gpu); }
+};
+
+void process_error(DeviceImpl* d, RTCError code, const char* msg) {
+  if (!d) {
+    if (t_noDeviceError.code == RTC_ERROR_NONE) { t_noDeviceError.code = code; if (msg && *msg) t_noDeviceError.msg = msg; }
+    return;
+  }
+  d->report(code, msg);
+}
+
+#define API_BEGIN try {
+#define API_END(dev)                                                                     \
+  }                                                                                      \
+  catch (std::bad_alloc&) { process_error(dev, RTC_ERROR_OUT_OF_MEMORY, "out of memory"); } \
+  catch (ApiError & e) { process_error(dev, e.code, e.msg.c_str()); }                    \
+  catch (std::exception & e) { process_error(dev, RTC_ERROR_UNKNOWN, e.what()); }        \
+  catch (...) { process_error(dev, RTC_ERROR_UNKNOWN, "unknown exception caught"); }
+#define VERIFY_HANDLE(h) if ((h) == nullptr) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid argument")
+
+void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    if (e == cudaErrorMemoryAllocation) fail(RTC_ERROR_OUT_OF_MEMORY, buf);
+    fail(RTC_ERROR_UNKNOWN, buf);
+  }
+}
+
+struct BufferImpl : RefCounted {
+  DeviceImpl* dev;
+  char* ptr = nullptr;
+  size_t bytes = 0;
+  bool shared = false;
+  BufferImpl(DeviceImpl* d, size_t n, void* user) : dev(d), bytes(n), shared(user != nullptr) {
+    dev->retain();
+    if (user) ptr = static_cast<char*>(user);
+    else {
+      const size_t padded = (n + 15) & ~size_t(15);  // owned memory is 16-byte rounded (buffer.h:29-30)
+      if (posix_memalign(reinterpret_cast<void**>(&ptr), 64, padded ? padded : 16) != 0) throw std::bad_alloc();
+      memset(ptr, 0, padded ? padded : 16);
+    }
+  }
+  ~BufferImpl() override {
+    if (!shared) free(ptr);
+    dev->release();
+  }
+};
+
+struct BufferView {
+  BufferImpl* buf = nullptr;
+  size_t offset = 0, stride = 0, count = 0;
+  RTCFormat format = RTC_FORMAT_UNDEFINED;
+  void set(BufferImpl* b, size_t off, size_t st, size_t n, RTCFormat f) {
+    if (b) b->retain();
+    if (buf) buf->release();
+    buf = b; offset = off; stride = st; count = n; format = f;
+  }
+  const char* data() const { return buf ? buf->ptr + offset : nullptr; }
+  ~BufferView() { if (buf) buf->release(); }
+};
+
+enum class GeomState { MODIFIED, COMMITTED };
+
+struct GeometryImpl : RefCounted {
+  DeviceImpl* dev;
+  BufferView vertices, indices;
+  std::vector<BufferView> attribs;
+  unsigned mask = 1;  // reference default (geometry.cpp:48)
+  bool enabled = true;
+  RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
+  void* userPtr = nullptr;
+  GeomState state = GeomState::MODIFIED;
+  unsigned modCounter = 1;
+  explicit GeometryImpl(DeviceImpl* d) : dev(d) { dev->retain(); }
+  ~GeometryImpl() override { dev->release(); }
+  void update() { ++modCounter; state = GeomState::MODIFIED; }  // geometry.cpp:97-101
+};
+
+struct SceneImpl : RefCounted {
+  DeviceImpl* dev;
+  std::mutex geomMutex;     // attach/detach are thread safe (README.md:921-924)
+  std::mutex commitMutex;
+  std::vector<GeometryImpl*> geoms;      // index == geomID
+  std::vector<unsigned> committedCounter;  // modCounter snapshot of the last commit (scene.cpp:878-884)
+  RTCSceneFlags flags = RTC_SCENE_FLAG_NONE;
+  RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
+  bool flagsModified = true;  // forces the first commit (scene_verify.cpp:11-22 isModified())
+  bool everCommitted = false;
+  RTCProgressMonitorFunction progFn = nullptr;
+  void* progPtr = nullptr;
+  rtk::SceneGPU gpu;
+  std::vector<void*> deviceBuffers;  // uploaded vertex/index bytes of the current commit
+  bool statCounters = false;
+  double lastTraceMs = -1.0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  explicit SceneImpl(DeviceImpl* d) : dev(d) { dev->retain(); gpu.device = d->gpu; }
+  ~SceneImpl() override {
+    dev->use();
+    for (GeometryImpl* g : geoms) if (g) g->release();
+    for (void* p : deviceBuffers) cudaFree(p);
+    rtk::free_scene(gpu);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    dev->release();
+  }
+  bool isModified() {
+    if (flagsModified) return true;
+    for (size_t i = 0; i < geoms.size(); ++i) {
+      const unsigned cur = geoms[i] ? geoms[i]->modCounter : 0u;
+      const unsigned old = i < committedCounter.size() ? committedCounter[i] : 0u;
+      if (cur != old) return true;
+    }
+    return geoms.size() != committedCounter.size();
+  }
+};
+
+DeviceImpl* D(RTCDevice h) { return reinterpret_cast<DeviceImpl*>(h); }
+BufferImpl* B(RTCBuffer h) { return reinterpret_cast<BufferImpl*>(h); }
+GeometryImpl* G(RTCGeometry h) { return reinterpret_cast<GeometryImpl*>(h); }
+SceneImpl* S(RTCScene h) { return reinterpret_cast<SceneImpl*>(h); }
+
+// "key=value,key=value" device configuration (state.cpp:263-457); unknown keys are accepted and ignored
+void parse_config(DeviceImpl* d, const char* cfg) {
+  if (!cfg) return;
+  std::string s(cfg);
+  size_t pos = 0;
+  while (pos < s.size()) {
+    size_t end = s.find_first_of(",; ", pos);
+    if (end == std::string::npos) end = s.size();
+    const std::string tok = s.substr(pos, end - pos);
+    const size_t eq = tok.find('=');
+    if (eq != std::string::npos) {
+      const std::string k = tok.substr(0, eq), v = tok.substr(eq + 1);
+      if (k == "verbose") d->verbose = atoi(v.c_str());
+      else if (k == "gpu") d->gpu = atoi(v.c_str());
+    }
+    pos = end + 1;
+  }
+}
+
+// ---- commit: upload the enabled meshes and build on the device (scene.cpp:828-887) --------------------------
+void commit_scene(SceneImpl* s) {
+  std::lock_guard<std::mutex> lk(s->commitMutex);
+  std::vector<GeometryImpl*> geoms;
+  {
+    std::lock_guard<std::mutex> lg(s->geomMutex);
+    if (!s->isModified()) return;
+    geoms = s->geoms;
+  }
+  for (GeometryImpl* g : geoms)
+    if (g && g->enabled && g->state == GeomState::MODIFIED) fail(RTC_ERROR_INVALID_OPERATION, "geometry not committed");
+  if (s->progFn && !s->progFn(s->progPtr, 0.0)) fail(RTC_ERROR_CANCELLED, "progress monitor forced termination");
+  s->dev->use();
+  for (void* p : s->deviceBuffers) cudaFree(p);
+  s->deviceBuffers.clear();
+  std::vector<rtk::GeomDesc> descs;
+  for (size_t id = 0; id < geoms.size(); ++id) {
+    GeometryImpl* g = geoms[id];
+    if (!g || !g->enabled) continue;
+    const size_t ntris = g->indices.count, nverts = g->vertices.count;
+    if (ntris == 0 || !g->indices.buf) continue;
+    if (!g->vertices.buf) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer not set");
+    if (ntris > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "mesh too large");
+    const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 12 : 0;
+    const size_t ibytes = (ntris - 1) * g->indices.stride + 12;
+    void *dv = nullptr, *di = nullptr;
+    cuda_check(cudaMalloc(&dv, vbytes ? vbytes : 16), "cudaMalloc(vertices)");
+    s->deviceBuffers.push_back(dv);
+    cuda_check(cudaMalloc(&di, ibytes), "cudaMalloc(indices)");
+    s->deviceBuffers.push_back(di);
+    if (vbytes) cuda_check(cudaMemcpy(dv, g->vertices.data(), vbytes, cudaMemcpyHostToDevice), "upload vertices");
+    cuda_check(cudaMemcpy(di, g->indices.data(), ibytes, cudaMemcpyHostToDevice), "upload indices");
+    rtk::GeomDesc d;
+    d.verts = static_cast<const uint8_t*>(dv); d.idx = static_cast<const uint8_t*>(di);
+    d.vstride = g->vertices.stride; d.istride = g->indices.stride;
+    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)ntris;
+    d.geomID = (uint32_t)id; d.mask = g->mask;
+    descs.push_back(d);
+  }
+  // quality -> builder (scene.cpp:163-206: LOW = Morton two-level builder, MEDIUM/HIGH = SAH).  The env override
+  // exists for A/B measurements of the two device builders only.
+  rtk::BuilderKind kind = (s->quality == RTC_BUILD_QUALITY_LOW) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
+  if (const char* e = getenv("RTCB200_BUILDER")) kind = (strcmp(e, "lbvh") == 0) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
+  char errmsg[256];
+  const int r = rtk::build_scene(s->gpu, descs.data(), (int)descs.size(), kind, 0, errmsg);
+  // vertex/index copies are only needed during the build (triangles are baked into the leaf records)
+  for (void* p : s->deviceBuffers) cudaFree(p);
+  s->deviceBuffers.clear();
+  if (r != 0) {
+    rtk::free_scene(s->gpu);
+    fail(r == (int)cudaErrorMemoryAllocation ? RTC_ERROR_OUT_OF_MEMORY : RTC_ERROR_UNKNOWN, errmsg);
+  }
+  if (s->dev->verbose >= 2)
+    fprintf(stderr, "[b200] commit: %u tris, %u nodes (%.1f MB) + %.1f MB tris, builder=%s, %.3f ms (%.1f Mprim/s), SAH %.2f, depth %u\n",
+            s->gpu.num_tris, s->gpu.num_nodes, s->gpu.num_nodes * 80e-6, s->gpu.num_tris * 48e-6,
+            s->gpu.builder ? "sah" : "lbvh", s->gpu.build_ms, s->gpu.build_ms > 0 ? s->gpu.num_tris / s->gpu.build_ms * 1e-3 : 0.0,
+            s->gpu.sah_cost, s->gpu.max_depth);
+  {
+    std::lock_guard<std::mutex> lg(s->geomMutex);
+    s->committedCounter.assign(geoms.size(), 0u);
+    for (size_t i = 0; i < geoms.size(); ++i) s->committedCounter[i] = geoms[i] ? geoms[i]->modCounter : 0u;
+    // geometries attached while we were building keep the scene modified
+    s->flagsModified = false;
+    s->everCommitted = true;
+  }
+  if (s->progFn) s->progFn(s->progPtr, 1.0);
+}
+
+// ---- query plumbing ----------------------------------------------------------------------------------------------
+struct ThreadCtx {  // per calling thread: a stream and a mapped pinned staging record for the single-call path
+  int gpu = -1;
+  cudaStream_t stream = nullptr;
+  char* staging = nullptr;  // 1344 B packet + 64 B valid
+  ~ThreadCtx() {
+    if (staging) cudaFreeHost(staging);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  void ensure(int g) {
+    if (gpu == g && stream) return;
+    if (staging) { cudaFreeHost(staging); staging = nullptr; }
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    cudaSetDevice(g);
+    cuda_check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    cuda_check(cudaHostAlloc(reinterpret_cast<void**>(&staging), 2048, cudaHostAllocMapped), "cudaHostAlloc");
+    gpu = g;
+  }
+};
+thread_local ThreadCtx t_ctx;
+
+template <typename Args>
+void check_args(SceneImpl* s, const Args* a, uint32_t& instID, uint32_t& instPrimID) {
+  instID = instPrimID = RTC_INVALID_GEOMETRY_ID;
+  if (!a) return;
+  if (a->filter) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the device");
+  if (a->context) { instID = a->context->instID[0]; instPrimID = a->context->instPrimID[0]; }
+  (void)s;
+}
+
+rtk::TraceParams make_params(SceneImpl* s, void* rays, const int* valid, unsigned long long n, uint32_t instID,
+                             uint32_t instPrimID) {
+  rtk::TraceParams p;
+  p.nodes = s->gpu.nodes; p.tris = s->gpu.tris; p.root_valid = s->gpu.root_valid;
+  p.rays = rays; p.valid = valid; p.n = n; p.instID = instID; p.instPrimID = instPrimID;
+  p.stat = s->statCounters ? s->gpu.d_stat : nullptr;
+  return p;
+}
+
+void require_committed(SceneImpl* s) {
+  if (!s->everCommitted) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed");  // scene.cpp:36,65
+}
+
+// one synchronous record (single ray or one packet): stage in mapped pinned memory, one launch, one sync
+void trace_one(SceneImpl* s, void* rec, size_t recBytes, const int* valid, int K, int occluded, uint32_t instID,
+               uint32_t instPrimID) {
+  require_committed(s);
+  if (!s->gpu.root_valid) return;
+  t_ctx.ensure(s->dev->gpu);
+  cudaSetDevice(s->dev->gpu);
+  memcpy(t_ctx.staging, rec, recBytes);
+  int* sv = reinterpret_cast<int*>(t_ctx.staging + 1408);
+  if (K > 1) memcpy(sv, valid, 4 * K);
+  rtk::TraceParams p = make_params(s, t_ctx.staging, K > 1 ? sv : nullptr, (unsigned long long)K, instID, instPrimID);
+  cuda_check((cudaError_t)rtk::launch_trace(p, occluded, K, t_ctx.stream), "trace launch");
+  cuda_check(cudaStreamSynchronize(t_ctx.stream), "trace");
+  memcpy(rec, t_ctx.staging, recBytes);
+}
+
+// batched, device pointers: enqueue only
+void trace_device(SceneImpl* s, void* d_rays, const int* d_valid, int K, size_t M, int occluded, uint32_t instID,
+                  uint32_t instPrimID, cudaStream_t st, bool timeit) {
+  require_committed(s);
+  if (!s->gpu.root_valid || M == 0) return;
+  cudaSetDevice(s->dev->gpu);
+  rtk::TraceParams p = make_params(s, d_rays, d_valid, (unsigned long long)M * K, instID, instPrimID);
+  if (timeit) {
+    if (!s->ev0) { cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); }
+    cudaEventRecord(s->ev0, st);
+  }
+  cuda_check((cudaError_t)rtk::launch_trace(p, occluded, K, st), "trace launch");
+  if (timeit) cudaEventRecord(s->ev1, st);
+}
+
+// batched, host pointers: chunked H2D -> trace -> D2H pipeline over three streams
+struct HostPipe {
+  int gpu = -1;
+  static constexpr int kStreams = 3;
+  cudaStream_t st[kStreams] = {};
+  char* buf[kStreams] = {};
+  int* vbuf[kStreams] = {};
+  size_t cap = 0, vcap = 0;
+  ~HostPipe() { reset(); }
+  void reset() {
+    for (int i = 0; i < kStreams; ++i) {
+      if (buf[i]) cudaFree(buf[i]);
+      if (vbuf[i]) cudaFree(vbuf[i]);
+      if (st[i]) cudaStreamDestroy(st[i]);
+      buf[i] = nullptr; vbuf[i] = nullptr; st[i] = nullptr;
+    }
+    cap = vcap = 0; gpu = -1;
+  }
+  void ensure(int g, size_t bytes, size_t vbytes) {
+    if (gpu != g) reset();
+    cudaSetDevice(g);
+    gpu = g;
+    for (int i = 0; i < kStreams; ++i)
+      if (!st[i]) cuda_check(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking), "cudaStreamCreate");
+    if (bytes > cap) {
+      for (int i = 0; i < kStreams; ++i) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; cuda_check(cudaMalloc(&buf[i], bytes), "cudaMalloc(ray chunk)"); }
+      cap = bytes;
+    }
+    if (vbytes > vcap) {
+      for (int i = 0; i < kStreams; ++i) { if (vbuf[i]) cudaFree(vbuf[i]); vbuf[i] = nullptr; cuda_check(cudaMalloc(&vbuf[i], vbytes), "cudaMalloc(valid chunk)"); }
+      vcap = vbytes;
+    }
+  }
+};
+thread_local HostPipe t_pipe;
+
+void trace_host(SceneImpl* s, void* rays, const int* valid, int K, size_t M, size_t recBytes, int occluded,
+                uint32_t instID, uint32_t instPrimID) {
+  require_committed(s);
+  if (!s->gpu.root_valid || M == 0) return;
+  const size_t chunkRecs = std::max<size_t>(1, (size_t(1) << 22) / K);  // 4 Mi rays per chunk
+  const size_t chunks = (M + chunkRecs - 1) / chunkRecs;
+  const size_t perChunk = std::min(M, chunkRecs);
+  t_pipe.ensure(s->dev->gpu, perChunk * recBytes, valid ? perChunk * K * 4 : 0);
+  for (size_t c = 0; c < chunks; ++c) {
+    const int b = (int)(c % HostPipe::kStreams);
+    cudaStream_t st = t_pipe.st[b];
+    const size_t first = c * chunkRecs, cnt = std::min(chunkRecs, M - first);
+    char* h = static_cast<char*>(rays) + first * recBytes;
+    // the stream order serialises reuse of buffer b: its previous D2H precedes this H2D
+    cuda_check(cudaMemcpyAsync(t_pipe.buf[b], h, cnt * recBytes, cudaMemcpyHostToDevice, st), "H2D rays");
+    const int* dvalid = nullptr;
+    if (valid) {
+      cuda_check(cudaMemcpyAsync(t_pipe.vbuf[b], valid + first * K, cnt * K * 4, cudaMemcpyHostToDevice, st), "H2D valid");
+      dvalid = t_pipe.vbuf[b];
+    }
+    rtk::TraceParams p = make_params(s, t_pipe.buf[b], dvalid, (unsigned long long)cnt * K, instID, instPrimID);
+    cuda_check((cudaError_t)rtk::launch_trace(p, occluded, K, st), "trace launch");
+    cuda_check(cudaMemcpyAsync(h, t_pipe.buf[b], cnt * recBytes, cudaMemcpyDeviceToHost, st), "D2H rays");
+  }
+  for (int i = 0; i < HostPipe::kStreams; ++i) cuda_check(cudaStreamSynchronize(t_pipe.st[i]), "trace");
+}
+
+size_t rec_bytes(int K, int occluded) { return (size_t)(occluded ? 12 : 21) * 4 * K + (K == 1 && !occluded ? 12 : 0); }
+
+}  // namespace
+
+// =====================================================================================================================
+// extern "C" entry points
+// =====================================================================================================================
+extern "C" {
+
+const char* rtcGetErrorString(enum RTCError e) {
+  switch (e) {
+    case RTC_ERROR_NONE: return "No error";
+    case RTC_ERROR_UNKNOWN: return "Unknown error";
+    case RTC_ERROR_INVALID_ARGUMENT: return "Invalid argument";
+    case RTC_ERROR_INVALID_OPERATION: return "Invalid operation";
+    case RTC_ERROR_OUT_OF_MEMORY: return "Out of memory";
+    case RTC_ERROR_UNSUPPORTED_CPU: return "Unsupported CPU";
+    case RTC_ERROR_CANCELLED: return "Cancelled";
+    case RTC_ERROR_LEVEL_ZERO_RAYTRACING_SUPPORT_MISSING: return "Level Zero raytracing support missing";
+  }
+  return "Invalid error code";
+}
+
+RTCDevice rtcNewDevice(const char* config) {
+  std::lock_guard<std::mutex> lk(g_deviceMutex);
+  DeviceImpl* d = nullptr;
+  API_BEGIN
+  d = new DeviceImpl();
+  int cur = 0;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e != cudaSuccess) { std::string m = std::string("no CUDA device: ") + cudaGetErrorString(e); delete d; d = nullptr; fail(RTC_ERROR_UNKNOWN, m.c_str()); }
+  d->gpu = cur;
+  parse_config(d, config);
+  int count = 0;
+  cudaGetDeviceCount(&count);
+  if (d->gpu < 0 || d->gpu >= count) { delete d; d = nullptr; fail(RTC_ERROR_INVALID_ARGUMENT, "gpu ordinal out of range"); }
+  cuda_check(cudaGetDeviceProperties(&d->prop, d->gpu), "cudaGetDeviceProperties");
+  if (d->prop.major < 10) {
+    std::string m = std::string("this library contains sm_100a code only; device is ") + d->prop.name;
+    delete d; d = nullptr;
+    fail(RTC_ERROR_UNKNOWN, m.c_str());
+  }
+  if (d->verbose >= 1)
+    fprintf(stderr, "Embree-API B200 kernels %s: GPU %d %s, %d SMs, %.0f GB\n", RTC_VERSION_STRING, d->gpu, d->prop.name,
+            d->prop.multiProcessorCount, d->prop.totalGlobalMem / 1e9);
+  return reinterpret_cast<RTCDevice>(d);
+  API_END(nullptr)
+  return nullptr;
+}
+void rtcRetainDevice(RTCDevice h) { API_BEGIN VERIFY_HANDLE(h); std::lock_guard<std::mutex> lk(g_deviceMutex); D(h)->retain(); API_END(D(h)) }
+void rtcReleaseDevice(RTCDevice h) { API_BEGIN VERIFY_HANDLE(h); std::lock_guard<std::mutex> lk(g_deviceMutex); t_err.erase(D(h)); D(h)->release(); API_END(nullptr) }
+
+ssize_t rtcGetDeviceProperty(RTCDevice h, enum RTCDeviceProperty prop) {
+  API_BEGIN
+  VERIFY_HANDLE(h);
+  switch (prop) {  // reference values: kernels/common/device.cpp:461-531
+    case RTC_DEVICE_PROPERTY_VERSION: return RTC_VERSION;
+    case RTC_DEVICE_PROPERTY_VERSION_MAJOR: return RTC_VERSION_MAJOR;
+    case RTC_DEVICE_PROPERTY_VERSION_MINOR: return RTC_VERSION_MINOR;
+    case RTC_DEVICE_PROPERTY_VERSION_PATCH: return RTC_VERSION_PATCH;
+    case RTC_DEVICE_PROPERTY_NATIVE_RAY4_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_NATIVE_RAY8_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_NATIVE_RAY16_SUPPORTED: return 1;
+    case RTC_DEVICE_PROPERTY_BACKFACE_CULLING_SPHERES_ENABLED:
+    case RTC_DEVICE_PROPERTY_BACKFACE_CULLING_CURVES_ENABLED: return 0;
+    case RTC_DEVICE_PROPERTY_RAY_MASK_SUPPORTED: return 1;
+    case RTC_DEVICE_PROPERTY_BACKFACE_CULLING_ENABLED: return 0;
+    case RTC_DEVICE_PROPERTY_FILTER_FUNCTION_SUPPORTED: return 0;  // host callbacks cannot run in a device traversal
+    case RTC_DEVICE_PROPERTY_IGNORE_INVALID_RAYS_ENABLED: return 0;
+    case RTC_DEVICE_PROPERTY_COMPACT_POLYS_ENABLED: return 0;
+    case RTC_DEVICE_PROPERTY_TRIANGLE_GEOMETRY_SUPPORTED: return 1;
+    case RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_USER_GEOMETRY_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_POINT_GEOMETRY_SUPPORTED: return 0;
+    case RTC_DEVICE_PROPERTY_TASKING_SYSTEM: return 0;
+    case RTC_DEVICE_PROPERTY_JOIN_COMMIT_SUPPORTED: return 1;
+    case RTC_DEVICE_PROPERTY_PARALLEL_COMMIT_SUPPORTED: return 0;
+    case RTC_DEVICE_PROPERTY_CPU_DEVICE: return 0;
+    case RTC_DEVICE_PROPERTY_SYCL_DEVICE: return 0;
+  }
+  fail(RTC_ERROR_INVALID_ARGUMENT, "unknown readable property");
+  API_END(D(h))
+  return 0;
+}
+void rtcSetDeviceProperty(RTCDevice h, enum RTCDeviceProperty, ssize_t) {
+  API_BEGIN VERIFY_HANDLE(h); fail(RTC_ERROR_INVALID_ARGUMENT, "unknown writable property"); API_END(D(h))
+}
+enum RTCError rtcGetDeviceError(RTCDevice h) {
+  ErrSlot& s = h ? t_err[D(h)] : t_noDeviceError;
+  const RTCError e = s.code;
+  s.code = RTC_ERROR_NONE;
+  return e;
+}
+const char* rtcGetDeviceLastErrorMessage(RTCDevice h) {
+  ErrSlot& s = h ? t_err[D(h)] : t_noDeviceError;
+  return s.msg.c_str();
+}
+void rtcSetDeviceErrorFunction(RTCDevice h, RTCErrorFunction fn, void* p) { API_BEGIN VERIFY_HANDLE(h); D(h)->errFn = fn; D(h)->errPtr = p; API_END(D(h)) }
+void rtcSetDeviceMemoryMonitorFunction(RTCDevice h, RTCMemoryMonitorFunction fn, void* p) { API_BEGIN VERIFY_HANDLE(h); D(h)->memFn = fn; D(h)->memPtr = p; API_END(D(h)) }
+
+// ---- buffers ------------------------------------------------------------------------------------------------------
+RTCBuffer rtcNewBuffer(RTCDevice h, size_t n) { API_BEGIN VERIFY_HANDLE(h); return reinterpret_cast<RTCBuffer>(new BufferImpl(D(h), n, nullptr)); API_END(D(h)) return nullptr; }
+RTCBuffer rtcNewSharedBuffer(RTCDevice h, void* ptr, size_t n) { API_BEGIN VERIFY_HANDLE(h); VERIFY_HANDLE(ptr); return reinterpret_cast<RTCBuffer>(new BufferImpl(D(h), n, ptr)); API_END(D(h)) return nullptr; }
+RTCBuffer rtcNewBufferHostDevice(RTCDevice h, size_t n) { return rtcNewBuffer(h, n); }
+RTCBuffer rtcNewSharedBufferHostDevice(RTCDevice h, void* p, size_t n) { return rtcNewSharedBuffer(h, p, n); }
+void* rtcGetBufferData(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; API_BEGIN VERIFY_HANDLE(b); return B(b)->ptr; API_END(d) return nullptr; }
+void* rtcGetBufferDataDevice(RTCBuffer b) { return rtcGetBufferData(b); }
+void rtcCommitBuffer(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; API_BEGIN VERIFY_HANDLE(b); API_END(d) }
+void rtcRetainBuffer(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; API_BEGIN VERIFY_HANDLE(b); B(b)->retain(); API_END(d) }
+void rtcReleaseBuffer(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; API_BEGIN VERIFY_HANDLE(b); B(b)->release(); API_END(d) }
+
+// ---- geometry -----------------------------------------------------------------------------------------------------
+RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
+  API_BEGIN
+  VERIFY_HANDLE(h);
+  if (type != RTC_GEOMETRY_TYPE_TRIANGLE) fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE is supported by the B200 back-end");
+  return reinterpret_cast<RTCGeometry>(new GeometryImpl(D(h)));
+  API_END(D(h))
+  return nullptr;
+}
+#define GEOM_BEGIN(g) DeviceImpl* dev_ = (g) ? G(g)->dev : nullptr; API_BEGIN VERIFY_HANDLE(g);
+#define GEOM_END API_END(dev_)
+void rtcRetainGeometry(RTCGeometry g) { GEOM_BEGIN(g) G(g)->retain(); GEOM_END }
+void rtcReleaseGeometry(RTCGeometry g) { GEOM_BEGIN(g) G(g)->release(); GEOM_END }
+void rtcCommitGeometry(RTCGeometry g) { GEOM_BEGIN(g) ++G(g)->modCounter; G(g)->state = GeomState::COMMITTED; GEOM_END }  // geometry.cpp:103-107
+void rtcEnableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (!G(g)->enabled) { G(g)->enabled = true; ++G(g)->modCounter; } GEOM_END }
+void rtcDisableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (G(g)->enabled) { G(g)->enabled = false; ++G(g)->modCounter; } GEOM_END }
+void rtcSetGeometryTimeStepCount(RTCGeometry g, unsigned int n) { GEOM_BEGIN(g) if (n != 1) fail(RTC_ERROR_INVALID_OPERATION, "motion blur is not supported by the B200 back-end"); GEOM_END }
+void rtcSetGeometryVertexAttributeCount(RTCGeometry g, unsigned int n) { GEOM_BEGIN(g) G(g)->attribs.resize(n); G(g)->update(); GEOM_END }
+void rtcSetGeometryMask(RTCGeometry g, unsigned int mask) { GEOM_BEGIN(g) G(g)->mask = mask; G(g)->update(); GEOM_END }
+void rtcSetGeometryBuildQuality(RTCGeometry g, enum RTCBuildQuality q) {
+  GEOM_BEGIN(g)
+  if (q != RTC_BUILD_QUALITY_LOW && q != RTC_BUILD_QUALITY_MEDIUM && q != RTC_BUILD_QUALITY_HIGH && q != RTC_BUILD_QUALITY_REFIT)
+    throw std::runtime_error("invalid build quality");
+  G(g)->quality = q; G(g)->update();
+  GEOM_END
+}
+
+static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFormat format, BufferImpl* buf, size_t off, size_t stride, size_t num) {
+  // scene_triangle_mesh.cpp:35-80
+  if (((size_t)(buf->ptr) + off) & 3 || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
+  if (num > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_ARGUMENT, "buffer too large");
+  if (type == RTC_BUFFER_TYPE_VERTEX) {
+    if (format != RTC_FORMAT_FLOAT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex buffer format");
+    if (stride * num > 16ull * 1024 * 1024 * 1024) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer can be at most 16GB large");
+    if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid vertex buffer slot");
+    g->vertices.set(buf, off, stride, num, format);
+  } else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) {
+    if (format < RTC_FORMAT_FLOAT || format > RTC_FORMAT_FLOAT4 + 12) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex attribute buffer format");
+    if (slot >= g->attribs.size()) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex attribute buffer slot");
+    g->attribs[slot].set(buf, off, stride, num, format);
+  } else if (type == RTC_BUFFER_TYPE_INDEX) {
+    if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot");
+    if (format != RTC_FORMAT_UINT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid index buffer format");
+    g->indices.set(buf, off, stride, num, format);
+  } else
+    fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
+  g->update();
+}
+static size_t format_bytes(RTCFormat f) {
+  if (f >= RTC_FORMAT_UINT && f <= RTC_FORMAT_UINT4) return 4 * (size_t)(f - RTC_FORMAT_UINT + 1);
+  if (f >= RTC_FORMAT_FLOAT && f <= RTC_FORMAT_FLOAT4 + 12) return 4 * (size_t)(f - RTC_FORMAT_FLOAT + 1);
+  fail(RTC_ERROR_INVALID_ARGUMENT, "invalid format");
+}
+void rtcSetGeometryBuffer(RTCGeometry g, enum RTCBufferType type, unsigned int slot, enum RTCFormat format, RTCBuffer buffer, size_t off, size_t stride, size_t num) {
+  GEOM_BEGIN(g)
+  VERIFY_HANDLE(buffer);
+  if (G(g)->dev != B(buffer)->dev) fail(RTC_ERROR_INVALID_ARGUMENT, "inputs are from different devices");
+  if (num > 0 && off + (num - 1) * stride + format_bytes(format) > B(buffer)->bytes) fail(RTC_ERROR_INVALID_ARGUMENT, "buffer range out of bounds");  // rtcore.cpp rtcSetGeometryBuffer
+  set_buffer(G(g), type, slot, format, B(buffer), off, stride, num);
+  GEOM_END
+}
+void rtcSetSharedGeometryBuffer(RTCGeometry g, enum RTCBufferType type, unsigned int slot, enum RTCFormat format, const void* ptr, size_t off, size_t stride, size_t num) {
+  GEOM_BEGIN(g)
+  if (num > 0) VERIFY_HANDLE(ptr);
+  BufferImpl* b = new BufferImpl(G(g)->dev, off + (num ? (num - 1) * stride + format_bytes(format) : 0), const_cast<void*>(ptr ? ptr : (const void*)g));
+  try { set_buffer(G(g), type, slot, format, b, off, stride, num); } catch (...) { b->release(); throw; }
+  b->release();
+  GEOM_END
+}
+void* rtcSetNewGeometryBuffer(RTCGeometry g, enum RTCBufferType type, unsigned int slot, enum RTCFormat format, size_t stride, size_t num) {
+  GEOM_BEGIN(g)
+  size_t bytes = num * stride;
+  if (type == RTC_BUFFER_TYPE_VERTEX || type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) bytes += (16 - (stride % 16)) % 16;  // rtcore.cpp: vertex buffers get padding
+  BufferImpl* b = new BufferImpl(G(g)->dev, bytes, nullptr);
+  try { set_buffer(G(g), type, slot, format, b, 0, stride, num); } catch (...) { b->release(); throw; }
+  void* p = b->ptr;
+  b->release();
+  return p;
+  GEOM_END
+  return nullptr;
+}
+void* rtcGetGeometryBufferData(RTCGeometry g, enum RTCBufferType type, unsigned int slot) {
+  GEOM_BEGIN(g)
+  const BufferView* v = nullptr;
+  if (type == RTC_BUFFER_TYPE_INDEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->indices; }
+  else if (type == RTC_BUFFER_TYPE_VERTEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->vertices; }
+  else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) { if (slot >= G(g)->attribs.size()) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->attribs[slot]; }
+  else fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
+  return const_cast<char*>(v->data());
+  GEOM_END
+  return nullptr;
+}
+void rtcUpdateGeometryBuffer(RTCGeometry g, enum RTCBufferType type, unsigned int slot) {
+  GEOM_BEGIN(g)
+  if (type == RTC_BUFFER_TYPE_INDEX || type == RTC_BUFFER_TYPE_VERTEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); }
+  else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) { if (slot >= G(g)->attribs.size()) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); }
+  else fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
+  G(g)->update();
+  GEOM_END
+}
+void rtcSetGeometryUserData(RTCGeometry g, void* p) { GEOM_BEGIN(g) G(g)->userPtr = p; GEOM_END }
+void* rtcGetGeometryUserData(RTCGeometry g) { GEOM_BEGIN(g) return G(g)->userPtr; GEOM_END return nullptr; }
+void rtcSetGeometryEnableFilterFunctionFromArguments(RTCGeometry g, bool) { GEOM_BEGIN(g) G(g)->update(); GEOM_END }
+void rtcSetGeometryIntersectFilterFunction(RTCGeometry g, RTCFilterFunctionN f) { GEOM_BEGIN(g) if (f) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the device"); GEOM_END }
+void rtcSetGeometryOccludedFilterFunction(RTCGeometry g, RTCFilterFunctionN f) { GEOM_BEGIN(g) if (f) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the device"); GEOM_END }
+
+// ---- scene --------------------------------------------------------------------------------------------------------
+#define SCENE_BEGIN(s) DeviceImpl* dev_ = (s) ? S(s)->dev : nullptr; API_BEGIN VERIFY_HANDLE(s);
+#define SCENE_END API_END(dev_)
+RTCScene rtcNewScene(RTCDevice h) { API_BEGIN VERIFY_HANDLE(h); return reinterpret_cast<RTCScene>(new SceneImpl(D(h))); API_END(D(h)) return nullptr; }
+RTCDevice rtcGetSceneDevice(RTCScene s) { SCENE_BEGIN(s) S(s)->dev->retain(); return reinterpret_cast<RTCDevice>(S(s)->dev); SCENE_END return nullptr; }
+void rtcRetainScene(RTCScene s) { SCENE_BEGIN(s) S(s)->retain(); SCENE_END }
+void rtcReleaseScene(RTCScene s) { SCENE_BEGIN(s) S(s)->release(); SCENE_END }
+RTCTraversable rtcGetSceneTraversable(RTCScene s) {
+  SCENE_BEGIN(s)
+  if (!S(s)->everCommitted) fail(RTC_ERROR_INVALID_OPERATION, "Traversable is NULL. The scene has to be committed first.");
+  return reinterpret_cast<RTCTraversable>(s);
+  SCENE_END
+  return nullptr;
+}
+static void attach_at(SceneImpl* s, GeometryImpl* g, unsigned id) {
+  if (s->dev != g->dev) fail(RTC_ERROR_INVALID_ARGUMENT, "inputs are from different devices");
+  if (id >= s->geoms.size()) s->geoms.resize((size_t)id + 1, nullptr);
+  if (s->geoms[id]) fail(RTC_ERROR_INVALID_ARGUMENT, "geometry ID already in use");  // scene.cpp bind()
+  g->retain();
+  s->geoms[id] = g;
+  s->flagsModified = true;
+}
+unsigned int rtcAttachGeometry(RTCScene s, RTCGeometry g) {
+  SCENE_BEGIN(s)
+  VERIFY_HANDLE(g);
+  std::lock_guard<std::mutex> lk(S(s)->geomMutex);
+  unsigned id = 0;
+  while (id < S(s)->geoms.size() && S(s)->geoms[id]) ++id;  // lowest free ID, as the reference's IDPool
+  attach_at(S(s), G(g), id);
+  return id;
+  SCENE_END
+  return RTC_INVALID_GEOMETRY_ID;
+}
+void rtcAttachGeometryByID(RTCScene s, RTCGeometry g, unsigned int id) {
+  SCENE_BEGIN(s)
+  VERIFY_HANDLE(g);
+  if (id == RTC_INVALID_GEOMETRY_ID) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid argument");
+  std::lock_guard<std::mutex> lk(S(s)->geomMutex);
+  attach_at(S(s), G(g), id);
+  SCENE_END
+}
+void rtcDetachGeometry(RTCScene s, unsigned int id) {
+  SCENE_BEGIN(s)
+  if (id == RTC_INVALID_GEOMETRY_ID) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid argument");
+  std::lock_guard<std::mutex> lk(S(s)->geomMutex);
+  if (id >= S(s)->geoms.size() || !S(s)->geoms[id]) fail(RTC_ERROR_INVALID_OPERATION, "invalid geometry");
+  S(s)->geoms[id]->release();
+  S(s)->geoms[id] = nullptr;
+  S(s)->flagsModified = true;
+  SCENE_END
+}
+RTCGeometry rtcGetGeometry(RTCScene s, unsigned int id) {
+  SCENE_BEGIN(s)
+  if (id >= S(s)->geoms.size() || !S(s)->geoms[id]) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid geometry ID");
+  return reinterpret_cast<RTCGeometry>(S(s)->geoms[id]);
+  SCENE_END
+  return nullptr;
+}
+RTCGeometry rtcGetGeometryThreadSafe(RTCScene s, unsigned int id) {
+  SCENE_BEGIN(s)
+  std::lock_guard<std::mutex> lk(S(s)->geomMutex);
+  if (id >= S(s)->geoms.size() || !S(s)->geoms[id]) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid geometry ID");
+  return reinterpret_cast<RTCGeometry>(S(s)->geoms[id]);
+  SCENE_END
+  return nullptr;
+}
+void* rtcGetGeometryUserDataFromScene(RTCScene s, unsigned int id) {
+  SCENE_BEGIN(s)
+  if (id >= S(s)->geoms.size() || !S(s)->geoms[id]) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid geometry ID");
+  return S(s)->geoms[id]->userPtr;
+  SCENE_END
+  return nullptr;
+}
+void rtcCommitScene(RTCScene s) { SCENE_BEGIN(s) commit_scene(S(s)); SCENE_END }
+void rtcJoinCommitScene(RTCScene s) { SCENE_BEGIN(s) commit_scene(S(s)); SCENE_END }
+void rtcSetSceneProgressMonitorFunction(RTCScene s, RTCProgressMonitorFunction fn, void* p) { SCENE_BEGIN(s) S(s)->progFn = fn; S(s)->progPtr = p; SCENE_END }
+void rtcSetSceneBuildQuality(RTCScene s, enum RTCBuildQuality q) {
+  SCENE_BEGIN(s)
+  if (q != RTC_BUILD_QUALITY_LOW && q != RTC_BUILD_QUALITY_MEDIUM && q != RTC_BUILD_QUALITY_HIGH) throw std::runtime_error("invalid build quality");
+  if (S(s)->quality != q) { S(s)->quality = q; S(s)->flagsModified = true; }
+  SCENE_END
+}
+void rtcSetSceneFlags(RTCScene s, enum RTCSceneFlags f) { SCENE_BEGIN(s) if (S(s)->flags != f) { S(s)->flags = f; S(s)->flagsModified = true; } SCENE_END }
+enum RTCSceneFlags rtcGetSceneFlags(RTCScene s) { SCENE_BEGIN(s) return S(s)->flags; SCENE_END return RTC_SCENE_FLAG_NONE; }
+void rtcGetSceneBounds(RTCScene s, struct RTCBounds* b) {
+  SCENE_BEGIN(s)
+  VERIFY_HANDLE(b);
+  { std::lock_guard<std::mutex> lk(S(s)->geomMutex); if (S(s)->isModified()) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed"); }
+  const float* g = S(s)->gpu.bounds;
+  b->lower_x = g[0]; b->lower_y = g[1]; b->lower_z = g[2]; b->align0 = 0;
+  b->upper_x = g[3]; b->upper_y = g[4]; b->upper_z = g[5]; b->align1 = 0;
+  SCENE_END
+}
+void rtcGetSceneLinearBounds(RTCScene s, struct RTCLinearBounds* b) {
+  SCENE_BEGIN(s)
+  VERIFY_HANDLE(b);
+  rtcGetSceneBounds(s, &b->bounds0);
+  b->bounds1 = b->bounds0;
+  SCENE_END
+}
+
+// ---- queries.  No argument checks, like the reference's release build (rtcore.cpp:604-608); failures inside
+// (uncommitted scene, CUDA errors) are reported through the device error slot. -----------------------------------
+#define QUERY(scene, body) \
+  SceneImpl* s_ = S(scene); \
+  DeviceImpl* dev_ = s_ ? s_->dev : nullptr; \
+  API_BEGIN uint32_t iid, ipid; body API_END(dev_)
+
+void rtcIntersect1(RTCScene sc, struct RTCRayHit* rh, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, rh, 96, nullptr, 1, 0, iid, ipid);) }
+void rtcIntersect4(const int* v, RTCScene sc, struct RTCRayHit4* rh, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, rh, sizeof(RTCRayHit4), v, 4, 0, iid, ipid);) }
+void rtcIntersect8(const int* v, RTCScene sc, struct RTCRayHit8* rh, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, rh, sizeof(RTCRayHit8), v, 8, 0, iid, ipid);) }
+void rtcIntersect16(const int* v, RTCScene sc, struct RTCRayHit16* rh, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, rh, sizeof(RTCRayHit16), v, 16, 0, iid, ipid);) }
+void rtcOccluded1(RTCScene sc, struct RTCRay* r, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, r, 48, nullptr, 1, 1, iid, ipid);) }
+void rtcOccluded4(const int* v, RTCScene sc, struct RTCRay4* r, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, r, sizeof(RTCRay4), v, 4, 1, iid, ipid);) }
+void rtcOccluded8(const int* v, RTCScene sc, struct RTCRay8* r, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, r, sizeof(RTCRay8), v, 8, 1, iid, ipid);) }
+void rtcOccluded16(const int* v, RTCScene sc, struct RTCRay16* r, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, r, sizeof(RTCRay16), v, 16, 1, iid, ipid);) }
+
+void rtcTraversableIntersect1(RTCTraversable t, struct RTCRayHit* rh, struct RTCIntersectArguments* a) { rtcIntersect1(reinterpret_cast<RTCScene>(t), rh, a); }
+void rtcTraversableIntersect4(const int* v, RTCTraversable t, struct RTCRayHit4* rh, struct RTCIntersectArguments* a) { rtcIntersect4(v, reinterpret_cast<RTCScene>(t), rh, a); }
+void rtcTraversableIntersect8(const int* v, RTCTraversable t, struct RTCRayHit8* rh, struct RTCIntersectArguments* a) { rtcIntersect8(v, reinterpret_cast<RTCScene>(t), rh, a); }
+void rtcTraversableIntersect16(const int* v, RTCTraversable t, struct RTCRayHit16* rh, struct RTCIntersectArguments* a) { rtcIntersect16(v, reinterpret_cast<RTCScene>(t), rh, a); }
+void rtcTraversableOccluded1(RTCTraversable t, struct RTCRay* r, struct RTCOccludedArguments* a) { rtcOccluded1(reinterpret_cast<RTCScene>(t), r, a); }
+void rtcTraversableOccluded4(const int* v, RTCTraversable t, struct RTCRay4* r, struct RTCOccludedArguments* a) { rtcOccluded4(v, reinterpret_cast<RTCScene>(t), r, a); }
+void rtcTraversableOccluded8(const int* v, RTCTraversable t, struct RTCRay8* r, struct RTCOccludedArguments* a) { rtcOccluded8(v, reinterpret_cast<RTCScene>(t), r, a); }
+void rtcTraversableOccluded16(const int* v, RTCTraversable t, struct RTCRay16* r, struct RTCOccludedArguments* a) { rtcOccluded16(v, reinterpret_cast<RTCScene>(t), r, a); }
+
+// ---- batched extension ---------------------------------------------------------------------------------------------
+static void check_K(unsigned K) { if (K != 4 && K != 8 && K != 16) fail(RTC_ERROR_INVALID_ARGUMENT, "packet width must be 4, 8 or 16"); }
+void rtcb200Intersect1M(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_host(s_, rh, nullptr, 1, M, 96, 0, iid, ipid);) }
+void rtcb200Occluded1M(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_host(s_, r, nullptr, 1, M, 48, 1, iid, ipid);) }
+void rtcb200IntersectNM(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_host(s_, rh, v, (int)K, M, (size_t)84 * K, 0, iid, ipid);) }
+void rtcb200OccludedNM(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_host(s_, r, v, (int)K, M, (size_t)48 * K, 1, iid, ipid);) }
+void rtcb200Intersect1MDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, rh, nullptr, 1, M, 0, iid, ipid, (cudaStream_t)st, true);) }
+void rtcb200Occluded1MDevice(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, r, nullptr, 1, M, 1, iid, ipid, (cudaStream_t)st, true);) }
+void rtcb200IntersectNMDevice(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_device(s_, rh, v, (int)K, M, 0, iid, ipid, (cudaStream_t)st, true);) }
+void rtcb200OccludedNMDevice(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_device(s_, r, v, (int)K, M, 1, iid, ipid, (cudaStream_t)st, true);) }
+
+void rtcb200GetSceneStats(RTCScene sc, struct RTCB200SceneStats* o) {
+  SCENE_BEGIN(sc)
+  VERIFY_HANDLE(o);
+  SceneImpl* s = S(sc);
+  memset(o, 0, sizeof *o);
+  o->num_triangles = s->gpu.num_tris; o->num_nodes = s->gpu.num_nodes;
+  o->node_bytes = (unsigned long long)s->gpu.num_nodes * sizeof(rtk::Node8);
+  o->tri_bytes = (unsigned long long)s->gpu.num_tris * sizeof(rtk::TriRec);
+  o->build_ms = s->gpu.build_ms; o->sah_cost = s->gpu.sah_cost; o->builder = s->gpu.builder; o->max_depth = s->gpu.max_depth;
+  if (s->gpu.d_stat) {
+    s->dev->use();
+    unsigned long long c[3];
+    cuda_check(cudaMemcpy(c, s->gpu.d_stat, sizeof c, cudaMemcpyDeviceToHost), "read stat counters");
+    o->trav_rays = c[0]; o->trav_nodes = c[1]; o->trav_tris = c[2];
+  }
+  SCENE_END
+}
+void rtcb200SetSceneStatCounters(RTCScene sc, int enable) { SCENE_BEGIN(sc) S(sc)->statCounters = enable != 0; SCENE_END }
+void rtcb200ResetSceneStatCounters(RTCScene sc) { SCENE_BEGIN(sc) if (S(sc)->gpu.d_stat) { S(sc)->dev->use(); cuda_check(cudaMemset(S(sc)->gpu.d_stat, 0, 24), "reset stat counters"); } SCENE_END }
+unsigned long long rtcb200GetLaunchCount(void) { return rtk::launch_count(); }
+double rtcb200GetLastTraceMs(RTCScene sc) {
+  SCENE_BEGIN(sc)
+  SceneImpl* s = S(sc);
+  if (!s->ev0) return -1.0;
+  s->dev->use();
+  cuda_check(cudaEventSynchronize(s->ev1), "event sync");
+  float ms = 0;
+  cuda_check(cudaEventElapsedTime(&ms, s->ev0, s->ev1), "event elapsed");
+  return ms;
+  SCENE_END
+  return -1.0;
+}
+
+}  // extern "C"

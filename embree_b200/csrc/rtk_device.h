@@ -1,0 +1,57 @@
+// rtk_device.h -- internal interface between the host shim (rtcore_shim.cpp) and the CUDA code
+// (build.cu, trace.cu).  Plain structs and status codes only; no exceptions cross this boundary.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "rt_core.cuh"
+
+namespace rtk {
+
+// one enabled triangle mesh, buffers already resident on the device (raw bytes, caller's stride honoured:
+// kernels/common/buffer.h BufferView semantics)
+struct GeomDesc {
+  const uint8_t* verts;  // first vertex (byteOffset applied)
+  const uint8_t* idx;    // first index triple
+  uint64_t vstride, istride;
+  uint32_t nverts, ntris;
+  uint32_t geomID, mask;
+};
+
+enum BuilderKind : uint32_t { BUILDER_LBVH = 0, BUILDER_SAH = 1 };
+
+struct SceneGPU {
+  int device = 0;
+  Node8* nodes = nullptr;
+  TriRec* tris = nullptr;
+  uint32_t num_nodes = 0, num_tris = 0;
+  uint32_t root_valid = 0;              // 0: empty scene -> queries return immediately
+  float bounds[6] = {0, 0, 0, 0, 0, 0};  // lower xyz, upper xyz of all valid triangles
+  double build_ms = 0, sah_cost = 0;
+  uint32_t builder = 0, max_depth = 0;
+  unsigned long long* d_stat = nullptr;  // [3] rays, nodes, tris (device)
+  size_t node_capacity = 0, tri_capacity = 0;
+};
+
+// Build the BVH8 over `ngeoms` meshes.  Returns cudaSuccess (0) or a CUDA error code; `errmsg` (>=256 B) gets text.
+int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind, cudaStream_t stream, char* errmsg);
+void free_scene(SceneGPU& s);
+
+struct TraceParams {
+  const Node8* nodes;
+  const TriRec* tris;
+  uint32_t root_valid;
+  void* rays;            // RTCRayHit[] / RTCRay[] / RTCRayHitK[] / RTCRayK[]  (device-accessible)
+  const int* valid;      // per lane, -1 active; NULL = all active (always NULL for K == 1)
+  unsigned long long n;  // number of rays = records * K
+  uint32_t instID, instPrimID;
+  unsigned long long* stat;  // non-NULL -> counting kernel
+};
+// occluded: 0 = closest hit (rtcIntersect*), 1 = any hit (rtcOccluded*); K in {1,4,8,16}
+int launch_trace(const TraceParams& p, int occluded, int K, cudaStream_t stream);
+
+unsigned long long launch_count();
+void count_launch(unsigned n = 1);
+
+}  // namespace rtk

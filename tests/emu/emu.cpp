@@ -1,0 +1,193 @@
+// emu.cpp -- TEST TOOL ONLY: runs the host instantiation of embree_b200/csrc/rt_core.cuh serially on the CPU so the
+// shared core routines (LBVH node construction, BVH8 collapse + slot assignment + box quantisation, the traversal
+// loop and the triangle test) can be debugged in a container without a GPU.  It is compiled by tests/emu/build.sh
+// into tests/emu/_build/libemu.so, loaded only by tests/test_emu_*.py, never by the product and never by bench.py.
+// The GPU-only parts (radix sort, atomics-based refit, level scheduling) are replaced by trivial serial code here.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "../../embree_b200/csrc/rt_core.cuh"
+
+using namespace rtk;
+
+namespace {
+struct EmuScene {
+  std::vector<Node8> nodes;
+  std::vector<TriRec> tris;
+  uint32_t root_valid = 0;
+  uint32_t depth = 0;
+  double sah = 0;
+};
+
+struct HostAlloc {
+  uint32_t* node_tail;
+  uint32_t* tri_tail;
+  double* sah_acc;
+  uint32_t nodes(uint32_t k) const { uint32_t o = *node_tail; *node_tail += k; return o; }
+  uint32_t tris(uint32_t k) const { uint32_t o = *tri_tail; *tri_tail += k; return o; }
+  void sah(double x) const { *sah_acc += x; }
+};
+
+uint64_t expand21(uint32_t v) {
+  uint64_t x = v & 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+}  // namespace
+
+extern "C" {
+
+// vertices: float[nverts][3] (stride 12), indices: uint32[ntris][3]; mode 0 = LBVH order, 1 = median-split tree
+void* emu_build(const float* verts, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint32_t geomID, uint32_t mask, int mode) {
+  EmuScene* sc = new EmuScene();
+  std::vector<PrimRef> prims;
+  float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  float glo[3] = {INFINITY, INFINITY, INFINITY}, ghi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint32_t p = 0; p < ntris; ++p) {
+    const uint32_t i0 = idx[3 * p], i1 = idx[3 * p + 1], i2 = idx[3 * p + 2];
+    if (i0 >= nverts || i1 >= nverts || i2 >= nverts) continue;
+    bool ok = true;
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+      const float x = verts[3 * i0 + a], y = verts[3 * i1 + a], z = verts[3 * i2 + a];
+      ok &= (x > -kFltLarge) & (x < kFltLarge) & (y > -kFltLarge) & (y < kFltLarge) & (z > -kFltLarge) & (z < kFltLarge);
+      lo[a] = fminf(fminf(x, y), z); hi[a] = fmaxf(fmaxf(x, y), z);
+    }
+    if (!ok) continue;
+    PrimRef pr;
+    pr.lox = lo[0]; pr.loy = lo[1]; pr.loz = lo[2]; pr.prim = p;
+    pr.hix = hi[0]; pr.hiy = hi[1]; pr.hiz = hi[2]; pr.valid = 1;
+    prims.push_back(pr);
+    for (int a = 0; a < 3; ++a) {
+      clo[a] = fminf(clo[a], lo[a] + hi[a]); chi[a] = fmaxf(chi[a], lo[a] + hi[a]);
+      glo[a] = fminf(glo[a], lo[a]); ghi[a] = fmaxf(ghi[a], hi[a]);
+    }
+  }
+  const uint32_t n = (uint32_t)prims.size();
+  if (n == 0) return sc;
+  std::vector<uint64_t> keys(n);
+  for (uint32_t k = 0; k < n; ++k) {
+    uint32_t q[3];
+    const float c[3] = {prims[k].lox + prims[k].hix, prims[k].loy + prims[k].hiy, prims[k].loz + prims[k].hiz};
+    for (int a = 0; a < 3; ++a) {
+      const float ext = chi[a] - clo[a];
+      float f = ext > 0.0f ? (c[a] - clo[a]) / ext : 0.0f;
+      f = fminf(fmaxf(f * 2097152.0f, 0.0f), 2097151.0f);
+      q[a] = (uint32_t)f;
+    }
+    keys[k] = (expand21(q[2]) << 2) | (expand21(q[1]) << 1) | expand21(q[0]);
+  }
+  std::vector<uint32_t> order(n);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  std::vector<uint64_t> skeys(n);
+  std::vector<uint32_t> sorted(n);  // sorted[j] = index into prims
+  for (uint32_t j = 0; j < n; ++j) { skeys[j] = keys[order[j]]; sorted[j] = order[j]; }
+
+  std::vector<Node2> n2(2 * (size_t)n);
+  memset(n2.data(), 0, n2.size() * sizeof(Node2));
+  (void)mode;
+  for (int i = 0; i + 1 < (int)n; ++i) lbvh_node(skeys.data(), (int)n, i, n2.data());
+  for (uint32_t j = 0; j < n; ++j) {
+    Node2& lf = n2[n - 1 + j];
+    const PrimRef& pr = prims[sorted[j]];
+    lf.lox = pr.lox; lf.loy = pr.loy; lf.loz = pr.loz; lf.left = (int)j;
+    lf.hix = pr.hix; lf.hiy = pr.hiy; lf.hiz = pr.hiz; lf.right = -1;
+    lf.first = j; lf.count = 1;
+    if (n == 1) lf.parent = 0xFFFFFFFFu;
+  }
+  // serial refit: process internal nodes by decreasing range size is not needed -- recurse
+  if (n > 1) {
+    std::vector<int> stack{0};
+    std::vector<int> post;
+    while (!stack.empty()) {
+      int i = stack.back(); stack.pop_back();
+      post.push_back(i);
+      if (n2[i].left < (int)n - 1) stack.push_back(n2[i].left);
+      if (n2[i].right < (int)n - 1) stack.push_back(n2[i].right);
+    }
+    for (auto it = post.rbegin(); it != post.rend(); ++it) {
+      Node2& nd = n2[*it];
+      const Node2 &l = n2[nd.left], &r = n2[nd.right];
+      nd.lox = fminf(l.lox, r.lox); nd.loy = fminf(l.loy, r.loy); nd.loz = fminf(l.loz, r.loz);
+      nd.hix = fmaxf(l.hix, r.hix); nd.hiy = fmaxf(l.hiy, r.hiy); nd.hiz = fmaxf(l.hiz, r.hiz);
+    }
+  }
+  // collapse
+  std::vector<uint32_t> src(n + 1), tri_src(n);
+  sc->nodes.resize(n + 1);
+  uint32_t node_tail = 1, tri_tail = 0;
+  src[0] = 0;  // root: internal node 0, or leaf 0 when n == 1 (id n-1+0 == 0)
+  const float ex = ghi[0] - glo[0], ey = ghi[1] - glo[1], ez = ghi[2] - glo[2];
+  const float ra = ex * (ey + ez) + ey * ez;
+  const float inv_ra = ra > 0 ? 1.0f / ra : 0.0f;
+  HostAlloc alloc{&node_tail, &tri_tail, &sc->sah};
+  uint32_t begin = 0, end = 1, depth = 0;
+  std::vector<uint32_t> sorted_prim(n);
+  for (uint32_t j = 0; j < n; ++j) sorted_prim[j] = prims[sorted[j]].prim;
+  while (begin < end) {
+    for (uint32_t q = begin; q < end; ++q)
+      collapse_node(n2.data(), src.data(), q, sc->nodes.data(), tri_src.data(), sorted_prim.data(), inv_ra, alloc);
+    begin = end; end = node_tail; ++depth;
+  }
+  sc->nodes.resize(node_tail);
+  sc->depth = depth;
+  sc->tris.resize(n);
+  for (uint32_t t = 0; t < n; ++t) {
+    const uint32_t p = tri_src[t];
+    const float* a = verts + 3 * (size_t)idx[3 * p];
+    const float* b = verts + 3 * (size_t)idx[3 * p + 1];
+    const float* c = verts + 3 * (size_t)idx[3 * p + 2];
+    TriRec& r = sc->tris[t];
+    r.v0x = a[0]; r.v0y = a[1]; r.v0z = a[2]; r.primID = p;
+    r.e1x = sub_rn(a[0], b[0]); r.e1y = sub_rn(a[1], b[1]); r.e1z = sub_rn(a[2], b[2]); r.geomID = geomID;
+    r.e2x = sub_rn(c[0], a[0]); r.e2y = sub_rn(c[1], a[1]); r.e2z = sub_rn(c[2], a[2]); r.mask = mask;
+  }
+  sc->root_valid = (tri_tail == n) ? 1 : 0;
+  return sc;
+}
+
+void emu_free(void* h) { delete static_cast<EmuScene*>(h); }
+uint32_t emu_num_nodes(void* h) { return (uint32_t)static_cast<EmuScene*>(h)->nodes.size(); }
+uint32_t emu_depth(void* h) { return static_cast<EmuScene*>(h)->depth; }
+double emu_sah(void* h) { return static_cast<EmuScene*>(h)->sah; }
+
+// rayhits: RTCRayHit[n] (96 B) when occluded == 0, RTCRay[n] (48 B) when occluded == 1; stats: u64[2] nodes, tris (or NULL)
+void emu_trace(void* h, void* rays, uint64_t n, int occluded, uint64_t* stats) {
+  EmuScene* sc = static_cast<EmuScene*>(h);
+  const Node8* nodes = sc->nodes.data();
+  const TriRec* tris = sc->tris.data();
+  auto ldn = [nodes](uint32_t node, int k) { const uint32_t* w = nodes[node].w + 4 * k; return u32x4{w[0], w[1], w[2], w[3]}; };
+  auto ldt = [tris](uint32_t t, int k) { const uint32_t* w = reinterpret_cast<const uint32_t*>(&tris[t]) + 4 * k; return u32x4{w[0], w[1], w[2], w[3]}; };
+  const size_t stride = occluded ? 48 : 96;
+  for (uint64_t i = 0; i < n; ++i) {
+    char* rec = static_cast<char*>(rays) + i * stride;
+    Ray r;
+    memcpy(&r, rec, 48);
+    Hit hit;
+    TravStats st{0, 0};
+    bool found;
+    if (occluded) found = traverse<true, true>(r, hit, ldn, ldt, sc->root_valid, &st);
+    else found = traverse<false, true>(r, hit, ldn, ldt, sc->root_valid, &st);
+    if (stats) { stats[0] += st.nodes; stats[1] += st.tris; }
+    if (!found) continue;
+    if (occluded) { float ninf = -INFINITY; memcpy(rec + 32, &ninf, 4); continue; }
+    memcpy(rec + 32, &hit.t, 4);
+    float h4[5] = {hit.ngx, hit.ngy, hit.ngz, hit.u, hit.v};
+    memcpy(rec + 48, h4, 20);
+    uint32_t ids[4] = {hit.primID, hit.geomID, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    memcpy(rec + 68, ids, 16);
+  }
+}
+
+}  // extern "C"
