@@ -1,0 +1,138 @@
+"""Parity helpers shared by the tests, __graft_entry__.smoke() and bench.py's checker leg.
+
+`load_oracle()` returns the CPU restatement (oracle/liboracle.so); `load_reference()` the unmodified reference
+built by oracle/build_ref.py (oracle/_ref/libembree4.so.4) or None when it is not present.  Both are CHECKERS: the
+product library never sees them."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libembree4.so.4")
+
+
+class Oracle:
+    def __init__(self, path=ORACLE_SO):
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `make -C oracle`")
+        d = C.CDLL(path)
+        d.orc_new.restype = C.c_void_p
+        d.orc_free.argtypes = [C.c_void_p]
+        d.orc_add_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint]
+        d.orc_commit.argtypes = [C.c_void_p]
+        d.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        d.orc_get_bounds.argtypes = [C.c_void_p, C.c_void_p]
+        d.orc_get_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        d.orc_count_stats.argtypes = [C.c_void_p, C.c_int]
+        d.orc_api_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_uint, C.c_int]
+        self.d = d
+
+    def scene(self, meshes):
+        """meshes: list of (vertices[nv,3] f32, indices[nt,3] u32, geomID, mask).  Returns an OracleScene."""
+        return OracleScene(self, meshes)
+
+    def trace(self, v, t, rayhits, occluded=False, mask=0xFFFFFFFF, nthreads=1):
+        sc = self.scene([(v, t, 0, mask)])
+        out = sc.trace(rayhits, occluded, nthreads)
+        sc.free()
+        return out
+
+
+class OracleScene:
+    def __init__(self, o, meshes):
+        self.o = o
+        self.h = o.d.orc_new()
+        self.keep = []
+        for (v, t, gid, mask) in meshes:
+            v = np.ascontiguousarray(v, np.float32).reshape(-1, 3)
+            t = np.ascontiguousarray(t, np.uint32).reshape(-1, 3)
+            self.keep += [v, t]
+            o.d.orc_add_mesh(self.h, v.ctypes.data, 12, v.shape[0], t.ctypes.data, 12, t.shape[0], gid, mask)
+        o.d.orc_commit(self.h)
+
+    def trace(self, rays, occluded=False, nthreads=1):
+        self.o.d.orc_trace(self.h, rays.ctypes.data, len(rays), 1 if occluded else 0, nthreads)
+        return rays
+
+    def bounds(self):
+        b = np.zeros(6, np.float32)
+        self.o.d.orc_get_bounds(self.h, b.ctypes.data)
+        return b
+
+    def stats(self):
+        s = np.zeros(6, np.uint64)
+        sah = C.c_double()
+        self.o.d.orc_get_stats(self.h, s.ctypes.data, C.byref(sah))
+        return dict(prims=int(s[0]), nodes=int(s[1]), blocks=int(s[2]), trav_nodes=int(s[3]), trav_leaves=int(s[4]),
+                    trav_blocks=int(s[5]), sah=sah.value)
+
+    def count_stats(self, on=True):
+        self.o.d.orc_count_stats(self.h, 1 if on else 0)
+
+    def free(self):
+        if self.h:
+            self.o.d.orc_free(self.h)
+            self.h = None
+
+
+_oracle = None
+
+
+def load_oracle():
+    global _oracle
+    if _oracle is None:
+        _oracle = Oracle()
+    return _oracle
+
+
+_ref = None
+
+
+def load_reference():
+    """The unmodified reference library through the same ctypes binding, or None if oracle/_ref was not built."""
+    global _ref
+    if _ref is None and os.path.exists(REF_SO):
+        from embree_b200.rtc import RTCLib
+        _ref = RTCLib(REF_SO)
+    return _ref
+
+
+def api_trace_mt(lib, scene, recs, nthreads, K=1, occluded=False, coherent=False, valid=None):
+    """Loop lib's rtcIntersect1 / rtcOccluded1 / rtcIntersect{K} over `recs` on `nthreads` host threads (FTZ|DAZ set),
+    i.e. how a host application drives the reference."""
+    name = ("rtcOccluded" if occluded else "rtcIntersect") + str(K)
+    fn = C.cast(getattr(lib.dll, name), C.c_void_p)
+    o = load_oracle()
+    o.d.orc_api_loop(fn, C.c_void_p(scene), recs.ctypes.data, len(recs), recs.dtype.itemsize, K,
+                     valid.ctypes.data if valid is not None else None, (1 << 16) if coherent else 0, nthreads)
+    return recs
+
+
+def compare_hits(want, got, tol=1e-4):
+    """Hit-record parity as BASELINE.json states it: primID/geomID/instID exact, tfar/u/v within `tol` relative
+    (u, v relative to 1 since they live in [0,1]).  Returns counts; `tie` = id mismatches where both libraries
+    report the same distance (|dt| <= tol*t): equal-distance hits on a shared edge/vertex, whose winner depends on
+    traversal order in the reference itself (SURVEY 7 hard part 2)."""
+    n = len(want)
+    wh = want["geomID"] != 0xFFFFFFFF
+    gh = got["geomID"] != 0xFFFFFFFF
+    both = wh & gh
+    id_mis = (want["primID"] != got["primID"]) | (want["geomID"] != got["geomID"]) | (want["instID"] != got["instID"])
+    wt, gt = want["tfar"].astype(np.float64), got["tfar"].astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel_t = np.where(both, np.abs(wt - gt) / np.maximum(np.abs(wt), 1e-30), 0.0)
+    same_t = both & (rel_t <= tol)
+    tie = id_mis & same_t
+    hard = id_mis & ~same_t
+    ok = both & ~id_mis
+    du = np.abs(want["u"].astype(np.float64) - got["u"])[ok]
+    dv = np.abs(want["v"].astype(np.float64) - got["v"])[ok]
+    ng_exact = all(((want[f].view(np.uint32) == got[f].view(np.uint32)) | ~ok).all() for f in ("Ng_x", "Ng_y", "Ng_z"))
+    miss_tfar_same = ((want["tfar"].view(np.uint32) == got["tfar"].view(np.uint32)) | wh | gh).all()
+    return dict(n=int(n), hits=int(wh.sum()), id_mismatch=int(hard.sum()), tie=int(tie.sum()),
+                hit_miss_disagree=int((wh != gh).sum()),
+                max_rel_t=float(rel_t[ok].max()) if ok.any() else 0.0,
+                max_abs_uv=float(max(du.max() if du.size else 0.0, dv.max() if dv.size else 0.0)),
+                ng_bit_exact=bool(ng_exact), miss_untouched=bool(miss_tfar_same))
