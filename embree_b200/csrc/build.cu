@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) lbvh_leaves_refit(const PrimRef* __restri
   Node2& lf = nodes[n - 1 + j];
   lf.lox = pr.lox; lf.loy = pr.loy; lf.loz = pr.loz; lf.left = j;
   lf.hix = pr.hix; lf.hiy = pr.hiy; lf.hiz = pr.hiz; lf.right = -1;
-  lf.first = (uint32_t)j; lf.count = 1;
+  lf.first = (uint32_t)j; lf.count = 1; lf.pad = 0;
   if (n == 1) { lf.parent = 0xFFFFFFFFu; return; }
   uint32_t cur = lf.parent;
   __threadfence();
@@ -337,11 +337,11 @@ struct DeviceAlloc {  // allocation callbacks of collapse_node() on the device: 
 
 __global__ void __launch_bounds__(128) collapse_level(const Node2* __restrict__ n2, uint32_t* __restrict__ src,
                                                       uint32_t begin, uint32_t end, Node8* __restrict__ n8,
-                                                      uint32_t* __restrict__ tri_src, const uint32_t* __restrict__ sorted,
-                                                      BuildInfo* info, float inv_root_area) {
+                                                      uint32_t* __restrict__ tri_src, const uint32_t* __restrict__ sortedA,
+                                                      const uint32_t* __restrict__ sortedB, BuildInfo* info, float inv_root_area) {
   const uint32_t q = begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= end) return;
-  collapse_node(n2, src, q, n8, tri_src, sorted, inv_root_area, DeviceAlloc{info});
+  collapse_node(n2, src, q, n8, tri_src, sortedA, sortedB, inv_root_area, DeviceAlloc{info});
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -366,8 +366,8 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
 }
 
 // binned-SAH top-down build of the binary tree (build_sah.cu)
-int build_sah_tree(const PrimRef* prims, uint32_t* sorted, uint32_t n, Node2* nodes, const float* cent_bounds,
-                   cudaStream_t stream, char* errmsg);
+int build_sah_tree(const PrimRef* prims, uint32_t* idsA, uint32_t* idsB, uint32_t n, Node2* nodes, const float* scene_bounds,
+                   const float* cent_bounds, cudaStream_t stream, char* errmsg);
 
 // ---------------------------------------------------------------------------------------------------
 // host driver
@@ -447,7 +447,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   if (kind == BUILDER_SAH && n > 1) {
     float cb[6];
     for (int a = 0; a < 3; ++a) { cb[a] = ord2f_host(hinfo.cent_lo[a]); cb[3 + a] = ord2f_host(hinfo.cent_hi[a]); }
-    int r = build_sah_tree(d_prims.p, vin, n, d_n2.p, cb, st, errmsg);
+    int r = build_sah_tree(d_prims.p, vin, vout, n, d_n2.p, s.bounds, cb, st, errmsg);
     if (r) return r;
     root2 = 0;
   } else {
@@ -471,7 +471,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   const float inv_ra = ra > 0.0f ? 1.0f / ra : 0.0f;
   uint32_t begin = 0, end = 1, depth = 0;
   while (begin < end) {
-    collapse_level<<<(end - begin + 127) / 128, 128, 0, st>>>(d_n2.p, d_src.p, begin, end, n8, d_trisrc.p, vin, d_info.p, inv_ra);
+    collapse_level<<<(end - begin + 127) / 128, 128, 0, st>>>(d_n2.p, d_src.p, begin, end, n8, d_trisrc.p, vin, vout, d_info.p, inv_ra);
     count_launch();
     uint32_t tail;
     CK(cudaMemcpyAsync(&tail, &d_info.p->node_tail, 4, cudaMemcpyDeviceToHost, st));

@@ -277,7 +277,7 @@ RT_HD void lbvh_node(const uint64_t* keys, int n, int i, Node2* nodes) {
   const int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
   Node2& nd = nodes[i];
   nd.left = left; nd.right = right;
-  nd.first = (uint32_t)first; nd.count = (uint32_t)(last - first + 1);
+  nd.first = (uint32_t)first; nd.count = (uint32_t)(last - first + 1); nd.pad = 0;
   nodes[left].parent = (uint32_t)i;
   nodes[right].parent = (uint32_t)i;
   if (i == 0) nd.parent = 0xFFFFFFFFu;
@@ -348,20 +348,20 @@ RT_HD void assign_slots(const ChildBox* cb, int n, const float plo[3], const flo
 // their boxes, reserve the node ids of internal children / the triangle slots of leaf children through `alloc`
 // (atomic bump counters on the device), and queue the internal children (src[child id] = binary node).
 template <typename Alloc>
-RT_HD void collapse_node(const Node2* n2, uint32_t* src, uint32_t q, Node8* n8, uint32_t* tri_src, const uint32_t* sorted,
-                         float inv_root_area, const Alloc& alloc) {
+RT_HD void collapse_node(const Node2* n2, uint32_t* src, uint32_t q, Node8* n8, uint32_t* tri_src, const uint32_t* sortedA,
+                         const uint32_t* sortedB, float inv_root_area, const Alloc& alloc) {
   const uint32_t root = src[q];
   uint32_t cand[8];
   const int n = select_children(n2, root, cand);
   const Node2 self = n2[root];
   const float plo[3] = {self.lox, self.loy, self.loz}, phi[3] = {self.hix, self.hiy, self.hiz};
   ChildBox cb[8];
-  uint32_t cnt[8], first[8];
+  uint32_t cnt[8], first[8], half[8];  // half: which ping-pong half of the sorted ids holds the child's range
   for (int c = 0; c < n; ++c) {
     const Node2 ch = n2[cand[c]];
     cb[c].lo[0] = ch.lox; cb[c].lo[1] = ch.loy; cb[c].lo[2] = ch.loz;
     cb[c].hi[0] = ch.hix; cb[c].hi[1] = ch.hiy; cb[c].hi[2] = ch.hiz;
-    cnt[c] = ch.count; first[c] = ch.first;
+    cnt[c] = ch.count; first[c] = ch.first; half[c] = ch.pad;
   }
   uint8_t slot_of[8];
   assign_slots(cb, n, plo, phi, slot_of);
@@ -396,6 +396,7 @@ RT_HD void collapse_node(const Node2* n2, uint32_t* src, uint32_t q, Node8* n8, 
     } else {
       const uint32_t k = cnt[c];
       meta[s] = (((1u << k) - 1u) << 5) | toff;
+      const uint32_t* sorted = half[c] ? sortedB : sortedA;
       for (uint32_t t = 0; t < k; ++t) tri_src[tri_base + toff + t] = sorted[first[c] + t];
       toff += k;
       const float dx = cb[c].hi[0] - cb[c].lo[0], dy = cb[c].hi[1] - cb[c].lo[1], dz = cb[c].hi[2] - cb[c].lo[2];

@@ -1,0 +1,62 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def load_golden(name):
+    """tests/golden/<name>.npz -> (meshes, rays_in, intersect_out, occluded_out, bounds); records as structured arrays."""
+    from embree_b200.rtc import RAYHIT_DTYPE, RAY_DTYPE, aligned_empty
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    meshes = [(z[f"v{i}"], z[f"t{i}"], int(z[f"gid{i}"]), int(z[f"mask{i}"])) for i in range(int(z["n_meshes"]))]
+
+    def rec(a, dt):
+        out = aligned_empty(a.shape[0], dt)
+        out.view(np.uint8).reshape(a.shape)[:] = a
+        return out
+    return meshes, rec(z["rays_in"], RAYHIT_DTYPE), rec(z["intersect_out"], RAYHIT_DTYPE), rec(z["occluded_out"], RAY_DTYPE), z["bounds"]
+
+
+GOLDEN = ["cube_ground", "sphere21", "terrain_masks"]
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    from tests.parity import load_oracle
+    return load_oracle()
+
+
+@pytest.fixture(scope="session")
+def emu():
+    import ctypes as C
+    import subprocess
+    subprocess.check_call([os.path.join(ROOT, "tests", "emu", "build.sh")])
+    e = C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libemu.so"))
+    e.emu_build.restype = C.c_void_p
+    e.emu_build.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_int]
+    e.emu_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    e.emu_free.argtypes = [C.c_void_p]
+    e.emu_num_nodes.argtypes = [C.c_void_p]
+    e.emu_depth.argtypes = [C.c_void_p]
+    return e
+
+
+@pytest.fixture(scope="session")
+def b200():
+    """The product library + a device on cuda:0 (GPU tests only)."""
+    import embree_b200
+    lib = embree_b200.load()
+    dev = lib.new_device(None)
+    yield lib, dev
+    lib.rtcReleaseDevice(dev)

@@ -137,7 +137,7 @@ void* emu_build(const float* verts, uint32_t nverts, const uint32_t* idx, uint32
   for (uint32_t j = 0; j < n; ++j) sorted_prim[j] = prims[sorted[j]].prim;
   while (begin < end) {
     for (uint32_t q = begin; q < end; ++q)
-      collapse_node(n2.data(), src.data(), q, sc->nodes.data(), tri_src.data(), sorted_prim.data(), inv_ra, alloc);
+      collapse_node(n2.data(), src.data(), q, sc->nodes.data(), tri_src.data(), sorted_prim.data(), sorted_prim.data(), inv_ra, alloc);
     begin = end; end = node_tail; ++depth;
   }
   sc->nodes.resize(node_tail);

@@ -1,0 +1,100 @@
+"""Generate golden input/output vectors by running the UNMODIFIED reference (oracle/_ref/libembree4.so.4, built
+from /root/reference by oracle/build_ref.py) in this container.  Committed outputs: tests/golden/*.npz.
+
+    python tests/golden/make_golden.py
+
+Each fixture holds the scene (vertices/indices per geometry, masks), the RTCRayHit inputs and the reference's
+outputs for rtcIntersect1 and rtcOccluded1, plus rtcGetSceneBounds.  Scenes/rays are seeded and small so the
+fixtures stay a few hundred KB.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from embree_b200 import scenes  # noqa: E402
+from embree_b200.rtc import RTCBounds, make_rayhits, rays_of  # noqa: E402
+from tests.parity import load_reference  # noqa: E402
+import ctypes as C  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def random_rays_box(n, lo, hi, seed):
+    rng = np.random.RandomState(seed)
+    org = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    return org, d
+
+
+def run(name, meshes, rayhits):
+    R = load_reference()
+    dev = R.new_device(None)
+    sc = R.rtcNewScene(dev)
+    keep = []
+    for (v, t, gid, mask) in meshes:
+        _, k = R.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)
+        keep.append(k)
+    R.rtcCommitScene(sc)
+    R.check(dev)
+    b = RTCBounds()
+    R.rtcGetSceneBounds(sc, C.byref(b))
+    out_i = R.intersect(sc, rayhits.copy(), "1")
+    occ = rays_of(rayhits)
+    out_o = R.occluded(sc, occ, "1")
+    out_16 = R.intersect(sc, rayhits.copy(), "16")
+    assert (out_16["primID"] == out_i["primID"]).all(), "reference packet path disagrees with its single-ray path"
+    R.check(dev)
+    d = dict(rays_in=rayhits.view(np.uint8).reshape(-1, 96), intersect_out=out_i.view(np.uint8).reshape(-1, 96),
+             occluded_out=out_o.view(np.uint8).reshape(-1, 48),
+             bounds=np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32),
+             n_meshes=np.array(len(meshes)))
+    for i, (v, t, gid, mask) in enumerate(meshes):
+        d[f"v{i}"], d[f"t{i}"], d[f"gid{i}"], d[f"mask{i}"] = v, t, np.array(gid, np.uint32), np.array(mask, np.uint32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    hits = (out_i["geomID"] != 0xFFFFFFFF).mean()
+    print(f"{name}: {len(rayhits)} rays, hit rate {hits:.3f}, occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
+    R.rtcReleaseScene(sc)
+    R.rtcReleaseDevice(dev)
+
+
+def main():
+    # 1. the triangle_geometry tutorial scene: cube (geomID 0) + ground plane (geomID 1), camera-like + random rays
+    (cv, ct), (gv, gt) = scenes.cube_and_ground()
+    prim = scenes.as_numpy_rayhits(scenes.primary_rays(48, 32, eye=(1.5, 1.5, -1.5), look=(-1.5, -1.5, 1.5), fov=90.0))
+    org, d = random_rays_box(1024, -3, 3, 1)
+    rnd = make_rayhits(org, d)
+    both = np.concatenate([prim, rnd]).view(prim.dtype)
+    both["id"] = np.arange(len(both))
+    run("cube_ground", [(cv, ct, 0, 0xFFFFFFFF), (gv, gt, 1, 0xFFFFFFFF)], both)
+    # 2. small sphere seen from inside (reference "incoherent" definition) and from outside, with tnear/tfar windows
+    v, t = scenes.triangle_sphere(21)
+    a = scenes.as_numpy_rayhits(scenes.incoherent_rays_reference(1536))
+    org, d = random_rays_box(1024, -2, 2, 2)
+    b = make_rayhits(org, d)
+    b["tnear"][::3] = 0.5
+    b["tfar"][::5] = 1.5
+    ab = np.concatenate([a, b]).view(a.dtype)
+    run("sphere21", [(v, t, 0, 0xFFFFFFFF)], ab)
+    # 3. terrain with grazing rays + a second, masked geometry (ray masks select which one is visible)
+    tv, tt = scenes.terrain(24, seed=3)
+    pv, pt = scenes.triangle_plane((-1, 0.05, -1), (2, 0, 0), (0, 0, 2), 3, 3)
+    org, d = random_rays_box(2048, -1, 1, 4)
+    org[:, 1] = np.abs(org[:, 1]) * 0.3 + 0.2
+    d[:, 1] = -np.abs(d[:, 1]) * 0.3
+    r = make_rayhits(org, d)
+    r["mask"][0::4] = 0x1
+    r["mask"][1::4] = 0x2
+    r["mask"][2::4] = 0x4
+    r["mask"][3::4] = 0x3
+    run("terrain_masks", [(tv, tt, 0, 0x1), (pv, pt, 3, 0x2)], r)
+
+
+if __name__ == "__main__":
+    if load_reference() is None:
+        sys.exit("oracle/_ref/libembree4.so.4 missing: run python oracle/build_ref.py first")
+    torch.manual_seed(0)
+    main()

@@ -1,0 +1,101 @@
+"""Drop-in boundary checks that need no GPU: the product library loads, exports every symbol that
+include/embree4_b200.h declares, the POD layouts equal the reference's (measured values from SURVEY 8b and, when
+the reference headers are available in this container, compiled side by side), and the library fails loudly --
+it has no CPU fallback -- when no CUDA device exists."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "embree4_b200.h")
+LIB = os.path.join(ROOT, "embree_b200", "csrc", "libembree4_b200.so")
+
+PROBE = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include HEADER
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n",
+    sizeof(struct RTCRay), sizeof(struct RTCHit), sizeof(struct RTCRayHit), offsetof(struct RTCRayHit, hit),
+    sizeof(struct RTCRayHit4), sizeof(struct RTCRayHit8), sizeof(struct RTCRayHit16), sizeof(struct RTCRay16),
+    offsetof(struct RTCRayHit16, hit), offsetof(struct RTCHit, primID), offsetof(struct RTCRay, tfar),
+    sizeof(struct RTCBounds), sizeof(struct RTCIntersectArguments), sizeof(struct RTCRayQueryContext));
+  printf("%d %d %d %d %d %d\n", (int)RTC_FORMAT_FLOAT3, (int)RTC_FORMAT_UINT3, (int)RTC_BUFFER_TYPE_VERTEX,
+    (int)RTC_ERROR_INVALID_OPERATION, (int)RTC_RAY_QUERY_FLAG_COHERENT, (int)RTC_DEVICE_PROPERTY_RAY_MASK_SUPPORTED);
+  return 0;
+}
+"""
+
+
+def _probe(header_path, extra_inc=()):
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "p.c")
+        open(src, "w").write(PROBE.replace("HEADER", f'"{header_path}"'))
+        exe = os.path.join(d, "p")
+        subprocess.check_call(["gcc", "-std=gnu11", "-o", exe, src] + [f"-I{i}" for i in extra_inc])
+        return subprocess.check_output([exe]).decode().split()
+
+
+def test_layout_matches_reference_values():
+    got = _probe(HEADER)
+    # sizeof(RTCRay)=48, RTCHit=48, RTCRayHit=96, offsetof(hit)=48, RTCRayHit4/8/16 = 336/672/1344 (measured)
+    assert got[:7] == ["48", "48", "96", "48", "336", "672", "1344"]
+    assert got[7] == "768" and got[8] == "768"
+    ref_inc = "/root/reference/include"
+    gen = os.path.join(ROOT, "oracle", "_ref", "gen_rel", "include", "embree4")
+    if os.path.exists(os.path.join(ref_inc, "embree4", "rtcore.h")) and os.path.exists(gen):
+        want = _probe("embree4/rtcore.h", extra_inc=(ref_inc, gen))
+        assert got == want
+
+
+def _declared_symbols():
+    txt = open(HEADER).read()
+    return sorted(set(re.findall(r"RTCB200_API[^;(]*?\b(rtc\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    names = _declared_symbols()
+    assert len(names) > 80
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB]).decode()
+    exported = set(l.split()[-1] for l in out.splitlines() if " T " in l)
+    missing = [n for n in names if n not in exported]
+    assert not missing, missing
+    dll = C.CDLL(LIB)
+    for n in names:
+        getattr(dll, n)
+
+
+def test_only_rtc_symbols_and_sm100a_code():
+    """Nothing but the C-ABI is exported, and the embedded device code is sm_100a only."""
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB]).decode()
+    funcs = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    stray = [f for f in funcs if not f.startswith("rtc") and not f.startswith("_")]
+    assert not stray, stray
+    cu = subprocess.run(["cuobjdump", "-lelf", LIB], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", cu))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a machine without CUDA, rtcNewDevice returns NULL and reports why."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import embree_b200
+    lib = embree_b200.load()
+    d = lib.rtcNewDevice(None)
+    assert not d
+    assert lib.rtcGetDeviceError(None) == 1  # RTC_ERROR_UNKNOWN
+    assert b"CUDA" in lib.rtcGetDeviceLastErrorMessage(None)
+
+
+def test_error_strings():
+    import embree_b200
+    lib = embree_b200.load()
+    assert lib.rtcGetErrorString(0) == b"No error"
+    assert lib.rtcGetErrorString(3) == b"Invalid operation"

@@ -1,0 +1,97 @@
+"""CPU emulation of the shared core (embree_b200/csrc/rt_core.cuh compiled for the host by tests/emu): the LBVH
+node construction, BVH8 collapse / slot assignment / 8-bit box quantisation, the traversal loop and the triangle
+test are the exact routines the CUDA kernels call per thread.  They are checked against the oracle on small scenes
+so logic errors surface without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from embree_b200 import scenes
+from embree_b200.rtc import make_rayhits, rays_of
+from tests.conftest import GOLDEN, load_golden
+from tests.parity import compare_hits
+
+
+def _emu_trace(emu, v, t, rays, occluded=False, mask=0xFFFFFFFF):
+    v = np.ascontiguousarray(v, np.float32)
+    t = np.ascontiguousarray(t, np.uint32)
+    h = emu.emu_build(v.ctypes.data, len(v), t.ctypes.data, len(t), 0, mask, 0)
+    stats = np.zeros(2, np.uint64)
+    emu.emu_trace(h, rays.ctypes.data, len(rays), 1 if occluded else 0, stats.ctypes.data)
+    info = dict(nodes=emu.emu_num_nodes(h), depth=emu.emu_depth(h), trav_nodes=int(stats[0]), trav_tris=int(stats[1]))
+    emu.emu_free(h)
+    return rays, info
+
+
+@pytest.mark.parametrize("num_phi", [3, 8, 33])
+def test_sphere_matches_oracle(emu, oracle, num_phi):
+    v, t = scenes.triangle_sphere(num_phi)
+    rays = scenes.as_numpy_rayhits(scenes.incoherent_rays_reference(5000))
+    want = oracle.trace(v, t, rays.copy())
+    got, info = _emu_trace(emu, v, t, rays.copy())
+    rep = compare_hits(want, got)
+    assert rep["id_mismatch"] == 0 and rep["tie"] == 0 and rep["hit_miss_disagree"] == 0, (rep, info)
+    assert rep["max_rel_t"] == 0.0 and rep["ng_bit_exact"], rep  # same arithmetic -> same bits
+    wo = oracle.trace(v, t, rays_of(rays), occluded=True)
+    go, _ = _emu_trace(emu, v, t, rays_of(rays), occluded=True)
+    assert (wo["tfar"].view(np.uint32) == go["tfar"].view(np.uint32)).all()
+
+
+def test_golden_single_mesh(emu):
+    meshes, rin, want_i, want_o, _ = load_golden("sphere21")
+    (v, t, gid, mask) = meshes[0]
+    got, _ = _emu_trace(emu, v, t, rin.copy(), mask=mask)
+    rep = compare_hits(want_i, got)
+    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["max_rel_t"] <= 1e-4 and rep["ng_bit_exact"], rep
+
+
+def test_tiny_scenes(emu, oracle):
+    """1, 2, 3, 4, 9 triangles: root-only trees, partially filled nodes."""
+    rng = np.random.RandomState(5)
+    for n in (1, 2, 3, 4, 9, 25):
+        v = rng.uniform(-1, 1, (3 * n, 3)).astype(np.float32)
+        t = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+        org = rng.uniform(-2, 2, (2000, 3)).astype(np.float32)
+        d = (rng.uniform(-1, 1, (2000, 3)) - org * 0.5).astype(np.float32)
+        rays = make_rayhits(org, d)
+        want = oracle.trace(v, t, rays.copy())
+        got, info = _emu_trace(emu, v, t, rays.copy())
+        rep = compare_hits(want, got)
+        assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] == 0, (n, rep)
+
+
+def test_axis_aligned_and_degenerate(emu, oracle):
+    """Flat boxes (axis-aligned cube faces), zero direction components, degenerate (zero-area) triangles."""
+    (cv, ct), _ = scenes.cube_and_ground()
+    extra_v = np.array([[0, 0, 0], [0, 0, 0], [0, 0, 0], [3, 3, 3], [3, 3, 3], [4, 4, 4]], np.float32)
+    v = np.concatenate([cv, extra_v])
+    t = np.concatenate([ct, np.array([[8, 9, 10], [11, 12, 13]], np.uint32)])
+    org = np.array([[0.3, 0.2, -5], [0.3, 0.2, 5], [-5, 0.1, 0.2], [0.5, 5, 0.5], [1, 1, -5], [0, 0, 0], [0.25, -5, 0.25]], np.float32)
+    d = np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, -1, 0], [0, 0, 1], [1, 1, 1], [0, 1, 0]], np.float32)
+    rays = make_rayhits(org, d)
+    want = oracle.trace(v, t, rays.copy())
+    got, _ = _emu_trace(emu, v, t, rays.copy())
+    rep = compare_hits(want, got)
+    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0, rep
+    assert (want["geomID"][:4] == 0).all()
+
+
+def test_watertight_sphere_from_inside(emu):
+    """WatertightTest (verify.cpp:3611-3690): rays from inside a closed sphere must not leak (<= 2e-5)."""
+    v, t = scenes.triangle_sphere(50)
+    rays = scenes.as_numpy_rayhits(scenes.incoherent_rays_reference(50000, org=(0.1, -0.2, 0.05)))
+    got, _ = _emu_trace(emu, v, t, rays)
+    assert (got["geomID"] == 0xFFFFFFFF).mean() <= 2e-5
+
+
+def test_nan_inf_rays_terminate(emu):
+    """NaNTest/InfTest (verify.cpp:3813-3963): invalid rays must terminate and leave a miss."""
+    v, t = scenes.triangle_sphere(8)
+    bad = [np.nan, np.inf, -np.inf]
+    org, d = [], []
+    for b in bad:
+        org += [[b, 0, 0], [0, 0, 0], [0, b, 0]]
+        d += [[0, 0, 1], [b, 0, 1], [1, b, b]]
+    rays = make_rayhits(np.array(org, np.float32), np.array(d, np.float32))
+    _emu_trace(emu, v, t, rays)  # must return

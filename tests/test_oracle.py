@@ -1,0 +1,88 @@
+"""The oracle (oracle/embree_oracle.c, a scalar restatement of the reference hot path) is pinned here against
+(1) the reference's own known-answer tests restated from tutorials/verify/verify.cpp, (2) golden vectors produced
+by the unmodified reference (tests/golden/*.npz, tests/golden/make_golden.py) and (3) the reference library itself
+when oracle/_ref has been built in this container."""
+import numpy as np
+import pytest
+
+from embree_b200 import scenes
+from embree_b200.rtc import make_rayhits, rays_of
+from tests.conftest import GOLDEN, load_golden
+from tests.parity import compare_hits, load_reference
+
+
+def test_triangle_hit_kat(oracle):
+    """TriangleHitTest (verify.cpp:2462-2547): 256 rays from z=-1 onto the unit triangle; geomID=0, primID=0,
+    u,v,t within 16 ulp, Ng == (0,0,1), org+t*dir == v0+u(v1-v0)+v(v2-v0)."""
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    t = np.array([[0, 1, 2]], np.uint32)
+    u0, v0 = np.meshgrid((np.arange(16) + 0.5) / 16 * 0.45, (np.arange(16) + 0.5) / 16 * 0.45)  # stays inside, off the edges
+    org = np.stack([u0.ravel(), v0.ravel(), -np.ones(256)], 1).astype(np.float32)
+    r = make_rayhits(org, np.tile([[0, 0, 1]], (256, 1)))
+    out = oracle.trace(v, t, r)
+    ulp = 16 * np.finfo(np.float32).eps
+    assert (out["geomID"] == 0).all() and (out["primID"] == 0).all()
+    assert np.abs(out["u"] - org[:, 0]).max() <= ulp and np.abs(out["v"] - org[:, 1]).max() <= ulp
+    assert np.abs(out["tfar"] - 1.0).max() <= ulp
+    assert (out["Ng_x"] == 0).all() and (out["Ng_y"] == 0).all() and (out["Ng_z"] == 1).all()
+    assert (out["instID"] == 0xFFFFFFFF).all()
+
+
+def test_minimal_tutorial_kat(oracle):
+    """tutorials/minimal/minimal.cpp:159-206: ray (0.33,0.33,-1)+(0,0,1) hits at t=1; ray from (1,1,-1) misses."""
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    t = np.array([[0, 1, 2]], np.uint32)
+    out = oracle.trace(v, t, make_rayhits([[0.33, 0.33, -1], [1, 1, -1]], [[0, 0, 1], [0, 0, 1]]))
+    assert out["geomID"][0] == 0 and out["primID"][0] == 0 and out["tfar"][0] == 1.0
+    assert abs(out["u"][0] - 0.33) < 1e-6 and abs(out["v"][0] - 0.33) < 1e-6
+    assert out["geomID"][1] == 0xFFFFFFFF and np.isinf(out["tfar"][1])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_oracle_vs_golden(oracle, name):
+    meshes, rin, want_i, want_o, bounds = load_golden(name)
+    sc = oracle.scene(meshes)
+    got = sc.trace(rin.copy())
+    rep = compare_hits(want_i, got)
+    assert rep["id_mismatch"] == 0 and rep["tie"] == 0 and rep["hit_miss_disagree"] == 0, rep
+    assert rep["max_rel_t"] <= 1e-4 and rep["max_abs_uv"] <= 1e-4 and rep["ng_bit_exact"] and rep["miss_untouched"], rep
+    occ = sc.trace(rays_of(rin), occluded=True)
+    assert (occ["tfar"].view(np.uint32) == want_o["tfar"].view(np.uint32)).all()
+    assert np.array_equal(sc.bounds(), bounds)
+    sc.free()
+
+
+def test_oracle_vs_reference_live(oracle):
+    R = load_reference()
+    if R is None:
+        pytest.skip("oracle/_ref not built here (python oracle/build_ref.py)")
+    v, t = scenes.triangle_sphere(41)
+    rays = scenes.as_numpy_rayhits(scenes.incoherent_rays_reference(20000))
+    dev = R.new_device(None)
+    sc = R.rtcNewScene(dev)
+    _, keep = R.add_triangle_mesh(dev, sc, v, t, mask=0xFFFFFFFF)
+    R.rtcCommitScene(sc)
+    want = R.intersect(sc, rays.copy(), "1")
+    got = oracle.trace(v, t, rays.copy())
+    rep = compare_hits(want, got)
+    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["max_rel_t"] <= 1e-4 and rep["ng_bit_exact"], rep
+    R.rtcReleaseScene(sc)
+    R.rtcReleaseDevice(dev)
+
+
+def test_invalid_triangles_are_dropped(oracle):
+    """scene_triangle_mesh.h:194-215: out-of-range index or non-finite / huge vertex drops the triangle."""
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [np.nan, 0, 0], [2e18, 0, 0]], np.float32)
+    t = np.array([[0, 1, 2], [0, 1, 3], [0, 1, 4], [0, 1, 7]], np.uint32)
+    sc = oracle.scene([(v, t, 0, 0xFFFFFFFF)])
+    assert sc.stats()["prims"] == 1
+    out = sc.trace(make_rayhits([[0.2, 0.2, -1]], [[0, 0, 1]]))
+    assert out["primID"][0] == 0
+    sc.free()
+
+
+def test_empty_scene(oracle):
+    sc = oracle.scene([(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), 0, 1)])
+    out = sc.trace(make_rayhits([[0, 0, -1]], [[0, 0, 1]]))
+    assert out["geomID"][0] == 0xFFFFFFFF and np.isinf(out["tfar"][0])
+    sc.free()
