@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json configs[2]).
+
+Workload: synthetic 10 M-triangle mesh (createTriangleSphere numPhi=1581 = 9 991 920 triangles, the reference's own
+benchmark generator), 64 Mi incoherent diffuse-bounce rays (33 cosine-weighted bounces per hit of a 1920x1080 pinhole
+image from inside the mesh, path-tracer style: tutorials/pathtracer/pathtracer_device.cpp:1119-1120,1597-1600), traced
+as batched rtcIntersect1 records.  A step = one pass of the 64 Mi-ray stream through the trace kernel.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rays R] [--phi P]
+
+value  : Mrays/s with the RTCRayHit[] stream resident in HBM (rtcb200Intersect1MDevice on torch's current stream),
+         whole job over all ranks (weak scaling: every rank traces its own 64 Mi rays; compact hit records are
+         gathered on rank 0 over NCCL inside the timed region).
+e2e    : the same stream through the host-pointer entry point rtcb200Intersect1M with pinned host buffers:
+         H2D copy + trace + D2H copy inside the timed region.
+--impl reference : the unmodified reference (oracle/_ref/libembree4.so.4, else the C port) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from embree_b200 import scenes  # noqa: E402
+
+PRIMARY_W, PRIMARY_H, REPLICATE = 1920, 1080, 33
+EYE, LOOK = (0.15, -0.1, 0.05), (0.3, 0.2, 1.0)
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def bounce_rays(primary_hits, ids, replicate=REPLICATE):
+    """Bounce ray `i` (global index) leaves the hit of primary ray i // replicate with random numbers seeded by i.
+    Primary rays that missed re-emit themselves so that indices never depend on hit/miss compaction."""
+    parent = (ids // replicate).clamp_max(primary_hits.shape[0] - 1)
+    src = primary_hits.index_select(0, parent)
+    pri = src.view(torch.int32)
+    missed = pri[:, 18] == -1
+    if missed.any():
+        pri[missed, 18] = 0
+        src[missed, 8] = 1.0
+        src[missed, 12:15] = -src[missed, 4:7]
+    out = scenes.diffuse_bounce_rays(src, seed=0, replicate=1, ids=ids)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_scene(phi):
+    t0 = time.time()
+    v, t = scenes.triangle_sphere(phi)
+    log(f"scene: sphere numPhi={phi}: {len(t)} triangles, {len(v)} vertices ({time.time() - t0:.1f}s)")
+    return v, t
+
+
+def commit(lib, dev, v, t, quality=1):
+    sc = lib.rtcNewScene(dev)
+    lib.rtcSetSceneBuildQuality(sc, quality)
+    _, keep = lib.add_triangle_mesh(dev, sc, v, t, mask=0xFFFFFFFF)
+    t0 = time.time()
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    return sc, keep, time.time() - t0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation on the host cores, same scene / ray definition; each step
+    traces a bounded strided sample of the 64 Mi-ray stream with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests.parity import api_trace_mt, load_oracle, load_reference
+    cores = os.cpu_count()
+    v, t = make_scene(args.phi)
+    R = load_reference()
+    kind = "reference" if R is not None else "port"
+    nsample = min(args.rays, 1 << 24)
+    stride = max(1, args.rays // nsample)
+    ids = torch.arange(0, nsample, dtype=torch.int64) * stride
+    prim = scenes.primary_rays(PRIMARY_W, PRIMARY_H, eye=EYE, look=LOOK)
+    if R is not None:
+        dev = R.new_device(None)
+        sc, keep, bt = commit(R, dev, v, t)
+        log(f"reference rtcCommitScene: {bt * 1e3:.0f} ms")
+        prim_np = scenes.as_numpy_rayhits(prim)
+        api_trace_mt(R, sc, prim_np, cores)
+        trace = lambda recs: api_trace_mt(R, sc, recs, cores)  # noqa: E731
+    else:
+        o = load_oracle()
+        osc = o.scene([(v, t, 0, 0xFFFFFFFF)])
+        prim_np = osc.trace(scenes.as_numpy_rayhits(prim), nthreads=cores)
+        trace = lambda recs: osc.trace(recs, nthreads=cores)  # noqa: E731
+    prim_hits = torch.from_numpy(prim_np.view(np.float32).reshape(-1, 24).copy())
+    rays = scenes.as_numpy_rayhits(bounce_rays(prim_hits, ids))
+    times = []
+    for it in range(args.warmup + args.steps):
+        work = rays.copy()
+        t0 = time.perf_counter()
+        trace(work)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = float(np.mean(times)) * 1e3
+    val = nsample / (ms * 1e-3) * 1e-6
+    line = {"impl": "reference", "metric": "Mrays/s incoherent diffuse-bounce, 10M-triangle scene", "value": val, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, len(t)),
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                             "sample": f"{nsample} rays = every {stride}th ray of the {args.rays}-ray stream per step, rtcIntersect1 on {cores} host threads (FTZ|DAZ)"},
+            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, ntris):
+    return {"workload": f"configs[2]: createTriangleSphere(numPhi={args.phi}) = {ntris} triangles, BUILD_QUALITY_MEDIUM (device binned-SAH); "
+                        f"{args.rays} incoherent diffuse-bounce rays ({REPLICATE} cosine-weighted bounces per hit of a {PRIMARY_W}x{PRIMARY_H} "
+                        f"pinhole image from inside the mesh), batched rtcIntersect1 over RTCRayHit[]",
+            "rays_per_gpu": args.rays, "triangles": ntris, "l2": "ray stream 6.4 GB and BVH 0.6 GB per step exceed the 126 MB L2",
+            "parallelism": f"ray-stream sharding x{args.gpus}, BVH replicated, compact hit gather to rank 0"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--rays", type=int, default=1 << 26)
+    ap.add_argument("--phi", type=int, default=1581)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import embree_b200
+    from embree_b200 import sharding
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    devt = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=devt)
+    lib = embree_b200.load()
+    dev = lib.new_device(f"gpu={local},verbose={2 if rank == 0 else 0}")
+    v, t = make_scene(args.phi)
+    sc, keep, commit_s = commit(lib, dev, v, t)
+    st = lib.scene_stats(sc)
+    log(f"rank {rank}: commit {commit_s * 1e3:.0f} ms wall, device build {st.build_ms:.1f} ms, {st.num_nodes} nodes")
+
+    a = lib.args()
+    stream = torch.cuda.current_stream().cuda_stream
+    n = args.rays
+
+    def trace_dev(tensor, count):
+        lib.rtcb200Intersect1MDevice(sc, C.c_void_p(tensor.data_ptr()), count, C.byref(a), C.c_void_p(stream))
+
+    # ---- ray stream, generated in HBM
+    prim = scenes.primary_rays(PRIMARY_W, PRIMARY_H, eye=EYE, look=LOOK, device=devt)
+    trace_dev(prim, prim.shape[0])
+    torch.cuda.synchronize()
+    A = torch.empty((n, 24), dtype=torch.float32, device=devt)
+    CH = 1 << 22
+    for c0 in range(0, n, CH):
+        ids = torch.arange(c0, min(c0 + CH, n), device=devt, dtype=torch.int64) + rank * n
+        A[c0:c0 + len(ids)] = bounce_rays(prim, ids)
+    del prim
+    B = A.clone()
+    torch.cuda.synchronize()
+    lib.check(dev)
+
+    # ---- traversal work per ray (device stat counters = EMBREE_STAT_COUNTERS analogue) on a 1 Mi-ray strided sample
+    ns = min(n, 1 << 20)
+    S = A[:: max(1, n // ns)][:ns].contiguous()
+    lib.rtcb200SetSceneStatCounters(sc, 1)
+    lib.rtcb200ResetSceneStatCounters(sc)
+    trace_dev(S, S.shape[0])
+    torch.cuda.synchronize()
+    st2 = lib.scene_stats(sc)
+    lib.rtcb200SetSceneStatCounters(sc, 0)
+    nodes_per_ray, tris_per_ray = st2.trav_nodes / st2.trav_rays, st2.trav_tris / st2.trav_rays
+    bytes_per_ray = 48 + 48 + 4 + nodes_per_ray * 80 + tris_per_ray * 48
+    del S
+
+    # ---- hit gather plumbing (N > 1): compact 32-byte records to rank 0, chunk c gathered while chunk c+1 traces
+    NCH = 8 if world > 1 else 1
+    bounds = [sharding.shard_bounds(n, c, NCH) for c in range(NCH)]
+    comm_stream = torch.cuda.Stream() if world > 1 else None
+    compact = torch.empty((n, 8), dtype=torch.float32, device=devt) if world > 1 else None
+    gathered = [torch.empty((n, 8), dtype=torch.float32, device=devt) for _ in range(world)] if (world > 1 and rank == 0) else None
+    kernel_ms = []
+
+    def step(record_kernel_ms=False):
+        B[:, 8] = float("inf")  # restore the only input field the trace overwrites (ray.tfar)
+        for (b, e) in bounds:
+            lib.rtcb200Intersect1MDevice(sc, C.c_void_p(B[b:e].data_ptr()), e - b, C.byref(a), C.c_void_p(stream))
+            if world > 1:
+                sharding.compact_hits(B[b:e], out=compact[b:e])
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(ev)
+                    dist.gather(compact[b:e], [g[b:e] for g in gathered] if rank == 0 else None, dst=0)
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(comm_stream)
+        if record_kernel_ms and world == 1:
+            kernel_ms.append(lib.rtcb200GetLastTraceMs(sc))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.rtcb200GetLaunchCount()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step(record_kernel_ms=True)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    launches = lib.rtcb200GetLaunchCount() - l0
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=devt)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item())
+    value = n * world / (ms_per_step * 1e-3) * 1e-6
+    lib.check(dev)
+    sampler.join(timeout=2)
+
+    # ---- end to end through the host-pointer entry point (pinned host memory, H2D + trace + D2H timed)
+    e2e = None
+    if not args.no_e2e:
+        H = torch.empty((n, 24), dtype=torch.float32).pin_memory()
+        H.copy_(A)
+        times = []
+        reps = max(1, min(args.steps, 3))
+        for it in range(1 + reps):
+            H[:, 8] = float("inf")
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            lib.rtcb200Intersect1M(sc, C.c_void_p(H.data_ptr()), n, C.byref(a))
+            dt = time.perf_counter() - t0
+            if it > 0:
+                times.append(dt)
+        tt = torch.tensor([float(np.mean(times))], device=devt)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world / float(tt.item()) * 1e-6, "unit": "Mrays/s", "h2d_bytes_per_step": n * 96 * world,
+               "d2h_bytes_per_step": n * 96 * world, "steps": reps, "ms_per_step": float(tt.item()) * 1e3,
+               "api": "rtcb200Intersect1M(scene, RTCRayHit* host, M, args), pinned host buffers, 3-stream chunked pipeline"}
+        lib.check(dev)
+        host_result = H
+    # ---- parity sample + CPU baseline (rank 0, N == 1)
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from tests.parity import api_trace_mt, compare_hits, load_oracle, load_reference
+        B.copy_(A)
+        trace_dev(B, n)
+        torch.cuda.synchronize()
+        cores = os.cpu_count()
+        nsample = min(n, 1 << 24)
+        stride = max(1, n // nsample)
+        sample_in = scenes.as_numpy_rayhits(A[::stride][:nsample].cpu())
+        got = scenes.as_numpy_rayhits(B[::stride][:nsample].cpu())
+        R = load_reference()
+        if R is not None:
+            rdev = R.new_device(None)
+            rsc, rkeep, rbt = commit(R, rdev, v, t)
+            log(f"reference rtcCommitScene ({cores} threads): {rbt * 1e3:.0f} ms")
+            best = 1e30
+            for _ in range(2):
+                w = sample_in.copy()
+                t0 = time.perf_counter()
+                api_trace_mt(R, rsc, w, cores)
+                best = min(best, time.perf_counter() - t0)
+            kind, want = "reference", w
+        else:
+            osc = load_oracle().scene([(v, t, 0, 0xFFFFFFFF)])
+            w = sample_in.copy()
+            t0 = time.perf_counter()
+            osc.trace(w, nthreads=cores)
+            best = time.perf_counter() - t0
+            kind, want, rbt = "port", w, None
+        cpu_baseline = {"value": nsample / best * 1e-6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                        "sample": f"{nsample} rays = every {stride}th ray of the stream, rtcIntersect1 loop on {cores} host threads (FTZ|DAZ), best of 2",
+                        "commit_ms": None if rbt is None else rbt * 1e3}
+        both = (want["geomID"] != 0xFFFFFFFF) | (got["geomID"] != 0xFFFFFFFF)
+        parity = compare_hits(want, got)
+        parity["checked_against"] = kind
+        del both
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        kms = float(np.mean(kernel_ms)) if kernel_ms else ms_per_step
+        achieved = bytes_per_ray * n / (kms * 1e-3) * 1e-9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line = {"metric": "Mrays/s incoherent diffuse-bounce, 10M-triangle scene", "value": value, "unit": "Mrays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, len(t)),
+                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "rtk::trace_kernel<1,false,false>",
+                             "kernel_ms": kms, "algorithmic_bytes_per_ray": bytes_per_ray,
+                             "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                             "note": "algorithmic bytes = 100 B ray/hit I/O + nodes/ray*80 B + tris/ray*48 B (device stat counters, 1 Mi-ray sample)"},
+                "cpu_baseline": cpu_baseline, "parity": parity,
+                "build": {"device_ms": st.build_ms, "commit_wall_ms": commit_s * 1e3, "nodes": int(st.num_nodes), "sah": st.sah_cost,
+                          "builder": "sah" if st.builder else "lbvh"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

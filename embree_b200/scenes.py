@@ -190,16 +190,21 @@ def incoherent_rays_reference(n, org=(0.0, 0.0, 0.0), device="cpu", first_id=0):
     return pack_rayhits(o, d, 0.0, float("inf"))
 
 
-def diffuse_bounce_rays(rayhits, seed=0, replicate=1):
-    """Cosine-weighted bounce off every *hit* of `rayhits` (traced RTCRayHit records), as the path tracer does:
+def diffuse_bounce_rays(rayhits, seed=0, replicate=1, ids=None):
+    """Cosine-weighted bounce off the hits in `rayhits` (traced RTCRayHit records), as the path tracer does:
     P = org + t*dir, N = normalize(Ng) facing the incoming ray, wi = frame(N) * cosineSampleHemisphere(u1,u2),
-    eps = 32 * 1.19209e-7 * max(|P|, t), org' = P + eps*N, tnear = eps, tfar = inf.  Each hit emits `replicate`
-    rays with different random numbers.  Returns a new ray set (only from hit records)."""
-    ri = rayhits.view(torch.int32)
-    hitmask = ri[:, 18] != -1
-    r = rayhits[hitmask]
-    if replicate > 1:
-        r = r.repeat_interleave(replicate, dim=0)
+    eps = 32 * 1.19209e-7 * max(|P|, t), org' = P + eps*N, tnear = eps, tfar = inf.
+    ids is None: only hit records emit, `replicate` rays each, random numbers seeded by the output index.
+    ids given  : row k of `rayhits` (which must be a hit) emits exactly one ray seeded by ids[k]."""
+    if ids is None:
+        ri = rayhits.view(torch.int32)
+        r = rayhits[ri[:, 18] != -1]
+        if replicate > 1:
+            r = r.repeat_interleave(replicate, dim=0)
+        ids = torch.arange(r.shape[0], device=r.device, dtype=torch.int64)
+    else:
+        r = rayhits
+    ids = ids + seed * 7919
     n = r.shape[0]
     dev = r.device
     org, d, t = r[:, 0:3], r[:, 4:7], r[:, 8:9]
@@ -208,7 +213,6 @@ def diffuse_bounce_rays(rayhits, seed=0, replicate=1):
     N = Ng / Ng.norm(dim=1, keepdim=True).clamp_min(1e-30)
     flip = (N * d).sum(1, keepdim=True) > 0
     N = torch.where(flip, -N, N)
-    ids = torch.arange(n, device=dev, dtype=torch.int64) + (seed << 32 >> 32) * 7919
     rs = RandomSampler(ids)
     u1, u2 = rs.get1d(), rs.get1d()
     phi = 2.0 * math.pi * u1
