@@ -88,47 +88,167 @@ struct RayIO {
 };
 
 constexpr int TRACE_THREADS = 128;
+constexpr int TRACE_WARPS = TRACE_THREADS / 32;
+constexpr int kTriWaitMax = 3;    // ... but never make a lane wait longer than this many iterations
+constexpr int kTriBatchMin = 6;   // run a triangle step only when this many lanes wait for one (or no lane has node work)
 
+// Persistent warps.  Every warp owns the 32-ray blocks w, w+W, w+2W, ... of the stream (W = warps in the grid) and
+// keeps its 32 lanes busy: a lane whose ray has terminated writes its result and immediately takes the warp's next
+// unassigned ray (ballot + popc ranking, no atomics).  One loop iteration = at most one node step (pop a child of the
+// current node group, fetch the 80-byte node, slab-test its 8 children) for the lanes that want it, and at most one
+// triangle step for the lanes that have triangle hits pending; the two phases are warp-synchronous so lanes in the
+// same phase execute together instead of serialising through a per-thread while-while loop.
 template <int K, bool OCCLUDED, bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS) trace_kernel(const TraceParams p) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * TRACE_THREADS + threadIdx.x;
-  TravStats st{0, 0};
-  bool active = false;
-  if (i < p.n) {
-    Ray r;
-    active = RayIO<K, OCCLUDED>::load(p, i, r);
-    if (active) {
-      Hit h;
-      const NodeLoadG ldn{reinterpret_cast<const uint4*>(p.nodes)};
-      const TriLoadG ldt{reinterpret_cast<const uint4*>(p.tris)};
-      const bool found = traverse<OCCLUDED, STATS>(r, h, ldn, ldt, p.root_valid, &st);
-      if (found) {
-        if (OCCLUDED) RayIO<K, OCCLUDED>::store_tfar(p, i, -INFINITY);  // bvh_intersector1.cpp:186-188
-        else RayIO<K, OCCLUDED>::store_hit(p, i, h);
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned long long warp_id = (unsigned long long)blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5);
+  const unsigned long long num_warps = (unsigned long long)gridDim.x * TRACE_WARPS;
+  const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(p.nodes);
+  const uint4* __restrict__ tris = reinterpret_cast<const uint4*>(p.tris);
+
+  // per-lane ray state
+  Ray r;
+  float idx = 0, idy = 0, idz = 0, tnear_c = 0, tfar_c = 0, tfar_tri = 0;
+  uint32_t oct = 0, oct_inv4 = 0;
+  bool negx = false, negy = false, negz = false;
+  Hit hit;
+  hit.t = 0; hit.u = 0; hit.v = 0; hit.ngx = 0; hit.ngy = 0; hit.ngz = 0; hit.primID = 0; hit.geomID = 0;
+  bool found = false, active = false;
+  unsigned long long ray_index = 0;
+  uint32_t ngx = 0, ngy = 0, tgx = 0, tgy = 0;
+  uint32_t stack_x[kStackSize], stack_y[kStackSize];
+  int sp = 0;
+  unsigned long long j_next = 0;        // warp-uniform: next unassigned ray of this warp's private sequence
+  unsigned long long st_rays = 0, st_nodes = 0, st_tris = 0;
+  bool exhausted = false;                // this lane was handed an index beyond the stream
+  int tri_wait = 0;                      // warp-uniform: iterations some lane has been waiting for a triangle step
+
+  for (;;) {
+    // ---- 1. refill idle lanes
+    const unsigned idle = __ballot_sync(FULL, !active);
+    if (idle) {
+      if (!active && !exhausted) {
+        const unsigned long long j = j_next + __popc(idle & lt_mask);
+        ray_index = ((j >> 5) * num_warps + warp_id) * 32ull + (j & 31ull);
+        if (ray_index >= p.n) exhausted = true;
+        else if (RayIO<K, OCCLUDED>::load(p, ray_index, r)) {
+          if (STATS) ++st_rays;
+          found = false;
+          sp = 0; tgx = 0; tgy = 0;
+          // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129)
+          const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
+          idx = rcp_safe(r.dx); idy = rcp_safe(r.dy); idz = rcp_safe(r.dz);
+          negx = idx < 0.0f; negy = idy < 0.0f; negz = idz < 0.0f;
+          oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
+          oct_inv4 = (7u - oct) * 0x01010101u;
+          tnear_c = fmaxf(r.tnear, 0.0f);
+          tfar_c = fmaxf(r.tfar, 0.0f);
+          tfar_tri = r.tfar;
+          ngx = 0; ngy = go ? 0x80000000u : 0u;   // root entered as "one pending internal child, imask 0"
+          active = go;
+        }
+      }
+      j_next += __popc(idle);
+      if (!__any_sync(FULL, active)) {
+        if (__all_sync(FULL, exhausted)) break;
+        continue;
+      }
+    }
+    // ---- 2. node step for lanes that have no triangle pending and a node child pending
+    const bool want_node = active && tgy == 0 && (ngy & 0xFF000000u);
+    if (want_node) {
+      const int bit = 31 - __clz((int)ngy);
+      ngy &= ~(1u << bit);
+      if (ngy & 0xFF000000u) { stack_x[sp] = ngx; stack_y[sp] = ngy; ++sp; }
+      const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
+      const uint32_t node_index = ngx + (uint32_t)__popc(ngy & 0xFFu & ((1u << slot) - 1u));
+      const uint4* np = nodes + (size_t)node_index * 5;
+      const uint4 a0 = __ldg(np), a1 = __ldg(np + 1), a2 = __ldg(np + 2), a3 = __ldg(np + 3), a4 = __ldg(np + 4);
+      if (STATS) ++st_nodes;
+      const u32x4 n0{a0.x, a0.y, a0.z, a0.w}, n1{a1.x, a1.y, a1.z, a1.w}, n2{a2.x, a2.y, a2.z, a2.w},
+          n3{a3.x, a3.y, a3.z, a3.w}, n4{a4.x, a4.y, a4.z, a4.w};
+      const uint32_t hm = node_hitmask<OCCLUDED>(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz,
+                                                 tnear_c, tfar_c, oct_inv4);
+      ngx = n1.x;
+      ngy = (hm & 0xFF000000u) | (n0.w >> 24);
+      tgx = n1.y;
+      tgy = hm & 0x00FFFFFFu;
+    }
+    // ---- 3. triangle step, batched across the warp
+    const unsigned tri_lanes = __ballot_sync(FULL, active && tgy != 0);
+    const unsigned node_lanes = __ballot_sync(FULL, active && tgy == 0 && (ngy & 0xFF000000u));
+    if (tri_lanes && (__popc(tri_lanes) >= kTriBatchMin || node_lanes == 0 || ++tri_wait >= kTriWaitMax)) {
+      tri_wait = 0;
+      if (active && tgy != 0) {
+        const int tb = 31 - __clz((int)tgy);
+        tgy &= ~(1u << tb);
+        const uint4* tp = tris + (size_t)(tgx + (uint32_t)tb) * 3;
+        const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        if (STATS) ++st_tris;
+        TriHit th;
+        if (tri_test(r, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
+                     __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
+                     __uint_as_float(c.z), th) &&
+            (c.w & r.mask) != 0) {
+          found = true;
+          if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; }     // any hit terminates the ray
+          else {
+            const float rcpAbsDen = 1.0f / th.absDen;
+            hit.t = th.T * rcpAbsDen; hit.u = th.U * rcpAbsDen; hit.v = th.V * rcpAbsDen;
+            hit.ngx = th.ngx; hit.ngy = th.ngy; hit.ngz = th.ngz;
+            hit.primID = a.w; hit.geomID = b.w;
+            tfar_tri = hit.t;
+            tfar_c = fmaxf(hit.t, 0.0f);
+          }
+        }
+      }
+    }
+    // ---- 4. pop or finish
+    if (active && tgy == 0 && (ngy & 0xFF000000u) == 0) {
+      if (sp > 0) {
+        --sp;
+        const uint32_t px = stack_x[sp], py = stack_y[sp];
+        if (py & 0xFF000000u) { ngx = px; ngy = py; }
+        else { tgx = px; tgy = py; ngx = 0; ngy = 0; }
+      } else {
+        if (found) {
+          if (OCCLUDED) RayIO<K, OCCLUDED>::store_tfar(p, ray_index, -INFINITY);   // bvh_intersector1.cpp:186-188
+          else RayIO<K, OCCLUDED>::store_hit(p, ray_index, hit);
+        }
+        active = false;
       }
     }
   }
   if (STATS) {
-    unsigned long long rays = active ? 1 : 0, nodes = st.nodes, tris = st.tris;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
-      nodes += __shfl_xor_sync(0xFFFFFFFFu, nodes, o);
-      tris += __shfl_xor_sync(0xFFFFFFFFu, tris, o);
+      st_rays += __shfl_xor_sync(FULL, st_rays, o);
+      st_nodes += __shfl_xor_sync(FULL, st_nodes, o);
+      st_tris += __shfl_xor_sync(FULL, st_tris, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&p.stat[0], rays); atomicAdd(&p.stat[1], nodes); atomicAdd(&p.stat[2], tris);
-    }
+    if (lane == 0) { atomicAdd(&p.stat[0], st_rays); atomicAdd(&p.stat[1], st_nodes); atomicAdd(&p.stat[2], st_tris); }
   }
 }
 
+static int g_num_sms = 0;
+
 template <int K, bool OCCLUDED>
 static int launch_k(const TraceParams& p, cudaStream_t st) {
-  const unsigned long long blocks = (p.n + TRACE_THREADS - 1) / TRACE_THREADS;
-  if (blocks == 0) return 0;
-  if (blocks > 0x7FFFFFFFull) return (int)cudaErrorInvalidValue;
-  if (p.stat) trace_kernel<K, OCCLUDED, true><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(p);
-  else trace_kernel<K, OCCLUDED, false><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(p);
+  if (p.n == 0) return 0;
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  // persistent grid: a multiple of the SM count, capped by the work available
+  const unsigned long long need = (p.n + TRACE_THREADS - 1) / TRACE_THREADS;
+  const unsigned long long cap = (unsigned long long)g_num_sms * 6;
+  const unsigned blocks = (unsigned)(need < cap ? need : cap);
+  if (p.stat) trace_kernel<K, OCCLUDED, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
+  else trace_kernel<K, OCCLUDED, false><<<blocks, TRACE_THREADS, 0, st>>>(p);
   count_launch();
   return (int)cudaGetLastError();
 }
