@@ -338,10 +338,49 @@ struct DeviceAlloc {  // allocation callbacks of collapse_node() on the device: 
 __global__ void __launch_bounds__(128) collapse_level(const Node2* __restrict__ n2, uint32_t* __restrict__ src,
                                                       uint32_t begin, uint32_t end, Node8* __restrict__ n8,
                                                       uint32_t* __restrict__ tri_src, const uint32_t* __restrict__ sortedA,
-                                                      const uint32_t* __restrict__ sortedB, BuildInfo* info, float inv_root_area) {
+                                                      const uint32_t* __restrict__ sortedB, BuildInfo* info, float inv_root_area, int policy,
+                                                      const uint32_t* __restrict__ dec) {
   const uint32_t q = begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= end) return;
-  collapse_node(n2, src, q, n8, tri_src, sortedA, sortedB, inv_root_area, DeviceAlloc{info});
+  collapse_node(n2, src, q, n8, tri_src, sortedA, sortedB, inv_root_area, policy, dec, DeviceAlloc{info});
+}
+
+// bottom-up dynamic programme for the SAH-optimal collapse (rt_core.cuh dp_node): one thread per primitive climbs
+// towards the root; the second arrival at a node (atomic flag) owns it, exactly like the refit.
+__global__ void __launch_bounds__(256) collapse_dp(const Node2* __restrict__ nodes, int n, uint32_t* __restrict__ flags,
+                                                   float* F /*[2n][8]*/, uint32_t* dec, float c_node, float c_tri) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t leaf = (uint32_t)(n - 1 + j);
+  {
+    float f[8];
+    uint32_t d;
+    dp_leaf(half_area(nodes[leaf]), c_tri, f, &d);
+    float4* dst = reinterpret_cast<float4*>(F + (size_t)leaf * 8);
+    dst[0] = make_float4(f[0], f[1], f[2], f[3]); dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+    dec[leaf] = d;
+  }
+  if (n == 1) return;
+  uint32_t cur = nodes[leaf].parent;
+  __threadfence();
+  while (cur != 0xFFFFFFFFu) {
+    if (atomicAdd(&flags[cur], 1u) == 0) return;
+    __threadfence();
+    const Node2 nd = nodes[cur];
+    float fl[8], fr[8], f[8];
+    const float4* L = reinterpret_cast<const float4*>(F + (size_t)nd.left * 8);
+    const float4* R = reinterpret_cast<const float4*>(F + (size_t)nd.right * 8);
+    const float4 l0 = __ldcg(L), l1 = __ldcg(L + 1), r0 = __ldcg(R), r1 = __ldcg(R + 1);
+    fl[0] = l0.x; fl[1] = l0.y; fl[2] = l0.z; fl[3] = l0.w; fl[4] = l1.x; fl[5] = l1.y; fl[6] = l1.z; fl[7] = l1.w;
+    fr[0] = r0.x; fr[1] = r0.y; fr[2] = r0.z; fr[3] = r0.w; fr[4] = r1.x; fr[5] = r1.y; fr[6] = r1.z; fr[7] = r1.w;
+    uint32_t d;
+    dp_node(half_area(nd), nd.count, fl, fr, c_node, c_tri, f, &d);
+    float4* dst = reinterpret_cast<float4*>(F + (size_t)cur * 8);
+    dst[0] = make_float4(f[0], f[1], f[2], f[3]); dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+    dec[cur] = d;
+    __threadfence();
+    cur = nd.parent;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -459,8 +498,16 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
     root2 = (n == 1) ? 0u : 0u;  // n == 1: the only node is leaf id n-1+0 == 0
   }
 
-  // ---- collapse into BVH8, level by level
-  DevBuf<uint32_t> d_src, d_trisrc;
+  // ---- collapse into BVH8, level by level (children chosen by the SAH-optimal DP unless policy says greedy)
+  DevBuf<uint32_t> d_src, d_trisrc, d_dec;
+  DevBuf<float> d_F;
+  const bool use_dp = tuning().collapse_policy >= 3 && n > 1;
+  if (use_dp) {
+    CK(d_F.alloc((size_t)2 * n * 8)); CK(d_dec.alloc((size_t)2 * n));
+    CK(cudaMemsetAsync(d_flags.p, 0, 4 * (size_t)n, st));
+    collapse_dp<<<(n + 255) / 256, 256, 0, st>>>(d_n2.p, (int)n, d_flags.p, d_F.p, d_dec.p, tuning().c_node * 0.01f, tuning().c_tri * 0.01f);
+    count_launch();
+  }
   s.node_capacity = (size_t)n + 1; s.tri_capacity = n;
   CK(d_src.alloc(s.node_capacity)); CK(d_trisrc.alloc(n));
   Node8* n8 = nullptr;
@@ -471,7 +518,8 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   const float inv_ra = ra > 0.0f ? 1.0f / ra : 0.0f;
   uint32_t begin = 0, end = 1, depth = 0;
   while (begin < end) {
-    collapse_level<<<(end - begin + 127) / 128, 128, 0, st>>>(d_n2.p, d_src.p, begin, end, n8, d_trisrc.p, vin, vout, d_info.p, inv_ra);
+    collapse_level<<<(end - begin + 127) / 128, 128, 0, st>>>(d_n2.p, d_src.p, begin, end, n8, d_trisrc.p, vin, vout, d_info.p, inv_ra, tuning().collapse_policy,
+                                                               use_dp ? d_dec.p : nullptr);
     count_launch();
     uint32_t tail;
     CK(cudaMemcpyAsync(&tail, &d_info.p->node_tail, 4, cudaMemcpyDeviceToHost, st));

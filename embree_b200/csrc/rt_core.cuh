@@ -292,25 +292,101 @@ RT_HD float half_area(const Node2& n) {
   return dx * (dy + dz) + dy * dz;
 }
 
-RT_HD int select_children(const Node2* nodes, uint32_t root, uint32_t* cand /*[8]*/) {
+// policy 0: open the largest-area candidate that has more than one primitive, whatever its size (leaves end up as
+//           single triangles wherever slots are free);
+// policy 1: first open only candidates that MUST be opened (> kMaxLeafTris primitives), largest area first, and keep
+//           candidates of 2..3 primitives closed as multi-triangle leaf slots (fewer, fuller nodes at the bottom);
+// policy 2: as 1, then spend the remaining slots on opening 2..3-primitive candidates by area.
+RT_HD int select_children(const Node2* nodes, uint32_t root, uint32_t* cand /*[8]*/, int policy) {
   int n = 0;
   const Node2& r = nodes[root];
   if (r.right < 0) { cand[0] = root; return 1; }        // the build tree is a single leaf
   cand[n++] = (uint32_t)r.left;
   cand[n++] = (uint32_t)r.right;
-  while (n < 8) {
-    int best = -1;
-    float bestA = -1.0f;
-    for (int i = 0; i < n; ++i) {
-      const Node2& c = nodes[cand[i]];
-      if (c.right < 0) continue;                         // a single primitive cannot be opened
-      const float a = half_area(c);
-      if (a > bestA) { bestA = a; best = i; }
+  for (int phase = (policy == 0 ? 1 : 0); phase < 2; ++phase) {
+    if (phase == 1 && policy == 1) break;
+    while (n < 8) {
+      int best = -1;
+      float bestA = -1.0f;
+      for (int i = 0; i < n; ++i) {
+        const Node2& c = nodes[cand[i]];
+        if (c.right < 0) continue;                         // a single primitive cannot be opened
+        if (phase == 0 && c.count <= (uint32_t)kMaxLeafTris) continue;
+        const float a = half_area(c);
+        if (a > bestA) { bestA = a; best = i; }
+      }
+      if (best < 0) break;
+      const Node2& c = nodes[cand[best]];
+      cand[best] = (uint32_t)c.left;
+      cand[n++] = (uint32_t)c.right;
     }
-    if (best < 0) break;
-    const Node2& c = nodes[cand[best]];
-    cand[best] = (uint32_t)c.left;
-    cand[n++] = (uint32_t)c.right;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SAH-optimal collapse of the binary tree into 8-wide nodes (dynamic programme over the binary tree, after
+// Ylitie et al. 2017, "Efficient incoherent ray traversal on GPUs through compressed wide BVHs", section 4):
+//   F(n,i) = cheapest way to represent the subtree of binary node n as a forest of at most i roots, each root
+//            either a leaf slot (<= kMaxLeafTris triangles, cost A*count*c_tri) or an internal BVH8 node
+//            (cost A*c_node + F-forest of its <= 8 children).
+// dp_node() fills F(n,1..8) and the 22-bit decision word of one binary node from its children's rows:
+//   bit 0      : i == 1 -> 1 = internal BVH8 node, 0 = leaf slot
+//   bits 3i-5.. : i in 2..8 -> 0 = "same as F(n,i-1)", k in 1..7 = give k roots to the left child, i-k to the right.
+// The reference grows N-wide nodes greedily by area (bvh_builder_sah.h:252-279); with single-triangle leaf slots
+// that leaves the bottom nodes a third full, the DP trades child count against leaf fill explicitly.
+// ------------------------------------------------------------------------------------------------
+RT_HD void dp_leaf(float area, float c_tri, float* F, uint32_t* dec) {
+  for (int i = 0; i < 8; ++i) F[i] = area * c_tri;
+  *dec = 0;
+}
+RT_HD void dp_node(float area, uint32_t count, const float* Fl, const float* Fr, float c_node, float c_tri, float* F,
+                   uint32_t* dec) {
+  float D[9];      // D[j]: best split of exactly-at-most j roots between the two children, j = 2..8
+  uint32_t K[9];
+  for (int j = 2; j <= 8; ++j) {
+    float best = INFINITY;
+    uint32_t bk = 1;
+    for (int k = 1; k < j; ++k) {
+      const float c = Fl[k - 1] + Fr[j - k - 1];
+      if (c < best) { best = c; bk = (uint32_t)k; }
+    }
+    D[j] = best; K[j] = bk;
+  }
+  const float leaf = count <= (uint32_t)kMaxLeafTris ? area * (float)count * c_tri : INFINITY;
+  const float inner = area * c_node + D[8];
+  uint32_t d = 0;
+  if (inner < leaf) { F[0] = inner; d |= 1u; } else F[0] = leaf;
+  for (int i = 2; i <= 8; ++i) {
+    if (D[i] < F[i - 2]) { F[i - 1] = D[i]; d |= K[i] << (3 * i - 5); }
+    else F[i - 1] = F[i - 2];
+  }
+  // the children of n when n itself becomes an internal node: D[8] split, kept in bits 22..24
+  d |= K[8] << 22;
+  *dec = d;
+}
+
+// children of the BVH8 node rooted at binary node `root` according to the decision words
+RT_HD int select_children_dp(const Node2* nodes, const uint32_t* dec, uint32_t root, uint32_t* cand /*[8]*/) {
+  const Node2& r = nodes[root];
+  if (r.right < 0) { cand[0] = root; return 1; }
+  uint32_t st_n[8], st_i[8];
+  int sp = 0, n = 0;
+  const uint32_t k8 = (dec[root] >> 22) & 7u;
+  st_n[sp] = (uint32_t)r.right; st_i[sp] = 8u - k8; ++sp;
+  st_n[sp] = (uint32_t)r.left; st_i[sp] = k8; ++sp;
+  while (sp > 0) {
+    --sp;
+    uint32_t c = st_n[sp], i = st_i[sp];
+    for (;;) {
+      const Node2& cn = nodes[c];
+      if (cn.right < 0) { cand[n++] = c; break; }           // single primitive
+      if (i == 1) { cand[n++] = c; break; }                   // one root: leaf slot or internal child (by count)
+      const uint32_t k = (dec[c] >> (3 * i - 5)) & 7u;
+      if (k == 0) { --i; continue; }                          // F(c,i) == F(c,i-1)
+      st_n[sp] = (uint32_t)cn.right; st_i[sp] = i - k; ++sp;
+      c = (uint32_t)cn.left; i = k;
+    }
   }
   return n;
 }
@@ -349,10 +425,10 @@ RT_HD void assign_slots(const ChildBox* cb, int n, const float plo[3], const flo
 // (atomic bump counters on the device), and queue the internal children (src[child id] = binary node).
 template <typename Alloc>
 RT_HD void collapse_node(const Node2* n2, uint32_t* src, uint32_t q, Node8* n8, uint32_t* tri_src, const uint32_t* sortedA,
-                         const uint32_t* sortedB, float inv_root_area, const Alloc& alloc) {
+                         const uint32_t* sortedB, float inv_root_area, int policy, const uint32_t* dec, const Alloc& alloc) {
   const uint32_t root = src[q];
   uint32_t cand[8];
-  const int n = select_children(n2, root, cand);
+  const int n = dec ? select_children_dp(n2, dec, root, cand) : select_children(n2, root, cand, policy);
   const Node2 self = n2[root];
   const float plo[3] = {self.lox, self.loy, self.loz}, phi[3] = {self.hix, self.hiy, self.hiz};
   ChildBox cb[8];

@@ -785,6 +785,19 @@ void rtcb200GetSceneStats(RTCScene sc, struct RTCB200SceneStats* o) {
 void rtcb200SetSceneStatCounters(RTCScene sc, int enable) { SCENE_BEGIN(sc) S(sc)->statCounters = enable != 0; SCENE_END }
 void rtcb200ResetSceneStatCounters(RTCScene sc) { SCENE_BEGIN(sc) if (S(sc)->gpu.d_stat) { S(sc)->dev->use(); cuda_check(cudaMemset(S(sc)->gpu.d_stat, 0, 24), "reset stat counters"); } SCENE_END }
 unsigned long long rtcb200GetLaunchCount(void) { return rtk::launch_count(); }
+int rtcb200SetTuning(const char* key, int value) {
+  if (!key) return -1;
+  rtk::Tuning& t = rtk::tuning();
+  if (!strcmp(key, "collapse_policy")) t.collapse_policy = value;
+  else if (!strcmp(key, "c_node")) t.c_node = value;
+  else if (!strcmp(key, "c_tri")) t.c_tri = value;
+  else if (!strcmp(key, "tri_batch_min")) t.tri_batch_min = value;
+  else if (!strcmp(key, "tri_wait_max")) t.tri_wait_max = value;
+  else if (!strcmp(key, "blocks_per_sm")) t.blocks_per_sm = value;
+  else if (!strcmp(key, "use_tma")) t.use_tma = value;
+  else return -1;
+  return 0;
+}
 double rtcb200GetLastTraceMs(RTCScene sc) {
   SCENE_BEGIN(sc)
   SceneImpl* s = S(sc);

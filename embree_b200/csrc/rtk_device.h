@@ -47,9 +47,21 @@ struct TraceParams {
   unsigned long long n;  // number of rays = records * K
   uint32_t instID, instPrimID;
   unsigned long long* stat;  // non-NULL -> counting kernel
+  int tri_batch_min = 6, tri_wait_max = 3;  // filled by launch_trace from tuning()
 };
 // occluded: 0 = closest hit (rtcIntersect*), 1 = any hit (rtcOccluded*); K in {1,4,8,16}
 int launch_trace(const TraceParams& p, int occluded, int K, cudaStream_t stream);
+
+// run-time tuning knobs (defaults = shipped configuration; overridable through rtcb200SetTuning / RTCB200_* env)
+struct Tuning {
+  int collapse_policy = 3;   // 0/1/2 greedy variants (rt_core.cuh select_children), 3 = SAH-optimal dynamic programme
+  int c_node = 100, c_tri = 50;  // DP cost of a BVH8 node visit / a triangle test, in 1/100
+  int tri_batch_min = 6;
+  int tri_wait_max = 3;
+  int blocks_per_sm = 8;
+  int use_tma = 1;
+};
+Tuning& tuning();
 
 unsigned long long launch_count();
 void count_launch(unsigned n = 1);

@@ -35,13 +35,14 @@ struct RayIO;
 template <bool OCCLUDED>
 struct RayIO<1, OCCLUDED> {
   static constexpr int kStride = OCCLUDED ? 48 : 96;
-  static __device__ __forceinline__ bool load(const TraceParams& p, unsigned long long i, Ray& r) {
-    const float4* src = reinterpret_cast<const float4*>(static_cast<const char*>(p.rays) + i * kStride);
+  static constexpr int kRayBytes = kStride;   // bytes per ray of a contiguous 32-ray block
+  // `base` is either p.rays (i = global ray index) or a shared-memory copy of one 32-ray block (i = index in block)
+  static __device__ __forceinline__ void load(const char* base, unsigned long long i, Ray& r) {
+    const float4* src = reinterpret_cast<const float4*>(base + i * kStride);
     const float4 a = src[0], b = src[1], c = src[2];
     r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tnear = a.w;
     r.dx = b.x; r.dy = b.y; r.dz = b.z; r.time = b.w;
     r.tfar = c.x; r.mask = __float_as_uint(c.y); r.id = __float_as_uint(c.z); r.flags = __float_as_uint(c.w);
-    return true;
   }
   static __device__ __forceinline__ void store_tfar(const TraceParams& p, unsigned long long i, float tfar) {
     *reinterpret_cast<float*>(static_cast<char*>(p.rays) + i * kStride + 32) = tfar;
@@ -61,18 +62,20 @@ struct RayIO<1, OCCLUDED> {
 template <int K, bool OCCLUDED>
 struct RayIO {
   static constexpr int kPacket = (OCCLUDED ? 12 : 21) * 4 * K;
+  static constexpr int kRayBytes = (OCCLUDED ? 12 : 21) * 4;   // 32 consecutive rays = 32/K consecutive packets
   static __device__ __forceinline__ char* field(const TraceParams& p, unsigned long long i, int f) {
     return static_cast<char*>(p.rays) + (i / K) * kPacket + ((size_t)f * K + (i % K)) * 4;
   }
-  static __device__ __forceinline__ bool load(const TraceParams& p, unsigned long long i, Ray& r) {
-    if (p.valid && p.valid[i] != -1) return false;  // inactive lane: record must come back untouched
-    r.ox = *reinterpret_cast<float*>(field(p, i, 0)); r.oy = *reinterpret_cast<float*>(field(p, i, 1));
-    r.oz = *reinterpret_cast<float*>(field(p, i, 2)); r.tnear = *reinterpret_cast<float*>(field(p, i, 3));
-    r.dx = *reinterpret_cast<float*>(field(p, i, 4)); r.dy = *reinterpret_cast<float*>(field(p, i, 5));
-    r.dz = *reinterpret_cast<float*>(field(p, i, 6)); r.time = *reinterpret_cast<float*>(field(p, i, 7));
-    r.tfar = *reinterpret_cast<float*>(field(p, i, 8)); r.mask = *reinterpret_cast<uint32_t*>(field(p, i, 9));
+  static __device__ __forceinline__ const char* cfield(const char* base, unsigned long long i, int f) {
+    return base + (i / K) * kPacket + ((size_t)f * K + (i % K)) * 4;
+  }
+  static __device__ __forceinline__ void load(const char* base, unsigned long long i, Ray& r) {
+    r.ox = *reinterpret_cast<const float*>(cfield(base, i, 0)); r.oy = *reinterpret_cast<const float*>(cfield(base, i, 1));
+    r.oz = *reinterpret_cast<const float*>(cfield(base, i, 2)); r.tnear = *reinterpret_cast<const float*>(cfield(base, i, 3));
+    r.dx = *reinterpret_cast<const float*>(cfield(base, i, 4)); r.dy = *reinterpret_cast<const float*>(cfield(base, i, 5));
+    r.dz = *reinterpret_cast<const float*>(cfield(base, i, 6)); r.time = *reinterpret_cast<const float*>(cfield(base, i, 7));
+    r.tfar = *reinterpret_cast<const float*>(cfield(base, i, 8)); r.mask = *reinterpret_cast<const uint32_t*>(cfield(base, i, 9));
     r.id = 0; r.flags = 0;
-    return true;
   }
   static __device__ __forceinline__ void store_tfar(const TraceParams& p, unsigned long long i, float tfar) {
     *reinterpret_cast<float*>(field(p, i, 8)) = tfar;
@@ -89,70 +92,106 @@ struct RayIO {
 
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_WARPS = TRACE_THREADS / 32;
-constexpr int kTriWaitMax = 3;    // ... but never make a lane wait longer than this many iterations
-constexpr int kTriBatchMin = 6;   // run a triangle step only when this many lanes wait for one (or no lane has node work)
 
-// Persistent warps.  Every warp owns the 32-ray blocks w, w+W, w+2W, ... of the stream (W = warps in the grid) and
-// keeps its 32 lanes busy: a lane whose ray has terminated writes its result and immediately takes the warp's next
-// unassigned ray (ballot + popc ranking, no atomics).  One loop iteration = at most one node step (pop a child of the
-// current node group, fetch the 80-byte node, slab-test its 8 children) for the lanes that want it, and at most one
-// triangle step for the lanes that have triangle hits pending; the two phases are warp-synchronous so lanes in the
-// same phase execute together instead of serialising through a per-thread while-while loop.
-template <int K, bool OCCLUDED, bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS) trace_kernel(const TraceParams p) {
+// ---- TMA bulk prefetch of one 32-ray block (1.5 .. 3 KB contiguous) into L2 ------------------------------------------
+// Staging the blocks in shared memory (cp.async.bulk.shared + mbarrier) was measured SLOWER (1012 vs 1380 Mrays/s):
+// 24 KB of shared memory per CTA x 8 CTAs/SM leaves only ~30 KB of L1, and the BVH lives on L1 hits.  The bulk
+// prefetch keeps the TMA unit pulling the ray stream ahead of the warps without costing L1 capacity.
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// Persistent warps.  Every warp owns the 32-ray blocks w, w+W, w+2W, ... of the stream (W = warps in the grid).  When
+// a warp starts consuming a block, lane 0 issues a TMA bulk prefetch (cp.async.bulk.prefetch.L2) of the block two ahead,
+// so the ray records are L2-resident by the time lanes load them.  A lane whose ray has terminated writes its result
+// and takes the next unassigned ray of the current block (ballot + popc ranking, no atomics).  One loop iteration = at most one node step (pop a child of the current node group, fetch the 80-byte
+// node, slab-test its 8 children) for the lanes that want it, and at most one triangle step, batched across the warp;
+// the phases are warp-synchronous so lanes in the same phase execute together instead of serialising through a
+// per-thread while-while loop.  The top stack entry lives in registers; deeper entries in (L1-resident) local memory.
+template <int K, bool OCCLUDED, bool STATS, bool USE_TMA>
+__global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TraceParams p) {
+  using IO = RayIO<K, OCCLUDED>;
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned long long warp_id = (unsigned long long)blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5);
-  const unsigned long long num_warps = (unsigned long long)gridDim.x * TRACE_WARPS;
+  const uint32_t warp_id = blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5);
+  const uint32_t num_warps = gridDim.x * TRACE_WARPS;
+  const uint32_t n = (uint32_t)p.n;
   const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(p.nodes);
   const uint4* __restrict__ tris = reinterpret_cast<const uint4*>(p.tris);
+  const int tri_batch_min = p.tri_batch_min, tri_wait_max = p.tri_wait_max;
 
   // per-lane ray state
   Ray r;
-  float idx = 0, idy = 0, idz = 0, tnear_c = 0, tfar_c = 0, tfar_tri = 0;
-  uint32_t oct = 0, oct_inv4 = 0;
-  bool negx = false, negy = false, negz = false;
-  Hit hit;
-  hit.t = 0; hit.u = 0; hit.v = 0; hit.ngx = 0; hit.ngy = 0; hit.ngz = 0; hit.primID = 0; hit.geomID = 0;
+  float idx = 0, idy = 0, idz = 0, tfar_tri = 0;
+  uint32_t oct = 0;
+  float hit_u = 0, hit_v = 0;            // closest hit so far: t = tfar_tri, barycentrics, triangle record index
+  uint32_t hit_tri = 0;
   bool found = false, active = false;
-  unsigned long long ray_index = 0;
+  uint32_t ray_index = 0;
   uint32_t ngx = 0, ngy = 0, tgx = 0, tgy = 0;
+  uint32_t top_x = 0, top_y = 0;          // top of the traversal stack (top_y == 0: stack empty)
   uint32_t stack_x[kStackSize], stack_y[kStackSize];
   int sp = 0;
-  unsigned long long j_next = 0;        // warp-uniform: next unassigned ray of this warp's private sequence
+  // warp-uniform block cursor
+  int blk = -1;                           // index into this warp's block sequence
+  uint32_t blk_first = 0, blk_count = 0, consumed = 0;
+  bool warp_done = false;
+  int tri_wait = 0;
   unsigned long long st_rays = 0, st_nodes = 0, st_tris = 0;
-  bool exhausted = false;                // this lane was handed an index beyond the stream
-  int tri_wait = 0;                      // warp-uniform: iterations some lane has been waiting for a triangle step
+
+  auto block_first = [&](int b) -> unsigned long long { return ((unsigned long long)b * num_warps + warp_id) * 32ull; };
+  auto prefetch = [&](int b) {   // lane 0 only
+    const unsigned long long first = block_first(b);
+    if (first >= n) return;
+    const uint32_t cnt = (n - first) < 32u ? (uint32_t)(n - first) : 32u;
+    tma_prefetch_l2(static_cast<const char*>(p.rays) + first * IO::kRayBytes, cnt * IO::kRayBytes);
+  };
+  if (USE_TMA && lane == 0) { prefetch(0); prefetch(1); }
 
   for (;;) {
-    // ---- 1. refill idle lanes
+    // ---- 1. refill idle lanes from the resident ray block
     const unsigned idle = __ballot_sync(FULL, !active);
     if (idle) {
-      if (!active && !exhausted) {
-        const unsigned long long j = j_next + __popc(idle & lt_mask);
-        ray_index = ((j >> 5) * num_warps + warp_id) * 32ull + (j & 31ull);
-        if (ray_index >= p.n) exhausted = true;
-        else if (RayIO<K, OCCLUDED>::load(p, ray_index, r)) {
-          if (STATS) ++st_rays;
-          found = false;
-          sp = 0; tgx = 0; tgy = 0;
-          // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129)
-          const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
-          idx = rcp_safe(r.dx); idy = rcp_safe(r.dy); idz = rcp_safe(r.dz);
-          negx = idx < 0.0f; negy = idy < 0.0f; negz = idz < 0.0f;
-          oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
-          oct_inv4 = (7u - oct) * 0x01010101u;
-          tnear_c = fmaxf(r.tnear, 0.0f);
-          tfar_c = fmaxf(r.tfar, 0.0f);
-          tfar_tri = r.tfar;
-          ngx = 0; ngy = go ? 0x80000000u : 0u;   // root entered as "one pending internal child, imask 0"
-          active = go;
+      if (!warp_done) {
+        if (consumed == blk_count) {       // resident block used up (or nothing loaded yet): move to the next one
+          if (USE_TMA && lane == 0) prefetch(blk + 3);   // keep the stream two blocks ahead in L2
+          ++blk;
+          const unsigned long long first = block_first(blk);
+          if (first >= n) { warp_done = true; blk_count = 0; consumed = 0; }
+          else {
+            blk_first = (uint32_t)first;
+            blk_count = (n - blk_first) < 32u ? (n - blk_first) : 32u;
+            consumed = 0;
+          }
+        }
+        if (!warp_done) {
+          const uint32_t avail = blk_count - consumed;
+          const uint32_t rank = __popc(idle & lt_mask);
+          if (!active && rank < avail) {
+            ray_index = blk_first + consumed + rank;
+            bool valid = true;
+            if (K > 1) valid = (p.valid == nullptr) || (p.valid[ray_index] == -1);   // inactive lanes stay untouched
+            if (valid) {
+              IO::load(static_cast<const char*>(p.rays), ray_index, r);
+              if (STATS) ++st_rays;
+              found = false;
+              sp = 0; top_y = 0; tgx = 0; tgy = 0;
+              // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129)
+              const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
+              idx = rcp_safe(r.dx); idy = rcp_safe(r.dy); idz = rcp_safe(r.dz);
+              oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
+              tfar_tri = r.tfar;
+              ngx = 0; ngy = go ? 0x80000000u : 0u;   // root entered as "one pending internal child, imask 0"
+              active = go;
+            }
+          }
+          const uint32_t want = __popc(idle);
+          consumed += want < avail ? want : avail;
         }
       }
-      j_next += __popc(idle);
       if (!__any_sync(FULL, active)) {
-        if (__all_sync(FULL, exhausted)) break;
+        if (warp_done) break;
         continue;
       }
     }
@@ -161,7 +200,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_kernel(const TraceParams 
     if (want_node) {
       const int bit = 31 - __clz((int)ngy);
       ngy &= ~(1u << bit);
-      if (ngy & 0xFF000000u) { stack_x[sp] = ngx; stack_y[sp] = ngy; ++sp; }
+      if (ngy & 0xFF000000u) {           // push the rest of the group
+        if (top_y) { stack_x[sp] = top_x; stack_y[sp] = top_y; ++sp; }
+        top_x = ngx; top_y = ngy;
+      }
       const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
       const uint32_t node_index = ngx + (uint32_t)__popc(ngy & 0xFFu & ((1u << slot) - 1u));
       const uint4* np = nodes + (size_t)node_index * 5;
@@ -169,8 +211,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_kernel(const TraceParams 
       if (STATS) ++st_nodes;
       const u32x4 n0{a0.x, a0.y, a0.z, a0.w}, n1{a1.x, a1.y, a1.z, a1.w}, n2{a2.x, a2.y, a2.z, a2.w},
           n3{a3.x, a3.y, a3.z, a3.w}, n4{a4.x, a4.y, a4.z, a4.w};
-      const uint32_t hm = node_hitmask<OCCLUDED>(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz,
-                                                 tnear_c, tfar_c, oct_inv4);
+      // TravRay clamps tnear/tfar at 0 for the slab test only (bvh_intersector1.cpp:65); after a hit tray.tfar = ray.tfar (:105)
+      const uint32_t hm = node_hitmask<OCCLUDED>(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, (oct & 1u) != 0,
+                                                 (oct & 2u) != 0, (oct & 4u) != 0, fmaxf(r.tnear, 0.0f), fmaxf(tfar_tri, 0.0f),
+                                                 (7u - oct) * 0x01010101u);
       ngx = n1.x;
       ngy = (hm & 0xFF000000u) | (n0.w >> 24);
       tgx = n1.y;
@@ -179,12 +223,13 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_kernel(const TraceParams 
     // ---- 3. triangle step, batched across the warp
     const unsigned tri_lanes = __ballot_sync(FULL, active && tgy != 0);
     const unsigned node_lanes = __ballot_sync(FULL, active && tgy == 0 && (ngy & 0xFF000000u));
-    if (tri_lanes && (__popc(tri_lanes) >= kTriBatchMin || node_lanes == 0 || ++tri_wait >= kTriWaitMax)) {
+    if (tri_lanes && (__popc(tri_lanes) >= tri_batch_min || node_lanes == 0 || ++tri_wait >= tri_wait_max)) {
       tri_wait = 0;
       if (active && tgy != 0) {
         const int tb = 31 - __clz((int)tgy);
         tgy &= ~(1u << tb);
-        const uint4* tp = tris + (size_t)(tgx + (uint32_t)tb) * 3;
+        const uint32_t ti = tgx + (uint32_t)tb;
+        const uint4* tp = tris + (size_t)ti * 3;
         const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         if (STATS) ++st_tris;
         TriHit th;
@@ -193,29 +238,40 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_kernel(const TraceParams 
                      __uint_as_float(c.z), th) &&
             (c.w & r.mask) != 0) {
           found = true;
-          if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; }     // any hit terminates the ray
+          if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }     // any hit terminates the ray
           else {
-            const float rcpAbsDen = 1.0f / th.absDen;
-            hit.t = th.T * rcpAbsDen; hit.u = th.U * rcpAbsDen; hit.v = th.V * rcpAbsDen;
-            hit.ngx = th.ngx; hit.ngy = th.ngy; hit.ngz = th.ngz;
-            hit.primID = a.w; hit.geomID = b.w;
-            tfar_tri = hit.t;
-            tfar_c = fmaxf(hit.t, 0.0f);
+            const float rcpAbsDen = 1.0f / th.absDen;      // finalize(): t,u,v = T,U,V * rcp(absDen)
+            tfar_tri = th.T * rcpAbsDen; hit_u = th.U * rcpAbsDen; hit_v = th.V * rcpAbsDen;
+            hit_tri = ti;
           }
         }
       }
     }
     // ---- 4. pop or finish
     if (active && tgy == 0 && (ngy & 0xFF000000u) == 0) {
-      if (sp > 0) {
-        --sp;
-        const uint32_t px = stack_x[sp], py = stack_y[sp];
+      if (top_y) {
+        const uint32_t px = top_x, py = top_y;
+        if (sp > 0) { --sp; top_x = stack_x[sp]; top_y = stack_y[sp]; }   // next entry loads while this one is used
+        else top_y = 0;
         if (py & 0xFF000000u) { ngx = px; ngy = py; }
         else { tgx = px; tgy = py; ngx = 0; ngy = 0; }
       } else {
         if (found) {
-          if (OCCLUDED) RayIO<K, OCCLUDED>::store_tfar(p, ray_index, -INFINITY);   // bvh_intersector1.cpp:186-188
-          else RayIO<K, OCCLUDED>::store_hit(p, ray_index, hit);
+          if (OCCLUDED) IO::store_tfar(p, ray_index, -INFINITY);   // bvh_intersector1.cpp:186-188
+          else {
+            // Ng = cross(e2, e1) and the ids come from the winning triangle's record (same arithmetic as tri_test)
+            const uint4* tp = tris + (size_t)hit_tri * 3;
+            const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            const float e1x = __uint_as_float(b.x), e1y = __uint_as_float(b.y), e1z = __uint_as_float(b.z);
+            const float e2x = __uint_as_float(c.x), e2y = __uint_as_float(c.y), e2z = __uint_as_float(c.z);
+            Hit hit;
+            hit.t = tfar_tri; hit.u = hit_u; hit.v = hit_v;
+            hit.ngx = msub(e2y, e1z, mul_rn(e2z, e1y));
+            hit.ngy = msub(e2z, e1x, mul_rn(e2x, e1z));
+            hit.ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
+            hit.primID = a.w; hit.geomID = b.w;
+            IO::store_hit(p, ray_index, hit);
+          }
         }
         active = false;
       }
@@ -233,22 +289,34 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_kernel(const TraceParams 
 }
 
 static int g_num_sms = 0;
+static Tuning g_tuning;
+Tuning& tuning() { return g_tuning; }
 
 template <int K, bool OCCLUDED>
-static int launch_k(const TraceParams& p, cudaStream_t st) {
+static int launch_k(TraceParams p, cudaStream_t st) {
   if (p.n == 0) return 0;
+  if (p.n > 0x7FFFFFFFull) return (int)cudaErrorInvalidValue;   // callers split longer streams
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
+  p.tri_batch_min = g_tuning.tri_batch_min;
+  p.tri_wait_max = g_tuning.tri_wait_max;
   // persistent grid: a multiple of the SM count, capped by the work available
   const unsigned long long need = (p.n + TRACE_THREADS - 1) / TRACE_THREADS;
-  const unsigned long long cap = (unsigned long long)g_num_sms * 6;
+  const unsigned long long cap = (unsigned long long)g_num_sms * g_tuning.blocks_per_sm;
   const unsigned blocks = (unsigned)(need < cap ? need : cap);
-  if (p.stat) trace_kernel<K, OCCLUDED, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
-  else trace_kernel<K, OCCLUDED, false><<<blocks, TRACE_THREADS, 0, st>>>(p);
+  // tiny launches (single-record API calls read a mapped pinned host record) skip the bulk prefetch
+  const bool tma = p.n >= 1024 && g_tuning.use_tma;
+  if (p.stat) {
+    if (tma) trace_kernel<K, OCCLUDED, true, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
+    else trace_kernel<K, OCCLUDED, true, false><<<blocks, TRACE_THREADS, 0, st>>>(p);
+  } else {
+    if (tma) trace_kernel<K, OCCLUDED, false, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
+    else trace_kernel<K, OCCLUDED, false, false><<<blocks, TRACE_THREADS, 0, st>>>(p);
+  }
   count_launch();
   return (int)cudaGetLastError();
 }

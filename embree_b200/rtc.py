@@ -204,6 +204,7 @@ class RTCLib:
         "rtcb200SetSceneStatCounters": (None, [C.c_void_p, C.c_int]),
         "rtcb200ResetSceneStatCounters": (None, [C.c_void_p]),
         "rtcb200GetLaunchCount": (C.c_ulonglong, []),
+        "rtcb200SetTuning": (C.c_int, [C.c_char_p, C.c_int]),
         "rtcb200GetLastTraceMs": (C.c_double, [C.c_void_p]),
     }
 

@@ -309,6 +309,9 @@ RTCB200_API void rtcb200SetSceneStatCounters(RTCScene scene, int enable); /* rou
 RTCB200_API void rtcb200ResetSceneStatCounters(RTCScene scene);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 RTCB200_API unsigned long long rtcb200GetLaunchCount(void);
+/* experiment knobs of the kernels ("collapse_policy", "tri_batch_min", "tri_wait_max", "blocks_per_sm", "use_tma");
+ * the defaults are the shipped configuration.  Returns 0, or -1 for an unknown key. */
+RTCB200_API int rtcb200SetTuning(const char* key, int value);
 /* device time (ms) of the most recent batched Device trace launch, measured with events on its stream; -1 if none */
 RTCB200_API double rtcb200GetLastTraceMs(RTCScene scene);
 

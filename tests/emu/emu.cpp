@@ -47,7 +47,7 @@ uint64_t expand21(uint32_t v) {
 
 extern "C" {
 
-// vertices: float[nverts][3] (stride 12), indices: uint32[ntris][3]; mode 0 = LBVH order, 1 = median-split tree
+// vertices: float[nverts][3] (stride 12), indices: uint32[ntris][3]; mode = collapse policy (0, 1, 2 greedy variants; 3 = SAH-optimal DP)
 void* emu_build(const float* verts, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint32_t geomID, uint32_t mask, int mode) {
   EmuScene* sc = new EmuScene();
   std::vector<PrimRef> prims;
@@ -96,7 +96,6 @@ void* emu_build(const float* verts, uint32_t nverts, const uint32_t* idx, uint32
 
   std::vector<Node2> n2(2 * (size_t)n);
   memset(n2.data(), 0, n2.size() * sizeof(Node2));
-  (void)mode;
   for (int i = 0; i + 1 < (int)n; ++i) lbvh_node(skeys.data(), (int)n, i, n2.data());
   for (uint32_t j = 0; j < n; ++j) {
     Node2& lf = n2[n - 1 + j];
@@ -123,6 +122,23 @@ void* emu_build(const float* verts, uint32_t nverts, const uint32_t* idx, uint32
       nd.hix = fmaxf(l.hix, r.hix); nd.hiy = fmaxf(l.hiy, r.hiy); nd.hiz = fmaxf(l.hiz, r.hiz);
     }
   }
+  // SAH-optimal collapse decisions (mode 3): children before parents
+  std::vector<float> F((size_t)2 * n * 8);
+  std::vector<uint32_t> dec((size_t)2 * n, 0u);
+  if (mode >= 3 && n > 1) {
+    for (uint32_t j = 0; j < n; ++j) dp_leaf(half_area(n2[n - 1 + j]), 0.3f, &F[(size_t)(n - 1 + j) * 8], &dec[n - 1 + j]);
+    std::vector<int> stack{0}, post;
+    while (!stack.empty()) {
+      int i = stack.back(); stack.pop_back();
+      post.push_back(i);
+      if (n2[i].left < (int)n - 1) stack.push_back(n2[i].left);
+      if (n2[i].right < (int)n - 1) stack.push_back(n2[i].right);
+    }
+    for (auto it = post.rbegin(); it != post.rend(); ++it) {
+      const Node2& nd = n2[*it];
+      dp_node(half_area(nd), nd.count, &F[(size_t)nd.left * 8], &F[(size_t)nd.right * 8], 1.0f, 0.3f, &F[(size_t)*it * 8], &dec[*it]);
+    }
+  }
   // collapse
   std::vector<uint32_t> src(n + 1), tri_src(n);
   sc->nodes.resize(n + 1);
@@ -137,7 +153,8 @@ void* emu_build(const float* verts, uint32_t nverts, const uint32_t* idx, uint32
   for (uint32_t j = 0; j < n; ++j) sorted_prim[j] = prims[sorted[j]].prim;
   while (begin < end) {
     for (uint32_t q = begin; q < end; ++q)
-      collapse_node(n2.data(), src.data(), q, sc->nodes.data(), tri_src.data(), sorted_prim.data(), sorted_prim.data(), inv_ra, alloc);
+      collapse_node(n2.data(), src.data(), q, sc->nodes.data(), tri_src.data(), sorted_prim.data(), sorted_prim.data(), inv_ra, mode,
+                    (mode >= 3 && n > 1) ? dec.data() : nullptr, alloc);
     begin = end; end = node_tail; ++depth;
   }
   sc->nodes.resize(node_tail);
@@ -191,3 +208,68 @@ void emu_trace(void* h, void* rays, uint64_t n, int occluded, uint64_t* stats) {
 }
 
 }  // extern "C"
+
+// ---- experiment (test tool): the same BVH8 traversed with exact front-to-back child ordering (per-child stack
+// entries sorted by entry distance, far entries culled against the current hit) to measure how many node visits the
+// octant-order approximation of the production traversal costs.
+extern "C" void emu_trace_sorted(void* h, void* rays, uint64_t n, uint64_t* stats) {
+  EmuScene* sc = static_cast<EmuScene*>(h);
+  const Node8* nodes = sc->nodes.data();
+  const TriRec* tris = sc->tris.data();
+  for (uint64_t ri = 0; ri < n; ++ri) {
+    char* rec = static_cast<char*>(rays) + ri * 96;
+    Ray r; memcpy(&r, rec, 48);
+    if (!sc->root_valid) continue;
+    const float idx = rcp_safe(r.dx), idy = rcp_safe(r.dy), idz = rcp_safe(r.dz);
+    float tfar = r.tfar; bool found = false; Hit hit{};
+    struct E { uint32_t node; float t; };
+    std::vector<E> st; st.push_back({0u, 0.0f});
+    while (!st.empty()) {
+      E e = st.back(); st.pop_back();
+      if (e.t > tfar) continue;
+      const Node8& nd = nodes[e.node];
+      stats[0]++;
+      const uint32_t ex = nd.w[3];
+      const float sx = u2f((ex & 0xFF) << 23) * idx, sy = u2f(((ex >> 8) & 0xFF) << 23) * idy, sz = u2f(((ex >> 16) & 0xFF) << 23) * idz;
+      const float bx = (u2f(nd.w[0]) - r.ox) * idx, by = (u2f(nd.w[1]) - r.oy) * idy, bz = (u2f(nd.w[2]) - r.oz) * idz;
+      const uint8_t* q = reinterpret_cast<const uint8_t*>(&nd.w[8]);   // qlox[8] qloy[8] qloz[8] qhix[8] qhiy[8] qhiz[8]
+      const uint8_t* meta = reinterpret_cast<const uint8_t*>(&nd.w[6]);
+      const uint32_t imask = ex >> 24;
+      E kids[8]; int nk = 0;
+      for (int s = 0; s < 8; ++s) {
+        if (meta[s] == 0) continue;
+        const float lx = q[s], ly = q[8 + s], lz = q[16 + s], hx = q[24 + s], hy = q[32 + s], hz = q[40 + s];
+        const float tnx = (idx < 0 ? hx : lx) * sx + bx, tfx = (idx < 0 ? lx : hx) * sx + bx;
+        const float tny = (idy < 0 ? hy : ly) * sy + by, tfy = (idy < 0 ? ly : hy) * sy + by;
+        const float tnz = (idz < 0 ? hz : lz) * sz + bz, tfz = (idz < 0 ? lz : hz) * sz + bz;
+        const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, fmaxf(r.tnear, 0.0f)));
+        const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, fmaxf(tfar, 0.0f))) * 1.0000003f;
+        if (!(tmin <= tmax)) continue;
+        if (imask & (1u << s)) {
+          const uint32_t child = nd.w[4] + (uint32_t)popc32(imask & ((1u << s) - 1u));
+          kids[nk++] = {child, tmin};
+        } else {
+          const uint32_t cnt = popc32(meta[s] >> 5), off = meta[s] & 31u;
+          for (uint32_t k = 0; k < cnt; ++k) {
+            const TriRec& t = tris[nd.w[5] + off + k];
+            stats[1]++;
+            TriHit th;
+            if (tri_test(r, tfar, t.v0x, t.v0y, t.v0z, t.e1x, t.e1y, t.e1z, t.e2x, t.e2y, t.e2z, th) && (t.mask & r.mask)) {
+              const float rcp = 1.0f / th.absDen;
+              hit.t = th.T * rcp; hit.u = th.U * rcp; hit.v = th.V * rcp; hit.ngx = th.ngx; hit.ngy = th.ngy; hit.ngz = th.ngz;
+              hit.primID = t.primID; hit.geomID = t.geomID; tfar = hit.t; found = true;
+            }
+          }
+        }
+      }
+      std::sort(kids, kids + nk, [](const E& a, const E& b) { return a.t > b.t; });  // far first -> near popped first
+      for (int k = 0; k < nk; ++k) st.push_back(kids[k]);
+    }
+    if (!found) continue;
+    memcpy(rec + 32, &hit.t, 4);
+    float h4[5] = {hit.ngx, hit.ngy, hit.ngz, hit.u, hit.v};
+    memcpy(rec + 48, h4, 20);
+    uint32_t ids[4] = {hit.primID, hit.geomID, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    memcpy(rec + 68, ids, 16);
+  }
+}
