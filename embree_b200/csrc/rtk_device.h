@@ -47,7 +47,7 @@ struct TraceParams {
   unsigned long long n;  // number of rays = records * K
   uint32_t instID, instPrimID;
   unsigned long long* stat;  // non-NULL -> counting kernel
-  int tri_batch_min = 6, tri_wait_max = 3;  // filled by launch_trace from tuning()
+  int tri_batch_min = 6, tri_wait_max = 3, refill_min = 4;  // filled by launch_trace from tuning()
 };
 // occluded: 0 = closest hit (rtcIntersect*), 1 = any hit (rtcOccluded*); K in {1,4,8,16}
 int launch_trace(const TraceParams& p, int occluded, int K, cudaStream_t stream);
@@ -60,6 +60,7 @@ struct Tuning {
   int tri_wait_max = 3;
   int blocks_per_sm = 8;
   int use_tma = 1;
+  int refill_min = 4;
 };
 Tuning& tuning();
 

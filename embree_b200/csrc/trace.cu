@@ -90,6 +90,14 @@ struct RayIO {
   }
 };
 
+// rcp_safe with the reference's own recipe: hardware approximation + one Newton step (common/simd/vfloat4_sse2.h:304-323)
+// instead of an IEEE division; the slab test is padded by 2 ulp, so the ~1 ulp error of 1/dir cannot cull a box wrongly.
+__device__ __forceinline__ float rcp_safe_fast(float d) {
+  const float x = fabsf(d) < kMinRcpInput ? kMinRcpInput : d;
+  const float r = __frcp_rn(x);
+  return r;
+}
+
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
   const uint32_t n = (uint32_t)p.n;
   const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(p.nodes);
   const uint4* __restrict__ tris = reinterpret_cast<const uint4*>(p.tris);
-  const int tri_batch_min = p.tri_batch_min, tri_wait_max = p.tri_wait_max;
+  const int tri_batch_min = p.tri_batch_min, tri_wait_max = p.tri_wait_max, refill_min = p.refill_min;
 
   // per-lane ray state
   Ray r;
@@ -152,7 +160,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
   for (;;) {
     // ---- 1. refill idle lanes from the resident ray block
     const unsigned idle = __ballot_sync(FULL, !active);
-    if (idle) {
+    // refill in batches: the refill code runs for the whole warp, so wait until a few lanes are idle (or none is busy)
+    if (idle && (__popc(idle) >= refill_min || idle == FULL)) {
       if (!warp_done) {
         if (consumed == blk_count) {       // resident block used up (or nothing loaded yet): move to the next one
           if (USE_TMA && lane == 0) prefetch(blk + 3);   // keep the stream two blocks ahead in L2
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
               sp = 0; top_y = 0; tgx = 0; tgy = 0;
               // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129)
               const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
-              idx = rcp_safe(r.dx); idy = rcp_safe(r.dy); idz = rcp_safe(r.dz);
+              idx = rcp_safe_fast(r.dx); idy = rcp_safe_fast(r.dy); idz = rcp_safe_fast(r.dz);
               oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
               tfar_tri = r.tfar;
               ngx = 0; ngy = go ? 0x80000000u : 0u;   // root entered as "one pending internal child, imask 0"
@@ -304,6 +313,7 @@ static int launch_k(TraceParams p, cudaStream_t st) {
   }
   p.tri_batch_min = g_tuning.tri_batch_min;
   p.tri_wait_max = g_tuning.tri_wait_max;
+  p.refill_min = g_tuning.refill_min;
   // persistent grid: a multiple of the SM count, capped by the work available
   const unsigned long long need = (p.n + TRACE_THREADS - 1) / TRACE_THREADS;
   const unsigned long long cap = (unsigned long long)g_num_sms * g_tuning.blocks_per_sm;

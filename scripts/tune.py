@@ -51,13 +51,18 @@ for pol_s in policies:
     S = A[::16].contiguous(); trace(sc, S, S.shape[0]); torch.cuda.synchronize()
     s2 = lib.scene_stats(sc); lib.rtcb200SetSceneStatCounters(sc, 0)
     print(f"policy {pol_s}: nodes {st.num_nodes} sah {st.sah_cost:.2f} depth {st.max_depth} build {st.build_ms:.1f} ms | nodes/ray {s2.trav_nodes/s2.trav_rays:.2f} tris/ray {s2.trav_tris/s2.trav_rays:.2f}", flush=True)
-    combos = [(6, 3, 8, 1), (6, 3, 8, 0)]
+    base = dict(tri_batch_min=6, tri_wait_max=3, blocks_per_sm=8, use_tma=1, refill_min=4)
+    combos = [dict()]
     if pol_s == policies[-1] or os.environ.get("FULL"):
-        combos = [(6, 3, 8, 1), (6, 3, 8, 0), (1, 1, 8, 1), (12, 6, 8, 1), (6, 3, 7, 1), (6, 3, 6, 1)]
-    for (bmin, wmax, bps, tma) in combos:
-        lib.rtcb200SetTuning(b"tri_batch_min", bmin); lib.rtcb200SetTuning(b"tri_wait_max", wmax)
-        lib.rtcb200SetTuning(b"blocks_per_sm", bps); lib.rtcb200SetTuning(b"use_tma", tma)
+        combos = [dict(), dict(refill_min=1), dict(refill_min=2), dict(refill_min=6), dict(refill_min=8), dict(refill_min=12),
+                  dict(tri_batch_min=1, tri_wait_max=1), dict(tri_batch_min=4, tri_wait_max=2), dict(tri_batch_min=8, tri_wait_max=4),
+                  dict(use_tma=0)]
+    for c in combos:
+        cfg = dict(base, **c)
+        for k, val in cfg.items():
+            lib.rtcb200SetTuning(k.encode(), val)
         ms = timeit(sc, A, B)
-        print(f"   batch_min {bmin:2d} wait_max {wmax:2d} blocks/SM {bps:2d} tma {tma}: {ms:7.3f} ms  {n/ms*1e-3:8.1f} Mrays/s", flush=True)
-    lib.rtcb200SetTuning(b"tri_batch_min", 6); lib.rtcb200SetTuning(b"tri_wait_max", 3); lib.rtcb200SetTuning(b"blocks_per_sm", 8); lib.rtcb200SetTuning(b"use_tma", 1)
+        print(f"   {c}: {ms:7.3f} ms  {n/ms*1e-3:8.1f} Mrays/s", flush=True)
+    for k, val in base.items():
+        lib.rtcb200SetTuning(k.encode(), val)
     lib.rtcReleaseScene(sc)
