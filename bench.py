@@ -9,8 +9,8 @@ as batched rtcIntersect1 records.  A step = one pass of the 64 Mi-ray stream thr
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rays R] [--phi P]
 
 value  : Mrays/s with the RTCRayHit[] stream resident in HBM (rtcb200Intersect1MDevice on torch's current stream),
-         whole job over all ranks (weak scaling: every rank traces its own 64 Mi rays; compact hit records are
-         gathered on rank 0 over NCCL inside the timed region).
+         whole job over all ranks (weak scaling: every rank traces its own 64 Mi rays; inside the timed region the
+         trace kernel itself stores a compact hit record per ray into rank 0's buffer over NVLink peer memory).
 e2e    : the same stream through the host-pointer entry point rtcb200Intersect1M with pinned host buffers:
          H2D copy + trace + D2H copy inside the timed region.
 --impl reference : the unmodified reference (oracle/_ref/libembree4.so.4, else the C port) on the host cores.
@@ -163,7 +163,7 @@ def workload_config(args, ntris):
                         f"{args.rays} incoherent diffuse-bounce rays ({REPLICATE} cosine-weighted bounces per hit of a {PRIMARY_W}x{PRIMARY_H} "
                         f"pinhole image from inside the mesh), batched rtcIntersect1 over RTCRayHit[]",
             "rays_per_gpu": args.rays, "triangles": ntris, "l2": "ray stream 6.4 GB and BVH 0.6 GB per step exceed the 126 MB L2",
-            "parallelism": f"ray-stream sharding x{args.gpus}, BVH replicated, compact hit gather to rank 0"}
+            "parallelism": f"ray-stream sharding x{args.gpus}, BVH replicated, compact hit records stored to rank 0 over NVLink by the trace kernel"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -231,28 +231,37 @@ def main():
     bytes_per_ray = 48 + 48 + 4 + nodes_per_ray * 80 + tris_per_ray * 48
     del S
 
-    # ---- hit gather plumbing (N > 1): compact 32-byte records to rank 0, chunk c gathered while chunk c+1 traces
-    NCH = 8 if world > 1 else 1
-    bounds = [sharding.shard_bounds(n, c, NCH) for c in range(NCH)]
-    comm_stream = torch.cuda.Stream() if world > 1 else None
-    compact = torch.empty((n, 8), dtype=torch.float32, device=devt) if world > 1 else None
-    gathered = [torch.empty((n, 8), dtype=torch.float32, device=devt) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # ---- hit gather (N > 1), fused into the trace kernel: rank 0 owns a [world, n, 8] float buffer, every rank maps it
+    # through CUDA IPC and its trace kernel stores one compact 32-byte hit record per ray straight into its slice over
+    # NVLink (rtcb200Intersect1MGatherDevice).  A tiny NCCL all-reduce, stream-ordered after the kernel, is the
+    # per-step "all hits have arrived" signal.  No separate collective moves hit data.
+    gbuf, my_out, flag = None, None, None
+    if world > 1:
+        nbytes = world * n * 32
+        handle = [None]
+        if rank == 0:
+            gbuf = lib.rtcb200PeerAlloc(dev, nbytes)
+            h64 = (C.c_ubyte * 64)()
+            assert lib.rtcb200PeerExport(dev, C.c_void_p(gbuf), h64) == 0
+            handle = [bytes(h64)]
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            h64 = (C.c_ubyte * 64).from_buffer_copy(handle[0])
+            gbuf = lib.rtcb200PeerImport(dev, h64)
+        lib.check(dev)
+        assert gbuf
+        my_out = gbuf + rank * n * 32
+        flag = torch.zeros(1, device=devt)
     kernel_ms = []
 
     def step(record_kernel_ms=False):
         B[:, 8] = float("inf")  # restore the only input field the trace overwrites (ray.tfar)
-        for (b, e) in bounds:
-            lib.rtcb200Intersect1MDevice(sc, C.c_void_p(B[b:e].data_ptr()), e - b, C.byref(a), C.c_void_p(stream))
-            if world > 1:
-                sharding.compact_hits(B[b:e], out=compact[b:e])
-                ev = torch.cuda.Event()
-                ev.record()
-                with torch.cuda.stream(comm_stream):
-                    comm_stream.wait_event(ev)
-                    dist.gather(compact[b:e], [g[b:e] for g in gathered] if rank == 0 else None, dst=0)
         if world > 1:
-            torch.cuda.current_stream().wait_stream(comm_stream)
-        if record_kernel_ms and world == 1:
+            lib.rtcb200Intersect1MGatherDevice(sc, C.c_void_p(B.data_ptr()), n, C.byref(a), C.c_void_p(stream), C.c_void_p(my_out))
+            dist.all_reduce(flag)
+        else:
+            lib.rtcb200Intersect1MDevice(sc, C.c_void_p(B.data_ptr()), n, C.byref(a), C.c_void_p(stream))
+        if record_kernel_ms:
             kernel_ms.append(lib.rtcb200GetLastTraceMs(sc))
 
     for _ in range(args.warmup):
@@ -281,6 +290,20 @@ def main():
     value = n * world / (ms_per_step * 1e-3) * 1e-6
     lib.check(dev)
     sampler.join(timeout=2)
+    gather_ok = None
+    if world > 1:   # untimed: the NVLink-written records on rank 0 must equal what an NCCL gather of the same hits delivers
+        local = sharding.compact_hits(B)
+        ri = B.view(torch.int32)
+        miss = ri[:, 18] == -1
+        local[miss, 1:6] = 0.0
+        local.view(torch.int32)[miss, 6] = -1
+        local.view(torch.int32)[miss, 7] = -1
+        bufs, _ = sharding.gather_hits(local, dst=0)
+        if rank == 0:
+            got = torch.empty((world, n, 8), dtype=torch.float32, device=devt)
+            lib.rtcb200PeerCopy(dev, C.c_void_p(got.data_ptr()), C.c_void_p(gbuf), world * n * 32)
+            gather_ok = all(bool(torch.equal(got[r].view(torch.int32), bufs[r].view(torch.int32))) for r in range(world))
+            log(f"fused NVLink gather == NCCL gather: {gather_ok}")
 
     # ---- end to end through the host-pointer entry point (pinned host memory, H2D + trace + D2H timed)
     e2e = None
@@ -356,7 +379,7 @@ def main():
         line = {"metric": "Mrays/s incoherent diffuse-bounce, 10M-triangle scene", "value": value, "unit": "Mrays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, len(t)),
-                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "gather_verified": gather_ok,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                              "traffic": traffic, "peak_source": peak_src, "kernel": "rtk::trace_kernel<1,false,false>",
                              "kernel_ms": kms, "algorithmic_bytes_per_ray": bytes_per_ray,

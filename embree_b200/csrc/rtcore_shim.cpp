@@ -333,11 +333,12 @@ void trace_one(SceneImpl* s, void* rec, size_t recBytes, const int* valid, int K
 
 // batched, device pointers: enqueue only
 void trace_device(SceneImpl* s, void* d_rays, const int* d_valid, int K, size_t M, int occluded, uint32_t instID,
-                  uint32_t instPrimID, cudaStream_t st, bool timeit) {
+                  uint32_t instPrimID, cudaStream_t st, bool timeit, void* compact_out = nullptr) {
   require_committed(s);
   if (!s->gpu.root_valid || M == 0) return;
   cudaSetDevice(s->dev->gpu);
   rtk::TraceParams p = make_params(s, d_rays, d_valid, (unsigned long long)M * K, instID, instPrimID);
+  p.compact_out = compact_out;
   if (timeit) {
     if (!s->ev0) { cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); }
     cudaEventRecord(s->ev0, st);
@@ -761,6 +762,7 @@ void rtcb200Occluded1M(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOcclud
 void rtcb200IntersectNM(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_host(s_, rh, v, (int)K, M, (size_t)84 * K, 0, iid, ipid);) }
 void rtcb200OccludedNM(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_host(s_, r, v, (int)K, M, (size_t)48 * K, 1, iid, ipid);) }
 void rtcb200Intersect1MDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, rh, nullptr, 1, M, 0, iid, ipid, (cudaStream_t)st, true);) }
+void rtcb200Intersect1MGatherDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st, void* compact_out) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, rh, nullptr, 1, M, 0, iid, ipid, (cudaStream_t)st, true, compact_out);) }
 void rtcb200Occluded1MDevice(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, r, nullptr, 1, M, 1, iid, ipid, (cudaStream_t)st, true);) }
 void rtcb200IntersectNMDevice(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_device(s_, rh, v, (int)K, M, 0, iid, ipid, (cudaStream_t)st, true);) }
 void rtcb200OccludedNMDevice(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_device(s_, r, v, (int)K, M, 1, iid, ipid, (cudaStream_t)st, true);) }
@@ -785,6 +787,47 @@ void rtcb200GetSceneStats(RTCScene sc, struct RTCB200SceneStats* o) {
 void rtcb200SetSceneStatCounters(RTCScene sc, int enable) { SCENE_BEGIN(sc) S(sc)->statCounters = enable != 0; SCENE_END }
 void rtcb200ResetSceneStatCounters(RTCScene sc) { SCENE_BEGIN(sc) if (S(sc)->gpu.d_stat) { S(sc)->dev->use(); cuda_check(cudaMemset(S(sc)->gpu.d_stat, 0, 24), "reset stat counters"); } SCENE_END }
 unsigned long long rtcb200GetLaunchCount(void) { return rtk::launch_count(); }
+
+// ---- peer-visible device buffers for the fused multi-GPU hit gather (one process per GPU: CUDA IPC over NVLink) ----
+void* rtcb200PeerAlloc(RTCDevice h, size_t bytes) {
+  API_BEGIN
+  VERIFY_HANDLE(h);
+  D(h)->use();
+  void* p = nullptr;
+  cuda_check(cudaMalloc(&p, bytes ? bytes : 16), "cudaMalloc(peer buffer)");
+  return p;
+  API_END(D(h))
+  return nullptr;
+}
+void rtcb200PeerFree(RTCDevice h, void* p) { API_BEGIN VERIFY_HANDLE(h); D(h)->use(); if (p) cuda_check(cudaFree(p), "cudaFree(peer buffer)"); API_END(D(h)) }
+int rtcb200PeerExport(RTCDevice h, void* p, unsigned char handle[64]) {
+  API_BEGIN
+  VERIFY_HANDLE(h); VERIFY_HANDLE(p); VERIFY_HANDLE(handle);
+  D(h)->use();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t ih;
+  cuda_check(cudaIpcGetMemHandle(&ih, p), "cudaIpcGetMemHandle");
+  memcpy(handle, &ih, 64);
+  return 0;
+  API_END(D(h))
+  return -1;
+}
+void* rtcb200PeerImport(RTCDevice h, const unsigned char handle[64]) {
+  API_BEGIN
+  VERIFY_HANDLE(h); VERIFY_HANDLE(handle);
+  D(h)->use();
+  cudaIpcMemHandle_t ih;
+  memcpy(&ih, handle, 64);
+  void* p = nullptr;
+  cuda_check(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+  return p;
+  API_END(D(h))
+  return nullptr;
+}
+void rtcb200PeerCopy(RTCDevice h, void* dst, const void* src, size_t bytes) {
+  API_BEGIN VERIFY_HANDLE(h); D(h)->use(); cuda_check(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault), "cudaMemcpy(peer buffer)"); API_END(D(h))
+}
+void rtcb200PeerClose(RTCDevice h, void* p) { API_BEGIN VERIFY_HANDLE(h); D(h)->use(); if (p) cuda_check(cudaIpcCloseMemHandle(p), "cudaIpcCloseMemHandle"); API_END(D(h)) }
 int rtcb200SetTuning(const char* key, int value) {
   if (!key) return -1;
   rtk::Tuning& t = rtk::tuning();

@@ -47,6 +47,10 @@ struct TraceParams {
   unsigned long long n;  // number of rays = records * K
   uint32_t instID, instPrimID;
   unsigned long long* stat;  // non-NULL -> counting kernel
+  // optional second output (K == 1 closest-hit only): one 32-byte record per ray {tfar, Ng.xyz, u, v, primID, geomID}
+  // written when the ray terminates.  May point into a PEER GPU's memory (NVLink): this is how the multi-GPU
+  // hit gather is fused into the trace kernel instead of being a separate collective.
+  void* compact_out = nullptr;
   int tri_batch_min = 6, tri_wait_max = 3, refill_min = 4;  // filled by launch_trace from tuning()
 };
 // occluded: 0 = closest hit (rtcIntersect*), 1 = any hit (rtcOccluded*); K in {1,4,8,16}

@@ -265,6 +265,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
         if (py & 0xFF000000u) { ngx = px; ngy = py; }
         else { tgx = px; tgy = py; ngx = 0; ngy = 0; }
       } else {
+        float cngx = 0.0f, cngy = 0.0f, cngz = 0.0f;
+        uint32_t cprim = kInvalidID, cgeom = kInvalidID;
         if (found) {
           if (OCCLUDED) IO::store_tfar(p, ray_index, -INFINITY);   // bvh_intersector1.cpp:186-188
           else {
@@ -280,7 +282,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
             hit.ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
             hit.primID = a.w; hit.geomID = b.w;
             IO::store_hit(p, ray_index, hit);
+            cngx = hit.ngx; cngy = hit.ngy; cngz = hit.ngz; cprim = hit.primID; cgeom = hit.geomID;
           }
+        }
+        if (K == 1 && !OCCLUDED && p.compact_out) {   // fused hit gather: compact record, possibly over NVLink
+          float4* co = reinterpret_cast<float4*>(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32);
+          co[0] = make_float4(tfar_tri, cngx, cngy, cngz);
+          co[1] = make_float4(found ? hit_u : 0.0f, found ? hit_v : 0.0f, __uint_as_float(cprim), __uint_as_float(cgeom));
         }
         active = false;
       }

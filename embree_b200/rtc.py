@@ -197,6 +197,13 @@ class RTCLib:
         "rtcb200IntersectNM": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t, C.c_void_p]),
         "rtcb200OccludedNM": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t, C.c_void_p]),
         "rtcb200Intersect1MDevice": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+        "rtcb200Intersect1MGatherDevice": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "rtcb200PeerAlloc": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+        "rtcb200PeerFree": (None, [C.c_void_p, C.c_void_p]),
+        "rtcb200PeerExport": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+        "rtcb200PeerImport": (C.c_void_p, [C.c_void_p, C.c_void_p]),
+        "rtcb200PeerClose": (None, [C.c_void_p, C.c_void_p]),
+        "rtcb200PeerCopy": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
         "rtcb200Occluded1MDevice": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
         "rtcb200IntersectNMDevice": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t, C.c_void_p, C.c_void_p]),
         "rtcb200OccludedNMDevice": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t, C.c_void_p, C.c_void_p]),

@@ -288,9 +288,22 @@ RTCB200_API void rtcb200Occluded1M(RTCScene scene, struct RTCRay* rays, size_t M
 RTCB200_API void rtcb200IntersectNM(const int* valid, RTCScene scene, void* rayhitK, unsigned int K, size_t M, struct RTCIntersectArguments* args);
 RTCB200_API void rtcb200OccludedNM(const int* valid, RTCScene scene, void* rayK, unsigned int K, size_t M, struct RTCOccludedArguments* args);
 RTCB200_API void rtcb200Intersect1MDevice(RTCScene scene, struct RTCRayHit* d_rayhits, size_t M, struct RTCIntersectArguments* args, void* cuda_stream);
+/* as rtcb200Intersect1MDevice, and additionally writes one compact 32-byte record {tfar, Ng.xyz, u, v, primID, geomID} per
+ * ray (primID = geomID = -1 on a miss) to compact_out[i].  compact_out may be memory of ANOTHER GPU imported with
+ * rtcb200PeerImport: the kernel then stores straight over NVLink, which fuses the multi-GPU hit gather into the trace. */
+RTCB200_API void rtcb200Intersect1MGatherDevice(RTCScene scene, struct RTCRayHit* d_rayhits, size_t M, struct RTCIntersectArguments* args, void* cuda_stream, void* compact_out);
 RTCB200_API void rtcb200Occluded1MDevice(RTCScene scene, struct RTCRay* d_rays, size_t M, struct RTCOccludedArguments* args, void* cuda_stream);
 RTCB200_API void rtcb200IntersectNMDevice(const int* d_valid, RTCScene scene, void* d_rayhitK, unsigned int K, size_t M, struct RTCIntersectArguments* args, void* cuda_stream);
 RTCB200_API void rtcb200OccludedNMDevice(const int* d_valid, RTCScene scene, void* d_rayK, unsigned int K, size_t M, struct RTCOccludedArguments* args, void* cuda_stream);
+
+/* Peer-visible device buffers (one process per GPU): allocate on the owner, export a 64-byte handle, import it in the
+ * other processes (CUDA IPC, peer access over NVLink enabled on import). */
+RTCB200_API void* rtcb200PeerAlloc(RTCDevice device, size_t bytes);
+RTCB200_API void rtcb200PeerFree(RTCDevice device, void* ptr);
+RTCB200_API int rtcb200PeerExport(RTCDevice device, void* ptr, unsigned char handle[64]);
+RTCB200_API void* rtcb200PeerImport(RTCDevice device, const unsigned char handle[64]);
+RTCB200_API void rtcb200PeerClose(RTCDevice device, void* ptr);
+RTCB200_API void rtcb200PeerCopy(RTCDevice device, void* dst, const void* src, size_t bytes); /* blocking cudaMemcpyDefault */
 
 /* Build / traversal statistics of the last commit and, when enabled, of traced rays
  * (device analogue of EMBREE_STAT_COUNTERS, kernels/common/stat.h:82-90). */
