@@ -411,16 +411,35 @@ int build_sah_tree(const PrimRef* prims, uint32_t* idsA, uint32_t* idsB, uint32_
 // ---------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------
+// Build temporaries come from the device's stream-ordered memory pool (cudaMallocAsync): after the first commit the
+// pool serves every later build without touching the driver allocator, which is what keeps per-frame rebuilds of
+// dynamic scenes at kernel time (a plain cudaMalloc/cudaFree pair per buffer cost 10-300 ms at 10 M triangles).
+static void ensure_pool(int device) {
+  static bool done[64] = {};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done[device] = true;
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+  cudaStream_t st = nullptr;
+  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+  cudaError_t alloc(size_t n, cudaStream_t stream) {
+    st = stream;
+    return cudaMallocAsync(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T), stream);
+  }
 };
 
 void free_scene(SceneGPU& s) {
-  if (s.nodes) cudaFree(s.nodes);
-  if (s.tris) cudaFree(s.tris);
+  if (s.nodes) cudaFreeAsync(s.nodes, 0);   // pool memory: goes back to the pool for the next commit
+  if (s.tris) cudaFreeAsync(s.tris, 0);
   if (s.d_stat) cudaFree(s.d_stat);
   s.nodes = nullptr; s.tris = nullptr; s.d_stat = nullptr;
   s.num_nodes = s.num_tris = 0; s.root_valid = 0;
@@ -428,8 +447,8 @@ void free_scene(SceneGPU& s) {
 
 int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind, cudaStream_t st, char* errmsg) {
   errmsg[0] = 0;
-  if (s.nodes) { cudaFree(s.nodes); s.nodes = nullptr; }
-  if (s.tris) { cudaFree(s.tris); s.tris = nullptr; }
+  if (s.nodes) { cudaFreeAsync(s.nodes, st); s.nodes = nullptr; }
+  if (s.tris) { cudaFreeAsync(s.tris, st); s.tris = nullptr; }
   s.num_nodes = s.num_tris = 0; s.root_valid = 0; s.max_depth = 0; s.sah_cost = 0; s.builder = kind;
   for (int a = 0; a < 3; ++a) { s.bounds[a] = INFINITY; s.bounds[3 + a] = -INFINITY; }
   if (!s.d_stat) { CK(cudaMalloc(&s.d_stat, 3 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s.d_stat, 0, 24, st)); }
@@ -441,6 +460,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   offs[ngeoms] = (uint32_t)tot64;
   const uint32_t ntot = (uint32_t)tot64;
   if (ntot == 0) return 0;  // empty scene: queries return immediately (bvh_intersector1.cpp:39)
+  ensure_pool(s.device);
 
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
@@ -448,10 +468,10 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
 
   DevBuf<GeomDesc> d_geoms; DevBuf<uint32_t> d_offs; DevBuf<BuildInfo> d_info; DevBuf<PrimRef> d_prims;
   DevBuf<uint64_t> d_k0, d_k1; DevBuf<uint32_t> d_v0, d_v1, d_hist, d_dtot, d_dbase;
-  CK(d_geoms.alloc(ngeoms)); CK(d_offs.alloc(ngeoms + 1)); CK(d_info.alloc(1)); CK(d_prims.alloc(ntot));
-  CK(d_k0.alloc(ntot)); CK(d_k1.alloc(ntot)); CK(d_v0.alloc(ntot)); CK(d_v1.alloc(ntot));
+  CK(d_geoms.alloc(ngeoms, st)); CK(d_offs.alloc(ngeoms + 1, st)); CK(d_info.alloc(1, st)); CK(d_prims.alloc(ntot, st));
+  CK(d_k0.alloc(ntot, st)); CK(d_k1.alloc(ntot, st)); CK(d_v0.alloc(ntot, st)); CK(d_v1.alloc(ntot, st));
   const uint32_t nb = (ntot + RS_TILE - 1) / RS_TILE;
-  CK(d_hist.alloc((size_t)256 * nb)); CK(d_dtot.alloc(256)); CK(d_dbase.alloc(256));
+  CK(d_hist.alloc((size_t)256 * nb, st)); CK(d_dtot.alloc(256, st)); CK(d_dbase.alloc(256, st));
   CK(cudaMemcpyAsync(d_geoms.p, geoms, sizeof(GeomDesc) * ngeoms, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_offs.p, offs.data(), 4 * (ngeoms + 1), cudaMemcpyHostToDevice, st));
 
@@ -481,7 +501,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
 
   // ---- binary tree
   DevBuf<Node2> d_n2; DevBuf<uint32_t> d_flags;
-  CK(d_n2.alloc((size_t)2 * n)); CK(d_flags.alloc(n));
+  CK(d_n2.alloc((size_t)2 * n, st)); CK(d_flags.alloc(n, st));
   uint32_t root2 = 0;
   if (kind == BUILDER_SAH && n > 1) {
     float cb[6];
@@ -503,15 +523,15 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   DevBuf<float> d_F;
   const bool use_dp = tuning().collapse_policy >= 3 && n > 1;
   if (use_dp) {
-    CK(d_F.alloc((size_t)2 * n * 8)); CK(d_dec.alloc((size_t)2 * n));
+    CK(d_F.alloc((size_t)2 * n * 8, st)); CK(d_dec.alloc((size_t)2 * n, st));
     CK(cudaMemsetAsync(d_flags.p, 0, 4 * (size_t)n, st));
     collapse_dp<<<(n + 255) / 256, 256, 0, st>>>(d_n2.p, (int)n, d_flags.p, d_F.p, d_dec.p, tuning().c_node * 0.01f, tuning().c_tri * 0.01f);
     count_launch();
   }
   s.node_capacity = (size_t)n + 1; s.tri_capacity = n;
-  CK(d_src.alloc(s.node_capacity)); CK(d_trisrc.alloc(n));
+  CK(d_src.alloc(s.node_capacity, st)); CK(d_trisrc.alloc(n, st));
   Node8* n8 = nullptr;
-  CK(cudaMalloc(&n8, s.node_capacity * sizeof(Node8)));
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&n8), s.node_capacity * sizeof(Node8), st));
   CK(cudaMemcpyAsync(d_src.p, &root2, 4, cudaMemcpyHostToDevice, st));
   const float ex = s.bounds[3] - s.bounds[0], ey = s.bounds[4] - s.bounds[1], ez = s.bounds[5] - s.bounds[2];
   const float ra = ex * (ey + ez) + ey * ez;
@@ -525,25 +545,25 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
     CK(cudaMemcpyAsync(&tail, &d_info.p->node_tail, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     begin = end; end = tail; ++depth;
-    if (depth > 4096) { snprintf(errmsg, 256, "collapse did not terminate"); cudaFree(n8); return -1; }
+    if (depth > 4096) { snprintf(errmsg, 256, "collapse did not terminate"); cudaFreeAsync(n8, st); return -1; }
   }
   CK(cudaMemcpyAsync(&hinfo, d_info.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (hinfo.tri_tail != n) { snprintf(errmsg, 256, "internal: packed %u of %u triangles", hinfo.tri_tail, n); cudaFree(n8); return -1; }
-  if (depth >= (uint32_t)kStackSize) { snprintf(errmsg, 256, "BVH too deep for the traversal stack (%u)", depth); cudaFree(n8); return -1; }
+  if (hinfo.tri_tail != n) { snprintf(errmsg, 256, "internal: packed %u of %u triangles", hinfo.tri_tail, n); cudaFreeAsync(n8, st); return -1; }
+  if (depth >= (uint32_t)kStackSize) { snprintf(errmsg, 256, "BVH too deep for the traversal stack (%u)", depth); cudaFreeAsync(n8, st); return -1; }
 
   // ---- triangle records, then shrink the node array to its final size
   TriRec* tris = nullptr;
-  CK(cudaMalloc(&tris, (size_t)n * sizeof(TriRec)));
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&tris), (size_t)n * sizeof(TriRec), st));
   leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, tris);
   count_launch();
   Node8* n8_final = nullptr;
-  CK(cudaMalloc(&n8_final, (size_t)end * sizeof(Node8)));
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&n8_final), (size_t)end * sizeof(Node8), st));
   CK(cudaMemcpyAsync(n8_final, n8, (size_t)end * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
   CK(cudaEventRecord(ev1, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
-  cudaFree(n8);
+  cudaFreeAsync(n8, st);
   float ms = 0;
   cudaEventElapsedTime(&ms, ev0, ev1);
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);

@@ -571,24 +571,24 @@ int build_sah_tree(const PrimRef* prims, uint32_t* idsA, uint32_t* idsB, uint32_
   const size_t max_chunks = (size_t)n / kChunk + max_large + 2;
   int rc = 0;
   auto cleanup = [&]() {
-    for (int p = 0; p < 2; ++p) for (int k = 0; k < 3; ++k) if (lists[p][k]) cudaFree(lists[p][k]);
-    if (d_ctr) cudaFree(d_ctr);
-    if (d_scr) cudaFree(d_scr);
-    if (d_chunk_task) cudaFree(d_chunk_task);
-    if (d_b) cudaFree(d_b);
-    if (d_lists) cudaFree(d_lists);
+    for (int p = 0; p < 2; ++p) for (int k = 0; k < 3; ++k) if (lists[p][k]) cudaFreeAsync(lists[p][k], st);
+    if (d_ctr) cudaFreeAsync(d_ctr, st);
+    if (d_scr) cudaFreeAsync(d_scr, st);
+    if (d_chunk_task) cudaFreeAsync(d_chunk_task, st);
+    if (d_b) cudaFreeAsync(d_b, st);
+    if (d_lists) cudaFreeAsync(d_lists, st);
   };
 #define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(errmsg, 256, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); cleanup(); return (int)e_; } } while (0)
   for (int p = 0; p < 2; ++p) {
-    CKC(cudaMalloc(&lists[p][0], max_large * sizeof(SahTask)));
-    CKC(cudaMalloc(&lists[p][1], ((size_t)n / kWarpCap + 2) * sizeof(SahTask)));
-    CKC(cudaMalloc(&lists[p][2], max_tasks * sizeof(SahTask)));
+    CKC(cudaMallocAsync(reinterpret_cast<void**>(&lists[p][0]), max_large * sizeof(SahTask), st));
+    CKC(cudaMallocAsync(reinterpret_cast<void**>(&lists[p][1]), ((size_t)n / kWarpCap + 2) * sizeof(SahTask), st));
+    CKC(cudaMallocAsync(reinterpret_cast<void**>(&lists[p][2]), max_tasks * sizeof(SahTask), st));
   }
-  CKC(cudaMalloc(&d_ctr, sizeof(SahCounters)));
-  CKC(cudaMalloc(&d_scr, max_large * sizeof(LargeScratch)));
-  CKC(cudaMalloc(&d_chunk_task, max_chunks * 4));
-  CKC(cudaMalloc(&d_b, 12 * sizeof(float)));
-  CKC(cudaMalloc(&d_lists, 3 * sizeof(SahTask*)));
+  CKC(cudaMallocAsync(reinterpret_cast<void**>(&d_ctr), sizeof(SahCounters), st));
+  CKC(cudaMallocAsync(reinterpret_cast<void**>(&d_scr), max_large * sizeof(LargeScratch), st));
+  CKC(cudaMallocAsync(reinterpret_cast<void**>(&d_chunk_task), max_chunks * 4, st));
+  CKC(cudaMallocAsync(reinterpret_cast<void**>(&d_b), 12 * sizeof(float), st));
+  CKC(cudaMallocAsync(reinterpret_cast<void**>(&d_lists), 3 * sizeof(SahTask*), st));
   float hb[12];
   for (int k = 0; k < 6; ++k) { hb[k] = scene_bounds[k]; hb[6 + k] = cent_bounds[k]; }
   CKC(cudaMemcpyAsync(d_b, hb, sizeof hb, cudaMemcpyHostToDevice, st));

@@ -163,7 +163,7 @@ struct SceneImpl : RefCounted {
   ~SceneImpl() override {
     dev->use();
     for (GeometryImpl* g : geoms) if (g) g->release();
-    for (void* p : deviceBuffers) cudaFree(p);
+    for (void* p : deviceBuffers) cudaFreeAsync(p, 0);
     rtk::free_scene(gpu);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -217,7 +217,7 @@ void commit_scene(SceneImpl* s) {
     if (g && g->enabled && g->state == GeomState::MODIFIED) fail(RTC_ERROR_INVALID_OPERATION, "geometry not committed");
   if (s->progFn && !s->progFn(s->progPtr, 0.0)) fail(RTC_ERROR_CANCELLED, "progress monitor forced termination");
   s->dev->use();
-  for (void* p : s->deviceBuffers) cudaFree(p);
+  for (void* p : s->deviceBuffers) cudaFreeAsync(p, 0);
   s->deviceBuffers.clear();
   std::vector<rtk::GeomDesc> descs;
   for (size_t id = 0; id < geoms.size(); ++id) {
@@ -230,12 +230,12 @@ void commit_scene(SceneImpl* s) {
     const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 12 : 0;
     const size_t ibytes = (ntris - 1) * g->indices.stride + 12;
     void *dv = nullptr, *di = nullptr;
-    cuda_check(cudaMalloc(&dv, vbytes ? vbytes : 16), "cudaMalloc(vertices)");
+    cuda_check(cudaMallocAsync(&dv, vbytes ? vbytes : 16, 0), "cudaMallocAsync(vertices)");
     s->deviceBuffers.push_back(dv);
-    cuda_check(cudaMalloc(&di, ibytes), "cudaMalloc(indices)");
+    cuda_check(cudaMallocAsync(&di, ibytes, 0), "cudaMallocAsync(indices)");
     s->deviceBuffers.push_back(di);
-    if (vbytes) cuda_check(cudaMemcpy(dv, g->vertices.data(), vbytes, cudaMemcpyHostToDevice), "upload vertices");
-    cuda_check(cudaMemcpy(di, g->indices.data(), ibytes, cudaMemcpyHostToDevice), "upload indices");
+    if (vbytes) cuda_check(cudaMemcpyAsync(dv, g->vertices.data(), vbytes, cudaMemcpyHostToDevice, 0), "upload vertices");
+    cuda_check(cudaMemcpyAsync(di, g->indices.data(), ibytes, cudaMemcpyHostToDevice, 0), "upload indices");
     rtk::GeomDesc d;
     d.verts = static_cast<const uint8_t*>(dv); d.idx = static_cast<const uint8_t*>(di);
     d.vstride = g->vertices.stride; d.istride = g->indices.stride;
@@ -250,7 +250,7 @@ void commit_scene(SceneImpl* s) {
   char errmsg[256];
   const int r = rtk::build_scene(s->gpu, descs.data(), (int)descs.size(), kind, 0, errmsg);
   // vertex/index copies are only needed during the build (triangles are baked into the leaf records)
-  for (void* p : s->deviceBuffers) cudaFree(p);
+  for (void* p : s->deviceBuffers) cudaFreeAsync(p, 0);
   s->deviceBuffers.clear();
   if (r != 0) {
     rtk::free_scene(s->gpu);
