@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) collapse_dp(const Node2* __restrict__ nod
 // 6. leaf_pack: gather vertices through the index buffer, store v0, e1 = v0 - v1, e2 = v2 - v0 (triangle.h:98-120)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ offs, int ngeoms,
-                                                 const uint32_t* __restrict__ tri_src, uint32_t ntris, TriRec* __restrict__ out) {
+                                                 const uint32_t* __restrict__ tri_src, uint32_t ntris, TriRec* __restrict__ out, int robust) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntris) return;
   const uint32_t p = tri_src[t];
@@ -398,8 +398,15 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
   load_tri_verts(gd, p - offs[g], v, ok);
   float4 a, b, c;
   a.x = v[0]; a.y = v[1]; a.z = v[2]; a.w = __uint_as_float(p - offs[g]);
-  b.x = __fsub_rn(v[0], v[3]); b.y = __fsub_rn(v[1], v[4]); b.z = __fsub_rn(v[2], v[5]); b.w = __uint_as_float(gd.geomID);
-  c.x = __fsub_rn(v[6], v[0]); c.y = __fsub_rn(v[7], v[1]); c.z = __fsub_rn(v[8], v[2]); c.w = __uint_as_float(gd.mask);
+  if (robust) {   // Triangle4v: full vertices for the Pluecker test (kernels/geometry/trianglev.h)
+    b.x = v[3]; b.y = v[4]; b.z = v[5];
+    c.x = v[6]; c.y = v[7]; c.z = v[8];
+  } else {
+    b.x = __fsub_rn(v[0], v[3]); b.y = __fsub_rn(v[1], v[4]); b.z = __fsub_rn(v[2], v[5]);
+    c.x = __fsub_rn(v[6], v[0]); c.y = __fsub_rn(v[7], v[1]); c.z = __fsub_rn(v[8], v[2]);
+  }
+  b.w = __uint_as_float(gd.geomID);
+  c.w = __uint_as_float(gd.mask);
   float4* dst = reinterpret_cast<float4*>(&out[t]);
   dst[0] = a; dst[1] = b; dst[2] = c;
 }
@@ -555,7 +562,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   // ---- triangle records, then shrink the node array to its final size
   TriRec* tris = nullptr;
   CK(cudaMallocAsync(reinterpret_cast<void**>(&tris), (size_t)n * sizeof(TriRec), st));
-  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, tris);
+  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, tris, s.robust);
   count_launch();
   Node8* n8_final = nullptr;
   CK(cudaMallocAsync(reinterpret_cast<void**>(&n8_final), (size_t)end * sizeof(Node8), st));

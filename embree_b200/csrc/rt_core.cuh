@@ -169,6 +169,73 @@ RT_HD bool tri_test(const Ray& r, float tfar, float v0x, float v0y, float v0z, f
 }
 
 // ------------------------------------------------------------------------------------------------
+// robust mode (RTC_SCENE_FLAG_ROBUST): PlueckerIntersector1<M>::intersect restated for one lane
+// (kernels/geometry/triangle_intersector_pluecker.h:62-118, finalize :30-37, stable_triangle_normal
+// common/math/vec3.h:210-222).  Vertices are taken relative to the ray origin; the edge tests are watertight along
+// shared edges; t is accepted on the closed interval [tnear, tfar].
+// ------------------------------------------------------------------------------------------------
+struct PlueckerHit { float t, U, V, UVW, ngx, ngy, ngz; };
+
+RT_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b; return r;
+#endif
+}
+RT_HD float rcp_rn(float a) { return 1.0f / a; }
+
+RT_HD void stable_normal(float ax, float ay, float az, float bx, float by, float bz, float cx, float cy, float cz, float& nx,
+                         float& ny, float& nz) {
+  const float ab_x = mul_rn(az, by), ab_y = mul_rn(ax, bz), ab_z = mul_rn(ay, bx);
+  const float bc_x = mul_rn(bz, cy), bc_y = mul_rn(bx, cz), bc_z = mul_rn(by, cx);
+  const float cab_x = msub(ay, bz, ab_x), cab_y = msub(az, bx, ab_y), cab_z = msub(ax, by, ab_z);
+  const float cbc_x = msub(by, cz, bc_x), cbc_y = msub(bz, cx, bc_y), cbc_z = msub(bx, cy, bc_z);
+  nx = fabsf(ab_x) < fabsf(bc_x) ? cab_x : cbc_x;
+  ny = fabsf(ab_y) < fabsf(bc_y) ? cab_y : cbc_y;
+  nz = fabsf(ab_z) < fabsf(bc_z) ? cab_z : cbc_z;
+}
+
+RT_HD bool tri_test_pluecker(const Ray& r, float tfar, float p0x, float p0y, float p0z, float p1x, float p1y, float p1z,
+                             float p2x, float p2y, float p2z, PlueckerHit& h) {
+  const float v0x = sub_rn(p0x, r.ox), v0y = sub_rn(p0y, r.oy), v0z = sub_rn(p0z, r.oz);
+  const float v1x = sub_rn(p1x, r.ox), v1y = sub_rn(p1y, r.oy), v1z = sub_rn(p1z, r.oz);
+  const float v2x = sub_rn(p2x, r.ox), v2y = sub_rn(p2y, r.oy), v2z = sub_rn(p2z, r.oz);
+  const float e0x = sub_rn(v2x, v0x), e0y = sub_rn(v2y, v0y), e0z = sub_rn(v2z, v0z);
+  const float e1x = sub_rn(v0x, v1x), e1y = sub_rn(v0y, v1y), e1z = sub_rn(v0z, v1z);
+  const float e2x = sub_rn(v1x, v2x), e2y = sub_rn(v1y, v2y), e2z = sub_rn(v1z, v2z);
+  // U = dot(cross(e0, v2+v0), D) etc.
+  const float s0x = add_rn(v2x, v0x), s0y = add_rn(v2y, v0y), s0z = add_rn(v2z, v0z);
+  const float s1x = add_rn(v0x, v1x), s1y = add_rn(v0y, v1y), s1z = add_rn(v0z, v1z);
+  const float s2x = add_rn(v1x, v2x), s2y = add_rn(v1y, v2y), s2z = add_rn(v1z, v2z);
+  const float U = dot3(msub(e0y, s0z, mul_rn(e0z, s0y)), msub(e0z, s0x, mul_rn(e0x, s0z)), msub(e0x, s0y, mul_rn(e0y, s0x)),
+                       r.dx, r.dy, r.dz);
+  const float V = dot3(msub(e1y, s1z, mul_rn(e1z, s1y)), msub(e1z, s1x, mul_rn(e1x, s1z)), msub(e1x, s1y, mul_rn(e1y, s1x)),
+                       r.dx, r.dy, r.dz);
+  const float W = dot3(msub(e2y, s2z, mul_rn(e2z, s2y)), msub(e2z, s2x, mul_rn(e2x, s2z)), msub(e2x, s2y, mul_rn(e2y, s2x)),
+                       r.dx, r.dy, r.dz);
+  const float UVW = add_rn(add_rn(U, V), W);
+  const float eps = mul_rn(1.1920929e-07f, fabsf(UVW));
+  const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
+  if (!((mn >= -eps) | (mx <= eps))) return false;
+  float ngx, ngy, ngz;
+  stable_normal(e0x, e0y, e0z, e1x, e1y, e1z, e2x, e2y, e2z, ngx, ngy, ngz);
+  const float d = dot3(ngx, ngy, ngz, r.dx, r.dy, r.dz);
+  const float den = add_rn(d, d);
+  const float T0 = dot3(v0x, v0y, v0z, ngx, ngy, ngz);
+  const float T = add_rn(T0, T0);
+  const float t = mul_rn(rcp_rn(den), T);
+  if (!((r.tnear <= t) & (t <= tfar) & (den != 0.0f))) return false;
+  h.t = t; h.U = U; h.V = V; h.UVW = UVW; h.ngx = ngx; h.ngy = ngy; h.ngz = ngz;
+  return true;
+}
+RT_HD void pluecker_uv(const PlueckerHit& h, float& u, float& v) {   // PlueckerHitM::finalize
+  const float rcpUVW = fabsf(h.UVW) < kMinRcpInput ? 0.0f : rcp_rn(h.UVW);
+  u = fminf(mul_rn(h.U, rcpUVW), 1.0f);
+  v = fminf(mul_rn(h.V, rcpUVW), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Node8 encoding (build side)
 // ------------------------------------------------------------------------------------------------
 struct ChildBox { float lo[3], hi[3]; };
@@ -551,7 +618,7 @@ RT_HD uint32_t node_hitmask(const u32x4& n0, const u32x4& n1, const u32x4& n2, c
 
 // One closest-hit (ANYHIT=false) or any-hit (ANYHIT=true) query.  On a closest hit `hit` is filled and
 // r.tfar shrunk; for any-hit the function returns true as soon as one triangle is accepted.
-template <bool ANYHIT, bool STATS, typename NodeLoad, typename TriLoad>
+template <bool ANYHIT, bool STATS, bool ROBUST, typename NodeLoad, typename TriLoad>
 RT_HD bool traverse(Ray& r, Hit& hit, const NodeLoad& ldn, const TriLoad& ldt, uint32_t root_valid, TravStats* st) {
   if (!root_valid) return false;                                         // empty scene (bvh_intersector1.cpp:39)
   if (ANYHIT && r.tfar < 0.0f) return false;                             // already occluded (:128-129)
@@ -596,6 +663,19 @@ RT_HD bool traverse(Ray& r, Hit& hit, const NodeLoad& ldn, const TriLoad& ldt, u
       const uint32_t ti = tgx + (uint32_t)tb;
       const u32x4 a = ldt(ti, 0), b = ldt(ti, 1), c = ldt(ti, 2);
       if (STATS) st->tris++;
+      if (ROBUST) {     // record holds v0, v1, v2 (Triangle4v); Pluecker test
+        PlueckerHit ph;
+        if (tri_test_pluecker(r, tfar_tri, u2f(a.x), u2f(a.y), u2f(a.z), u2f(b.x), u2f(b.y), u2f(b.z), u2f(c.x), u2f(c.y),
+                              u2f(c.z), ph)) {
+          if ((c.w & r.mask) == 0) continue;
+          if (ANYHIT) return true;
+          hit.t = ph.t; pluecker_uv(ph, hit.u, hit.v);
+          hit.ngx = ph.ngx; hit.ngy = ph.ngy; hit.ngz = ph.ngz;
+          hit.primID = a.w; hit.geomID = b.w;
+          tfar_tri = hit.t; tfar_c = fmaxf(hit.t, 0.0f); found = true;
+        }
+        continue;
+      }
       TriHit th;
       if (tri_test(r, tfar_tri, u2f(a.x), u2f(a.y), u2f(a.z), u2f(b.x), u2f(b.y), u2f(b.z), u2f(c.x), u2f(c.y),
                    u2f(c.z), th)) {

@@ -247,6 +247,7 @@ void commit_scene(SceneImpl* s) {
   // exists for A/B measurements of the two device builders only.
   rtk::BuilderKind kind = (s->quality == RTC_BUILD_QUALITY_LOW) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
   if (const char* e = getenv("RTCB200_BUILDER")) kind = (strcmp(e, "lbvh") == 0) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
+  s->gpu.robust = (s->flags & RTC_SCENE_FLAG_ROBUST) ? 1 : 0;   // scene.cpp:181-188: Triangle4v + Pluecker
   char errmsg[256];
   const int r = rtk::build_scene(s->gpu, descs.data(), (int)descs.size(), kind, 0, errmsg);
   // vertex/index copies are only needed during the build (triangles are baked into the leaf records)
@@ -305,7 +306,7 @@ void check_args(SceneImpl* s, const Args* a, uint32_t& instID, uint32_t& instPri
 rtk::TraceParams make_params(SceneImpl* s, void* rays, const int* valid, unsigned long long n, uint32_t instID,
                              uint32_t instPrimID) {
   rtk::TraceParams p;
-  p.nodes = s->gpu.nodes; p.tris = s->gpu.tris; p.root_valid = s->gpu.root_valid;
+  p.nodes = s->gpu.nodes; p.tris = s->gpu.tris; p.root_valid = s->gpu.root_valid; p.robust = s->gpu.robust;
   p.rays = rays; p.valid = valid; p.n = n; p.instID = instID; p.instPrimID = instPrimID;
   p.stat = s->statCounters ? s->gpu.d_stat : nullptr;
   return p;

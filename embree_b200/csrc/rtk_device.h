@@ -27,6 +27,7 @@ struct SceneGPU {
   TriRec* tris = nullptr;
   uint32_t num_nodes = 0, num_tris = 0;
   uint32_t root_valid = 0;              // 0: empty scene -> queries return immediately
+  int robust = 0;                       // RTC_SCENE_FLAG_ROBUST: leaf records are (v0, v1, v2), Pluecker intersector
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // lower xyz, upper xyz of all valid triangles
   double build_ms = 0, sah_cost = 0;
   uint32_t builder = 0, max_depth = 0;
@@ -51,7 +52,8 @@ struct TraceParams {
   // written when the ray terminates.  May point into a PEER GPU's memory (NVLink): this is how the multi-GPU
   // hit gather is fused into the trace kernel instead of being a separate collective.
   void* compact_out = nullptr;
-  int tri_batch_min = 6, tri_wait_max = 3, refill_min = 4;  // filled by launch_trace from tuning()
+  int tri_batch_min = 6, tri_wait_max = 3, refill_min = 4, use_prefetch = 1;  // filled by launch_trace from tuning()
+  int robust = 0;  // scene built with RTC_SCENE_FLAG_ROBUST: triangle records hold v0,v1,v2, Pluecker test
 };
 // occluded: 0 = closest hit (rtcIntersect*), 1 = any hit (rtcOccluded*); K in {1,4,8,16}
 int launch_trace(const TraceParams& p, int occluded, int K, cudaStream_t stream);

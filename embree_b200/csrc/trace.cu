@@ -116,8 +116,9 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 // node, slab-test its 8 children) for the lanes that want it, and at most one triangle step, batched across the warp;
 // the phases are warp-synchronous so lanes in the same phase execute together instead of serialising through a
 // per-thread while-while loop.  The top stack entry lives in registers; deeper entries in (L1-resident) local memory.
-template <int K, bool OCCLUDED, bool STATS, bool USE_TMA>
+template <int K, bool OCCLUDED, bool STATS, bool ROBUST>
 __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TraceParams p) {
+  const bool USE_TMA = p.use_prefetch != 0;
   using IO = RayIO<K, OCCLUDED>;
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -241,17 +242,29 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
         const uint4* tp = tris + (size_t)ti * 3;
         const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         if (STATS) ++st_tris;
-        TriHit th;
-        if (tri_test(r, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
-                     __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
-                     __uint_as_float(c.z), th) &&
-            (c.w & r.mask) != 0) {
-          found = true;
-          if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }     // any hit terminates the ray
-          else {
-            const float rcpAbsDen = 1.0f / th.absDen;      // finalize(): t,u,v = T,U,V * rcp(absDen)
-            tfar_tri = th.T * rcpAbsDen; hit_u = th.U * rcpAbsDen; hit_v = th.V * rcpAbsDen;
-            hit_tri = ti;
+        if (ROBUST) {   // RTC_SCENE_FLAG_ROBUST: the record holds v0, v1, v2; watertight Pluecker test
+          PlueckerHit ph;
+          if (tri_test_pluecker(r, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
+                                __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
+                                __uint_as_float(c.z), ph) &&
+              (c.w & r.mask) != 0) {
+            found = true;
+            if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
+            else { tfar_tri = ph.t; pluecker_uv(ph, hit_u, hit_v); hit_tri = ti; }
+          }
+        } else {
+          TriHit th;
+          if (tri_test(r, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
+                       __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
+                       __uint_as_float(c.z), th) &&
+              (c.w & r.mask) != 0) {
+            found = true;
+            if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }     // any hit terminates the ray
+            else {
+              const float rcpAbsDen = 1.0f / th.absDen;      // finalize(): t,u,v = T,U,V * rcp(absDen)
+              tfar_tri = th.T * rcpAbsDen; hit_u = th.U * rcpAbsDen; hit_v = th.V * rcpAbsDen;
+              hit_tri = ti;
+            }
           }
         }
       }
@@ -273,13 +286,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
             // Ng = cross(e2, e1) and the ids come from the winning triangle's record (same arithmetic as tri_test)
             const uint4* tp = tris + (size_t)hit_tri * 3;
             const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-            const float e1x = __uint_as_float(b.x), e1y = __uint_as_float(b.y), e1z = __uint_as_float(b.z);
-            const float e2x = __uint_as_float(c.x), e2y = __uint_as_float(c.y), e2z = __uint_as_float(c.z);
             Hit hit;
             hit.t = tfar_tri; hit.u = hit_u; hit.v = hit_v;
-            hit.ngx = msub(e2y, e1z, mul_rn(e2z, e1y));
-            hit.ngy = msub(e2z, e1x, mul_rn(e2x, e1z));
-            hit.ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
+            if (ROBUST) {   // stable_triangle_normal of the origin-relative edges, exactly as in tri_test_pluecker
+              const float v0x = sub_rn(__uint_as_float(a.x), r.ox), v0y = sub_rn(__uint_as_float(a.y), r.oy), v0z = sub_rn(__uint_as_float(a.z), r.oz);
+              const float v1x = sub_rn(__uint_as_float(b.x), r.ox), v1y = sub_rn(__uint_as_float(b.y), r.oy), v1z = sub_rn(__uint_as_float(b.z), r.oz);
+              const float v2x = sub_rn(__uint_as_float(c.x), r.ox), v2y = sub_rn(__uint_as_float(c.y), r.oy), v2z = sub_rn(__uint_as_float(c.z), r.oz);
+              stable_normal(sub_rn(v2x, v0x), sub_rn(v2y, v0y), sub_rn(v2z, v0z), sub_rn(v0x, v1x), sub_rn(v0y, v1y), sub_rn(v0z, v1z),
+                            sub_rn(v1x, v2x), sub_rn(v1y, v2y), sub_rn(v1z, v2z), hit.ngx, hit.ngy, hit.ngz);
+            } else {
+              const float e1x = __uint_as_float(b.x), e1y = __uint_as_float(b.y), e1z = __uint_as_float(b.z);
+              const float e2x = __uint_as_float(c.x), e2y = __uint_as_float(c.y), e2z = __uint_as_float(c.z);
+              hit.ngx = msub(e2y, e1z, mul_rn(e2z, e1y));
+              hit.ngy = msub(e2z, e1x, mul_rn(e2x, e1z));
+              hit.ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
+            }
             hit.primID = a.w; hit.geomID = b.w;
             IO::store_hit(p, ray_index, hit);
             cngx = hit.ngx; cngy = hit.ngy; cngz = hit.ngz; cprim = hit.primID; cgeom = hit.geomID;
@@ -327,12 +348,12 @@ static int launch_k(TraceParams p, cudaStream_t st) {
   const unsigned long long cap = (unsigned long long)g_num_sms * g_tuning.blocks_per_sm;
   const unsigned blocks = (unsigned)(need < cap ? need : cap);
   // tiny launches (single-record API calls read a mapped pinned host record) skip the bulk prefetch
-  const bool tma = p.n >= 1024 && g_tuning.use_tma;
+  p.use_prefetch = (p.n >= 1024 && g_tuning.use_tma) ? 1 : 0;
   if (p.stat) {
-    if (tma) trace_kernel<K, OCCLUDED, true, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
+    if (p.robust) trace_kernel<K, OCCLUDED, true, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
     else trace_kernel<K, OCCLUDED, true, false><<<blocks, TRACE_THREADS, 0, st>>>(p);
   } else {
-    if (tma) trace_kernel<K, OCCLUDED, false, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
+    if (p.robust) trace_kernel<K, OCCLUDED, false, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
     else trace_kernel<K, OCCLUDED, false, false><<<blocks, TRACE_THREADS, 0, st>>>(p);
   }
   count_launch();

@@ -13,8 +13,9 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
-def load_golden(name):
-    """tests/golden/<name>.npz -> (meshes, rays_in, intersect_out, occluded_out, bounds); records as structured arrays."""
+def load_golden(name, robust=False):
+    """tests/golden/<name>.npz -> (meshes, rays_in, intersect_out, occluded_out, bounds); records as structured arrays.
+    robust=True returns the reference's outputs for the same scene committed with RTC_SCENE_FLAG_ROBUST."""
     from embree_b200.rtc import RAYHIT_DTYPE, RAY_DTYPE, aligned_empty
     z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     meshes = [(z[f"v{i}"], z[f"t{i}"], int(z[f"gid{i}"]), int(z[f"mask{i}"])) for i in range(int(z["n_meshes"]))]
@@ -23,7 +24,9 @@ def load_golden(name):
         out = aligned_empty(a.shape[0], dt)
         out.view(np.uint8).reshape(a.shape)[:] = a
         return out
-    return meshes, rec(z["rays_in"], RAYHIT_DTYPE), rec(z["intersect_out"], RAYHIT_DTYPE), rec(z["occluded_out"], RAY_DTYPE), z["bounds"]
+    sfx = "_robust" if robust else ""
+    return (meshes, rec(z["rays_in"], RAYHIT_DTYPE), rec(z["intersect_out" + sfx], RAYHIT_DTYPE),
+            rec(z["occluded_out" + sfx], RAY_DTYPE), z["bounds"])
 
 
 GOLDEN = ["cube_ground", "sphere21", "terrain_masks"]

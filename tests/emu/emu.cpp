@@ -21,6 +21,7 @@ struct EmuScene {
   std::vector<Node8> nodes;
   std::vector<TriRec> tris;
   uint32_t root_valid = 0;
+  int robust = 0;
   uint32_t depth = 0;
   double sah = 0;
 };
@@ -50,6 +51,8 @@ extern "C" {
 // vertices: float[nverts][3] (stride 12), indices: uint32[ntris][3]; mode = collapse policy (0, 1, 2 greedy variants; 3 = SAH-optimal DP)
 void* emu_build(const float* verts, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint32_t geomID, uint32_t mask, int mode) {
   EmuScene* sc = new EmuScene();
+  sc->robust = (mode & 0x100) ? 1 : 0;   // bit 8 of `mode`: RTC_SCENE_FLAG_ROBUST (records keep v0,v1,v2)
+  mode &= 0xFF;
   std::vector<PrimRef> prims;
   float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
   float glo[3] = {INFINITY, INFINITY, INFINITY}, ghi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -167,8 +170,12 @@ void* emu_build(const float* verts, uint32_t nverts, const uint32_t* idx, uint32
     const float* c = verts + 3 * (size_t)idx[3 * p + 2];
     TriRec& r = sc->tris[t];
     r.v0x = a[0]; r.v0y = a[1]; r.v0z = a[2]; r.primID = p;
-    r.e1x = sub_rn(a[0], b[0]); r.e1y = sub_rn(a[1], b[1]); r.e1z = sub_rn(a[2], b[2]); r.geomID = geomID;
-    r.e2x = sub_rn(c[0], a[0]); r.e2y = sub_rn(c[1], a[1]); r.e2z = sub_rn(c[2], a[2]); r.mask = mask;
+    if (sc->robust) { r.e1x = b[0]; r.e1y = b[1]; r.e1z = b[2]; r.e2x = c[0]; r.e2y = c[1]; r.e2z = c[2]; }
+    else {
+      r.e1x = sub_rn(a[0], b[0]); r.e1y = sub_rn(a[1], b[1]); r.e1z = sub_rn(a[2], b[2]);
+      r.e2x = sub_rn(c[0], a[0]); r.e2y = sub_rn(c[1], a[1]); r.e2z = sub_rn(c[2], a[2]);
+    }
+    r.geomID = geomID; r.mask = mask;
   }
   sc->root_valid = (tri_tail == n) ? 1 : 0;
   return sc;
@@ -194,8 +201,10 @@ void emu_trace(void* h, void* rays, uint64_t n, int occluded, uint64_t* stats) {
     Hit hit;
     TravStats st{0, 0};
     bool found;
-    if (occluded) found = traverse<true, true>(r, hit, ldn, ldt, sc->root_valid, &st);
-    else found = traverse<false, true>(r, hit, ldn, ldt, sc->root_valid, &st);
+    if (sc->robust) found = occluded ? traverse<true, true, true>(r, hit, ldn, ldt, sc->root_valid, &st)
+                                     : traverse<false, true, true>(r, hit, ldn, ldt, sc->root_valid, &st);
+    else found = occluded ? traverse<true, true, false>(r, hit, ldn, ldt, sc->root_valid, &st)
+                          : traverse<false, true, false>(r, hit, ldn, ldt, sc->root_valid, &st);
     if (stats) { stats[0] += st.nodes; stats[1] += st.tris; }
     if (!found) continue;
     if (occluded) { float ninf = -INFINITY; memcpy(rec + 32, &ninf, 4); continue; }

@@ -31,9 +31,18 @@ def random_rays_box(n, lo, hi, seed):
 
 
 def run(name, meshes, rayhits):
+    d = run_flags(name, meshes, rayhits, 0)
+    r = run_flags(name, meshes, rayhits, 4)   # RTC_SCENE_FLAG_ROBUST: Triangle4v + Pluecker (scene.cpp:181-188)
+    d["intersect_out_robust"], d["occluded_out_robust"] = r["intersect_out"], r["occluded_out"]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+
+
+def run_flags(name, meshes, rayhits, flags):
     R = load_reference()
     dev = R.new_device(None)
     sc = R.rtcNewScene(dev)
+    if flags:
+        R.rtcSetSceneFlags(sc, flags)
     keep = []
     for (v, t, gid, mask) in meshes:
         _, k = R.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)
@@ -54,11 +63,11 @@ def run(name, meshes, rayhits):
              n_meshes=np.array(len(meshes)))
     for i, (v, t, gid, mask) in enumerate(meshes):
         d[f"v{i}"], d[f"t{i}"], d[f"gid{i}"], d[f"mask{i}"] = v, t, np.array(gid, np.uint32), np.array(mask, np.uint32)
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
     hits = (out_i["geomID"] != 0xFFFFFFFF).mean()
-    print(f"{name}: {len(rayhits)} rays, hit rate {hits:.3f}, occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
+    print(f"{name} flags={flags}: {len(rayhits)} rays, hit rate {hits:.3f}, occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
     R.rtcReleaseScene(sc)
     R.rtcReleaseDevice(dev)
+    return d
 
 
 def main():

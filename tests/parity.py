@@ -22,6 +22,7 @@ class Oracle:
         d.orc_free.argtypes = [C.c_void_p]
         d.orc_add_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint]
         d.orc_commit.argtypes = [C.c_void_p]
+        d.orc_set_robust.argtypes = [C.c_void_p, C.c_int]
         d.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
         d.orc_get_bounds.argtypes = [C.c_void_p, C.c_void_p]
         d.orc_get_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -29,9 +30,9 @@ class Oracle:
         d.orc_api_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_uint, C.c_int]
         self.d = d
 
-    def scene(self, meshes):
+    def scene(self, meshes, robust=False):
         """meshes: list of (vertices[nv,3] f32, indices[nt,3] u32, geomID, mask).  Returns an OracleScene."""
-        return OracleScene(self, meshes)
+        return OracleScene(self, meshes, robust)
 
     def trace(self, v, t, rayhits, occluded=False, mask=0xFFFFFFFF, nthreads=1):
         sc = self.scene([(v, t, 0, mask)])
@@ -41,9 +42,10 @@ class Oracle:
 
 
 class OracleScene:
-    def __init__(self, o, meshes):
+    def __init__(self, o, meshes, robust=False):
         self.o = o
         self.h = o.d.orc_new()
+        o.d.orc_set_robust(self.h, 1 if robust else 0)
         self.keep = []
         for (v, t, gid, mask) in meshes:
             v = np.ascontiguousarray(v, np.float32).reshape(-1, 3)

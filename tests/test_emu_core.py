@@ -13,10 +13,10 @@ from tests.conftest import GOLDEN, load_golden
 from tests.parity import compare_hits
 
 
-def _emu_trace(emu, v, t, rays, occluded=False, mask=0xFFFFFFFF):
+def _emu_trace(emu, v, t, rays, occluded=False, mask=0xFFFFFFFF, policy=3, robust=False):
     v = np.ascontiguousarray(v, np.float32)
     t = np.ascontiguousarray(t, np.uint32)
-    h = emu.emu_build(v.ctypes.data, len(v), t.ctypes.data, len(t), 0, mask, 0)
+    h = emu.emu_build(v.ctypes.data, len(v), t.ctypes.data, len(t), 0, mask, policy | (0x100 if robust else 0))
     stats = np.zeros(2, np.uint64)
     emu.emu_trace(h, rays.ctypes.data, len(rays), 1 if occluded else 0, stats.ctypes.data)
     info = dict(nodes=emu.emu_num_nodes(h), depth=emu.emu_depth(h), trav_nodes=int(stats[0]), trav_tris=int(stats[1]))
@@ -38,12 +38,25 @@ def test_sphere_matches_oracle(emu, oracle, num_phi):
     assert (wo["tfar"].view(np.uint32) == go["tfar"].view(np.uint32)).all()
 
 
-def test_golden_single_mesh(emu):
-    meshes, rin, want_i, want_o, _ = load_golden("sphere21")
+@pytest.mark.parametrize("robust", [False, True])
+@pytest.mark.parametrize("policy", [0, 3])
+def test_golden_single_mesh(emu, policy, robust):
+    """Both collapse policies (greedy / SAH-optimal DP) and both intersectors (Moeller-Trumbore / robust Pluecker)."""
+    meshes, rin, want_i, want_o, _ = load_golden("sphere21", robust)
     (v, t, gid, mask) = meshes[0]
-    got, _ = _emu_trace(emu, v, t, rin.copy(), mask=mask)
+    got, _ = _emu_trace(emu, v, t, rin.copy(), mask=mask, policy=policy, robust=robust)
     rep = compare_hits(want_i, got)
     assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["max_rel_t"] <= 1e-4 and rep["ng_bit_exact"], rep
+    go, _ = _emu_trace(emu, v, t, rays_of(rin), occluded=True, mask=mask, policy=policy, robust=robust)
+    assert (go["tfar"].view(np.uint32) == want_o["tfar"].view(np.uint32)).all()
+
+
+def test_robust_is_watertight(emu):
+    """RTC_SCENE_FLAG_ROBUST: the Pluecker edge tests are watertight -- no ray from inside a closed mesh escapes."""
+    v, t = scenes.triangle_sphere(50)
+    rays = scenes.as_numpy_rayhits(scenes.incoherent_rays_reference(100000, org=(0.1, -0.2, 0.05)))
+    got, _ = _emu_trace(emu, v, t, rays, robust=True)
+    assert (got["geomID"] == 0).all()
 
 
 def test_tiny_scenes(emu, oracle):

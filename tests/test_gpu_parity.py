@@ -43,12 +43,14 @@ def assert_parity(want, got, allow_ties=0):
     return rep
 
 
+@pytest.mark.parametrize("robust", [False, True])
 @pytest.mark.parametrize("quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
 @pytest.mark.parametrize("name", GOLDEN)
-def test_golden_all_entry_points(b200, name, quality):
+def test_golden_all_entry_points(b200, name, quality, robust):
+    """robust=True: RTC_SCENE_FLAG_ROBUST (Triangle4v + Pluecker in the reference, scene.cpp:181-188)."""
     lib, dev = b200
-    meshes, rin, want_i, want_o, bounds = load_golden(name)
-    sc, keep = build_scene(lib, dev, meshes, quality)
+    meshes, rin, want_i, want_o, bounds = load_golden(name, robust)
+    sc, keep = build_scene(lib, dev, meshes, quality, flags=4 if robust else 0)
     for mode in MODES:
         got = lib.intersect(sc, rin.copy(), mode)
         rep = assert_parity(want_i, got)
@@ -326,6 +328,35 @@ def test_watertight_and_reference_side_by_side(b200, oracle, quality):
         rep = compare_hits(ref[both], got[both], TOL)
         assert rep["id_mismatch"] == 0 and rep["tie"] <= 2 and rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= TOL, rep
         assert (~both).mean() <= 2e-5
+        R.rtcReleaseScene(rs)
+        R.rtcReleaseDevice(rd)
+    lib.rtcReleaseScene(sc)
+
+
+def test_robust_watertight_and_reference(b200, oracle):
+    """RTC_SCENE_FLAG_ROBUST at scale: no leaks at all from inside a closed 160 k-triangle sphere, ids equal to the
+    oracle's (and the reference's, when present) Pluecker path for 400 k rays."""
+    lib, dev = b200
+    v, t = scenes.triangle_sphere(201)
+    sc, keep = build_scene(lib, dev, [(v, t, 0, 0xFFFFFFFF)], RTC_BUILD_QUALITY_MEDIUM, flags=4)
+    rays = scenes.as_numpy_rayhits(scenes.incoherent_rays_reference(400000, org=(0.05, -0.1, 0.02)))
+    got = lib.intersect(sc, rays.copy(), "1M")
+    assert (got["geomID"] == 0).all()
+    want = oracle.scene([(v, t, 0, 0xFFFFFFFF)], robust=True).trace(rays.copy(), nthreads=8)
+    rep = assert_parity(want, got, allow_ties=4)
+    assert rep["ng_bit_exact"]
+    occ = lib.occluded(sc, rays_of(rays), "1M")
+    assert (occ["tfar"] == -np.inf).all()
+    R = load_reference()
+    if R is not None:
+        from tests.parity import api_trace_mt
+        rd = R.new_device(None)
+        rs = R.rtcNewScene(rd)
+        R.rtcSetSceneFlags(rs, 4)
+        _, k2 = R.add_triangle_mesh(rd, rs, v, t, mask=0xFFFFFFFF)
+        R.rtcCommitScene(rs)
+        ref = api_trace_mt(R, rs, rays.copy(), 16)
+        assert_parity(ref, got, allow_ties=4)
         R.rtcReleaseScene(rs)
         R.rtcReleaseDevice(rd)
     lib.rtcReleaseScene(sc)

@@ -38,10 +38,11 @@ def test_minimal_tutorial_kat(oracle):
     assert out["geomID"][1] == 0xFFFFFFFF and np.isinf(out["tfar"][1])
 
 
+@pytest.mark.parametrize("robust", [False, True])
 @pytest.mark.parametrize("name", GOLDEN)
-def test_oracle_vs_golden(oracle, name):
-    meshes, rin, want_i, want_o, bounds = load_golden(name)
-    sc = oracle.scene(meshes)
+def test_oracle_vs_golden(oracle, name, robust):
+    meshes, rin, want_i, want_o, bounds = load_golden(name, robust)
+    sc = oracle.scene(meshes, robust=robust)
     got = sc.trace(rin.copy())
     rep = compare_hits(want_i, got)
     assert rep["id_mismatch"] == 0 and rep["tie"] == 0 and rep["hit_miss_disagree"] == 0, rep
