@@ -183,7 +183,7 @@ template <int NT, int GROUPS, uint32_t CAP>
 __global__ void __launch_bounds__(NT* GROUPS) sah_group_kernel(const SahTask* __restrict__ tasks, uint32_t ntasks,
                                                                const PrimRef* __restrict__ prims, uint32_t* idsA, uint32_t* idsB,
                                                                Node2* nodes, uint32_t n, SahCounters* ctr, SahTask* out_large,
-                                                               SahTask* out_block, SahTask* out_warp) {
+                                                               SahTask* out_block, SahTask* out_warp, uint32_t small_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int group = threadIdx.x / NT, tid = threadIdx.x % NT, lane = threadIdx.x & 31, gwarp = tid >> 5;
   GroupSmem* gs = reinterpret_cast<GroupSmem*>(smem_raw) + group;
@@ -194,6 +194,45 @@ __global__ void __launch_bounds__(NT* GROUPS) sah_group_kernel(const SahTask* __
     const SahTask t = tasks[ti];
     uint32_t* ids = t.buf ? idsB : idsA;
     const uint32_t count = t.end - t.begin;
+    // ---- tiny segments (warp groups only): split in the middle of the (still Morton-ordered: the partitions are
+    // stable) segment instead of binning.  7/8 of all split tasks of a build are at the last three levels; a full
+    // 3 x 32-bin sweep for 2..8 primitives costs ~3000 warp instructions and decides almost nothing.
+    if (NT == 32 && count <= small_max) {
+      const uint32_t nl = count / 2;
+      float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+      const bool in = (uint32_t)lane < count, left = (uint32_t)lane < nl;
+      if (in) {
+        const uint32_t id = ids[t.begin + lane];
+        const float4 plo = __ldg(reinterpret_cast<const float4*>(&prims[id]));
+        const float4 phi = __ldg(reinterpret_cast<const float4*>(&prims[id]) + 1);
+        lo[0] = plo.x; lo[1] = plo.y; lo[2] = plo.z; hi[0] = phi.x; hi[1] = phi.y; hi[2] = phi.z;
+      }
+      float lb[6], rb[6], lcl[3], lch[3], rcl[3], rch[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float c = lo[k] + hi[k];
+        float a0 = (in && left) ? lo[k] : INFINITY, a1 = (in && left) ? hi[k] : -INFINITY;
+        float b0 = (in && !left) ? lo[k] : INFINITY, b1 = (in && !left) ? hi[k] : -INFINITY;
+        float c0 = (in && left) ? c : INFINITY, c1 = (in && left) ? c : -INFINITY;
+        float d0 = (in && !left) ? c : INFINITY, d1 = (in && !left) ? c : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a0 = fminf(a0, __shfl_xor_sync(0xFFFFFFFFu, a0, o)); a1 = fmaxf(a1, __shfl_xor_sync(0xFFFFFFFFu, a1, o));
+          b0 = fminf(b0, __shfl_xor_sync(0xFFFFFFFFu, b0, o)); b1 = fmaxf(b1, __shfl_xor_sync(0xFFFFFFFFu, b1, o));
+          c0 = fminf(c0, __shfl_xor_sync(0xFFFFFFFFu, c0, o)); c1 = fmaxf(c1, __shfl_xor_sync(0xFFFFFFFFu, c1, o));
+          d0 = fminf(d0, __shfl_xor_sync(0xFFFFFFFFu, d0, o)); d1 = fmaxf(d1, __shfl_xor_sync(0xFFFFFFFFu, d1, o));
+        }
+        lb[k] = a0; lb[3 + k] = a1; rb[k] = b0; rb[3 + k] = b1; lcl[k] = c0; lch[k] = c1; rcl[k] = d0; rch[k] = d1;
+      }
+      if (lane == 0) {
+        const uint32_t l = emit_child(nodes, n, t.node, t.begin, t.begin + nl, t.buf, lb, lcl, lch, ctr, out_large, out_block, out_warp);
+        const uint32_t r = emit_child(nodes, n, t.node, t.begin + nl, t.end, t.buf, rb, rcl, rch, ctr, out_large, out_block, out_warp);
+        nodes[t.node].left = (int32_t)l;
+        nodes[t.node].right = (int32_t)r;
+      }
+      __syncwarp();
+      continue;
+    }
     const BinMap map = make_map(t.clo, t.chi);
     // ---- clear bins
     for (int i = tid; i < 3 * kBins; i += NT) {
@@ -630,13 +669,13 @@ int build_sah_tree(const PrimRef* prims, uint32_t* idsA, uint32_t* idsB, uint32_
     if (nB) {
       const uint32_t grid = std::min<uint32_t>(nB, (uint32_t)sms * 8);
       sah_group_kernel<BLOCK_NT, 1, kBlockCap><<<grid, BLOCK_NT, smem_block, st>>>(in[1], nB, prims, idsA, idsB, nodes, n, d_ctr,
-                                                                                  out[0], out[1], out[2]);
+                                                                                  out[0], out[1], out[2], 0u);
       count_launch();
     }
     if (nW) {
       const uint32_t grid = std::min<uint32_t>((nW + WARP_GROUPS - 1) / WARP_GROUPS, (uint32_t)sms * 32);
       sah_group_kernel<32, WARP_GROUPS, kWarpCap><<<grid, 32 * WARP_GROUPS, smem_warp, st>>>(in[2], nW, prims, idsA, idsB, nodes, n,
-                                                                                             d_ctr, out[0], out[1], out[2]);
+                                                                                             d_ctr, out[0], out[1], out[2], (uint32_t)tuning().sah_small);
       count_launch();
     }
     CKC(cudaGetLastError());

@@ -834,6 +834,7 @@ int rtcb200SetTuning(const char* key, int value) {
   rtk::Tuning& t = rtk::tuning();
   if (!strcmp(key, "collapse_policy")) t.collapse_policy = value;
   else if (!strcmp(key, "refill_min")) t.refill_min = value;
+  else if (!strcmp(key, "sah_small")) t.sah_small = value;
   else if (!strcmp(key, "c_node")) t.c_node = value;
   else if (!strcmp(key, "c_tri")) t.c_tri = value;
   else if (!strcmp(key, "tri_batch_min")) t.tri_batch_min = value;

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
   uint32_t ray_index = 0;
   uint32_t ngx = 0, ngy = 0, tgx = 0, tgy = 0;
   uint32_t top_x = 0, top_y = 0;          // top of the traversal stack (top_y == 0: stack empty)
-  uint32_t stack_x[kStackSize], stack_y[kStackSize];
+  uint2 stack[kStackSize];                // deeper entries: one 8-byte local-memory slot each (L1-resident)
   int sp = 0;
   // warp-uniform block cursor
   int blk = -1;                           // index into this warp's block sequence
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
       const int bit = 31 - __clz((int)ngy);
       ngy &= ~(1u << bit);
       if (ngy & 0xFF000000u) {           // push the rest of the group
-        if (top_y) { stack_x[sp] = top_x; stack_y[sp] = top_y; ++sp; }
+        if (top_y) { stack[sp] = make_uint2(top_x, top_y); ++sp; }
         top_x = ngx; top_y = ngy;
       }
       const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
     if (active && tgy == 0 && (ngy & 0xFF000000u) == 0) {
       if (top_y) {
         const uint32_t px = top_x, py = top_y;
-        if (sp > 0) { --sp; top_x = stack_x[sp]; top_y = stack_y[sp]; }   // next entry loads while this one is used
+        if (sp > 0) { --sp; const uint2 e = stack[sp]; top_x = e.x; top_y = e.y; }   // loads while the popped one is used
         else top_y = 0;
         if (py & 0xFF000000u) { ngx = px; ngy = py; }
         else { tgx = px; tgy = py; ngx = 0; ngy = 0; }

@@ -31,6 +31,7 @@ A = None
 policies = [x for x in os.environ.get("POLICIES", "0,3,3:20,3:50,3:80").split(",")]
 for pol_s in policies:
     pol = int(pol_s.split(":")[0])
+    lib.rtcb200SetTuning(b"sah_small", int(pol_s.split(":")[2]) if pol_s.count(":") > 1 else 8)
     lib.rtcb200SetTuning(b"collapse_policy", pol)
     lib.rtcb200SetTuning(b"c_tri", int(pol_s.split(":")[1]) if ":" in pol_s else 30)
     sc = lib.rtcNewScene(dev)
