@@ -194,19 +194,34 @@ __global__ void __launch_bounds__(NT* GROUPS) sah_group_kernel(const SahTask* __
     const SahTask t = tasks[ti];
     uint32_t* ids = t.buf ? idsB : idsA;
     const uint32_t count = t.end - t.begin;
-    // ---- tiny segments (warp groups only): split in the middle of the (still Morton-ordered: the partitions are
-    // stable) segment instead of binning.  7/8 of all split tasks of a build are at the last three levels; a full
-    // 3 x 32-bin sweep for 2..8 primitives costs ~3000 warp instructions and decides almost nothing.
+    // ---- tiny segments (warp groups only): no binning.  7/8 of all split tasks of a build are at the last three
+    // levels; a full 3 x 32-bin sweep for 2..4 primitives costs ~3000 warp instructions and decides almost nothing.
     if (NT == 32 && count <= small_max) {
+      // object-median split along the longest centroid axis.  The lanes first put the segment into a canonical order
+      // (centre along that axis, primitive id as tie-break), so the result depends only on the SET of primitives --
+      // the LARGE-phase partition reserves ranges with atomics and leaves the order inside a segment run-dependent.
       const uint32_t nl = count / 2;
+      const bool in = (uint32_t)lane < count;
       float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-      const bool in = (uint32_t)lane < count, left = (uint32_t)lane < nl;
+      uint32_t id = 0xFFFFFFFFu;
       if (in) {
-        const uint32_t id = ids[t.begin + lane];
+        id = ids[t.begin + lane];
         const float4 plo = __ldg(reinterpret_cast<const float4*>(&prims[id]));
         const float4 phi = __ldg(reinterpret_cast<const float4*>(&prims[id]) + 1);
         lo[0] = plo.x; lo[1] = plo.y; lo[2] = plo.z; hi[0] = phi.x; hi[1] = phi.y; hi[2] = phi.z;
       }
+      const float ex = t.chi[0] - t.clo[0], ey = t.chi[1] - t.clo[1], ez = t.chi[2] - t.clo[2];
+      const int ax = (ex >= ey && ex >= ez) ? 0 : (ey >= ez ? 1 : 2);
+      const float key = in ? (ax == 0 ? lo[0] + hi[0] : (ax == 1 ? lo[1] + hi[1] : lo[2] + hi[2])) : INFINITY;
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < count; ++j) {
+        const float kj = __shfl_sync(0xFFFFFFFFu, key, (int)j);
+        const uint32_t ij = __shfl_sync(0xFFFFFFFFu, id, (int)j);
+        if (kj < key || (kj == key && ij < id)) ++rank;
+      }
+      __syncwarp();
+      if (in) ids[t.begin + rank] = id;
+      const bool left = in && rank < nl;
       float lb[6], rb[6], lcl[3], lch[3], rcl[3], rch[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -224,6 +239,7 @@ __global__ void __launch_bounds__(NT* GROUPS) sah_group_kernel(const SahTask* __
         }
         lb[k] = a0; lb[3 + k] = a1; rb[k] = b0; rb[3 + k] = b1; lcl[k] = c0; lch[k] = c1; rcl[k] = d0; rch[k] = d1;
       }
+      __syncwarp();
       if (lane == 0) {
         const uint32_t l = emit_child(nodes, n, t.node, t.begin, t.begin + nl, t.buf, lb, lcl, lch, ctr, out_large, out_block, out_warp);
         const uint32_t r = emit_child(nodes, n, t.node, t.begin + nl, t.end, t.buf, rb, rcl, rch, ctr, out_large, out_block, out_warp);
