@@ -857,4 +857,103 @@ double rtcb200GetLastTraceMs(RTCScene sc) {
   return -1.0;
 }
 
+// ---- entry points of the reference that are thin variants of supported ones -----------------------------------------
+void* rtcGetGeometryBufferDataDevice(RTCGeometry g, enum RTCBufferType type, unsigned int slot) { return rtcGetGeometryBufferData(g, type, slot); }
+void rtcSetSharedGeometryBufferHostDevice(RTCGeometry g, enum RTCBufferType type, unsigned int slot, enum RTCFormat format, const void* ptr,
+                                          const void* /*dptr*/, size_t off, size_t stride, size_t num) {
+  rtcSetSharedGeometryBuffer(g, type, slot, format, ptr, off, stride, num);   // buffers are uploaded at commit; the host copy is the source
+}
+void rtcSetNewGeometryBufferHostDevice(RTCGeometry g, enum RTCBufferType type, unsigned int slot, enum RTCFormat format, size_t stride,
+                                       size_t num, void** ptr, void** dptr) {
+  void* p = rtcSetNewGeometryBuffer(g, type, slot, format, stride, num);
+  if (ptr) *ptr = p;
+  if (dptr) *dptr = p;
+}
+void* rtcGetGeometryUserDataFromTraversable(RTCTraversable t, unsigned int id) { return rtcGetGeometryUserDataFromScene(reinterpret_cast<RTCScene>(t), id); }
+void rtcSetGeometryTimeRange(RTCGeometry g, float, float) { GEOM_BEGIN(g) G(g)->update(); GEOM_END }          // one time step only
+void rtcSetGeometryMaxRadiusScale(RTCGeometry g, float) { GEOM_BEGIN(g) G(g)->update(); GEOM_END }            // curves/points only
+
+// ---- everything else the reference library exports (other geometry types, user callbacks, point queries, rtcBuildBVH,
+// instancing, interpolation): exported so that ANY Embree 4 caller links against this library; each call records
+// RTC_ERROR_INVALID_OPERATION (thread error slot, read with rtcGetDeviceError(NULL)) and returns 0 / NULL / false.
+#define RTCB200_UNSUPPORTED(name)                                                                              \
+  void* name(void) {                                                                                           \
+    process_error(nullptr, RTC_ERROR_INVALID_OPERATION, #name " is not supported by the B200 triangle back-end"); \
+    return nullptr;                                                                                            \
+  }
+RTCB200_UNSUPPORTED(rtcBuildBVH)
+RTCB200_UNSUPPORTED(rtcCollide)
+RTCB200_UNSUPPORTED(rtcForwardIntersect1)
+RTCB200_UNSUPPORTED(rtcForwardIntersect16)
+RTCB200_UNSUPPORTED(rtcForwardIntersect16Ex)
+RTCB200_UNSUPPORTED(rtcForwardIntersect1Ex)
+RTCB200_UNSUPPORTED(rtcForwardIntersect4)
+RTCB200_UNSUPPORTED(rtcForwardIntersect4Ex)
+RTCB200_UNSUPPORTED(rtcForwardIntersect8)
+RTCB200_UNSUPPORTED(rtcForwardIntersect8Ex)
+RTCB200_UNSUPPORTED(rtcForwardOccluded1)
+RTCB200_UNSUPPORTED(rtcForwardOccluded16)
+RTCB200_UNSUPPORTED(rtcForwardOccluded16Ex)
+RTCB200_UNSUPPORTED(rtcForwardOccluded1Ex)
+RTCB200_UNSUPPORTED(rtcForwardOccluded4)
+RTCB200_UNSUPPORTED(rtcForwardOccluded4Ex)
+RTCB200_UNSUPPORTED(rtcForwardOccluded8)
+RTCB200_UNSUPPORTED(rtcForwardOccluded8Ex)
+RTCB200_UNSUPPORTED(rtcGetGeometryFace)
+RTCB200_UNSUPPORTED(rtcGetGeometryFirstHalfEdge)
+RTCB200_UNSUPPORTED(rtcGetGeometryNextHalfEdge)
+RTCB200_UNSUPPORTED(rtcGetGeometryOppositeHalfEdge)
+RTCB200_UNSUPPORTED(rtcGetGeometryPreviousHalfEdge)
+RTCB200_UNSUPPORTED(rtcGetGeometryTransform)
+RTCB200_UNSUPPORTED(rtcGetGeometryTransformEx)
+RTCB200_UNSUPPORTED(rtcGetGeometryTransformFromScene)
+RTCB200_UNSUPPORTED(rtcGetGeometryTransformFromTraversable)
+RTCB200_UNSUPPORTED(rtcInterpolate)
+RTCB200_UNSUPPORTED(rtcInterpolateN)
+RTCB200_UNSUPPORTED(rtcInvokeIntersectFilterFromGeometry)
+RTCB200_UNSUPPORTED(rtcInvokeOccludedFilterFromGeometry)
+RTCB200_UNSUPPORTED(rtcMakeStaticBVH)
+RTCB200_UNSUPPORTED(rtcNewBVH)
+RTCB200_UNSUPPORTED(rtcPointQuery)
+RTCB200_UNSUPPORTED(rtcPointQuery16)
+RTCB200_UNSUPPORTED(rtcPointQuery4)
+RTCB200_UNSUPPORTED(rtcPointQuery8)
+RTCB200_UNSUPPORTED(rtcReleaseBVH)
+RTCB200_UNSUPPORTED(rtcRetainBVH)
+RTCB200_UNSUPPORTED(rtcSetGeometryBoundsFunction)
+RTCB200_UNSUPPORTED(rtcSetGeometryDisplacementFunction)
+RTCB200_UNSUPPORTED(rtcSetGeometryInstancedScene)
+RTCB200_UNSUPPORTED(rtcSetGeometryInstancedScenes)
+RTCB200_UNSUPPORTED(rtcSetGeometryIntersectFunction)
+RTCB200_UNSUPPORTED(rtcSetGeometryOccludedFunction)
+RTCB200_UNSUPPORTED(rtcSetGeometryPointQueryFunction)
+RTCB200_UNSUPPORTED(rtcSetGeometrySubdivisionMode)
+RTCB200_UNSUPPORTED(rtcSetGeometryTessellationRate)
+RTCB200_UNSUPPORTED(rtcSetGeometryTopologyCount)
+RTCB200_UNSUPPORTED(rtcSetGeometryTransform)
+RTCB200_UNSUPPORTED(rtcSetGeometryTransformQuaternion)
+RTCB200_UNSUPPORTED(rtcSetGeometryUserPrimitiveCount)
+RTCB200_UNSUPPORTED(rtcSetGeometryVertexAttributeTopology)
+RTCB200_UNSUPPORTED(rtcThreadLocalAlloc)
+RTCB200_UNSUPPORTED(rtcTraversableForwardIntersect1)
+RTCB200_UNSUPPORTED(rtcTraversableForwardIntersect16)
+RTCB200_UNSUPPORTED(rtcTraversableForwardIntersect16Ex)
+RTCB200_UNSUPPORTED(rtcTraversableForwardIntersect1Ex)
+RTCB200_UNSUPPORTED(rtcTraversableForwardIntersect4)
+RTCB200_UNSUPPORTED(rtcTraversableForwardIntersect4Ex)
+RTCB200_UNSUPPORTED(rtcTraversableForwardIntersect8)
+RTCB200_UNSUPPORTED(rtcTraversableForwardIntersect8Ex)
+RTCB200_UNSUPPORTED(rtcTraversableForwardOccluded1)
+RTCB200_UNSUPPORTED(rtcTraversableForwardOccluded16)
+RTCB200_UNSUPPORTED(rtcTraversableForwardOccluded16Ex)
+RTCB200_UNSUPPORTED(rtcTraversableForwardOccluded1Ex)
+RTCB200_UNSUPPORTED(rtcTraversableForwardOccluded4)
+RTCB200_UNSUPPORTED(rtcTraversableForwardOccluded4Ex)
+RTCB200_UNSUPPORTED(rtcTraversableForwardOccluded8)
+RTCB200_UNSUPPORTED(rtcTraversableForwardOccluded8Ex)
+RTCB200_UNSUPPORTED(rtcTraversablePointQuery)
+RTCB200_UNSUPPORTED(rtcTraversablePointQuery16)
+RTCB200_UNSUPPORTED(rtcTraversablePointQuery4)
+RTCB200_UNSUPPORTED(rtcTraversablePointQuery8)
+
 }  // extern "C"

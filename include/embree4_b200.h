@@ -328,6 +328,97 @@ RTCB200_API int rtcb200SetTuning(const char* key, int value);
 /* device time (ms) of the most recent batched Device trace launch, measured with events on its stream; -1 if none */
 RTCB200_API double rtcb200GetLastTraceMs(RTCScene scene);
 
+/* =====================================================================================================
+ * Section C -- the rest of the reference library's export list (kernels/export.linux.map: every rtc* symbol).
+ * Thin variants of supported calls are implemented; the others (geometry types other than triangles, host
+ * callbacks, point queries, rtcBuildBVH, instancing, interpolation) exist so that any Embree 4 caller LINKS
+ * unchanged: calling one records RTC_ERROR_INVALID_OPERATION in the thread error slot and returns 0/NULL/false.
+ * They are declared without prototypes on purpose -- compile callers against the reference's own headers.
+ * ===================================================================================================== */
+RTCB200_API void* rtcGetGeometryBufferDataDevice(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot);
+RTCB200_API void rtcSetSharedGeometryBufferHostDevice(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot, enum RTCFormat format,
+                                                      const void* ptr, const void* dptr, size_t byteOffset, size_t byteStride, size_t itemCount);
+RTCB200_API void rtcSetNewGeometryBufferHostDevice(RTCGeometry geometry, enum RTCBufferType type, unsigned int slot, enum RTCFormat format,
+                                                   size_t byteStride, size_t itemCount, void** ptr, void** dptr);
+RTCB200_API void* rtcGetGeometryUserDataFromTraversable(RTCTraversable traversable, unsigned int geomID);
+RTCB200_API void rtcSetGeometryTimeRange(RTCGeometry geometry, float startTime, float endTime);
+RTCB200_API void rtcSetGeometryMaxRadiusScale(RTCGeometry geometry, float maxRadiusScale);
+#define RTCB200_DECLARE_UNSUPPORTED(name) RTCB200_API void* name(void);
+RTCB200_DECLARE_UNSUPPORTED(rtcBuildBVH)
+RTCB200_DECLARE_UNSUPPORTED(rtcCollide)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardIntersect1)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardIntersect16)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardIntersect16Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardIntersect1Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardIntersect4)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardIntersect4Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardIntersect8)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardIntersect8Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardOccluded1)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardOccluded16)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardOccluded16Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardOccluded1Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardOccluded4)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardOccluded4Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardOccluded8)
+RTCB200_DECLARE_UNSUPPORTED(rtcForwardOccluded8Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryFace)
+RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryFirstHalfEdge)
+RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryNextHalfEdge)
+RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryOppositeHalfEdge)
+RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryPreviousHalfEdge)
+RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryTransform)
+RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryTransformEx)
+RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryTransformFromScene)
+RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryTransformFromTraversable)
+RTCB200_DECLARE_UNSUPPORTED(rtcInterpolate)
+RTCB200_DECLARE_UNSUPPORTED(rtcInterpolateN)
+RTCB200_DECLARE_UNSUPPORTED(rtcInvokeIntersectFilterFromGeometry)
+RTCB200_DECLARE_UNSUPPORTED(rtcInvokeOccludedFilterFromGeometry)
+RTCB200_DECLARE_UNSUPPORTED(rtcMakeStaticBVH)
+RTCB200_DECLARE_UNSUPPORTED(rtcNewBVH)
+RTCB200_DECLARE_UNSUPPORTED(rtcPointQuery)
+RTCB200_DECLARE_UNSUPPORTED(rtcPointQuery16)
+RTCB200_DECLARE_UNSUPPORTED(rtcPointQuery4)
+RTCB200_DECLARE_UNSUPPORTED(rtcPointQuery8)
+RTCB200_DECLARE_UNSUPPORTED(rtcReleaseBVH)
+RTCB200_DECLARE_UNSUPPORTED(rtcRetainBVH)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryBoundsFunction)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryDisplacementFunction)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryInstancedScene)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryInstancedScenes)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryIntersectFunction)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryOccludedFunction)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryPointQueryFunction)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometrySubdivisionMode)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTessellationRate)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTopologyCount)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTransform)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTransformQuaternion)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryUserPrimitiveCount)
+RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryVertexAttributeTopology)
+RTCB200_DECLARE_UNSUPPORTED(rtcThreadLocalAlloc)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardIntersect1)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardIntersect16)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardIntersect16Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardIntersect1Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardIntersect4)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardIntersect4Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardIntersect8)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardIntersect8Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardOccluded1)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardOccluded16)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardOccluded16Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardOccluded1Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardOccluded4)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardOccluded4Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardOccluded8)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversableForwardOccluded8Ex)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversablePointQuery)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversablePointQuery16)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversablePointQuery4)
+RTCB200_DECLARE_UNSUPPORTED(rtcTraversablePointQuery8)
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,7 +54,9 @@ def test_layout_matches_reference_values():
 
 def _declared_symbols():
     txt = open(HEADER).read()
-    return sorted(set(re.findall(r"RTCB200_API[^;(]*?\b(rtc\w+)\s*\(", txt)))
+    names = set(re.findall(r"RTCB200_API[^;(]*?\b(rtc\w+)\s*\(", txt))
+    names |= set(re.findall(r"RTCB200_DECLARE_UNSUPPORTED\((rtc\w+)\)", txt))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -68,6 +70,29 @@ def test_library_exports_every_declared_symbol():
     dll = C.CDLL(LIB)
     for n in names:
         getattr(dll, n)
+
+
+def test_every_reference_export_is_present():
+    """Any Embree 4 caller links: every rtc* symbol the unmodified reference library exports (list in
+    tests/reference_exports.txt, taken with nm -D from oracle/_ref) is exported here too; unsupported ones report
+    RTC_ERROR_INVALID_OPERATION when called."""
+    want = [l.strip() for l in open(os.path.join(ROOT, "tests", "reference_exports.txt")) if l.strip() and not l.startswith("#")]
+    assert len(want) >= 150
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libembree4.so.4")
+    if os.path.exists(ref_so):   # the committed list is what the reference build really exports
+        out = subprocess.check_output(["nm", "-D", "--defined-only", ref_so]).decode()
+        live = sorted(set(l.split()[-1] for l in out.splitlines() if l.split()[-1].startswith("rtc")))
+        assert live == sorted(want)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB]).decode()
+    have = set(l.split()[-1] for l in out.splitlines())
+    assert not [w for w in want if w not in have]
+    dll = C.CDLL(LIB)
+    dll.rtcGetDeviceError.argtypes = [C.c_void_p]
+    dll.rtcGetDeviceError(None)
+    dll.rtcNewBVH.restype = C.c_void_p
+    assert dll.rtcNewBVH(None) is None
+    assert dll.rtcGetDeviceError(None) == 3     # RTC_ERROR_INVALID_OPERATION
+    assert dll.rtcGetDeviceError(None) == 0
 
 
 def test_only_rtc_symbols_and_sm100a_code():
