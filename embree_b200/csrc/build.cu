@@ -469,8 +469,12 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   if (ntot == 0) return 0;  // empty scene: queries return immediately (bvh_intersector1.cpp:39)
   ensure_pool(s.device);
 
-  cudaEvent_t ev0, ev1;
-  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  struct Events {   // released on every exit path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } evs;
+  CK(cudaEventCreate(&evs.a)); CK(cudaEventCreate(&evs.b));
+  const cudaEvent_t ev0 = evs.a, ev1 = evs.b;
   CK(cudaEventRecord(ev0, st));
 
   DevBuf<GeomDesc> d_geoms; DevBuf<uint32_t> d_offs; DevBuf<BuildInfo> d_info; DevBuf<PrimRef> d_prims;
@@ -503,7 +507,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   CK(cudaMemcpyAsync(&hinfo, d_info.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   const uint32_t n = hinfo.num_valid;  // valid primitives are sorted[0..n); invalid ones carry key ~0 at the end
-  if (n == 0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return 0; }
+  if (n == 0) return 0;
   for (int a = 0; a < 3; ++a) { s.bounds[a] = ord2f_host(hinfo.geom_lo[a]); s.bounds[3 + a] = ord2f_host(hinfo.geom_hi[a]); }
 
   // ---- binary tree
@@ -537,8 +541,9 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   }
   s.node_capacity = (size_t)n + 1; s.tri_capacity = n;
   CK(d_src.alloc(s.node_capacity, st)); CK(d_trisrc.alloc(n, st));
-  Node8* n8 = nullptr;
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&n8), s.node_capacity * sizeof(Node8), st));
+  DevBuf<Node8> d_n8;      // worst-case sized scratch; the final array is an exact-size copy
+  CK(d_n8.alloc(s.node_capacity, st));
+  Node8* n8 = d_n8.p;
   CK(cudaMemcpyAsync(d_src.p, &root2, 4, cudaMemcpyHostToDevice, st));
   const float ex = s.bounds[3] - s.bounds[0], ey = s.bounds[4] - s.bounds[1], ez = s.bounds[5] - s.bounds[2];
   const float ra = ex * (ey + ez) + ey * ez;
@@ -552,29 +557,28 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
     CK(cudaMemcpyAsync(&tail, &d_info.p->node_tail, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     begin = end; end = tail; ++depth;
-    if (depth > 4096) { snprintf(errmsg, 256, "collapse did not terminate"); cudaFreeAsync(n8, st); return -1; }
+    if (depth > 4096) { snprintf(errmsg, 256, "collapse did not terminate"); return -1; }
   }
   CK(cudaMemcpyAsync(&hinfo, d_info.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (hinfo.tri_tail != n) { snprintf(errmsg, 256, "internal: packed %u of %u triangles", hinfo.tri_tail, n); cudaFreeAsync(n8, st); return -1; }
-  if (depth >= (uint32_t)kStackSize) { snprintf(errmsg, 256, "BVH too deep for the traversal stack (%u)", depth); cudaFreeAsync(n8, st); return -1; }
+  if (hinfo.tri_tail != n) { snprintf(errmsg, 256, "internal: packed %u of %u triangles", hinfo.tri_tail, n); return -1; }
+  if (depth >= (uint32_t)kStackSize) { snprintf(errmsg, 256, "BVH too deep for the traversal stack (%u)", depth); return -1; }
 
   // ---- triangle records, then shrink the node array to its final size
-  TriRec* tris = nullptr;
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&tris), (size_t)n * sizeof(TriRec), st));
-  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, tris, s.robust);
+  DevBuf<TriRec> d_tris;
+  DevBuf<Node8> d_final;
+  CK(d_tris.alloc(n, st));
+  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, d_tris.p, s.robust);
   count_launch();
-  Node8* n8_final = nullptr;
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&n8_final), (size_t)end * sizeof(Node8), st));
-  CK(cudaMemcpyAsync(n8_final, n8, (size_t)end * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
+  CK(d_final.alloc(end, st));
+  CK(cudaMemcpyAsync(d_final.p, n8, (size_t)end * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
   CK(cudaEventRecord(ev1, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
-  cudaFreeAsync(n8, st);
   float ms = 0;
   cudaEventElapsedTime(&ms, ev0, ev1);
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-  s.nodes = n8_final; s.tris = tris; s.num_nodes = end; s.num_tris = n; s.root_valid = 1;
+  s.nodes = d_final.p; s.tris = d_tris.p; d_final.p = nullptr; d_tris.p = nullptr;   // ownership moves to the scene
+  s.num_nodes = end; s.num_tris = n; s.root_valid = 1;
   s.build_ms = ms; s.sah_cost = hinfo.sah; s.max_depth = depth;
   return 0;
 }
