@@ -49,6 +49,7 @@ struct BuildInfo {        // device-resident scalars of one build
   uint32_t tri_tail;            // triangle records allocated so far
   uint32_t pad;
   double sah;                   // accumulated SAH cost numerator
+  int api_lo[3], api_hi[3];     // bounds of the non-instanced triangles only (rtcGetSceneBounds merges instance boxes on the host)
 };
 
 __device__ __forceinline__ int find_geom(const uint32_t* __restrict__ offs, int ngeoms, uint32_t p) {
@@ -60,7 +61,7 @@ __device__ __forceinline__ int find_geom(const uint32_t* __restrict__ offs, int 
   return lo;
 }
 
-__device__ __forceinline__ void load_tri_verts(const GeomDesc& g, uint32_t lp, float v[9], bool& ok) {
+__device__ __forceinline__ void load_tri_verts(const GeomDesc& g, uint32_t lp, float v[9], bool& ok, bool world) {
   const uint32_t* ip = reinterpret_cast<const uint32_t*>(g.idx + (uint64_t)lp * g.istride);
   const uint32_t i0 = ip[0], i1 = ip[1], i2 = ip[2];
   ok = (i0 < g.nverts) & (i1 < g.nverts) & (i2 < g.nverts);          // scene_triangle_mesh.h:197-199
@@ -73,6 +74,16 @@ __device__ __forceinline__ void load_tri_verts(const GeomDesc& g, uint32_t lp, f
   v[6] = p2[0]; v[7] = p2[1]; v[8] = p2[2];
 #pragma unroll
   for (int k = 0; k < 9; ++k) ok &= (v[k] > -kFltLarge) & (v[k] < kFltLarge);  // isvalid(), vec3fa.h:304 (NaN fails)
+  if (world && g.has_xfm) {   // instance: vertices to world space for the BVH (xfmPoint, common/math/affinespace.h:102)
+#pragma unroll
+    for (int k = 0; k < 9; k += 3) {
+      const float x = v[k], y = v[k + 1], z = v[k + 2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) v[k + a] = __fmaf_rn(x, g.xfm[a], __fmaf_rn(y, g.xfm[3 + a], __fmaf_rn(z, g.xfm[6 + a], g.xfm[9 + a])));
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) ok &= (v[k] > -kFltLarge) & (v[k] < kFltLarge);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -83,16 +94,21 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
                                                    BuildInfo* __restrict__ info) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  bool ok = false;
+  bool ok = false, skipb = false;
   if (p < ntot) {
     const int g = find_geom(offs, ngeoms, p);
     float v[9];
-    load_tri_verts(geoms[g], p - offs[g], v, ok);
+    load_tri_verts(geoms[g], p - offs[g], v, ok, true);
+    skipb = geoms[g].skip_bounds != 0;
     if (ok) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         lo[a] = fminf(fminf(v[a], v[3 + a]), v[6 + a]);
         hi[a] = fmaxf(fmaxf(v[a], v[3 + a]), v[6 + a]);
+      }
+      if (geoms[g].has_xfm) {   // the triangle test runs in object space: keep the world box conservative by 2 ulp
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] -= fabsf(lo[a]) * 2.4e-7f; hi[a] += fabsf(hi[a]) * 2.4e-7f; }
       }
     }
     PrimRef pr;
@@ -104,6 +120,9 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
   float c_lo[3], c_hi[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) { c_lo[a] = ok ? lo[a] + hi[a] : INFINITY; c_hi[a] = ok ? lo[a] + hi[a] : -INFINITY; }
+  float a_lo[3], a_hi[3];   // API-visible bounds: instanced triangles are represented by their instance box (host side)
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { a_lo[a] = skipb ? INFINITY : lo[a]; a_hi[a] = skipb ? -INFINITY : hi[a]; }
   unsigned cnt = ok ? 1u : 0u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -113,6 +132,8 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
       hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
       c_lo[a] = fminf(c_lo[a], __shfl_xor_sync(0xFFFFFFFFu, c_lo[a], o));
       c_hi[a] = fmaxf(c_hi[a], __shfl_xor_sync(0xFFFFFFFFu, c_hi[a], o));
+      a_lo[a] = fminf(a_lo[a], __shfl_xor_sync(0xFFFFFFFFu, a_lo[a], o));
+      a_hi[a] = fmaxf(a_hi[a], __shfl_xor_sync(0xFFFFFFFFu, a_hi[a], o));
     }
     cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
   }
@@ -123,6 +144,8 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
       atomicMax(&info->geom_hi[a], f2ord(hi[a]));
       atomicMin(&info->cent_lo[a], f2ord(c_lo[a]));
       atomicMax(&info->cent_hi[a], f2ord(c_hi[a]));
+      atomicMin(&info->api_lo[a], f2ord(a_lo[a]));
+      atomicMax(&info->api_hi[a], f2ord(a_hi[a]));
     }
     atomicAdd(&info->num_valid, cnt);
   }
@@ -132,6 +155,7 @@ __global__ void init_info(BuildInfo* info) {
   for (int a = 0; a < 3; ++a) {
     info->geom_lo[a] = info->cent_lo[a] = f2ord(INFINITY);
     info->geom_hi[a] = info->cent_hi[a] = f2ord(-INFINITY);
+    info->api_lo[a] = f2ord(INFINITY); info->api_hi[a] = f2ord(-INFINITY);
   }
   info->num_valid = 0; info->node_tail = 1; info->tri_tail = 0; info->pad = 0; info->sah = 0.0;
 }
@@ -387,7 +411,8 @@ __global__ void __launch_bounds__(256) collapse_dp(const Node2* __restrict__ nod
 // 6. leaf_pack: gather vertices through the index buffer, store v0, e1 = v0 - v1, e2 = v2 - v0 (triangle.h:98-120)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ offs, int ngeoms,
-                                                 const uint32_t* __restrict__ tri_src, uint32_t ntris, TriRec* __restrict__ out, int robust) {
+                                                 const uint32_t* __restrict__ tri_src, uint32_t ntris, TriRec* __restrict__ out, int robust,
+                                                 int instanced) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntris) return;
   const uint32_t p = tri_src[t];
@@ -395,7 +420,7 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
   const GeomDesc gd = geoms[g];
   float v[9];
   bool ok;
-  load_tri_verts(gd, p - offs[g], v, ok);
+  load_tri_verts(gd, p - offs[g], v, ok, false);   // instances keep OBJECT-space triangles (see trace.cu to_object_space)
   float4 a, b, c;
   a.x = v[0]; a.y = v[1]; a.z = v[2]; a.w = __uint_as_float(p - offs[g]);
   if (robust) {   // Triangle4v: full vertices for the Pluecker test (kernels/geometry/trianglev.h)
@@ -405,7 +430,7 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
     b.x = __fsub_rn(v[0], v[3]); b.y = __fsub_rn(v[1], v[4]); b.z = __fsub_rn(v[2], v[5]);
     c.x = __fsub_rn(v[6], v[0]); c.y = __fsub_rn(v[7], v[1]); c.z = __fsub_rn(v[8], v[2]);
   }
-  b.w = __uint_as_float(gd.geomID);
+  b.w = __uint_as_float(instanced ? (uint32_t)g : gd.geomID);   // instanced scenes: descriptor index (geomID/instID via table)
   c.w = __uint_as_float(gd.mask);
   float4* dst = reinterpret_cast<float4*>(&out[t]);
   dst[0] = a; dst[1] = b; dst[2] = c;
@@ -447,8 +472,9 @@ struct DevBuf {
 void free_scene(SceneGPU& s) {
   if (s.nodes) cudaFreeAsync(s.nodes, 0);   // pool memory: goes back to the pool for the next commit
   if (s.tris) cudaFreeAsync(s.tris, 0);
+  if (s.d_descs) cudaFreeAsync(s.d_descs, 0);
   if (s.d_stat) cudaFree(s.d_stat);
-  s.nodes = nullptr; s.tris = nullptr; s.d_stat = nullptr;
+  s.nodes = nullptr; s.tris = nullptr; s.d_stat = nullptr; s.d_descs = nullptr;
   s.num_nodes = s.num_tris = 0; s.root_valid = 0;
 }
 
@@ -456,8 +482,9 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   errmsg[0] = 0;
   if (s.nodes) { cudaFreeAsync(s.nodes, st); s.nodes = nullptr; }
   if (s.tris) { cudaFreeAsync(s.tris, st); s.tris = nullptr; }
+  if (s.d_descs) { cudaFreeAsync(s.d_descs, st); s.d_descs = nullptr; }
   s.num_nodes = s.num_tris = 0; s.root_valid = 0; s.max_depth = 0; s.sah_cost = 0; s.builder = kind;
-  for (int a = 0; a < 3; ++a) { s.bounds[a] = INFINITY; s.bounds[3 + a] = -INFINITY; }
+  for (int a = 0; a < 3; ++a) { s.bounds[a] = s.api_bounds[a] = INFINITY; s.bounds[3 + a] = s.api_bounds[3 + a] = -INFINITY; }
   if (!s.d_stat) { CK(cudaMalloc(&s.d_stat, 3 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s.d_stat, 0, 24, st)); }
 
   std::vector<uint32_t> offs(ngeoms + 1, 0);
@@ -508,7 +535,10 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   CK(cudaStreamSynchronize(st));
   const uint32_t n = hinfo.num_valid;  // valid primitives are sorted[0..n); invalid ones carry key ~0 at the end
   if (n == 0) return 0;
-  for (int a = 0; a < 3; ++a) { s.bounds[a] = ord2f_host(hinfo.geom_lo[a]); s.bounds[3 + a] = ord2f_host(hinfo.geom_hi[a]); }
+  for (int a = 0; a < 3; ++a) {
+    s.bounds[a] = ord2f_host(hinfo.geom_lo[a]); s.bounds[3 + a] = ord2f_host(hinfo.geom_hi[a]);
+    s.api_bounds[a] = ord2f_host(hinfo.api_lo[a]); s.api_bounds[3 + a] = ord2f_host(hinfo.api_hi[a]);
+  }
 
   // ---- binary tree
   DevBuf<Node2> d_n2; DevBuf<uint32_t> d_flags;
@@ -568,7 +598,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   DevBuf<TriRec> d_tris;
   DevBuf<Node8> d_final;
   CK(d_tris.alloc(n, st));
-  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, d_tris.p, s.robust);
+  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, d_tris.p, s.robust, s.instanced);
   count_launch();
   CK(d_final.alloc(end, st));
   CK(cudaMemcpyAsync(d_final.p, n8, (size_t)end * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
@@ -578,6 +608,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   float ms = 0;
   cudaEventElapsedTime(&ms, ev0, ev1);
   s.nodes = d_final.p; s.tris = d_tris.p; d_final.p = nullptr; d_tris.p = nullptr;   // ownership moves to the scene
+  if (s.instanced) { s.d_descs = d_geoms.p; d_geoms.p = nullptr; }
   s.num_nodes = end; s.num_tris = n; s.root_valid = 1;
   s.build_ms = ms; s.sah_cost = hinfo.sah; s.max_depth = depth;
   return 0;

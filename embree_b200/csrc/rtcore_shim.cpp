@@ -127,8 +127,16 @@ struct BufferView {
 
 enum class GeomState { MODIFIED, COMMITTED };
 
+struct SceneImpl;
+void release_scene_ref(SceneImpl* s);
+
 struct GeometryImpl : RefCounted {
   DeviceImpl* dev;
+  RTCGeometryType type = RTC_GEOMETRY_TYPE_TRIANGLE;
+  SceneImpl* instScene = nullptr;                       // RTC_GEOMETRY_TYPE_INSTANCE: the instanced scene (retained)
+  float xfm[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};  // local2world columns vx | vy | vz | p (AffineSpace3fa)
+  float w2l[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};  // world2local0 = rcp(local2world) (scene_instance.cpp:153)
+  void update_world2local();
   BufferView vertices, indices;
   std::vector<BufferView> attribs;
   unsigned mask = 1;  // reference default (geometry.cpp:48)
@@ -138,7 +146,7 @@ struct GeometryImpl : RefCounted {
   GeomState state = GeomState::MODIFIED;
   unsigned modCounter = 1;
   explicit GeometryImpl(DeviceImpl* d) : dev(d) { dev->retain(); }
-  ~GeometryImpl() override { dev->release(); }
+  ~GeometryImpl() override { if (instScene) release_scene_ref(instScene); dev->release(); }
   void update() { ++modCounter; state = GeomState::MODIFIED; }  // geometry.cpp:97-101
 };
 
@@ -155,6 +163,7 @@ struct SceneImpl : RefCounted {
   RTCProgressMonitorFunction progFn = nullptr;
   void* progPtr = nullptr;
   rtk::SceneGPU gpu;
+  float apiBounds[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};  // what rtcGetSceneBounds reports
   std::vector<void*> deviceBuffers;  // uploaded vertex/index bytes of the current commit
   bool statCounters = false;
   double lastTraceMs = -1.0;
@@ -179,6 +188,33 @@ struct SceneImpl : RefCounted {
     return geoms.size() != committedCounter.size();
   }
 };
+
+void release_scene_ref(SceneImpl* s) { s->release(); }
+
+// rcp(AffineSpace3fa) = (il, -(il * p)), il = adjoint / det (affinespace.h:83, linearspace3.h:44-51).  The reference runs
+// this once per commit in its lowest-ISA (non-FMA) code, so the products below must stay unfused: volatile keeps a
+// contracting host compiler from fusing them.
+void GeometryImpl::update_world2local() {
+  const float *vx = xfm, *vy = xfm + 3, *vz = xfm + 6, *p = xfm + 9;
+  auto cross = [](const float* a, const float* b, float* o) {
+    for (int i = 0; i < 3; ++i) {
+      const int j = (i + 1) % 3, k = (i + 2) % 3;
+      volatile float m0 = a[j] * b[k], m1 = a[k] * b[j];
+      o[i] = m0 - m1;
+    }
+  };
+  float c0[3], c1[3], c2[3];
+  cross(vy, vz, c0); cross(vz, vx, c1); cross(vx, vy, c2);
+  volatile float d0 = vx[0] * c0[0], d1 = vx[1] * c0[1], d2 = vx[2] * c0[2];
+  volatile float d01 = d0 + d1;
+  const float det = d01 + d2;
+  for (int a = 0; a < 3; ++a) { w2l[3 * a] = c0[a] / det; w2l[3 * a + 1] = c1[a] / det; w2l[3 * a + 2] = c2[a] / det; }
+  for (int a = 0; a < 3; ++a) {
+    volatile float m0 = p[0] * w2l[a], m1 = p[1] * w2l[3 + a], m2 = p[2] * w2l[6 + a];
+    volatile float s12 = m1 + m2;
+    w2l[9 + a] = -(m0 + s12);
+  }
+}
 
 DeviceImpl* D(RTCDevice h) { return reinterpret_cast<DeviceImpl*>(h); }
 BufferImpl* B(RTCBuffer h) { return reinterpret_cast<BufferImpl*>(h); }
@@ -220,29 +256,71 @@ void commit_scene(SceneImpl* s) {
   for (void* p : s->deviceBuffers) cudaFreeAsync(p, 0);
   s->deviceBuffers.clear();
   std::vector<rtk::GeomDesc> descs;
+  std::unordered_map<GeometryImpl*, std::pair<void*, void*>> uploaded;   // a mesh instanced many times is uploaded once
+  bool instanced = false;
+  float instBounds[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  auto add_mesh = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
+    const size_t ntris = g->indices.count, nverts = g->vertices.count;
+    if (ntris == 0 || !g->indices.buf) return;
+    if (!g->vertices.buf) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer not set");
+    if (ntris > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "mesh too large");
+    auto it = uploaded.find(g);
+    if (it == uploaded.end()) {
+      const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 12 : 0;
+      const size_t ibytes = (ntris - 1) * g->indices.stride + 12;
+      void *dv = nullptr, *di = nullptr;
+      cuda_check(cudaMallocAsync(&dv, vbytes ? vbytes : 16, 0), "cudaMallocAsync(vertices)");
+      s->deviceBuffers.push_back(dv);
+      cuda_check(cudaMallocAsync(&di, ibytes, 0), "cudaMallocAsync(indices)");
+      s->deviceBuffers.push_back(di);
+      if (vbytes) cuda_check(cudaMemcpyAsync(dv, g->vertices.data(), vbytes, cudaMemcpyHostToDevice, 0), "upload vertices");
+      cuda_check(cudaMemcpyAsync(di, g->indices.data(), ibytes, cudaMemcpyHostToDevice, 0), "upload indices");
+      it = uploaded.emplace(g, std::make_pair(dv, di)).first;
+    }
+    rtk::GeomDesc d;
+    d.verts = static_cast<const uint8_t*>(it->second.first); d.idx = static_cast<const uint8_t*>(it->second.second);
+    d.vstride = g->vertices.stride; d.istride = g->indices.stride;
+    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)ntris;
+    d.geomID = geomID; d.mask = g->mask;
+    if (xfm) {
+      d.has_xfm = 1; d.instID = instID; d.inst_mask = instMask; d.skip_bounds = 1;
+      memcpy(d.xfm, xfm, sizeof d.xfm);
+      memcpy(d.w2l, w2l, sizeof d.w2l);
+    }
+    descs.push_back(d);
+  };
   for (size_t id = 0; id < geoms.size(); ++id) {
     GeometryImpl* g = geoms[id];
     if (!g || !g->enabled) continue;
-    const size_t ntris = g->indices.count, nverts = g->vertices.count;
-    if (ntris == 0 || !g->indices.buf) continue;
-    if (!g->vertices.buf) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer not set");
-    if (ntris > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "mesh too large");
-    const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 12 : 0;
-    const size_t ibytes = (ntris - 1) * g->indices.stride + 12;
-    void *dv = nullptr, *di = nullptr;
-    cuda_check(cudaMallocAsync(&dv, vbytes ? vbytes : 16, 0), "cudaMallocAsync(vertices)");
-    s->deviceBuffers.push_back(dv);
-    cuda_check(cudaMallocAsync(&di, ibytes, 0), "cudaMallocAsync(indices)");
-    s->deviceBuffers.push_back(di);
-    if (vbytes) cuda_check(cudaMemcpyAsync(dv, g->vertices.data(), vbytes, cudaMemcpyHostToDevice, 0), "upload vertices");
-    cuda_check(cudaMemcpyAsync(di, g->indices.data(), ibytes, cudaMemcpyHostToDevice, 0), "upload indices");
-    rtk::GeomDesc d;
-    d.verts = static_cast<const uint8_t*>(dv); d.idx = static_cast<const uint8_t*>(di);
-    d.vstride = g->vertices.stride; d.istride = g->indices.stride;
-    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)ntris;
-    d.geomID = (uint32_t)id; d.mask = g->mask;
-    descs.push_back(d);
+    if (g->type == RTC_GEOMETRY_TYPE_TRIANGLE) { add_mesh(g, (uint32_t)id, nullptr, nullptr, RTC_INVALID_GEOMETRY_ID, 0xFFFFFFFFu); continue; }
+    // RTC_GEOMETRY_TYPE_INSTANCE (kernels/geometry/instance_intersector.cpp:15-38): flattened here -- every mesh of the
+    // instanced scene enters the top-level BVH through the instance transform; hits report the instance id, the
+    // CHILD scene's geomID / primID and an object-space Ng exactly as the reference's two-level traversal does.
+    SceneImpl* child = g->instScene;
+    if (!child) fail(RTC_ERROR_INVALID_OPERATION, "instance has no instanced scene");
+    if (!child->everCommitted) fail(RTC_ERROR_INVALID_OPERATION, "instanced scene not committed");
+    instanced = true;
+    std::vector<GeometryImpl*> cgeoms;
+    { std::lock_guard<std::mutex> lg(child->geomMutex); cgeoms = child->geoms; }
+    for (size_t cid = 0; cid < cgeoms.size(); ++cid) {
+      GeometryImpl* cg = cgeoms[cid];
+      if (!cg || !cg->enabled) continue;
+      if (cg->type != RTC_GEOMETRY_TYPE_TRIANGLE)   // RTC_MAX_INSTANCE_LEVEL_COUNT == 1, as in the reference's default build
+        fail(RTC_ERROR_INVALID_OPERATION, "multi-level instancing is not supported (RTC_MAX_INSTANCE_LEVEL_COUNT is 1)");
+      add_mesh(cg, (uint32_t)cid, g->xfm, g->w2l, (uint32_t)id, g->mask);
+    }
+    // instance box as the reference computes it: xfmBounds(local2world, child scene bounds) (affinespace.h:106-118)
+    const float* cb = child->apiBounds;
+    if (cb[0] <= cb[3])
+      for (int c = 0; c < 8; ++c) {
+        const float x = (c & 4) ? cb[3] : cb[0], y = (c & 2) ? cb[4] : cb[1], z = (c & 1) ? cb[5] : cb[2];
+        for (int a = 0; a < 3; ++a) {
+          const float w = fmaf(x, g->xfm[a], fmaf(y, g->xfm[3 + a], fmaf(z, g->xfm[6 + a], g->xfm[9 + a])));
+          instBounds[a] = fminf(instBounds[a], w); instBounds[3 + a] = fmaxf(instBounds[3 + a], w);
+        }
+      }
   }
+  s->gpu.instanced = instanced ? 1 : 0;
   // quality -> builder (scene.cpp:163-206: LOW = Morton two-level builder, MEDIUM/HIGH = SAH).  The env override
   // exists for A/B measurements of the two device builders only.
   rtk::BuilderKind kind = (s->quality == RTC_BUILD_QUALITY_LOW) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
@@ -256,6 +334,10 @@ void commit_scene(SceneImpl* s) {
   if (r != 0) {
     rtk::free_scene(s->gpu);
     fail(r == (int)cudaErrorMemoryAllocation ? RTC_ERROR_OUT_OF_MEMORY : RTC_ERROR_UNKNOWN, errmsg);
+  }
+  for (int a = 0; a < 3; ++a) {   // rtcGetSceneBounds: own triangles + instance boxes
+    s->apiBounds[a] = fminf(s->gpu.api_bounds[a], instBounds[a]);
+    s->apiBounds[3 + a] = fmaxf(s->gpu.api_bounds[3 + a], instBounds[3 + a]);
   }
   if (s->dev->verbose >= 2)
     fprintf(stderr, "[b200] commit: %u tris, %u nodes (%.1f MB) + %.1f MB tris, builder=%s, %.3f ms (%.1f Mprim/s), SAH %.2f, depth %u\n",
@@ -307,6 +389,7 @@ rtk::TraceParams make_params(SceneImpl* s, void* rays, const int* valid, unsigne
                              uint32_t instPrimID) {
   rtk::TraceParams p;
   p.nodes = s->gpu.nodes; p.tris = s->gpu.tris; p.root_valid = s->gpu.root_valid; p.robust = s->gpu.robust;
+  p.descs = s->gpu.instanced ? s->gpu.d_descs : nullptr;
   p.rays = rays; p.valid = valid; p.n = n; p.instID = instID; p.instPrimID = instPrimID;
   p.stat = s->statCounters ? s->gpu.d_stat : nullptr;
   return p;
@@ -528,8 +611,11 @@ void rtcReleaseBuffer(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; AP
 RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
   API_BEGIN
   VERIFY_HANDLE(h);
-  if (type != RTC_GEOMETRY_TYPE_TRIANGLE) fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE is supported by the B200 back-end");
-  return reinterpret_cast<RTCGeometry>(new GeometryImpl(D(h)));
+  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_INSTANCE)
+    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE and RTC_GEOMETRY_TYPE_INSTANCE are supported by the B200 back-end");
+  GeometryImpl* g = new GeometryImpl(D(h));
+  g->type = type;
+  return reinterpret_cast<RTCGeometry>(g);
   API_END(D(h))
   return nullptr;
 }
@@ -553,6 +639,7 @@ void rtcSetGeometryBuildQuality(RTCGeometry g, enum RTCBuildQuality q) {
 
 static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFormat format, BufferImpl* buf, size_t off, size_t stride, size_t num) {
   // scene_triangle_mesh.cpp:35-80
+  if (g->type != RTC_GEOMETRY_TYPE_TRIANGLE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
   if (((size_t)(buf->ptr) + off) & 3 || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
   if (num > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_ARGUMENT, "buffer too large");
   if (type == RTC_BUFFER_TYPE_VERTEX) {
@@ -718,7 +805,7 @@ void rtcGetSceneBounds(RTCScene s, struct RTCBounds* b) {
   SCENE_BEGIN(s)
   VERIFY_HANDLE(b);
   { std::lock_guard<std::mutex> lk(S(s)->geomMutex); if (S(s)->isModified()) fail(RTC_ERROR_INVALID_OPERATION, "scene not committed"); }
-  const float* g = S(s)->gpu.bounds;
+  const float* g = S(s)->apiBounds;
   b->lower_x = g[0]; b->lower_y = g[1]; b->lower_z = g[2]; b->align0 = 0;
   b->upper_x = g[3]; b->upper_y = g[4]; b->upper_z = g[5]; b->align1 = 0;
   SCENE_END
@@ -857,6 +944,61 @@ double rtcb200GetLastTraceMs(RTCScene sc) {
   return -1.0;
 }
 
+// ---- instancing (rtcore_geometry.h:231-250, kernels/common/rtcore.cpp:1408-1515) ----------------------------------
+static void load_transform(RTCFormat format, const float* x, float out[12]) {   // loadTransform, rtcore.cpp:1408-1439
+  switch ((int)format) {
+    case 0x9134: { const float m[12] = {x[0], x[4], x[8], x[1], x[5], x[9], x[2], x[6], x[10], x[3], x[7], x[11]}; memcpy(out, m, sizeof m); break; }  // FLOAT3X4_ROW_MAJOR
+    case 0x9234: memcpy(out, x, 12 * sizeof(float)); break;                                                                                          // FLOAT3X4_COLUMN_MAJOR
+    case 0x9244: { const float m[12] = {x[0], x[1], x[2], x[4], x[5], x[6], x[8], x[9], x[10], x[12], x[13], x[14]}; memcpy(out, m, sizeof m); break; }  // FLOAT4X4_COLUMN_MAJOR
+    default: fail(RTC_ERROR_INVALID_OPERATION, "invalid matrix format");
+  }
+}
+static void store_transform(const float m[12], RTCFormat format, float* x) {    // storeTransform, rtcore.cpp
+  switch ((int)format) {
+    case 0x9134: { const float o[12] = {m[0], m[3], m[6], m[9], m[1], m[4], m[7], m[10], m[2], m[5], m[8], m[11]}; memcpy(x, o, sizeof o); break; }
+    case 0x9234: memcpy(x, m, 12 * sizeof(float)); break;
+    case 0x9244: { const float o[16] = {m[0], m[1], m[2], 0, m[3], m[4], m[5], 0, m[6], m[7], m[8], 0, m[9], m[10], m[11], 1}; memcpy(x, o, sizeof o); break; }
+    default: fail(RTC_ERROR_INVALID_OPERATION, "invalid matrix format");
+  }
+}
+void rtcSetGeometryInstancedScene(RTCGeometry g, RTCScene scene) {
+  GEOM_BEGIN(g)
+  VERIFY_HANDLE(scene);
+  if (G(g)->type != RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+  if (G(g)->dev != S(scene)->dev) fail(RTC_ERROR_INVALID_ARGUMENT, "inputs are from different devices");
+  S(scene)->retain();
+  if (G(g)->instScene) G(g)->instScene->release();
+  G(g)->instScene = S(scene);
+  G(g)->update();
+  GEOM_END
+}
+void rtcSetGeometryTransform(RTCGeometry g, unsigned int timeStep, enum RTCFormat format, const void* xfm) {
+  GEOM_BEGIN(g)
+  VERIFY_HANDLE(xfm);
+  if (G(g)->type != RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+  if (timeStep != 0) fail(RTC_ERROR_INVALID_OPERATION, "invalid timestep");
+  load_transform(format, static_cast<const float*>(xfm), G(g)->xfm);
+  G(g)->update_world2local();
+  G(g)->update();
+  GEOM_END
+}
+void rtcGetGeometryTransform(RTCGeometry g, float, enum RTCFormat format, void* xfm) {
+  GEOM_BEGIN(g)
+  VERIFY_HANDLE(xfm);
+  store_transform(G(g)->xfm, format, static_cast<float*>(xfm));
+  GEOM_END
+}
+void rtcGetGeometryTransformEx(RTCGeometry g, unsigned int, float time, enum RTCFormat format, void* xfm) { rtcGetGeometryTransform(g, time, format, xfm); }
+void rtcGetGeometryTransformFromScene(RTCScene s, unsigned int id, float time, enum RTCFormat format, void* xfm) {
+  SCENE_BEGIN(s)
+  if (id >= S(s)->geoms.size() || !S(s)->geoms[id]) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid geometry ID");
+  rtcGetGeometryTransform(reinterpret_cast<RTCGeometry>(S(s)->geoms[id]), time, format, xfm);
+  SCENE_END
+}
+void rtcGetGeometryTransformFromTraversable(RTCTraversable t, unsigned int id, float time, enum RTCFormat format, void* xfm) {
+  rtcGetGeometryTransformFromScene(reinterpret_cast<RTCScene>(t), id, time, format, xfm);
+}
+
 // ---- entry points of the reference that are thin variants of supported ones -----------------------------------------
 void* rtcGetGeometryBufferDataDevice(RTCGeometry g, enum RTCBufferType type, unsigned int slot) { return rtcGetGeometryBufferData(g, type, slot); }
 void rtcSetSharedGeometryBufferHostDevice(RTCGeometry g, enum RTCBufferType type, unsigned int slot, enum RTCFormat format, const void* ptr,
@@ -904,10 +1046,6 @@ RTCB200_UNSUPPORTED(rtcGetGeometryFirstHalfEdge)
 RTCB200_UNSUPPORTED(rtcGetGeometryNextHalfEdge)
 RTCB200_UNSUPPORTED(rtcGetGeometryOppositeHalfEdge)
 RTCB200_UNSUPPORTED(rtcGetGeometryPreviousHalfEdge)
-RTCB200_UNSUPPORTED(rtcGetGeometryTransform)
-RTCB200_UNSUPPORTED(rtcGetGeometryTransformEx)
-RTCB200_UNSUPPORTED(rtcGetGeometryTransformFromScene)
-RTCB200_UNSUPPORTED(rtcGetGeometryTransformFromTraversable)
 RTCB200_UNSUPPORTED(rtcInterpolate)
 RTCB200_UNSUPPORTED(rtcInterpolateN)
 RTCB200_UNSUPPORTED(rtcInvokeIntersectFilterFromGeometry)
@@ -922,7 +1060,6 @@ RTCB200_UNSUPPORTED(rtcReleaseBVH)
 RTCB200_UNSUPPORTED(rtcRetainBVH)
 RTCB200_UNSUPPORTED(rtcSetGeometryBoundsFunction)
 RTCB200_UNSUPPORTED(rtcSetGeometryDisplacementFunction)
-RTCB200_UNSUPPORTED(rtcSetGeometryInstancedScene)
 RTCB200_UNSUPPORTED(rtcSetGeometryInstancedScenes)
 RTCB200_UNSUPPORTED(rtcSetGeometryIntersectFunction)
 RTCB200_UNSUPPORTED(rtcSetGeometryOccludedFunction)
@@ -930,7 +1067,6 @@ RTCB200_UNSUPPORTED(rtcSetGeometryPointQueryFunction)
 RTCB200_UNSUPPORTED(rtcSetGeometrySubdivisionMode)
 RTCB200_UNSUPPORTED(rtcSetGeometryTessellationRate)
 RTCB200_UNSUPPORTED(rtcSetGeometryTopologyCount)
-RTCB200_UNSUPPORTED(rtcSetGeometryTransform)
 RTCB200_UNSUPPORTED(rtcSetGeometryTransformQuaternion)
 RTCB200_UNSUPPORTED(rtcSetGeometryUserPrimitiveCount)
 RTCB200_UNSUPPORTED(rtcSetGeometryVertexAttributeTopology)

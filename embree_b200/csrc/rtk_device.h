@@ -17,6 +17,12 @@ struct GeomDesc {
   uint64_t vstride, istride;
   uint32_t nverts, ntris;
   uint32_t geomID, mask;
+  // instancing (RTC_GEOMETRY_TYPE_INSTANCE, flattened at commit): this mesh is seen through the instance transform
+  // xfm = (vx | vy | vz | p) columns of local2world (places the triangles in the world-space BVH), w2l its inverse
+  // (takes the ray to the object-space triangle records); hits report instID and must also pass inst_mask.
+  uint32_t has_xfm = 0, instID = 0xFFFFFFFFu, inst_mask = 0xFFFFFFFFu, skip_bounds = 0;
+  float xfm[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+  float w2l[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
 };
 
 enum BuilderKind : uint32_t { BUILDER_LBVH = 0, BUILDER_SAH = 1 };
@@ -28,7 +34,10 @@ struct SceneGPU {
   uint32_t num_nodes = 0, num_tris = 0;
   uint32_t root_valid = 0;              // 0: empty scene -> queries return immediately
   int robust = 0;                       // RTC_SCENE_FLAG_ROBUST: leaf records are (v0, v1, v2), Pluecker intersector
-  float bounds[6] = {0, 0, 0, 0, 0, 0};  // lower xyz, upper xyz of all valid triangles
+  int instanced = 0;                    // scene contains instances: records carry a descriptor index instead of geomID
+  GeomDesc* d_descs = nullptr;          // device copy of the mesh descriptors (kept while instanced)
+  float bounds[6] = {0, 0, 0, 0, 0, 0};  // lower xyz, upper xyz of all valid triangles (world space, instances flattened)
+  float api_bounds[6] = {0, 0, 0, 0, 0, 0};  // the same without instanced triangles
   double build_ms = 0, sah_cost = 0;
   uint32_t builder = 0, max_depth = 0;
   unsigned long long* d_stat = nullptr;  // [3] rays, nodes, tris (device)
@@ -53,6 +62,7 @@ struct TraceParams {
   // hit gather is fused into the trace kernel instead of being a separate collective.
   void* compact_out = nullptr;
   int tri_batch_min = 6, tri_wait_max = 3, refill_min = 4, use_prefetch = 1;  // filled by launch_trace from tuning()
+  const GeomDesc* descs = nullptr;  // non-NULL: instanced scene, record.geomID slot holds a descriptor index
   int robust = 0;  // scene built with RTC_SCENE_FLAG_ROBUST: triangle records hold v0,v1,v2, Pluecker test
 };
 // occluded: 0 = closest hit (rtcIntersect*), 1 = any hit (rtcOccluded*); K in {1,4,8,16}

@@ -47,15 +47,15 @@ struct RayIO<1, OCCLUDED> {
   static __device__ __forceinline__ void store_tfar(const TraceParams& p, unsigned long long i, float tfar) {
     *reinterpret_cast<float*>(static_cast<char*>(p.rays) + i * kStride + 32) = tfar;
   }
-  static __device__ __forceinline__ void store_hit(const TraceParams& p, unsigned long long i, const Hit& h) {
+  static __device__ __forceinline__ void store_hit(const TraceParams& p, unsigned long long i, const Hit& h, uint32_t instID, uint32_t instPrimID) {
     char* rec = static_cast<char*>(p.rays) + i * kStride;
     *reinterpret_cast<float*>(rec + 32) = h.t;
     float4 a, b;
     a.x = h.ngx; a.y = h.ngy; a.z = h.ngz; a.w = h.u;
-    b.x = h.v; b.y = __uint_as_float(h.primID); b.z = __uint_as_float(h.geomID); b.w = __uint_as_float(p.instID);
+    b.x = h.v; b.y = __uint_as_float(h.primID); b.z = __uint_as_float(h.geomID); b.w = __uint_as_float(instID);
     *reinterpret_cast<float4*>(rec + 48) = a;
     *reinterpret_cast<float4*>(rec + 64) = b;
-    *reinterpret_cast<uint32_t*>(rec + 80) = p.instPrimID;
+    *reinterpret_cast<uint32_t*>(rec + 80) = instPrimID;
   }
 };
 
@@ -80,13 +80,13 @@ struct RayIO {
   static __device__ __forceinline__ void store_tfar(const TraceParams& p, unsigned long long i, float tfar) {
     *reinterpret_cast<float*>(field(p, i, 8)) = tfar;
   }
-  static __device__ __forceinline__ void store_hit(const TraceParams& p, unsigned long long i, const Hit& h) {
+  static __device__ __forceinline__ void store_hit(const TraceParams& p, unsigned long long i, const Hit& h, uint32_t instID, uint32_t instPrimID) {
     *reinterpret_cast<float*>(field(p, i, 8)) = h.t;
     *reinterpret_cast<float*>(field(p, i, 12)) = h.ngx; *reinterpret_cast<float*>(field(p, i, 13)) = h.ngy;
     *reinterpret_cast<float*>(field(p, i, 14)) = h.ngz; *reinterpret_cast<float*>(field(p, i, 15)) = h.u;
     *reinterpret_cast<float*>(field(p, i, 16)) = h.v; *reinterpret_cast<uint32_t*>(field(p, i, 17)) = h.primID;
-    *reinterpret_cast<uint32_t*>(field(p, i, 18)) = h.geomID; *reinterpret_cast<uint32_t*>(field(p, i, 19)) = p.instID;
-    *reinterpret_cast<uint32_t*>(field(p, i, 20)) = p.instPrimID;
+    *reinterpret_cast<uint32_t*>(field(p, i, 18)) = h.geomID; *reinterpret_cast<uint32_t*>(field(p, i, 19)) = instID;
+    *reinterpret_cast<uint32_t*>(field(p, i, 20)) = instPrimID;
   }
 };
 
@@ -96,6 +96,20 @@ __device__ __forceinline__ float rcp_safe_fast(float d) {
   const float x = fabsf(d) < kMinRcpInput ? kMinRcpInput : d;
   const float r = __frcp_rn(x);
   return r;
+}
+
+// instanced scenes (kernels/geometry/instance_intersector.cpp:15-38): the records of an instance hold the OBJECT-space
+// triangle; the ray is taken into that space with the instance's world2local exactly as the reference does before it
+// traces the instanced scene (xfmPoint / xfmVector, affinespace.h:102-103) -- t is unchanged by the affine map, so the
+// world-space BVH above and the object-space triangle test below share one parametrisation.
+__device__ __forceinline__ void to_object_space(const GeomDesc& d, Ray& r) {
+  const float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
+  r.ox = fma_rn(ox, d.w2l[0], fma_rn(oy, d.w2l[3], fma_rn(oz, d.w2l[6], d.w2l[9])));
+  r.oy = fma_rn(ox, d.w2l[1], fma_rn(oy, d.w2l[4], fma_rn(oz, d.w2l[7], d.w2l[10])));
+  r.oz = fma_rn(ox, d.w2l[2], fma_rn(oy, d.w2l[5], fma_rn(oz, d.w2l[8], d.w2l[11])));
+  r.dx = fma_rn(dx, d.w2l[0], fma_rn(dy, d.w2l[3], mul_rn(dz, d.w2l[6])));
+  r.dy = fma_rn(dx, d.w2l[1], fma_rn(dy, d.w2l[4], mul_rn(dz, d.w2l[7])));
+  r.dz = fma_rn(dx, d.w2l[2], fma_rn(dy, d.w2l[5], mul_rn(dz, d.w2l[8])));
 }
 
 constexpr int TRACE_THREADS = 128;
@@ -116,7 +130,7 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 // node, slab-test its 8 children) for the lanes that want it, and at most one triangle step, batched across the warp;
 // the phases are warp-synchronous so lanes in the same phase execute together instead of serialising through a
 // per-thread while-while loop.  The top stack entry lives in registers; deeper entries in (L1-resident) local memory.
-template <int K, bool OCCLUDED, bool STATS, bool ROBUST>
+template <int K, bool OCCLUDED, bool STATS, bool ROBUST, bool INSTANCED>
 __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TraceParams p) {
   const bool USE_TMA = p.use_prefetch != 0;
   using IO = RayIO<K, OCCLUDED>;
@@ -242,22 +256,27 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
         const uint4* tp = tris + (size_t)ti * 3;
         const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         if (STATS) ++st_tris;
+        Ray lr = r;
+        bool visible = (c.w & r.mask) != 0;
+        if (INSTANCED) {   // b.w = descriptor index: instance mask (instance_intersector.cpp:19-22) + object-space ray
+          const GeomDesc& d = p.descs[b.w];
+          visible = visible && (d.inst_mask & r.mask) != 0;
+          if (d.has_xfm) to_object_space(d, lr);
+        }
         if (ROBUST) {   // RTC_SCENE_FLAG_ROBUST: the record holds v0, v1, v2; watertight Pluecker test
           PlueckerHit ph;
-          if (tri_test_pluecker(r, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
+          if (visible && tri_test_pluecker(lr, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
                                 __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
-                                __uint_as_float(c.z), ph) &&
-              (c.w & r.mask) != 0) {
+                                __uint_as_float(c.z), ph)) {
             found = true;
             if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
             else { tfar_tri = ph.t; pluecker_uv(ph, hit_u, hit_v); hit_tri = ti; }
           }
         } else {
           TriHit th;
-          if (tri_test(r, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
+          if (visible && tri_test(lr, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
                        __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
-                       __uint_as_float(c.z), th) &&
-              (c.w & r.mask) != 0) {
+                       __uint_as_float(c.z), th)) {
             found = true;
             if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }     // any hit terminates the ray
             else {
@@ -288,10 +307,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
             const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             Hit hit;
             hit.t = tfar_tri; hit.u = hit_u; hit.v = hit_v;
+            hit.primID = a.w; hit.geomID = b.w;
+            uint32_t instID = p.instID, instPrimID = p.instPrimID;
+            float lox = r.ox, loy = r.oy, loz = r.oz;   // ray origin in the space the record's triangle lives in
+            if (INSTANCED) {   // ids through the descriptor; Ng stays in OBJECT space as in the reference
+              const GeomDesc& d = p.descs[b.w];
+              hit.geomID = d.geomID;
+              if (d.has_xfm) {
+                instID = d.instID; instPrimID = 0u;   // instance_id_stack::push(context, instID, 0)
+                if (ROBUST) { Ray lr = r; to_object_space(d, lr); lox = lr.ox; loy = lr.oy; loz = lr.oz; }
+              }
+            }
             if (ROBUST) {   // stable_triangle_normal of the origin-relative edges, exactly as in tri_test_pluecker
-              const float v0x = sub_rn(__uint_as_float(a.x), r.ox), v0y = sub_rn(__uint_as_float(a.y), r.oy), v0z = sub_rn(__uint_as_float(a.z), r.oz);
-              const float v1x = sub_rn(__uint_as_float(b.x), r.ox), v1y = sub_rn(__uint_as_float(b.y), r.oy), v1z = sub_rn(__uint_as_float(b.z), r.oz);
-              const float v2x = sub_rn(__uint_as_float(c.x), r.ox), v2y = sub_rn(__uint_as_float(c.y), r.oy), v2z = sub_rn(__uint_as_float(c.z), r.oz);
+              const float v0x = sub_rn(__uint_as_float(a.x), lox), v0y = sub_rn(__uint_as_float(a.y), loy), v0z = sub_rn(__uint_as_float(a.z), loz);
+              const float v1x = sub_rn(__uint_as_float(b.x), lox), v1y = sub_rn(__uint_as_float(b.y), loy), v1z = sub_rn(__uint_as_float(b.z), loz);
+              const float v2x = sub_rn(__uint_as_float(c.x), lox), v2y = sub_rn(__uint_as_float(c.y), loy), v2z = sub_rn(__uint_as_float(c.z), loz);
               stable_normal(sub_rn(v2x, v0x), sub_rn(v2y, v0y), sub_rn(v2z, v0z), sub_rn(v0x, v1x), sub_rn(v0y, v1y), sub_rn(v0z, v1z),
                             sub_rn(v1x, v2x), sub_rn(v1y, v2y), sub_rn(v1z, v2z), hit.ngx, hit.ngy, hit.ngz);
             } else {
@@ -301,8 +331,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
               hit.ngy = msub(e2z, e1x, mul_rn(e2x, e1z));
               hit.ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
             }
-            hit.primID = a.w; hit.geomID = b.w;
-            IO::store_hit(p, ray_index, hit);
+            IO::store_hit(p, ray_index, hit, instID, instPrimID);
             cngx = hit.ngx; cngy = hit.ngy; cngz = hit.ngz; cprim = hit.primID; cgeom = hit.geomID;
           }
         }
@@ -349,12 +378,18 @@ static int launch_k(TraceParams p, cudaStream_t st) {
   const unsigned blocks = (unsigned)(need < cap ? need : cap);
   // tiny launches (single-record API calls read a mapped pinned host record) skip the bulk prefetch
   p.use_prefetch = (p.n >= 1024 && g_tuning.use_tma) ? 1 : 0;
-  if (p.stat) {
-    if (p.robust) trace_kernel<K, OCCLUDED, true, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
-    else trace_kernel<K, OCCLUDED, true, false><<<blocks, TRACE_THREADS, 0, st>>>(p);
-  } else {
-    if (p.robust) trace_kernel<K, OCCLUDED, false, true><<<blocks, TRACE_THREADS, 0, st>>>(p);
-    else trace_kernel<K, OCCLUDED, false, false><<<blocks, TRACE_THREADS, 0, st>>>(p);
+  const int variant = (p.stat ? 4 : 0) | (p.robust ? 2 : 0) | (p.descs ? 1 : 0);
+  switch (variant) {
+#define RTK_LAUNCH(ST, RB, IN) trace_kernel<K, OCCLUDED, ST, RB, IN><<<blocks, TRACE_THREADS, 0, st>>>(p); break
+    case 0: RTK_LAUNCH(false, false, false);
+    case 1: RTK_LAUNCH(false, false, true);
+    case 2: RTK_LAUNCH(false, true, false);
+    case 3: RTK_LAUNCH(false, true, true);
+    case 4: RTK_LAUNCH(true, false, false);
+    case 5: RTK_LAUNCH(true, false, true);
+    case 6: RTK_LAUNCH(true, true, false);
+    case 7: RTK_LAUNCH(true, true, true);
+#undef RTK_LAUNCH
   }
   count_launch();
   return (int)cudaGetLastError();

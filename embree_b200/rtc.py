@@ -18,6 +18,10 @@ RTC_FORMAT_FLOAT3 = 0x9003
 RTC_BUFFER_TYPE_INDEX = 0
 RTC_BUFFER_TYPE_VERTEX = 1
 RTC_GEOMETRY_TYPE_TRIANGLE = 0
+RTC_GEOMETRY_TYPE_INSTANCE = 121
+RTC_FORMAT_FLOAT3X4_ROW_MAJOR = 0x9134
+RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR = 0x9234
+RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR = 0x9244
 RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM, RTC_BUILD_QUALITY_HIGH, RTC_BUILD_QUALITY_REFIT = 0, 1, 2, 3
 RTC_SCENE_FLAG_NONE, RTC_SCENE_FLAG_DYNAMIC, RTC_SCENE_FLAG_COMPACT, RTC_SCENE_FLAG_ROBUST = 0, 1, 2, 4
 RTC_RAY_QUERY_FLAG_INCOHERENT = 0
@@ -168,6 +172,9 @@ class RTCLib:
         "rtcUpdateGeometryBuffer": (None, [C.c_void_p, C.c_int, C.c_uint]),
         "rtcSetGeometryUserData": (None, [C.c_void_p, C.c_void_p]),
         "rtcGetGeometryUserData": (C.c_void_p, [C.c_void_p]),
+        "rtcSetGeometryInstancedScene": (None, [C.c_void_p, C.c_void_p]),
+        "rtcSetGeometryTransform": (None, [C.c_void_p, C.c_uint, C.c_int, C.c_void_p]),
+        "rtcGetGeometryTransform": (None, [C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
         "rtcNewScene": (C.c_void_p, [C.c_void_p]),
         "rtcGetSceneDevice": (C.c_void_p, [C.c_void_p]),
         "rtcRetainScene": (None, [C.c_void_p]),
@@ -266,6 +273,24 @@ class RTCLib:
             gid = geom_id
         self.rtcReleaseGeometry(g)
         return gid, (vpad, idx)
+
+    def add_instance(self, device, scene, child_scene, xfm, mask=None, geom_id=None, fmt=RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR):
+        """rtcNewGeometry(INSTANCE) + instanced scene + transform + commit + attach (tutorials/instanced_geometry).
+        `xfm`: 12 floats, column-major 3x4 (vx | vy | vz | p) unless `fmt` says otherwise."""
+        m = np.ascontiguousarray(xfm, np.float32).reshape(-1)
+        g = self.rtcNewGeometry(device, RTC_GEOMETRY_TYPE_INSTANCE)
+        self.rtcSetGeometryInstancedScene(g, child_scene)
+        self.rtcSetGeometryTransform(g, 0, fmt, _ptr(m))
+        if mask is not None:
+            self.rtcSetGeometryMask(g, mask)
+        self.rtcCommitGeometry(g)
+        if geom_id is None:
+            gid = self.rtcAttachGeometry(scene, g)
+        else:
+            self.rtcAttachGeometryByID(scene, g, geom_id)
+            gid = geom_id
+        self.rtcReleaseGeometry(g)
+        return gid
 
     def args(self, coherent=False):
         a = _IntersectArguments()

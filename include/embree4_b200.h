@@ -55,7 +55,8 @@ typedef struct RTCTraversableTy* RTCTraversable; /* on this back-end == the scen
 enum RTCFormat {
   RTC_FORMAT_UNDEFINED = 0,
   RTC_FORMAT_UINT = 0x5001, RTC_FORMAT_UINT2, RTC_FORMAT_UINT3, RTC_FORMAT_UINT4,
-  RTC_FORMAT_FLOAT = 0x9001, RTC_FORMAT_FLOAT2, RTC_FORMAT_FLOAT3, RTC_FORMAT_FLOAT4
+  RTC_FORMAT_FLOAT = 0x9001, RTC_FORMAT_FLOAT2, RTC_FORMAT_FLOAT3, RTC_FORMAT_FLOAT4,
+  RTC_FORMAT_FLOAT3X4_ROW_MAJOR = 0x9134, RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR = 0x9234, RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR = 0x9244
 };
 enum RTCBuildQuality {
   RTC_BUILD_QUALITY_LOW = 0,    /* -> device LBVH (Morton) build      */
@@ -82,7 +83,10 @@ enum RTCFeatureFlags {
   RTC_FEATURE_FLAG_TRIANGLE = 1 << 1,
   RTC_FEATURE_FLAG_ALL = 0xffffffff
 };
-enum RTCGeometryType { RTC_GEOMETRY_TYPE_TRIANGLE = 0 /* the only type this library accepts */ };
+enum RTCGeometryType {
+  RTC_GEOMETRY_TYPE_TRIANGLE = 0,
+  RTC_GEOMETRY_TYPE_INSTANCE = 121 /* single-level instances of triangle scenes (rtcore_geometry.h:51) */
+};
 enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2 };
 enum RTCError {
   RTC_ERROR_NONE = 0, RTC_ERROR_UNKNOWN = 1, RTC_ERROR_INVALID_ARGUMENT = 2, RTC_ERROR_INVALID_OPERATION = 3,
@@ -229,6 +233,15 @@ RTCB200_API void rtcUpdateGeometryBuffer(RTCGeometry geometry, enum RTCBufferTyp
 RTCB200_API void rtcSetGeometryUserData(RTCGeometry geometry, void* ptr);
 RTCB200_API void* rtcGetGeometryUserData(RTCGeometry geometry);
 RTCB200_API void rtcSetGeometryEnableFilterFunctionFromArguments(RTCGeometry geometry, bool enable);
+/* instancing (rtcore_geometry.h:231-250 / kernels/geometry/instance_intersector.cpp:15-38): an INSTANCE geometry shows a
+ * committed triangle scene through an affine transform; hits report instID[0] = the instance's geomID, the instanced
+ * scene's geomID/primID and Ng in object space.  One instancing level (RTC_MAX_INSTANCE_LEVEL_COUNT == 1). */
+RTCB200_API void rtcSetGeometryInstancedScene(RTCGeometry geometry, RTCScene scene);
+RTCB200_API void rtcSetGeometryTransform(RTCGeometry geometry, unsigned int timeStep, enum RTCFormat format, const void* xfm);
+RTCB200_API void rtcGetGeometryTransform(RTCGeometry geometry, float time, enum RTCFormat format, void* xfm);
+RTCB200_API void rtcGetGeometryTransformEx(RTCGeometry geometry, unsigned int instPrimID, float time, enum RTCFormat format, void* xfm);
+RTCB200_API void rtcGetGeometryTransformFromScene(RTCScene scene, unsigned int geomID, float time, enum RTCFormat format, void* xfm);
+RTCB200_API void rtcGetGeometryTransformFromTraversable(RTCTraversable traversable, unsigned int geomID, float time, enum RTCFormat format, void* xfm);
 /* host callbacks: a non-NULL function raises RTC_ERROR_INVALID_OPERATION (cannot run on the device) */
 RTCB200_API void rtcSetGeometryIntersectFilterFunction(RTCGeometry geometry, RTCFilterFunctionN filter);
 RTCB200_API void rtcSetGeometryOccludedFilterFunction(RTCGeometry geometry, RTCFilterFunctionN filter);
@@ -367,10 +380,6 @@ RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryFirstHalfEdge)
 RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryNextHalfEdge)
 RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryOppositeHalfEdge)
 RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryPreviousHalfEdge)
-RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryTransform)
-RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryTransformEx)
-RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryTransformFromScene)
-RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryTransformFromTraversable)
 RTCB200_DECLARE_UNSUPPORTED(rtcInterpolate)
 RTCB200_DECLARE_UNSUPPORTED(rtcInterpolateN)
 RTCB200_DECLARE_UNSUPPORTED(rtcInvokeIntersectFilterFromGeometry)
@@ -385,7 +394,6 @@ RTCB200_DECLARE_UNSUPPORTED(rtcReleaseBVH)
 RTCB200_DECLARE_UNSUPPORTED(rtcRetainBVH)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryBoundsFunction)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryDisplacementFunction)
-RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryInstancedScene)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryInstancedScenes)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryIntersectFunction)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryOccludedFunction)
@@ -393,7 +401,6 @@ RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryPointQueryFunction)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometrySubdivisionMode)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTessellationRate)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTopologyCount)
-RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTransform)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTransformQuaternion)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryUserPrimitiveCount)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryVertexAttributeTopology)

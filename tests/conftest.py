@@ -29,6 +29,25 @@ def load_golden(name, robust=False):
             rec(z["occluded_out" + sfx], RAY_DTYPE), z["bounds"])
 
 
+def load_golden_instances(name="instances"):
+    """tests/golden/instances.npz -> dict(child=[meshes], top=[meshes], xfms[n,12], inst_masks, first_inst, rays_in,
+    intersect_out, occluded_out, bounds): the two-level scene of make_golden.run_instances and the reference's outputs."""
+    from embree_b200.rtc import RAYHIT_DTYPE, RAY_DTYPE, aligned_empty
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+    def rec(a, dt):
+        out = aligned_empty(a.shape[0], dt)
+        out.view(np.uint8).reshape(a.shape)[:] = a
+        return out
+
+    def meshes(pre, n):
+        return [(z[f"{pre}v{i}"], z[f"{pre}t{i}"], int(z[f"{pre}gid{i}"]), int(z[f"{pre}mask{i}"])) for i in range(n)]
+    return dict(child=meshes("c", int(z["n_child"])), top=meshes("m", int(z["n_top"])), xfms=z["xfms"],
+                inst_masks=z["inst_masks"], first_inst=int(z["first_inst"]), rays_in=rec(z["rays_in"], RAYHIT_DTYPE),
+                intersect_out=rec(z["intersect_out"], RAYHIT_DTYPE), occluded_out=rec(z["occluded_out"], RAY_DTYPE),
+                bounds=z["bounds"])
+
+
 GOLDEN = ["cube_ground", "sphere21", "terrain_masks"]
 
 

@@ -70,6 +70,56 @@ def run_flags(name, meshes, rayhits, flags):
     return d
 
 
+def instance_transforms(n, seed):
+    """n affine transforms (rotation * non-uniform scale + translation), 12 floats each: columns vx | vy | vz | p."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        m = (q * rng.uniform(0.5, 1.5, 3)).astype(np.float32)      # columns scaled
+        p = rng.uniform(-4, 4, 3).astype(np.float32)
+        out.append(np.concatenate([m.T.reshape(-1), p]).astype(np.float32))
+    return np.stack(out)
+
+
+def run_instances(name, child_meshes, top_meshes, xfms, inst_masks, rayhits):
+    """Two-level scene (tutorials/instanced_geometry): `top_meshes` + one RTC_GEOMETRY_TYPE_INSTANCE of the child scene
+    per row of xfms, attached after the meshes (geomIDs len(top_meshes)...)."""
+    R = load_reference()
+    dev = R.new_device(None)
+    child = R.rtcNewScene(dev)
+    keep = [R.add_triangle_mesh(dev, child, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in child_meshes]
+    R.rtcCommitScene(child)
+    top = R.rtcNewScene(dev)
+    keep += [R.add_triangle_mesh(dev, top, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in top_meshes]
+    first = max([g for (_, _, g, _) in top_meshes] + [-1]) + 1
+    for i, m in enumerate(xfms):
+        R.add_instance(dev, top, child, m, mask=int(inst_masks[i]), geom_id=first + i)
+    R.rtcCommitScene(top)
+    R.check(dev)
+    b = RTCBounds()
+    R.rtcGetSceneBounds(top, C.byref(b))
+    out_i = R.intersect(top, rayhits.copy(), "1")
+    out_o = R.occluded(top, rays_of(rayhits), "1")
+    out_8 = R.intersect(top, rayhits.copy(), "8")
+    assert (out_8["primID"] == out_i["primID"]).all() and (out_8["instID"] == out_i["instID"]).all()
+    R.check(dev)
+    d = dict(rays_in=rayhits.view(np.uint8).reshape(-1, 96), intersect_out=out_i.view(np.uint8).reshape(-1, 96),
+             occluded_out=out_o.view(np.uint8).reshape(-1, 48),
+             bounds=np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32),
+             n_child=np.array(len(child_meshes)), n_top=np.array(len(top_meshes)), xfms=xfms,
+             inst_masks=np.asarray(inst_masks, np.uint32), first_inst=np.array(first, np.uint32))
+    for pre, ms in (("c", child_meshes), ("m", top_meshes)):
+        for i, (v, t, gid, mask) in enumerate(ms):
+            d[f"{pre}v{i}"], d[f"{pre}t{i}"], d[f"{pre}gid{i}"], d[f"{pre}mask{i}"] = v, t, np.array(gid, np.uint32), np.array(mask, np.uint32)
+    print(f"{name}: {len(rayhits)} rays, hit rate {(out_i['geomID'] != 0xFFFFFFFF).mean():.3f}, "
+          f"instance hits {(out_i['instID'] != 0xFFFFFFFF).mean():.3f}, occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    R.rtcReleaseScene(top)
+    R.rtcReleaseScene(child)
+    R.rtcReleaseDevice(dev)
+
+
 def main():
     # 1. the triangle_geometry tutorial scene: cube (geomID 0) + ground plane (geomID 1), camera-like + random rays
     (cv, ct), (gv, gt) = scenes.cube_and_ground()
@@ -100,6 +150,20 @@ def main():
     r["mask"][2::4] = 0x4
     r["mask"][3::4] = 0x3
     run("terrain_masks", [(tv, tt, 0, 0x1), (pv, pt, 3, 0x2)], r)
+    # 4. single-level instancing: a ground plane + 7 transformed instances of a two-mesh child scene, with instance and
+    #    geometry masks selecting subsets
+    sv, st = scenes.triangle_sphere(10)
+    sv2 = (sv * np.float32(0.5) + np.float32([1.2, 0, 0])).astype(np.float32)
+    gv, gt = scenes.triangle_plane((-8, -3, -8), (16, 0, 0), (0, 0, 16), 4, 4)
+    xf = instance_transforms(7, 11)
+    org, d = random_rays_box(4096, -6, 6, 12)
+    r = make_rayhits(org, d)
+    r["mask"][0::5] = 0x2
+    r["mask"][1::5] = 0x4
+    r["tnear"][2::7] = 1.0
+    r["id"] = np.arange(len(r))
+    run_instances("instances", [(sv, st, 0, 0xFFFFFFFF), (sv2, st, 1, 0x3)], [(gv, gt, 0, 0xFFFFFFFF)], xf,
+                  [0xFFFFFFFF if i % 3 else 0x5 for i in range(7)], r)
 
 
 if __name__ == "__main__":

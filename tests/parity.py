@@ -22,6 +22,7 @@ class Oracle:
         d.orc_free.argtypes = [C.c_void_p]
         d.orc_add_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint]
         d.orc_commit.argtypes = [C.c_void_p]
+        d.orc_add_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
         d.orc_set_robust.argtypes = [C.c_void_p, C.c_int]
         d.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
         d.orc_get_bounds.argtypes = [C.c_void_p, C.c_void_p]
@@ -30,9 +31,10 @@ class Oracle:
         d.orc_api_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_uint, C.c_int]
         self.d = d
 
-    def scene(self, meshes, robust=False):
-        """meshes: list of (vertices[nv,3] f32, indices[nt,3] u32, geomID, mask).  Returns an OracleScene."""
-        return OracleScene(self, meshes, robust)
+    def scene(self, meshes, robust=False, instances=()):
+        """meshes: list of (vertices[nv,3] f32, indices[nt,3] u32, geomID, mask); instances: list of
+        (child OracleScene, xfm[12] column-major 3x4, geomID, mask).  Returns an OracleScene."""
+        return OracleScene(self, meshes, robust, instances)
 
     def trace(self, v, t, rayhits, occluded=False, mask=0xFFFFFFFF, nthreads=1):
         sc = self.scene([(v, t, 0, mask)])
@@ -42,7 +44,7 @@ class Oracle:
 
 
 class OracleScene:
-    def __init__(self, o, meshes, robust=False):
+    def __init__(self, o, meshes, robust=False, instances=()):
         self.o = o
         self.h = o.d.orc_new()
         o.d.orc_set_robust(self.h, 1 if robust else 0)
@@ -52,6 +54,10 @@ class OracleScene:
             t = np.ascontiguousarray(t, np.uint32).reshape(-1, 3)
             self.keep += [v, t]
             o.d.orc_add_mesh(self.h, v.ctypes.data, 12, v.shape[0], t.ctypes.data, 12, t.shape[0], gid, mask)
+        for (child, xfm, gid, mask) in instances:
+            m = np.ascontiguousarray(xfm, np.float32).reshape(12)
+            self.keep += [child, m]
+            o.d.orc_add_instance(self.h, child.h, m.ctypes.data, gid, mask)
         o.d.orc_commit(self.h)
 
     def trace(self, rays, occluded=False, nthreads=1):

@@ -12,9 +12,10 @@ import pytest
 
 from embree_b200 import scenes
 from embree_b200.rtc import (RTCBounds, RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM, RTC_FORMAT_FLOAT3, RTC_FORMAT_UINT3,
-                             RTC_BUFFER_TYPE_INDEX, RTC_BUFFER_TYPE_VERTEX, RTC_GEOMETRY_TYPE_TRIANGLE, aligned_empty,
+                             RTC_BUFFER_TYPE_INDEX, RTC_BUFFER_TYPE_VERTEX, RTC_GEOMETRY_TYPE_TRIANGLE, RTC_GEOMETRY_TYPE_INSTANCE, RTC_FORMAT_FLOAT3X4_ROW_MAJOR,
+                             RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR, aligned_empty,
                              make_rayhits, rays_of, to_packets, from_packets, _ptr)
-from tests.conftest import GOLDEN, load_golden
+from tests.conftest import GOLDEN, load_golden, load_golden_instances
 from tests.parity import compare_hits, load_reference
 
 pytestmark = pytest.mark.gpu
@@ -271,6 +272,136 @@ def test_commit_state_machine_and_errors(b200):
     assert lib.rtcGetDeviceError(dev) == 0
     lib.rtcReleaseGeometry(g)
     lib.rtcReleaseScene(sc)
+
+
+def build_instanced(lib, dev, g, quality=RTC_BUILD_QUALITY_MEDIUM):
+    child, keep = build_scene(lib, dev, g["child"], quality)
+    top = lib.rtcNewScene(dev)
+    lib.rtcSetSceneBuildQuality(top, quality)
+    for (v, t, gid, mask) in g["top"]:
+        keep.append(lib.add_triangle_mesh(dev, top, v, t, mask=mask, geom_id=gid)[1])
+    for i, m in enumerate(g["xfms"]):
+        lib.add_instance(dev, top, child, m, mask=int(g["inst_masks"][i]), geom_id=g["first_inst"] + i)
+    lib.rtcCommitScene(top)
+    lib.check(dev)
+    return top, child, keep
+
+
+@pytest.mark.parametrize("quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
+def test_instances_golden_all_entry_points(b200, quality):
+    """Single-level instancing (tutorials/instanced_geometry, instance_intersector.cpp:15-67) against the reference's own
+    outputs: geomID / primID / instID / instPrimID exact, object-space Ng bit-exact, t/u/v within 1e-4 (the device
+    intersects the world-space triangle, the reference the object-space one with a transformed ray)."""
+    lib, dev = b200
+    g = load_golden_instances()
+    top, child, keep = build_instanced(lib, dev, g, quality)
+    want = g["intersect_out"]
+    for mode in MODES:
+        got = lib.intersect(top, g["rays_in"].copy(), mode)
+        rep = assert_parity(want, got)
+        assert rep["ng_bit_exact"], (mode, rep)
+        assert (got["instPrimID"] == want["instPrimID"]).all(), mode
+        occ = lib.occluded(top, rays_of(g["rays_in"]), mode)
+        assert (occ["tfar"].view(np.uint32) == g["occluded_out"]["tfar"].view(np.uint32)).all(), mode
+    b = RTCBounds()
+    lib.rtcGetSceneBounds(top, C.byref(b))
+    assert np.array_equal(np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32), g["bounds"])
+    lib.rtcReleaseScene(top)
+    lib.rtcReleaseScene(child)
+
+
+def test_instances_many_vs_oracle(b200, oracle):
+    """400 instances of a 3.2k-triangle mesh (1.3M flattened triangles) + 200k random rays against the C oracle's
+    two-level traversal; transforms include mirrored (negative determinant) and strongly anisotropic ones."""
+    lib, dev = b200
+    rng = np.random.RandomState(21)
+    v, t = scenes.triangle_sphere(40)
+    xf = []
+    for i in range(400):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        sc = rng.uniform(0.3, 2.0, 3) * (1 if i % 5 else -1)
+        m = (q * sc).astype(np.float32)
+        xf.append(np.concatenate([m.T.reshape(-1), rng.uniform(-20, 20, 3)]).astype(np.float32))
+    g = dict(child=[(v, t, 0, 0xFFFFFFFF)], top=[], xfms=np.stack(xf), inst_masks=np.full(400, 0xFFFFFFFF, np.uint32), first_inst=0)
+    top, child, keep = build_instanced(lib, dev, g)
+    org = rng.uniform(-25, 25, (200000, 3)).astype(np.float32)
+    d = rng.normal(size=(200000, 3)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    got = lib.intersect(top, rays.copy(), "1M")
+    oc = oracle.scene(g["child"])
+    ot = oracle.scene([], instances=[(oc, m, i, 0xFFFFFFFF) for i, m in enumerate(xf)])
+    want = ot.trace(rays.copy(), nthreads=16)
+    rep = compare_hits(want, got, TOL)
+    assert rep["hits"] > 20000, rep
+    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] <= 2 and rep["tie"] <= 4, rep   # overlapping instances: exact ties are order-dependent
+    assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= TOL and rep["ng_bit_exact"], rep
+    occ = lib.occluded(top, rays_of(rays), "1M")
+    assert ((occ["tfar"] == -np.inf) != (got["geomID"] != 0xFFFFFFFF)).sum() == 0
+    ot.free()
+    oc.free()
+    lib.rtcReleaseScene(top)
+    lib.rtcReleaseScene(child)
+
+
+def test_instance_api_and_errors(b200):
+    """rtcSetGeometryTransform formats (rtcore.cpp:1408-1439), get/set round trip, commit protocol of instances."""
+    lib, dev = b200
+    v, t = scenes.triangle_sphere(8)
+    child, keep = build_scene(lib, dev, [(v, t, 0, 0xFFFFFFFF)])
+    g = lib.rtcNewGeometry(dev, RTC_GEOMETRY_TYPE_INSTANCE)
+    top = lib.rtcNewScene(dev)
+    lib.rtcAttachGeometry(top, g)
+    lib.rtcCommitGeometry(g)
+    lib.rtcCommitScene(top)
+    assert lib.rtcGetDeviceError(dev) == 3                      # no instanced scene set
+    lib.rtcSetGeometryInstancedScene(g, child)
+    col = np.array([2, 0, 0, 0, 2, 0, 0, 0, 2, 5, 6, 7], np.float32)   # scale 2, translate (5,6,7)
+    row = np.array([2, 0, 0, 5, 0, 2, 0, 6, 0, 0, 2, 7], np.float32)
+    c44 = np.array([2, 0, 0, 0, 0, 2, 0, 0, 0, 0, 2, 0, 5, 6, 7, 1], np.float32)
+    for fmt, m in ((RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, col), (RTC_FORMAT_FLOAT3X4_ROW_MAJOR, row), (RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR, c44)):
+        lib.rtcSetGeometryTransform(g, 0, fmt, _ptr(m))
+        lib.rtcCommitGeometry(g)
+        lib.rtcCommitScene(top)
+        lib.check(dev)
+        out = lib.intersect(top, make_rayhits([[5, 6, 0]], [[0, 0, 1]]), "1")
+        assert out["geomID"][0] == 0 and out["instID"][0] == 0 and abs(out["tfar"][0] - 5.0) < 1e-5, (fmt, out)
+        for f2, m2 in ((RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, col), (RTC_FORMAT_FLOAT3X4_ROW_MAJOR, row), (RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR, c44)):
+            back = np.zeros(len(m2), np.float32)
+            lib.rtcGetGeometryTransform(g, 0.0, f2, _ptr(back))
+            assert np.array_equal(back, m2), (fmt, f2, back)
+    lib.rtcSetGeometryTransform(g, 0, RTC_FORMAT_FLOAT3, _ptr(col))
+    assert lib.rtcGetDeviceError(dev) == 3                      # invalid matrix format
+    lib.rtcSetGeometryTransform(g, 1, RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, _ptr(col))
+    assert lib.rtcGetDeviceError(dev) == 3                      # motion blur time steps are out of scope
+    mesh = lib.rtcNewGeometry(dev, RTC_GEOMETRY_TYPE_TRIANGLE)
+    lib.rtcSetGeometryInstancedScene(mesh, child)
+    assert lib.rtcGetDeviceError(dev) == 3                      # not an instance
+    lib.rtcReleaseGeometry(mesh)
+    # moving the instance = set transform + commit geometry + commit scene (dynamic_scene / instanced_geometry tutorials)
+    col[9:] = (0, 0, 10)
+    lib.rtcSetGeometryTransform(g, 0, RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, _ptr(col))
+    lib.rtcCommitGeometry(g)
+    lib.rtcCommitScene(top)
+    out = lib.intersect(top, make_rayhits([[0, 0, 0]], [[0, 0, 1]]), "1")
+    assert abs(out["tfar"][0] - 8.0) < 1e-5 and out["instID"][0] == 0
+    # instance mask and ray mask (instance_intersector.cpp:19-23)
+    lib.rtcSetGeometryMask(g, 0x4)
+    lib.rtcCommitGeometry(g)
+    lib.rtcCommitScene(top)
+    assert lib.intersect(top, make_rayhits([[0, 0, 0]], [[0, 0, 1]], mask=0x3), "1")["geomID"][0] == 0xFFFFFFFF
+    assert lib.intersect(top, make_rayhits([[0, 0, 0]], [[0, 0, 1]], mask=0x4), "1")["geomID"][0] == 0
+    # two-level nesting is rejected (RTC_MAX_INSTANCE_LEVEL_COUNT == 1)
+    top2 = lib.rtcNewScene(dev)
+    lib.add_instance(dev, top2, top, col)
+    lib.rtcCommitScene(top2)
+    assert lib.rtcGetDeviceError(dev) == 3
+    # the instanced scene stays alive through the instance's reference
+    lib.rtcReleaseScene(child)
+    assert lib.intersect(top, make_rayhits([[0, 0, 0]], [[0, 0, 1]], mask=0x4), "1")["geomID"][0] == 0
+    lib.check(dev)
+    lib.rtcReleaseGeometry(g)
+    lib.rtcReleaseScene(top)
+    lib.rtcReleaseScene(top2)
 
 
 def test_update_and_recommit(b200):

@@ -7,7 +7,7 @@ import pytest
 
 from embree_b200 import scenes
 from embree_b200.rtc import make_rayhits, rays_of
-from tests.conftest import GOLDEN, load_golden
+from tests.conftest import GOLDEN, load_golden, load_golden_instances
 from tests.parity import compare_hits, load_reference
 
 
@@ -51,6 +51,31 @@ def test_oracle_vs_golden(oracle, name, robust):
     assert (occ["tfar"].view(np.uint32) == want_o["tfar"].view(np.uint32)).all()
     assert np.array_equal(sc.bounds(), bounds)
     sc.free()
+
+
+def oracle_instanced_scene(oracle, g):
+    child = oracle.scene(g["child"])
+    top = oracle.scene(g["top"], instances=[(child, m, g["first_inst"] + i, int(g["inst_masks"][i])) for i, m in enumerate(g["xfms"])])
+    return top, child
+
+
+def test_oracle_instances_vs_golden(oracle):
+    """Single-level instancing (instance_intersector.cpp:15-67) against the reference's outputs: ids (incl. instID) and
+    the object-space Ng exact; t/u/v agree to an ulp or two."""
+    g = load_golden_instances()
+    top, child = oracle_instanced_scene(oracle, g)
+    got = top.trace(g["rays_in"].copy())
+    want = g["intersect_out"]
+    rep = compare_hits(want, got)
+    assert (want["instID"] != 0xFFFFFFFF).sum() > 200
+    assert rep["id_mismatch"] == 0 and rep["tie"] == 0 and rep["hit_miss_disagree"] == 0, rep
+    assert rep["max_rel_t"] <= 1e-6 and rep["max_abs_uv"] <= 1e-6 and rep["ng_bit_exact"] and rep["miss_untouched"], rep
+    assert (got["instPrimID"] == want["instPrimID"]).all()
+    occ = top.trace(rays_of(g["rays_in"]), occluded=True)
+    assert (occ["tfar"].view(np.uint32) == g["occluded_out"]["tfar"].view(np.uint32)).all()
+    assert np.array_equal(top.bounds(), g["bounds"])
+    top.free()
+    child.free()
 
 
 def test_oracle_vs_reference_live(oracle):
