@@ -62,10 +62,23 @@ __device__ __forceinline__ int find_geom(const uint32_t* __restrict__ offs, int 
 }
 
 __device__ __forceinline__ void load_tri_verts(const GeomDesc& g, uint32_t lp, float v[9], bool& ok, bool world) {
-  const uint32_t* ip = reinterpret_cast<const uint32_t*>(g.idx + (uint64_t)lp * g.istride);
-  const uint32_t i0 = ip[0], i1 = ip[1], i2 = ip[2];
-  ok = (i0 < g.nverts) & (i1 < g.nverts) & (i2 < g.nverts);          // scene_triangle_mesh.h:197-199
-  if (!ok) return;
+  uint32_t i0, i1, i2;
+  if (g.is_quad) {   // halves (v0,v1,v3) and (v2,v1,v3); the whole quad must be valid (scene_quad_mesh.h:186-203)
+    const uint32_t* ip = reinterpret_cast<const uint32_t*>(g.idx + (uint64_t)(lp >> 1) * g.istride);
+    const uint32_t q0 = ip[0], q1 = ip[1], q2 = ip[2], q3 = ip[3];
+    ok = (q0 < g.nverts) & (q1 < g.nverts) & (q2 < g.nverts) & (q3 < g.nverts);
+    if (!ok) return;
+    const uint32_t other = (lp & 1u) ? q0 : q2;   // the vertex this half does not use still has to be finite
+    const float* po = reinterpret_cast<const float*>(g.verts + (uint64_t)other * g.vstride);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ok &= (po[k] > -kFltLarge) & (po[k] < kFltLarge);
+    i0 = (lp & 1u) ? q2 : q0; i1 = q1; i2 = q3;
+  } else {
+    const uint32_t* ip = reinterpret_cast<const uint32_t*>(g.idx + (uint64_t)lp * g.istride);
+    i0 = ip[0]; i1 = ip[1]; i2 = ip[2];
+    ok = (i0 < g.nverts) & (i1 < g.nverts) & (i2 < g.nverts);          // scene_triangle_mesh.h:197-199
+    if (!ok) return;
+  }
   const float* p0 = reinterpret_cast<const float*>(g.verts + (uint64_t)i0 * g.vstride);
   const float* p1 = reinterpret_cast<const float*>(g.verts + (uint64_t)i1 * g.vstride);
   const float* p2 = reinterpret_cast<const float*>(g.verts + (uint64_t)i2 * g.vstride);
@@ -412,7 +425,7 @@ __global__ void __launch_bounds__(256) collapse_dp(const Node2* __restrict__ nod
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ offs, int ngeoms,
                                                  const uint32_t* __restrict__ tri_src, uint32_t ntris, TriRec* __restrict__ out, int robust,
-                                                 int instanced) {
+                                                 int general) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntris) return;
   const uint32_t p = tri_src[t];
@@ -422,7 +435,8 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
   bool ok;
   load_tri_verts(gd, p - offs[g], v, ok, false);   // instances keep OBJECT-space triangles (see trace.cu to_object_space)
   float4 a, b, c;
-  a.x = v[0]; a.y = v[1]; a.z = v[2]; a.w = __uint_as_float(p - offs[g]);
+  const uint32_t lp = p - offs[g];   // quads: primID = quad index, bit 31 marks the second half (uv / Ng fix-up in trace.cu)
+  a.x = v[0]; a.y = v[1]; a.z = v[2]; a.w = __uint_as_float(gd.is_quad ? ((lp >> 1) | ((lp & 1u) << 31)) : lp);
   if (robust) {   // Triangle4v: full vertices for the Pluecker test (kernels/geometry/trianglev.h)
     b.x = v[3]; b.y = v[4]; b.z = v[5];
     c.x = v[6]; c.y = v[7]; c.z = v[8];
@@ -430,7 +444,7 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
     b.x = __fsub_rn(v[0], v[3]); b.y = __fsub_rn(v[1], v[4]); b.z = __fsub_rn(v[2], v[5]);
     c.x = __fsub_rn(v[6], v[0]); c.y = __fsub_rn(v[7], v[1]); c.z = __fsub_rn(v[8], v[2]);
   }
-  b.w = __uint_as_float(instanced ? (uint32_t)g : gd.geomID);   // instanced scenes: descriptor index (geomID/instID via table)
+  b.w = __uint_as_float(general ? (uint32_t)g : gd.geomID);   // general scenes: descriptor index (geomID/instID via table)
   c.w = __uint_as_float(gd.mask);
   float4* dst = reinterpret_cast<float4*>(&out[t]);
   dst[0] = a; dst[1] = b; dst[2] = c;
@@ -598,7 +612,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   DevBuf<TriRec> d_tris;
   DevBuf<Node8> d_final;
   CK(d_tris.alloc(n, st));
-  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, d_tris.p, s.robust, s.instanced);
+  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, d_trisrc.p, n, d_tris.p, s.robust, s.general);
   count_launch();
   CK(d_final.alloc(end, st));
   CK(cudaMemcpyAsync(d_final.p, n8, (size_t)end * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
@@ -608,7 +622,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   float ms = 0;
   cudaEventElapsedTime(&ms, ev0, ev1);
   s.nodes = d_final.p; s.tris = d_tris.p; d_final.p = nullptr; d_tris.p = nullptr;   // ownership moves to the scene
-  if (s.instanced) { s.d_descs = d_geoms.p; d_geoms.p = nullptr; }
+  if (s.general) { s.d_descs = d_geoms.p; d_geoms.p = nullptr; }
   s.num_nodes = end; s.num_tris = n; s.root_valid = 1;
   s.build_ms = ms; s.sah_cost = hinfo.sah; s.max_depth = depth;
   return 0;

@@ -257,17 +257,20 @@ void commit_scene(SceneImpl* s) {
   s->deviceBuffers.clear();
   std::vector<rtk::GeomDesc> descs;
   std::unordered_map<GeometryImpl*, std::pair<void*, void*>> uploaded;   // a mesh instanced many times is uploaded once
-  bool instanced = false;
+  bool instanced = false, quads = false;
   float instBounds[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
   auto add_mesh = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
-    const size_t ntris = g->indices.count, nverts = g->vertices.count;
+    const bool quad = g->type == RTC_GEOMETRY_TYPE_QUAD;
+    const size_t nprims = g->indices.count, nverts = g->vertices.count;
+    const size_t ntris = quad ? 2 * nprims : nprims;   // a quad contributes its two halves (quad_intersector_moeller.h:190-200)
     if (ntris == 0 || !g->indices.buf) return;
     if (!g->vertices.buf) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer not set");
     if (ntris > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "mesh too large");
+    quads |= quad;
     auto it = uploaded.find(g);
     if (it == uploaded.end()) {
       const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 12 : 0;
-      const size_t ibytes = (ntris - 1) * g->indices.stride + 12;
+      const size_t ibytes = (nprims - 1) * g->indices.stride + (quad ? 16 : 12);
       void *dv = nullptr, *di = nullptr;
       cuda_check(cudaMallocAsync(&dv, vbytes ? vbytes : 16, 0), "cudaMallocAsync(vertices)");
       s->deviceBuffers.push_back(dv);
@@ -281,7 +284,7 @@ void commit_scene(SceneImpl* s) {
     d.verts = static_cast<const uint8_t*>(it->second.first); d.idx = static_cast<const uint8_t*>(it->second.second);
     d.vstride = g->vertices.stride; d.istride = g->indices.stride;
     d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)ntris;
-    d.geomID = geomID; d.mask = g->mask;
+    d.geomID = geomID; d.mask = g->mask; d.is_quad = quad ? 1 : 0;
     if (xfm) {
       d.has_xfm = 1; d.instID = instID; d.inst_mask = instMask; d.skip_bounds = 1;
       memcpy(d.xfm, xfm, sizeof d.xfm);
@@ -292,7 +295,7 @@ void commit_scene(SceneImpl* s) {
   for (size_t id = 0; id < geoms.size(); ++id) {
     GeometryImpl* g = geoms[id];
     if (!g || !g->enabled) continue;
-    if (g->type == RTC_GEOMETRY_TYPE_TRIANGLE) { add_mesh(g, (uint32_t)id, nullptr, nullptr, RTC_INVALID_GEOMETRY_ID, 0xFFFFFFFFu); continue; }
+    if (g->type != RTC_GEOMETRY_TYPE_INSTANCE) { add_mesh(g, (uint32_t)id, nullptr, nullptr, RTC_INVALID_GEOMETRY_ID, 0xFFFFFFFFu); continue; }
     // RTC_GEOMETRY_TYPE_INSTANCE (kernels/geometry/instance_intersector.cpp:15-38): flattened here -- every mesh of the
     // instanced scene enters the top-level BVH through the instance transform; hits report the instance id, the
     // CHILD scene's geomID / primID and an object-space Ng exactly as the reference's two-level traversal does.
@@ -305,7 +308,7 @@ void commit_scene(SceneImpl* s) {
     for (size_t cid = 0; cid < cgeoms.size(); ++cid) {
       GeometryImpl* cg = cgeoms[cid];
       if (!cg || !cg->enabled) continue;
-      if (cg->type != RTC_GEOMETRY_TYPE_TRIANGLE)   // RTC_MAX_INSTANCE_LEVEL_COUNT == 1, as in the reference's default build
+      if (cg->type == RTC_GEOMETRY_TYPE_INSTANCE)   // RTC_MAX_INSTANCE_LEVEL_COUNT == 1, as in the reference's default build
         fail(RTC_ERROR_INVALID_OPERATION, "multi-level instancing is not supported (RTC_MAX_INSTANCE_LEVEL_COUNT is 1)");
       add_mesh(cg, (uint32_t)cid, g->xfm, g->w2l, (uint32_t)id, g->mask);
     }
@@ -320,7 +323,7 @@ void commit_scene(SceneImpl* s) {
         }
       }
   }
-  s->gpu.instanced = instanced ? 1 : 0;
+  s->gpu.general = (instanced || quads) ? 1 : 0;
   // quality -> builder (scene.cpp:163-206: LOW = Morton two-level builder, MEDIUM/HIGH = SAH).  The env override
   // exists for A/B measurements of the two device builders only.
   rtk::BuilderKind kind = (s->quality == RTC_BUILD_QUALITY_LOW) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
@@ -389,7 +392,7 @@ rtk::TraceParams make_params(SceneImpl* s, void* rays, const int* valid, unsigne
                              uint32_t instPrimID) {
   rtk::TraceParams p;
   p.nodes = s->gpu.nodes; p.tris = s->gpu.tris; p.root_valid = s->gpu.root_valid; p.robust = s->gpu.robust;
-  p.descs = s->gpu.instanced ? s->gpu.d_descs : nullptr;
+  p.descs = s->gpu.general ? s->gpu.d_descs : nullptr;
   p.rays = rays; p.valid = valid; p.n = n; p.instID = instID; p.instPrimID = instPrimID;
   p.stat = s->statCounters ? s->gpu.d_stat : nullptr;
   return p;
@@ -611,8 +614,8 @@ void rtcReleaseBuffer(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; AP
 RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
   API_BEGIN
   VERIFY_HANDLE(h);
-  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_INSTANCE)
-    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE and RTC_GEOMETRY_TYPE_INSTANCE are supported by the B200 back-end");
+  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE)
+    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD and _INSTANCE are supported by the B200 back-end");
   GeometryImpl* g = new GeometryImpl(D(h));
   g->type = type;
   return reinterpret_cast<RTCGeometry>(g);
@@ -638,8 +641,8 @@ void rtcSetGeometryBuildQuality(RTCGeometry g, enum RTCBuildQuality q) {
 }
 
 static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFormat format, BufferImpl* buf, size_t off, size_t stride, size_t num) {
-  // scene_triangle_mesh.cpp:35-80
-  if (g->type != RTC_GEOMETRY_TYPE_TRIANGLE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+  // scene_triangle_mesh.cpp:35-80, scene_quad_mesh.cpp:35-80
+  if (g->type == RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
   if (((size_t)(buf->ptr) + off) & 3 || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
   if (num > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_ARGUMENT, "buffer too large");
   if (type == RTC_BUFFER_TYPE_VERTEX) {
@@ -653,7 +656,7 @@ static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFo
     g->attribs[slot].set(buf, off, stride, num, format);
   } else if (type == RTC_BUFFER_TYPE_INDEX) {
     if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot");
-    if (format != RTC_FORMAT_UINT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid index buffer format");
+    if (format != (g->type == RTC_GEOMETRY_TYPE_QUAD ? RTC_FORMAT_UINT4 : RTC_FORMAT_UINT3)) fail(RTC_ERROR_INVALID_OPERATION, "invalid index buffer format");
     g->indices.set(buf, off, stride, num, format);
   } else
     fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");

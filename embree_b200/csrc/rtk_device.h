@@ -15,12 +15,15 @@ struct GeomDesc {
   const uint8_t* verts;  // first vertex (byteOffset applied)
   const uint8_t* idx;    // first index triple
   uint64_t vstride, istride;
-  uint32_t nverts, ntris;
+  uint32_t nverts, ntris;   // ntris = 2 * quads for a quad mesh (each half is one record)
   uint32_t geomID, mask;
   // instancing (RTC_GEOMETRY_TYPE_INSTANCE, flattened at commit): this mesh is seen through the instance transform
   // xfm = (vx | vy | vz | p) columns of local2world (places the triangles in the world-space BVH), w2l its inverse
   // (takes the ray to the object-space triangle records); hits report instID and must also pass inst_mask.
   uint32_t has_xfm = 0, instID = 0xFFFFFFFFu, inst_mask = 0xFFFFFFFFu, skip_bounds = 0;
+  // quad mesh (RTC_GEOMETRY_TYPE_QUAD): idx holds 4 indices per primitive; local prim 2q / 2q+1 are the halves
+  // (v0,v1,v3) / (v2,v1,v3) of quad q exactly as quad_intersector_moeller.h:190-200 splits them.
+  uint32_t is_quad = 0, pad_ = 0;
   float xfm[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
   float w2l[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
 };
@@ -34,8 +37,8 @@ struct SceneGPU {
   uint32_t num_nodes = 0, num_tris = 0;
   uint32_t root_valid = 0;              // 0: empty scene -> queries return immediately
   int robust = 0;                       // RTC_SCENE_FLAG_ROBUST: leaf records are (v0, v1, v2), Pluecker intersector
-  int instanced = 0;                    // scene contains instances: records carry a descriptor index instead of geomID
-  GeomDesc* d_descs = nullptr;          // device copy of the mesh descriptors (kept while instanced)
+  int general = 0;                      // scene has instances or quads: records carry a descriptor index instead of geomID
+  GeomDesc* d_descs = nullptr;          // device copy of the mesh descriptors (kept while general)
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // lower xyz, upper xyz of all valid triangles (world space, instances flattened)
   float api_bounds[6] = {0, 0, 0, 0, 0, 0};  // the same without instanced triangles
   double build_ms = 0, sah_cost = 0;

@@ -130,7 +130,7 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 // node, slab-test its 8 children) for the lanes that want it, and at most one triangle step, batched across the warp;
 // the phases are warp-synchronous so lanes in the same phase execute together instead of serialising through a
 // per-thread while-while loop.  The top stack entry lives in registers; deeper entries in (L1-resident) local memory.
-template <int K, bool OCCLUDED, bool STATS, bool ROBUST, bool INSTANCED>
+template <int K, bool OCCLUDED, bool STATS, bool ROBUST, bool GENERAL>
 __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TraceParams p) {
   const bool USE_TMA = p.use_prefetch != 0;
   using IO = RayIO<K, OCCLUDED>;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
         if (STATS) ++st_tris;
         Ray lr = r;
         bool visible = (c.w & r.mask) != 0;
-        if (INSTANCED) {   // b.w = descriptor index: instance mask (instance_intersector.cpp:19-22) + object-space ray
+        if (GENERAL) {   // b.w = descriptor index: instance mask (instance_intersector.cpp:19-22) + object-space ray
           const GeomDesc& d = p.descs[b.w];
           visible = visible && (d.inst_mask & r.mask) != 0;
           if (d.has_xfm) to_object_space(d, lr);
@@ -270,7 +270,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
                                 __uint_as_float(c.z), ph)) {
             found = true;
             if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
-            else { tfar_tri = ph.t; pluecker_uv(ph, hit_u, hit_v); hit_tri = ti; }
+            else {
+              tfar_tri = ph.t; pluecker_uv(ph, hit_u, hit_v); hit_tri = ti;
+              if (GENERAL && (a.w >> 31)) {   // second half of a quad (QuadHitPlueckerM::finalize, AVX form)
+                const float u1 = sub_rn(1.0f, hit_u), v1 = sub_rn(1.0f, hit_v);
+                hit_u = v1; hit_v = u1;
+              }
+            }
           }
         } else {
           TriHit th;
@@ -281,7 +287,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
             if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }     // any hit terminates the ray
             else {
               const float rcpAbsDen = 1.0f / th.absDen;      // finalize(): t,u,v = T,U,V * rcp(absDen)
-              tfar_tri = th.T * rcpAbsDen; hit_u = th.U * rcpAbsDen; hit_v = th.V * rcpAbsDen;
+              tfar_tri = th.T * rcpAbsDen;
+              if (GENERAL && (a.w >> 31)) {   // second half of a quad: U' = absDen - V, V' = absDen - U (quad_intersector_moeller.h:196-198)
+                hit_u = sub_rn(th.absDen, th.V) * rcpAbsDen; hit_v = sub_rn(th.absDen, th.U) * rcpAbsDen;
+              } else { hit_u = th.U * rcpAbsDen; hit_v = th.V * rcpAbsDen; }
               hit_tri = ti;
             }
           }
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
             hit.primID = a.w; hit.geomID = b.w;
             uint32_t instID = p.instID, instPrimID = p.instPrimID;
             float lox = r.ox, loy = r.oy, loz = r.oz;   // ray origin in the space the record's triangle lives in
-            if (INSTANCED) {   // ids through the descriptor; Ng stays in OBJECT space as in the reference
+            if (GENERAL) {   // ids through the descriptor; Ng stays in OBJECT space as in the reference
               const GeomDesc& d = p.descs[b.w];
               hit.geomID = d.geomID;
               if (d.has_xfm) {
@@ -330,6 +339,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
               hit.ngx = msub(e2y, e1z, mul_rn(e2z, e1y));
               hit.ngy = msub(e2z, e1x, mul_rn(e2x, e1z));
               hit.ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
+            }
+            if (GENERAL && (a.w >> 31)) {   // quad halves share the quad's primID; the second one has flipped winding
+              hit.primID = a.w & 0x7FFFFFFFu;
+              hit.ngx = -hit.ngx; hit.ngy = -hit.ngy; hit.ngz = -hit.ngz;
             }
             IO::store_hit(p, ray_index, hit, instID, instPrimID);
             cngx = hit.ngx; cngy = hit.ngy; cngz = hit.ngz; cprim = hit.primID; cgeom = hit.geomID;

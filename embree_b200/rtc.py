@@ -14,10 +14,12 @@ import numpy as np
 
 RTC_INVALID_GEOMETRY_ID = 0xFFFFFFFF
 RTC_FORMAT_UINT3 = 0x5003
+RTC_FORMAT_UINT4 = 0x5004
 RTC_FORMAT_FLOAT3 = 0x9003
 RTC_BUFFER_TYPE_INDEX = 0
 RTC_BUFFER_TYPE_VERTEX = 1
 RTC_GEOMETRY_TYPE_TRIANGLE = 0
+RTC_GEOMETRY_TYPE_QUAD = 1
 RTC_GEOMETRY_TYPE_INSTANCE = 121
 RTC_FORMAT_FLOAT3X4_ROW_MAJOR = 0x9134
 RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR = 0x9234
@@ -265,6 +267,27 @@ class RTCLib:
             self.rtcSetGeometryMask(g, mask)
         if quality is not None:
             self.rtcSetGeometryBuildQuality(g, quality)
+        self.rtcCommitGeometry(g)
+        if geom_id is None:
+            gid = self.rtcAttachGeometry(scene, g)
+        else:
+            self.rtcAttachGeometryByID(scene, g, geom_id)
+            gid = geom_id
+        self.rtcReleaseGeometry(g)
+        return gid, (vpad, idx)
+
+    def add_quad_mesh(self, device, scene, vertices, indices, mask=None, geom_id=None):
+        """RTC_GEOMETRY_TYPE_QUAD with shared FLOAT3 vertex / UINT4 index buffers (quad (v0,v1,v2,v3); a triangle is a
+        quad with v2 == v3).  The arrays must stay alive."""
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        vpad = np.zeros(v.size + 4, np.float32)
+        vpad[:v.size] = v.reshape(-1)
+        idx = np.ascontiguousarray(indices, np.uint32).reshape(-1, 4)
+        g = self.rtcNewGeometry(device, RTC_GEOMETRY_TYPE_QUAD)
+        self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(vpad), 0, 12, v.shape[0])
+        self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT4, _ptr(idx), 0, 16, idx.shape[0])
+        if mask is not None:
+            self.rtcSetGeometryMask(g, mask)
         self.rtcCommitGeometry(g)
         if geom_id is None:
             gid = self.rtcAttachGeometry(scene, g)

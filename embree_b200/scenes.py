@@ -87,6 +87,15 @@ def terrain(n, seed=7, amplitude=0.15, octaves=5):
     return v, t
 
 
+def quad_terrain(n, seed=7, amplitude=0.15):
+    """(n+1)^2 height-field vertices over [-1,1]^2, n*n NON-planar quads (v0,v1,v2,v3 counter-clockwise seen from +y)."""
+    v, _ = terrain(n, seed=seed, amplitude=amplitude)
+    i, j = np.meshgrid(np.arange(n, dtype=np.uint32), np.arange(n, dtype=np.uint32), indexing="ij")
+    a = (i * (n + 1) + j).reshape(-1)
+    q = np.stack([a, a + 1, a + n + 2, a + n + 1], axis=1).astype(np.uint32)
+    return v, q
+
+
 def cube_and_ground():
     """The triangle_geometry tutorial scene (triangle_geometry_device.cpp:31-97): unit cube (12 tris, geomID 0)
     and a ground plane (2 tris, geomID 1)."""

@@ -127,7 +127,7 @@ def gen_headers(gen, stat):
     open(f"{gen}/include/embree4/rtcore_config.h", "w").write(t)
     # --- config.h from kernels/config.h.in
     t = open(f"{REF}/kernels/config.h.in").read()
-    cfg_on = {"EMBREE_RAY_MASK", "EMBREE_FILTER_FUNCTION", "EMBREE_GEOMETRY_TRIANGLE", "EMBREE_GEOMETRY_INSTANCE", "EMBREE_RAY_PACKETS"}
+    cfg_on = {"EMBREE_RAY_MASK", "EMBREE_FILTER_FUNCTION", "EMBREE_GEOMETRY_TRIANGLE", "EMBREE_GEOMETRY_QUAD", "EMBREE_GEOMETRY_INSTANCE", "EMBREE_RAY_PACKETS"}
     if stat:
         cfg_on.add("EMBREE_STAT_COUNTERS")
     t = re.sub(r"#cmakedefine (\w+)",

@@ -49,6 +49,7 @@ def load_golden_instances(name="instances"):
 
 
 GOLDEN = ["cube_ground", "sphere21", "terrain_masks"]
+GOLDEN_QUADS = ["quads"]   # meshes with [n,4] indices are RTC_GEOMETRY_TYPE_QUAD
 
 
 @pytest.fixture(scope="session")

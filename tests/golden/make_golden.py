@@ -45,7 +45,8 @@ def run_flags(name, meshes, rayhits, flags):
         R.rtcSetSceneFlags(sc, flags)
     keep = []
     for (v, t, gid, mask) in meshes:
-        _, k = R.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)
+        add = R.add_quad_mesh if t.shape[1] == 4 else R.add_triangle_mesh   # [n,4] indices: RTC_GEOMETRY_TYPE_QUAD
+        _, k = add(dev, sc, v, t, mask=mask, geom_id=gid)
         keep.append(k)
     R.rtcCommitScene(sc)
     R.check(dev)
@@ -150,6 +151,22 @@ def main():
     r["mask"][2::4] = 0x4
     r["mask"][3::4] = 0x3
     run("terrain_masks", [(tv, tt, 0, 0x1), (pv, pt, 3, 0x2)], r)
+    # 3b. quad meshes (non-planar height-field quads, a closed quad box with one triangle-as-quad) next to a triangle
+    #     mesh, with geometry masks; rays from above, from inside the box and at random
+    qv, qq = scenes.quad_terrain(20, seed=5)
+    bv = np.array([[x, y, z] for x in (-0.5, 0.5) for y in (0.3, 0.9) for z in (-0.5, 0.5)], np.float32)
+    bq = np.array([[0, 1, 3, 2], [4, 6, 7, 5], [0, 4, 5, 1], [2, 3, 7, 6], [0, 2, 6, 4], [1, 5, 7, 7]], np.uint32)  # last: triangle as quad
+    sv, st = scenes.triangle_sphere(8)
+    sv = (sv * np.float32(0.25) + np.float32([0.0, 0.6, 0.0])).astype(np.float32)
+    org, d = random_rays_box(3072, -1, 1, 6)
+    org[:1024, 1] = 1.5
+    d[:1024, 1] = -np.abs(d[:1024, 1]) - 0.2
+    org[1024:2048] = org[1024:2048] * np.float32(0.2) + np.float32([0, 0.6, 0])
+    r = make_rayhits(org, d)
+    r["mask"][0::6] = 0x1
+    r["mask"][1::6] = 0x2
+    r["id"] = np.arange(len(r))
+    run("quads", [(qv, qq, 0, 0x1), (bv, bq, 1, 0xFFFFFFFF), (sv, st, 2, 0x3)], r)
     # 4. single-level instancing: a ground plane + 7 transformed instances of a two-mesh child scene, with instance and
     #    geometry masks selecting subsets
     sv, st = scenes.triangle_sphere(10)

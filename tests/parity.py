@@ -22,6 +22,7 @@ class Oracle:
         d.orc_free.argtypes = [C.c_void_p]
         d.orc_add_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint]
         d.orc_commit.argtypes = [C.c_void_p]
+        d.orc_add_quad_mesh.argtypes = d.orc_add_mesh.argtypes
         d.orc_add_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
         d.orc_set_robust.argtypes = [C.c_void_p, C.c_int]
         d.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
@@ -32,8 +33,8 @@ class Oracle:
         self.d = d
 
     def scene(self, meshes, robust=False, instances=()):
-        """meshes: list of (vertices[nv,3] f32, indices[nt,3] u32, geomID, mask); instances: list of
-        (child OracleScene, xfm[12] column-major 3x4, geomID, mask).  Returns an OracleScene."""
+        """meshes: list of (vertices[nv,3] f32, indices[nt,3] u32 (or [nq,4] for a quad mesh), geomID, mask); instances:
+        list of (child OracleScene, xfm[12] column-major 3x4, geomID, mask).  Returns an OracleScene."""
         return OracleScene(self, meshes, robust, instances)
 
     def trace(self, v, t, rayhits, occluded=False, mask=0xFFFFFFFF, nthreads=1):
@@ -51,9 +52,12 @@ class OracleScene:
         self.keep = []
         for (v, t, gid, mask) in meshes:
             v = np.ascontiguousarray(v, np.float32).reshape(-1, 3)
-            t = np.ascontiguousarray(t, np.uint32).reshape(-1, 3)
+            t = np.ascontiguousarray(t, np.uint32)
+            quad = t.ndim == 2 and t.shape[1] == 4
+            t = t.reshape(-1, 4 if quad else 3)
             self.keep += [v, t]
-            o.d.orc_add_mesh(self.h, v.ctypes.data, 12, v.shape[0], t.ctypes.data, 12, t.shape[0], gid, mask)
+            (o.d.orc_add_quad_mesh if quad else o.d.orc_add_mesh)(self.h, v.ctypes.data, 12, v.shape[0], t.ctypes.data,
+                                                                   16 if quad else 12, t.shape[0], gid, mask)
         for (child, xfm, gid, mask) in instances:
             m = np.ascontiguousarray(xfm, np.float32).reshape(12)
             self.keep += [child, m]

@@ -15,7 +15,7 @@ from embree_b200.rtc import (RTCBounds, RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY
                              RTC_BUFFER_TYPE_INDEX, RTC_BUFFER_TYPE_VERTEX, RTC_GEOMETRY_TYPE_TRIANGLE, RTC_GEOMETRY_TYPE_INSTANCE, RTC_FORMAT_FLOAT3X4_ROW_MAJOR,
                              RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR, aligned_empty,
                              make_rayhits, rays_of, to_packets, from_packets, _ptr)
-from tests.conftest import GOLDEN, load_golden, load_golden_instances
+from tests.conftest import GOLDEN, GOLDEN_QUADS, load_golden, load_golden_instances
 from tests.parity import compare_hits, load_reference
 
 pytestmark = pytest.mark.gpu
@@ -30,7 +30,8 @@ def build_scene(lib, dev, meshes, quality=RTC_BUILD_QUALITY_MEDIUM, flags=0):
         lib.rtcSetSceneFlags(sc, flags)
     keep = []
     for (v, t, gid, mask) in meshes:
-        _, k = lib.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)
+        add = lib.add_quad_mesh if np.asarray(t).shape[1] == 4 else lib.add_triangle_mesh
+        _, k = add(dev, sc, v, t, mask=mask, geom_id=gid)
         keep.append(k)
     lib.rtcCommitScene(sc)
     lib.check(dev)
@@ -257,7 +258,7 @@ def test_commit_state_machine_and_errors(b200):
     assert lib.rtcGetDeviceError(dev) == 2
     lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(vpad), 2, 12, len(v))
     assert lib.rtcGetDeviceError(dev) == 3          # not 4-byte aligned
-    assert not lib.rtcNewGeometry(dev, 1)           # quads unsupported
+    assert not lib.rtcNewGeometry(dev, 8)           # subdivision surfaces unsupported
     assert lib.rtcGetDeviceError(dev) == 3
     # disable / enable / detach
     lib.rtcDisableGeometry(g)
@@ -271,6 +272,73 @@ def test_commit_state_machine_and_errors(b200):
     assert lib.intersect(sc, make_rayhits([[0, 0, 0]], [[0, 0, 1]]), "1")["geomID"][0] == 0xFFFFFFFF
     assert lib.rtcGetDeviceError(dev) == 0
     lib.rtcReleaseGeometry(g)
+    lib.rtcReleaseScene(sc)
+
+
+@pytest.mark.parametrize("robust", [False, True])
+@pytest.mark.parametrize("quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
+@pytest.mark.parametrize("name", GOLDEN_QUADS)
+def test_quads_golden_all_entry_points(b200, name, quality, robust):
+    """RTC_GEOMETRY_TYPE_QUAD next to triangle meshes against the reference's own outputs (quad_intersector_moeller.h,
+    quad_intersector_pluecker.h): ids exact, t/u/v within 1e-4, Ng bit-exact away from the quad diagonal (ON the shared
+    diagonal the reference's 8-wide min-t selection between the two halves is decided by rounding noise)."""
+    lib, dev = b200
+    meshes, rin, want_i, want_o, bounds = load_golden(name, robust)
+    sc, keep = build_scene(lib, dev, meshes, quality, flags=4 if robust else 0)
+    for mode in MODES:
+        got = lib.intersect(sc, rin.copy(), mode)
+        assert_parity(want_i, got)
+        hit = want_i["geomID"] != 0xFFFFFFFF
+        off_diag = hit & (np.abs(want_i["u"] + want_i["v"] - 1.0) > 1e-4)
+        for f in ("Ng_x", "Ng_y", "Ng_z"):
+            assert (want_i[f].view(np.uint32) == got[f].view(np.uint32))[off_diag].all(), (mode, f)
+        occ = lib.occluded(sc, rays_of(rin), mode)
+        assert (occ["tfar"].view(np.uint32) == want_o["tfar"].view(np.uint32)).all(), mode
+    b = RTCBounds()
+    lib.rtcGetSceneBounds(sc, C.byref(b))
+    assert np.array_equal(np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32), bounds)
+    lib.rtcReleaseScene(sc)
+
+
+def test_quads_large_vs_oracle(b200, oracle):
+    """1M non-planar quads (2M half records) + an instanced quad scene against the C oracle: invalid quads dropped
+    whole, quad primIDs reported, instancing of quad meshes."""
+    lib, dev = b200
+    v, q = scenes.quad_terrain(1000, seed=9)
+    q = q.copy()
+    q[5] = (0, 1, 2, 0xFFFFFFF0)        # out-of-range index: the WHOLE quad is invalid (scene_quad_mesh.h:186-203)
+    v = v.copy()
+    v[int(q[77, 2])] = np.nan            # NaN vertex: every quad that references it is dropped
+    sc, keep = build_scene(lib, dev, [(v, q, 0, 0xFFFFFFFF)])
+    rng = np.random.RandomState(3)
+    org = rng.uniform(-1, 1, (300000, 3)).astype(np.float32)
+    org[:, 1] = 0.5
+    d = rng.normal(size=(300000, 3)).astype(np.float32)
+    d[:, 1] = -np.abs(d[:, 1])
+    rays = make_rayhits(org, d)
+    got = lib.intersect(sc, rays.copy(), "1M")
+    osc = oracle.scene([(v, q, 0, 0xFFFFFFFF)])
+    want = osc.trace(rays.copy(), nthreads=16)
+    rep = compare_hits(want, got, TOL)
+    assert rep["hits"] > 100000 and rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] <= 3 and rep["tie"] <= 30, rep
+    assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= TOL, rep
+    assert got["primID"][got["geomID"] == 0].max() < len(q)
+    # the same quad mesh seen through two instances
+    top = lib.rtcNewScene(dev)
+    xf = [np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32), np.array([0.5, 0, 0, 0, 0.5, 0, 0, 0, 0.5, 0, 0.3, 0], np.float32)]
+    for m in xf:
+        lib.add_instance(dev, top, sc, m, mask=0xFFFFFFFF)
+    lib.rtcCommitScene(top)
+    lib.check(dev)
+    got2 = lib.intersect(top, rays[:50000].copy(), "1M")
+    otop = oracle.scene([], instances=[(osc, m, i, 0xFFFFFFFF) for i, m in enumerate(xf)])
+    want2 = otop.trace(rays[:50000].copy(), nthreads=16)
+    rep2 = compare_hits(want2, got2, TOL)
+    assert rep2["id_mismatch"] == 0 and rep2["hit_miss_disagree"] <= 2 and rep2["tie"] <= 10, rep2
+    assert (got2["instID"][got2["geomID"] != 0xFFFFFFFF] <= 1).all() and (got2["instID"] == 1).sum() > 1000
+    otop.free()
+    osc.free()
+    lib.rtcReleaseScene(top)
     lib.rtcReleaseScene(sc)
 
 

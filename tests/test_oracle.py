@@ -7,7 +7,7 @@ import pytest
 
 from embree_b200 import scenes
 from embree_b200.rtc import make_rayhits, rays_of
-from tests.conftest import GOLDEN, load_golden, load_golden_instances
+from tests.conftest import GOLDEN, GOLDEN_QUADS, load_golden, load_golden_instances
 from tests.parity import compare_hits, load_reference
 
 
@@ -39,7 +39,7 @@ def test_minimal_tutorial_kat(oracle):
 
 
 @pytest.mark.parametrize("robust", [False, True])
-@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("name", GOLDEN + GOLDEN_QUADS)
 def test_oracle_vs_golden(oracle, name, robust):
     meshes, rin, want_i, want_o, bounds = load_golden(name, robust)
     sc = oracle.scene(meshes, robust=robust)
