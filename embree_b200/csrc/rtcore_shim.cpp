@@ -435,9 +435,12 @@ void trace_device(SceneImpl* s, void* d_rays, const int* d_valid, int K, size_t 
 }
 
 // batched, host pointers: chunked H2D -> trace -> D2H pipeline over three streams
+// host-buffer pipeline shape (rtcb200SetTuning "host_chunk_log2" / "host_streams"): rays per chunk and chunks in flight
+static int g_host_chunk_log2 = 20, g_host_streams = 3;   // measured: 2^20 -> 492 Mrays/s, 2^22 -> 474 (scripts/e2e_sweep.py)
+
 struct HostPipe {
   int gpu = -1;
-  static constexpr int kStreams = 3;
+  static constexpr int kStreams = 6;   // upper bound; g_host_streams of them are used
   cudaStream_t st[kStreams] = {};
   char* buf[kStreams] = {};
   int* vbuf[kStreams] = {};
@@ -474,12 +477,13 @@ void trace_host(SceneImpl* s, void* rays, const int* valid, int K, size_t M, siz
                 uint32_t instID, uint32_t instPrimID) {
   require_committed(s);
   if (!s->gpu.root_valid || M == 0) return;
-  const size_t chunkRecs = std::max<size_t>(1, (size_t(1) << 22) / K);  // 4 Mi rays per chunk
+  const size_t chunkRecs = std::max<size_t>(1, (size_t(1) << g_host_chunk_log2) / K);  // 1 Mi rays per chunk by default
+  const int nst = std::min(std::max(g_host_streams, 1), (int)HostPipe::kStreams);
   const size_t chunks = (M + chunkRecs - 1) / chunkRecs;
   const size_t perChunk = std::min(M, chunkRecs);
   t_pipe.ensure(s->dev->gpu, perChunk * recBytes, valid ? perChunk * K * 4 : 0);
   for (size_t c = 0; c < chunks; ++c) {
-    const int b = (int)(c % HostPipe::kStreams);
+    const int b = (int)(c % nst);
     cudaStream_t st = t_pipe.st[b];
     const size_t first = c * chunkRecs, cnt = std::min(chunkRecs, M - first);
     char* h = static_cast<char*>(rays) + first * recBytes;
@@ -931,6 +935,8 @@ int rtcb200SetTuning(const char* key, int value) {
   else if (!strcmp(key, "tri_wait_max")) t.tri_wait_max = value;
   else if (!strcmp(key, "blocks_per_sm")) t.blocks_per_sm = value;
   else if (!strcmp(key, "use_tma")) t.use_tma = value;
+  else if (!strcmp(key, "host_chunk_log2") && value >= 10 && value <= 26) g_host_chunk_log2 = value;
+  else if (!strcmp(key, "host_streams") && value >= 1 && value <= HostPipe::kStreams) g_host_streams = value;
   else return -1;
   return 0;
 }
