@@ -434,6 +434,100 @@ void trace_device(SceneImpl* s, void* d_rays, const int* d_valid, int K, size_t 
   if (timeit) cudaEventRecord(s->ev1, st);
 }
 
+// ---- multi-GPU hit gather into another GPU's memory ------------------------------------------------------------------
+// Two ways to get the compact 32-byte hit records into the gather buffer (rtcb200Intersect1MGatherDevice):
+//   direct  the trace kernel stores each record to `compact_out` as its ray terminates.  Right when the buffer is LOCAL
+//           (rank 0's own slice); over NVLink the scattered 16-byte stores of 7 peers converge on one GPU as small
+//           packets and the step time at N=8 grew from 48 to 86 ms.
+//   staged  the ray stream is traced in `gather_chunks` launches that alternate between the caller's stream and an
+//           auxiliary one (the next launch fills the SMs the previous launch's tail vacates); each launch writes its
+//           records to a local staging buffer and a copy-engine peer copy pushes the finished chunk over NVLink in
+//           full-size packets while the following chunks are traced.  Only the last chunk's push is not overlapped.
+static int g_gather_mode = -1 /* -1 auto: staged iff compact_out is not local memory */, g_gather_chunks = 8;
+
+struct GatherPipe {
+  static constexpr int kMaxChunks = 64;
+  int gpu = -1;
+  cudaStream_t aux = nullptr, copy = nullptr;
+  cudaEvent_t evStart = nullptr, evAux = nullptr, evCopy = nullptr, evK[kMaxChunks] = {};
+  char* stage = nullptr;
+  size_t cap = 0;
+  ~GatherPipe() { reset(); }
+  void reset() {
+    if (stage) cudaFree(stage);
+    if (aux) cudaStreamDestroy(aux);
+    if (copy) cudaStreamDestroy(copy);
+    for (cudaEvent_t e : {evStart, evAux, evCopy}) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < kMaxChunks; ++i) if (evK[i]) { cudaEventDestroy(evK[i]); evK[i] = nullptr; }
+    stage = nullptr; aux = copy = nullptr; evStart = evAux = evCopy = nullptr; cap = 0; gpu = -1;
+  }
+  void ensure(int g, size_t bytes) {
+    if (gpu != g) reset();
+    cudaSetDevice(g);
+    gpu = g;
+    if (!aux) {
+      cuda_check(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking), "cudaStreamCreate");
+      cuda_check(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking), "cudaStreamCreate");
+      for (cudaEvent_t* e : {&evStart, &evAux, &evCopy}) cuda_check(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
+      for (int i = 0; i < kMaxChunks; ++i) cuda_check(cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    if (bytes > cap) {
+      if (stage) cudaFree(stage);
+      stage = nullptr; cap = 0;
+      cuda_check(cudaMalloc(&stage, bytes), "cudaMalloc(gather staging)");
+      cap = bytes;
+    }
+  }
+};
+static thread_local GatherPipe t_gather;
+
+void trace_gather(SceneImpl* s, void* d_rays, size_t M, uint32_t instID, uint32_t instPrimID, cudaStream_t st, void* compact_out) {
+  require_committed(s);
+  if (M == 0) return;
+  cudaSetDevice(s->dev->gpu);
+  bool staged = g_gather_mode == 1;
+  if (g_gather_mode < 0) {
+    cudaPointerAttributes at{};
+    staged = !(cudaPointerGetAttributes(&at, compact_out) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == s->dev->gpu);
+    cudaGetLastError();
+  }
+  if (!s->ev0) { cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); }
+  if (!staged || !s->gpu.root_valid) {   // (an empty scene still has to write its "miss" records)
+    cudaEventRecord(s->ev0, st);
+    rtk::TraceParams p = make_params(s, d_rays, nullptr, (unsigned long long)M, instID, instPrimID);
+    p.compact_out = compact_out;
+    if (s->gpu.root_valid) cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, st), "trace launch");
+    cudaEventRecord(s->ev1, st);
+    return;
+  }
+  GatherPipe& g = t_gather;
+  g.ensure(s->dev->gpu, M * 32);
+  int chunks = std::min(std::max(g_gather_chunks, 1), (int)GatherPipe::kMaxChunks);
+  while (chunks > 1 && M / chunks < (size_t(1) << 20)) --chunks;   // keep every launch big enough to fill the machine
+  const size_t per = (M + chunks - 1) / chunks;
+  cudaEventRecord(s->ev0, st);
+  cuda_check(cudaEventRecord(g.evStart, st), "event record");
+  cuda_check(cudaStreamWaitEvent(g.aux, g.evStart, 0), "stream wait");
+  cuda_check(cudaStreamWaitEvent(g.copy, g.evStart, 0), "stream wait");
+  for (int c = 0; c < chunks; ++c) {
+    const size_t first = (size_t)c * per;
+    if (first >= M) break;
+    const size_t cnt = std::min(per, M - first);
+    cudaStream_t ks = (c & 1) ? g.aux : st;
+    rtk::TraceParams p = make_params(s, static_cast<char*>(d_rays) + first * 96, nullptr, (unsigned long long)cnt, instID, instPrimID);
+    p.compact_out = g.stage + first * 32;
+    cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, ks), "trace launch");
+    cuda_check(cudaEventRecord(g.evK[c], ks), "event record");
+    cuda_check(cudaStreamWaitEvent(g.copy, g.evK[c], 0), "stream wait");
+    cuda_check(cudaMemcpyAsync(static_cast<char*>(compact_out) + first * 32, g.stage + first * 32, cnt * 32, cudaMemcpyDefault, g.copy), "peer push");
+  }
+  cuda_check(cudaEventRecord(g.evAux, g.aux), "event record");
+  cuda_check(cudaEventRecord(g.evCopy, g.copy), "event record");
+  cuda_check(cudaStreamWaitEvent(st, g.evAux, 0), "stream wait");
+  cuda_check(cudaStreamWaitEvent(st, g.evCopy, 0), "stream wait");   // stream-ordered consumers see the pushed records
+  cudaEventRecord(s->ev1, st);
+}
+
 // batched, host pointers: chunked H2D -> trace -> D2H pipeline over three streams
 // host-buffer pipeline shape (rtcb200SetTuning "host_chunk_log2" / "host_streams"): rays per chunk and chunks in flight
 static int g_host_chunk_log2 = 20, g_host_streams = 3;   // measured: 2^20 -> 492 Mrays/s, 2^22 -> 474 (scripts/e2e_sweep.py)
@@ -857,7 +951,7 @@ void rtcb200Occluded1M(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOcclud
 void rtcb200IntersectNM(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_host(s_, rh, v, (int)K, M, (size_t)84 * K, 0, iid, ipid);) }
 void rtcb200OccludedNM(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_host(s_, r, v, (int)K, M, (size_t)48 * K, 1, iid, ipid);) }
 void rtcb200Intersect1MDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, rh, nullptr, 1, M, 0, iid, ipid, (cudaStream_t)st, true);) }
-void rtcb200Intersect1MGatherDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st, void* compact_out) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, rh, nullptr, 1, M, 0, iid, ipid, (cudaStream_t)st, true, compact_out);) }
+void rtcb200Intersect1MGatherDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st, void* compact_out) { QUERY(sc, check_args(s_, a, iid, ipid); VERIFY_HANDLE(compact_out); trace_gather(s_, rh, M, iid, ipid, (cudaStream_t)st, compact_out);) }
 void rtcb200Occluded1MDevice(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, r, nullptr, 1, M, 1, iid, ipid, (cudaStream_t)st, true);) }
 void rtcb200IntersectNMDevice(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_device(s_, rh, v, (int)K, M, 0, iid, ipid, (cudaStream_t)st, true);) }
 void rtcb200OccludedNMDevice(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_device(s_, r, v, (int)K, M, 1, iid, ipid, (cudaStream_t)st, true);) }
@@ -935,6 +1029,8 @@ int rtcb200SetTuning(const char* key, int value) {
   else if (!strcmp(key, "tri_wait_max")) t.tri_wait_max = value;
   else if (!strcmp(key, "blocks_per_sm")) t.blocks_per_sm = value;
   else if (!strcmp(key, "use_tma")) t.use_tma = value;
+  else if (!strcmp(key, "gather_mode") && value >= -1 && value <= 1) g_gather_mode = value;
+  else if (!strcmp(key, "gather_chunks") && value >= 1 && value <= GatherPipe::kMaxChunks) g_gather_chunks = value;
   else if (!strcmp(key, "host_chunk_log2") && value >= 10 && value <= 26) g_host_chunk_log2 = value;
   else if (!strcmp(key, "host_streams") && value >= 1 && value <= HostPipe::kStreams) g_host_streams = value;
   else return -1;
