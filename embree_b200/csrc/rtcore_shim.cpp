@@ -436,14 +436,16 @@ void trace_device(SceneImpl* s, void* d_rays, const int* d_valid, int K, size_t 
 
 // ---- multi-GPU hit gather into another GPU's memory ------------------------------------------------------------------
 // Two ways to get the compact 32-byte hit records into the gather buffer (rtcb200Intersect1MGatherDevice):
-//   direct  the trace kernel stores each record to `compact_out` as its ray terminates.  Right when the buffer is LOCAL
-//           (rank 0's own slice); over NVLink the scattered 16-byte stores of 7 peers converge on one GPU as small
-//           packets and the step time at N=8 grew from 48 to 86 ms.
-//   staged  the ray stream is traced in `gather_chunks` launches that alternate between the caller's stream and an
-//           auxiliary one (the next launch fills the SMs the previous launch's tail vacates); each launch writes its
-//           records to a local staging buffer and a copy-engine peer copy pushes the finished chunk over NVLink in
-//           full-size packets while the following chunks are traced.  Only the last chunk's push is not overlapped.
-static int g_gather_mode = -1 /* -1 auto: staged iff compact_out is not local memory */, g_gather_chunks = 8;
+//   direct  (default) the trace kernel stores each record to `compact_out` as its ray terminates -- local memory or a
+//           peer's memory over NVLink; the transfer is spread over the whole launch.
+//   staged  (rtcb200SetTuning "gather_mode" 1) the ray stream is traced in `gather_chunks` launches that alternate
+//           between the caller's stream and an auxiliary one (the next launch fills the SMs the previous launch's tail
+//           vacates); each launch writes its records to a local staging buffer and a copy-engine peer copy pushes the
+//           finished chunk over NVLink in full-size packets while the following chunks are traced.
+// Measured (profiles/r1_bench_n{2,4,8}*.json): both modes give the same step time -- 99 % / 98 % of linear at 2 / 4 GPUs
+// and 86 ms instead of 50 ms at 8 GPUs, where seven peers deliver 15 GB per step into rank 0: the limit there is what one
+// GPU ingests (~175 GB/s observed with either small kernel stores or bulk DMA), not how the records are sent.
+static int g_gather_mode = 0, g_gather_chunks = 8;
 
 struct GatherPipe {
   static constexpr int kMaxChunks = 64;
@@ -485,12 +487,7 @@ void trace_gather(SceneImpl* s, void* d_rays, size_t M, uint32_t instID, uint32_
   require_committed(s);
   if (M == 0) return;
   cudaSetDevice(s->dev->gpu);
-  bool staged = g_gather_mode == 1;
-  if (g_gather_mode < 0) {
-    cudaPointerAttributes at{};
-    staged = !(cudaPointerGetAttributes(&at, compact_out) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == s->dev->gpu);
-    cudaGetLastError();
-  }
+  const bool staged = g_gather_mode == 1;
   if (!s->ev0) { cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); }
   if (!staged || !s->gpu.root_valid) {   // (an empty scene still has to write its "miss" records)
     cudaEventRecord(s->ev0, st);
@@ -1029,7 +1026,7 @@ int rtcb200SetTuning(const char* key, int value) {
   else if (!strcmp(key, "tri_wait_max")) t.tri_wait_max = value;
   else if (!strcmp(key, "blocks_per_sm")) t.blocks_per_sm = value;
   else if (!strcmp(key, "use_tma")) t.use_tma = value;
-  else if (!strcmp(key, "gather_mode") && value >= -1 && value <= 1) g_gather_mode = value;
+  else if (!strcmp(key, "gather_mode") && value >= 0 && value <= 1) g_gather_mode = value;
   else if (!strcmp(key, "gather_chunks") && value >= 1 && value <= GatherPipe::kMaxChunks) g_gather_chunks = value;
   else if (!strcmp(key, "host_chunk_log2") && value >= 10 && value <= 26) g_host_chunk_log2 = value;
   else if (!strcmp(key, "host_streams") && value >= 1 && value <= HostPipe::kStreams) g_host_streams = value;

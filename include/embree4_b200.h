@@ -304,10 +304,10 @@ RTCB200_API void rtcb200OccludedNM(const int* valid, RTCScene scene, void* rayK,
 RTCB200_API void rtcb200Intersect1MDevice(RTCScene scene, struct RTCRayHit* d_rayhits, size_t M, struct RTCIntersectArguments* args, void* cuda_stream);
 /* as rtcb200Intersect1MDevice, and additionally writes one compact 32-byte record {tfar, Ng.xyz, u, v, primID, geomID} per
  * ray (primID = geomID = -1 on a miss) to compact_out[i].  compact_out may be memory of ANOTHER GPU imported with
- * rtcb200PeerImport (the multi-GPU hit gather).  Local memory: the trace kernel stores the records itself.  Peer memory:
- * the stream is traced in chunks whose records are pushed over NVLink by the copy engine while the next chunks are
- * traced (rtcb200SetTuning "gather_mode" 0 forces direct kernel stores to the peer, "gather_chunks" sets the chunking).
- * Work enqueued on cuda_stream after this call sees the complete buffer. */
+ * rtcb200PeerImport (the multi-GPU hit gather): the trace kernel stores each record as its ray terminates, straight over
+ * NVLink when the buffer is a peer's.  rtcb200SetTuning("gather_mode", 1) selects the alternative pipeline: the stream
+ * is traced in "gather_chunks" launches whose records are pushed by the copy engine while the next chunks are traced.
+ * Either way, work enqueued on cuda_stream after this call sees the complete buffer. */
 RTCB200_API void rtcb200Intersect1MGatherDevice(RTCScene scene, struct RTCRayHit* d_rayhits, size_t M, struct RTCIntersectArguments* args, void* cuda_stream, void* compact_out);
 RTCB200_API void rtcb200Occluded1MDevice(RTCScene scene, struct RTCRay* d_rays, size_t M, struct RTCOccludedArguments* args, void* cuda_stream);
 RTCB200_API void rtcb200IntersectNMDevice(const int* d_valid, RTCScene scene, void* d_rayhitK, unsigned int K, size_t M, struct RTCIntersectArguments* args, void* cuda_stream);

@@ -1,0 +1,49 @@
+"""Hit-gather entry point (rtcb200Intersect1MGatherDevice) on one GPU: the compact record stream in both delivery modes.
+Named to sort after the other GPU test files: it is the newest entry point and must not shadow them under `-x`."""
+import ctypes as C
+
+import pytest
+
+from embree_b200 import scenes
+from tests.test_gpu_parity import build_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gather_records_direct_and_staged(b200):
+    """rtcb200Intersect1MGatherDevice: the compact 32-byte record per ray {tfar, Ng, u, v, primID, geomID} equals the
+    RTCRayHit result, both when the kernel stores the records itself (local buffer) and when the chunked
+    trace + copy-engine push pipeline is forced (the path peers take over NVLink), with work enqueued on the caller's
+    stream after the call seeing the complete buffer."""
+    import torch
+    from embree_b200 import sharding
+    lib, dev = b200
+    v, t = scenes.triangle_sphere(60)
+    sc, keep = build_scene(lib, dev, [(v, t, 0, 0xFFFFFFFF)])
+    rays = scenes.incoherent_rays_reference(3 << 20, device=torch.device("cuda", 0))
+    rays[::5, 8] = 0.5                                     # some misses (tfar inside the sphere)
+    a = lib.args()
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    try:
+        for mode, chunks in ((0, 8), (1, 3), (1, 8)):
+            assert lib.rtcb200SetTuning(b"gather_mode", mode) == 0 and lib.rtcb200SetTuning(b"gather_chunks", chunks) == 0
+            B = rays.clone()
+            out = torch.full((B.shape[0], 8), 7.0, device=B.device)
+            lib.rtcb200Intersect1MGatherDevice(sc, C.c_void_p(B.data_ptr()), B.shape[0], C.byref(a), C.c_void_p(st), C.c_void_p(out.data_ptr()))
+            got = out.clone()                              # stream-ordered after the call: must already see every record
+            torch.cuda.synchronize()
+            lib.check(dev)
+            want = sharding.compact_hits(B)
+            miss = B.view(torch.int32)[:, 18] == -1
+            want[miss, 1:6] = 0.0
+            want.view(torch.int32)[miss, 6] = -1
+            want.view(torch.int32)[miss, 7] = -1
+            assert miss.any() and (~miss).any()
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32)), (mode, chunks)
+            outs.append(got)
+        assert torch.equal(outs[0].view(torch.int32), outs[1].view(torch.int32)) and torch.equal(outs[0].view(torch.int32), outs[2].view(torch.int32))
+    finally:
+        lib.rtcb200SetTuning(b"gather_mode", -1)
+        lib.rtcb200SetTuning(b"gather_chunks", 8)
+    lib.rtcReleaseScene(sc)
