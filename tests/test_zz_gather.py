@@ -44,6 +44,6 @@ def test_gather_records_direct_and_staged(b200):
             outs.append(got)
         assert torch.equal(outs[0].view(torch.int32), outs[1].view(torch.int32)) and torch.equal(outs[0].view(torch.int32), outs[2].view(torch.int32))
     finally:
-        lib.rtcb200SetTuning(b"gather_mode", -1)
+        lib.rtcb200SetTuning(b"gather_mode", 0)
         lib.rtcb200SetTuning(b"gather_chunks", 8)
     lib.rtcReleaseScene(sc)
