@@ -465,7 +465,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, len(t)),
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "gather_verified": gather_ok,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                             "traffic": traffic, "peak_source": peak_src, "kernel": "rtk::trace_kernel<1,false,false>",
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "rtk::trace_kernel<K=1,OCCLUDED=false,STATS=false,ROBUST=false,GENERAL=false>",
                              "kernel_ms": kms, "algorithmic_bytes_per_ray": bytes_per_ray,
                              "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                              "note": "algorithmic bytes = 100 B ray/hit I/O + nodes/ray*80 B + tris/ray*48 B (device stat counters, 1 Mi-ray sample)"},
