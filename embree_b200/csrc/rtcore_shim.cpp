@@ -1026,6 +1026,7 @@ int rtcb200SetTuning(const char* key, int value) {
   else if (!strcmp(key, "tri_wait_max")) t.tri_wait_max = value;
   else if (!strcmp(key, "blocks_per_sm")) t.blocks_per_sm = value;
   else if (!strcmp(key, "use_tma")) t.use_tma = value;
+  else if (!strcmp(key, "tri_spread")) t.tri_spread = value != 0;
   else if (!strcmp(key, "gather_mode") && value >= 0 && value <= 1) g_gather_mode = value;
   else if (!strcmp(key, "gather_chunks") && value >= 1 && value <= GatherPipe::kMaxChunks) g_gather_chunks = value;
   else if (!strcmp(key, "host_chunk_log2") && value >= 10 && value <= 26) g_host_chunk_log2 = value;

@@ -80,6 +80,7 @@ struct Tuning {
   int blocks_per_sm = 8;
   int use_tma = 1;
   int refill_min = 4;
+  int tri_spread = 0;        // EXPERIMENTAL warp-wide triangle redistribution in the trace kernel (trace.cu SPREAD), off
   int sah_small = 4;         // SAH builder: segments of <= this many primitives are split in the middle (no binning)
 };
 Tuning& tuning();

@@ -130,7 +130,7 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 // node, slab-test its 8 children) for the lanes that want it, and at most one triangle step, batched across the warp;
 // the phases are warp-synchronous so lanes in the same phase execute together instead of serialising through a
 // per-thread while-while loop.  The top stack entry lives in registers; deeper entries in (L1-resident) local memory.
-template <int K, bool OCCLUDED, bool STATS, bool ROBUST, bool GENERAL>
+template <int K, bool OCCLUDED, bool STATS, bool ROBUST, bool GENERAL, bool SPREAD = false>
 __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TraceParams p) {
   const bool USE_TMA = p.use_prefetch != 0;
   using IO = RayIO<K, OCCLUDED>;
@@ -249,7 +249,74 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
     const unsigned node_lanes = __ballot_sync(FULL, active && tgy == 0 && (ngy & 0xFF000000u));
     if (tri_lanes && (__popc(tri_lanes) >= tri_batch_min || node_lanes == 0 || ++tri_wait >= tri_wait_max)) {
       tri_wait = 0;
-      if (active && tgy != 0) {
+      if (SPREAD) {
+        // EXPERIMENTAL (rtcb200SetTuning "tri_spread" 1; off by default, closest-hit Moeller-Trumbore triangle scenes
+        // only): the pending triangles of ALL lanes become work items that the whole warp tests in one step, instead
+        // of each lane testing one of its own while the others idle (scripts/warp_model.py: -20 % warp instructions
+        // per ray).  Owners queue (record index, owner lane) in shared memory; worker lane w takes item w, fetches the
+        // owner's ray by shuffles and tests the record; hits meet in a 64-bit atomicMin per owner keyed by (t, item) --
+        // among equal t the later item wins, as in the sequential order -- and the owner reads u, v back by shuffle.
+        __shared__ uint32_t s_tri[TRACE_WARPS][32];
+        __shared__ uint32_t s_owner[TRACE_WARPS][32];
+        __shared__ unsigned long long s_best[TRACE_WARPS][32];
+        const int wi = threadIdx.x >> 5;
+        const bool isT = active && tgy != 0;
+        const int cnt = isT ? __popc(tgy) : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        int slot = incl - cnt;                                  // first queue slot of this lane's items
+        const int total = min(__shfl_sync(FULL, incl, 31), 32);
+        s_best[wi][lane] = ~0ull;
+        while (isT && tgy != 0 && slot < 32) {                  // highest bit first = the sequential test order
+          const int tb = 31 - __clz((int)tgy);
+          tgy &= ~(1u << tb);
+          s_tri[wi][slot] = tgx + (uint32_t)tb;
+          s_owner[wi][slot] = (uint32_t)lane;
+          ++slot;
+        }
+        __syncwarp();
+        const bool work = lane < total;
+        const uint32_t ti = work ? s_tri[wi][lane] : 0u;
+        const int owner = work ? (int)s_owner[wi][lane] : lane;
+        Ray lr;
+        lr.ox = __shfl_sync(FULL, r.ox, owner); lr.oy = __shfl_sync(FULL, r.oy, owner); lr.oz = __shfl_sync(FULL, r.oz, owner);
+        lr.dx = __shfl_sync(FULL, r.dx, owner); lr.dy = __shfl_sync(FULL, r.dy, owner); lr.dz = __shfl_sync(FULL, r.dz, owner);
+        lr.tnear = __shfl_sync(FULL, r.tnear, owner);
+        const float o_tfar = __shfl_sync(FULL, tfar_tri, owner);
+        const uint32_t o_mask = __shfl_sync(FULL, r.mask, owner);
+        float w_u = 0.0f, w_v = 0.0f;
+        unsigned long long key = ~0ull;
+        if (work) {
+          const uint4* tp = tris + (size_t)ti * 3;
+          const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+          TriHit th;
+          if ((c.w & o_mask) != 0 &&
+              tri_test(lr, o_tfar, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
+                       __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z), th)) {
+            const float rcpAbsDen = 1.0f / th.absDen;
+            const float t = th.T * rcpAbsDen;
+            w_u = th.U * rcpAbsDen; w_v = th.V * rcpAbsDen;
+            uint32_t tb32 = __float_as_uint(t);
+            tb32 ^= (tb32 >> 31) ? 0xFFFFFFFFu : 0x80000000u;   // order-preserving float -> uint
+            key = ((unsigned long long)tb32 << 32) | (uint32_t)(31 - lane);
+            atomicMin(&s_best[wi][owner], key);
+          }
+        }
+        __syncwarp();
+        const unsigned long long best = s_best[wi][lane];       // as owner
+        const bool got = isT && best != ~0ull;
+        const int win = got ? 31 - (int)(best & 31ull) : lane;  // worker lane that holds the winning item
+        const float b_u = __shfl_sync(FULL, w_u, win), b_v = __shfl_sync(FULL, w_v, win);
+        if (got) {
+          uint32_t tb32 = (uint32_t)(best >> 32);
+          tb32 ^= (tb32 >> 31) ? 0x80000000u : 0xFFFFFFFFu;     // inverse of the transform above
+          tfar_tri = __uint_as_float(tb32);
+          hit_u = b_u; hit_v = b_v; hit_tri = s_tri[wi][win];
+          found = true;
+        }
+        __syncwarp();                                           // the queue is reused by the next triangle step
+      } else if (active && tgy != 0) {
         const int tb = 31 - __clz((int)tgy);
         tgy &= ~(1u << tb);
         const uint32_t ti = tgx + (uint32_t)tb;
@@ -392,6 +459,11 @@ static int launch_k(TraceParams p, cudaStream_t st) {
   // tiny launches (single-record API calls read a mapped pinned host record) skip the bulk prefetch
   p.use_prefetch = (p.n >= 1024 && g_tuning.use_tma) ? 1 : 0;
   const int variant = (p.stat ? 4 : 0) | (p.robust ? 2 : 0) | (p.descs ? 1 : 0);
+  if (K == 1 && !OCCLUDED && variant == 0 && g_tuning.tri_spread) {   // experimental triangle redistribution, opt-in
+    trace_kernel<K, OCCLUDED, false, false, false, (K == 1 && !OCCLUDED)><<<blocks, TRACE_THREADS, 0, st>>>(p);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   switch (variant) {
 #define RTK_LAUNCH(ST, RB, IN) trace_kernel<K, OCCLUDED, ST, RB, IN><<<blocks, TRACE_THREADS, 0, st>>>(p); break
     case 0: RTK_LAUNCH(false, false, false);

@@ -282,3 +282,62 @@ extern "C" void emu_trace_sorted(void* h, void* rays, uint64_t n, uint64_t* stat
     memcpy(rec + 68, ids, 16);
   }
 }
+
+// ---- experiment (test tool): the production traversal order, logging the per-ray operation sequence -- 'N' = one node
+// step (fetch + 8-child slab test), 'T' = one triangle test, each ray terminated by 0 -- for the offline warp-scheduling
+// model in scripts/warp_model.py.  Same loop as rtk::traverse<false,...> (closest hit, Moeller-Trumbore).
+extern "C" uint64_t emu_trace_ops(void* h, void* rays, uint64_t n, uint8_t* ops, uint64_t cap) {
+  EmuScene* sc = static_cast<EmuScene*>(h);
+  const Node8* nodes = sc->nodes.data();
+  const TriRec* tris = sc->tris.data();
+  uint64_t len = 0;
+  auto put = [&](uint8_t c) { if (len < cap) ops[len] = c; ++len; };
+  for (uint64_t ri = 0; ri < n; ++ri) {
+    char* rec = static_cast<char*>(rays) + ri * 96;
+    Ray r; memcpy(&r, rec, 48);
+    if (sc->root_valid) {
+      const float idx = rcp_safe(r.dx), idy = rcp_safe(r.dy), idz = rcp_safe(r.dz);
+      const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
+      const uint32_t oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
+      const uint32_t oct_inv4 = (7u - oct) * 0x01010101u;
+      const float tnear_c = fmaxf(r.tnear, 0.0f);
+      float tfar_c = fmaxf(r.tfar, 0.0f), tfar_tri = r.tfar;
+      uint32_t stack_x[kStackSize], stack_y[kStackSize];
+      int sp = 0;
+      uint32_t ngx = 0, ngy = 0x80000000u, tgx = 0, tgy = 0;
+      while (true) {
+        if (ngy & 0xFF000000u) {
+          const int bit = 31 - clz32(ngy);
+          ngy &= ~(1u << bit);
+          if (ngy & 0xFF000000u) { stack_x[sp] = ngx; stack_y[sp] = ngy; ++sp; }
+          const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
+          const uint32_t ni = ngx + (uint32_t)popc32(ngy & 0xFFu & ((1u << slot) - 1u));
+          const uint32_t* w = nodes[ni].w;
+          const u32x4 n0{w[0], w[1], w[2], w[3]}, n1{w[4], w[5], w[6], w[7]}, n2{w[8], w[9], w[10], w[11]}, n3{w[12], w[13], w[14], w[15]}, n4{w[16], w[17], w[18], w[19]};
+          put('N');
+          const uint32_t hm = node_hitmask<false>(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz, tnear_c, tfar_c, oct_inv4);
+          ngx = n1.x; ngy = (hm & 0xFF000000u) | (n0.w >> 24);
+          tgx = n1.y; tgy = hm & 0x00FFFFFFu;
+        } else { tgx = ngx; tgy = ngy; ngx = 0; ngy = 0; }
+        while (tgy) {
+          const int tb = 31 - clz32(tgy);
+          tgy &= ~(1u << tb);
+          const uint32_t* t = reinterpret_cast<const uint32_t*>(&tris[tgx + (uint32_t)tb]);
+          put('T');
+          TriHit th;
+          if (tri_test(r, tfar_tri, u2f(t[0]), u2f(t[1]), u2f(t[2]), u2f(t[4]), u2f(t[5]), u2f(t[6]), u2f(t[8]), u2f(t[9]), u2f(t[10]), th) &&
+              (t[11] & r.mask) != 0) {
+            tfar_tri = th.T * (1.0f / th.absDen);
+            tfar_c = fmaxf(tfar_tri, 0.0f);
+          }
+        }
+        if ((ngy & 0xFF000000u) == 0) {
+          if (sp == 0) break;
+          --sp; ngx = stack_x[sp]; ngy = stack_y[sp];
+        }
+      }
+    }
+    put(0);
+  }
+  return len;
+}
