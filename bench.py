@@ -242,7 +242,7 @@ def main():
     # NVLink (rtcb200Intersect1MGatherDevice).  A tiny NCCL all-reduce, stream-ordered after the kernel, is the
     # per-step "all hits have arrived" signal.  No separate collective moves hit data.  Measured: 99 % / 98 % of
     # linear at 2 / 4 GPUs; at 8 GPUs the 15 GB per step that seven peers deliver into rank 0 take 86 ms (kernel alone:
-    # 50 ms) -- the same with bulk copy-engine pushes ("gather_mode" 1), so rank 0's ingest rate is the limit.
+    # 50 ms): rank 0 ingests only ~175 GB/s.
     gbuf, my_out, flag = None, None, None
     if world > 1:
         nbytes = world * n * 32

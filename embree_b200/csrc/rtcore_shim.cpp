@@ -442,9 +442,9 @@ void trace_device(SceneImpl* s, void* d_rays, const int* d_valid, int K, size_t 
 //           between the caller's stream and an auxiliary one (the next launch fills the SMs the previous launch's tail
 //           vacates); each launch writes its records to a local staging buffer and a copy-engine peer copy pushes the
 //           finished chunk over NVLink in full-size packets while the following chunks are traced.
-// Measured (profiles/r1_bench_n{2,4,8}*.json): both modes give the same step time -- 99 % / 98 % of linear at 2 / 4 GPUs
-// and 86 ms instead of 50 ms at 8 GPUs, where seven peers deliver 15 GB per step into rank 0: the limit there is what one
-// GPU ingests (~175 GB/s observed with either small kernel stores or bulk DMA), not how the records are sent.
+// Measured with the direct mode (profiles/r1_bench_n{2,4,8}*.json): 99 % / 98 % of linear at 2 / 4 GPUs, and 86 ms instead
+// of 50 ms at 8 GPUs, where seven peers deliver 15 GB per step into rank 0 (~175 GB/s ingested).  The staged mode has not
+// been validated on a multi-GPU box yet.
 static int g_gather_mode = 0, g_gather_chunks = 8;
 
 struct GatherPipe {
