@@ -25,6 +25,7 @@ def main():
     rep = int(sys.argv[3]) if len(sys.argv) > 3 else 8
     e = load_emu()
     e.emu_trace_h16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_void_p]
+    e.emu_trace_h2.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     for name, (v, t) in (("sphere", scenes.triangle_sphere(phi)), ("terrain", scenes.terrain(int(phi * 1.0)))):
         h = e.emu_build(v.ctypes.data, len(v), t.ctypes.data, len(t), 0, 0xFFFFFFFF, 3)
         if name == "sphere":
@@ -50,6 +51,12 @@ def main():
                 farther = int(((base["geomID"] != 0xFFFFFFFF) & (got["geomID"] != 0xFFFFFFFF) & (got["tfar"] > base["tfar"])).sum())
                 print(f"  half, magic={magic} pad={pad:4.2f} cells: nodes/ray {s2[0] / len(rays):6.2f} ({s2[0] / st[0] * 100 - 100:+5.1f} %)  tris/ray {s2[1] / len(rays):5.2f} "
                       f"({s2[1] / st[1] * 100 - 100:+5.1f} %)  lost hits {lost}  farther hits {farther}  id mismatches {rep_['id_mismatch']} ties {rep_['tie']}")
+        s2 = np.zeros(2, np.uint64)
+        got = rays.copy()
+        e.emu_trace_h2(h, got.ctypes.data, len(got), s2.ctypes.data)
+        same = all((base[f].view(np.uint32) == got[f].view(np.uint32)).all() for f in ("tfar", "u", "v", "Ng_x", "Ng_y", "Ng_z", "primID", "geomID"))
+        print(f"  rt_core_h2.cuh node_hitmask_h2 (the device source, _Float16 emulation): nodes/ray {s2[0] / len(rays):6.2f} ({s2[0] / st[0] * 100 - 100:+5.1f} %)  "
+              f"tris/ray {s2[1] / len(rays):5.2f} ({s2[1] / st[1] * 100 - 100:+5.1f} %)  results bit-identical to the fp32 traversal: {same}")
         e.emu_free(h)
 
 

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../embree_b200/csrc/rt_core.cuh"
+#include "rt_core_h2.cuh"
 
 using namespace rtk;
 
@@ -393,7 +394,8 @@ static uint32_t node_hitmask_h16(const Node8& nd, const Ray& r, float idx, float
 }
 
 // stats: [0] node steps, [1] triangle tests.  Hits are written to the RTCRayHit records like emu_trace does.
-extern "C" void emu_trace_h16(void* h, void* rays, uint64_t n, float pad_cells, int magic, uint64_t* stats) {
+template <typename NodeTest>
+static void trace_with_node_test(void* h, void* rays, uint64_t n, uint64_t* stats, const NodeTest& node_test) {
   EmuScene* sc = static_cast<EmuScene*>(h);
   const Node8* nodes = sc->nodes.data();
   const TriRec* tris = sc->tris.data();
@@ -419,7 +421,7 @@ extern "C" void emu_trace_h16(void* h, void* rays, uint64_t n, float pad_cells, 
         const uint32_t ni = ngx + (uint32_t)popc32(ngy & 0xFFu & ((1u << slot) - 1u));
         const Node8& nd = nodes[ni];
         stats[0]++;
-        const uint32_t hm = node_hitmask_h16(nd, r, idx, idy, idz, negx, negy, negz, tnear_c, tfar_c, oct, pad_cells, magic);
+        const uint32_t hm = node_test(nd, r, idx, idy, idz, negx, negy, negz, tnear_c, tfar_c, oct);
         ngx = nd.w[4]; ngy = (hm & 0xFF000000u) | (nd.w[3] >> 24);
         tgx = nd.w[5]; tgy = hm & 0x00FFFFFFu;
       } else { tgx = ngx; tgy = ngy; ngx = 0; ngy = 0; }
@@ -449,4 +451,21 @@ extern "C" void emu_trace_h16(void* h, void* rays, uint64_t n, float pad_cells, 
     uint32_t ids[4] = {hit.primID, hit.geomID, 0xFFFFFFFFu, 0xFFFFFFFFu};
     memcpy(rec + 68, ids, 16);
   }
+}
+
+extern "C" void emu_trace_h16(void* h, void* rays, uint64_t n, float pad_cells, int magic, uint64_t* stats) {
+  trace_with_node_test(h, rays, n, stats, [=](const Node8& nd, const Ray& r, float idx, float idy, float idz, bool negx, bool negy, bool negz,
+                                             float tn, float tf, uint32_t oct) {
+    return node_hitmask_h16(nd, r, idx, idy, idz, negx, negy, negz, tn, tf, oct, pad_cells, magic);
+  });
+}
+
+// the packed-half node test the device would run (embree_b200/csrc/rt_core_h2.cuh, same source, _Float16 emulation)
+extern "C" void emu_trace_h2(void* h, void* rays, uint64_t n, uint64_t* stats) {
+  trace_with_node_test(h, rays, n, stats, [](const Node8& nd, const Ray& r, float idx, float idy, float idz, bool negx, bool negy, bool negz,
+                                            float tn, float tf, uint32_t oct) {
+    const uint32_t* w = nd.w;
+    const u32x4 n0{w[0], w[1], w[2], w[3]}, n1{w[4], w[5], w[6], w[7]}, n2{w[8], w[9], w[10], w[11]}, n3{w[12], w[13], w[14], w[15]}, n4{w[16], w[17], w[18], w[19]};
+    return node_hitmask_h2(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz, tn, tf, (7u - oct) * 0x01010101u);
+  });
 }
