@@ -291,9 +291,27 @@ def main():
         dist.barrier()
     sampler.stop_flag = True
     launches = lib.rtcb200GetLaunchCount() - l0
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=devt)
+    ms_local = e0.elapsed_time(e1) / args.steps
+    ms = torch.tensor([ms_local], device=devt)
+    per_rank = None
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # diagnostics only: every rank's own step time, trace time (direct mode: includes stalls on the peer stores) and
+        # SM clock, so that a slow step can be attributed to the gather (all ranks but 0 slow) or to single GPUs
+        vals = [float(ms_local), 0.0, 0.0, 0.0]
+        try:   # rank-local parsing must never keep a rank out of the collective below
+            vals[1] = float(np.mean(kernel_ms)) if kernel_ms else 0.0
+            sampler.join(timeout=2)
+            cs = sampler.summary()
+            vals[2] = float(cs.get("sm_mhz") or 0.0)
+            vals[3] = 1.0 if cs.get("reasons") and cs["reasons"] != ["unavailable"] else 0.0
+        except Exception as ex:   # noqa: BLE001
+            log(f"per-rank diagnostics incomplete: {ex}")
+        mine = torch.tensor(vals, dtype=torch.float32, device=devt)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        per_rank = {"ms_per_step": [round(float(x[0]), 3) for x in allv], "trace_ms": [round(float(x[1]), 3) for x in allv],
+                    "sm_mhz": [float(x[2]) for x in allv], "throttled": [bool(x[3] > 0) for x in allv]}
     ms_per_step = float(ms.item())
     value = n * world / (ms_per_step * 1e-3) * 1e-6
     lib.check(dev)
@@ -463,7 +481,7 @@ def main():
         line = {"metric": "Mrays/s incoherent diffuse-bounce, 10M-triangle scene", "value": value, "unit": "Mrays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, len(t)),
-                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "gather_verified": gather_ok,
+                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "gather_verified": gather_ok, "per_rank": per_rank,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                              "traffic": traffic, "peak_source": peak_src, "kernel": "rtk::trace_kernel<K=1,OCCLUDED=false,STATS=false,ROBUST=false,GENERAL=false>",
                              "kernel_ms": kms, "algorithmic_bytes_per_ray": bytes_per_ray,
