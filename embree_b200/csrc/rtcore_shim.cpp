@@ -486,6 +486,7 @@ static thread_local GatherPipe t_gather;
 void trace_gather(SceneImpl* s, void* d_rays, size_t M, uint32_t instID, uint32_t instPrimID, cudaStream_t st, void* compact_out) {
   require_committed(s);
   if (M == 0) return;
+  if (reinterpret_cast<uintptr_t>(compact_out) & 31) fail(RTC_ERROR_INVALID_ARGUMENT, "compact_out must be 32-byte aligned (one 256-bit store per record)");
   cudaSetDevice(s->dev->gpu);
   const bool staged = g_gather_mode == 1;
   if (!s->ev0) { cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); }

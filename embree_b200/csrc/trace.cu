@@ -112,6 +112,13 @@ __device__ __forceinline__ void to_object_space(const GeomDesc& d, Ray& r) {
   r.dz = fma_rn(dx, d.w2l[2], fma_rn(dy, d.w2l[5], mul_rn(dz, d.w2l[8])));
 }
 
+// 32-byte aligned 256-bit global store (PTX st.global.v8.f32 -> STG.E.256 on sm_100a)
+__device__ __forceinline__ void store_256(void* dst, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4),
+               "f"(a5), "f"(a6), "f"(a7)
+               : "memory");
+}
+
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_WARPS = TRACE_THREADS / 32;
 
@@ -416,9 +423,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
           }
         }
         if (K == 1 && !OCCLUDED && p.compact_out) {   // fused hit gather: compact record, possibly over NVLink
-          float4* co = reinterpret_cast<float4*>(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32);
-          co[0] = make_float4(tfar_tri, cngx, cngy, cngz);
-          co[1] = make_float4(found ? hit_u : 0.0f, found ? hit_v : 0.0f, __uint_as_float(cprim), __uint_as_float(cgeom));
+          // one 256-bit store per record (STG.256, new on sm_100): over NVLink the record travels as ONE full 32-byte
+          // sector instead of two 16-byte partial writes
+          store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, tfar_tri, cngx, cngy, cngz, found ? hit_u : 0.0f,
+                    found ? hit_v : 0.0f, __uint_as_float(cprim), __uint_as_float(cgeom));
         }
         active = false;
       }

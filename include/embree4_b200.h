@@ -303,7 +303,7 @@ RTCB200_API void rtcb200IntersectNM(const int* valid, RTCScene scene, void* rayh
 RTCB200_API void rtcb200OccludedNM(const int* valid, RTCScene scene, void* rayK, unsigned int K, size_t M, struct RTCOccludedArguments* args);
 RTCB200_API void rtcb200Intersect1MDevice(RTCScene scene, struct RTCRayHit* d_rayhits, size_t M, struct RTCIntersectArguments* args, void* cuda_stream);
 /* as rtcb200Intersect1MDevice, and additionally writes one compact 32-byte record {tfar, Ng.xyz, u, v, primID, geomID} per
- * ray (primID = geomID = -1 on a miss) to compact_out[i].  compact_out may be memory of ANOTHER GPU imported with
+ * ray (primID = geomID = -1 on a miss) to compact_out[i] (32-byte aligned).  compact_out may be memory of ANOTHER GPU imported with
  * rtcb200PeerImport (the multi-GPU hit gather): the trace kernel stores each record as its ray terminates, straight over
  * NVLink when the buffer is a peer's.  rtcb200SetTuning("gather_mode", 1) selects the alternative pipeline: the stream
  * is traced in "gather_chunks" launches whose records are pushed by the copy engine while the next chunks are traced.
