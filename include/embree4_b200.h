@@ -339,8 +339,11 @@ RTCB200_API void rtcb200SetSceneStatCounters(RTCScene scene, int enable); /* rou
 RTCB200_API void rtcb200ResetSceneStatCounters(RTCScene scene);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 RTCB200_API unsigned long long rtcb200GetLaunchCount(void);
-/* experiment knobs of the kernels ("collapse_policy", "tri_batch_min", "tri_wait_max", "blocks_per_sm", "use_tma");
- * the defaults are the shipped configuration.  Returns 0, or -1 for an unknown key. */
+/* experiment knobs (process-wide): kernels "collapse_policy", "c_node", "c_tri", "sah_small", "tri_batch_min",
+ * "tri_wait_max", "refill_min", "blocks_per_sm", "use_tma"; host-pointer pipeline "host_chunk_log2", "host_streams";
+ * hit gather "gather_mode" (0 kernel stores, 1 staged copy-engine pushes), "gather_chunks"; EXPERIMENTAL, not yet run on
+ * a GPU: "tri_spread" (warp-wide triangle redistribution).  The defaults are the shipped, measured configuration.
+ * Returns 0, or -1 for an unknown key or an out-of-range value. */
 RTCB200_API int rtcb200SetTuning(const char* key, int value);
 /* device time (ms) of the most recent batched Device trace launch, measured with events on its stream; -1 if none */
 RTCB200_API double rtcb200GetLastTraceMs(RTCScene scene);
