@@ -112,3 +112,66 @@ def test_empty_scene(oracle):
     out = sc.trace(make_rayhits([[0, 0, -1]], [[0, 0, 1]]))
     assert out["geomID"][0] == 0xFFFFFFFF and np.isinf(out["tfar"][0])
     sc.free()
+
+
+@pytest.mark.parametrize("robust", [False, True])
+def test_oracle_quads_and_instances_vs_reference_live(oracle, robust):
+    """Randomised scenes beyond the golden fixtures, side by side with the unmodified reference when it is present: a
+    quad mesh (non-planar quads, a triangle-as-quad, an invalid quad), a triangle mesh and four instances of a child
+    scene that itself mixes quads and triangles, with geometry / instance / ray masks."""
+    R = load_reference()
+    if R is None:
+        pytest.skip("oracle/_ref not built here (python oracle/build_ref.py)")
+    rng = np.random.RandomState(11 + robust)
+    qv, qq = scenes.quad_terrain(24, seed=4)
+    qq = qq.copy()
+    qq[3, 3] = qq[3, 2]                      # triangle as quad
+    qq[7] = (0, 1, 2, 0x7FFFFFF0)            # invalid index: dropped whole
+    sv, st = scenes.triangle_sphere(9)
+    sv = (sv * np.float32(0.3) + np.float32([0.2, 0.5, -0.1])).astype(np.float32)
+    cv, cq = scenes.quad_terrain(6, seed=8)
+    cv = (cv * np.float32(0.4)).astype(np.float32)
+    xf = []
+    for i in range(4):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        m = (q * rng.uniform(0.5, 1.5, 3)).astype(np.float32)
+        xf.append(np.concatenate([m.T.reshape(-1), rng.uniform(-1, 1, 3) + (0, 0.8, 0)]).astype(np.float32))
+    imask = [0xFFFFFFFF, 0x1, 0x6, 0xFFFFFFFF]
+    flags = 4 if robust else 0
+    dev = R.new_device(None)
+    child = R.rtcNewScene(dev)
+    if flags:
+        R.rtcSetSceneFlags(child, flags)
+    keep = [R.add_quad_mesh(dev, child, cv, cq, mask=0x3, geom_id=0)[1], R.add_triangle_mesh(dev, child, sv * np.float32(0.5), st, mask=0xFFFFFFFF, geom_id=1)[1]]
+    R.rtcCommitScene(child)
+    top = R.rtcNewScene(dev)
+    if flags:
+        R.rtcSetSceneFlags(top, flags)
+    keep += [R.add_quad_mesh(dev, top, qv, qq, mask=0x5, geom_id=0)[1], R.add_triangle_mesh(dev, top, sv, st, mask=0xFFFFFFFF, geom_id=1)[1]]
+    for i, m in enumerate(xf):
+        R.add_instance(dev, top, child, m, mask=imask[i], geom_id=2 + i)
+    R.rtcCommitScene(top)
+    R.check(dev)
+    org = rng.uniform(-1.2, 1.2, (30000, 3)).astype(np.float32)
+    org[:, 1] = np.abs(org[:, 1]) + 0.3
+    rays = make_rayhits(org, rng.normal(size=(30000, 3)).astype(np.float32))
+    rays["mask"][0::4] = 0x1
+    rays["mask"][1::4] = 0x2
+    rays["mask"][2::4] = 0x4
+    want = R.intersect(top, rays.copy(), "1")
+    wocc = R.occluded(top, rays_of(rays), "1")
+    oc = oracle.scene([(cv, cq, 0, 0x3), (sv * np.float32(0.5), st, 1, 0xFFFFFFFF)], robust=robust)
+    ot = oracle.scene([(qv, qq, 0, 0x5), (sv, st, 1, 0xFFFFFFFF)], robust=robust,
+                      instances=[(oc, m, 2 + i, imask[i]) for i, m in enumerate(xf)])
+    got = ot.trace(rays.copy())
+    rep = compare_hits(want, got, 1e-5)
+    assert rep["hits"] > 3000 and (want["instID"] != 0xFFFFFFFF).sum() > 300
+    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 2, rep
+    assert rep["max_rel_t"] <= 1e-5 and rep["max_abs_uv"] <= 1e-5, rep
+    gocc = ot.trace(rays_of(rays), occluded=True)
+    assert (gocc["tfar"].view(np.uint32) == wocc["tfar"].view(np.uint32)).all()
+    ot.free()
+    oc.free()
+    R.rtcReleaseScene(top)
+    R.rtcReleaseScene(child)
+    R.rtcReleaseDevice(dev)
