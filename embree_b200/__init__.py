@@ -10,7 +10,8 @@ import os
 from .rtc import RTCLib  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libembree4_b200.so")
+# EMBREE_B200_LIB: A/B measurements of alternative BUILDS of this same library (scripts/ab.py); never a fallback
+LIB_PATH = os.environ.get("EMBREE_B200_LIB") or os.path.join(_HERE, "csrc", "libembree4_b200.so")
 _lib = None
 
 

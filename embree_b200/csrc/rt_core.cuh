@@ -28,20 +28,25 @@ namespace rtk {
 // ------------------------------------------------------------------------------------------------
 // HBM layout
 // ------------------------------------------------------------------------------------------------
-// BVH8 node, 80 bytes = 5 x 16 B (compressed wide BVH: 8-bit child boxes on a per-node power-of-two grid).
-//   w0 : px, py, pz (float bits)                | ex | ey<<8 | ez<<16 | imask<<24
-//   w1 : child_base | tri_base | meta[0..3] | meta[4..7]
-//   w2 : qlo_x[0..3] qlo_x[4..7] qlo_y[0..3] qlo_y[4..7]
-//   w3 : qlo_z[0..3] qlo_z[4..7] qhi_x[0..3] qhi_x[4..7]
-//   w4 : qhi_y[0..3] qhi_y[4..7] qhi_z[0..3] qhi_z[4..7]
-// meta[i]: 0 = empty slot; internal child: 0b001'sssss with sssss = 24 + i; leaf: high 3 bits = triangle count
-// in unary (1 -> 001, 2 -> 011, 3 -> 111), low 5 bits = offset of its first triangle from tri_base (0..23).
-// imask bit i is set when slot i holds an internal child; internal children of a node are stored consecutively
-// from child_base in slot order, triangles of its leaf slots consecutively from tri_base.
-struct alignas(16) Node8 {
-  uint32_t w[20];
+// BVH8 node, 96 bytes = 3 x 32 B, 32-byte aligned: one node is three 256-bit loads (LDG.E.256 on sm_100a), each a
+// whole DRAM/L2 sector (compressed wide BVH: 8-bit child boxes on a per-node power-of-two grid).
+//   w0..w2  : px, py, pz (float bits) -- origin of the node's grid
+//   w3      : ex | ey<<8 | ez<<16 | imask<<24   (biased exponents of the grid scale per axis; imask bit s = slot s
+//             holds an internal child)
+//   w4, w5  : child_base, tri_base
+//   w6..w11 : leaf masks, 3 bytes per slot (slot s at byte 24 + 3 s): bit k set = triangle tri_base + k belongs to the
+//             leaf in slot s (<= kMaxLeafTris bits per slot, <= 24 per node, disjoint); 0 for internal / empty slots
+//   w12..w23: quantised planes, one byte per slot: qlo_x[8] qlo_y[8] qlo_z[8] qhi_x[8] qhi_y[8] qhi_z[8]
+// Internal children of a node are stored consecutively from child_base in slot order, the triangles of its leaf slots
+// consecutively from tri_base.  Round 1 used an 80-byte node with one packed meta byte per slot: every visit then
+// decoded count/offset per child and straddled three sectors with five 16-byte loads; the precomputed masks cost
+// 16 bytes per node and remove the decode from the inner loop.
+struct alignas(32) Node8 {
+  uint32_t w[24];
 };
-static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+static_assert(sizeof(Node8) == 96, "Node8 must be 96 bytes");
+constexpr int kNodePlaneWord = 12;   // first word of the quantised planes
+constexpr int kNodeMaskByte = 24;    // first byte of the per-slot leaf masks
 
 // Triangle record, 48 bytes = 3 x 16 B; what the reference keeps per lane of a Triangle4 block
 // (kernels/geometry/triangle.h:98-120: v0, e1 = v0 - v1, e2 = v2 - v0) plus ids and the geometry mask.
@@ -240,6 +245,32 @@ RT_HD void pluecker_uv(const PlueckerHit& h, float& u, float& v) {   // Pluecker
 // ------------------------------------------------------------------------------------------------
 struct ChildBox { float lo[3], hi[3]; };
 
+// per-slot leaf masks: 3 bytes at byte kNodeMaskByte + 3 s of the node
+RT_HD void node_set_leafmask(Node8& nd, int s, uint32_t m24) {
+  for (int k = 0; k < 3; ++k) {
+    const int b = kNodeMaskByte + 3 * s + k;
+    nd.w[b >> 2] |= ((m24 >> (8 * k)) & 0xFFu) << (8 * (b & 3));
+  }
+}
+// the 24-bit mask of slot s in the low bits; bits 24..31 are NOT cleared (callers mask the union once)
+RT_HD uint32_t node_leafmask_raw(const uint32_t* w, int s) {
+  const int b = kNodeMaskByte + 3 * s;
+  const uint32_t lo = w[b >> 2], hi = w[(b >> 2) + 1];
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, 8 * (b & 3));
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> (8 * (b & 3)));
+#endif
+}
+// permute the 8 bits of x so that bit j moves to position j ^ k (k in 0..7)
+RT_HD uint32_t xor_permute8(uint32_t x, uint32_t k) {
+  if (k & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+  if (k & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+  if (k & 4u) x = ((x & 0x0Fu) << 4) | ((x >> 4) & 0x0Fu);
+  return x;
+}
+
+
 // smallest biased exponent e such that (extent / 2^(e-127)) <= 255
 RT_HD uint32_t grid_exponent(float extent) {
   if (!(extent > 0.0f)) return 1;                     // degenerate axis: any tiny scale works, q = 0
@@ -301,8 +332,8 @@ RT_HD void encode_node_boxes(Node8& nd, const float plo[3], const float phi[3], 
   for (int a = 0; a < 6; ++a) {
     const uint32_t lo4 = q[a][0] | (q[a][1] << 8) | (q[a][2] << 16) | ((uint32_t)q[a][3] << 24);
     const uint32_t hi4 = q[a][4] | (q[a][5] << 8) | (q[a][6] << 16) | ((uint32_t)q[a][7] << 24);
-    nd.w[8 + 2 * a] = lo4;
-    nd.w[8 + 2 * a + 1] = hi4;
+    nd.w[kNodePlaneWord + 2 * a] = lo4;
+    nd.w[kNodePlaneWord + 2 * a + 1] = hi4;
   }
 }
 
@@ -521,24 +552,21 @@ RT_HD void collapse_node(const Node2* n2, uint32_t* src, uint32_t q, Node8* n8, 
   const uint32_t child_base = n_inner ? alloc.nodes(n_inner) : 0;
   const uint32_t tri_base = n_tris ? alloc.tris(n_tris) : 0;
   Node8 nd;
-  for (int k = 0; k < 20; ++k) nd.w[k] = 0;
+  for (int k = 0; k < 24; ++k) nd.w[k] = 0;
   encode_node_boxes(nd, plo, phi, cb, slot_of, n);
   nd.w[3] = (nd.w[3] & 0x00FFFFFFu) | (imask << 24);
   nd.w[4] = child_base; nd.w[5] = tri_base;
-  uint32_t meta[8];
   uint32_t ir = 0, toff = 0;
   double sah = 0.0;
   for (int s = 0; s < 8; ++s) {
-    meta[s] = 0;
     const int c = child_at[s];
     if (c < 0) continue;
     if (imask & (1u << s)) {
-      meta[s] = (1u << 5) | (24u + (uint32_t)s);
       src[child_base + ir] = cand[c];
       ++ir;
     } else {
       const uint32_t k = cnt[c];
-      meta[s] = (((1u << k) - 1u) << 5) | toff;
+      node_set_leafmask(nd, s, ((1u << k) - 1u) << toff);
       const uint32_t* sorted = half[c] ? sortedB : sortedA;
       for (uint32_t t = 0; t < k; ++t) tri_src[tri_base + toff + t] = sorted[first[c] + t];
       toff += k;
@@ -546,8 +574,6 @@ RT_HD void collapse_node(const Node2* n2, uint32_t* src, uint32_t q, Node8* n8, 
       sah += (double)((dx * (dy + dz) + dy * dz) * inv_root_area) * k;
     }
   }
-  nd.w[6] = meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24);
-  nd.w[7] = meta[4] | (meta[5] << 8) | (meta[6] << 16) | (meta[7] << 24);
   n8[q] = nd;
   sah += (double)(half_area(self) * inv_root_area);
   alloc.sah(sah);
@@ -558,37 +584,28 @@ RT_HD void collapse_node(const Node2* n2, uint32_t* src, uint32_t q, Node8* n8, 
 // pointers and the device can use the read-only / cache-hinted path.
 // ------------------------------------------------------------------------------------------------
 struct u32x4 { uint32_t x, y, z, w; };
+struct NodeW { uint32_t w[24]; };   // one node in registers (three 256-bit loads)
 struct TravStats { uint32_t nodes, tris; };
 
-RT_HD uint32_t sign_extend_s8x4(uint32_t x) {  // each byte: bit7 set -> 0xFF else 0x00
-  return ((x >> 7) & 0x01010101u) * 0xFFu;
-}
-
 // Slab test of the 8 quantised children of one node; returns the hit mask in the layout
-// [31:24] internal children ordered by traversal priority, [23:0] one bit per triangle of the node's leaf slots.
-template <bool ANYHIT>
-RT_HD uint32_t node_hitmask(const u32x4& n0, const u32x4& n1, const u32x4& n2, const u32x4& n3, const u32x4& n4,
-                            float ox, float oy, float oz, float idx, float idy, float idz, bool negx, bool negy,
-                            bool negz, float tnear, float tfar, uint32_t oct_inv4) {
-  const uint32_t e = n0.w;
+// [31:24] internal children ordered by traversal priority (slot s at bit 24 + (s ^ oct_inv), oct_inv = 7 - ray octant),
+// [23:0] one bit per triangle of the node's leaf slots.
+RT_HD uint32_t node_hitmask(const uint32_t* w, float ox, float oy, float oz, float idx, float idy, float idz, bool negx,
+                            bool negy, bool negz, float tnear, float tfar, uint32_t oct_inv) {
+  const uint32_t e = w[3];
   // per-axis: t = q * (2^e * idir) + (p - org) * idir
   const float sx = u2f((e & 0xFFu) << 23) * idx;
   const float sy = u2f(((e >> 8) & 0xFFu) << 23) * idy;
   const float sz = u2f(((e >> 16) & 0xFFu) << 23) * idz;
-  const float bx = (u2f(n0.x) - ox) * idx;
-  const float by = (u2f(n0.y) - oy) * idy;
-  const float bz = (u2f(n0.z) - oz) * idz;
-  uint32_t hitmask = 0;
+  const float bx = (u2f(w[0]) - ox) * idx;
+  const float by = (u2f(w[1]) - oy) * idy;
+  const float bz = (u2f(w[2]) - oz) * idz;
+  uint32_t leaf = 0, slots = 0;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    const uint32_t meta4 = half ? n1.w : n1.z;
-    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-    const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
-    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     // near / far planes per axis picked by the ray's direction sign
-    const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
-    const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+    const uint32_t qlox = w[kNodePlaneWord + half], qloy = w[kNodePlaneWord + 2 + half], qloz = w[kNodePlaneWord + 4 + half];
+    const uint32_t qhix = w[kNodePlaneWord + 6 + half], qhiy = w[kNodePlaneWord + 8 + half], qhiz = w[kNodePlaneWord + 10 + half];
     const uint32_t nx = negx ? qhix : qlox, fx = negx ? qlox : qhix;
     const uint32_t ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
     const uint32_t nz = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
@@ -606,14 +623,12 @@ RT_HD uint32_t node_hitmask(const u32x4& n0, const u32x4& n1, const u32x4& n2, c
       // accepts (the reference's robust mode pads by 3 ulp, node_intersector1.h:106-110)
       const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar)) * 1.0000003f;
       if (tmin <= tmax) {
-        const uint32_t bits = (child_bits4 >> sh) & 0xFFu;
-        const uint32_t idx = (bit_index4 >> sh) & 0xFFu;
-        hitmask |= bits << idx;
+        leaf |= node_leafmask_raw(w, 4 * half + j);
+        slots |= 1u << (4 * half + j);
       }
     }
   }
-  (void)ANYHIT;
-  return hitmask;
+  return (xor_permute8(slots & (e >> 24), oct_inv) << 24) | (leaf & 0x00FFFFFFu);
 }
 
 // One closest-hit (ANYHIT=false) or any-hit (ANYHIT=true) query.  On a closest hit `hit` is filled and
@@ -625,7 +640,6 @@ RT_HD bool traverse(Ray& r, Hit& hit, const NodeLoad& ldn, const TriLoad& ldt, u
   const float idx = rcp_safe(r.dx), idy = rcp_safe(r.dy), idz = rcp_safe(r.dz);
   const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;    // near/far plane selectors (node_intersector1.h:47-52)
   const uint32_t oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
-  const uint32_t oct_inv4 = (7u - oct) * 0x01010101u;
   const float tnear_c = fmaxf(r.tnear, 0.0f);                            // TravRay clamps (bvh_intersector1.cpp:65)
   float tfar_c = fmaxf(r.tfar, 0.0f);
   float tfar_tri = r.tfar;                                               // the triangle test sees the raw value
@@ -645,14 +659,12 @@ RT_HD bool traverse(Ray& r, Hit& hit, const NodeLoad& ldn, const TriLoad& ldt, u
       if (ngy & 0xFF000000u) { stack_x[sp] = ngx; stack_y[sp] = ngy; ++sp; }
       const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
       const uint32_t node_index = ngx + (uint32_t)popc32(ngy & 0xFFu & ((1u << slot) - 1u));
-      const u32x4 n0 = ldn(node_index, 0), n1 = ldn(node_index, 1), n2 = ldn(node_index, 2), n3 = ldn(node_index, 3),
-                  n4 = ldn(node_index, 4);
+      const NodeW nw = ldn(node_index);
       if (STATS) st->nodes++;
-      const uint32_t hm = node_hitmask<ANYHIT>(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz,
-                                               tnear_c, tfar_c, oct_inv4);
-      ngx = n1.x;
-      ngy = (hm & 0xFF000000u) | (n0.w >> 24);
-      tgx = n1.y;
+      const uint32_t hm = node_hitmask(nw.w, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz, tnear_c, tfar_c, 7u - oct);
+      ngx = nw.w[4];
+      ngy = (hm & 0xFF000000u) | (nw.w[3] >> 24);
+      tgx = nw.w[5];
       tgy = hm & 0x00FFFFFFu;
     } else {
       tgx = ngx; tgy = ngy; ngx = 0; ngy = 0;                            // popped entry was a triangle group

@@ -156,6 +156,11 @@ struct SceneImpl : RefCounted {
   std::mutex commitMutex;
   std::vector<GeometryImpl*> geoms;      // index == geomID
   std::vector<unsigned> committedCounter;  // modCounter snapshot of the last commit (scene.cpp:878-884)
+  // Instances are flattened into this scene's BVH at commit, so a re-committed CHILD scene must make the parent's next
+  // rtcCommitScene rebuild (the reference traverses the child BVH live and sees child edits without this): every
+  // successful commit bumps `generation`, and the parent remembers the generation of each instanced scene it baked in.
+  std::atomic<unsigned long long> generation{0};
+  std::vector<unsigned long long> committedChildGen;
   RTCSceneFlags flags = RTC_SCENE_FLAG_NONE;
   RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
   bool flagsModified = true;  // forces the first commit (scene_verify.cpp:11-22 isModified())
@@ -184,6 +189,10 @@ struct SceneImpl : RefCounted {
       const unsigned cur = geoms[i] ? geoms[i]->modCounter : 0u;
       const unsigned old = i < committedCounter.size() ? committedCounter[i] : 0u;
       if (cur != old) return true;
+      if (geoms[i] && geoms[i]->instScene) {
+        const unsigned long long g = i < committedChildGen.size() ? committedChildGen[i] : ~0ull;
+        if (geoms[i]->instScene->generation.load() != g) return true;
+      }
     }
     return geoms.size() != committedCounter.size();
   }
@@ -256,6 +265,7 @@ void commit_scene(SceneImpl* s) {
   for (void* p : s->deviceBuffers) cudaFreeAsync(p, 0);
   s->deviceBuffers.clear();
   std::vector<rtk::GeomDesc> descs;
+  std::vector<unsigned long long> childGen(geoms.size(), 0ull);   // generation of every instanced scene as baked in below
   std::unordered_map<GeometryImpl*, std::pair<void*, void*>> uploaded;   // a mesh instanced many times is uploaded once
   bool instanced = false, quads = false;
   float instBounds[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -303,6 +313,7 @@ void commit_scene(SceneImpl* s) {
     if (!child) fail(RTC_ERROR_INVALID_OPERATION, "instance has no instanced scene");
     if (!child->everCommitted) fail(RTC_ERROR_INVALID_OPERATION, "instanced scene not committed");
     instanced = true;
+    childGen[id] = child->generation.load();
     std::vector<GeometryImpl*> cgeoms;
     { std::lock_guard<std::mutex> lg(child->geomMutex); cgeoms = child->geoms; }
     for (size_t cid = 0; cid < cgeoms.size(); ++cid) {
@@ -351,6 +362,8 @@ void commit_scene(SceneImpl* s) {
     std::lock_guard<std::mutex> lg(s->geomMutex);
     s->committedCounter.assign(geoms.size(), 0u);
     for (size_t i = 0; i < geoms.size(); ++i) s->committedCounter[i] = geoms[i] ? geoms[i]->modCounter : 0u;
+    s->committedChildGen = childGen;
+    s->generation.fetch_add(1);
     // geometries attached while we were building keep the scene modified
     s->flagsModified = false;
     s->everCommitted = true;
@@ -494,7 +507,7 @@ void trace_gather(SceneImpl* s, void* d_rays, size_t M, uint32_t instID, uint32_
     cudaEventRecord(s->ev0, st);
     rtk::TraceParams p = make_params(s, d_rays, nullptr, (unsigned long long)M, instID, instPrimID);
     p.compact_out = compact_out;
-    if (s->gpu.root_valid) cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, st), "trace launch");
+    cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, st), "trace launch");   // empty scene: every ray stores its miss record
     cudaEventRecord(s->ev1, st);
     return;
   }
@@ -643,7 +656,7 @@ RTCDevice rtcNewDevice(const char* config) {
   return nullptr;
 }
 void rtcRetainDevice(RTCDevice h) { API_BEGIN VERIFY_HANDLE(h); std::lock_guard<std::mutex> lk(g_deviceMutex); D(h)->retain(); API_END(D(h)) }
-void rtcReleaseDevice(RTCDevice h) { API_BEGIN VERIFY_HANDLE(h); std::lock_guard<std::mutex> lk(g_deviceMutex); t_err.erase(D(h)); D(h)->release(); API_END(nullptr) }
+void rtcReleaseDevice(RTCDevice h) { API_BEGIN VERIFY_HANDLE(h); std::lock_guard<std::mutex> lk(g_deviceMutex); if (D(h)->rc.load() == 1) t_err.erase(D(h)); D(h)->release(); API_END(nullptr) }
 
 ssize_t rtcGetDeviceProperty(RTCDevice h, enum RTCDeviceProperty prop) {
   API_BEGIN
@@ -664,7 +677,7 @@ ssize_t rtcGetDeviceProperty(RTCDevice h, enum RTCDeviceProperty prop) {
     case RTC_DEVICE_PROPERTY_IGNORE_INVALID_RAYS_ENABLED: return 0;
     case RTC_DEVICE_PROPERTY_COMPACT_POLYS_ENABLED: return 0;
     case RTC_DEVICE_PROPERTY_TRIANGLE_GEOMETRY_SUPPORTED: return 1;
-    case RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED:
+    case RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED: return 1;
     case RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED:
     case RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED:
     case RTC_DEVICE_PROPERTY_USER_GEOMETRY_SUPPORTED:

@@ -10,21 +10,19 @@
 
 namespace rtk {
 
-// ---- 16-byte loads of the BVH through the read-only path ------------------------------------------------------
-struct NodeLoadG {
-  const uint4* __restrict__ base;
-  __device__ __forceinline__ u32x4 operator()(uint32_t node, int k) const {
-    const uint4 v = __ldg(base + (size_t)node * 5 + k);
-    return u32x4{v.x, v.y, v.z, v.w};
-  }
-};
-struct TriLoadG {
-  const uint4* __restrict__ base;
-  __device__ __forceinline__ u32x4 operator()(uint32_t tri, int k) const {
-    const uint4 v = __ldg(base + (size_t)tri * 3 + k);
-    return u32x4{v.x, v.y, v.z, v.w};
-  }
-};
+// ---- loads of the BVH through the read-only path -----------------------------------------------------------------
+// A node is 96 bytes, 32-byte aligned: three 256-bit loads (ld.global.nc.v8.b32 -> LDG.E.ENL2.256.CONSTANT on sm_100a),
+// each exactly one sector.  Round 1 fetched an 80-byte node with five 16-byte loads: 5 L1 tag lookups per lane per node
+// instead of 3, and the same three sectors from L2 / HBM.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* d) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void load_node(const Node8* __restrict__ nodes, uint32_t node_index, NodeW& nw) {
+  const char* np = reinterpret_cast<const char*>(nodes) + (size_t)node_index * sizeof(Node8);
+  ldg256(np, nw.w); ldg256(np + 32, nw.w + 8); ldg256(np + 64, nw.w + 16);
+}
 
 // ---- ray / hit I/O adapters ------------------------------------------------------------------------------------
 // K == 1 : AoS RTCRayHit (96 B, hit at +48) or RTCRay (48 B).  K in {4,8,16}: SoA inside each packet
@@ -130,15 +128,30 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
+// compile-time experiment switch (A/B builds only; the shipped value is the default below)
+#ifndef RTK_MIN_BLOCKS
+#define RTK_MIN_BLOCKS 8   // resident CTAs per SM the register allocation is bounded for (8 x 128 threads -> 64 registers)
+#endif
+#ifndef RTK_TRI2
+#define RTK_TRI2 1   // a lane with two or more pending triangles tests two per triangle step (both records fetched together)
+#endif
+
 // Persistent warps.  Every warp owns the 32-ray blocks w, w+W, w+2W, ... of the stream (W = warps in the grid).  When
 // a warp starts consuming a block, lane 0 issues a TMA bulk prefetch (cp.async.bulk.prefetch.L2) of the block two ahead,
-// so the ray records are L2-resident by the time lanes load them.  A lane whose ray has terminated writes its result
-// and takes the next unassigned ray of the current block (ballot + popc ranking, no atomics).  One loop iteration = at most one node step (pop a child of the current node group, fetch the 80-byte
-// node, slab-test its 8 children) for the lanes that want it, and at most one triangle step, batched across the warp;
-// the phases are warp-synchronous so lanes in the same phase execute together instead of serialising through a
-// per-thread while-while loop.  The top stack entry lives in registers; deeper entries in (L1-resident) local memory.
+// so the ray records are L2-resident by the time lanes load them.  A lane is EMPTY (no ray), TRACING, or DONE (its ray
+// has terminated, the result is still in registers).  One loop iteration =
+//   1. when enough lanes are not TRACING: DONE lanes write their hit records back together (the winning triangle's
+//      record is re-read for Ng and the ids: batching overlaps those loads across lanes instead of paying the latency
+//      once per ray), then EMPTY lanes take the next unassigned rays of the block (ballot + popc ranking, no atomics);
+//   2. at most one node step (pop a child of the current node group, fetch the 96-byte node, slab-test 8 children);
+//   3. at most one triangle step, batched across the warp;
+//   4. pop.  The top stack entry lives in registers as a write-back cache of the local-memory stack: a pop that
+//      follows a push costs no memory access, and a local-memory load is only waited for when two pops follow each
+//      other (round 1 reloaded the register copy on every pop and stalled on it: 7.5 % of all issue-stall samples).
+// The phases are warp-synchronous so lanes in the same phase execute together instead of serialising through a
+// per-thread while-while loop.
 template <int K, bool OCCLUDED, bool STATS, bool ROBUST, bool GENERAL, bool SPREAD = false>
-__global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TraceParams p) {
+__global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(const TraceParams p) {
   const bool USE_TMA = p.use_prefetch != 0;
   using IO = RayIO<K, OCCLUDED>;
   const unsigned FULL = 0xFFFFFFFFu;
@@ -147,21 +160,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
   const uint32_t warp_id = blockIdx.x * TRACE_WARPS + (threadIdx.x >> 5);
   const uint32_t num_warps = gridDim.x * TRACE_WARPS;
   const uint32_t n = (uint32_t)p.n;
-  const uint4* __restrict__ nodes = reinterpret_cast<const uint4*>(p.nodes);
+  const Node8* __restrict__ nodes = p.nodes;
   const uint4* __restrict__ tris = reinterpret_cast<const uint4*>(p.tris);
   const int tri_batch_min = p.tri_batch_min, tri_wait_max = p.tri_wait_max, refill_min = p.refill_min;
 
   // per-lane ray state
+  enum : uint32_t { EMPTY = 0, TRACING = 1, DONE = 2 };
+  uint32_t state = EMPTY;
   Ray r;
   float idx = 0, idy = 0, idz = 0, tfar_tri = 0;
   uint32_t oct = 0;
   float hit_u = 0, hit_v = 0;            // closest hit so far: t = tfar_tri, barycentrics, triangle record index
   uint32_t hit_tri = 0;
-  bool found = false, active = false;
+  bool found = false;
   uint32_t ray_index = 0;
   uint32_t ngx = 0, ngy = 0, tgx = 0, tgy = 0;
-  uint32_t top_x = 0, top_y = 0;          // top of the traversal stack (top_y == 0: stack empty)
-  uint2 stack[kStackSize];                // deeper entries: one 8-byte local-memory slot each (L1-resident)
+  uint32_t top_x = 0, top_y = 0;          // register copy of the newest stack entry (top_y == 0: none)
+  uint2 stack[kStackSize];                // older entries: one 8-byte local-memory slot each (L1-resident)
   int sp = 0;
   // warp-uniform block cursor
   int blk = -1;                           // index into this warp's block sequence
@@ -179,11 +194,107 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
   };
   if (USE_TMA && lane == 0) { prefetch(0); prefetch(1); }
 
+  // hit epilogue of one terminated ray (intersector_epilog.h:285-299; occluded: bvh_intersector1.cpp:186-188)
+  auto write_back = [&]() {
+    float cngx = 0.0f, cngy = 0.0f, cngz = 0.0f;
+    uint32_t cprim = kInvalidID, cgeom = kInvalidID;
+    if (found) {
+      if (OCCLUDED) IO::store_tfar(p, ray_index, -INFINITY);
+      else {
+        // Ng = cross(e2, e1) and the ids come from the winning triangle's record (same arithmetic as tri_test)
+        const uint4* tp = tris + (size_t)hit_tri * 3;
+        const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        Hit hit;
+        hit.t = tfar_tri; hit.u = hit_u; hit.v = hit_v;
+        hit.primID = a.w; hit.geomID = b.w;
+        uint32_t instID = p.instID, instPrimID = p.instPrimID;
+        float lox = r.ox, loy = r.oy, loz = r.oz;   // ray origin in the space the record's triangle lives in
+        if (GENERAL) {   // ids through the descriptor; Ng stays in OBJECT space as in the reference
+          const GeomDesc& d = p.descs[b.w];
+          hit.geomID = d.geomID;
+          if (d.has_xfm) {
+            instID = d.instID; instPrimID = 0u;   // instance_id_stack::push(context, instID, 0)
+            if (ROBUST) { Ray lr = r; to_object_space(d, lr); lox = lr.ox; loy = lr.oy; loz = lr.oz; }
+          }
+        }
+        if (ROBUST) {   // stable_triangle_normal of the origin-relative edges, exactly as in tri_test_pluecker
+          const float v0x = sub_rn(__uint_as_float(a.x), lox), v0y = sub_rn(__uint_as_float(a.y), loy), v0z = sub_rn(__uint_as_float(a.z), loz);
+          const float v1x = sub_rn(__uint_as_float(b.x), lox), v1y = sub_rn(__uint_as_float(b.y), loy), v1z = sub_rn(__uint_as_float(b.z), loz);
+          const float v2x = sub_rn(__uint_as_float(c.x), lox), v2y = sub_rn(__uint_as_float(c.y), loy), v2z = sub_rn(__uint_as_float(c.z), loz);
+          stable_normal(sub_rn(v2x, v0x), sub_rn(v2y, v0y), sub_rn(v2z, v0z), sub_rn(v0x, v1x), sub_rn(v0y, v1y), sub_rn(v0z, v1z),
+                        sub_rn(v1x, v2x), sub_rn(v1y, v2y), sub_rn(v1z, v2z), hit.ngx, hit.ngy, hit.ngz);
+        } else {
+          const float e1x = __uint_as_float(b.x), e1y = __uint_as_float(b.y), e1z = __uint_as_float(b.z);
+          const float e2x = __uint_as_float(c.x), e2y = __uint_as_float(c.y), e2z = __uint_as_float(c.z);
+          hit.ngx = msub(e2y, e1z, mul_rn(e2z, e1y));
+          hit.ngy = msub(e2z, e1x, mul_rn(e2x, e1z));
+          hit.ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
+        }
+        if (GENERAL && (a.w >> 31)) {   // quad halves share the quad's primID; the second one has flipped winding
+          hit.primID = a.w & 0x7FFFFFFFu;
+          hit.ngx = -hit.ngx; hit.ngy = -hit.ngy; hit.ngz = -hit.ngz;
+        }
+        IO::store_hit(p, ray_index, hit, instID, instPrimID);
+        cngx = hit.ngx; cngy = hit.ngy; cngz = hit.ngz; cprim = hit.primID; cgeom = hit.geomID;
+      }
+    }
+    if (K == 1 && !OCCLUDED && p.compact_out) {   // fused hit gather: compact record, possibly over NVLink
+      // one 256-bit store per record (STG.256, new on sm_100): over NVLink the record travels as ONE full 32-byte
+      // sector instead of two 16-byte partial writes.  A miss (also: empty scene) writes {tfar, 0.., -1, -1}.
+      store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, tfar_tri, cngx, cngy, cngz, found ? hit_u : 0.0f,
+                found ? hit_v : 0.0f, __uint_as_float(cprim), __uint_as_float(cgeom));
+    }
+  };
+
+  // one triangle record against this lane's ray (closest hit: shrinks tfar_tri; any hit: terminates the ray)
+  auto test_tri = [&](uint32_t ti, const uint4& a, const uint4& b, const uint4& c) {
+    Ray lr = r;
+    bool visible = (c.w & r.mask) != 0;              // ray mask (intersector_epilog.h:256-262)
+    if (GENERAL) {   // b.w = descriptor index: instance mask (instance_intersector.cpp:19-22) + object-space ray
+      const GeomDesc& d = p.descs[b.w];
+      visible = visible && (d.inst_mask & r.mask) != 0;
+      if (d.has_xfm) to_object_space(d, lr);
+    }
+    if (ROBUST) {   // RTC_SCENE_FLAG_ROBUST: the record holds v0, v1, v2; watertight Pluecker test
+      PlueckerHit ph;
+      if (visible && tri_test_pluecker(lr, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
+                            __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
+                            __uint_as_float(c.z), ph)) {
+        found = true;
+        if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
+        else {
+          tfar_tri = ph.t; pluecker_uv(ph, hit_u, hit_v); hit_tri = ti;
+          if (GENERAL && (a.w >> 31)) {   // second half of a quad (QuadHitPlueckerM::finalize, AVX form)
+            const float u1 = sub_rn(1.0f, hit_u), v1 = sub_rn(1.0f, hit_v);
+            hit_u = v1; hit_v = u1;
+          }
+        }
+      }
+    } else {
+      TriHit th;
+      if (visible && tri_test(lr, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
+                   __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
+                   __uint_as_float(c.z), th)) {
+        found = true;
+        if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }     // any hit terminates the ray
+        else {
+          const float rcpAbsDen = 1.0f / th.absDen;      // finalize(): t,u,v = T,U,V * rcp(absDen)
+          tfar_tri = th.T * rcpAbsDen;
+          if (GENERAL && (a.w >> 31)) {   // second half of a quad: U' = absDen - V, V' = absDen - U (quad_intersector_moeller.h:196-198)
+            hit_u = sub_rn(th.absDen, th.V) * rcpAbsDen; hit_v = sub_rn(th.absDen, th.U) * rcpAbsDen;
+          } else { hit_u = th.U * rcpAbsDen; hit_v = th.V * rcpAbsDen; }
+          hit_tri = ti;
+        }
+      }
+    }
+  };
+
   for (;;) {
-    // ---- 1. refill idle lanes from the resident ray block
-    const unsigned idle = __ballot_sync(FULL, !active);
-    // refill in batches: the refill code runs for the whole warp, so wait until a few lanes are idle (or none is busy)
+    // ---- 1. write back finished rays and refill, in batches: this code runs for the whole warp, so wait until a few
+    // lanes have nothing to trace (or none has)
+    const unsigned idle = __ballot_sync(FULL, state != TRACING);
     if (idle && (__popc(idle) >= refill_min || idle == FULL)) {
+      if (state == DONE) { write_back(); state = EMPTY; }
       if (!warp_done) {
         if (consumed == blk_count) {       // resident block used up (or nothing loaded yet): move to the next one
           if (USE_TMA && lane == 0) prefetch(blk + 3);   // keep the stream two blocks ahead in L2
@@ -199,7 +310,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
         if (!warp_done) {
           const uint32_t avail = blk_count - consumed;
           const uint32_t rank = __popc(idle & lt_mask);
-          if (!active && rank < avail) {
+          if (state == EMPTY && rank < avail) {
             ray_index = blk_first + consumed + rank;
             bool valid = true;
             if (K > 1) valid = (p.valid == nullptr) || (p.valid[ray_index] == -1);   // inactive lanes stay untouched
@@ -208,27 +319,28 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
               if (STATS) ++st_rays;
               found = false;
               sp = 0; top_y = 0; tgx = 0; tgy = 0;
-              // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129)
+              // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129); they still
+              // pass through DONE so that a gather buffer receives their miss record
               const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
               idx = rcp_safe_fast(r.dx); idy = rcp_safe_fast(r.dy); idz = rcp_safe_fast(r.dz);
               oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
               tfar_tri = r.tfar;
               ngx = 0; ngy = go ? 0x80000000u : 0u;   // root entered as "one pending internal child, imask 0"
-              active = go;
+              state = go ? TRACING : DONE;
             }
           }
           const uint32_t want = __popc(idle);
           consumed += want < avail ? want : avail;
         }
       }
-      if (!__any_sync(FULL, active)) {
-        if (warp_done) break;
+      if (!__any_sync(FULL, state == TRACING)) {
+        if (warp_done && !__any_sync(FULL, state == DONE)) break;
         continue;
       }
     }
+    const bool tracing = state == TRACING;
     // ---- 2. node step for lanes that have no triangle pending and a node child pending
-    const bool want_node = active && tgy == 0 && (ngy & 0xFF000000u);
-    if (want_node) {
+    if (tracing && tgy == 0 && (ngy & 0xFF000000u)) {
       const int bit = 31 - __clz((int)ngy);
       ngy &= ~(1u << bit);
       if (ngy & 0xFF000000u) {           // push the rest of the group
@@ -237,23 +349,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
       }
       const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
       const uint32_t node_index = ngx + (uint32_t)__popc(ngy & 0xFFu & ((1u << slot) - 1u));
-      const uint4* np = nodes + (size_t)node_index * 5;
-      const uint4 a0 = __ldg(np), a1 = __ldg(np + 1), a2 = __ldg(np + 2), a3 = __ldg(np + 3), a4 = __ldg(np + 4);
+      NodeW nw;
+      load_node(nodes, node_index, nw);
       if (STATS) ++st_nodes;
-      const u32x4 n0{a0.x, a0.y, a0.z, a0.w}, n1{a1.x, a1.y, a1.z, a1.w}, n2{a2.x, a2.y, a2.z, a2.w},
-          n3{a3.x, a3.y, a3.z, a3.w}, n4{a4.x, a4.y, a4.z, a4.w};
       // TravRay clamps tnear/tfar at 0 for the slab test only (bvh_intersector1.cpp:65); after a hit tray.tfar = ray.tfar (:105)
-      const uint32_t hm = node_hitmask<OCCLUDED>(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, (oct & 1u) != 0,
-                                                 (oct & 2u) != 0, (oct & 4u) != 0, fmaxf(r.tnear, 0.0f), fmaxf(tfar_tri, 0.0f),
-                                                 (7u - oct) * 0x01010101u);
-      ngx = n1.x;
-      ngy = (hm & 0xFF000000u) | (n0.w >> 24);
-      tgx = n1.y;
+      const uint32_t hm = node_hitmask(nw.w, r.ox, r.oy, r.oz, idx, idy, idz, (oct & 1u) != 0, (oct & 2u) != 0, (oct & 4u) != 0,
+                                       fmaxf(r.tnear, 0.0f), fmaxf(tfar_tri, 0.0f), 7u - oct);
+      ngx = nw.w[4];
+      ngy = (hm & 0xFF000000u) | (nw.w[3] >> 24);
+      tgx = nw.w[5];
       tgy = hm & 0x00FFFFFFu;
     }
     // ---- 3. triangle step, batched across the warp
-    const unsigned tri_lanes = __ballot_sync(FULL, active && tgy != 0);
-    const unsigned node_lanes = __ballot_sync(FULL, active && tgy == 0 && (ngy & 0xFF000000u));
+    const unsigned tri_lanes = __ballot_sync(FULL, tracing && tgy != 0);
+    const unsigned node_lanes = __ballot_sync(FULL, tracing && tgy == 0 && (ngy & 0xFF000000u));
     if (tri_lanes && (__popc(tri_lanes) >= tri_batch_min || node_lanes == 0 || ++tri_wait >= tri_wait_max)) {
       tri_wait = 0;
       if (SPREAD) {
@@ -267,7 +376,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
         __shared__ uint32_t s_owner[TRACE_WARPS][32];
         __shared__ unsigned long long s_best[TRACE_WARPS][32];
         const int wi = threadIdx.x >> 5;
-        const bool isT = active && tgy != 0;
+        const bool isT = tracing && tgy != 0;
         const int cnt = isT ? __popc(tgy) : 0;
         int incl = cnt;
 #pragma unroll
@@ -323,113 +432,38 @@ __global__ void __launch_bounds__(TRACE_THREADS, 8) trace_kernel(const TracePara
           found = true;
         }
         __syncwarp();                                           // the queue is reused by the next triangle step
-      } else if (active && tgy != 0) {
+      } else if (tracing && tgy != 0) {
         const int tb = 31 - __clz((int)tgy);
         tgy &= ~(1u << tb);
         const uint32_t ti = tgx + (uint32_t)tb;
         const uint4* tp = tris + (size_t)ti * 3;
         const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         if (STATS) ++st_tris;
-        Ray lr = r;
-        bool visible = (c.w & r.mask) != 0;
-        if (GENERAL) {   // b.w = descriptor index: instance mask (instance_intersector.cpp:19-22) + object-space ray
-          const GeomDesc& d = p.descs[b.w];
-          visible = visible && (d.inst_mask & r.mask) != 0;
-          if (d.has_xfm) to_object_space(d, lr);
-        }
-        if (ROBUST) {   // RTC_SCENE_FLAG_ROBUST: the record holds v0, v1, v2; watertight Pluecker test
-          PlueckerHit ph;
-          if (visible && tri_test_pluecker(lr, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
-                                __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
-                                __uint_as_float(c.z), ph)) {
-            found = true;
-            if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
-            else {
-              tfar_tri = ph.t; pluecker_uv(ph, hit_u, hit_v); hit_tri = ti;
-              if (GENERAL && (a.w >> 31)) {   // second half of a quad (QuadHitPlueckerM::finalize, AVX form)
-                const float u1 = sub_rn(1.0f, hit_u), v1 = sub_rn(1.0f, hit_v);
-                hit_u = v1; hit_v = u1;
-              }
-            }
+        if (RTK_TRI2) {
+          // a second pending triangle of the same lane rides along: its record is fetched together with the first
+          // (one latency instead of two) and tested after it, against the tfar the first one left -- the sequential order
+          const bool two = tgy != 0;
+          const int tb2 = two ? 31 - __clz((int)tgy) : tb;
+          const uint32_t ti2 = tgx + (uint32_t)tb2;
+          const uint4* tp2 = tris + (size_t)ti2 * 3;
+          uint4 a2, b2, c2;
+          if (two) { a2 = __ldg(tp2); b2 = __ldg(tp2 + 1); c2 = __ldg(tp2 + 2); }
+          test_tri(ti, a, b, c);
+          if (two && tgy != 0) {          // (any hit: the first test may have terminated the ray and cleared tgy)
+            tgy &= ~(1u << tb2);
+            if (STATS) ++st_tris;
+            test_tri(ti2, a2, b2, c2);
           }
         } else {
-          TriHit th;
-          if (visible && tri_test(lr, tfar_tri, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
-                       __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y),
-                       __uint_as_float(c.z), th)) {
-            found = true;
-            if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }     // any hit terminates the ray
-            else {
-              const float rcpAbsDen = 1.0f / th.absDen;      // finalize(): t,u,v = T,U,V * rcp(absDen)
-              tfar_tri = th.T * rcpAbsDen;
-              if (GENERAL && (a.w >> 31)) {   // second half of a quad: U' = absDen - V, V' = absDen - U (quad_intersector_moeller.h:196-198)
-                hit_u = sub_rn(th.absDen, th.V) * rcpAbsDen; hit_v = sub_rn(th.absDen, th.U) * rcpAbsDen;
-              } else { hit_u = th.U * rcpAbsDen; hit_v = th.V * rcpAbsDen; }
-              hit_tri = ti;
-            }
-          }
+          test_tri(ti, a, b, c);
         }
       }
     }
     // ---- 4. pop or finish
-    if (active && tgy == 0 && (ngy & 0xFF000000u) == 0) {
-      if (top_y) {
-        const uint32_t px = top_x, py = top_y;
-        if (sp > 0) { --sp; const uint2 e = stack[sp]; top_x = e.x; top_y = e.y; }   // loads while the popped one is used
-        else top_y = 0;
-        if (py & 0xFF000000u) { ngx = px; ngy = py; }
-        else { tgx = px; tgy = py; ngx = 0; ngy = 0; }
-      } else {
-        float cngx = 0.0f, cngy = 0.0f, cngz = 0.0f;
-        uint32_t cprim = kInvalidID, cgeom = kInvalidID;
-        if (found) {
-          if (OCCLUDED) IO::store_tfar(p, ray_index, -INFINITY);   // bvh_intersector1.cpp:186-188
-          else {
-            // Ng = cross(e2, e1) and the ids come from the winning triangle's record (same arithmetic as tri_test)
-            const uint4* tp = tris + (size_t)hit_tri * 3;
-            const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-            Hit hit;
-            hit.t = tfar_tri; hit.u = hit_u; hit.v = hit_v;
-            hit.primID = a.w; hit.geomID = b.w;
-            uint32_t instID = p.instID, instPrimID = p.instPrimID;
-            float lox = r.ox, loy = r.oy, loz = r.oz;   // ray origin in the space the record's triangle lives in
-            if (GENERAL) {   // ids through the descriptor; Ng stays in OBJECT space as in the reference
-              const GeomDesc& d = p.descs[b.w];
-              hit.geomID = d.geomID;
-              if (d.has_xfm) {
-                instID = d.instID; instPrimID = 0u;   // instance_id_stack::push(context, instID, 0)
-                if (ROBUST) { Ray lr = r; to_object_space(d, lr); lox = lr.ox; loy = lr.oy; loz = lr.oz; }
-              }
-            }
-            if (ROBUST) {   // stable_triangle_normal of the origin-relative edges, exactly as in tri_test_pluecker
-              const float v0x = sub_rn(__uint_as_float(a.x), lox), v0y = sub_rn(__uint_as_float(a.y), loy), v0z = sub_rn(__uint_as_float(a.z), loz);
-              const float v1x = sub_rn(__uint_as_float(b.x), lox), v1y = sub_rn(__uint_as_float(b.y), loy), v1z = sub_rn(__uint_as_float(b.z), loz);
-              const float v2x = sub_rn(__uint_as_float(c.x), lox), v2y = sub_rn(__uint_as_float(c.y), loy), v2z = sub_rn(__uint_as_float(c.z), loz);
-              stable_normal(sub_rn(v2x, v0x), sub_rn(v2y, v0y), sub_rn(v2z, v0z), sub_rn(v0x, v1x), sub_rn(v0y, v1y), sub_rn(v0z, v1z),
-                            sub_rn(v1x, v2x), sub_rn(v1y, v2y), sub_rn(v1z, v2z), hit.ngx, hit.ngy, hit.ngz);
-            } else {
-              const float e1x = __uint_as_float(b.x), e1y = __uint_as_float(b.y), e1z = __uint_as_float(b.z);
-              const float e2x = __uint_as_float(c.x), e2y = __uint_as_float(c.y), e2z = __uint_as_float(c.z);
-              hit.ngx = msub(e2y, e1z, mul_rn(e2z, e1y));
-              hit.ngy = msub(e2z, e1x, mul_rn(e2x, e1z));
-              hit.ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
-            }
-            if (GENERAL && (a.w >> 31)) {   // quad halves share the quad's primID; the second one has flipped winding
-              hit.primID = a.w & 0x7FFFFFFFu;
-              hit.ngx = -hit.ngx; hit.ngy = -hit.ngy; hit.ngz = -hit.ngz;
-            }
-            IO::store_hit(p, ray_index, hit, instID, instPrimID);
-            cngx = hit.ngx; cngy = hit.ngy; cngz = hit.ngz; cprim = hit.primID; cgeom = hit.geomID;
-          }
-        }
-        if (K == 1 && !OCCLUDED && p.compact_out) {   // fused hit gather: compact record, possibly over NVLink
-          // one 256-bit store per record (STG.256, new on sm_100): over NVLink the record travels as ONE full 32-byte
-          // sector instead of two 16-byte partial writes
-          store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, tfar_tri, cngx, cngy, cngz, found ? hit_u : 0.0f,
-                    found ? hit_v : 0.0f, __uint_as_float(cprim), __uint_as_float(cgeom));
-        }
-        active = false;
-      }
+    if (tracing && tgy == 0 && (ngy & 0xFF000000u) == 0) {
+      if (top_y) { ngx = top_x; ngy = top_y; top_y = 0; }
+      else if (sp > 0) { --sp; const uint2 e = stack[sp]; ngx = e.x; ngy = e.y; }
+      else state = DONE;
     }
   }
   if (STATS) {
@@ -450,7 +484,19 @@ Tuning& tuning() { return g_tuning; }
 template <int K, bool OCCLUDED>
 static int launch_k(TraceParams p, cudaStream_t st) {
   if (p.n == 0) return 0;
-  if (p.n > 0x7FFFFFFFull) return (int)cudaErrorInvalidValue;   // callers split longer streams
+  if (p.n > 0x40000000ull) {   // the kernel indexes rays with 32 bits: longer streams run as consecutive 2^30-ray launches
+    const unsigned long long chunk = 0x40000000ull;   // a multiple of every packet width and of the 32-ray block
+    for (unsigned long long first = 0; first < p.n; first += chunk) {
+      TraceParams q = p;
+      q.n = (p.n - first) < chunk ? (p.n - first) : chunk;
+      q.rays = static_cast<char*>(p.rays) + first * RayIO<K, OCCLUDED>::kRayBytes;
+      if (p.valid) q.valid = p.valid + first;
+      if (p.compact_out) q.compact_out = static_cast<char*>(p.compact_out) + first * 32;
+      const int r = launch_k<K, OCCLUDED>(q, st);
+      if (r != 0) return r;
+    }
+    return 0;
+  }
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -13,7 +13,6 @@
 #include <vector>
 
 #include "../../embree_b200/csrc/rt_core.cuh"
-#include "rt_core_h2.cuh"
 
 using namespace rtk;
 
@@ -192,7 +191,7 @@ void emu_trace(void* h, void* rays, uint64_t n, int occluded, uint64_t* stats) {
   EmuScene* sc = static_cast<EmuScene*>(h);
   const Node8* nodes = sc->nodes.data();
   const TriRec* tris = sc->tris.data();
-  auto ldn = [nodes](uint32_t node, int k) { const uint32_t* w = nodes[node].w + 4 * k; return u32x4{w[0], w[1], w[2], w[3]}; };
+  auto ldn = [nodes](uint32_t node) { NodeW nw; memcpy(nw.w, nodes[node].w, sizeof nw.w); return nw; };
   auto ldt = [tris](uint32_t t, int k) { const uint32_t* w = reinterpret_cast<const uint32_t*>(&tris[t]) + 4 * k; return u32x4{w[0], w[1], w[2], w[3]}; };
   const size_t stride = occluded ? 48 : 96;
   for (uint64_t i = 0; i < n; ++i) {
@@ -242,12 +241,12 @@ extern "C" void emu_trace_sorted(void* h, void* rays, uint64_t n, uint64_t* stat
       const uint32_t ex = nd.w[3];
       const float sx = u2f((ex & 0xFF) << 23) * idx, sy = u2f(((ex >> 8) & 0xFF) << 23) * idy, sz = u2f(((ex >> 16) & 0xFF) << 23) * idz;
       const float bx = (u2f(nd.w[0]) - r.ox) * idx, by = (u2f(nd.w[1]) - r.oy) * idy, bz = (u2f(nd.w[2]) - r.oz) * idz;
-      const uint8_t* q = reinterpret_cast<const uint8_t*>(&nd.w[8]);   // qlox[8] qloy[8] qloz[8] qhix[8] qhiy[8] qhiz[8]
-      const uint8_t* meta = reinterpret_cast<const uint8_t*>(&nd.w[6]);
+      const uint8_t* q = reinterpret_cast<const uint8_t*>(&nd.w[kNodePlaneWord]);   // qlox[8] qloy[8] qloz[8] qhix[8] qhiy[8] qhiz[8]
       const uint32_t imask = ex >> 24;
       E kids[8]; int nk = 0;
       for (int s = 0; s < 8; ++s) {
-        if (meta[s] == 0) continue;
+        const uint32_t lm = node_leafmask_raw(nd.w, s) & 0xFFFFFFu;
+        if (lm == 0 && !(imask & (1u << s))) continue;
         const float lx = q[s], ly = q[8 + s], lz = q[16 + s], hx = q[24 + s], hy = q[32 + s], hz = q[40 + s];
         const float tnx = (idx < 0 ? hx : lx) * sx + bx, tfx = (idx < 0 ? lx : hx) * sx + bx;
         const float tny = (idy < 0 ? hy : ly) * sy + by, tfy = (idy < 0 ? ly : hy) * sy + by;
@@ -259,9 +258,10 @@ extern "C" void emu_trace_sorted(void* h, void* rays, uint64_t n, uint64_t* stat
           const uint32_t child = nd.w[4] + (uint32_t)popc32(imask & ((1u << s) - 1u));
           kids[nk++] = {child, tmin};
         } else {
-          const uint32_t cnt = popc32(meta[s] >> 5), off = meta[s] & 31u;
-          for (uint32_t k = 0; k < cnt; ++k) {
-            const TriRec& t = tris[nd.w[5] + off + k];
+          for (uint32_t m = lm; m;) {       // highest bit first, as the production loop
+            const int tb = 31 - clz32(m);
+            m &= ~(1u << tb);
+            const TriRec& t = tris[nd.w[5] + (uint32_t)tb];
             stats[1]++;
             TriHit th;
             if (tri_test(r, tfar, t.v0x, t.v0y, t.v0z, t.e1x, t.e1y, t.e1z, t.e2x, t.e2y, t.e2z, th) && (t.mask & r.mask)) {
@@ -300,7 +300,6 @@ extern "C" uint64_t emu_trace_ops(void* h, void* rays, uint64_t n, uint8_t* ops,
       const float idx = rcp_safe(r.dx), idy = rcp_safe(r.dy), idz = rcp_safe(r.dz);
       const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
       const uint32_t oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
-      const uint32_t oct_inv4 = (7u - oct) * 0x01010101u;
       const float tnear_c = fmaxf(r.tnear, 0.0f);
       float tfar_c = fmaxf(r.tfar, 0.0f), tfar_tri = r.tfar;
       uint32_t stack_x[kStackSize], stack_y[kStackSize];
@@ -314,11 +313,10 @@ extern "C" uint64_t emu_trace_ops(void* h, void* rays, uint64_t n, uint8_t* ops,
           const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
           const uint32_t ni = ngx + (uint32_t)popc32(ngy & 0xFFu & ((1u << slot) - 1u));
           const uint32_t* w = nodes[ni].w;
-          const u32x4 n0{w[0], w[1], w[2], w[3]}, n1{w[4], w[5], w[6], w[7]}, n2{w[8], w[9], w[10], w[11]}, n3{w[12], w[13], w[14], w[15]}, n4{w[16], w[17], w[18], w[19]};
           put('N');
-          const uint32_t hm = node_hitmask<false>(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz, tnear_c, tfar_c, oct_inv4);
-          ngx = n1.x; ngy = (hm & 0xFF000000u) | (n0.w >> 24);
-          tgx = n1.y; tgy = hm & 0x00FFFFFFu;
+          const uint32_t hm = node_hitmask(w, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz, tnear_c, tfar_c, 7u - oct);
+          ngx = w[4]; ngy = (hm & 0xFF000000u) | (w[3] >> 24);
+          tgx = w[5]; tgy = hm & 0x00FFFFFFu;
         } else { tgx = ngx; tgy = ngy; ngx = 0; ngy = 0; }
         while (tgy) {
           const int tb = 31 - clz32(tgy);
@@ -341,131 +339,4 @@ extern "C" uint64_t emu_trace_ops(void* h, void* rays, uint64_t n, uint8_t* ops,
     put(0);
   }
   return len;
-}
-
-// ---- experiment (test tool): the node test evaluated in HALF precision relative to the ray's entry time into the node,
-// as a packed-half (HFMA2/HMNMX2) device version would compute it -- two children per instruction.  Measures how many
-// extra node / triangle visits the required padding costs and checks that no hit is lost.  pad_cells = outward shift of
-// every plane in grid cells; magic = 1 folds the byte->half conversion into the FMA (h = 1024 + q, b - 1024 s).
-static inline float hround(float x) { return (float)(_Float16)x; }
-static inline float hfma(float a, float b, float c) { return hround((float)((double)a * (double)b + (double)c)); }
-static inline float hclamp(float x) { return fminf(fmaxf(x, -60000.0f), 60000.0f); }
-
-static uint32_t node_hitmask_h16(const Node8& nd, const Ray& r, float idx, float idy, float idz, bool negx, bool negy, bool negz,
-                                 float tnear, float tfar, uint32_t oct, float pad_cells, int magic) {
-  const uint32_t e = nd.w[3];
-  const float s[3] = {u2f((e & 0xFFu) << 23) * idx, u2f(((e >> 8) & 0xFFu) << 23) * idy, u2f(((e >> 16) & 0xFFu) << 23) * idz};
-  const float b[3] = {(u2f(nd.w[0]) - r.ox) * idx, (u2f(nd.w[1]) - r.oy) * idy, (u2f(nd.w[2]) - r.oz) * idz};
-  float t0 = tnear, smax = 0.0f;
-  for (int a = 0; a < 3; ++a) { t0 = fmaxf(t0, fminf(b[a], fmaf(255.0f, s[a], b[a]))); smax = fmaxf(smax, fabsf(s[a]) * 255.0f); }
-  int ex; frexpf(smax / 32768.0f, &ex);
-  const float k = ldexpf(1.0f, -ex);
-  const float slack = fabsf(t0) * 4.8e-7f * k;                       // fp32 rounding of b - t0 (2 ulp of t0)
-  float sh[3], bn[3], bf[3];
-  for (int a = 0; a < 3; ++a) {
-    sh[a] = hround(hclamp(s[a] * k));
-    const float bb = (b[a] - t0) * k, pd = pad_cells * fabsf(s[a] * k) + slack;
-    bn[a] = hclamp(bb - pd); bf[a] = hclamp(bb + pd);
-    if (magic) { bn[a] = hround(bn[a] - 1024.0f * sh[a]); bf[a] = hround(bf[a] - 1024.0f * sh[a]); }
-    else { bn[a] = hround(bn[a]); bf[a] = hround(bf[a]); }
-  }
-  float tn_h = hround(hclamp((tnear - t0) * k)); tn_h -= fabsf(tn_h) * 0.001f + 1e-7f;
-  float tf_h = hround(hclamp((tfar - t0) * k)); tf_h += fabsf(tf_h) * 0.001f + 1e-7f;
-  const uint8_t* q = reinterpret_cast<const uint8_t*>(&nd.w[8]);   // qlox[8] qloy[8] qloz[8] qhix[8] qhiy[8] qhiz[8]
-  const uint8_t* meta = reinterpret_cast<const uint8_t*>(&nd.w[6]);
-  const bool neg[3] = {negx, negy, negz};
-  uint32_t hitmask = 0;
-  for (int c = 0; c < 8; ++c) {
-    if (meta[c] == 0) continue;
-    float tmin = tn_h, tmax = tf_h;
-    for (int a = 0; a < 3; ++a) {
-      const float qn = neg[a] ? q[24 + 8 * a + c] : q[8 * a + c], qf = neg[a] ? q[8 * a + c] : q[24 + 8 * a + c];
-      const float add = magic ? 1024.0f : 0.0f;
-      tmin = fmaxf(tmin, hfma(qn + add, sh[a], bn[a]));
-      tmax = fminf(tmax, hfma(qf + add, sh[a], bf[a]));
-    }
-    if (!(tmin <= tmax)) continue;
-    const uint32_t m = meta[c];
-    const bool inner = ((m & (m << 1)) & 0x10u) != 0;               // same decoding as node_hitmask
-    const uint32_t bit_index = (m ^ (inner ? (7u - oct) : 0u)) & 0x1Fu;
-    hitmask |= ((m >> 5) & 7u) << bit_index;
-  }
-  return hitmask;
-}
-
-// stats: [0] node steps, [1] triangle tests.  Hits are written to the RTCRayHit records like emu_trace does.
-template <typename NodeTest>
-static void trace_with_node_test(void* h, void* rays, uint64_t n, uint64_t* stats, const NodeTest& node_test) {
-  EmuScene* sc = static_cast<EmuScene*>(h);
-  const Node8* nodes = sc->nodes.data();
-  const TriRec* tris = sc->tris.data();
-  for (uint64_t ri = 0; ri < n; ++ri) {
-    char* rec = static_cast<char*>(rays) + ri * 96;
-    Ray r; memcpy(&r, rec, 48);
-    if (!sc->root_valid) continue;
-    const float idx = rcp_safe(r.dx), idy = rcp_safe(r.dy), idz = rcp_safe(r.dz);
-    const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
-    const uint32_t oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
-    const float tnear_c = fmaxf(r.tnear, 0.0f);
-    float tfar_c = fmaxf(r.tfar, 0.0f), tfar_tri = r.tfar;
-    bool found = false; Hit hit{};
-    uint32_t stack_x[kStackSize], stack_y[kStackSize];
-    int sp = 0;
-    uint32_t ngx = 0, ngy = 0x80000000u, tgx = 0, tgy = 0;
-    while (true) {
-      if (ngy & 0xFF000000u) {
-        const int bit = 31 - clz32(ngy);
-        ngy &= ~(1u << bit);
-        if (ngy & 0xFF000000u) { stack_x[sp] = ngx; stack_y[sp] = ngy; ++sp; }
-        const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
-        const uint32_t ni = ngx + (uint32_t)popc32(ngy & 0xFFu & ((1u << slot) - 1u));
-        const Node8& nd = nodes[ni];
-        stats[0]++;
-        const uint32_t hm = node_test(nd, r, idx, idy, idz, negx, negy, negz, tnear_c, tfar_c, oct);
-        ngx = nd.w[4]; ngy = (hm & 0xFF000000u) | (nd.w[3] >> 24);
-        tgx = nd.w[5]; tgy = hm & 0x00FFFFFFu;
-      } else { tgx = ngx; tgy = ngy; ngx = 0; ngy = 0; }
-      while (tgy) {
-        const int tb = 31 - clz32(tgy);
-        tgy &= ~(1u << tb);
-        const uint32_t* t = reinterpret_cast<const uint32_t*>(&tris[tgx + (uint32_t)tb]);
-        stats[1]++;
-        TriHit th;
-        if (tri_test(r, tfar_tri, u2f(t[0]), u2f(t[1]), u2f(t[2]), u2f(t[4]), u2f(t[5]), u2f(t[6]), u2f(t[8]), u2f(t[9]), u2f(t[10]), th) &&
-            (t[11] & r.mask) != 0) {
-          const float rcpAbsDen = 1.0f / th.absDen;
-          hit.t = th.T * rcpAbsDen; hit.u = th.U * rcpAbsDen; hit.v = th.V * rcpAbsDen;
-          hit.ngx = th.ngx; hit.ngy = th.ngy; hit.ngz = th.ngz; hit.primID = t[3]; hit.geomID = t[7];
-          tfar_tri = hit.t; tfar_c = fmaxf(hit.t, 0.0f); found = true;
-        }
-      }
-      if ((ngy & 0xFF000000u) == 0) {
-        if (sp == 0) break;
-        --sp; ngx = stack_x[sp]; ngy = stack_y[sp];
-      }
-    }
-    if (!found) continue;
-    memcpy(rec + 32, &hit.t, 4);
-    float h4[5] = {hit.ngx, hit.ngy, hit.ngz, hit.u, hit.v};
-    memcpy(rec + 48, h4, 20);
-    uint32_t ids[4] = {hit.primID, hit.geomID, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    memcpy(rec + 68, ids, 16);
-  }
-}
-
-extern "C" void emu_trace_h16(void* h, void* rays, uint64_t n, float pad_cells, int magic, uint64_t* stats) {
-  trace_with_node_test(h, rays, n, stats, [=](const Node8& nd, const Ray& r, float idx, float idy, float idz, bool negx, bool negy, bool negz,
-                                             float tn, float tf, uint32_t oct) {
-    return node_hitmask_h16(nd, r, idx, idy, idz, negx, negy, negz, tn, tf, oct, pad_cells, magic);
-  });
-}
-
-// the packed-half node test the device would run (embree_b200/csrc/rt_core_h2.cuh, same source, _Float16 emulation)
-extern "C" void emu_trace_h2(void* h, void* rays, uint64_t n, uint64_t* stats) {
-  trace_with_node_test(h, rays, n, stats, [](const Node8& nd, const Ray& r, float idx, float idy, float idz, bool negx, bool negy, bool negz,
-                                            float tn, float tf, uint32_t oct) {
-    const uint32_t* w = nd.w;
-    const u32x4 n0{w[0], w[1], w[2], w[3]}, n1{w[4], w[5], w[6], w[7]}, n2{w[8], w[9], w[10], w[11]}, n3{w[12], w[13], w[14], w[15]}, n4{w[16], w[17], w[18], w[19]};
-    return node_hitmask_h2(n0, n1, n2, n3, n4, r.ox, r.oy, r.oz, idx, idy, idz, negx, negy, negz, tn, tf, (7u - oct) * 0x01010101u);
-  });
 }

@@ -472,6 +472,41 @@ def test_instance_api_and_errors(b200):
     lib.rtcReleaseScene(top2)
 
 
+def test_child_scene_recommit_reaches_the_instance(b200):
+    """Instances are flattened into the top-level BVH at commit; the reference traverses the child BVH live, so there
+    `rtcCommitScene(child); rtcCommitScene(top)` shows the edited child.  Same protocol, same result here."""
+    lib, dev = b200
+    v, t = scenes.triangle_sphere(10)
+    vpad = np.zeros(v.size + 4, np.float32)
+    vpad[:v.size] = v.ravel()
+    g = lib.rtcNewGeometry(dev, RTC_GEOMETRY_TYPE_TRIANGLE)
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(vpad), 0, 12, len(v))
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT3, _ptr(t), 0, 12, len(t))
+    lib.rtcSetGeometryMask(g, 0xFFFFFFFF)
+    lib.rtcCommitGeometry(g)
+    child = lib.rtcNewScene(dev)
+    lib.rtcAttachGeometry(child, g)
+    lib.rtcCommitScene(child)
+    top = lib.rtcNewScene(dev)
+    col = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 10], np.float32)
+    lib.add_instance(dev, top, child, col)
+    lib.rtcCommitScene(top)
+    lib.check(dev)
+    r = make_rayhits([[0, 0, 0]], [[0, 0, 1]])
+    assert abs(lib.intersect(top, r.copy(), "1")["tfar"][0] - 9.0) < 1e-5
+    vpad[:v.size] *= 2.0                                        # the child sphere grows to radius 2
+    lib.rtcUpdateGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0)
+    lib.rtcCommitGeometry(g)
+    lib.rtcCommitScene(child)
+    lib.rtcCommitScene(top)                                     # the instance geometry itself was not touched
+    lib.check(dev)
+    out = lib.intersect(top, r.copy(), "1")
+    assert abs(out["tfar"][0] - 8.0) < 1e-5 and out["instID"][0] == 0, out
+    lib.rtcReleaseGeometry(g)
+    lib.rtcReleaseScene(child)
+    lib.rtcReleaseScene(top)
+
+
 def test_update_and_recommit(b200):
     """UpdateTest (verify.cpp:1835) / dynamic_scene: move the vertices, rtcUpdateGeometryBuffer, re-commit."""
     lib, dev = b200

@@ -51,6 +51,26 @@ def test_gather_records(b200):
     lib.rtcReleaseScene(sc)
 
 
+def test_gather_empty_scene_writes_miss_records(b200):
+    """A rank whose scene is empty (or holds only invalid triangles) must still deliver its slice of the gather buffer:
+    one miss record {ray.tfar, 0, 0, 0, 0, 0, -1, -1} per ray, as the header promises."""
+    import torch
+    lib, dev = b200
+    sc = lib.rtcNewScene(dev)
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    rays = scenes.incoherent_rays_reference(100000, device=torch.device("cuda", 0))
+    rays[::3, 8] = 2.5
+    out = torch.full((rays.shape[0], 8), 7.0, device=rays.device)
+    a = lib.args()
+    st = torch.cuda.current_stream().cuda_stream
+    lib.rtcb200Intersect1MGatherDevice(sc, C.c_void_p(rays.data_ptr()), rays.shape[0], C.byref(a), C.c_void_p(st), C.c_void_p(out.data_ptr()))
+    torch.cuda.synchronize()
+    lib.check(dev)
+    assert torch.equal(out[:, 0], rays[:, 8]) and (out[:, 1:6] == 0).all() and (out.view(torch.int32)[:, 6:8] == -1).all()
+    lib.rtcReleaseScene(sc)
+
+
 @pytest.mark.skipif(not __import__("os").environ.get("RTCB200_TEST_SPREAD"), reason="experimental kernel variant: set RTCB200_TEST_SPREAD=1")
 def test_tri_spread_matches_default(b200):
     """The opt-in warp-wide triangle redistribution (trace.cu SPREAD, "tri_spread" 1) must report the same hits as the
