@@ -91,6 +91,32 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def usable_cores():
+    """Host threads this process can really run: scheduler affinity intersected with the cgroup CPU quota (a box may
+    report 128 logical CPUs while the container is limited to a fraction of them).  Returns (usable, detail)."""
+    logical = os.cpu_count() or 1
+    try:
+        affinity = len(os.sched_getaffinity(0))
+    except Exception:   # noqa: BLE001
+        affinity = logical
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read().split()[0])
+            break
+        except Exception:   # noqa: BLE001
+            continue
+    usable = affinity if quota is None else max(1, min(affinity, int(quota + 0.999)))
+    return usable, {"os_cpu_count": logical, "sched_affinity": affinity, "cgroup_quota_cpus": quota}
+
+
 def make_scene(phi):
     t0 = time.time()
     v, t = scenes.triangle_sphere(phi)
@@ -116,7 +142,7 @@ def run_reference(args):
     if rank != 0:
         return
     from tests.parity import api_trace_mt, load_oracle, load_reference
-    cores = os.cpu_count()
+    cores, core_detail = usable_cores()
     v, t = make_scene(args.phi)
     R = load_reference()
     kind = "reference" if R is not None else "port"
@@ -152,7 +178,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, len(t)),
-            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": kind,
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "cores_detail": core_detail, "kind": kind,
                              "sample": f"{nsample} rays = every {stride}th ray of the {args.rays}-ray stream per step, rtcIntersect1 on {cores} host threads (FTZ|DAZ)"},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -438,7 +464,7 @@ def main():
         B.copy_(A)
         trace_dev(B, n)
         torch.cuda.synchronize()
-        cores = os.cpu_count()
+        cores, core_detail = usable_cores()
         nsample = min(n, 1 << 24)
         stride = max(1, n // nsample)
         sample_in = scenes.as_numpy_rayhits(A[::stride][:nsample].cpu())
@@ -462,7 +488,7 @@ def main():
             osc.trace(w, nthreads=cores)
             best = time.perf_counter() - t0
             kind, want, rbt = "port", w, None
-        cpu_baseline = {"value": nsample / best * 1e-6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+        cpu_baseline = {"value": nsample / best * 1e-6, "unit": "Mrays/s", "cores": cores, "cores_detail": core_detail, "kind": kind,
                         "sample": f"{nsample} rays = every {stride}th ray of the stream, rtcIntersect1 loop on {cores} host threads (FTZ|DAZ), best of 2",
                         "commit_ms": None if rbt is None else rbt * 1e3}
         both = (want["geomID"] != 0xFFFFFFFF) | (got["geomID"] != 0xFFFFFFFF)

@@ -448,94 +448,22 @@ void trace_device(SceneImpl* s, void* d_rays, const int* d_valid, int K, size_t 
 }
 
 // ---- multi-GPU hit gather into another GPU's memory ------------------------------------------------------------------
-// Two ways to get the compact 32-byte hit records into the gather buffer (rtcb200Intersect1MGatherDevice):
-//   direct  (default) the trace kernel stores each record to `compact_out` as its ray terminates -- local memory or a
-//           peer's memory over NVLink; the transfer is spread over the whole launch.
-//   staged  (rtcb200SetTuning "gather_mode" 1) the ray stream is traced in `gather_chunks` launches that alternate
-//           between the caller's stream and an auxiliary one (the next launch fills the SMs the previous launch's tail
-//           vacates); each launch writes its records to a local staging buffer and a copy-engine peer copy pushes the
-//           finished chunk over NVLink in full-size packets while the following chunks are traced.
-// Measured with the direct mode (profiles/r1_bench_n{2,4,8}*.json): 99 % / 98 % of linear at 2 / 4 GPUs, and 86 ms instead
-// of 50 ms at 8 GPUs, where seven peers deliver 15 GB per step into rank 0 (~175 GB/s ingested).  The staged mode has not
-// been validated on a multi-GPU box yet.
-static int g_gather_mode = 0, g_gather_chunks = 8;
-
-struct GatherPipe {
-  static constexpr int kMaxChunks = 64;
-  int gpu = -1;
-  cudaStream_t aux = nullptr, copy = nullptr;
-  cudaEvent_t evStart = nullptr, evAux = nullptr, evCopy = nullptr, evK[kMaxChunks] = {};
-  char* stage = nullptr;
-  size_t cap = 0;
-  ~GatherPipe() { reset(); }
-  void reset() {
-    if (stage) cudaFree(stage);
-    if (aux) cudaStreamDestroy(aux);
-    if (copy) cudaStreamDestroy(copy);
-    for (cudaEvent_t e : {evStart, evAux, evCopy}) if (e) cudaEventDestroy(e);
-    for (int i = 0; i < kMaxChunks; ++i) if (evK[i]) { cudaEventDestroy(evK[i]); evK[i] = nullptr; }
-    stage = nullptr; aux = copy = nullptr; evStart = evAux = evCopy = nullptr; cap = 0; gpu = -1;
-  }
-  void ensure(int g, size_t bytes) {
-    if (gpu != g) reset();
-    cudaSetDevice(g);
-    gpu = g;
-    if (!aux) {
-      cuda_check(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking), "cudaStreamCreate");
-      cuda_check(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking), "cudaStreamCreate");
-      for (cudaEvent_t* e : {&evStart, &evAux, &evCopy}) cuda_check(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
-      for (int i = 0; i < kMaxChunks; ++i) cuda_check(cudaEventCreateWithFlags(&evK[i], cudaEventDisableTiming), "cudaEventCreate");
-    }
-    if (bytes > cap) {
-      if (stage) cudaFree(stage);
-      stage = nullptr; cap = 0;
-      cuda_check(cudaMalloc(&stage, bytes), "cudaMalloc(gather staging)");
-      cap = bytes;
-    }
-  }
-};
-static thread_local GatherPipe t_gather;
-
+// rtcb200Intersect1MGatherDevice: the trace kernel itself delivers one compact 32-byte hit record per ray into
+// `compact_out` -- local memory or a peer's memory over NVLink -- so the transfer is spread over the whole launch and no
+// separate collective moves hit data.  rtcb200SetTuning("gather_mode", m): 1 (default) stages each 32-ray block's
+// records in shared memory and stores complete blocks as 1 KB (eight full lines); 0 stores every record on its own as
+// one 256-bit sector when its ray terminates (round 1: 99 % / 98 % of linear at 2 / 4 GPUs but only ~225 GB/s into
+// rank 0 at 8 GPUs).  The copy-engine pipeline round 1 carried as an unvalidated option is gone.
 void trace_gather(SceneImpl* s, void* d_rays, size_t M, uint32_t instID, uint32_t instPrimID, cudaStream_t st, void* compact_out) {
   require_committed(s);
   if (M == 0) return;
   if (reinterpret_cast<uintptr_t>(compact_out) & 31) fail(RTC_ERROR_INVALID_ARGUMENT, "compact_out must be 32-byte aligned (one 256-bit store per record)");
   cudaSetDevice(s->dev->gpu);
-  const bool staged = g_gather_mode == 1;
   if (!s->ev0) { cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); }
-  if (!staged || !s->gpu.root_valid) {   // (an empty scene still has to write its "miss" records)
-    cudaEventRecord(s->ev0, st);
-    rtk::TraceParams p = make_params(s, d_rays, nullptr, (unsigned long long)M, instID, instPrimID);
-    p.compact_out = compact_out;
-    cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, st), "trace launch");   // empty scene: every ray stores its miss record
-    cudaEventRecord(s->ev1, st);
-    return;
-  }
-  GatherPipe& g = t_gather;
-  g.ensure(s->dev->gpu, M * 32);
-  int chunks = std::min(std::max(g_gather_chunks, 1), (int)GatherPipe::kMaxChunks);
-  while (chunks > 1 && M / chunks < (size_t(1) << 20)) --chunks;   // keep every launch big enough to fill the machine
-  const size_t per = (M + chunks - 1) / chunks;
   cudaEventRecord(s->ev0, st);
-  cuda_check(cudaEventRecord(g.evStart, st), "event record");
-  cuda_check(cudaStreamWaitEvent(g.aux, g.evStart, 0), "stream wait");
-  cuda_check(cudaStreamWaitEvent(g.copy, g.evStart, 0), "stream wait");
-  for (int c = 0; c < chunks; ++c) {
-    const size_t first = (size_t)c * per;
-    if (first >= M) break;
-    const size_t cnt = std::min(per, M - first);
-    cudaStream_t ks = (c & 1) ? g.aux : st;
-    rtk::TraceParams p = make_params(s, static_cast<char*>(d_rays) + first * 96, nullptr, (unsigned long long)cnt, instID, instPrimID);
-    p.compact_out = g.stage + first * 32;
-    cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, ks), "trace launch");
-    cuda_check(cudaEventRecord(g.evK[c], ks), "event record");
-    cuda_check(cudaStreamWaitEvent(g.copy, g.evK[c], 0), "stream wait");
-    cuda_check(cudaMemcpyAsync(static_cast<char*>(compact_out) + first * 32, g.stage + first * 32, cnt * 32, cudaMemcpyDefault, g.copy), "peer push");
-  }
-  cuda_check(cudaEventRecord(g.evAux, g.aux), "event record");
-  cuda_check(cudaEventRecord(g.evCopy, g.copy), "event record");
-  cuda_check(cudaStreamWaitEvent(st, g.evAux, 0), "stream wait");
-  cuda_check(cudaStreamWaitEvent(st, g.evCopy, 0), "stream wait");   // stream-ordered consumers see the pushed records
+  rtk::TraceParams p = make_params(s, d_rays, nullptr, (unsigned long long)M, instID, instPrimID);
+  p.compact_out = compact_out;
+  cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, st), "trace launch");   // empty scene: every ray stores its miss record
   cudaEventRecord(s->ev1, st);
 }
 
@@ -1041,8 +969,7 @@ int rtcb200SetTuning(const char* key, int value) {
   else if (!strcmp(key, "blocks_per_sm")) t.blocks_per_sm = value;
   else if (!strcmp(key, "use_tma")) t.use_tma = value;
   else if (!strcmp(key, "tri_spread")) t.tri_spread = value != 0;
-  else if (!strcmp(key, "gather_mode") && value >= 0 && value <= 1) g_gather_mode = value;
-  else if (!strcmp(key, "gather_chunks") && value >= 1 && value <= GatherPipe::kMaxChunks) g_gather_chunks = value;
+  else if (!strcmp(key, "gather_mode") && value >= 0 && value <= 1) t.gather_mode = value;
   else if (!strcmp(key, "host_chunk_log2") && value >= 10 && value <= 26) g_host_chunk_log2 = value;
   else if (!strcmp(key, "host_streams") && value >= 1 && value <= HostPipe::kStreams) g_host_streams = value;
   else return -1;

@@ -80,6 +80,7 @@ struct Tuning {
   int blocks_per_sm = 8;
   int use_tma = 1;
   int refill_min = 4;
+  int gather_mode = 1;       // fused hit gather: 0 = one 256-bit store per record, 1 = blocks staged in shared memory, 1 KB stores
   int tri_spread = 0;        // EXPERIMENTAL warp-wide triangle redistribution in the trace kernel (trace.cu SPREAD), off
   int sah_small = 4;         // SAH builder: segments of <= this many primitives are split in the middle (no binning)
 };

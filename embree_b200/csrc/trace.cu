@@ -150,7 +150,16 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 //      other (round 1 reloaded the register copy on every pop and stalled on it: 7.5 % of all issue-stall samples).
 // The phases are warp-synchronous so lanes in the same phase execute together instead of serialising through a
 // per-thread while-while loop.
-template <int K, bool OCCLUDED, bool STATS, bool ROBUST, bool GENERAL, bool SPREAD = false>
+//
+// GATHER (K == 1 closest hit only) adds the fused multi-GPU hit gather: every ray also produces one compact 32-byte
+// record {tfar, Ng, u, v, primID, geomID} in `compact_out`, which may be a PEER GPU's memory (NVLink).
+//   GATHER 1: the lane stores its record when the ray is written back -- one 256-bit store (STG.E.256), one sector.
+//   GATHER 2: records are staged per 32-ray block in shared memory (two 1 KB slots per warp) and a complete block leaves
+//             as ONE warp-wide store of 1 KB = eight full 128-byte lines.  At 8 GPUs seven peers store into rank 0; with
+//             single-sector stores rank 0 ingested only ~225 GB/s (request-rate bound), which held the 8-GPU step at 67 ms
+//             instead of 50 ms.  A block whose slot is needed before all its rays have finished is flushed partially
+//             (masked lanes) and its stragglers fall back to the direct store.
+template <int K, bool OCCLUDED, bool STATS, bool ROBUST, bool GENERAL, int GATHER = 0, bool SPREAD = false>
 __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(const TraceParams p) {
   const bool USE_TMA = p.use_prefetch != 0;
   using IO = RayIO<K, OCCLUDED>;
@@ -184,6 +193,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   bool warp_done = false;
   int tri_wait = 0;
   unsigned long long st_rays = 0, st_nodes = 0, st_tris = 0;
+  // GATHER 2: two staging slots per warp; slot_blk = index (in this warp's block sequence) of the block a slot holds,
+  // slot_have = which of its 32 record positions are filled (warp-uniform values)
+  __shared__ float4 s_rec[GATHER == 2 ? TRACE_WARPS * 2 * 32 * 2 : 1];
+  int slot_blk0 = -1, slot_blk1 = -1, ray_blk = -1;
+  unsigned slot_have0 = 0, slot_have1 = 0;
 
   auto block_first = [&](int b) -> unsigned long long { return ((unsigned long long)b * num_warps + warp_id) * 32ull; };
   auto prefetch = [&](int b) {   // lane 0 only
@@ -195,7 +209,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   if (USE_TMA && lane == 0) { prefetch(0); prefetch(1); }
 
   // hit epilogue of one terminated ray (intersector_epilog.h:285-299; occluded: bvh_intersector1.cpp:186-188)
-  auto write_back = [&]() {
+  auto write_back = [&](float* rec) {
     float cngx = 0.0f, cngy = 0.0f, cngz = 0.0f;
     uint32_t cprim = kInvalidID, cgeom = kInvalidID;
     if (found) {
@@ -238,12 +252,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         cngx = hit.ngx; cngy = hit.ngy; cngz = hit.ngz; cprim = hit.primID; cgeom = hit.geomID;
       }
     }
-    if (K == 1 && !OCCLUDED && p.compact_out) {   // fused hit gather: compact record, possibly over NVLink
-      // one 256-bit store per record (STG.256, new on sm_100): over NVLink the record travels as ONE full 32-byte
-      // sector instead of two 16-byte partial writes.  A miss (also: empty scene) writes {tfar, 0.., -1, -1}.
-      store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, tfar_tri, cngx, cngy, cngz, found ? hit_u : 0.0f,
-                found ? hit_v : 0.0f, __uint_as_float(cprim), __uint_as_float(cgeom));
+    if (GATHER) {   // a miss (also: empty scene) yields {tfar, 0.., -1, -1}
+      rec[0] = tfar_tri; rec[1] = cngx; rec[2] = cngy; rec[3] = cngz; rec[4] = found ? hit_u : 0.0f; rec[5] = found ? hit_v : 0.0f;
+      rec[6] = __uint_as_float(cprim); rec[7] = __uint_as_float(cgeom);
     }
+  };
+  // GATHER 2: write the filled positions of a staging slot to the gather buffer, lane i = record i of the block
+  auto flush_slot = [&](int slot, int b, unsigned have) {
+    __syncwarp();
+    if (have & (1u << lane)) {
+      const float4* src = &s_rec[(((threadIdx.x >> 5) * 2 + slot) * 32 + lane) * 2];
+      const float4 x = src[0], y = src[1];
+      store_256(static_cast<char*>(p.compact_out) + (size_t)(block_first(b) + lane) * 32, x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w);
+    }
+    __syncwarp();
   };
 
   // one triangle record against this lane's ray (closest hit: shrinks tfar_tri; any hit: terminates the ray)
@@ -294,7 +316,31 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     // lanes have nothing to trace (or none has)
     const unsigned idle = __ballot_sync(FULL, state != TRACING);
     if (idle && (__popc(idle) >= refill_min || idle == FULL)) {
-      if (state == DONE) { write_back(); state = EMPTY; }
+      float rec[8];
+      const bool has_rec = state == DONE;
+      if (has_rec) { write_back(rec); state = EMPTY; }
+      if (GATHER == 1) {
+        // one 256-bit store per record (STG.256, new on sm_100): over NVLink the record travels as ONE full 32-byte sector
+        if (has_rec) store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
+      }
+      if (GATHER == 2) {
+        const int slot = !has_rec ? -1 : (ray_blk == slot_blk0 ? 0 : (ray_blk == slot_blk1 ? 1 : -1));
+        if (has_rec && slot < 0)   // straggler of a block that already lost its slot
+          store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
+        if (slot >= 0) {
+          float4* dst = &s_rec[(((threadIdx.x >> 5) * 2 + slot) * 32 + (ray_index & 31u)) * 2];
+          dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+          dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+        }
+        slot_have0 |= __reduce_or_sync(FULL, slot == 0 ? 1u << (ray_index & 31u) : 0u);
+        slot_have1 |= __reduce_or_sync(FULL, slot == 1 ? 1u << (ray_index & 31u) : 0u);
+        auto full_mask = [&](int b) -> unsigned {
+          const unsigned long long first = block_first(b);
+          return (n - first) >= 32ull ? 0xFFFFFFFFu : ((1u << (unsigned)(n - first)) - 1u);
+        };
+        if (slot_blk0 >= 0 && slot_have0 == full_mask(slot_blk0)) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
+        if (slot_blk1 >= 0 && slot_have1 == full_mask(slot_blk1)) { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
+      }
       if (!warp_done) {
         if (consumed == blk_count) {       // resident block used up (or nothing loaded yet): move to the next one
           if (USE_TMA && lane == 0) prefetch(blk + 3);   // keep the stream two blocks ahead in L2
@@ -305,6 +351,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
             blk_first = (uint32_t)first;
             blk_count = (n - blk_first) < 32u ? (n - blk_first) : 32u;
             consumed = 0;
+            if (GATHER == 2) {   // the new block needs a staging slot: a free one, else the older block is flushed as far as it got
+              if (slot_blk0 >= 0 && slot_blk1 >= 0) {
+                if (slot_blk0 < slot_blk1) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
+                else { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
+              }
+              if (slot_blk0 < 0) slot_blk0 = blk; else slot_blk1 = blk;
+            }
           }
         }
         if (!warp_done) {
@@ -312,6 +365,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
           const uint32_t rank = __popc(idle & lt_mask);
           if (state == EMPTY && rank < avail) {
             ray_index = blk_first + consumed + rank;
+            ray_blk = blk;
             bool valid = true;
             if (K > 1) valid = (p.valid == nullptr) || (p.valid[ray_index] == -1);   // inactive lanes stay untouched
             if (valid) {
@@ -466,6 +520,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
       else state = DONE;
     }
   }
+  if (GATHER == 2) {   // every block is complete by now and has left; this only covers a slot that never filled (n == 0 tail)
+    if (slot_blk0 >= 0 && slot_have0) flush_slot(0, slot_blk0, slot_have0);
+    if (slot_blk1 >= 0 && slot_have1) flush_slot(1, slot_blk1, slot_have1);
+  }
   if (STATS) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -513,21 +571,28 @@ static int launch_k(TraceParams p, cudaStream_t st) {
   // tiny launches (single-record API calls read a mapped pinned host record) skip the bulk prefetch
   p.use_prefetch = (p.n >= 1024 && g_tuning.use_tma) ? 1 : 0;
   const int variant = (p.stat ? 4 : 0) | (p.robust ? 2 : 0) | (p.descs ? 1 : 0);
-  if (K == 1 && !OCCLUDED && variant == 0 && g_tuning.tri_spread) {   // experimental triangle redistribution, opt-in
-    trace_kernel<K, OCCLUDED, false, false, false, (K == 1 && !OCCLUDED)><<<blocks, TRACE_THREADS, 0, st>>>(p);
+  if (K == 1 && !OCCLUDED && variant == 0 && g_tuning.tri_spread && !p.compact_out) {   // experimental triangle redistribution, opt-in
+    trace_kernel<K, OCCLUDED, false, false, false, 0, (K == 1 && !OCCLUDED)><<<blocks, TRACE_THREADS, 0, st>>>(p);
     count_launch();
     return (int)cudaGetLastError();
   }
-  switch (variant) {
-#define RTK_LAUNCH(ST, RB, IN) trace_kernel<K, OCCLUDED, ST, RB, IN><<<blocks, TRACE_THREADS, 0, st>>>(p); break
-    case 0: RTK_LAUNCH(false, false, false);
-    case 1: RTK_LAUNCH(false, false, true);
-    case 2: RTK_LAUNCH(false, true, false);
-    case 3: RTK_LAUNCH(false, true, true);
-    case 4: RTK_LAUNCH(true, false, false);
-    case 5: RTK_LAUNCH(true, false, true);
-    case 6: RTK_LAUNCH(true, true, false);
-    case 7: RTK_LAUNCH(true, true, true);
+  constexpr bool CAN_GATHER = (K == 1 && !OCCLUDED);
+  const int gather = (CAN_GATHER && p.compact_out) ? (g_tuning.gather_mode == 0 ? 1 : 2) : 0;
+  switch (variant + 8 * gather) {
+#define RTK_LAUNCH(ST, RB, IN, GA) trace_kernel<K, OCCLUDED, ST, RB, IN, (CAN_GATHER ? GA : 0)><<<blocks, TRACE_THREADS, 0, st>>>(p); break
+#define RTK_LAUNCH8(GA)                                   \
+    case 8 * GA + 0: RTK_LAUNCH(false, false, false, GA); \
+    case 8 * GA + 1: RTK_LAUNCH(false, false, true, GA);  \
+    case 8 * GA + 2: RTK_LAUNCH(false, true, false, GA);  \
+    case 8 * GA + 3: RTK_LAUNCH(false, true, true, GA);   \
+    case 8 * GA + 4: RTK_LAUNCH(true, false, false, GA);  \
+    case 8 * GA + 5: RTK_LAUNCH(true, false, true, GA);   \
+    case 8 * GA + 6: RTK_LAUNCH(true, true, false, GA);   \
+    case 8 * GA + 7: RTK_LAUNCH(true, true, true, GA);
+    RTK_LAUNCH8(0)
+    RTK_LAUNCH8(1)
+    RTK_LAUNCH8(2)
+#undef RTK_LAUNCH8
 #undef RTK_LAUNCH
   }
   count_launch();

@@ -304,9 +304,9 @@ RTCB200_API void rtcb200OccludedNM(const int* valid, RTCScene scene, void* rayK,
 RTCB200_API void rtcb200Intersect1MDevice(RTCScene scene, struct RTCRayHit* d_rayhits, size_t M, struct RTCIntersectArguments* args, void* cuda_stream);
 /* as rtcb200Intersect1MDevice, and additionally writes one compact 32-byte record {tfar, Ng.xyz, u, v, primID, geomID} per
  * ray (primID = geomID = -1 on a miss) to compact_out[i] (32-byte aligned).  compact_out may be memory of ANOTHER GPU imported with
- * rtcb200PeerImport (the multi-GPU hit gather): the trace kernel stores each record as its ray terminates, straight over
- * NVLink when the buffer is a peer's.  rtcb200SetTuning("gather_mode", 1) selects the alternative pipeline: the stream
- * is traced in "gather_chunks" launches whose records are pushed by the copy engine while the next chunks are traced.
+ * rtcb200PeerImport (the multi-GPU hit gather): the trace kernel stores the records itself, straight over NVLink when
+ * the buffer is a peer's -- by default staged per 32-ray block in shared memory and stored as 1 KB (eight full lines) when
+ * the block is complete; rtcb200SetTuning("gather_mode", 0) selects one 256-bit store per record as its ray terminates.
  * Either way, work enqueued on cuda_stream after this call sees the complete buffer. */
 RTCB200_API void rtcb200Intersect1MGatherDevice(RTCScene scene, struct RTCRayHit* d_rayhits, size_t M, struct RTCIntersectArguments* args, void* cuda_stream, void* compact_out);
 RTCB200_API void rtcb200Occluded1MDevice(RTCScene scene, struct RTCRay* d_rays, size_t M, struct RTCOccludedArguments* args, void* cuda_stream);
@@ -341,8 +341,8 @@ RTCB200_API void rtcb200ResetSceneStatCounters(RTCScene scene);
 RTCB200_API unsigned long long rtcb200GetLaunchCount(void);
 /* experiment knobs (process-wide): kernels "collapse_policy", "c_node", "c_tri", "sah_small", "tri_batch_min",
  * "tri_wait_max", "refill_min", "blocks_per_sm", "use_tma"; host-pointer pipeline "host_chunk_log2", "host_streams";
- * hit gather "gather_mode" (0 kernel stores, 1 staged copy-engine pushes), "gather_chunks"; EXPERIMENTAL, not yet run on
- * a GPU: "tri_spread" (warp-wide triangle redistribution).  The defaults are the shipped, measured configuration.
+ * hit gather "gather_mode" (0 one store per record, 1 blocks staged in shared memory); EXPERIMENTAL: "tri_spread"
+ * (warp-wide triangle redistribution).  The defaults are the shipped, measured configuration.
  * Returns 0, or -1 for an unknown key or an out-of-range value. */
 RTCB200_API int rtcb200SetTuning(const char* key, int value);
 /* device time (ms) of the most recent batched Device trace launch, measured with events on its stream; -1 if none */

@@ -122,29 +122,78 @@ def api_trace_mt(lib, scene, recs, nthreads, K=1, occluded=False, coherent=False
     return recs
 
 
-def compare_hits(want, got, tol=1e-4):
+TIE_ULPS = 4
+
+
+def _share_a_vertex(meshes, ga, pa, gb, pb):
+    """Per pair of (geomID, primID): do the two triangles have a vertex POSITION in common (shared edge / vertex)?"""
+    by_id = {int(gid): (np.asarray(v, np.float32), np.asarray(t)) for (v, t, gid, _m) in meshes}
+    out = np.zeros(len(ga), bool)
+    for i in range(len(ga)):
+        va, ta = by_id[int(ga[i])]
+        vb, tb = by_id[int(gb[i])]
+        if ta.shape[1] != 3 or tb.shape[1] != 3:
+            out[i] = True          # quads: the two halves of one quad share the diagonal by construction
+            continue
+        A, B = va[ta[int(pa[i])]], vb[tb[int(pb[i])]]
+        out[i] = bool((A[:, None, :] == B[None, :, :]).all(axis=2).any())
+    return out
+
+
+def compare_hits(want, got, tol=1e-4, meshes=None):
     """Hit-record parity as BASELINE.json states it: primID/geomID/instID exact, tfar/u/v within `tol` relative
-    (u, v relative to 1 since they live in [0,1]).  Returns counts; `tie` = id mismatches where both libraries
-    report the same distance (|dt| <= tol*t): equal-distance hits on a shared edge/vertex, whose winner depends on
-    traversal order in the reference itself (SURVEY 7 hard part 2)."""
+    (u, v relative to 1 since they live in [0,1]).  Returns counts.  `tie` = id mismatches where both libraries report
+    the SAME distance -- tfar within TIE_ULPS ulp (the reference's rcp+Newton vs IEEE division is 1 ulp) -- and, when
+    `meshes` = [(verts, tris, geomID, mask), ...] is given, the two primitives share a vertex position: the ray hits
+    exactly on a shared edge / vertex, both triangles accept it at the same t, and the reference's own winner depends on
+    its traversal order (SURVEY 7 hard part 2).  Every other id difference is `id_mismatch`."""
     n = len(want)
     wh = want["geomID"] != 0xFFFFFFFF
     gh = got["geomID"] != 0xFFFFFFFF
     both = wh & gh
-    id_mis = (want["primID"] != got["primID"]) | (want["geomID"] != got["geomID"]) | (want["instID"] != got["instID"])
+    id_mis = both & ((want["primID"] != got["primID"]) | (want["geomID"] != got["geomID"]) | (want["instID"] != got["instID"]))
     wt, gt = want["tfar"].astype(np.float64), got["tfar"].astype(np.float64)
     with np.errstate(invalid="ignore", divide="ignore"):
         rel_t = np.where(both, np.abs(wt - gt) / np.maximum(np.abs(wt), 1e-30), 0.0)
-    same_t = both & (rel_t <= tol)
+    ulps = np.abs(want["tfar"].view(np.int32).astype(np.int64) - got["tfar"].view(np.int32).astype(np.int64))
+    same_t = both & (ulps <= TIE_ULPS) & (want["tfar"] > 0) & (got["tfar"] > 0)
     tie = id_mis & same_t
-    hard = id_mis & ~same_t
+    shared_checked = meshes is not None
+    if shared_checked and tie.any():
+        k = np.nonzero(tie)[0]
+        tie[k] = _share_a_vertex(meshes, want["geomID"][k], want["primID"][k], got["geomID"][k], got["primID"][k])
+    hard = id_mis & ~tie
     ok = both & ~id_mis
     du = np.abs(want["u"].astype(np.float64) - got["u"])[ok]
     dv = np.abs(want["v"].astype(np.float64) - got["v"])[ok]
     ng_exact = all(((want[f].view(np.uint32) == got[f].view(np.uint32)) | ~ok).all() for f in ("Ng_x", "Ng_y", "Ng_z"))
     miss_tfar_same = ((want["tfar"].view(np.uint32) == got["tfar"].view(np.uint32)) | wh | gh).all()
     return dict(n=int(n), hits=int(wh.sum()), id_mismatch=int(hard.sum()), tie=int(tie.sum()),
+                tie_rule=f"tfar within {TIE_ULPS} ulp" + (" and a shared vertex" if shared_checked else ""),
                 hit_miss_disagree=int((wh != gh).sum()),
                 max_rel_t=float(rel_t[ok].max()) if ok.any() else 0.0,
                 max_abs_uv=float(max(du.max() if du.size else 0.0, dv.max() if dv.size else 0.0)),
                 ng_bit_exact=bool(ng_exact), miss_untouched=bool(miss_tfar_same))
+
+
+def explain_hit_miss(oracle, rays, want, got, single_prim_scene):
+    """Every ray on which `got` (the GPU) and `want` (the oracle / the reference) disagree about hit vs miss must be an
+    edge case of the REFERENCE algorithm, shown ray by ray -- none is waved through:
+      * want hits, got misses: never acceptable (returned in `lost`);
+      * got hits, want misses: `single_prim_scene(geomID, primID, instID)` builds an oracle scene that holds ONLY the
+        primitive the GPU reports; the reference's own triangle arithmetic must accept it there with bit-equal t, u, v.
+        Then the full-scene miss is the reference's non-conservative fast box test culling that leaf by a rounding error
+        (node_intersector1.h:484-531 carries no padding; ours is padded by 2 ulp), not a wrong GPU hit.
+    Returns (lost, unexplained_extra)."""
+    wh = want["geomID"] != 0xFFFFFFFF
+    gh = got["geomID"] != 0xFFFFFFFF
+    lost = int((wh & ~gh).sum())
+    bad = 0
+    for i in np.nonzero(gh & ~wh)[0]:
+        sc = single_prim_scene(int(got["geomID"][i]), int(got["primID"][i]), int(got["instID"][i]))
+        r = rays[i:i + 1].copy()
+        sc.trace(r)
+        same = all(r[f].view(np.uint32)[0] == got[f].view(np.uint32)[i] for f in ("tfar", "u", "v"))
+        bad += 0 if (r["geomID"][0] != 0xFFFFFFFF and same) else 1
+        sc.free()
+    return lost, bad

@@ -16,7 +16,7 @@ from embree_b200.rtc import (RTCBounds, RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY
                              RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR, RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR, aligned_empty,
                              make_rayhits, rays_of, to_packets, from_packets, _ptr)
 from tests.conftest import GOLDEN, GOLDEN_QUADS, load_golden, load_golden_instances
-from tests.parity import compare_hits, load_reference
+from tests.parity import compare_hits, explain_hit_miss, load_reference
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -319,9 +319,13 @@ def test_quads_large_vs_oracle(b200, oracle):
     got = lib.intersect(sc, rays.copy(), "1M")
     osc = oracle.scene([(v, q, 0, 0xFFFFFFFF)])
     want = osc.trace(rays.copy(), nthreads=16)
-    rep = compare_hits(want, got, TOL)
-    assert rep["hits"] > 100000 and rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] <= 3 and rep["tie"] <= 30, rep
+    rep = compare_hits(want, got, TOL, meshes=[(v, q, 0, 0xFFFFFFFF)])
+    assert rep["hits"] > 100000 and rep["id_mismatch"] == 0, rep       # ties: same t (4 ulp) on a shared edge / vertex only
     assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= TOL, rep
+    # hit/miss disagreements are explained ray by ray: the GPU never loses a hit, and each extra GPU hit is accepted by
+    # the reference arithmetic on that quad alone (the reference's unpadded box test culled it in the full scene)
+    lost, unexplained = explain_hit_miss(oracle, rays, want, got, lambda g_, p_, i_: oracle.scene([(v, q[p_:p_ + 1], 0, 0xFFFFFFFF)]))
+    assert lost == 0 and unexplained == 0, (rep, lost, unexplained)
     assert got["primID"][got["geomID"] == 0].max() < len(q)
     # the same quad mesh seen through two instances
     top = lib.rtcNewScene(dev)
@@ -334,7 +338,13 @@ def test_quads_large_vs_oracle(b200, oracle):
     otop = oracle.scene([], instances=[(osc, m, i, 0xFFFFFFFF) for i, m in enumerate(xf)])
     want2 = otop.trace(rays[:50000].copy(), nthreads=16)
     rep2 = compare_hits(want2, got2, TOL)
-    assert rep2["id_mismatch"] == 0 and rep2["hit_miss_disagree"] <= 2 and rep2["tie"] <= 10, rep2
+    assert rep2["id_mismatch"] == 0, rep2
+
+    def one_quad_instanced(g_, p_, i_):
+        c = oracle.scene([(v, q[p_:p_ + 1], 0, 0xFFFFFFFF)])
+        return oracle.scene([], instances=[(c, xf[i_], i_, 0xFFFFFFFF)])
+    lost2, unexplained2 = explain_hit_miss(oracle, rays[:50000], want2, got2, one_quad_instanced)
+    assert lost2 == 0 and unexplained2 == 0, (rep2, lost2, unexplained2)
     assert (got2["instID"][got2["geomID"] != 0xFFFFFFFF] <= 1).all() and (got2["instID"] == 1).sum() > 1000
     otop.free()
     osc.free()
@@ -401,7 +411,13 @@ def test_instances_many_vs_oracle(b200, oracle):
     want = ot.trace(rays.copy(), nthreads=16)
     rep = compare_hits(want, got, TOL)
     assert rep["hits"] > 20000, rep
-    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] <= 2 and rep["tie"] <= 4, rep   # overlapping instances: exact ties are order-dependent
+    assert rep["id_mismatch"] == 0, rep   # overlapping instances: hits at the same t (4 ulp) are order-dependent ties
+
+    def one_tri_instanced(g_, p_, i_):
+        c = oracle.scene([(v, t[p_:p_ + 1], 0, 0xFFFFFFFF)])
+        return oracle.scene([], instances=[(c, xf[i_], i_, 0xFFFFFFFF)])
+    lost, unexplained = explain_hit_miss(oracle, rays, want, got, one_tri_instanced)
+    assert lost == 0 and unexplained == 0, (rep, lost, unexplained)
     assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= TOL and rep["ng_bit_exact"], rep
     occ = lib.occluded(top, rays_of(rays), "1M")
     assert ((occ["tfar"] == -np.inf) != (got["geomID"] != 0xFFFFFFFF)).sum() == 0

@@ -12,24 +12,22 @@ pytestmark = pytest.mark.gpu
 
 def test_gather_records(b200):
     """rtcb200Intersect1MGatherDevice: the compact 32-byte record per ray {tfar, Ng, u, v, primID, geomID} equals the
-    RTCRayHit result when the kernel stores the records itself (the default), with work enqueued on the caller's stream
-    after the call seeing the complete buffer.  RTCB200_TEST_STAGED=1 also forces the opt-in chunked
-    trace + copy-engine push pipeline ("gather_mode" 1), which has not been validated on a GPU yet."""
-    import os
+    RTCRayHit result in both delivery modes ("gather_mode" 1: blocks staged in shared memory and stored as 1 KB, the
+    default; 0: one 256-bit store per record), with work enqueued on the caller's stream after the call seeing the complete
+    buffer; a ray count that is not a multiple of 32 exercises the partial tail block."""
     import torch
     from embree_b200 import sharding
     lib, dev = b200
     v, t = scenes.triangle_sphere(60)
     sc, keep = build_scene(lib, dev, [(v, t, 0, 0xFFFFFFFF)])
-    rays = scenes.incoherent_rays_reference(3 << 20, device=torch.device("cuda", 0))
+    rays = scenes.incoherent_rays_reference((3 << 20) + 13, device=torch.device("cuda", 0))
     rays[::5, 8] = 0.5                                     # some misses (tfar inside the sphere)
     a = lib.args()
     st = torch.cuda.current_stream().cuda_stream
     outs = []
     try:
-        modes = ((0, 8), (1, 3), (1, 8)) if os.environ.get("RTCB200_TEST_STAGED") else ((0, 8), (0, 8))
-        for mode, chunks in modes:
-            assert lib.rtcb200SetTuning(b"gather_mode", mode) == 0 and lib.rtcb200SetTuning(b"gather_chunks", chunks) == 0
+        for mode in (1, 0, 1):
+            assert lib.rtcb200SetTuning(b"gather_mode", mode) == 0
             B = rays.clone()
             out = torch.full((B.shape[0], 8), 7.0, device=B.device)
             lib.rtcb200Intersect1MGatherDevice(sc, C.c_void_p(B.data_ptr()), B.shape[0], C.byref(a), C.c_void_p(st), C.c_void_p(out.data_ptr()))
@@ -42,12 +40,11 @@ def test_gather_records(b200):
             want.view(torch.int32)[miss, 6] = -1
             want.view(torch.int32)[miss, 7] = -1
             assert miss.any() and (~miss).any()
-            assert torch.equal(got.view(torch.int32), want.view(torch.int32)), (mode, chunks)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32)), mode
             outs.append(got)
         assert all(torch.equal(outs[0].view(torch.int32), o.view(torch.int32)) for o in outs[1:])   # and deterministic
     finally:
-        lib.rtcb200SetTuning(b"gather_mode", 0)
-        lib.rtcb200SetTuning(b"gather_chunks", 8)
+        lib.rtcb200SetTuning(b"gather_mode", 1)
     lib.rtcReleaseScene(sc)
 
 
