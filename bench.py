@@ -192,6 +192,382 @@ def workload_config(args, ntris):
             "parallelism": f"ray-stream sharding x{args.gpus}, BVH replicated, compact hit records stored to rank 0 over NVLink by the trace kernel"}
 
 
+def reference_counters(phi, sample, cores):
+    """Traversal counters of the UNMODIFIED reference (EMBREE_STAT_COUNTERS build, kernels/common/stat.h:82-86) on a
+    sample of the headline stream, next to ours: the roofline's algorithmic bytes use OUR visit counts, so a looser
+    traversal would inflate `achieved`; this shows how many nodes the reference's ordered BVH8 traversal visits on the
+    same rays.  Runs oracle/ref_stat.py in a subprocess (the counters print from a static destructor at exit)."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libembree4_stat.so.4")
+    if not os.path.exists(so):
+        return None
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_stat
+    with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+        np.save(f.name, np.ascontiguousarray(sample).view(np.uint8))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_stat.py"), str(phi), f.name, str(cores)],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    d = ref_stat.parse(r.stdout)
+    if not d.get("rays"):
+        log("reference counters unavailable: " + r.stderr[-300:])
+        return None
+    return {"rays": int(d["rays"]), "nodes_per_ray": d["nodes"] / d["rays"], "leaves_per_ray": d["leaves"] / d["rays"],
+            "triangle4_blocks_per_ray": d["blocks"] / d["rays"],
+            "note": "reference BVH8<Triangle4> (256-B nodes, 4-triangle blocks), ordered traversal with pop-time distance culling"}
+
+
+def coherent_leg(lib, dev, devt, stream, workload, phi, rays, args):
+    """One coherent configuration, measured like the headline: device-resident value (CUDA events, 3 warm-up + 5 timed
+    passes over a packet stream larger than L2), e2e through the host-pointer entry point rtcb200IntersectNM with pinned
+    buffers, the reference's rtcIntersect16 with RTC_RAY_QUERY_FLAG_COHERENT on the usable host cores, parity of the FULL
+    frame, and the algorithmic roofline of the launch.  `rays`: [n,24] RTCRayHit records on the device in packet order."""
+    import embree_b200  # noqa: F401
+    from embree_b200.rtc import from_packets, packet_dtype
+    v1, t1 = scenes.triangle_sphere(phi)
+    sc1, keep1, _ = commit(lib, dev, v1, t1)
+    n = rays.shape[0]
+    npk = n // 16
+    pk0 = rays.view(npk, 16, 24).permute(0, 2, 1)[:, :21, :].contiguous()   # AoS -> RTCRayHit16 SoA (21 fields x 16 lanes)
+    pk = pk0.clone()
+    ac = lib.args(coherent=True)
+
+    def go():
+        lib.rtcb200IntersectNMDevice(None, sc1, C.c_void_p(pk.data_ptr()), 16, npk, C.byref(ac), C.c_void_p(stream))
+    lib.rtcb200SetSceneStatCounters(sc1, 1)
+    lib.rtcb200ResetSceneStatCounters(sc1)
+    go()
+    torch.cuda.synchronize()
+    s2 = lib.scene_stats(sc1)
+    lib.rtcb200SetSceneStatCounters(sc1, 0)
+    npr, tpr = s2.trav_nodes / s2.trav_rays, s2.trav_tris / s2.trav_rays
+    times = []
+    for it in range(8):
+        pk.copy_(pk0)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        go()
+        c1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            times.append(c0.elapsed_time(c1))
+    ms = float(np.mean(times))
+    lib.check(dev)
+    bytes_per_ray = 40 + 40 + npr * 96 + tpr * 48        # 10 ray fields read, tfar + 9 hit fields written, per lane
+    peaks, peak_src = measured_peaks()
+    out = {"workload": workload, "rays": n, "value": n / ms * 1e-3, "unit": "Mrays/s", "ms_per_step": ms, "steps": len(times), "warmup": 3,
+           "hits": int((pk.view(torch.int32)[:, 18, :] != -1).sum().item()),
+           "roofline": {"bound": "hbm", "achieved": bytes_per_ray * n / (ms * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": bytes_per_ray * n / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"], "algorithmic_bytes_per_ray": bytes_per_ray,
+                        "nodes_per_ray": npr, "tris_per_ray": tpr, "traffic": None, "peak_source": peak_src,
+                        "kernel": "rtk::trace_kernel<K=16,OCCLUDED=false,...>", "packet_stream_bytes": n * 84}}
+    if not args.no_e2e:
+        H = torch.empty(pk0.shape, dtype=torch.float32).pin_memory()
+        times = []
+        for it in range(4):
+            H.copy_(pk0)
+            t0 = time.perf_counter()
+            lib.rtcb200IntersectNM(None, sc1, C.c_void_p(H.data_ptr()), 16, npk, C.byref(ac))
+            dt = time.perf_counter() - t0
+            if it > 0:
+                times.append(dt)
+        lib.check(dev)
+        out["e2e"] = {"value": n / float(np.mean(times)) * 1e-6, "unit": "Mrays/s", "h2d_bytes_per_step": n * 84, "d2h_bytes_per_step": n * 84,
+                      "api": "rtcb200IntersectNM(NULL, scene, RTCRayHit16* host, 16, M, args), pinned host buffers"}
+        assert torch.equal(H.view(torch.int32)[:, 17:19, :], pk.cpu().view(torch.int32)[:, 17:19, :])   # host path == device path
+        del H
+    if not args.no_cpu:
+        from tests.parity import api_trace_mt, compare_hits, load_reference
+        R = load_reference()
+        if R is not None:
+            cores, detail = usable_cores()
+            rdev = R.new_device(None)
+            rsc, rkeep, _ = commit(R, rdev, v1, t1)
+            src = pk0.cpu().numpy().reshape(-1).view(packet_dtype(16))
+            best, w = 1e30, None
+            for _ in range(2):
+                w = src.copy()
+                t0 = time.perf_counter()
+                api_trace_mt(R, rsc, w, cores, K=16, coherent=True)
+                best = min(best, time.perf_counter() - t0)
+            out["cpu_baseline"] = {"value": n / best * 1e-6, "unit": "Mrays/s", "cores": cores, "cores_detail": detail, "kind": "reference",
+                                   "sample": f"all {n} rays, rtcIntersect16 + RTC_RAY_QUERY_FLAG_COHERENT on {cores} host threads (FTZ|DAZ), best of 2"}
+            got = from_packets(pk.cpu().numpy().reshape(-1).view(packet_dtype(16)), n)
+            out["parity"] = compare_hits(from_packets(w, n), got, meshes=[(v1, t1, 0, 0xFFFFFFFF)])
+            out["parity"]["checked_against"] = "reference, full frame"
+            R.rtcReleaseScene(rsc)
+            R.rtcReleaseDevice(rdev)
+    lib.rtcReleaseScene(sc1)
+    lib.check(dev)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# --workload pathtracer: BASELINE configs[4] -- 10 M-triangle scene, 8 bounces, the path stream sharded over the GPUs
+# ----------------------------------------------------------------------------------------------------------------------
+PT_BOUNCES, PT_SPP = 8, 16
+PT_LIGHT = (0.2, 0.3, -0.1, 1.0, 0.8)      # point light inside the mesh (px, py, pz, intensity), matte albedo 0.8
+
+
+def pathtracer_config(args, ntris, world):
+    return {"workload": f"configs[4]: createTriangleSphere(numPhi={args.phi}) = {ntris} triangles; wavefront form of tutorials/pathtracer "
+                        f"(pathtracer_device.cpp:1489-1603): {args.rays} paths per GPU ({PRIMARY_W}x{PRIMARY_H} pinhole, jittered samples), "
+                        f"{PT_BOUNCES} bounces, per bounce one batched rtcIntersect1 pass + one rtcOccluded1 shadow pass (matte material, one point light)",
+            "paths_per_gpu": args.rays, "bounces": PT_BOUNCES, "rays_per_step_per_gpu": args.rays * PT_BOUNCES * 2, "triangles": ntris,
+            "l2": "each pass streams 3.2-6.4 GB of ray records: larger than the 126 MB L2",
+            "parallelism": f"path-stream sharding x{world}, BVH replicated, bounce generation local to each GPU, only the last bounce's compact "
+                           "hit records are gathered to rank 0 (stored over NVLink by the trace kernel)"}
+
+
+def run_pathtracer(args):
+    import torch.distributed as dist
+    import embree_b200
+    from embree_b200 import pathstream
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    devt = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=devt)
+    lib, pts = embree_b200.load(), pathstream.load()
+    dev = lib.new_device(f"gpu={local},verbose={2 if rank == 0 else 0}")
+    v, t = make_scene(args.phi)
+    sc, keep, _ = commit(lib, dev, v, t)
+    lib.rtcReleaseScene(sc)
+    sc, keep, commit_s = commit(lib, dev, v, t)
+    st = lib.scene_stats(sc)
+    a, ao = lib.args(), lib.args()
+    stream = torch.cuda.current_stream().cuda_stream
+    n = args.rays
+    cam = scenes.camera_basis(PRIMARY_W, PRIMARY_H, EYE, LOOK)
+    cam_c = (C.c_float * 12)(*cam.tolist())
+    light_c = (C.c_float * 5)(*PT_LIGHT)
+    R = torch.empty((n, 24), dtype=torch.float32, device=devt)       # RTCRayHit[] path records, reused in place by every bounce
+    S = torch.empty((n, 12), dtype=torch.float32, device=devt)       # RTCRay[] shadow rays
+    rng = torch.empty(n, dtype=torch.int32, device=devt)
+    Lw, pend, L = (torch.empty(n, dtype=torch.float32, device=devt) for _ in range(3))
+    gbuf, my_out, flag = None, None, None
+    if world > 1:
+        handle = [None]
+        if rank == 0:
+            gbuf = lib.rtcb200PeerAlloc(dev, world * n * 32)
+            h64 = (C.c_ubyte * 64)()
+            assert lib.rtcb200PeerExport(dev, C.c_void_p(gbuf), h64) == 0
+            handle = [bytes(h64)]
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            gbuf = lib.rtcb200PeerImport(dev, (C.c_ubyte * 64).from_buffer_copy(handle[0]))
+        lib.check(dev)
+        my_out = gbuf + rank * n * 32
+        flag = torch.zeros(1, device=devt)
+    P = lambda x: C.c_void_p(x.data_ptr())   # noqa: E731
+    first_path = rank * n
+    ev = None
+
+    def step(events=None, capture=None):
+        L.zero_()
+        assert pts.pts200_primary(P(R), P(rng), P(Lw), first_path, n, cam_c, PRIMARY_W, PRIMARY_H, PT_SPP, C.c_void_p(stream)) == 0
+        for b in range(PT_BOUNCES):
+            if capture is not None:
+                capture["in"].append(R[capture["idx"]].clone())
+            if events is not None:
+                events[b][0].record()
+            if world > 1 and b == PT_BOUNCES - 1:
+                lib.rtcb200Intersect1MGatherDevice(sc, P(R), n, C.byref(a), C.c_void_p(stream), C.c_void_p(my_out))
+            else:
+                lib.rtcb200Intersect1MDevice(sc, P(R), n, C.byref(a), C.c_void_p(stream))
+            if events is not None:
+                events[b][1].record()
+            if capture is not None:
+                capture["out"].append(R[capture["idx"]].clone())
+            assert pts.pts200_bounce(P(R), P(S), P(rng), P(Lw), P(pend), n, light_c, C.c_void_p(stream)) == 0
+            if capture is not None:
+                capture["sin"].append(S[capture["idx"]].clone())
+            if events is not None:
+                events[b][2].record()
+            lib.rtcb200Occluded1MDevice(sc, P(S), n, C.byref(ao), C.c_void_p(stream))
+            if events is not None:
+                events[b][3].record()
+            if capture is not None:
+                capture["sout"].append(S[capture["idx"]].clone())
+            assert pts.pts200_shade(P(S), P(pend), P(L), n, C.c_void_p(stream)) == 0
+        if world > 1:
+            dist.all_reduce(flag)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.rtcb200GetLaunchCount()
+    evs = [[[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(PT_BOUNCES)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(args.steps):
+        step(events=evs[k])
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    launches = (lib.rtcb200GetLaunchCount() - l0) + args.steps * (1 + 2 * PT_BOUNCES)      # + primary / bounce / shade kernels
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=devt)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item())
+    rays_per_step = n * PT_BOUNCES * 2
+    value = rays_per_step * world / (ms_per_step * 1e-3) * 1e-6
+    per_bounce = []
+    for b in range(PT_BOUNCES):
+        ti = float(np.mean([evs[k][b][0].elapsed_time(evs[k][b][1]) for k in range(args.steps)]))
+        tb = float(np.mean([evs[k][b][1].elapsed_time(evs[k][b][2]) for k in range(args.steps)]))
+        to = float(np.mean([evs[k][b][2].elapsed_time(evs[k][b][3]) for k in range(args.steps)]))
+        per_bounce.append({"bounce": b, "intersect_Mrays_per_s": n / ti * 1e-3, "occluded_Mrays_per_s": n / to * 1e-3,
+                           "intersect_ms": ti, "bounce_kernel_ms": tb, "occluded_ms": to})
+    lib.check(dev)
+    sampler.join(timeout=2)
+    radiance_mean = float(L.mean().item())
+    alive_last = float((R[:, 8] >= 0).float().mean().item())
+
+    # ---- end to end: the host provides the camera, receives the radiance of every path and the final hit records
+    e2e = None
+    if not args.no_e2e:
+        Lh = torch.empty(n, dtype=torch.float32).pin_memory()
+        Hh = torch.empty((n, 24), dtype=torch.float32).pin_memory()
+        times = []
+        for it in range(3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step()
+            Lh.copy_(L, non_blocking=True)
+            Hh.copy_(R, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it > 0:
+                times.append(dt)
+        tt = torch.tensor([float(np.mean(times))], device=devt)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": rays_per_step * world / float(tt.item()) * 1e-6, "unit": "Mrays/s", "h2d_bytes_per_step": 48 * world,
+               "d2h_bytes_per_step": n * (4 + 96) * world, "ms_per_step": float(tt.item()) * 1e3,
+               "api": "pts200_primary + 8 x (rtcb200Intersect1MDevice, pts200_bounce, rtcb200Occluded1MDevice, pts200_shade); the camera goes in, "
+                      "the radiance per path and the last bounce's RTCRayHit records come back to pinned host memory"}
+
+    # ---- parity of every bounce on a strided sample + CPU baseline on the same sampled streams (rank 0, N == 1)
+    parity, cpu_baseline = None, None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from tests.parity import api_trace_mt, compare_hits, load_reference
+        ns = min(n, 1 << 19)
+        cap = {"idx": torch.arange(0, n, max(1, n // ns), device=devt)[:ns], "in": [], "out": [], "sin": [], "sout": []}
+        step(capture=cap)
+        torch.cuda.synchronize()
+        Rl = load_reference()
+        if Rl is not None:
+            cores, detail = usable_cores()
+            rdev = Rl.new_device(None)
+            rsc, rkeep, rbt = commit(Rl, rdev, v, t)
+            t_int, t_occ, reps = 0.0, 0.0, []
+            for b in range(PT_BOUNCES):
+                w = scenes.as_numpy_rayhits(cap["in"][b].cpu())
+                t0 = time.perf_counter()
+                api_trace_mt(Rl, rsc, w, cores)
+                t_int += time.perf_counter() - t0
+                rep = compare_hits(w, scenes.as_numpy_rayhits(cap["out"][b].cpu()), meshes=[(v, t, 0, 0xFFFFFFFF)])
+                from embree_b200.rtc import RAY_DTYPE, aligned_empty
+                sw = aligned_empty(len(w), RAY_DTYPE)
+                sw.view(np.float32).reshape(-1, 12)[:] = cap["sin"][b].cpu().numpy()
+                t0 = time.perf_counter()
+                api_trace_mt(Rl, rsc, sw, cores, occluded=True)
+                t_occ += time.perf_counter() - t0
+                got_s = cap["sout"][b].cpu().numpy()[:, 8]
+                rep["shadow_disagree"] = int(((sw["tfar"] < 0) != (got_s < 0)).sum())
+                rep["bounce"] = b
+                reps.append(rep)
+            parity = {"checked_against": "reference", "sample_paths": int(len(cap["idx"])), "per_bounce": reps,
+                      "id_mismatch": sum(r["id_mismatch"] for r in reps), "tie": sum(r["tie"] for r in reps),
+                      "hit_miss_disagree": sum(r["hit_miss_disagree"] for r in reps), "shadow_disagree": sum(r["shadow_disagree"] for r in reps),
+                      "max_rel_t": max(r["max_rel_t"] for r in reps), "ng_bit_exact": all(r["ng_bit_exact"] for r in reps)}
+            nr = len(cap["idx"]) * PT_BOUNCES * 2
+            cpu_baseline = {"value": nr / (t_int + t_occ) * 1e-6, "unit": "Mrays/s", "cores": cores, "cores_detail": detail, "kind": "reference",
+                            "sample": f"{len(cap['idx'])} paths (every {max(1, n // ns)}th) x {PT_BOUNCES} bounces: the GPU's own bounce / shadow streams "
+                                      f"traced with rtcIntersect1 / rtcOccluded1 on {cores} host threads (FTZ|DAZ)", "commit_ms": rbt * 1e3,
+                            "intersect_Mrays_per_s": nr / 2 / t_int * 1e-6, "occluded_Mrays_per_s": nr / 2 / t_occ * 1e-6}
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        bk = float(np.mean([pb["bounce_kernel_ms"] for pb in per_bounce]))
+        bk_bytes = n * (80 + 4 + 4 + 64 + 48 + 4 + 4 + 4)   # record read (5 x 16 B) + rng/Lw r/w + next ray (4 x 16 B) + shadow ray + pending
+        line = {"metric": "Mrays/s path-tracer stream (8 bounces, closest-hit + shadow rays), 10M-triangle scene", "value": value, "unit": "Mrays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": pathtracer_config(args, len(t), world),
+                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "per_bounce": per_bounce,
+                "radiance_mean": radiance_mean, "alive_after_last_bounce": alive_last,
+                "roofline": {"bound": "hbm", "kernel": "pts200 bounce_kernel (the workload's own kernel; the trace kernels' roofline is the headline bench's)",
+                             "achieved": bk_bytes / (bk * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": bk_bytes / (bk * 1e-3) * 1e-9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src, "kernel_ms": bk,
+                             "algorithmic_bytes_per_path": bk_bytes / n},
+                "cpu_baseline": cpu_baseline, "parity": parity,
+                "build": {"device_ms": st.build_ms, "commit_wall_ms": commit_s * 1e3, "nodes": int(st.num_nodes)}}
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_pathtracer_reference(args):
+    """Reference arm of the path-tracer workload: the unmodified reference traces the same kind of stream on the host
+    cores -- primary rays, then per bounce rtcIntersect1 + rtcOccluded1 -- with the bounce rays generated between the timed
+    calls by the torch restatement of the bounce kernel (scenes.path_bounce, untimed).  Bounded sample of paths."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from embree_b200.rtc import RAY_DTYPE, aligned_empty
+    from tests.parity import api_trace_mt, load_oracle, load_reference
+    cores, detail = usable_cores()
+    v, t = make_scene(args.phi)
+    R = load_reference()
+    kind = "reference" if R is not None else "port"
+    if R is not None:
+        dev = R.new_device(None)
+        sc, keep, bt = commit(R, dev, v, t)
+        trace = lambda recs, occ: api_trace_mt(R, sc, recs, cores, occluded=occ)   # noqa: E731
+    else:
+        osc = load_oracle().scene([(v, t, 0, 0xFFFFFFFF)])
+        trace = lambda recs, occ: osc.trace(recs, occluded=occ, nthreads=cores)   # noqa: E731
+    n = min(args.rays, 1 << 20)
+    stride = max(1, args.rays // n)
+    cam = scenes.camera_basis(PRIMARY_W, PRIMARY_H, EYE, LOOK)
+    times = []
+    for it in range(args.warmup + args.steps):
+        r, rng, Lw = scenes.path_primary(0, n * stride, cam, PRIMARY_W, PRIMARY_H, PT_SPP)
+        r, rng, Lw = r[::stride].contiguous(), rng[::stride].contiguous(), Lw[::stride].contiguous()
+        dt = 0.0
+        for b in range(PT_BOUNCES):
+            w = scenes.as_numpy_rayhits(r)
+            t0 = time.perf_counter()
+            trace(w, False)
+            dt += time.perf_counter() - t0
+            r = torch.from_numpy(w.view(np.float32).reshape(-1, 24).copy())
+            shadow, rng, Lw, _ = scenes.path_bounce(r, rng, Lw, PT_LIGHT)
+            sw = aligned_empty(n, RAY_DTYPE)
+            sw.view(np.float32).reshape(-1, 12)[:] = shadow.numpy()
+            t0 = time.perf_counter()
+            trace(sw, True)
+            dt += time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = float(np.mean(times)) * 1e3
+    val = n * PT_BOUNCES * 2 / (ms * 1e-3) * 1e-6
+    emit({"impl": "reference", "metric": "Mrays/s path-tracer stream (8 bounces, closest-hit + shadow rays), 10M-triangle scene", "value": val,
+          "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": pathtracer_config(args, len(t), args.gpus),
+          "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "cores_detail": detail, "kind": kind,
+                           "sample": f"{n} paths (every {stride}th) x {PT_BOUNCES} bounces per step, rtcIntersect1 + rtcOccluded1 on {cores} host threads; "
+                                     "bounce rays generated between the timed calls (untimed)"},
+          "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -204,7 +580,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--workload", default="diffuse", choices=["diffuse", "pathtracer"],
+                    help="diffuse = configs[2] headline (default); pathtracer = configs[4] 8-bounce path stream")
     args = ap.parse_args()
+    if args.workload == "pathtracer":
+        if "--rays" not in sys.argv:
+            args.rays = 1 << 25          # paths per GPU; a step traces 16 rays per path
+        return run_pathtracer_reference(args) if args.impl == "reference" else run_pathtracer(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -381,34 +763,21 @@ def main():
                "api": "rtcb200Intersect1M(scene, RTCRayHit* host, M, args), pinned host buffers, 3-stream chunked pipeline"}
         lib.check(dev)
         host_result = H
-    # ---- extra (not the headline): configs[1] -- 1 M-triangle sphere, 1920x1080 coherent primary rays as RTCRayHit16 packets
+    # ---- coherent leg of the metric: RTCRayHit16 packets with RTC_RAY_QUERY_FLAG_COHERENT (rank 0, N == 1)
     coherent = None
     if rank == 0 and world == 1 and not args.no_extras:
-        v1, t1 = scenes.triangle_sphere(501)
-        sc1, keep1, _ = commit(lib, dev, v1, t1)
+        coherent = {}
+        # (a) the reference's own coherent benchmark (tutorials/verify/verify.cpp:5757-5921): 1 M-triangle sphere, 4096^2 rays
+        #     from the origin, dir = (x/W, 1, y/H), 32x32 tiles of 4x4-pixel packets
+        coherent["verify_4096"] = coherent_leg(lib, dev, devt, stream, "verify CoherentRaysBenchmark: createTriangleSphere(numPhi=500) = 1 000 000 triangles, "
+                                               "4096x4096 rays dir=(x/W,1,y/H) from the origin, 32x32 tiles of 4x4-pixel RTCRayHit16 packets, COHERENT flag",
+                                               500, scenes.verify_coherent_rays(4096, 4096, 32, device=devt), args)
+        # (b) BASELINE configs[1]: 1 M-triangle mesh, 1920x1080 pinhole primary rays as 4x4-pixel packets
         pr = scenes.primary_rays(PRIMARY_W, PRIMARY_H, eye=EYE, look=LOOK, device=devt)
-        order = scenes.tile_order_16(PRIMARY_W, PRIMARY_H).to(devt)
-        pr = pr[order].contiguous()                                   # 4x4-pixel tiles -> one 16-wide packet each
-        npk = pr.shape[0] // 16
-        pk = pr.view(npk, 16, 24).permute(0, 2, 1)[:, :21, :].contiguous()   # AoS -> RTCRayHit16 SoA (21 fields x 16 lanes)
-        pk0 = pk.clone()
-        ac = lib.args(coherent=True)
-        best = 1e9
-        for it in range(6):
-            pk.copy_(pk0)
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
-            lib.rtcb200IntersectNMDevice(None, sc1, C.c_void_p(pk.data_ptr()), 16, npk, C.byref(ac), C.c_void_p(stream))
-            c1.record()
-            torch.cuda.synchronize()
-            if it > 0:
-                best = min(best, c0.elapsed_time(c1))
-        hits16 = int((pk.view(torch.int32)[:, 18, :] != -1).sum().item())
-        coherent = {"workload": "configs[1]: 1 002 000-triangle sphere, 1920x1080 primary rays, RTCRayHit16 packets of 4x4 pixels (rtcb200IntersectNMDevice, K=16)",
-                    "Mrays_per_s": npk * 16 / best * 1e-3, "ms": best, "rays": npk * 16, "hits": hits16,
-                    "note": "2 M rays finish in well under a millisecond: launch-latency bound, L2-resident"}
-        lib.rtcReleaseScene(sc1)
-        lib.check(dev)
+        pr = pr[scenes.tile_order_16(PRIMARY_W, PRIMARY_H).to(devt)].contiguous()
+        coherent["configs1_1080p"] = coherent_leg(lib, dev, devt, stream, "configs[1]: createTriangleSphere(numPhi=501) = 1 002 000 triangles, 1920x1080 pinhole "
+                                                  "primary rays, 4x4-pixel RTCRayHit16 packets, COHERENT flag", 501, pr, args)
+        del pr
 
     # ---- extras (not the headline): any-hit on the same stream, and a non-convex 10 M-triangle terrain (SURVEY 8d "S10b")
     extras = None
@@ -458,7 +827,7 @@ def main():
         lib.check(dev)
 
     # ---- parity sample + CPU baseline (rank 0, N == 1)
-    cpu_baseline, parity = None, None
+    cpu_baseline, parity, ref_counters = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu:
         from tests.parity import api_trace_mt, compare_hits, load_oracle, load_reference
         B.copy_(A)
@@ -491,10 +860,9 @@ def main():
         cpu_baseline = {"value": nsample / best * 1e-6, "unit": "Mrays/s", "cores": cores, "cores_detail": core_detail, "kind": kind,
                         "sample": f"{nsample} rays = every {stride}th ray of the stream, rtcIntersect1 loop on {cores} host threads (FTZ|DAZ), best of 2",
                         "commit_ms": None if rbt is None else rbt * 1e3}
-        both = (want["geomID"] != 0xFFFFFFFF) | (got["geomID"] != 0xFFFFFFFF)
-        parity = compare_hits(want, got)
+        parity = compare_hits(want, got, meshes=[(v, t, 0, 0xFFFFFFFF)])
         parity["checked_against"] = kind
-        del both
+        ref_counters = reference_counters(args.phi, sample_in[:: max(1, nsample >> 20)], cores)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -511,9 +879,9 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                              "traffic": traffic, "peak_source": peak_src, "kernel": "rtk::trace_kernel<K=1,OCCLUDED=false,STATS=false,ROBUST=false,GENERAL=false>",
                              "kernel_ms": kms, "algorithmic_bytes_per_ray": bytes_per_ray,
-                             "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                             "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "reference_counters": ref_counters,
                              "note": "algorithmic bytes = 100 B ray/hit I/O + nodes/ray*80 B + tris/ray*48 B (device stat counters, 1 Mi-ray sample)"},
-                "cpu_baseline": cpu_baseline, "parity": parity, "extra_coherent": coherent, "extras": extras,
+                "cpu_baseline": cpu_baseline, "parity": parity, "coherent": coherent, "extras": extras,
                 "build": {"device_ms": st.build_ms, "commit_wall_ms": commit_s * 1e3, "nodes": int(st.num_nodes), "sah": st.sah_cost,
                           "builder": "sah" if st.builder else "lbvh"}}
         emit(line)

@@ -183,6 +183,22 @@ def primary_rays(width, height, eye=(0.0, 0.0, 0.0), look=(0.0, 0.0, 1.0), up=(0
     return pack_rayhits(org, d, 0.0, float("inf"))
 
 
+def verify_coherent_rays(width, height, tile=32, device="cpu"):
+    """The reference's coherent benchmark rays (tutorials/verify/verify.cpp:5830-5897, MODE_INTERSECT16): origin 0,
+    dir = (x/W, 1, y/H) (not normalised), tnear 0, tfar inf; returned in the benchmark's packet order -- `tile` x `tile`
+    pixel tiles row-major, inside a tile 4x4-pixel packets row-major, lane = 4*dy + dx."""
+    assert width % tile == 0 and height % tile == 0 and tile % 4 == 0
+    ty, py, dy, tx, px, dx = torch.meshgrid(torch.arange(height // tile, device=device), torch.arange(tile // 4, device=device),
+                                            torch.arange(4, device=device), torch.arange(width // tile, device=device),
+                                            torch.arange(tile // 4, device=device), torch.arange(4, device=device), indexing="ij")
+    # order: tileY, tileX, packetY, packetX, dy, dx
+    perm = (0, 3, 1, 4, 2, 5)
+    y = (ty * tile + py * 4 + dy).permute(*perm).reshape(-1).to(torch.float32)
+    x = (tx * tile + px * 4 + dx).permute(*perm).reshape(-1).to(torch.float32)
+    d = torch.stack([x * (1.0 / width), torch.ones_like(x), y * (1.0 / height)], 1)
+    return pack_rayhits(torch.zeros_like(d), d, 0.0, float("inf"))
+
+
 def tile_order_16(width, height):
     """Permutation that packs 4x4-pixel tiles into consecutive groups of 16 (RTCRayHit16 packets of config 2)."""
     assert width % 4 == 0 and height % 4 == 0
@@ -250,3 +266,95 @@ def as_numpy_rayhits(t):
     out = aligned_empty(a.shape[0], RAYHIT_DTYPE)
     out.view(np.float32).reshape(-1, 24)[:] = a
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# path stream (BASELINE configs[4]): torch restatement of embree_b200/csrc/pathstream.cu -- the wavefront form of
+# tutorials/pathtracer/pathtracer_device.cpp:1489-1603.  Used by the tests as the checker of the CUDA kernels and by
+# bench.py's reference arm to generate the bounce streams on the CPU (untimed).
+# ------------------------------------------------------------------------------------------------------
+def camera_basis(width, height, eye, look, up=(0.0, 1.0, 0.0), fov=90.0):
+    """cam12 = (p, U, V, W0) with dir(fx, fy) = normalize(fx*U + fy*V + W0): the pinhole of primary_rays()."""
+    w = np.asarray(look, np.float64)
+    w /= np.linalg.norm(w)
+    u = np.cross(np.asarray(up, np.float64), w)
+    u /= np.linalg.norm(u)
+    v = np.cross(w, u)
+    fl = 0.5 * height / math.tan(0.5 * math.radians(fov))
+    w0 = fl * w - 0.5 * width * u + 0.5 * height * v
+    return np.concatenate([np.asarray(eye, np.float64), u, -v, w0]).astype(np.float32)
+
+
+def path_primary(first_path, n, cam12, width, height, spp, device="cpu"):
+    """-> (rayhits [n,24], rng int64 [n], Lw [n]): jittered primary rays, pixel = path // spp, sample = path % spp."""
+    path = torch.arange(first_path, first_path + n, device=device, dtype=torch.int64)
+    pixel, sample = path // spp, path % spp
+    x, y = pixel % width, pixel // width
+    s = _murmur_fin(_murmur_mix(_murmur_mix(torch.zeros_like(path), x | (y << 16)), sample))
+
+    def get1d():
+        nonlocal s
+        s = _u32(s * 1664525 + 1013904223)
+        return (s >> 1).to(torch.float32) * 4.656612873077392578125e-10
+    fx, fy = x.to(torch.float32) + get1d(), y.to(torch.float32) + get1d()
+    get1d()
+    c = torch.tensor(cam12, dtype=torch.float32, device=device)
+    d = fx.unsqueeze(1) * c[3:6] + fy.unsqueeze(1) * c[6:9] + c[9:12]
+    d = d / d.norm(dim=1, keepdim=True)
+    r = pack_rayhits(c[0:3].expand_as(d), d, 0.0, float("inf"))
+    return r, s, torch.ones(n, dtype=torch.float32, device=device)
+
+
+def path_bounce(r, rng, Lw, light5):
+    """One bounce on traced records `r` ([n,24], modified in place into the next rays).  Returns (shadow [n,12], rng, Lw,
+    pending [n]).  light5 = (px, py, pz, intensity, albedo)."""
+    n, dev = r.shape[0], r.device
+    ri = r.view(torch.int32)
+    alive = (r[:, 8] >= 0) & (ri[:, 18] != -1)
+    org, d, t = r[:, 0:3].clone(), r[:, 4:7].clone(), r[:, 8:9].clone()
+    P = org + t * d
+    eps = 32.0 * 1.19209e-07 * torch.maximum(P.abs().max(dim=1).values, t.squeeze(1))
+    Ng = r[:, 12:15] / r[:, 12:15].norm(dim=1, keepdim=True).clamp_min(1e-30)
+    Ng = torch.where(((d * Ng).sum(1, keepdim=True) >= 0), -Ng, Ng)
+    s = rng.clone()
+
+    def get1d():
+        nonlocal s
+        s = _u32(s * 1664525 + 1013904223)
+        return (s >> 1).to(torch.float32) * 4.656612873077392578125e-10
+    u1, u2 = get1d(), get1d()
+    phi, ct, st = 2.0 * math.pi * u1, torch.sqrt(u2), torch.sqrt(1.0 - u2)
+    zero = torch.zeros_like(Ng[:, 0])
+    dx0 = torch.stack([zero, -Ng[:, 2], Ng[:, 1]], 1)          # cross((1,0,0), N)
+    dx1 = torch.stack([Ng[:, 2], zero, -Ng[:, 0]], 1)          # cross((0,1,0), N)
+    dx = torch.where(((dx0 * dx0).sum(1) > (dx1 * dx1).sum(1)).unsqueeze(1), dx0, dx1)
+    dx = dx / dx.norm(dim=1, keepdim=True).clamp_min(1e-30)
+    dy = torch.linalg.cross(Ng, dx)
+    dy = dy / dy.norm(dim=1, keepdim=True).clamp_min(1e-30)
+    wi = (torch.cos(phi) * st).unsqueeze(1) * dx + (torch.sin(phi) * st).unsqueeze(1) * dy + ct.unsqueeze(1) * Ng
+    get1d(); get1d()
+    lp = torch.tensor(light5[0:3], dtype=torch.float32, device=dev)
+    toL = lp - P
+    dist2 = (toL * toL).sum(1)
+    dist = torch.sqrt(dist2)
+    ld = toL / dist.unsqueeze(1)
+    cosl = (ld * Ng).sum(1).clamp_min(0.0)
+    pending = torch.where(alive, Lw * (light5[3] / dist2) * (light5[4] * 0.318309886) * cosl, torch.zeros_like(Lw))
+    shadow = torch.zeros((n, 12), dtype=torch.float32, device=dev)
+    si = shadow.view(torch.int32)
+    shadow[:, 0:3], shadow[:, 3], shadow[:, 4:7], shadow[:, 8] = P, eps, ld, dist
+    si[:, 9], si[:, 10] = -1, ri[:, 10]
+    dead = ~alive
+    shadow[dead, 0:3] = 0.0
+    shadow[dead, 3] = float("inf")
+    shadow[dead, 4:7] = torch.tensor([0.0, 0.0, 1.0], device=dev)
+    shadow[dead, 8] = float("-inf")
+    Lw2 = torch.where(alive, Lw * light5[4], Lw)
+    sign = torch.where((wi * Ng).sum(1) < 0, -1.0, 1.0)
+    P2 = P + (sign * eps).unsqueeze(1) * Ng
+    d2 = wi / wi.norm(dim=1, keepdim=True).clamp_min(1e-30)
+    r[alive, 0:3], r[alive, 3], r[alive, 4:7], r[alive, 8] = P2[alive], eps[alive], d2[alive], float("inf")
+    ri[alive, 17:20] = -1
+    r[dead, 3] = float("inf")
+    r[dead, 8] = float("-inf")
+    return shadow, torch.where(alive, s, rng), Lw2, pending
