@@ -216,6 +216,52 @@ def reference_counters(phi, sample, cores):
             "note": "reference BVH8<Triangle4> (256-B nodes, 4-triangle blocks), ordered traversal with pop-time distance culling"}
 
 
+def dynamic_leg(lib, dev, args):
+    """configs[3]b: per-frame re-commit of a dynamic scene, measured as the reference's update.* benchmarks do
+    (verify.cpp:6173-6194 CreateGeometryBenchmark, update = true: rtcCommitGeometry + rtcCommitScene of an
+    RTC_SCENE_FLAG_DYNAMIC scene; Mprims/s).  Ours is wall time of the same two calls: the vertex upload over PCIe, the
+    device build (LBVH / binned SAH) or the refit, and the final synchronisation are all inside."""
+    from tests.parity import load_reference
+    out = []
+    R = load_reference() if not args.no_cpu else None
+    rdev = R.new_device(None) if R is not None else None
+    for label, phi in (("100k", 159), ("1000k", 501)):
+        v, t = scenes.triangle_sphere(phi)
+        for gq_name, scene_q, geom_q in (("LOW (Morton rebuild)", 0, 0), ("MEDIUM (binned-SAH rebuild)", 1, 1), ("REFIT", 0, 3)):
+            row = {"triangles": len(t), "mesh": f"createTriangleSphere(numPhi={phi})", "quality": gq_name}
+            for who, L, d in (("b200", lib, dev), ("reference", R, rdev)):
+                if L is None:
+                    continue
+                sc = L.rtcNewScene(d)
+                L.rtcSetSceneFlags(sc, 1)
+                L.rtcSetSceneBuildQuality(sc, scene_q)
+                gid, keep = L.add_triangle_mesh(d, sc, v, t, mask=0xFFFFFFFF, quality=geom_q)
+                L.rtcCommitScene(sc)
+                g = L.rtcGetGeometry(sc, gid)
+                ts = []
+                for it in range(8):
+                    keep[0][: v.size] *= 1.001                      # the vertices move every frame
+                    L.rtcUpdateGeometryBuffer(g, 1, 0)
+                    t0 = time.perf_counter()
+                    L.rtcCommitGeometry(g)
+                    L.rtcCommitScene(sc)
+                    dt = time.perf_counter() - t0
+                    if it >= 2:
+                        ts.append(dt)
+                L.check(d)
+                ms = float(np.mean(ts)) * 1e3
+                row[who] = {"commit_ms": ms, "Mprims_per_s": len(t) / ms * 1e-3}
+                if who == "b200":
+                    st = L.scene_stats(sc)
+                    row[who]["device_ms"] = st.build_ms
+                    row[who]["path"] = ["lbvh build", "sah build", "refit"][st.builder]
+                L.rtcReleaseScene(sc)
+            out.append(row)
+    if R is not None:
+        R.rtcReleaseDevice(rdev)
+    return out
+
+
 def coherent_leg(lib, dev, devt, stream, workload, phi, rays, args):
     """One coherent configuration, measured like the headline: device-resident value (CUDA events, 3 warm-up + 5 timed
     passes over a packet stream larger than L2), e2e through the host-pointer entry point rtcb200IntersectNM with pinned
@@ -825,6 +871,7 @@ def main():
         lib.rtcReleaseScene(sct)
         del T, Tw, cam, Rr, work
         lib.check(dev)
+        extras["dynamic_scene_recommit"] = dynamic_leg(lib, dev, args)
 
     # ---- parity sample + CPU baseline (rank 0, N == 1)
     cpu_baseline, parity, ref_counters = None, None, None

@@ -8,8 +8,11 @@
 //
 // Pipeline (all on one stream, counts stay on the device except two scalar read-backs):
 //   primref_gen -> morton_keys -> radix sort (8-bit digits, warp-match ranking) ->
-//   { lbvh_hierarchy + refit | binned SAH top-down (build_sah.cu) } -> collapse to 80-byte BVH8 nodes
-//   (level-synchronous, greedy largest-area opening) -> leaf_pack (48-byte triangle records).
+//   { lbvh_hierarchy + refit | binned SAH top-down (build_sah.cu) } -> collapse to 96-byte BVH8 nodes
+//   (ONE cooperative launch, grid-wide barrier per tree level; SAH-optimal child selection) -> leaf_pack
+//   (48-byte triangle records).  A committed scene keeps the record -> primitive map and the level ranges of its
+//   node array, so a later commit with unchanged topology can REFIT (refit_scene below) instead of rebuilding.
+#include <cooperative_groups.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -50,6 +53,8 @@ struct BuildInfo {        // device-resident scalars of one build
   uint32_t pad;
   double sah;                   // accumulated SAH cost numerator
   int api_lo[3], api_hi[3];     // bounds of the non-instanced triangles only (rtcGetSceneBounds merges instance boxes on the host)
+  uint32_t depth;               // BVH8 levels written by collapse_all
+  uint32_t level_begin[kStackSize + 1];   // node id range of level l = [level_begin[l], level_begin[l+1])
 };
 
 __device__ __forceinline__ int find_geom(const uint32_t* __restrict__ offs, int ngeoms, uint32_t p) {
@@ -61,7 +66,10 @@ __device__ __forceinline__ int find_geom(const uint32_t* __restrict__ offs, int 
   return lo;
 }
 
-__device__ __forceinline__ void load_tri_verts(const GeomDesc& g, uint32_t lp, float v[9], bool& ok, bool world) {
+// `pad` (optional, world && has_xfm only): per axis, a bound of the rounding error of the local2world FMA chain and of
+// the inverse map the trace kernel applies to the ray (to_object_space) -- 8 ulp of the summed term magnitudes, so the
+// world-space box stays conservative for the object-space triangle test even under cancellation (x*m0 ~ -p).
+__device__ __forceinline__ void load_tri_verts(const GeomDesc& g, uint32_t lp, float v[9], bool& ok, bool world, float* pad = nullptr) {
   uint32_t i0, i1, i2;
   if (g.is_quad) {   // halves (v0,v1,v3) and (v2,v1,v3); the whole quad must be valid (scene_quad_mesh.h:186-203)
     const uint32_t* ip = reinterpret_cast<const uint32_t*>(g.idx + (uint64_t)(lp >> 1) * g.istride);
@@ -92,7 +100,10 @@ __device__ __forceinline__ void load_tri_verts(const GeomDesc& g, uint32_t lp, f
     for (int k = 0; k < 9; k += 3) {
       const float x = v[k], y = v[k + 1], z = v[k + 2];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) v[k + a] = __fmaf_rn(x, g.xfm[a], __fmaf_rn(y, g.xfm[3 + a], __fmaf_rn(z, g.xfm[6 + a], g.xfm[9 + a])));
+      for (int a = 0; a < 3; ++a) {
+        v[k + a] = __fmaf_rn(x, g.xfm[a], __fmaf_rn(y, g.xfm[3 + a], __fmaf_rn(z, g.xfm[6 + a], g.xfm[9 + a])));
+        if (pad) pad[a] = fmaxf(pad[a], 9.6e-7f * (fabsf(x * g.xfm[a]) + fabsf(y * g.xfm[3 + a]) + fabsf(z * g.xfm[6 + a]) + fabsf(g.xfm[9 + a])));
+      }
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) ok &= (v[k] > -kFltLarge) & (v[k] < kFltLarge);
@@ -110,8 +121,8 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
   bool ok = false, skipb = false;
   if (p < ntot) {
     const int g = find_geom(offs, ngeoms, p);
-    float v[9];
-    load_tri_verts(geoms[g], p - offs[g], v, ok, true);
+    float v[9], pad[3] = {0.0f, 0.0f, 0.0f};
+    load_tri_verts(geoms[g], p - offs[g], v, ok, true, pad);
     skipb = geoms[g].skip_bounds != 0;
     if (ok) {
 #pragma unroll
@@ -119,9 +130,9 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
         lo[a] = fminf(fminf(v[a], v[3 + a]), v[6 + a]);
         hi[a] = fmaxf(fmaxf(v[a], v[3 + a]), v[6 + a]);
       }
-      if (geoms[g].has_xfm) {   // the triangle test runs in object space: keep the world box conservative by 2 ulp
+      if (geoms[g].has_xfm) {   // the triangle test runs in object space: widen the world box by the transform's error bound
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { lo[a] -= fabsf(lo[a]) * 2.4e-7f; hi[a] += fabsf(hi[a]) * 2.4e-7f; }
+        for (int a = 0; a < 3; ++a) { lo[a] -= pad[a]; hi[a] += pad[a]; }
       }
     }
     PrimRef pr;
@@ -170,7 +181,7 @@ __global__ void init_info(BuildInfo* info) {
     info->geom_hi[a] = info->cent_hi[a] = f2ord(-INFINITY);
     info->api_lo[a] = f2ord(INFINITY); info->api_hi[a] = f2ord(-INFINITY);
   }
-  info->num_valid = 0; info->node_tail = 1; info->tri_tail = 0; info->pad = 0; info->sah = 0.0;
+  info->num_valid = 0; info->node_tail = 1; info->tri_tail = 0; info->pad = 0; info->sah = 0.0; info->depth = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -372,14 +383,26 @@ struct DeviceAlloc {  // allocation callbacks of collapse_node() on the device: 
   __device__ __forceinline__ void sah(double x) const { atomicAdd(&info->sah, x); }
 };
 
-__global__ void __launch_bounds__(128) collapse_level(const Node2* __restrict__ n2, uint32_t* __restrict__ src,
-                                                      uint32_t begin, uint32_t end, Node8* __restrict__ n8,
-                                                      uint32_t* __restrict__ tri_src, const uint32_t* __restrict__ sortedA,
-                                                      const uint32_t* __restrict__ sortedB, BuildInfo* info, float inv_root_area, int policy,
-                                                      const uint32_t* __restrict__ dec) {
-  const uint32_t q = begin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= end) return;
-  collapse_node(n2, src, q, n8, tri_src, sortedA, sortedB, inv_root_area, policy, dec, DeviceAlloc{info});
+// All levels in ONE cooperative launch: the grid walks the queue level by level with a grid-wide barrier between
+// levels (round 1 launched one kernel per level and read the queue tail back to the host each time: 2 + depth host
+// round trips per commit).  The level boundaries are kept for refit_scene().
+__global__ void __launch_bounds__(128) collapse_all(const Node2* __restrict__ n2, uint32_t* __restrict__ src, Node8* __restrict__ n8,
+                                                    uint32_t* __restrict__ tri_src, const uint32_t* __restrict__ sortedA,
+                                                    const uint32_t* __restrict__ sortedB, BuildInfo* info, float inv_root_area, int policy,
+                                                    const uint32_t* __restrict__ dec) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  uint32_t begin = 0, end = 1, depth = 0;
+  while (begin < end && depth < (uint32_t)kStackSize) {
+    for (uint32_t q = begin + tid; q < end; q += nthreads)
+      collapse_node(n2, src, q, n8, tri_src, sortedA, sortedB, inv_root_area, policy, dec, DeviceAlloc{info});
+    grid.sync();
+    const uint32_t tail = *reinterpret_cast<volatile uint32_t*>(&info->node_tail);
+    if (tid == 0) info->level_begin[depth] = begin;
+    grid.sync();                      // everyone has read the tail before the next level bumps it
+    begin = end; end = tail; ++depth;
+  }
+  if (tid == 0) { info->level_begin[depth] = begin; info->depth = (begin < end) ? 0xFFFFFFFFu : depth; }   // too deep -> error on the host
 }
 
 // bottom-up dynamic programme for the SAH-optimal collapse (rt_core.cuh dp_node): one thread per primitive climbs
@@ -425,7 +448,7 @@ __global__ void __launch_bounds__(256) collapse_dp(const Node2* __restrict__ nod
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ offs, int ngeoms,
                                                  const uint32_t* __restrict__ tri_src, uint32_t ntris, TriRec* __restrict__ out, int robust,
-                                                 int general) {
+                                                 int general, float* __restrict__ tribox = nullptr) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntris) return;
   const uint32_t p = tri_src[t];
@@ -434,6 +457,18 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
   float v[9];
   bool ok;
   load_tri_verts(gd, p - offs[g], v, ok, false);   // instances keep OBJECT-space triangles (see trace.cu to_object_space)
+  if (tribox) {   // refit: bounds of the moved triangle (refit is limited to scenes without instances: object == world space)
+    float* tb = tribox + (size_t)t * 6;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      tb[a] = ok ? fminf(fminf(v[a], v[3 + a]), v[6 + a]) : INFINITY;        // a triangle that became invalid gets an empty box
+      tb[3 + a] = ok ? fmaxf(fmaxf(v[a], v[3 + a]), v[6 + a]) : -INFINITY;
+    }
+    if (!ok) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[k] = NAN;                                 // and a record no ray can hit
+    }
+  }
   float4 a, b, c;
   const uint32_t lp = p - offs[g];   // quads: primID = quad index, bit 31 marks the second half (uv / Ng fix-up in trace.cu)
   a.x = v[0]; a.y = v[1]; a.z = v[2]; a.w = __uint_as_float(gd.is_quad ? ((lp >> 1) | ((lp & 1u) << 31)) : lp);
@@ -487,8 +522,9 @@ void free_scene(SceneGPU& s) {
   if (s.nodes) cudaFreeAsync(s.nodes, 0);   // pool memory: goes back to the pool for the next commit
   if (s.tris) cudaFreeAsync(s.tris, 0);
   if (s.d_descs) cudaFreeAsync(s.d_descs, 0);
+  if (s.tri_src) cudaFreeAsync(s.tri_src, 0);
   if (s.d_stat) cudaFree(s.d_stat);
-  s.nodes = nullptr; s.tris = nullptr; s.d_stat = nullptr; s.d_descs = nullptr;
+  s.nodes = nullptr; s.tris = nullptr; s.d_stat = nullptr; s.d_descs = nullptr; s.tri_src = nullptr; s.levels.clear();
   s.num_nodes = s.num_tris = 0; s.root_valid = 0;
 }
 
@@ -497,6 +533,8 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   if (s.nodes) { cudaFreeAsync(s.nodes, st); s.nodes = nullptr; }
   if (s.tris) { cudaFreeAsync(s.tris, st); s.tris = nullptr; }
   if (s.d_descs) { cudaFreeAsync(s.d_descs, st); s.d_descs = nullptr; }
+  if (s.tri_src) { cudaFreeAsync(s.tri_src, st); s.tri_src = nullptr; }
+  s.levels.clear();
   s.num_nodes = s.num_tris = 0; s.root_valid = 0; s.max_depth = 0; s.sah_cost = 0; s.builder = kind;
   for (int a = 0; a < 3; ++a) { s.bounds[a] = s.api_bounds[a] = INFINITY; s.bounds[3 + a] = s.api_bounds[3 + a] = -INFINITY; }
   if (!s.d_stat) { CK(cudaMalloc(&s.d_stat, 3 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s.d_stat, 0, 24, st)); }
@@ -592,21 +630,26 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   const float ex = s.bounds[3] - s.bounds[0], ey = s.bounds[4] - s.bounds[1], ez = s.bounds[5] - s.bounds[2];
   const float ra = ex * (ey + ez) + ey * ez;
   const float inv_ra = ra > 0.0f ? 1.0f / ra : 0.0f;
-  uint32_t begin = 0, end = 1, depth = 0;
-  while (begin < end) {
-    collapse_level<<<(end - begin + 127) / 128, 128, 0, st>>>(d_n2.p, d_src.p, begin, end, n8, d_trisrc.p, vin, vout, d_info.p, inv_ra, tuning().collapse_policy,
-                                                               use_dp ? d_dec.p : nullptr);
+  {
+    static int coop_blocks = 0;       // co-resident blocks of collapse_all on this device (one grid-wide barrier per level)
+    if (!coop_blocks) {
+      int per_sm = 0, sms = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, collapse_all, 128, 0));
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device));
+      coop_blocks = std::max(1, per_sm * sms);
+    }
+    const Node2* a_n2 = d_n2.p; uint32_t* a_src = d_src.p; uint32_t* a_trisrc = d_trisrc.p; const uint32_t *a_vin = vin, *a_vout = vout;
+    BuildInfo* a_info = d_info.p; float a_inv = inv_ra; int a_pol = tuning().collapse_policy; const uint32_t* a_dec = use_dp ? d_dec.p : nullptr;
+    void* kargs[] = {&a_n2, &a_src, &n8, &a_trisrc, &a_vin, &a_vout, &a_info, &a_inv, &a_pol, &a_dec};
+    const int blocks = (int)std::min<size_t>((size_t)coop_blocks, std::max<size_t>(1, ((size_t)n + 127) / 128));
+    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(collapse_all), dim3(blocks), dim3(128), kargs, 0, st));
     count_launch();
-    uint32_t tail;
-    CK(cudaMemcpyAsync(&tail, &d_info.p->node_tail, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    begin = end; end = tail; ++depth;
-    if (depth > 4096) { snprintf(errmsg, 256, "collapse did not terminate"); return -1; }
   }
   CK(cudaMemcpyAsync(&hinfo, d_info.p, sizeof(BuildInfo), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  const uint32_t depth = hinfo.depth, end = hinfo.node_tail;
+  if (depth == 0xFFFFFFFFu || depth >= (uint32_t)kStackSize) { snprintf(errmsg, 256, "BVH too deep for the traversal stack (%u levels)", (unsigned)kStackSize); return -1; }
   if (hinfo.tri_tail != n) { snprintf(errmsg, 256, "internal: packed %u of %u triangles", hinfo.tri_tail, n); return -1; }
-  if (depth >= (uint32_t)kStackSize) { snprintf(errmsg, 256, "BVH too deep for the traversal stack (%u)", depth); return -1; }
 
   // ---- triangle records, then shrink the node array to its final size
   DevBuf<TriRec> d_tris;
@@ -625,6 +668,94 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   if (s.general) { s.d_descs = d_geoms.p; d_geoms.p = nullptr; }
   s.num_nodes = end; s.num_tris = n; s.root_valid = 1;
   s.build_ms = ms; s.sah_cost = hinfo.sah; s.max_depth = depth;
+  // kept for refit_scene(): which primitive every triangle record came from, and the level ranges of the node array
+  s.tri_src = d_trisrc.p; d_trisrc.p = nullptr;
+  s.total_prims = ntot;
+  s.levels.assign(hinfo.level_begin, hinfo.level_begin + depth + 1);
+  s.levels.back() = end;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// REFIT (RTC_BUILD_QUALITY_REFIT, kernels/bvh/bvh_refit.cpp): the vertices moved, the topology did not.  Triangle
+// records are re-packed from the new vertex data, then the BVH8 levels are revisited bottom-up: every node takes the
+// new boxes of its children (triangle bounds for leaf slots, the child's node box for internal slots), re-derives its
+// own box and re-quantises -- same slots, same child / triangle ranges, no sort, no hierarchy construction.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) refit_level(Node8* __restrict__ n8, uint32_t begin, uint32_t end, const float* __restrict__ tribox,
+                                                   float* __restrict__ nodebox) {
+  const uint32_t q = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= end) return;
+  Node8 nd = n8[q];
+  const uint32_t imask = nd.w[3] >> 24, child_base = nd.w[4], tri_base = nd.w[5];
+  ChildBox cb[8];
+  uint8_t slot_of[8];
+  bool empty[8];
+  int n = 0;
+  float plo[3] = {INFINITY, INFINITY, INFINITY}, phi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int sl = 0; sl < 8; ++sl) {
+    const uint32_t lm = node_leafmask_raw(nd.w, sl) & 0x00FFFFFFu;
+    const bool inner = (imask >> sl) & 1u;
+    if (!inner && lm == 0) continue;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (inner) {
+      const float* b = nodebox + (size_t)(child_base + __popc(imask & ((1u << sl) - 1u))) * 6;
+      for (int a = 0; a < 3; ++a) { lo[a] = b[a]; hi[a] = b[3 + a]; }
+    } else {
+      for (uint32_t m = lm; m; m &= m - 1) {
+        const float* b = tribox + (size_t)(tri_base + (uint32_t)(__ffs((int)m) - 1)) * 6;
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], b[a]); hi[a] = fmaxf(hi[a], b[3 + a]); }
+      }
+    }
+    empty[n] = !(lo[0] <= hi[0]);
+    for (int a = 0; a < 3; ++a) { cb[n].lo[a] = lo[a]; cb[n].hi[a] = hi[a]; plo[a] = fminf(plo[a], lo[a]); phi[a] = fmaxf(phi[a], hi[a]); }
+    slot_of[n] = (uint8_t)sl;
+    ++n;
+  }
+  if (!(plo[0] <= phi[0])) { for (int a = 0; a < 3; ++a) plo[a] = phi[a] = 0.0f; }
+  for (int c = 0; c < n; ++c)
+    if (empty[c]) for (int a = 0; a < 3; ++a) cb[c].lo[a] = cb[c].hi[a] = plo[a];   // nothing in it can be hit (NaN records / empty subtree)
+  float* out = nodebox + (size_t)q * 6;
+  const bool any = n > 0;
+  for (int a = 0; a < 3; ++a) { out[a] = any ? plo[a] : INFINITY; out[3 + a] = any ? phi[a] : -INFINITY; }
+  encode_node_boxes(nd, plo, phi, cb, slot_of, n);
+  n8[q] = nd;
+}
+
+int refit_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, cudaStream_t st, char* errmsg) {
+  errmsg[0] = 0;
+  if (!s.root_valid || !s.tri_src || s.levels.size() < 2) { snprintf(errmsg, 256, "refit: scene has no kept topology"); return -1; }
+  std::vector<uint32_t> offs(ngeoms + 1, 0);
+  uint64_t tot64 = 0;
+  for (int g = 0; g < ngeoms; ++g) { offs[g] = (uint32_t)tot64; tot64 += geoms[g].ntris; }
+  offs[ngeoms] = (uint32_t)tot64;
+  if (tot64 != s.total_prims) { snprintf(errmsg, 256, "refit: primitive count changed"); return -1; }
+  ensure_pool(s.device);
+  struct Events { cudaEvent_t a = nullptr, b = nullptr; ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evs;
+  CK(cudaEventCreate(&evs.a)); CK(cudaEventCreate(&evs.b));
+  CK(cudaEventRecord(evs.a, st));
+  const uint32_t n = s.num_tris;
+  DevBuf<GeomDesc> d_geoms; DevBuf<uint32_t> d_offs; DevBuf<float> d_tribox, d_nodebox;
+  CK(d_geoms.alloc(ngeoms, st)); CK(d_offs.alloc(ngeoms + 1, st)); CK(d_tribox.alloc((size_t)n * 6, st)); CK(d_nodebox.alloc((size_t)s.num_nodes * 6, st));
+  CK(cudaMemcpyAsync(d_geoms.p, geoms, sizeof(GeomDesc) * ngeoms, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_offs.p, offs.data(), 4 * (ngeoms + 1), cudaMemcpyHostToDevice, st));
+  leaf_pack<<<(n + 255) / 256, 256, 0, st>>>(d_geoms.p, d_offs.p, ngeoms, s.tri_src, n, s.tris, s.robust, s.general, d_tribox.p);
+  count_launch();
+  for (size_t l = s.levels.size() - 1; l-- > 0;) {
+    const uint32_t begin = s.levels[l], end = s.levels[l + 1];
+    if (end <= begin) continue;
+    refit_level<<<(end - begin + 127) / 128, 128, 0, st>>>(s.nodes, begin, end, d_tribox.p, d_nodebox.p);
+    count_launch();
+  }
+  float rb[6];
+  CK(cudaMemcpyAsync(rb, d_nodebox.p, sizeof rb, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(evs.b, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  for (int a = 0; a < 6; ++a) s.bounds[a] = s.api_bounds[a] = rb[a];
+  float ms = 0;
+  cudaEventElapsedTime(&ms, evs.a, evs.b);
+  s.build_ms = ms; s.builder = 2;
   return 0;
 }
 

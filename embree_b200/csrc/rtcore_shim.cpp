@@ -161,6 +161,12 @@ struct SceneImpl : RefCounted {
   // successful commit bumps `generation`, and the parent remembers the generation of each instanced scene it baked in.
   std::atomic<unsigned long long> generation{0};
   std::vector<unsigned long long> committedChildGen;
+  // topology signature of the last full build (geometry, type, primitive / vertex counts): a later commit whose enabled
+  // geometries all ask for RTC_BUILD_QUALITY_REFIT and match it refits the BVH instead of rebuilding (bvh_refit.cpp)
+  struct TopoEntry { GeometryImpl* g; size_t nprims, nverts; bool operator==(const TopoEntry& o) const { return g == o.g && nprims == o.nprims && nverts == o.nverts; } };
+  std::vector<TopoEntry> builtTopology;
+  RTCBuildQuality builtQuality = RTC_BUILD_QUALITY_MEDIUM;
+  RTCSceneFlags builtFlags = RTC_SCENE_FLAG_NONE;
   RTCSceneFlags flags = RTC_SCENE_FLAG_NONE;
   RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
   bool flagsModified = true;  // forces the first commit (scene_verify.cpp:11-22 isModified())
@@ -341,7 +347,23 @@ void commit_scene(SceneImpl* s) {
   if (const char* e = getenv("RTCB200_BUILDER")) kind = (strcmp(e, "lbvh") == 0) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
   s->gpu.robust = (s->flags & RTC_SCENE_FLAG_ROBUST) ? 1 : 0;   // scene.cpp:181-188: Triangle4v + Pluecker
   char errmsg[256];
-  const int r = rtk::build_scene(s->gpu, descs.data(), (int)descs.size(), kind, 0, errmsg);
+  // REFIT (geometry build quality, rtcore_geometry.h; kernels/bvh/bvh_refit.cpp): same meshes, same counts, moved vertices
+  std::vector<SceneImpl::TopoEntry> topo;
+  bool wantRefit = !instanced && !descs.empty();
+  for (size_t id = 0; id < geoms.size(); ++id) {
+    GeometryImpl* g = geoms[id];
+    if (!g || !g->enabled) continue;
+    topo.push_back({g, g->indices.count, g->vertices.count});
+    wantRefit = wantRefit && g->quality == RTC_BUILD_QUALITY_REFIT;
+  }
+  const bool canRefit = wantRefit && s->gpu.root_valid && s->everCommitted && topo == s->builtTopology && s->builtQuality == s->quality &&
+                        s->builtFlags == s->flags && !getenv("RTCB200_NO_REFIT");
+  int r;
+  if (canRefit) r = rtk::refit_scene(s->gpu, descs.data(), (int)descs.size(), 0, errmsg);
+  else {
+    r = rtk::build_scene(s->gpu, descs.data(), (int)descs.size(), kind, 0, errmsg);
+    s->builtTopology = topo; s->builtQuality = s->quality; s->builtFlags = s->flags;
+  }
   // vertex/index copies are only needed during the build (triangles are baked into the leaf records)
   for (void* p : s->deviceBuffers) cudaFreeAsync(p, 0);
   s->deviceBuffers.clear();
@@ -356,7 +378,7 @@ void commit_scene(SceneImpl* s) {
   if (s->dev->verbose >= 2)
     fprintf(stderr, "[b200] commit: %u tris, %u nodes (%.1f MB) + %.1f MB tris, builder=%s, %.3f ms (%.1f Mprim/s), SAH %.2f, depth %u\n",
             s->gpu.num_tris, s->gpu.num_nodes, s->gpu.num_nodes * 80e-6, s->gpu.num_tris * 48e-6,
-            s->gpu.builder ? "sah" : "lbvh", s->gpu.build_ms, s->gpu.build_ms > 0 ? s->gpu.num_tris / s->gpu.build_ms * 1e-3 : 0.0,
+            s->gpu.builder == 2 ? "refit" : s->gpu.builder ? "sah" : "lbvh", s->gpu.build_ms, s->gpu.build_ms > 0 ? s->gpu.num_tris / s->gpu.build_ms * 1e-3 : 0.0,
             s->gpu.sah_cost, s->gpu.max_depth);
   {
     std::lock_guard<std::mutex> lg(s->geomMutex);

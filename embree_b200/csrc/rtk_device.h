@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "rt_core.cuh"
 
 namespace rtk {
@@ -45,10 +47,17 @@ struct SceneGPU {
   uint32_t builder = 0, max_depth = 0;
   unsigned long long* d_stat = nullptr;  // [3] rays, nodes, tris (device)
   size_t node_capacity = 0, tri_capacity = 0;
+  // kept by build_scene for refit_scene: record -> global primitive index, number of primitives (valid or not) the
+  // scene was built from, and the node id where every BVH8 level starts (levels[l] .. levels[l+1])
+  uint32_t* tri_src = nullptr;
+  uint32_t total_prims = 0;
+  std::vector<uint32_t> levels;
 };
 
 // Build the BVH8 over `ngeoms` meshes.  Returns cudaSuccess (0) or a CUDA error code; `errmsg` (>=256 B) gets text.
 int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind, cudaStream_t stream, char* errmsg);
+// Refit the committed BVH to moved vertices (same meshes, same primitive counts, no instances); s.builder becomes 2.
+int refit_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, cudaStream_t stream, char* errmsg);
 void free_scene(SceneGPU& s);
 
 struct TraceParams {
@@ -81,7 +90,7 @@ struct Tuning {
   int use_tma = 1;
   int refill_min = 4;
   int gather_mode = 1;       // fused hit gather: 0 = one 256-bit store per record, 1 = blocks staged in shared memory, 1 KB stores
-  int tri_spread = 0;        // EXPERIMENTAL warp-wide triangle redistribution in the trace kernel (trace.cu SPREAD), off
+  int tri_spread = 1;        // warp-wide triangle redistribution in the trace kernel (trace.cu SPREAD; closest-hit triangle scenes)
   int sah_small = 4;         // SAH builder: segments of <= this many primitives are split in the middle (no binning)
 };
 Tuning& tuning();

@@ -132,6 +132,9 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 #ifndef RTK_MIN_BLOCKS
 #define RTK_MIN_BLOCKS 8   // resident CTAs per SM the register allocation is bounded for (8 x 128 threads -> 64 registers)
 #endif
+#ifndef RTK_SMEM_STACK
+#define RTK_SMEM_STACK 8   // traversal-stack entries per lane kept in shared memory (deeper ones spill to local memory)
+#endif
 #ifndef RTK_TRI2
 #define RTK_TRI2 1   // a lane with two or more pending triangles tests two per triangle step (both records fetched together)
 #endif
@@ -185,8 +188,22 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   uint32_t ray_index = 0;
   uint32_t ngx = 0, ngy = 0, tgx = 0, tgy = 0;
   uint32_t top_x = 0, top_y = 0;          // register copy of the newest stack entry (top_y == 0: none)
-  uint2 stack[kStackSize];                // older entries: one 8-byte local-memory slot each (L1-resident)
+  // older entries: the first RTK_SMEM_STACK per lane in shared memory ([entry][thread]: conflict-free 8-byte accesses),
+  // deeper ones in local memory.  Round 1 kept the whole stack in local memory: its lines compete with the streaming
+  // node / triangle data for L1, a pop that missed cost an L2 round trip (~500 cycles, 7 % of all stall samples) and
+  // every push was written through to L2 (26 GB per 64 Mi-ray launch).
+  __shared__ uint2 s_stack[RTK_SMEM_STACK > 0 ? RTK_SMEM_STACK * TRACE_THREADS : 1];
+  uint2 stack[kStackSize];
   int sp = 0;
+  auto push_entry = [&](uint32_t x, uint32_t y) {
+    if (sp < RTK_SMEM_STACK) s_stack[sp * TRACE_THREADS + threadIdx.x] = make_uint2(x, y);
+    else stack[sp - RTK_SMEM_STACK] = make_uint2(x, y);
+    ++sp;
+  };
+  auto pop_entry = [&]() -> uint2 {
+    --sp;
+    return sp < RTK_SMEM_STACK ? s_stack[sp * TRACE_THREADS + threadIdx.x] : stack[sp - RTK_SMEM_STACK];
+  };
   // warp-uniform block cursor
   int blk = -1;                           // index into this warp's block sequence
   uint32_t blk_first = 0, blk_count = 0, consumed = 0;
@@ -209,15 +226,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   if (USE_TMA && lane == 0) { prefetch(0); prefetch(1); }
 
   // hit epilogue of one terminated ray (intersector_epilog.h:285-299; occluded: bvh_intersector1.cpp:186-188)
-  auto write_back = [&](float* rec) {
+  // (a, b, c = the winning triangle's record, fetched by the caller together with the next rays)
+  auto write_back = [&](const uint4& a, const uint4& b, const uint4& c, float* rec) {
     float cngx = 0.0f, cngy = 0.0f, cngz = 0.0f;
     uint32_t cprim = kInvalidID, cgeom = kInvalidID;
     if (found) {
       if (OCCLUDED) IO::store_tfar(p, ray_index, -INFINITY);
       else {
         // Ng = cross(e2, e1) and the ids come from the winning triangle's record (same arithmetic as tri_test)
-        const uint4* tp = tris + (size_t)hit_tri * 3;
-        const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         Hit hit;
         hit.t = tfar_tri; hit.u = hit_u; hit.v = hit_v;
         hit.primID = a.w; hit.geomID = b.w;
@@ -316,31 +332,19 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     // lanes have nothing to trace (or none has)
     const unsigned idle = __ballot_sync(FULL, state != TRACING);
     if (idle && (__popc(idle) >= refill_min || idle == FULL)) {
+      // The two fetches of this phase -- the winning triangle records of the rays being written back and the ray
+      // records of the rays being taken -- are issued together, before either is consumed: one memory latency, not two.
       float rec[8];
       const bool has_rec = state == DONE;
-      if (has_rec) { write_back(rec); state = EMPTY; }
-      if (GATHER == 1) {
-        // one 256-bit store per record (STG.256, new on sm_100): over NVLink the record travels as ONE full 32-byte sector
-        if (has_rec) store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
+      uint4 wa = make_uint4(0, 0, 0, 0), wb = wa, wc = wa;
+      if (has_rec && found && !OCCLUDED) {
+        const uint4* tp = tris + (size_t)hit_tri * 3;
+        wa = __ldg(tp); wb = __ldg(tp + 1); wc = __ldg(tp + 2);
       }
-      if (GATHER == 2) {
-        const int slot = !has_rec ? -1 : (ray_blk == slot_blk0 ? 0 : (ray_blk == slot_blk1 ? 1 : -1));
-        if (has_rec && slot < 0)   // straggler of a block that already lost its slot
-          store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
-        if (slot >= 0) {
-          float4* dst = &s_rec[(((threadIdx.x >> 5) * 2 + slot) * 32 + (ray_index & 31u)) * 2];
-          dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-          dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-        }
-        slot_have0 |= __reduce_or_sync(FULL, slot == 0 ? 1u << (ray_index & 31u) : 0u);
-        slot_have1 |= __reduce_or_sync(FULL, slot == 1 ? 1u << (ray_index & 31u) : 0u);
-        auto full_mask = [&](int b) -> unsigned {
-          const unsigned long long first = block_first(b);
-          return (n - first) >= 32ull ? 0xFFFFFFFFu : ((1u << (unsigned)(n - first)) - 1u);
-        };
-        if (slot_blk0 >= 0 && slot_have0 == full_mask(slot_blk0)) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
-        if (slot_blk1 >= 0 && slot_have1 == full_mask(slot_blk1)) { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
-      }
+      bool take = false;
+      uint32_t new_index = 0;
+      int new_blk = blk;
+      Ray nr;
       if (!warp_done) {
         if (consumed == blk_count) {       // resident block used up (or nothing loaded yet): move to the next one
           if (USE_TMA && lane == 0) prefetch(blk + 3);   // keep the stream two blocks ahead in L2
@@ -351,41 +355,68 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
             blk_first = (uint32_t)first;
             blk_count = (n - blk_first) < 32u ? (n - blk_first) : 32u;
             consumed = 0;
-            if (GATHER == 2) {   // the new block needs a staging slot: a free one, else the older block is flushed as far as it got
-              if (slot_blk0 >= 0 && slot_blk1 >= 0) {
-                if (slot_blk0 < slot_blk1) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
-                else { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
-              }
-              if (slot_blk0 < 0) slot_blk0 = blk; else slot_blk1 = blk;
-            }
           }
         }
         if (!warp_done) {
           const uint32_t avail = blk_count - consumed;
           const uint32_t rank = __popc(idle & lt_mask);
-          if (state == EMPTY && rank < avail) {
-            ray_index = blk_first + consumed + rank;
-            ray_blk = blk;
+          if (state != TRACING && rank < avail) {
+            new_index = blk_first + consumed + rank;
+            new_blk = blk;
             bool valid = true;
-            if (K > 1) valid = (p.valid == nullptr) || (p.valid[ray_index] == -1);   // inactive lanes stay untouched
-            if (valid) {
-              IO::load(static_cast<const char*>(p.rays), ray_index, r);
-              if (STATS) ++st_rays;
-              found = false;
-              sp = 0; top_y = 0; tgx = 0; tgy = 0;
-              // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129); they still
-              // pass through DONE so that a gather buffer receives their miss record
-              const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
-              idx = rcp_safe_fast(r.dx); idy = rcp_safe_fast(r.dy); idz = rcp_safe_fast(r.dz);
-              oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
-              tfar_tri = r.tfar;
-              ngx = 0; ngy = go ? 0x80000000u : 0u;   // root entered as "one pending internal child, imask 0"
-              state = go ? TRACING : DONE;
-            }
+            if (K > 1) valid = (p.valid == nullptr) || (p.valid[new_index] == -1);   // inactive lanes stay untouched
+            if (valid) { IO::load(static_cast<const char*>(p.rays), new_index, nr); take = true; }
           }
           const uint32_t want = __popc(idle);
           consumed += want < avail ? want : avail;
         }
+      }
+      if (has_rec) { write_back(wa, wb, wc, rec); state = EMPTY; }
+      if (GATHER == 1) {
+        // one 256-bit store per record (STG.256, new on sm_100): over NVLink the record travels as ONE full 32-byte sector
+        if (has_rec) store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
+      }
+      if (GATHER == 2) {
+        auto full_mask = [&](int b) -> unsigned {
+          const unsigned long long first = block_first(b);
+          return (n - first) >= 32ull ? 0xFFFFFFFFu : ((1u << (unsigned)(n - first)) - 1u);
+        };
+        // a block that is being consumed owns a staging slot; when both are taken the older block is flushed as far as it got
+        if (!warp_done && blk != slot_blk0 && blk != slot_blk1) {
+          if (slot_blk0 >= 0 && slot_blk1 >= 0) {
+            if (slot_blk0 < slot_blk1) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
+            else { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
+          }
+          if (slot_blk0 < 0) slot_blk0 = blk; else slot_blk1 = blk;
+        }
+        const int slot = !has_rec ? -1 : (ray_blk == slot_blk0 ? 0 : (ray_blk == slot_blk1 ? 1 : -1));
+        if (has_rec && slot < 0)   // straggler of a block that already lost its slot
+          store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
+        if (slot >= 0) {
+          float4* dst = &s_rec[(((threadIdx.x >> 5) * 2 + slot) * 32 + (ray_index & 31u)) * 2];
+          dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+          dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+        }
+        slot_have0 |= __reduce_or_sync(FULL, slot == 0 ? 1u << (ray_index & 31u) : 0u);
+        slot_have1 |= __reduce_or_sync(FULL, slot == 1 ? 1u << (ray_index & 31u) : 0u);
+        if (slot_blk0 >= 0 && slot_have0 == full_mask(slot_blk0)) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
+        if (slot_blk1 >= 0 && slot_have1 == full_mask(slot_blk1)) { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
+      }
+      if (take) {
+        r = nr;
+        ray_index = new_index;
+        ray_blk = new_blk;
+        if (STATS) ++st_rays;
+        found = false;
+        sp = 0; top_y = 0; tgx = 0; tgy = 0;
+        // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129); they still pass
+        // through DONE so that a gather buffer receives their miss record
+        const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
+        idx = rcp_safe_fast(r.dx); idy = rcp_safe_fast(r.dy); idz = rcp_safe_fast(r.dz);
+        oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
+        tfar_tri = r.tfar;
+        ngx = 0; ngy = go ? 0x80000000u : 0u;   // root entered as "one pending internal child, imask 0"
+        state = go ? TRACING : DONE;
       }
       if (!__any_sync(FULL, state == TRACING)) {
         if (warp_done && !__any_sync(FULL, state == DONE)) break;
@@ -398,7 +429,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
       const int bit = 31 - __clz((int)ngy);
       ngy &= ~(1u << bit);
       if (ngy & 0xFF000000u) {           // push the rest of the group
-        if (top_y) { stack[sp] = make_uint2(top_x, top_y); ++sp; }
+        if (top_y) push_entry(top_x, top_y);
         top_x = ngx; top_y = ngy;
       }
       const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
@@ -420,10 +451,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     if (tri_lanes && (__popc(tri_lanes) >= tri_batch_min || node_lanes == 0 || ++tri_wait >= tri_wait_max)) {
       tri_wait = 0;
       if (SPREAD) {
-        // EXPERIMENTAL (rtcb200SetTuning "tri_spread" 1; off by default, closest-hit Moeller-Trumbore triangle scenes
-        // only): the pending triangles of ALL lanes become work items that the whole warp tests in one step, instead
-        // of each lane testing one of its own while the others idle (scripts/warp_model.py: -20 % warp instructions
-        // per ray).  Owners queue (record index, owner lane) in shared memory; worker lane w takes item w, fetches the
+        // Closest-hit Moeller-Trumbore triangle scenes (rtcb200SetTuning "tri_spread" 0 turns it off): the pending
+        // triangles of ALL lanes become work items that the whole warp tests in one step, instead of each lane testing
+        // one of its own while the others idle.  Measured on the headline stream: 12.6 triangle steps per 32 rays with
+        // 19 lanes busy instead of 27 steps with 9, +11 % Mrays/s (profiles/r2_ab_runs.txt).  Owners queue (record index, owner lane) in shared memory; worker lane w takes item w, fetches the
         // owner's ray by shuffles and tests the record; hits meet in a 64-bit atomicMin per owner keyed by (t, item) --
         // among equal t the later item wins, as in the sequential order -- and the owner reads u, v back by shuffle.
         __shared__ uint32_t s_tri[TRACE_WARPS][32];
@@ -460,6 +491,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         if (work) {
           const uint4* tp = tris + (size_t)ti * 3;
           const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+          if (STATS) ++st_tris;
           TriHit th;
           if ((c.w & o_mask) != 0 &&
               tri_test(lr, o_tfar, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
@@ -516,7 +548,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     // ---- 4. pop or finish
     if (tracing && tgy == 0 && (ngy & 0xFF000000u) == 0) {
       if (top_y) { ngx = top_x; ngy = top_y; top_y = 0; }
-      else if (sp > 0) { --sp; const uint2 e = stack[sp]; ngx = e.x; ngy = e.y; }
+      else if (sp > 0) { const uint2 e = pop_entry(); ngx = e.x; ngy = e.y; }
       else state = DONE;
     }
   }
@@ -570,25 +602,26 @@ static int launch_k(TraceParams p, cudaStream_t st) {
   const unsigned blocks = (unsigned)(need < cap ? need : cap);
   // tiny launches (single-record API calls read a mapped pinned host record) skip the bulk prefetch
   p.use_prefetch = (p.n >= 1024 && g_tuning.use_tma) ? 1 : 0;
+  // kernel variant: bit 0 GENERAL (instances / quads), bit 1 ROBUST, bit 2 STATS; closest-hit Moeller-Trumbore triangle
+  // scenes (no bit 0 / 1) run the SPREAD instantiation -- the pending triangles of all lanes are tested by the whole warp
+  constexpr bool CLOSEST = !OCCLUDED;
+  constexpr bool CAN_GATHER = (K == 1 && CLOSEST);
   const int variant = (p.stat ? 4 : 0) | (p.robust ? 2 : 0) | (p.descs ? 1 : 0);
-  if (K == 1 && !OCCLUDED && variant == 0 && g_tuning.tri_spread && !p.compact_out) {   // experimental triangle redistribution, opt-in
-    trace_kernel<K, OCCLUDED, false, false, false, 0, (K == 1 && !OCCLUDED)><<<blocks, TRACE_THREADS, 0, st>>>(p);
-    count_launch();
-    return (int)cudaGetLastError();
-  }
-  constexpr bool CAN_GATHER = (K == 1 && !OCCLUDED);
   const int gather = (CAN_GATHER && p.compact_out) ? (g_tuning.gather_mode == 0 ? 1 : 2) : 0;
-  switch (variant + 8 * gather) {
-#define RTK_LAUNCH(ST, RB, IN, GA) trace_kernel<K, OCCLUDED, ST, RB, IN, (CAN_GATHER ? GA : 0)><<<blocks, TRACE_THREADS, 0, st>>>(p); break
-#define RTK_LAUNCH8(GA)                                   \
-    case 8 * GA + 0: RTK_LAUNCH(false, false, false, GA); \
-    case 8 * GA + 1: RTK_LAUNCH(false, false, true, GA);  \
-    case 8 * GA + 2: RTK_LAUNCH(false, true, false, GA);  \
-    case 8 * GA + 3: RTK_LAUNCH(false, true, true, GA);   \
-    case 8 * GA + 4: RTK_LAUNCH(true, false, false, GA);  \
-    case 8 * GA + 5: RTK_LAUNCH(true, false, true, GA);   \
-    case 8 * GA + 6: RTK_LAUNCH(true, true, false, GA);   \
-    case 8 * GA + 7: RTK_LAUNCH(true, true, true, GA);
+  const bool spread = CLOSEST && g_tuning.tri_spread && !p.robust && !p.descs;
+  switch (variant + 8 * gather + (spread ? 32 : 0)) {
+#define RTK_LAUNCH(ST, RB, IN, GA, SP) trace_kernel<K, OCCLUDED, ST, RB, IN, (CAN_GATHER ? GA : 0), (CLOSEST && SP)><<<blocks, TRACE_THREADS, 0, st>>>(p); break
+#define RTK_LAUNCH8(GA)                                          \
+    case 8 * GA + 0: RTK_LAUNCH(false, false, false, GA, false); \
+    case 8 * GA + 1: RTK_LAUNCH(false, false, true, GA, false);  \
+    case 8 * GA + 2: RTK_LAUNCH(false, true, false, GA, false);  \
+    case 8 * GA + 3: RTK_LAUNCH(false, true, true, GA, false);   \
+    case 8 * GA + 4: RTK_LAUNCH(true, false, false, GA, false);  \
+    case 8 * GA + 5: RTK_LAUNCH(true, false, true, GA, false);   \
+    case 8 * GA + 6: RTK_LAUNCH(true, true, false, GA, false);   \
+    case 8 * GA + 7: RTK_LAUNCH(true, true, true, GA, false);    \
+    case 32 + 8 * GA + 0: RTK_LAUNCH(false, false, false, GA, true); \
+    case 32 + 8 * GA + 4: RTK_LAUNCH(true, false, false, GA, true);
     RTK_LAUNCH8(0)
     RTK_LAUNCH8(1)
     RTK_LAUNCH8(2)

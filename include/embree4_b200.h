@@ -331,7 +331,7 @@ struct RTCB200SceneStats {
   double build_ms;                       /* device time of the last rtcCommitScene build */
   double sah_cost;                       /* SAH cost of the committed BVH8 (area-weighted, c_trav=1, c_tri=1) */
   unsigned long long trav_rays, trav_nodes, trav_tris; /* accumulated while counting is enabled */
-  unsigned int builder;                  /* 0 = LBVH, 1 = binned SAH */
+  unsigned int builder;                  /* last commit: 0 = LBVH build, 1 = binned-SAH build, 2 = refit of the kept BVH */
   unsigned int max_depth;
 };
 RTCB200_API void rtcb200GetSceneStats(RTCScene scene, struct RTCB200SceneStats* out);

@@ -552,6 +552,67 @@ def test_update_and_recommit(b200):
     lib.rtcReleaseScene(sc)
 
 
+@pytest.mark.parametrize("scene_quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
+def test_refit_matches_rebuild(b200, oracle, scene_quality):
+    """RTC_BUILD_QUALITY_REFIT on the geometry (kernels/bvh/bvh_refit.cpp; verify.cpp update.* benchmarks): the first commit
+    builds, later commits with moved vertices and unchanged topology refit the same BVH8 (builder == 2).  Hits after a
+    refit equal the oracle's on the moved mesh and a from-scratch rebuild's; a primitive-count change falls back to a build."""
+    lib, dev = b200
+    v, t = scenes.triangle_sphere(80)
+    sc = lib.rtcNewScene(dev)
+    lib.rtcSetSceneFlags(sc, 1)            # DYNAMIC
+    lib.rtcSetSceneBuildQuality(sc, scene_quality)
+    g = lib.rtcNewGeometry(dev, RTC_GEOMETRY_TYPE_TRIANGLE)
+    vpad = np.zeros(v.size + 4, np.float32)
+    vpad[:v.size] = v.ravel()
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(vpad), 0, 12, len(v))
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT3, _ptr(t), 0, 12, len(t))
+    lib.rtcSetGeometryMask(g, 0xFFFFFFFF)
+    lib.rtcSetGeometryBuildQuality(g, 3)   # RTC_BUILD_QUALITY_REFIT
+    lib.rtcCommitGeometry(g)
+    lib.rtcAttachGeometry(sc, g)
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    assert lib.scene_stats(sc).builder in (0, 1)
+    rng = np.random.RandomState(4)
+    rays = scenes.as_numpy_rayhits(scenes.incoherent_rays_reference(100000, org=(0.1, -0.2, 0.05)))
+    for frame in range(3):
+        v2 = (v * np.array([1.0 + 0.3 * frame, 1.0, 1.0 - 0.2 * frame], np.float32) + rng.normal(scale=2e-3, size=v.shape)).astype(np.float32)
+        vpad[:v.size] = v2.ravel()
+        lib.rtcUpdateGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0)
+        lib.rtcCommitGeometry(g)
+        lib.rtcCommitScene(sc)
+        lib.check(dev)
+        assert lib.scene_stats(sc).builder == 2, "expected a refit"
+        b = RTCBounds()
+        lib.rtcGetSceneBounds(sc, C.byref(b))
+        assert np.allclose([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.concatenate([v2.min(0), v2.max(0)]), atol=0)
+        got = lib.intersect(sc, rays.copy(), "1M")
+        want = oracle.trace(v2, t, rays.copy(), nthreads=8)
+        rep = compare_hits(want, got, TOL, meshes=[(v2, t, 0, 0xFFFFFFFF)])
+        assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["max_rel_t"] <= TOL and rep["ng_bit_exact"], (frame, rep)
+        fresh, keep = build_scene(lib, dev, [(v2, t, 0, 0xFFFFFFFF)], scene_quality)
+        got2 = lib.intersect(fresh, rays.copy(), "1M")
+        rep2 = compare_hits(got2, got, TOL, meshes=[(v2, t, 0, 0xFFFFFFFF)])
+        assert rep2["id_mismatch"] == 0 and rep2["hit_miss_disagree"] == 0 and rep2["max_rel_t"] == 0.0, (frame, rep2)
+        occ = lib.occluded(sc, rays_of(rays), "1M")
+        assert ((occ["tfar"] == -np.inf) == (got["geomID"] != 0xFFFFFFFF)).all()
+        lib.rtcReleaseScene(fresh)
+    # a vertex turning NaN invalidates its triangles (scene_triangle_mesh.h:194-215) -- also under refit
+    vpad[0:3] = np.nan
+    lib.rtcUpdateGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0)
+    lib.rtcCommitGeometry(g)
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    got = lib.intersect(sc, rays.copy(), "1M")
+    v3 = vpad[:v.size].reshape(-1, 3).copy()
+    want = oracle.trace(v3, t, rays.copy(), nthreads=8)
+    rep = compare_hits(want, got, TOL)
+    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0, rep
+    lib.rtcReleaseGeometry(g)
+    lib.rtcReleaseScene(sc)
+
+
 @pytest.mark.parametrize("quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
 def test_watertight_and_reference_side_by_side(b200, oracle, quality):
     """WatertightTest (verify.cpp:3611-3690, <= 2e-5 leaks) + 200k-ray parity against the oracle and, when present,
