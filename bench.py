@@ -117,6 +117,38 @@ def usable_cores():
     return usable, {"os_cpu_count": logical, "sched_affinity": affinity, "cgroup_quota_cpus": quota}
 
 
+def bind_to_gpu_numa(local):
+    """Multi-GPU runs: pin this rank (CPU affinity + memory policy) to the NUMA node its GPU hangs off, BEFORE any pinned
+    host memory is allocated -- otherwise every rank's staging buffers land on the launching node and the ranks whose
+    GPUs sit on the other socket pull their rays across the inter-socket link (round 1: e2e scaled to 50 % at 8 GPUs)."""
+    info = {"node": None}
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        dom, bus, devi = getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id
+        node = int(open(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devi:02x}.0/numa_node").read())
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return info
+        os.sched_setaffinity(0, cpus)
+        info.update(node=node, cpus=len(cpus))
+        try:   # set_mempolicy(MPOL_PREFERRED, {node}): first-touch stays local even if a thread migrates
+            libc = C.CDLL(None, use_errno=True)
+            mask = (C.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            info["mempolicy"] = "preferred" if libc.syscall(238, 1, mask, 16 * 64) == 0 else "default (set_mempolicy failed)"
+        except Exception:   # noqa: BLE001
+            info["mempolicy"] = "default"
+    except Exception as ex:   # noqa: BLE001
+        info["error"] = str(ex)[:100]
+    return info
+
+
 def make_scene(phi):
     t0 = time.time()
     v, t = scenes.triangle_sphere(phi)
@@ -319,7 +351,7 @@ def coherent_leg(lib, dev, devt, stream, workload, phi, rays, args):
         lib.check(dev)
         out["e2e"] = {"value": n / float(np.mean(times)) * 1e-6, "unit": "Mrays/s", "h2d_bytes_per_step": n * 84, "d2h_bytes_per_step": n * 84,
                       "api": "rtcb200IntersectNM(NULL, scene, RTCRayHit16* host, 16, M, args), pinned host buffers"}
-        assert torch.equal(H.view(torch.int32)[:, 17:19, :], pk.cpu().view(torch.int32)[:, 17:19, :])   # host path == device path
+        out["e2e"]["host_equals_device"] = bool(torch.equal(H.view(torch.int32)[:, 8:19, :], pk.cpu().view(torch.int32)[:, 8:19, :]))   # bit-identical records
         del H
     if not args.no_cpu:
         from tests.parity import api_trace_mt, compare_hits, load_reference
@@ -372,6 +404,7 @@ def run_pathtracer(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     devt = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=devt)
     lib, pts = embree_b200.load(), pathstream.load()
@@ -550,7 +583,7 @@ def run_pathtracer(args):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": pathtracer_config(args, len(t), world),
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "per_bounce": per_bounce,
-                "radiance_mean": radiance_mean, "alive_after_last_bounce": alive_last,
+                "radiance_mean": radiance_mean, "alive_after_last_bounce": alive_last, "numa": numa,
                 "roofline": {"bound": "hbm", "kernel": "pts200 bounce_kernel (the workload's own kernel; the trace kernels' roofline is the headline bench's)",
                              "achieved": bk_bytes / (bk * 1e-3) * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": bk_bytes / (bk * 1e-3) * 1e-9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src, "kernel_ms": bk,
@@ -643,6 +676,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     devt = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=devt)
     lib = embree_b200.load()
@@ -770,6 +804,25 @@ def main():
     value = n * world / (ms_per_step * 1e-3) * 1e-6
     lib.check(dev)
     sampler.join(timeout=2)
+    gather_ab = None
+    if world > 1 and os.environ.get("RTCB200_GATHER_AB"):   # untimed extra: the same steps with the other delivery mode
+        gather_ab = {"default_mode_ms": ms_per_step}
+        for mode in (0, 1):
+            assert lib.rtcb200SetTuning(b"gather_mode", mode) == 0
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                step()
+            g1.record()
+            torch.cuda.synchronize()
+            tm = torch.tensor([g0.elapsed_time(g1) / args.steps], device=devt)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            gather_ab[f"mode{mode}_ms"] = float(tm.item())
+        lib.rtcb200SetTuning(b"gather_mode", 1)
     gather_ok = None
     if world > 1:   # untimed: the NVLink-written records on rank 0 must equal what an NCCL gather of the same hits delivers
         local = sharding.compact_hits(B)
@@ -923,6 +976,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, len(t)),
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "gather_verified": gather_ok, "per_rank": per_rank,
+                "gather_ab": gather_ab, "numa": numa,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                              "traffic": traffic, "peak_source": peak_src, "kernel": "rtk::trace_kernel<K=1,OCCLUDED=false,STATS=false,ROBUST=false,GENERAL=false>",
                              "kernel_ms": kms, "algorithmic_bytes_per_ray": bytes_per_ray,

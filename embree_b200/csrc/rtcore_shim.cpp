@@ -414,6 +414,12 @@ struct ThreadCtx {  // per calling thread: a stream and a mapped pinned staging 
 };
 thread_local ThreadCtx t_ctx;
 
+// RTCIntersectArguments / RTCOccludedArguments (rtcore_common.h:335-361, context.h:14-62).  `context->instID` seeds the
+// hit's instance ids.  `flags`: RTC_RAY_QUERY_FLAG_COHERENT only selects the reference's coherent packet traverser
+// (context.h:41-45) -- a performance hint with identical results, so every value is accepted; a warp here always traces 32
+// rays together.  `feature_mask`: "should get used in SYCL" (doc/src/api/rtcInitIntersectArguments.md:48); the reference's
+// CPU entry points never read it (kernels/common/rtcore.cpp), neither do we.  `filter` / `intersect` are host function
+// pointers that cannot run inside a device traversal: a non-NULL callback is an error instead of being silently skipped.
 template <typename Args>
 void check_args(SceneImpl* s, const Args* a, uint32_t& instID, uint32_t& instPrimID) {
   instID = instPrimID = RTC_INVALID_GEOMETRY_ID;

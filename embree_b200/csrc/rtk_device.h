@@ -73,7 +73,7 @@ struct TraceParams {
   // written when the ray terminates.  May point into a PEER GPU's memory (NVLink): this is how the multi-GPU
   // hit gather is fused into the trace kernel instead of being a separate collective.
   void* compact_out = nullptr;
-  int tri_batch_min = 6, tri_wait_max = 3, refill_min = 4, use_prefetch = 1;  // filled by launch_trace from tuning()
+  int tri_batch_min = 8, tri_wait_max = 4, refill_min = 4, use_prefetch = 1;  // filled by launch_trace from tuning()
   const GeomDesc* descs = nullptr;  // non-NULL: instanced scene, record.geomID slot holds a descriptor index
   int robust = 0;  // scene built with RTC_SCENE_FLAG_ROBUST: triangle records hold v0,v1,v2, Pluecker test
 };
@@ -84,8 +84,8 @@ int launch_trace(const TraceParams& p, int occluded, int K, cudaStream_t stream)
 struct Tuning {
   int collapse_policy = 3;   // 0/1/2 greedy variants (rt_core.cuh select_children), 3 = SAH-optimal dynamic programme
   int c_node = 100, c_tri = 50;  // DP cost of a BVH8 node visit / a triangle test, in 1/100
-  int tri_batch_min = 6;
-  int tri_wait_max = 3;
+  int tri_batch_min = 8;     // triangle step when >= this many lanes have triangles pending (or no lane has a node, or after tri_wait_max deferrals)
+  int tri_wait_max = 4;
   int blocks_per_sm = 8;
   int use_tma = 1;
   int refill_min = 4;

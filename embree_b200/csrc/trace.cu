@@ -226,14 +226,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   if (USE_TMA && lane == 0) { prefetch(0); prefetch(1); }
 
   // hit epilogue of one terminated ray (intersector_epilog.h:285-299; occluded: bvh_intersector1.cpp:186-188)
-  // (a, b, c = the winning triangle's record, fetched by the caller together with the next rays)
-  auto write_back = [&](const uint4& a, const uint4& b, const uint4& c, float* rec) {
+  auto write_back = [&](float* rec) {
     float cngx = 0.0f, cngy = 0.0f, cngz = 0.0f;
     uint32_t cprim = kInvalidID, cgeom = kInvalidID;
     if (found) {
       if (OCCLUDED) IO::store_tfar(p, ray_index, -INFINITY);
       else {
         // Ng = cross(e2, e1) and the ids come from the winning triangle's record (same arithmetic as tri_test)
+        const uint4* tp = tris + (size_t)hit_tri * 3;
+        const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         Hit hit;
         hit.t = tfar_tri; hit.u = hit_u; hit.v = hit_v;
         hit.primID = a.w; hit.geomID = b.w;
@@ -332,46 +333,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     // lanes have nothing to trace (or none has)
     const unsigned idle = __ballot_sync(FULL, state != TRACING);
     if (idle && (__popc(idle) >= refill_min || idle == FULL)) {
-      // The two fetches of this phase -- the winning triangle records of the rays being written back and the ray
-      // records of the rays being taken -- are issued together, before either is consumed: one memory latency, not two.
+      // (Issuing the record fetches of the write-back together with the ray fetches of the refill -- one latency instead
+      // of two -- was measured 10 % SLOWER, profiles/r2_ab_runs.txt run 3: the extra live registers spill in the node step.)
       float rec[8];
       const bool has_rec = state == DONE;
-      uint4 wa = make_uint4(0, 0, 0, 0), wb = wa, wc = wa;
-      if (has_rec && found && !OCCLUDED) {
-        const uint4* tp = tris + (size_t)hit_tri * 3;
-        wa = __ldg(tp); wb = __ldg(tp + 1); wc = __ldg(tp + 2);
-      }
-      bool take = false;
-      uint32_t new_index = 0;
-      int new_blk = blk;
-      Ray nr;
-      if (!warp_done) {
-        if (consumed == blk_count) {       // resident block used up (or nothing loaded yet): move to the next one
-          if (USE_TMA && lane == 0) prefetch(blk + 3);   // keep the stream two blocks ahead in L2
-          ++blk;
-          const unsigned long long first = block_first(blk);
-          if (first >= n) { warp_done = true; blk_count = 0; consumed = 0; }
-          else {
-            blk_first = (uint32_t)first;
-            blk_count = (n - blk_first) < 32u ? (n - blk_first) : 32u;
-            consumed = 0;
-          }
-        }
-        if (!warp_done) {
-          const uint32_t avail = blk_count - consumed;
-          const uint32_t rank = __popc(idle & lt_mask);
-          if (state != TRACING && rank < avail) {
-            new_index = blk_first + consumed + rank;
-            new_blk = blk;
-            bool valid = true;
-            if (K > 1) valid = (p.valid == nullptr) || (p.valid[new_index] == -1);   // inactive lanes stay untouched
-            if (valid) { IO::load(static_cast<const char*>(p.rays), new_index, nr); take = true; }
-          }
-          const uint32_t want = __popc(idle);
-          consumed += want < avail ? want : avail;
-        }
-      }
-      if (has_rec) { write_back(wa, wb, wc, rec); state = EMPTY; }
+      if (has_rec) { write_back(rec); state = EMPTY; }
       if (GATHER == 1) {
         // one 256-bit store per record (STG.256, new on sm_100): over NVLink the record travels as ONE full 32-byte sector
         if (has_rec) store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
@@ -381,14 +347,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
           const unsigned long long first = block_first(b);
           return (n - first) >= 32ull ? 0xFFFFFFFFu : ((1u << (unsigned)(n - first)) - 1u);
         };
-        // a block that is being consumed owns a staging slot; when both are taken the older block is flushed as far as it got
-        if (!warp_done && blk != slot_blk0 && blk != slot_blk1) {
-          if (slot_blk0 >= 0 && slot_blk1 >= 0) {
-            if (slot_blk0 < slot_blk1) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
-            else { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
-          }
-          if (slot_blk0 < 0) slot_blk0 = blk; else slot_blk1 = blk;
-        }
         const int slot = !has_rec ? -1 : (ray_blk == slot_blk0 ? 0 : (ray_blk == slot_blk1 ? 1 : -1));
         if (has_rec && slot < 0)   // straggler of a block that already lost its slot
           store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
@@ -402,21 +360,51 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         if (slot_blk0 >= 0 && slot_have0 == full_mask(slot_blk0)) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
         if (slot_blk1 >= 0 && slot_have1 == full_mask(slot_blk1)) { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
       }
-      if (take) {
-        r = nr;
-        ray_index = new_index;
-        ray_blk = new_blk;
-        if (STATS) ++st_rays;
-        found = false;
-        sp = 0; top_y = 0; tgx = 0; tgy = 0;
-        // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129); they still pass
-        // through DONE so that a gather buffer receives their miss record
-        const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
-        idx = rcp_safe_fast(r.dx); idy = rcp_safe_fast(r.dy); idz = rcp_safe_fast(r.dz);
-        oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
-        tfar_tri = r.tfar;
-        ngx = 0; ngy = go ? 0x80000000u : 0u;   // root entered as "one pending internal child, imask 0"
-        state = go ? TRACING : DONE;
+      if (!warp_done) {
+        if (consumed == blk_count) {       // resident block used up (or nothing loaded yet): move to the next one
+          if (USE_TMA && lane == 0) prefetch(blk + 3);   // keep the stream two blocks ahead in L2
+          ++blk;
+          const unsigned long long first = block_first(blk);
+          if (first >= n) { warp_done = true; blk_count = 0; consumed = 0; }
+          else {
+            blk_first = (uint32_t)first;
+            blk_count = (n - blk_first) < 32u ? (n - blk_first) : 32u;
+            consumed = 0;
+            if (GATHER == 2) {   // the new block needs a staging slot: a free one, else the older block is flushed as far as it got
+              if (slot_blk0 >= 0 && slot_blk1 >= 0) {
+                if (slot_blk0 < slot_blk1) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
+                else { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
+              }
+              if (slot_blk0 < 0) slot_blk0 = blk; else slot_blk1 = blk;
+            }
+          }
+        }
+        if (!warp_done) {
+          const uint32_t avail = blk_count - consumed;
+          const uint32_t rank = __popc(idle & lt_mask);
+          if (state == EMPTY && rank < avail) {
+            ray_index = blk_first + consumed + rank;
+            ray_blk = blk;
+            bool valid = true;
+            if (K > 1) valid = (p.valid == nullptr) || (p.valid[ray_index] == -1);   // inactive lanes stay untouched
+            if (valid) {
+              IO::load(static_cast<const char*>(p.rays), ray_index, r);
+              if (STATS) ++st_rays;
+              found = false;
+              sp = 0; top_y = 0; tgx = 0; tgy = 0;
+              // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129); they still
+              // pass through DONE so that a gather buffer receives their miss record
+              const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
+              idx = rcp_safe_fast(r.dx); idy = rcp_safe_fast(r.dy); idz = rcp_safe_fast(r.dz);
+              oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
+              tfar_tri = r.tfar;
+              ngx = 0; ngy = go ? 0x80000000u : 0u;   // root entered as "one pending internal child, imask 0"
+              state = go ? TRACING : DONE;
+            }
+          }
+          const uint32_t want = __popc(idle);
+          consumed += want < avail ? want : avail;
+        }
       }
       if (!__any_sync(FULL, state == TRACING)) {
         if (warp_done && !__any_sync(FULL, state == DONE)) break;
@@ -484,7 +472,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         lr.ox = __shfl_sync(FULL, r.ox, owner); lr.oy = __shfl_sync(FULL, r.oy, owner); lr.oz = __shfl_sync(FULL, r.oz, owner);
         lr.dx = __shfl_sync(FULL, r.dx, owner); lr.dy = __shfl_sync(FULL, r.dy, owner); lr.dz = __shfl_sync(FULL, r.dz, owner);
         lr.tnear = __shfl_sync(FULL, r.tnear, owner);
-        const float o_tfar = __shfl_sync(FULL, tfar_tri, owner);
+        // The winner must not depend on which other rays share the warp (an owner's items may be split over two steps
+        // when the queue is full): a triangle is a candidate when it passes the test against the ray's ORIGINAL tfar and
+        // its final t is <= the owner's current hit distance; among candidates the smallest t wins, the later item on
+        // equal t.  This is the minimum over all tested triangles whatever the batching, so the batched entry points,
+        // the packet entry points and the host-pointer pipeline return bit-identical hits for the same ray.
+        const float o_tfar = __shfl_sync(FULL, r.tfar, owner);
+        const float o_best = __shfl_sync(FULL, tfar_tri, owner);
         const uint32_t o_mask = __shfl_sync(FULL, r.mask, owner);
         float w_u = 0.0f, w_v = 0.0f;
         unsigned long long key = ~0ull;
@@ -498,11 +492,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
                        __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z), th)) {
             const float rcpAbsDen = 1.0f / th.absDen;
             const float t = th.T * rcpAbsDen;
-            w_u = th.U * rcpAbsDen; w_v = th.V * rcpAbsDen;
-            uint32_t tb32 = __float_as_uint(t);
-            tb32 ^= (tb32 >> 31) ? 0xFFFFFFFFu : 0x80000000u;   // order-preserving float -> uint
-            key = ((unsigned long long)tb32 << 32) | (uint32_t)(31 - lane);
-            atomicMin(&s_best[wi][owner], key);
+            if (t <= o_best) {
+              w_u = th.U * rcpAbsDen; w_v = th.V * rcpAbsDen;
+              uint32_t tb32 = __float_as_uint(t);
+              tb32 ^= (tb32 >> 31) ? 0xFFFFFFFFu : 0x80000000u;   // order-preserving float -> uint
+              key = ((unsigned long long)tb32 << 32) | (uint32_t)(31 - lane);
+              atomicMin(&s_best[wi][owner], key);
+            }
           }
         }
         __syncwarp();

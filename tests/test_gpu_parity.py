@@ -586,7 +586,8 @@ def test_refit_matches_rebuild(b200, oracle, scene_quality):
         assert lib.scene_stats(sc).builder == 2, "expected a refit"
         b = RTCBounds()
         lib.rtcGetSceneBounds(sc, C.byref(b))
-        assert np.allclose([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.concatenate([v2.min(0), v2.max(0)]), atol=0)
+        used = v2[t.ravel()]                 # bounds cover the vertices triangles reference (the generator leaves spare pole copies)
+        assert np.array_equal(np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32), np.concatenate([used.min(0), used.max(0)]))
         got = lib.intersect(sc, rays.copy(), "1M")
         want = oracle.trace(v2, t, rays.copy(), nthreads=8)
         rep = compare_hits(want, got, TOL, meshes=[(v2, t, 0, 0xFFFFFFFF)])
