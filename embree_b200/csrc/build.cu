@@ -110,6 +110,22 @@ __device__ __forceinline__ void load_tri_verts(const GeomDesc& g, uint32_t lp, f
   }
 }
 
+// round linear curve segment lp of geometry g (kernels/common/scene_line_segments.h:427-441 valid(), linei.h bounds()):
+// valid when both vertices exist, all four components are finite and no radius is negative
+__device__ __forceinline__ void load_curve(const GeomDesc& g, uint32_t lp, float4& p0, float4& p1, uint32_t& vid, bool& ok) {
+  vid = *reinterpret_cast<const uint32_t*>(g.idx + (uint64_t)lp * g.istride);
+  ok = (uint64_t)vid + 1 < g.nverts;
+  if (!ok) return;
+  const float* a = reinterpret_cast<const float*>(g.verts + (uint64_t)vid * g.vstride);
+  const float* b = reinterpret_cast<const float*>(g.verts + (uint64_t)(vid + 1) * g.vstride);
+  p0 = make_float4(a[0], a[1], a[2], a[3]);
+  p1 = make_float4(b[0], b[1], b[2], b[3]);
+  const float c[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ok &= (c[k] > -kFltLarge) & (c[k] < kFltLarge);
+  ok &= fminf(p0.w, p1.w) >= 0.0f;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // 1. PrimRef generation + scene / centroid bounds
 // ---------------------------------------------------------------------------------------------------
@@ -122,9 +138,22 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
   if (p < ntot) {
     const int g = find_geom(offs, ngeoms, p);
     float v[9], pad[3] = {0.0f, 0.0f, 0.0f};
-    load_tri_verts(geoms[g], p - offs[g], v, ok, true, pad);
+    if (geoms[g].is_curve) {   // merge(p0, p1) enlarged by the larger radius; two extra ulp of the magnitudes keep it conservative
+      float4 c0, c1;
+      uint32_t vid;
+      load_curve(geoms[g], p - offs[g], c0, c1, vid, ok);
+      if (ok) {
+        const float r = fmaxf(c0.w, c1.w);
+        const float a0[3] = {c0.x, c0.y, c0.z}, a1[3] = {c1.x, c1.y, c1.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          lo[a] = __fsub_rd(fminf(a0[a], a1[a]), r); hi[a] = __fadd_ru(fmaxf(a0[a], a1[a]), r);
+          lo[a] -= fabsf(lo[a]) * 2.4e-7f; hi[a] += fabsf(hi[a]) * 2.4e-7f;
+        }
+      }
+    } else load_tri_verts(geoms[g], p - offs[g], v, ok, true, pad);
     skipb = geoms[g].skip_bounds != 0;
-    if (ok) {
+    if (ok && !geoms[g].is_curve) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         lo[a] = fminf(fminf(v[a], v[3 + a]), v[6 + a]);
@@ -456,6 +485,18 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
   const GeomDesc gd = geoms[g];
   float v[9];
   bool ok;
+  if (gd.is_curve) {   // curve record: a = (p0.xyz, primID), b = (p1.xyz, descriptor), c = (r0, r1, first vertex | flags << 30, mask)
+    float4 c0, c1;
+    uint32_t vid;
+    const uint32_t lp = p - offs[g];
+    load_curve(gd, lp, c0, c1, vid, ok);
+    const uint32_t fl = gd.flags[lp] & 3u;
+    float4* dst = reinterpret_cast<float4*>(&out[t]);
+    dst[0] = make_float4(c0.x, c0.y, c0.z, __uint_as_float(lp));
+    dst[1] = make_float4(c1.x, c1.y, c1.z, __uint_as_float((uint32_t)g));
+    dst[2] = make_float4(c0.w, c1.w, __uint_as_float(vid | (fl << 30)), __uint_as_float(gd.mask));
+    return;
+  }
   load_tri_verts(gd, p - offs[g], v, ok, false);   // instances keep OBJECT-space triangles (see trace.cu to_object_space)
   if (tribox) {   // refit: bounds of the moved triangle (refit is limited to scenes without instances: object == world space)
     float* tb = tribox + (size_t)t * 6;

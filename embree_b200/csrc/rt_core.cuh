@@ -241,6 +241,135 @@ RT_HD void pluecker_uv(const PlueckerHit& h, float& u, float& v) {   // Pluecker
 }
 
 // ------------------------------------------------------------------------------------------------
+// round linear curve segment (RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE): __roundline_internal::intersectConeSphere restated for
+// one segment (kernels/geometry/roundline_intersector.h:560-650; cone :296-343, end spheres :350-395, neighbour cones
+// :137-205, normals / u :432-480).  Geometry = cone touching the spheres p0/r0 and p1/r1 plus the end sphere at p1 (plus
+// the one at p0 when there is no left neighbour), minus the capped cones of the neighbouring segments.  Backface culling
+// of curves is off in the reference's default build, so both the entry and the exit surface are candidates; a closest-hit
+// query takes the first candidate inside [tnear, tfar] exactly as the reference's epilog sequence does (:614-640).
+// ------------------------------------------------------------------------------------------------
+struct CurveHit { float t, u, ngx, ngy, ngz; };
+struct CurveVtx { float x, y, z, r; };
+
+struct ConeGeo {   // ConeGeometry<M> (:100-205)
+  float p0x, p0y, p0z, dPx, dPy, dPz, dPdP, r0, sqr_r0, r1, dr, r0dr, g;
+  bool exists;     // the reference marks a missing neighbour with p = +inf
+};
+RT_HD ConeGeo cone_geo(const CurveVtx& a, const CurveVtx& b, bool exists) {
+  ConeGeo c;
+  c.p0x = a.x; c.p0y = a.y; c.p0z = a.z;
+  c.dPx = b.x - a.x; c.dPy = b.y - a.y; c.dPz = b.z - a.z;
+  c.dPdP = c.dPx * c.dPx + c.dPy * c.dPy + c.dPz * c.dPz;
+  c.r0 = a.r; c.sqr_r0 = a.r * a.r; c.r1 = b.r; c.dr = b.r - a.r;
+  c.r0dr = c.r0 * c.dr; c.g = c.dPdP - c.dr * c.dr;
+  c.exists = exists;
+  return c;
+}
+RT_HD bool cone_clipped_by_plane(const ConeGeo& c, float px, float py, float pz) {           // isClippedByPlane (:137-144)
+  const float y = (px - c.p0x) * c.dPx + (py - c.p0y) * c.dPy + (pz - c.p0z) * c.dPz;
+  return c.exists & (y > -c.r0dr);
+}
+RT_HD bool cone_inside_capped(const ConeGeo& c, float px, float py, float pz) {              // isInsideCappedCone (:190-202)
+  const float qx = px - c.p0x, qy = py - c.p0y, qz = pz - c.p0z;
+  const float y = qx * c.dPx + qy * c.dPy + qz * c.dPz;
+  const float cap0 = -c.r0dr + 1.1920929e-07f, cap1 = -c.r1 * c.dr + c.dPdP;
+  const float qq = qx * qx + qy * qy + qz * qz;
+  return c.exists & (y > cap0) & (y < cap1) & (qq * c.g - y * y < c.dPdP * c.sqr_r0 + 2.0f * c.r0dr * y);
+}
+
+RT_HD bool curve_test(float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar, const CurveVtx& v0,
+                      const CurveVtx& v1, bool hasL, const CurveVtx& vL, bool hasR, const CurveVtx& vR, CurveHit& h) {
+  const float dOdO = dx * dx + dy * dy + dz * dz;
+  const float rcp_dOdO = 1.0f / dOdO;
+  // move the ray origin next to the segment (:571-574)
+  const float cx = 0.5f * (v0.x + v1.x), cy = 0.5f * (v0.y + v1.y), cz = 0.5f * (v0.z + v1.z);
+  const float dt = ((cx - ox) * dx + (cy - oy) * dy + (cz - oz) * dz) * rcp_dOdO;
+  const float qx = ox + dt * dx, qy = oy + dt * dy, qz = oz + dt * dz;
+  const ConeGeo c = cone_geo(v0, v1, true);
+  const float Ox = qx - c.p0x, Oy = qy - c.p0y, Oz = qz - c.p0z;
+  const float OdP = c.dPx * Ox + c.dPy * Oy + c.dPz * Oz;
+  const float dOdP = c.dPx * dx + c.dPy * dy + c.dPz * dz;
+  const float yp = OdP + c.r0dr;
+  // ---- cone (:296-343)
+  float t_cone_lower = INFINITY, t_cone_upper = -INFINITY;
+  float t_cone_front = 0.0f, t_cone_back = 0.0f, y_cone_front = 0.0f, y_cone_back = 0.0f;
+  bool validCone;
+  {
+    const float OO = Ox * Ox + Oy * Oy + Oz * Oz, OdO = dx * Ox + dy * Oy + dz * Oz;
+    const float A = c.g * dOdO - dOdP * dOdP;
+    const float B = 2.0f * (c.g * OdO - dOdP * yp);
+    const float C = c.g * OO - OdP * OdP - c.sqr_r0 * c.dPdP - 2.0f * c.r0dr * OdP;
+    const float D = B * B - 4.0f * A * C;
+    validCone = (D >= 0.0f) & (c.g > 0.0f) & (fabsf(A) > kMinRcpInput);
+    if (validCone) {
+      const float Q = sqrtf(D), rcp_2A = 1.0f / (2.0f * A);
+      t_cone_front = (-B - Q) * rcp_2A; y_cone_front = yp + t_cone_front * dOdP;
+      t_cone_back = (-B + Q) * rcp_2A;  y_cone_back = yp + t_cone_back * dOdP;
+      if ((y_cone_front > -1.1920929e-07f) & (y_cone_front <= c.g)) t_cone_lower = t_cone_front;
+      if ((y_cone_back > -1.1920929e-07f) & (y_cone_back <= c.g)) t_cone_upper = t_cone_back;
+    }
+  }
+  if (!(validCone | (c.g <= 0.0f))) return false;        // a cone entirely inside its end sphere still has the sphere (:579-581)
+  // ---- cone hits inside the neighbouring capped cones are inside the curve (:583-592)
+  const ConeGeo coneL = cone_geo(v0, vL, hasL), coneR = cone_geo(v1, vR, hasR);
+  if (validCone) {
+    const float lx = qx + t_cone_lower * dx, ly = qy + t_cone_lower * dy, lz = qz + t_cone_lower * dz;
+    const float ux = qx + t_cone_upper * dx, uy = qy + t_cone_upper * dy, uz = qz + t_cone_upper * dz;
+    if (cone_inside_capped(coneL, lx, ly, lz) | cone_inside_capped(coneR, lx, ly, lz)) t_cone_lower = INFINITY;
+    if (cone_inside_capped(coneL, ux, uy, uz) | cone_inside_capped(coneR, ux, uy, uz)) t_cone_upper = -INFINITY;
+  }
+  // ---- end sphere at p1, clipped by the right neighbour's start plane (:350-372)
+  float t_sph1_lower = INFINITY, t_sph1_upper = -INFINITY, t_sph1_front, t_sph1_back;
+  {
+    const float O1x = qx - v1.x, O1y = qy - v1.y, O1z = qz - v1.z;
+    const float O1dO = O1x * dx + O1y * dy + O1z * dz;
+    const float h2 = O1dO * O1dO - dOdO * (O1x * O1x + O1y * O1y + O1z * O1z - c.r1 * c.r1);
+    const float rhs1 = h2 >= 0.0f ? sqrtf(h2) : -INFINITY;
+    t_sph1_front = (-O1dO - rhs1) * rcp_dOdO;
+    t_sph1_back = (-O1dO + rhs1) * rcp_dOdO;
+    if ((h2 >= 0.0f) & (yp + t_sph1_front * dOdP > c.g) &
+        !cone_clipped_by_plane(coneR, qx + t_sph1_front * dx, qy + t_sph1_front * dy, qz + t_sph1_front * dz)) t_sph1_lower = t_sph1_front;
+    if ((h2 >= 0.0f) & (yp + t_sph1_back * dOdP > c.g) &
+        !cone_clipped_by_plane(coneR, qx + t_sph1_back * dx, qy + t_sph1_back * dy, qz + t_sph1_back * dz)) t_sph1_upper = t_sph1_back;
+  }
+  // ---- begin sphere at p0 when the curve starts here (:374-395, :598-601)
+  float t_sph0_lower = INFINITY, t_sph0_upper = -INFINITY, t_sph0_front = 0.0f, t_sph0_back = 0.0f;
+  if (!hasL) {
+    const float O1dO = Ox * dx + Oy * dy + Oz * dz;
+    const float h2 = O1dO * O1dO - dOdO * (Ox * Ox + Oy * Oy + Oz * Oz - c.r0 * c.r0);
+    const float rhs1 = h2 >= 0.0f ? sqrtf(h2) : -INFINITY;
+    t_sph0_front = (-O1dO - rhs1) * rcp_dOdO;
+    t_sph0_back = (-O1dO + rhs1) * rcp_dOdO;
+    if ((h2 >= 0.0f) & (yp + t_sph0_front * dOdP < 0.0f)) t_sph0_lower = t_sph0_front;
+    if ((h2 >= 0.0f) & (yp + t_sph0_back * dOdP < 0.0f)) t_sph0_upper = t_sph0_back;
+  }
+  // ---- CSG union, range test, first candidate (:603-625)
+  const float t_lower = fminf(t_cone_lower, fminf(t_sph0_lower, t_sph1_lower));
+  const float t_upper = fmaxf(t_cone_upper, fmaxf(t_sph0_upper, t_sph1_upper));
+  const bool valid_lower = (tnear <= dt + t_lower) & (dt + t_lower <= tfar) & (t_lower != INFINITY);
+  const bool valid_upper = (tnear <= dt + t_upper) & (dt + t_upper <= tfar) & (t_upper != -INFINITY);
+  if (!(valid_lower | valid_upper)) return false;
+  const float t_first = valid_lower ? t_lower : t_upper;
+  const bool cone_hit = (t_first == t_cone_lower) | (t_first == t_cone_upper);
+  const bool sph0_hit = (t_first == t_sph0_lower) | (t_first == t_sph0_upper);
+  if (cone_hit) {                                          // Ng_cone / u_cone (:432-447, :470-478)
+    const float y = valid_lower ? y_cone_front : y_cone_back, t = valid_lower ? t_cone_front : t_cone_back;
+    h.ngx = c.g * (Ox + t * dx) - c.dPx * y; h.ngy = c.g * (Oy + t * dy) - c.dPy * y; h.ngz = c.g * (Oz + t * dz) - c.dPz * y;
+    h.u = fminf(fmaxf(y * (1.0f / c.g), 0.0f), 1.0f);
+  } else if (sph0_hit) {
+    const float t = valid_lower ? t_sph0_front : t_sph0_back;
+    h.ngx = qx + t * dx - v0.x; h.ngy = qy + t * dy - v0.y; h.ngz = qz + t * dz - v0.z;
+    h.u = 0.0f;
+  } else {
+    const float t = valid_lower ? t_sph1_front : t_sph1_back;
+    h.ngx = qx + t * dx - v1.x; h.ngy = qy + t * dy - v1.y; h.ngz = qz + t * dz - v1.z;
+    h.u = 1.0f;
+  }
+  h.t = dt + t_first;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Node8 encoding (build side)
 // ------------------------------------------------------------------------------------------------
 struct ChildBox { float lo[3], hi[3]; };

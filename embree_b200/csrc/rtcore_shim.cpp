@@ -137,7 +137,7 @@ struct GeometryImpl : RefCounted {
   float xfm[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};  // local2world columns vx | vy | vz | p (AffineSpace3fa)
   float w2l[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};  // world2local0 = rcp(local2world) (scene_instance.cpp:153)
   void update_world2local();
-  BufferView vertices, indices;
+  BufferView vertices, indices, flags;   // flags: RTC_BUFFER_TYPE_FLAGS of a curve geometry (optional)
   std::vector<BufferView> attribs;
   unsigned mask = 1;  // reference default (geometry.cpp:48)
   bool enabled = true;
@@ -176,6 +176,7 @@ struct SceneImpl : RefCounted {
   rtk::SceneGPU gpu;
   float apiBounds[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};  // what rtcGetSceneBounds reports
   std::vector<void*> deviceBuffers;  // uploaded vertex/index bytes of the current commit
+  std::vector<void*> residentBuffers;  // curve vertex buffers: read by the trace kernel, live until the next commit
   bool statCounters = false;
   double lastTraceMs = -1.0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -184,6 +185,7 @@ struct SceneImpl : RefCounted {
     dev->use();
     for (GeometryImpl* g : geoms) if (g) g->release();
     for (void* p : deviceBuffers) cudaFreeAsync(p, 0);
+    for (void* p : residentBuffers) cudaFreeAsync(p, 0);
     rtk::free_scene(gpu);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -270,12 +272,56 @@ void commit_scene(SceneImpl* s) {
   s->dev->use();
   for (void* p : s->deviceBuffers) cudaFreeAsync(p, 0);
   s->deviceBuffers.clear();
+  for (void* p : s->residentBuffers) cudaFreeAsync(p, 0);
+  s->residentBuffers.clear();
   std::vector<rtk::GeomDesc> descs;
   std::vector<unsigned long long> childGen(geoms.size(), 0ull);   // generation of every instanced scene as baked in below
   std::unordered_map<GeometryImpl*, std::pair<void*, void*>> uploaded;   // a mesh instanced many times is uploaded once
-  bool instanced = false, quads = false;
+  bool instanced = false, quads = false, curves = false;
   float instBounds[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  // round linear curves (scene_line_segments.cpp): float4 vertices, one index per segment, neighbour flags from the
+  // application or derived from the index buffer as LineSegments::commit does (:209-232)
+  auto add_curves = [&](GeometryImpl* g, uint32_t geomID) {
+    const size_t nsegs = g->indices.count, nverts = g->vertices.count;
+    if (nsegs == 0 || !g->indices.buf) return;
+    if (!g->vertices.buf) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer not set");
+    if (nsegs > 0x3FFFFFFFull || nverts > 0x3FFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "curve geometry too large");
+    if (g->flags.buf && g->flags.count != nsegs) fail(RTC_ERROR_INVALID_OPERATION, "flags buffer must hold one entry per segment");
+    curves = true;
+    const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 16 : 16, ibytes = (nsegs - 1) * g->indices.stride + 4;
+    std::vector<unsigned char> fl(nsegs);
+    bool hasLeft = false;
+    for (size_t i = 0; i < nsegs; ++i) {
+      if (g->flags.buf) { fl[i] = *reinterpret_cast<const unsigned char*>(g->flags.data() + i * g->flags.stride) & 3u; continue; }
+      const unsigned cur = *reinterpret_cast<const unsigned*>(g->indices.data() + i * g->indices.stride);
+      const bool hasRight = (i + 1 < nsegs) && *reinterpret_cast<const unsigned*>(g->indices.data() + (i + 1) * g->indices.stride) == cur + 1;
+      fl[i] = (unsigned char)((hasLeft ? RTC_CURVE_FLAG_NEIGHBOR_LEFT : 0) | (hasRight ? RTC_CURVE_FLAG_NEIGHBOR_RIGHT : 0));
+      hasLeft = hasRight;
+    }
+    void *dv = nullptr, *di = nullptr, *df = nullptr;
+    cuda_check(cudaMallocAsync(&dv, vbytes, 0), "cudaMallocAsync(curve vertices)");
+    s->residentBuffers.push_back(dv);
+    cuda_check(cudaMallocAsync(&di, ibytes, 0), "cudaMallocAsync(curve indices)");
+    s->deviceBuffers.push_back(di);
+    cuda_check(cudaMallocAsync(&df, nsegs, 0), "cudaMallocAsync(curve flags)");
+    s->deviceBuffers.push_back(df);
+    cuda_check(cudaMemcpyAsync(dv, g->vertices.data(), vbytes, cudaMemcpyHostToDevice, 0), "upload curve vertices");
+    cuda_check(cudaMemcpyAsync(di, g->indices.data(), ibytes, cudaMemcpyHostToDevice, 0), "upload curve indices");
+    cuda_check(cudaMemcpyAsync(df, fl.data(), nsegs, cudaMemcpyHostToDevice, 0), "upload curve flags");
+    cuda_check(cudaStreamSynchronize(0), "upload curve flags");   // `fl` is a stack vector
+    rtk::GeomDesc d;
+    d.verts = static_cast<const uint8_t*>(dv); d.idx = static_cast<const uint8_t*>(di); d.flags = static_cast<const uint8_t*>(df);
+    d.vstride = g->vertices.stride; d.istride = g->indices.stride;
+    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)nsegs;
+    d.geomID = geomID; d.mask = g->mask; d.is_curve = 1;
+    descs.push_back(d);
+  };
   auto add_mesh = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
+    if (g->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE) {
+      if (xfm) fail(RTC_ERROR_INVALID_OPERATION, "instanced curve geometries are not supported by the B200 back-end");
+      add_curves(g, geomID);
+      return;
+    }
     const bool quad = g->type == RTC_GEOMETRY_TYPE_QUAD;
     const size_t nprims = g->indices.count, nverts = g->vertices.count;
     const size_t ntris = quad ? 2 * nprims : nprims;   // a quad contributes its two halves (quad_intersector_moeller.h:190-200)
@@ -340,7 +386,8 @@ void commit_scene(SceneImpl* s) {
         }
       }
   }
-  s->gpu.general = (instanced || quads) ? 1 : 0;
+  s->gpu.general = (instanced || quads || curves) ? 1 : 0;
+  s->gpu.curves = curves ? 1 : 0;
   // quality -> builder (scene.cpp:163-206: LOW = Morton two-level builder, MEDIUM/HIGH = SAH).  The env override
   // exists for A/B measurements of the two device builders only.
   rtk::BuilderKind kind = (s->quality == RTC_BUILD_QUALITY_LOW) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
@@ -349,7 +396,7 @@ void commit_scene(SceneImpl* s) {
   char errmsg[256];
   // REFIT (geometry build quality, rtcore_geometry.h; kernels/bvh/bvh_refit.cpp): same meshes, same counts, moved vertices
   std::vector<SceneImpl::TopoEntry> topo;
-  bool wantRefit = !instanced && !descs.empty();
+  bool wantRefit = !instanced && !curves && !descs.empty();
   for (size_t id = 0; id < geoms.size(); ++id) {
     GeometryImpl* g = geoms[id];
     if (!g || !g->enabled) continue;
@@ -434,6 +481,7 @@ rtk::TraceParams make_params(SceneImpl* s, void* rays, const int* valid, unsigne
   rtk::TraceParams p;
   p.nodes = s->gpu.nodes; p.tris = s->gpu.tris; p.root_valid = s->gpu.root_valid; p.robust = s->gpu.robust;
   p.descs = s->gpu.general ? s->gpu.d_descs : nullptr;
+  p.curves = s->gpu.curves;
   p.rays = rays; p.valid = valid; p.n = n; p.instID = instID; p.instPrimID = instPrimID;
   p.stat = s->statCounters ? s->gpu.d_stat : nullptr;
   return p;
@@ -634,8 +682,8 @@ ssize_t rtcGetDeviceProperty(RTCDevice h, enum RTCDeviceProperty prop) {
     case RTC_DEVICE_PROPERTY_COMPACT_POLYS_ENABLED: return 0;
     case RTC_DEVICE_PROPERTY_TRIANGLE_GEOMETRY_SUPPORTED: return 1;
     case RTC_DEVICE_PROPERTY_QUAD_GEOMETRY_SUPPORTED: return 1;
+    case RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED: return 1;   // round linear curves
     case RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED:
-    case RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED:
     case RTC_DEVICE_PROPERTY_USER_GEOMETRY_SUPPORTED:
     case RTC_DEVICE_PROPERTY_POINT_GEOMETRY_SUPPORTED: return 0;
     case RTC_DEVICE_PROPERTY_TASKING_SYSTEM: return 0;
@@ -679,8 +727,8 @@ void rtcReleaseBuffer(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; AP
 RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
   API_BEGIN
   VERIFY_HANDLE(h);
-  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE)
-    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD and _INSTANCE are supported by the B200 back-end");
+  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE && type != RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE)
+    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD, _ROUND_LINEAR_CURVE and _INSTANCE are supported by the B200 back-end");
   GeometryImpl* g = new GeometryImpl(D(h));
   g->type = type;
   return reinterpret_cast<RTCGeometry>(g);
@@ -708,10 +756,18 @@ void rtcSetGeometryBuildQuality(RTCGeometry g, enum RTCBuildQuality q) {
 static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFormat format, BufferImpl* buf, size_t off, size_t stride, size_t num) {
   // scene_triangle_mesh.cpp:35-80, scene_quad_mesh.cpp:35-80
   if (g->type == RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+  const bool curve = g->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE;   // scene_line_segments.cpp:35-100
+  if (curve && type == RTC_BUFFER_TYPE_FLAGS) {
+    if (format != RTC_FORMAT_UCHAR) fail(RTC_ERROR_INVALID_OPERATION, "invalid flag buffer format");
+    if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot");
+    g->flags.set(buf, off, stride, num, format);
+    g->update();
+    return;
+  }
   if (((size_t)(buf->ptr) + off) & 3 || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
   if (num > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_ARGUMENT, "buffer too large");
   if (type == RTC_BUFFER_TYPE_VERTEX) {
-    if (format != RTC_FORMAT_FLOAT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex buffer format");
+    if (format != (curve ? RTC_FORMAT_FLOAT4 : RTC_FORMAT_FLOAT3)) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex buffer format");
     if (stride * num > 16ull * 1024 * 1024 * 1024) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer can be at most 16GB large");
     if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid vertex buffer slot");
     g->vertices.set(buf, off, stride, num, format);
@@ -721,13 +777,14 @@ static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFo
     g->attribs[slot].set(buf, off, stride, num, format);
   } else if (type == RTC_BUFFER_TYPE_INDEX) {
     if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot");
-    if (format != (g->type == RTC_GEOMETRY_TYPE_QUAD ? RTC_FORMAT_UINT4 : RTC_FORMAT_UINT3)) fail(RTC_ERROR_INVALID_OPERATION, "invalid index buffer format");
+    if (format != (curve ? RTC_FORMAT_UINT : g->type == RTC_GEOMETRY_TYPE_QUAD ? RTC_FORMAT_UINT4 : RTC_FORMAT_UINT3)) fail(RTC_ERROR_INVALID_OPERATION, "invalid index buffer format");
     g->indices.set(buf, off, stride, num, format);
   } else
     fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
   g->update();
 }
 static size_t format_bytes(RTCFormat f) {
+  if (f == RTC_FORMAT_UCHAR) return 1;
   if (f >= RTC_FORMAT_UINT && f <= RTC_FORMAT_UINT4) return 4 * (size_t)(f - RTC_FORMAT_UINT + 1);
   if (f >= RTC_FORMAT_FLOAT && f <= RTC_FORMAT_FLOAT4 + 12) return 4 * (size_t)(f - RTC_FORMAT_FLOAT + 1);
   fail(RTC_ERROR_INVALID_ARGUMENT, "invalid format");
@@ -766,6 +823,7 @@ void* rtcGetGeometryBufferData(RTCGeometry g, enum RTCBufferType type, unsigned 
   if (type == RTC_BUFFER_TYPE_INDEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->indices; }
   else if (type == RTC_BUFFER_TYPE_VERTEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->vertices; }
   else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) { if (slot >= G(g)->attribs.size()) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->attribs[slot]; }
+  else if (type == RTC_BUFFER_TYPE_FLAGS && G(g)->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->flags; }
   else fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
   return const_cast<char*>(v->data());
   GEOM_END
@@ -773,7 +831,7 @@ void* rtcGetGeometryBufferData(RTCGeometry g, enum RTCBufferType type, unsigned 
 }
 void rtcUpdateGeometryBuffer(RTCGeometry g, enum RTCBufferType type, unsigned int slot) {
   GEOM_BEGIN(g)
-  if (type == RTC_BUFFER_TYPE_INDEX || type == RTC_BUFFER_TYPE_VERTEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); }
+  if (type == RTC_BUFFER_TYPE_INDEX || type == RTC_BUFFER_TYPE_VERTEX || type == RTC_BUFFER_TYPE_FLAGS) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); }
   else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) { if (slot >= G(g)->attribs.size()) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); }
   else fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
   G(g)->update();

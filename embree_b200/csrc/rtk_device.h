@@ -25,7 +25,12 @@ struct GeomDesc {
   uint32_t has_xfm = 0, instID = 0xFFFFFFFFu, inst_mask = 0xFFFFFFFFu, skip_bounds = 0;
   // quad mesh (RTC_GEOMETRY_TYPE_QUAD): idx holds 4 indices per primitive; local prim 2q / 2q+1 are the halves
   // (v0,v1,v3) / (v2,v1,v3) of quad q exactly as quad_intersector_moeller.h:190-200 splits them.
-  uint32_t is_quad = 0, pad_ = 0;
+  uint32_t is_quad = 0;
+  // round linear curves (RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE): verts = float4 (xyz, radius), idx = first vertex of each
+  // segment, ntris = segments; `flags` = one neighbour-flag byte per segment (device).  The vertex buffer stays resident
+  // after the build: the trace kernel fetches the neighbour vertices from it.
+  uint32_t is_curve = 0;
+  const uint8_t* flags = nullptr;
   float xfm[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
   float w2l[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
 };
@@ -39,7 +44,8 @@ struct SceneGPU {
   uint32_t num_nodes = 0, num_tris = 0;
   uint32_t root_valid = 0;              // 0: empty scene -> queries return immediately
   int robust = 0;                       // RTC_SCENE_FLAG_ROBUST: leaf records are (v0, v1, v2), Pluecker intersector
-  int general = 0;                      // scene has instances or quads: records carry a descriptor index instead of geomID
+  int general = 0;                      // scene has instances, quads or curves: records carry a descriptor index instead of geomID
+  int curves = 0;                       // scene has round linear curve records
   GeomDesc* d_descs = nullptr;          // device copy of the mesh descriptors (kept while general)
   float bounds[6] = {0, 0, 0, 0, 0, 0};  // lower xyz, upper xyz of all valid triangles (world space, instances flattened)
   float api_bounds[6] = {0, 0, 0, 0, 0, 0};  // the same without instanced triangles
@@ -75,6 +81,7 @@ struct TraceParams {
   void* compact_out = nullptr;
   int tri_batch_min = 8, tri_wait_max = 4, refill_min = 4, use_prefetch = 1;  // filled by launch_trace from tuning()
   const GeomDesc* descs = nullptr;  // non-NULL: instanced scene, record.geomID slot holds a descriptor index
+  int curves = 0;                   // the scene holds round linear curve records (descs != NULL)
   int robust = 0;  // scene built with RTC_SCENE_FLAG_ROBUST: triangle records hold v0,v1,v2, Pluecker test
 };
 // occluded: 0 = closest hit (rtcIntersect*), 1 = any hit (rtcOccluded*); K in {1,4,8,16}

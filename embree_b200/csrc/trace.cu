@@ -110,6 +110,20 @@ __device__ __forceinline__ void to_object_space(const GeomDesc& d, Ray& r) {
   r.dz = fma_rn(dx, d.w2l[2], fma_rn(dy, d.w2l[5], mul_rn(dz, d.w2l[8])));
 }
 
+// round linear curve record (build.cu leaf_pack): a = (p0.xyz, primID), b = (p1.xyz, descriptor), c = (r0, r1, first vertex | flags << 30,
+// mask).  The neighbour vertices -- needed to cut away what lies inside the adjacent segments -- come from the geometry's
+// resident float4 vertex buffer (LineSegments::gather, scene_line_segments.h:270-276).
+__device__ __forceinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h) {
+  const CurveVtx v0{__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(c.x)};
+  const CurveVtx v1{__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.y)};
+  const uint32_t vid = c.z & 0x3FFFFFFFu;
+  const bool hasL = (c.z >> 30) & 1u, hasR = (c.z >> 31) & 1u;
+  CurveVtx vL = v0, vR = v1;
+  if (hasL) { const float4 q = __ldg(reinterpret_cast<const float4*>(d.verts + (size_t)(vid - 1) * d.vstride)); vL = CurveVtx{q.x, q.y, q.z, q.w}; }
+  if (hasR) { const float4 q = __ldg(reinterpret_cast<const float4*>(d.verts + (size_t)(vid + 2) * d.vstride)); vR = CurveVtx{q.x, q.y, q.z, q.w}; }
+  return curve_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, v0, v1, hasL, vL, hasR, vR, h);
+}
+
 // 32-byte aligned 256-bit global store (PTX st.global.v8.f32 -> STG.E.256 on sm_100a)
 __device__ __forceinline__ void store_256(void* dst, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4),
@@ -162,7 +176,7 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 //             single-sector stores rank 0 ingested only ~225 GB/s (request-rate bound), which held the 8-GPU step at 67 ms
 //             instead of 50 ms.  A block whose slot is needed before all its rays have finished is flushed partially
 //             (masked lanes) and its stragglers fall back to the direct store.
-template <int K, bool OCCLUDED, bool STATS, bool ROBUST, bool GENERAL, int GATHER = 0, bool SPREAD = false>
+template <int K, bool OCCLUDED, bool STATS, bool ROBUST, int GENERAL, int GATHER = 0, bool SPREAD = false>
 __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(const TraceParams p) {
   const bool USE_TMA = p.use_prefetch != 0;
   using IO = RayIO<K, OCCLUDED>;
@@ -240,15 +254,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         hit.primID = a.w; hit.geomID = b.w;
         uint32_t instID = p.instID, instPrimID = p.instPrimID;
         float lox = r.ox, loy = r.oy, loz = r.oz;   // ray origin in the space the record's triangle lives in
+        bool is_curve = false;
         if (GENERAL) {   // ids through the descriptor; Ng stays in OBJECT space as in the reference
           const GeomDesc& d = p.descs[b.w];
           hit.geomID = d.geomID;
+          if (GENERAL == 2 && d.is_curve) {   // the normal of a curve hit depends on which surface was hit: re-run the (deterministic) test at the hit distance
+            CurveHit ch;
+            curve_record_test(d, r, tfar_tri, a, b, c, ch);
+            hit.ngx = ch.ngx; hit.ngy = ch.ngy; hit.ngz = ch.ngz;
+            is_curve = true;
+          }
           if (d.has_xfm) {
             instID = d.instID; instPrimID = 0u;   // instance_id_stack::push(context, instID, 0)
             if (ROBUST) { Ray lr = r; to_object_space(d, lr); lox = lr.ox; loy = lr.oy; loz = lr.oz; }
           }
         }
-        if (ROBUST) {   // stable_triangle_normal of the origin-relative edges, exactly as in tri_test_pluecker
+        if (is_curve) {
+        } else if (ROBUST) {   // stable_triangle_normal of the origin-relative edges, exactly as in tri_test_pluecker
           const float v0x = sub_rn(__uint_as_float(a.x), lox), v0y = sub_rn(__uint_as_float(a.y), loy), v0z = sub_rn(__uint_as_float(a.z), loz);
           const float v1x = sub_rn(__uint_as_float(b.x), lox), v1y = sub_rn(__uint_as_float(b.y), loy), v1z = sub_rn(__uint_as_float(b.z), loz);
           const float v2x = sub_rn(__uint_as_float(c.x), lox), v2y = sub_rn(__uint_as_float(c.y), loy), v2z = sub_rn(__uint_as_float(c.z), loz);
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
           hit.ngy = msub(e2z, e1x, mul_rn(e2x, e1z));
           hit.ngz = msub(e2x, e1y, mul_rn(e2y, e1x));
         }
-        if (GENERAL && (a.w >> 31)) {   // quad halves share the quad's primID; the second one has flipped winding
+        if (GENERAL && !is_curve && (a.w >> 31)) {   // quad halves share the quad's primID; the second one has flipped winding
           hit.primID = a.w & 0x7FFFFFFFu;
           hit.ngx = -hit.ngx; hit.ngy = -hit.ngy; hit.ngz = -hit.ngz;
         }
@@ -291,6 +313,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     bool visible = (c.w & r.mask) != 0;              // ray mask (intersector_epilog.h:256-262)
     if (GENERAL) {   // b.w = descriptor index: instance mask (instance_intersector.cpp:19-22) + object-space ray
       const GeomDesc& d = p.descs[b.w];
+      if (GENERAL == 2 && d.is_curve) {   // RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE: cone-sphere test, u along the segment, v = 0
+        CurveHit ch;
+        if (visible && curve_record_test(d, r, tfar_tri, a, b, c, ch)) {
+          found = true;
+          if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
+          else { tfar_tri = ch.t; hit_u = ch.u; hit_v = 0.0f; hit_tri = ti; }
+        }
+        return;
+      }
       visible = visible && (d.inst_mask & r.mask) != 0;
       if (d.has_xfm) to_object_space(d, lr);
     }
@@ -603,10 +634,28 @@ static int launch_k(TraceParams p, cudaStream_t st) {
   constexpr bool CLOSEST = !OCCLUDED;
   constexpr bool CAN_GATHER = (K == 1 && CLOSEST);
   const int variant = (p.stat ? 4 : 0) | (p.robust ? 2 : 0) | (p.descs ? 1 : 0);
+  if (p.descs && p.curves) {   // scenes with round linear curves: the GENERAL = 2 instantiations (kept apart: the curve test costs registers)
+    const int gmode = (CAN_GATHER && p.compact_out) ? (g_tuning.gather_mode == 0 ? 1 : 2) : 0;
+    switch ((variant >> 1) + 4 * gmode) {
+#define RTK_CURVE(ST, RB, GA) trace_kernel<K, OCCLUDED, ST, RB, 2, (CAN_GATHER ? GA : 0), false><<<blocks, TRACE_THREADS, 0, st>>>(p); break
+#define RTK_CURVE4(GA)                         \
+      case 4 * GA + 0: RTK_CURVE(false, false, GA); \
+      case 4 * GA + 1: RTK_CURVE(false, true, GA);  \
+      case 4 * GA + 2: RTK_CURVE(true, false, GA);  \
+      case 4 * GA + 3: RTK_CURVE(true, true, GA);
+      RTK_CURVE4(0)
+      RTK_CURVE4(1)
+      RTK_CURVE4(2)
+#undef RTK_CURVE4
+#undef RTK_CURVE
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   const int gather = (CAN_GATHER && p.compact_out) ? (g_tuning.gather_mode == 0 ? 1 : 2) : 0;
   const bool spread = CLOSEST && g_tuning.tri_spread && !p.robust && !p.descs;
   switch (variant + 8 * gather + (spread ? 32 : 0)) {
-#define RTK_LAUNCH(ST, RB, IN, GA, SP) trace_kernel<K, OCCLUDED, ST, RB, IN, (CAN_GATHER ? GA : 0), (CLOSEST && SP)><<<blocks, TRACE_THREADS, 0, st>>>(p); break
+#define RTK_LAUNCH(ST, RB, IN, GA, SP) trace_kernel<K, OCCLUDED, ST, RB, (IN ? 1 : 0), (CAN_GATHER ? GA : 0), (CLOSEST && SP)><<<blocks, TRACE_THREADS, 0, st>>>(p); break
 #define RTK_LAUNCH8(GA)                                          \
     case 8 * GA + 0: RTK_LAUNCH(false, false, false, GA, false); \
     case 8 * GA + 1: RTK_LAUNCH(false, false, true, GA, false);  \

@@ -20,7 +20,12 @@ RTC_BUFFER_TYPE_INDEX = 0
 RTC_BUFFER_TYPE_VERTEX = 1
 RTC_GEOMETRY_TYPE_TRIANGLE = 0
 RTC_GEOMETRY_TYPE_QUAD = 1
+RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE = 16
 RTC_GEOMETRY_TYPE_INSTANCE = 121
+RTC_FORMAT_UCHAR = 0x1001
+RTC_FORMAT_UINT = 0x5001
+RTC_FORMAT_FLOAT4 = 0x9004
+RTC_BUFFER_TYPE_FLAGS = 32
 RTC_FORMAT_FLOAT3X4_ROW_MAJOR = 0x9134
 RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR = 0x9234
 RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR = 0x9244
@@ -275,6 +280,30 @@ class RTCLib:
             gid = geom_id
         self.rtcReleaseGeometry(g)
         return gid, (vpad, idx)
+
+    def add_round_linear_curves(self, device, scene, vertices4, indices, flags=None, mask=None, geom_id=None):
+        """RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE with shared FLOAT4 (xyz, radius) vertex / UINT first-vertex index buffers and
+        an optional UCHAR neighbour-flags buffer (tutorials/hair_geometry, curve_geometry).  The arrays must stay alive."""
+        v = np.ascontiguousarray(vertices4, np.float32).reshape(-1, 4)
+        idx = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        g = self.rtcNewGeometry(device, RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE)
+        self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT4, _ptr(v), 0, 16, v.shape[0])
+        self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT, _ptr(idx), 0, 4, idx.shape[0])
+        keep = [v, idx]
+        if flags is not None:
+            f = np.ascontiguousarray(flags, np.uint8).reshape(-1)
+            self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_FLAGS, 0, RTC_FORMAT_UCHAR, _ptr(f), 0, 1, f.shape[0])
+            keep.append(f)
+        if mask is not None:
+            self.rtcSetGeometryMask(g, mask)
+        self.rtcCommitGeometry(g)
+        if geom_id is None:
+            gid = self.rtcAttachGeometry(scene, g)
+        else:
+            self.rtcAttachGeometryByID(scene, g, geom_id)
+            gid = geom_id
+        self.rtcReleaseGeometry(g)
+        return gid, tuple(keep)
 
     def add_quad_mesh(self, device, scene, vertices, indices, mask=None, geom_id=None):
         """RTC_GEOMETRY_TYPE_QUAD with shared FLOAT3 vertex / UINT4 index buffers (quad (v0,v1,v2,v3); a triangle is a

@@ -96,6 +96,27 @@ def quad_terrain(n, seed=7, amplitude=0.15):
     return v, q
 
 
+def hair_ball(strands, segments, seed=3, radius=1.0, length=0.35, width=0.004):
+    """A fur ball in the spirit of tutorials/hair_geometry: `strands` curves of `segments` round linear segments each grow
+    out of a sphere with a random walk and taper towards the tip.  Returns (vertices[nv,4] = xyz + radius, first-vertex
+    index per segment, None) -- the neighbour flags are left to the library, as the tutorial does."""
+    rng = np.random.RandomState(seed)
+    n = rng.normal(size=(strands, 3))
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    step = length / segments
+    pts = np.zeros((strands, segments + 1, 4), np.float32)
+    p, d = n * radius, n.copy()
+    for k in range(segments + 1):
+        pts[:, k, :3] = p
+        pts[:, k, 3] = width * (1.0 - 0.8 * k / segments)
+        d = d + rng.normal(scale=0.35, size=d.shape)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        p = p + d * step
+    verts = pts.reshape(-1, 4)
+    idx = (np.arange(strands)[:, None] * (segments + 1) + np.arange(segments)[None, :]).reshape(-1).astype(np.uint32)
+    return verts, idx, None
+
+
 def cube_and_ground():
     """The triangle_geometry tutorial scene (triangle_geometry_device.cpp:31-97): unit cube (12 tris, geomID 0)
     and a ground plane (2 tris, geomID 1)."""

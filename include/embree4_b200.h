@@ -54,6 +54,7 @@ typedef struct RTCTraversableTy* RTCTraversable; /* on this back-end == the scen
  *      rtcore_buffer.h:11-33, rtcore_scene.h:24-32) ---- */
 enum RTCFormat {
   RTC_FORMAT_UNDEFINED = 0,
+  RTC_FORMAT_UCHAR = 0x1001,       /* curve neighbour flags */
   RTC_FORMAT_UINT = 0x5001, RTC_FORMAT_UINT2, RTC_FORMAT_UINT3, RTC_FORMAT_UINT4,
   RTC_FORMAT_FLOAT = 0x9001, RTC_FORMAT_FLOAT2, RTC_FORMAT_FLOAT3, RTC_FORMAT_FLOAT4,
   RTC_FORMAT_FLOAT3X4_ROW_MAJOR = 0x9134, RTC_FORMAT_FLOAT3X4_COLUMN_MAJOR = 0x9234, RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR = 0x9244
@@ -62,7 +63,7 @@ enum RTCBuildQuality {
   RTC_BUILD_QUALITY_LOW = 0,    /* -> device LBVH (Morton) build      */
   RTC_BUILD_QUALITY_MEDIUM = 1, /* -> device binned-SAH build         */
   RTC_BUILD_QUALITY_HIGH = 2,   /* accepted; built as MEDIUM          */
-  RTC_BUILD_QUALITY_REFIT = 3   /* accepted; built as LOW (full rebuild beats refit on this device) */
+  RTC_BUILD_QUALITY_REFIT = 3   /* geometry quality: later commits with unchanged topology refit the kept BVH (bvh_refit.cpp) */
 };
 enum RTCSceneFlags {
   RTC_SCENE_FLAG_NONE = 0,
@@ -81,14 +82,20 @@ enum RTCRayQueryFlags {
 enum RTCFeatureFlags {
   RTC_FEATURE_FLAG_NONE = 0,
   RTC_FEATURE_FLAG_TRIANGLE = 1 << 1,
+  RTC_FEATURE_FLAG_QUAD = 1 << 2,
+  RTC_FEATURE_FLAG_ROUND_LINEAR_CURVE = 1 << 6,
+  RTC_FEATURE_FLAG_INSTANCE = 1 << 23,
   RTC_FEATURE_FLAG_ALL = 0xffffffff
 };
 enum RTCGeometryType {
   RTC_GEOMETRY_TYPE_TRIANGLE = 0,
   RTC_GEOMETRY_TYPE_QUAD = 1,      /* index buffer RTC_FORMAT_UINT4; intersected as the halves (v0,v1,v3), (v2,v1,v3) */
+  RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE = 16, /* vertex buffer RTC_FORMAT_FLOAT4 (xyz, radius), index buffer RTC_FORMAT_UINT = first vertex
+                                                of a segment, optional RTC_BUFFER_TYPE_FLAGS (rtcore_geometry.h:27; roundline_intersector.h) */
   RTC_GEOMETRY_TYPE_INSTANCE = 121 /* single-level instances of triangle scenes (rtcore_geometry.h:51) */
 };
-enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2 };
+enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2, RTC_BUFFER_TYPE_FLAGS = 32 };
+enum RTCCurveFlags { RTC_CURVE_FLAG_NEIGHBOR_LEFT = 1 << 0, RTC_CURVE_FLAG_NEIGHBOR_RIGHT = 1 << 1 };   /* rtcore_geometry.h:66-70 */
 enum RTCError {
   RTC_ERROR_NONE = 0, RTC_ERROR_UNKNOWN = 1, RTC_ERROR_INVALID_ARGUMENT = 2, RTC_ERROR_INVALID_OPERATION = 3,
   RTC_ERROR_OUT_OF_MEMORY = 4, RTC_ERROR_UNSUPPORTED_CPU = 5, RTC_ERROR_CANCELLED = 6,

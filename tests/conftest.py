@@ -48,6 +48,23 @@ def load_golden_instances(name="instances"):
                 bounds=z["bounds"])
 
 
+def load_golden_curves(name="curves"):
+    """tests/golden/curves.npz -> dict(meshes, curves=[(verts4, idx, flags or None, geomID, mask)], rays_in, intersect_out,
+    occluded_out, bounds): triangle meshes + round linear curve sets and the reference's outputs (make_golden.run_curves)."""
+    from embree_b200.rtc import RAYHIT_DTYPE, RAY_DTYPE, aligned_empty
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+    def rec(a, dt):
+        out = aligned_empty(a.shape[0], dt)
+        out.view(np.uint8).reshape(a.shape)[:] = a
+        return out
+    meshes = [(z[f"v{i}"], z[f"t{i}"], int(z[f"gid{i}"]), int(z[f"mask{i}"])) for i in range(int(z["n_meshes"]))]
+    curves = [(z[f"cv{i}"], z[f"ci{i}"], z[f"cf{i}"] if z[f"cf{i}"].size else None, int(z[f"cgid{i}"]), int(z[f"cmask{i}"]))
+              for i in range(int(z["n_curves"]))]
+    return dict(meshes=meshes, curves=curves, rays_in=rec(z["rays_in"], RAYHIT_DTYPE), intersect_out=rec(z["intersect_out"], RAYHIT_DTYPE),
+                occluded_out=rec(z["occluded_out"], RAY_DTYPE), bounds=z["bounds"])
+
+
 GOLDEN = ["cube_ground", "sphere21", "terrain_masks"]
 GOLDEN_QUADS = ["quads"]   # meshes with [n,4] indices are RTC_GEOMETRY_TYPE_QUAD
 

@@ -121,6 +121,58 @@ def run_instances(name, child_meshes, top_meshes, xfms, inst_masks, rayhits):
     R.rtcReleaseDevice(dev)
 
 
+def run_curves(name, meshes, curves, rayhits):
+    """Round linear curves (RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE, tutorials/hair_geometry / curve_geometry) next to
+    triangle meshes.  curves: list of (vertices[nv,4], first-vertex indices, flags or None, geomID, mask)."""
+    R = load_reference()
+    dev = R.new_device(None)
+    sc = R.rtcNewScene(dev)
+    keep = [R.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in meshes]
+    keep += [R.add_round_linear_curves(dev, sc, cv, ci, cf, mask=mask, geom_id=gid)[1] for (cv, ci, cf, gid, mask) in curves]
+    R.rtcCommitScene(sc)
+    R.check(dev)
+    b = RTCBounds()
+    R.rtcGetSceneBounds(sc, C.byref(b))
+    out_i = R.intersect(sc, rayhits.copy(), "1")
+    out_o = R.occluded(sc, rays_of(rayhits), "1")
+    out_8 = R.intersect(sc, rayhits.copy(), "8")
+    assert (out_8["primID"] == out_i["primID"]).all() and (out_8["geomID"] == out_i["geomID"]).all()
+    R.check(dev)
+    d = dict(rays_in=rayhits.view(np.uint8).reshape(-1, 96), intersect_out=out_i.view(np.uint8).reshape(-1, 96),
+             occluded_out=out_o.view(np.uint8).reshape(-1, 48),
+             bounds=np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32),
+             n_meshes=np.array(len(meshes)), n_curves=np.array(len(curves)))
+    for i, (v, t, gid, mask) in enumerate(meshes):
+        d[f"v{i}"], d[f"t{i}"], d[f"gid{i}"], d[f"mask{i}"] = v, t, np.array(gid, np.uint32), np.array(mask, np.uint32)
+    for i, (cv, ci, cf, gid, mask) in enumerate(curves):
+        d[f"cv{i}"], d[f"ci{i}"], d[f"cgid{i}"], d[f"cmask{i}"] = cv, ci, np.array(gid, np.uint32), np.array(mask, np.uint32)
+        d[f"cf{i}"] = np.zeros(0, np.uint8) if cf is None else np.asarray(cf, np.uint8)
+    print(f"{name}: {len(rayhits)} rays, hit rate {(out_i['geomID'] != 0xFFFFFFFF).mean():.3f}, curve hits "
+          f"{np.isin(out_i['geomID'], [c[3] for c in curves]).mean():.3f}, occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    R.rtcReleaseScene(sc)
+    R.rtcReleaseDevice(dev)
+
+
+def main_curves():
+    # a fur ball around a triangle sphere (geomID 0), two curve sets: library-derived neighbour flags (geomID 1, masked) and
+    # application flags that cut every strand into capped pieces (geomID 2)
+    v, t = scenes.triangle_sphere(12)
+    cv, ci, _ = scenes.hair_ball(160, 5, seed=3, width=0.03)
+    cv2, ci2, _ = scenes.hair_ball(40, 4, seed=8, radius=1.0, length=0.6, width=0.06)
+    fl2 = np.tile(np.array([0, 2, 1, 0], np.uint8), 40)          # per strand: lone segment, a pair, lone segment
+    rng = np.random.RandomState(11)
+    org = rng.normal(size=(6000, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * rng.uniform(1.05, 2.5, (6000, 1)).astype(np.float32)
+    d = (-org + rng.normal(scale=0.6, size=org.shape)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    rays["tnear"][::7] = 0.3
+    rays["tfar"][::5] = 1.2
+    rays["mask"][::3] = 0x2
+    rays["id"] = np.arange(len(rays))
+    run_curves("curves", [(v, t, 0, 0xFFFFFFFF)], [(cv, ci, None, 1, 0x3), (cv2, ci2, fl2, 2, 0xFFFFFFFD)], rays)
+
+
 def main():
     # 1. the triangle_geometry tutorial scene: cube (geomID 0) + ground plane (geomID 1), camera-like + random rays
     (cv, ct), (gv, gt) = scenes.cube_and_ground()
@@ -181,9 +233,13 @@ def main():
     r["id"] = np.arange(len(r))
     run_instances("instances", [(sv, st, 0, 0xFFFFFFFF), (sv2, st, 1, 0x3)], [(gv, gt, 0, 0xFFFFFFFF)], xf,
                   [0xFFFFFFFF if i % 3 else 0x5 for i in range(7)], r)
+    main_curves()
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "curves":
+        main_curves()
+        sys.exit(0)
     if load_reference() is None:
         sys.exit("oracle/_ref/libembree4.so.4 missing: run python oracle/build_ref.py first")
     torch.manual_seed(0)

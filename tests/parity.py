@@ -23,6 +23,7 @@ class Oracle:
         d.orc_add_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint]
         d.orc_commit.argtypes = [C.c_void_p]
         d.orc_add_quad_mesh.argtypes = d.orc_add_mesh.argtypes
+        d.orc_add_curves.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_uint, C.c_uint]
         d.orc_add_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
         d.orc_set_robust.argtypes = [C.c_void_p, C.c_int]
         d.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
@@ -32,10 +33,11 @@ class Oracle:
         d.orc_api_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_uint, C.c_int]
         self.d = d
 
-    def scene(self, meshes, robust=False, instances=()):
+    def scene(self, meshes, robust=False, instances=(), curves=()):
         """meshes: list of (vertices[nv,3] f32, indices[nt,3] u32 (or [nq,4] for a quad mesh), geomID, mask); instances:
-        list of (child OracleScene, xfm[12] column-major 3x4, geomID, mask).  Returns an OracleScene."""
-        return OracleScene(self, meshes, robust, instances)
+        list of (child OracleScene, xfm[12] column-major 3x4, geomID, mask); curves: list of (vertices[nv,4] f32 (xyz,
+        radius), first-vertex indices[ns] u32, flags[ns] u8 or None, geomID, mask) round linear curve sets."""
+        return OracleScene(self, meshes, robust, instances, curves)
 
     def trace(self, v, t, rayhits, occluded=False, mask=0xFFFFFFFF, nthreads=1):
         sc = self.scene([(v, t, 0, mask)])
@@ -45,7 +47,7 @@ class Oracle:
 
 
 class OracleScene:
-    def __init__(self, o, meshes, robust=False, instances=()):
+    def __init__(self, o, meshes, robust=False, instances=(), curves=()):
         self.o = o
         self.h = o.d.orc_new()
         o.d.orc_set_robust(self.h, 1 if robust else 0)
@@ -58,6 +60,13 @@ class OracleScene:
             self.keep += [v, t]
             (o.d.orc_add_quad_mesh if quad else o.d.orc_add_mesh)(self.h, v.ctypes.data, 12, v.shape[0], t.ctypes.data,
                                                                    16 if quad else 12, t.shape[0], gid, mask)
+        for (cv, ci, cf, gid, mask) in curves:
+            cv = np.ascontiguousarray(cv, np.float32).reshape(-1, 4)
+            ci = np.ascontiguousarray(ci, np.uint32).reshape(-1)
+            cf = None if cf is None else np.ascontiguousarray(cf, np.uint8).reshape(-1)
+            self.keep += [cv, ci, cf]
+            o.d.orc_add_curves(self.h, cv.ctypes.data, 16, cv.shape[0], ci.ctypes.data, 4, ci.shape[0],
+                               None if cf is None else cf.ctypes.data, gid, mask)
         for (child, xfm, gid, mask) in instances:
             m = np.ascontiguousarray(xfm, np.float32).reshape(12)
             self.keep += [child, m]
@@ -197,3 +206,45 @@ def explain_hit_miss(oracle, rays, want, got, single_prim_scene):
         bad += 0 if (r["geomID"][0] != 0xFFFFFFFF and same) else 1
         sc.free()
     return lost, bad
+
+
+def curve_grazing(cv, ci, prim, ray, limit=1e-2):
+    """Is `ray` (one RTCRayHit record) near-tangent to round linear segment `prim`?  The cone hit exists iff the
+    discriminant D = B^2 - 4AC of roundline_intersector.h:296-325 is >= 0; B and C are differences of nearly equal
+    products, so when D is a small fraction of B^2 (evaluated here in float64) its fp32 sign depends on the order of
+    rounding / FMA contraction, which differs between the reference's AVX code and any other implementation.  Also true
+    for the end spheres (h2 of :356, :380 against O1dO^2)."""
+    vid = int(ci[prim])
+    v0, v1 = cv[vid].astype(np.float64), cv[vid + 1].astype(np.float64)
+    O = np.array([ray["org_x"], ray["org_y"], ray["org_z"]], np.float64)
+    D = np.array([ray["dir_x"], ray["dir_y"], ray["dir_z"]], np.float64)
+    dP, dr = v1[:3] - v0[:3], v1[3] - v0[3]
+    g = dP @ dP - dr * dr
+    org = O + (((0.5 * (v0[:3] + v1[:3]) - O) @ D) / (D @ D)) * D
+    Ov = org - v0[:3]
+    dOdP, OdP = dP @ D, dP @ Ov
+    yp = OdP + v0[3] * dr
+    A, B = g * (D @ D) - dOdP ** 2, 2 * (g * (D @ Ov) - dOdP * yp)
+    Cc = g * (Ov @ Ov) - OdP ** 2 - v0[3] ** 2 * (dP @ dP) - 2 * v0[3] * dr * OdP
+    graz = abs(B * B - 4 * A * Cc) <= limit * max(B * B, abs(4 * A * Cc))
+    for c, r in ((v0, v0[3]), (v1, v1[3])):
+        O1 = org - c[:3]
+        b1 = O1 @ D
+        h2 = b1 * b1 - (D @ D) * (O1 @ O1 - r * r)
+        graz = graz or abs(h2) <= limit * max(b1 * b1, (D @ D) * abs(O1 @ O1 - r * r))
+    return bool(graz)
+
+
+def unexplained_curve_disagreements(rays, a, b, curve_sets):
+    """Rays on which two implementations of the curve test disagree (hit vs miss, or different primitives at different
+    distances) and for which NO involved curve segment is near-tangent to the ray (curve_grazing).  curve_sets:
+    {geomID: (vertices[nv,4], first-vertex indices)}.  Ties (same distance within TIE_ULPS) are not disagreements."""
+    ah, bh = a["geomID"] != 0xFFFFFFFF, b["geomID"] != 0xFFFFFFFF
+    ulps = np.abs(a["tfar"].view(np.int32).astype(np.int64) - b["tfar"].view(np.int32).astype(np.int64))
+    differ = (ah != bh) | (ah & bh & ((a["primID"] != b["primID"]) | (a["geomID"] != b["geomID"])) & (ulps > TIE_ULPS))
+    bad = 0
+    for i in np.nonzero(differ)[0]:
+        involved = [(int(x["geomID"][i]), int(x["primID"][i])) for x in (a, b) if int(x["geomID"][i]) in curve_sets]
+        if not any(curve_grazing(curve_sets[g][0], curve_sets[g][1], p, rays[i]) for (g, p) in involved):
+            bad += 1
+    return int(differ.sum()), bad

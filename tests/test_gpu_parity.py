@@ -523,6 +523,85 @@ def test_child_scene_recommit_reaches_the_instance(b200):
     lib.rtcReleaseScene(top)
 
 
+def build_curve_scene(lib, dev, meshes, curves, quality=RTC_BUILD_QUALITY_MEDIUM):
+    sc = lib.rtcNewScene(dev)
+    lib.rtcSetSceneBuildQuality(sc, quality)
+    keep = [lib.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in meshes]
+    keep += [lib.add_round_linear_curves(dev, sc, cv, ci, cf, mask=mask, geom_id=gid)[1] for (cv, ci, cf, gid, mask) in curves]
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    return sc, keep
+
+
+@pytest.mark.parametrize("quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
+def test_curves_golden_all_entry_points(b200, quality):
+    """RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE (tutorials/hair_geometry's shipped model; roundline_intersector.h) against the
+    reference's own outputs through every entry point: ids exact, t within 1e-4, u along the segment, v = 0, any-hit equal."""
+    from tests.conftest import load_golden_curves
+    lib, dev = b200
+    g = load_golden_curves()
+    sc, keep = build_curve_scene(lib, dev, g["meshes"], g["curves"], quality)
+    b = RTCBounds()
+    lib.rtcGetSceneBounds(sc, C.byref(b))
+    got_b = np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32)
+    assert np.allclose(got_b, g["bounds"], rtol=1e-6, atol=1e-6) and (got_b[:3] <= g["bounds"][:3]).all() and (got_b[3:] >= g["bounds"][3:]).all()
+    want = g["intersect_out"]
+    for mode in MODES:
+        got = lib.intersect(sc, g["rays_in"].copy(), mode)
+        rep = compare_hits(want, got, TOL)
+        assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 10, (mode, rep)   # ties: joints of two segments
+        assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= TOL and rep["miss_untouched"], (mode, rep)
+        ok = (got["geomID"] == want["geomID"]) & (got["primID"] == want["primID"]) & (got["geomID"] != 0xFFFFFFFF)
+        for f in ("Ng_x", "Ng_y", "Ng_z"):
+            assert np.allclose(got[f][ok], want[f][ok], rtol=1e-3, atol=1e-5), (mode, f)
+        occ = lib.occluded(sc, rays_of(g["rays_in"]), mode)
+        assert ((occ["tfar"] == -np.inf) == (g["occluded_out"]["tfar"] == -np.inf)).all(), mode
+    lib.rtcReleaseScene(sc)
+
+
+def test_curves_large_vs_oracle_and_errors(b200, oracle):
+    """200 k curve segments + a triangle mesh against the C oracle, and the curve-specific error paths."""
+    lib, dev = b200
+    cv, ci, cf = scenes.hair_ball(25000, 8, seed=9, width=0.004)
+    v, t = scenes.triangle_sphere(60)
+    cv = cv.copy()
+    cv[17, 0] = np.nan                       # invalid vertex: the segments that use it are dropped (scene_line_segments.h:427-441)
+    cv[40, 3] = -1.0                         # negative radius: dropped as well
+    sc, keep = build_curve_scene(lib, dev, [(v, t, 0, 0xFFFFFFFF)], [(cv, ci, cf, 1, 0xFFFFFFFF)])
+    rng = np.random.RandomState(6)
+    org = rng.normal(size=(300000, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * rng.uniform(1.02, 2.0, (300000, 1)).astype(np.float32)
+    d = (-org + rng.normal(scale=0.7, size=org.shape)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    got = lib.intersect(sc, rays.copy(), "1M")
+    osc = oracle.scene([(v, t, 0, 0xFFFFFFFF)], curves=[(cv, ci, cf, 1, 0xFFFFFFFF)])
+    want = osc.trace(rays.copy(), nthreads=16)
+    from tests.parity import unexplained_curve_disagreements
+    rep = compare_hits(want, got, TOL)
+    assert (want["geomID"] == 1).sum() > 20000, rep
+    # the only admissible differences are rays tangent to a segment (sign of the discriminant decided by rounding order)
+    n_differ, unexplained = unexplained_curve_disagreements(rays, want, got, {1: (cv, ci)})
+    assert n_differ <= 30 and unexplained == 0, (rep, n_differ, unexplained)
+    assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= 2e-4, rep
+    occ = lib.occluded(sc, rays_of(rays), "1M")
+    wocc = osc.trace(rays_of(rays), occluded=True, nthreads=16)
+    assert ((occ["tfar"] == -np.inf) != (wocc["tfar"] == -np.inf)).sum() <= n_differ
+    osc.free()
+    # a curve geometry cannot be instanced on this back-end, and its buffers have their own formats
+    top = lib.rtcNewScene(dev)
+    lib.add_instance(dev, top, sc, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32))
+    lib.rtcCommitScene(top)
+    assert lib.rtcGetDeviceError(dev) == 3
+    g = lib.rtcNewGeometry(dev, 16)
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(cv), 0, 16, len(cv))
+    assert lib.rtcGetDeviceError(dev) == 3                      # curves take FLOAT4 vertices
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT3, _ptr(ci), 0, 4, len(ci))
+    assert lib.rtcGetDeviceError(dev) == 3                      # and one UINT per segment
+    lib.rtcReleaseGeometry(g)
+    lib.rtcReleaseScene(top)
+    lib.rtcReleaseScene(sc)
+
+
 def test_update_and_recommit(b200):
     """UpdateTest (verify.cpp:1835) / dynamic_scene: move the vertices, rtcUpdateGeometryBuffer, re-commit."""
     lib, dev = b200

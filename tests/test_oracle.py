@@ -175,3 +175,58 @@ def test_oracle_quads_and_instances_vs_reference_live(oracle, robust):
     R.rtcReleaseScene(top)
     R.rtcReleaseScene(child)
     R.rtcReleaseDevice(dev)
+
+
+def test_oracle_curves_vs_golden(oracle):
+    """Round linear curves (roundline_intersector.h restated in oracle/embree_oracle.c) against the reference's own outputs:
+    two curve sets (library-derived and application neighbour flags, geometry masks) around a triangle sphere."""
+    from tests.conftest import load_golden_curves
+    g = load_golden_curves()
+    sc = oracle.scene(g["meshes"], curves=g["curves"])
+    got = sc.trace(g["rays_in"].copy())
+    rep = compare_hits(g["intersect_out"], got)
+    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 10, rep    # ties: the joint of two segments
+    assert rep["max_rel_t"] <= 1e-4 and rep["max_abs_uv"] <= 1e-4 and rep["miss_untouched"], rep
+    ok = (got["geomID"] == g["intersect_out"]["geomID"]) & (got["primID"] == g["intersect_out"]["primID"]) & (got["geomID"] != 0xFFFFFFFF)
+    for f in ("Ng_x", "Ng_y", "Ng_z"):
+        assert np.allclose(got[f][ok], g["intersect_out"][f][ok], rtol=1e-3, atol=1e-5), f
+    occ = sc.trace(rays_of(g["rays_in"]), occluded=True)
+    assert (occ["tfar"].view(np.uint32) == g["occluded_out"]["tfar"].view(np.uint32)).all()
+    assert np.array_equal(sc.bounds(), g["bounds"])
+    sc.free()
+
+
+def test_oracle_curves_vs_reference_live(oracle):
+    """Larger randomised check while the reference library is present: 3000 segments with neighbours, thin and thick."""
+    R = load_reference()
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    from tests.parity import api_trace_mt
+    cv, ci, cf = scenes.hair_ball(500, 6, seed=5, width=0.015)
+    v, t = scenes.triangle_sphere(16)
+    rng = np.random.RandomState(2)
+    org = rng.normal(size=(60000, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * 2.5
+    d = (-org + rng.normal(scale=0.5, size=org.shape)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    sc = oracle.scene([(v, t, 0, 0xFFFFFFFF)], curves=[(cv, ci, cf, 1, 0xFFFFFFFF)])
+    want = sc.trace(rays.copy(), nthreads=4)
+    dev = R.new_device(None)
+    rs = R.rtcNewScene(dev)
+    keep = [R.add_triangle_mesh(dev, rs, v, t, mask=0xFFFFFFFF, geom_id=0)[1], R.add_round_linear_curves(dev, rs, cv, ci, cf, mask=0xFFFFFFFF, geom_id=1)[1]]
+    R.rtcCommitScene(rs)
+    R.check(dev)
+    ref = api_trace_mt(R, rs, rays.copy(), 4)
+    from tests.parity import unexplained_curve_disagreements
+    rep = compare_hits(ref, want)
+    n_differ, unexplained = unexplained_curve_disagreements(rays, ref, want, {1: (cv, ci)})
+    # a ray tangent to a cone flips between hit and miss with the rounding of the discriminant: every disagreement must be one
+    assert (ref["geomID"] == 1).sum() > 3000 and n_differ <= 6 and unexplained == 0, (rep, n_differ, unexplained)
+    assert rep["max_rel_t"] <= 1e-4 and rep["max_abs_uv"] <= 2e-4, rep
+    ro = api_trace_mt(R, rs, rays_of(rays), 4, occluded=True)
+    wo = sc.trace(rays_of(rays), occluded=True, nthreads=4)
+    assert ((ro["tfar"] < 0) != (wo["tfar"] < 0)).sum() <= n_differ
+    R.rtcReleaseScene(rs)
+    R.rtcReleaseDevice(dev)
+    sc.free()
+    del keep
