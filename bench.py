@@ -360,10 +360,11 @@ def coherent_leg(lib, dev, devt, stream, workload, phi, rays, args):
             cores, detail = usable_cores()
             rdev = R.new_device(None)
             rsc, rkeep, _ = commit(R, rdev, v1, t1)
+            from embree_b200.rtc import aligned_empty
             src = pk0.cpu().numpy().reshape(-1).view(packet_dtype(16))
-            best, w = 1e30, None
+            best, w = 1e30, aligned_empty(npk, packet_dtype(16), align=64)    # RTCRayHit16 must be 64-byte aligned (rtcore.cpp:867)
             for _ in range(2):
-                w = src.copy()
+                w[:] = src
                 t0 = time.perf_counter()
                 api_trace_mt(R, rsc, w, cores, K=16, coherent=True)
                 best = min(best, time.perf_counter() - t0)

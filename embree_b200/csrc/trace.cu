@@ -149,6 +149,9 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 #ifndef RTK_SMEM_STACK
 #define RTK_SMEM_STACK 8   // traversal-stack entries per lane kept in shared memory (deeper ones spill to local memory)
 #endif
+#ifndef RTK_TOP_SMEM
+#define RTK_TOP_SMEM 0     // EXPERIMENT: this many nodes from the top of the (breadth-first) node array are staged in shared memory
+#endif                     // with one TMA bulk copy per CTA (cp.async.bulk + mbarrier); 73 = root + 8 + 64.  Measured: see DESIGN.md
 #ifndef RTK_TRI2
 #define RTK_TRI2 1   // a lane with two or more pending triangles tests two per triangle step (both records fetched together)
 #endif
@@ -238,6 +241,27 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     tma_prefetch_l2(static_cast<const char*>(p.rays) + first * IO::kRayBytes, cnt * IO::kRayBytes);
   };
   if (USE_TMA && lane == 0) { prefetch(0); prefetch(1); }
+#if RTK_TOP_SMEM > 0
+  // top of the tree in shared memory: one TMA bulk copy (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) per CTA
+  __shared__ alignas(128) uint32_t s_top[RTK_TOP_SMEM * 24];
+  __shared__ alignas(8) unsigned long long s_top_bar;
+  const uint32_t top_nodes = p.top_nodes < (uint32_t)RTK_TOP_SMEM ? p.top_nodes : (uint32_t)RTK_TOP_SMEM;
+  if (top_nodes) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_top_bar), dst = (uint32_t)__cvta_generic_to_shared(s_top);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(top_nodes * 96u) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(p.nodes),
+                   "r"(top_nodes * 96u), "r"(bar)
+                   : "memory");
+    }
+    __syncthreads();
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(bar) : "memory");
+  }
+#endif
 
   // hit epilogue of one terminated ray (intersector_epilog.h:285-299; occluded: bvh_intersector1.cpp:186-188)
   auto write_back = [&](float* rec) {
@@ -454,6 +478,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
       const uint32_t slot = ((uint32_t)(bit - 24)) ^ (7u - oct);
       const uint32_t node_index = ngx + (uint32_t)__popc(ngy & 0xFFu & ((1u << slot) - 1u));
       NodeW nw;
+#if RTK_TOP_SMEM > 0
+      if (node_index < top_nodes) {
+        const uint4* sp4 = reinterpret_cast<const uint4*>(s_top + node_index * 24);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { const uint4 q = sp4[k]; nw.w[4 * k] = q.x; nw.w[4 * k + 1] = q.y; nw.w[4 * k + 2] = q.z; nw.w[4 * k + 3] = q.w; }
+      } else
+#endif
       load_node(nodes, node_index, nw);
       if (STATS) ++st_nodes;
       // TravRay clamps tnear/tfar at 0 for the slab test only (bvh_intersector1.cpp:65); after a hit tray.tfar = ray.tfar (:105)
