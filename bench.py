@@ -723,7 +723,8 @@ def main():
     st2 = lib.scene_stats(sc)
     lib.rtcb200SetSceneStatCounters(sc, 0)
     nodes_per_ray, tris_per_ray = st2.trav_nodes / st2.trav_rays, st2.trav_tris / st2.trav_rays
-    bytes_per_ray = 48 + 48 + 4 + nodes_per_ray * 80 + tris_per_ray * 48
+    NODE_BYTES, TRI_BYTES = 96, 48      # sizeof(rtk::Node8), sizeof(rtk::TriRec) (embree_b200/csrc/rt_core.cuh)
+    bytes_per_ray = 48 + 48 + 4 + nodes_per_ray * NODE_BYTES + tris_per_ray * TRI_BYTES
     del S
 
     # ---- hit gather (N > 1), fused into the trace kernel: rank 0 owns a [world, n, 8] float buffer, every rank maps it
@@ -979,10 +980,14 @@ def main():
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "gather_verified": gather_ok, "per_rank": per_rank,
                 "gather_ab": gather_ab, "numa": numa,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                             "traffic": traffic, "peak_source": peak_src, "kernel": "rtk::trace_kernel<K=1,OCCLUDED=false,STATS=false,ROBUST=false,GENERAL=false>",
+                             "traffic": traffic, "peak_source": peak_src,
+                             "kernel": "rtk::trace_kernel<K=1,OCCLUDED=false,STATS=false,ROBUST=false,GENERAL=0,GATHER=0,SPREAD=true>",
                              "kernel_ms": kms, "algorithmic_bytes_per_ray": bytes_per_ray,
+                             "frac_with_round1_80B_nodes": (100 + nodes_per_ray * 80 + tris_per_ray * 48) * n / (kms * 1e-3) * 1e-9 / peaks["hbm_gbs"],
                              "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "reference_counters": ref_counters,
-                             "note": "algorithmic bytes = 100 B ray/hit I/O + nodes/ray*80 B + tris/ray*48 B (device stat counters, 1 Mi-ray sample)"},
+                             "note": "algorithmic bytes = 100 B ray/hit I/O + nodes/ray*96 B + tris/ray*48 B (device stat counters, 1 Mi-ray sample); the node "
+                                     "is 96 B = three whole 32-B sectors since round 2 (round 1: 80 B, which also occupied three sectors) -- "
+                                     "frac_with_round1_80B_nodes keeps the old accounting for comparison"},
                 "cpu_baseline": cpu_baseline, "parity": parity, "coherent": coherent, "extras": extras,
                 "build": {"device_ms": st.build_ms, "commit_wall_ms": commit_s * 1e3, "nodes": int(st.num_nodes), "sah": st.sah_cost,
                           "builder": "sah" if st.builder else "lbvh"}}

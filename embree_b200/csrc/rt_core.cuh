@@ -251,6 +251,9 @@ RT_HD void pluecker_uv(const PlueckerHit& h, float& u, float& v) {   // Pluecker
 struct CurveHit { float t, u, ngx, ngy, ngz; };
 struct CurveVtx { float x, y, z, r; };
 
+// Every product / sum below is an explicitly rounded fp32 operation (mul_rn / add_rn / sub_rn, dot products as the
+// reference's madd chain): the compiler may not contract them, so the device evaluates exactly the expressions of the C
+// oracle -- hit/miss decisions of near-tangent rays depend on the rounding of B*B - 4*A*C and of the clip tests.
 struct ConeGeo {   // ConeGeometry<M> (:100-205)
   float p0x, p0y, p0z, dPx, dPy, dPz, dPdP, r0, sqr_r0, r1, dr, r0dr, g;
   bool exists;     // the reference marks a missing neighbour with p = +inf
@@ -258,53 +261,54 @@ struct ConeGeo {   // ConeGeometry<M> (:100-205)
 RT_HD ConeGeo cone_geo(const CurveVtx& a, const CurveVtx& b, bool exists) {
   ConeGeo c;
   c.p0x = a.x; c.p0y = a.y; c.p0z = a.z;
-  c.dPx = b.x - a.x; c.dPy = b.y - a.y; c.dPz = b.z - a.z;
-  c.dPdP = c.dPx * c.dPx + c.dPy * c.dPy + c.dPz * c.dPz;
-  c.r0 = a.r; c.sqr_r0 = a.r * a.r; c.r1 = b.r; c.dr = b.r - a.r;
-  c.r0dr = c.r0 * c.dr; c.g = c.dPdP - c.dr * c.dr;
+  c.dPx = sub_rn(b.x, a.x); c.dPy = sub_rn(b.y, a.y); c.dPz = sub_rn(b.z, a.z);
+  c.dPdP = dot3(c.dPx, c.dPy, c.dPz, c.dPx, c.dPy, c.dPz);
+  c.r0 = a.r; c.sqr_r0 = mul_rn(a.r, a.r); c.r1 = b.r; c.dr = sub_rn(b.r, a.r);
+  c.r0dr = mul_rn(c.r0, c.dr); c.g = sub_rn(c.dPdP, mul_rn(c.dr, c.dr));
   c.exists = exists;
   return c;
 }
 RT_HD bool cone_clipped_by_plane(const ConeGeo& c, float px, float py, float pz) {           // isClippedByPlane (:137-144)
-  const float y = (px - c.p0x) * c.dPx + (py - c.p0y) * c.dPy + (pz - c.p0z) * c.dPz;
+  const float y = dot3(sub_rn(px, c.p0x), sub_rn(py, c.p0y), sub_rn(pz, c.p0z), c.dPx, c.dPy, c.dPz);
   return c.exists & (y > -c.r0dr);
 }
 RT_HD bool cone_inside_capped(const ConeGeo& c, float px, float py, float pz) {              // isInsideCappedCone (:190-202)
-  const float qx = px - c.p0x, qy = py - c.p0y, qz = pz - c.p0z;
-  const float y = qx * c.dPx + qy * c.dPy + qz * c.dPz;
-  const float cap0 = -c.r0dr + 1.1920929e-07f, cap1 = -c.r1 * c.dr + c.dPdP;
-  const float qq = qx * qx + qy * qy + qz * qz;
-  return c.exists & (y > cap0) & (y < cap1) & (qq * c.g - y * y < c.dPdP * c.sqr_r0 + 2.0f * c.r0dr * y);
+  const float qx = sub_rn(px, c.p0x), qy = sub_rn(py, c.p0y), qz = sub_rn(pz, c.p0z);
+  const float y = dot3(qx, qy, qz, c.dPx, c.dPy, c.dPz);
+  const float cap0 = add_rn(-c.r0dr, 1.1920929e-07f), cap1 = add_rn(mul_rn(-c.r1, c.dr), c.dPdP);
+  const float qq = dot3(qx, qy, qz, qx, qy, qz);
+  return c.exists & (y > cap0) & (y < cap1) &
+         (sub_rn(mul_rn(qq, c.g), mul_rn(y, y)) < add_rn(mul_rn(c.dPdP, c.sqr_r0), mul_rn(mul_rn(2.0f, c.r0dr), y)));
 }
 
 RT_HD bool curve_test(float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar, const CurveVtx& v0,
                       const CurveVtx& v1, bool hasL, const CurveVtx& vL, bool hasR, const CurveVtx& vR, CurveHit& h) {
-  const float dOdO = dx * dx + dy * dy + dz * dz;
-  const float rcp_dOdO = 1.0f / dOdO;
+  const float dOdO = dot3(dx, dy, dz, dx, dy, dz);
+  const float rcp_dOdO = rcp_rn(dOdO);
   // move the ray origin next to the segment (:571-574)
-  const float cx = 0.5f * (v0.x + v1.x), cy = 0.5f * (v0.y + v1.y), cz = 0.5f * (v0.z + v1.z);
-  const float dt = ((cx - ox) * dx + (cy - oy) * dy + (cz - oz) * dz) * rcp_dOdO;
-  const float qx = ox + dt * dx, qy = oy + dt * dy, qz = oz + dt * dz;
+  const float cx = mul_rn(0.5f, add_rn(v0.x, v1.x)), cy = mul_rn(0.5f, add_rn(v0.y, v1.y)), cz = mul_rn(0.5f, add_rn(v0.z, v1.z));
+  const float dt = mul_rn(dot3(sub_rn(cx, ox), sub_rn(cy, oy), sub_rn(cz, oz), dx, dy, dz), rcp_dOdO);
+  const float qx = add_rn(ox, mul_rn(dt, dx)), qy = add_rn(oy, mul_rn(dt, dy)), qz = add_rn(oz, mul_rn(dt, dz));
   const ConeGeo c = cone_geo(v0, v1, true);
-  const float Ox = qx - c.p0x, Oy = qy - c.p0y, Oz = qz - c.p0z;
-  const float OdP = c.dPx * Ox + c.dPy * Oy + c.dPz * Oz;
-  const float dOdP = c.dPx * dx + c.dPy * dy + c.dPz * dz;
-  const float yp = OdP + c.r0dr;
+  const float Ox = sub_rn(qx, c.p0x), Oy = sub_rn(qy, c.p0y), Oz = sub_rn(qz, c.p0z);
+  const float OdP = dot3(c.dPx, c.dPy, c.dPz, Ox, Oy, Oz);
+  const float dOdP = dot3(c.dPx, c.dPy, c.dPz, dx, dy, dz);
+  const float yp = add_rn(OdP, c.r0dr);
   // ---- cone (:296-343)
   float t_cone_lower = INFINITY, t_cone_upper = -INFINITY;
   float t_cone_front = 0.0f, t_cone_back = 0.0f, y_cone_front = 0.0f, y_cone_back = 0.0f;
   bool validCone;
   {
-    const float OO = Ox * Ox + Oy * Oy + Oz * Oz, OdO = dx * Ox + dy * Oy + dz * Oz;
-    const float A = c.g * dOdO - dOdP * dOdP;
-    const float B = 2.0f * (c.g * OdO - dOdP * yp);
-    const float C = c.g * OO - OdP * OdP - c.sqr_r0 * c.dPdP - 2.0f * c.r0dr * OdP;
-    const float D = B * B - 4.0f * A * C;
+    const float OO = dot3(Ox, Oy, Oz, Ox, Oy, Oz), OdO = dot3(dx, dy, dz, Ox, Oy, Oz);
+    const float A = sub_rn(mul_rn(c.g, dOdO), mul_rn(dOdP, dOdP));
+    const float B = mul_rn(2.0f, sub_rn(mul_rn(c.g, OdO), mul_rn(dOdP, yp)));
+    const float C = sub_rn(sub_rn(sub_rn(mul_rn(c.g, OO), mul_rn(OdP, OdP)), mul_rn(c.sqr_r0, c.dPdP)), mul_rn(mul_rn(2.0f, c.r0dr), OdP));
+    const float D = sub_rn(mul_rn(B, B), mul_rn(mul_rn(4.0f, A), C));
     validCone = (D >= 0.0f) & (c.g > 0.0f) & (fabsf(A) > kMinRcpInput);
     if (validCone) {
-      const float Q = sqrtf(D), rcp_2A = 1.0f / (2.0f * A);
-      t_cone_front = (-B - Q) * rcp_2A; y_cone_front = yp + t_cone_front * dOdP;
-      t_cone_back = (-B + Q) * rcp_2A;  y_cone_back = yp + t_cone_back * dOdP;
+      const float Q = sqrtf(D), rcp_2A = rcp_rn(mul_rn(2.0f, A));
+      t_cone_front = mul_rn(sub_rn(-B, Q), rcp_2A); y_cone_front = add_rn(yp, mul_rn(t_cone_front, dOdP));
+      t_cone_back = mul_rn(add_rn(-B, Q), rcp_2A);  y_cone_back = add_rn(yp, mul_rn(t_cone_back, dOdP));
       if ((y_cone_front > -1.1920929e-07f) & (y_cone_front <= c.g)) t_cone_lower = t_cone_front;
       if ((y_cone_back > -1.1920929e-07f) & (y_cone_back <= c.g)) t_cone_upper = t_cone_back;
     }
@@ -313,59 +317,63 @@ RT_HD bool curve_test(float ox, float oy, float oz, float dx, float dy, float dz
   // ---- cone hits inside the neighbouring capped cones are inside the curve (:583-592)
   const ConeGeo coneL = cone_geo(v0, vL, hasL), coneR = cone_geo(v1, vR, hasR);
   if (validCone) {
-    const float lx = qx + t_cone_lower * dx, ly = qy + t_cone_lower * dy, lz = qz + t_cone_lower * dz;
-    const float ux = qx + t_cone_upper * dx, uy = qy + t_cone_upper * dy, uz = qz + t_cone_upper * dz;
+    const float lx = add_rn(qx, mul_rn(t_cone_lower, dx)), ly = add_rn(qy, mul_rn(t_cone_lower, dy)), lz = add_rn(qz, mul_rn(t_cone_lower, dz));
+    const float ux = add_rn(qx, mul_rn(t_cone_upper, dx)), uy = add_rn(qy, mul_rn(t_cone_upper, dy)), uz = add_rn(qz, mul_rn(t_cone_upper, dz));
     if (cone_inside_capped(coneL, lx, ly, lz) | cone_inside_capped(coneR, lx, ly, lz)) t_cone_lower = INFINITY;
     if (cone_inside_capped(coneL, ux, uy, uz) | cone_inside_capped(coneR, ux, uy, uz)) t_cone_upper = -INFINITY;
   }
   // ---- end sphere at p1, clipped by the right neighbour's start plane (:350-372)
   float t_sph1_lower = INFINITY, t_sph1_upper = -INFINITY, t_sph1_front, t_sph1_back;
   {
-    const float O1x = qx - v1.x, O1y = qy - v1.y, O1z = qz - v1.z;
-    const float O1dO = O1x * dx + O1y * dy + O1z * dz;
-    const float h2 = O1dO * O1dO - dOdO * (O1x * O1x + O1y * O1y + O1z * O1z - c.r1 * c.r1);
+    const float O1x = sub_rn(qx, v1.x), O1y = sub_rn(qy, v1.y), O1z = sub_rn(qz, v1.z);
+    const float O1dO = dot3(O1x, O1y, O1z, dx, dy, dz);
+    const float h2 = sub_rn(mul_rn(O1dO, O1dO), mul_rn(dOdO, sub_rn(dot3(O1x, O1y, O1z, O1x, O1y, O1z), mul_rn(c.r1, c.r1))));
     const float rhs1 = h2 >= 0.0f ? sqrtf(h2) : -INFINITY;
-    t_sph1_front = (-O1dO - rhs1) * rcp_dOdO;
-    t_sph1_back = (-O1dO + rhs1) * rcp_dOdO;
-    if ((h2 >= 0.0f) & (yp + t_sph1_front * dOdP > c.g) &
-        !cone_clipped_by_plane(coneR, qx + t_sph1_front * dx, qy + t_sph1_front * dy, qz + t_sph1_front * dz)) t_sph1_lower = t_sph1_front;
-    if ((h2 >= 0.0f) & (yp + t_sph1_back * dOdP > c.g) &
-        !cone_clipped_by_plane(coneR, qx + t_sph1_back * dx, qy + t_sph1_back * dy, qz + t_sph1_back * dz)) t_sph1_upper = t_sph1_back;
+    t_sph1_front = mul_rn(sub_rn(-O1dO, rhs1), rcp_dOdO);
+    t_sph1_back = mul_rn(add_rn(-O1dO, rhs1), rcp_dOdO);
+    if ((h2 >= 0.0f) & (add_rn(yp, mul_rn(t_sph1_front, dOdP)) > c.g) &
+        !cone_clipped_by_plane(coneR, add_rn(qx, mul_rn(t_sph1_front, dx)), add_rn(qy, mul_rn(t_sph1_front, dy)), add_rn(qz, mul_rn(t_sph1_front, dz))))
+      t_sph1_lower = t_sph1_front;
+    if ((h2 >= 0.0f) & (add_rn(yp, mul_rn(t_sph1_back, dOdP)) > c.g) &
+        !cone_clipped_by_plane(coneR, add_rn(qx, mul_rn(t_sph1_back, dx)), add_rn(qy, mul_rn(t_sph1_back, dy)), add_rn(qz, mul_rn(t_sph1_back, dz))))
+      t_sph1_upper = t_sph1_back;
   }
   // ---- begin sphere at p0 when the curve starts here (:374-395, :598-601)
   float t_sph0_lower = INFINITY, t_sph0_upper = -INFINITY, t_sph0_front = 0.0f, t_sph0_back = 0.0f;
   if (!hasL) {
-    const float O1dO = Ox * dx + Oy * dy + Oz * dz;
-    const float h2 = O1dO * O1dO - dOdO * (Ox * Ox + Oy * Oy + Oz * Oz - c.r0 * c.r0);
+    const float O1dO = dot3(Ox, Oy, Oz, dx, dy, dz);
+    const float h2 = sub_rn(mul_rn(O1dO, O1dO), mul_rn(dOdO, sub_rn(dot3(Ox, Oy, Oz, Ox, Oy, Oz), mul_rn(c.r0, c.r0))));
     const float rhs1 = h2 >= 0.0f ? sqrtf(h2) : -INFINITY;
-    t_sph0_front = (-O1dO - rhs1) * rcp_dOdO;
-    t_sph0_back = (-O1dO + rhs1) * rcp_dOdO;
-    if ((h2 >= 0.0f) & (yp + t_sph0_front * dOdP < 0.0f)) t_sph0_lower = t_sph0_front;
-    if ((h2 >= 0.0f) & (yp + t_sph0_back * dOdP < 0.0f)) t_sph0_upper = t_sph0_back;
+    t_sph0_front = mul_rn(sub_rn(-O1dO, rhs1), rcp_dOdO);
+    t_sph0_back = mul_rn(add_rn(-O1dO, rhs1), rcp_dOdO);
+    if ((h2 >= 0.0f) & (add_rn(yp, mul_rn(t_sph0_front, dOdP)) < 0.0f)) t_sph0_lower = t_sph0_front;
+    if ((h2 >= 0.0f) & (add_rn(yp, mul_rn(t_sph0_back, dOdP)) < 0.0f)) t_sph0_upper = t_sph0_back;
   }
   // ---- CSG union, range test, first candidate (:603-625)
   const float t_lower = fminf(t_cone_lower, fminf(t_sph0_lower, t_sph1_lower));
   const float t_upper = fmaxf(t_cone_upper, fmaxf(t_sph0_upper, t_sph1_upper));
-  const bool valid_lower = (tnear <= dt + t_lower) & (dt + t_lower <= tfar) & (t_lower != INFINITY);
-  const bool valid_upper = (tnear <= dt + t_upper) & (dt + t_upper <= tfar) & (t_upper != -INFINITY);
+  const bool valid_lower = (tnear <= add_rn(dt, t_lower)) & (add_rn(dt, t_lower) <= tfar) & (t_lower != INFINITY);
+  const bool valid_upper = (tnear <= add_rn(dt, t_upper)) & (add_rn(dt, t_upper) <= tfar) & (t_upper != -INFINITY);
   if (!(valid_lower | valid_upper)) return false;
   const float t_first = valid_lower ? t_lower : t_upper;
   const bool cone_hit = (t_first == t_cone_lower) | (t_first == t_cone_upper);
   const bool sph0_hit = (t_first == t_sph0_lower) | (t_first == t_sph0_upper);
   if (cone_hit) {                                          // Ng_cone / u_cone (:432-447, :470-478)
     const float y = valid_lower ? y_cone_front : y_cone_back, t = valid_lower ? t_cone_front : t_cone_back;
-    h.ngx = c.g * (Ox + t * dx) - c.dPx * y; h.ngy = c.g * (Oy + t * dy) - c.dPy * y; h.ngz = c.g * (Oz + t * dz) - c.dPz * y;
-    h.u = fminf(fmaxf(y * (1.0f / c.g), 0.0f), 1.0f);
+    h.ngx = sub_rn(mul_rn(c.g, add_rn(Ox, mul_rn(t, dx))), mul_rn(c.dPx, y));
+    h.ngy = sub_rn(mul_rn(c.g, add_rn(Oy, mul_rn(t, dy))), mul_rn(c.dPy, y));
+    h.ngz = sub_rn(mul_rn(c.g, add_rn(Oz, mul_rn(t, dz))), mul_rn(c.dPz, y));
+    h.u = fminf(fmaxf(mul_rn(y, rcp_rn(c.g)), 0.0f), 1.0f);
   } else if (sph0_hit) {
     const float t = valid_lower ? t_sph0_front : t_sph0_back;
-    h.ngx = qx + t * dx - v0.x; h.ngy = qy + t * dy - v0.y; h.ngz = qz + t * dz - v0.z;
+    h.ngx = sub_rn(add_rn(qx, mul_rn(t, dx)), v0.x); h.ngy = sub_rn(add_rn(qy, mul_rn(t, dy)), v0.y); h.ngz = sub_rn(add_rn(qz, mul_rn(t, dz)), v0.z);
     h.u = 0.0f;
   } else {
     const float t = valid_lower ? t_sph1_front : t_sph1_back;
-    h.ngx = qx + t * dx - v1.x; h.ngy = qy + t * dy - v1.y; h.ngz = qz + t * dz - v1.z;
+    h.ngx = sub_rn(add_rn(qx, mul_rn(t, dx)), v1.x); h.ngy = sub_rn(add_rn(qy, mul_rn(t, dy)), v1.y); h.ngz = sub_rn(add_rn(qz, mul_rn(t, dz)), v1.z);
     h.u = 1.0f;
   }
-  h.t = dt + t_first;
+  h.t = add_rn(dt, t_first);
   return true;
 }
 

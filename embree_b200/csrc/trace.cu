@@ -113,7 +113,7 @@ __device__ __forceinline__ void to_object_space(const GeomDesc& d, Ray& r) {
 // round linear curve record (build.cu leaf_pack): a = (p0.xyz, primID), b = (p1.xyz, descriptor), c = (r0, r1, first vertex | flags << 30,
 // mask).  The neighbour vertices -- needed to cut away what lies inside the adjacent segments -- come from the geometry's
 // resident float4 vertex buffer (LineSegments::gather, scene_line_segments.h:270-276).
-__device__ __forceinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h) {
+__device__ __noinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h) {
   const CurveVtx v0{__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(c.x)};
   const CurveVtx v1{__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.y)};
   const uint32_t vid = c.z & 0x3FFFFFFFu;

@@ -340,3 +340,13 @@ extern "C" uint64_t emu_trace_ops(void* h, void* rays, uint64_t n, uint8_t* ops,
   }
   return len;
 }
+
+// ---- round linear curve segment test (rt_core.cuh curve_test), host instantiation of the routine the GENERAL = 2 trace kernels
+// call per curve record.  ray8 = ox oy oz tnear dx dy dz tfar; v* = float4 vertices; out5 = t, u, Ng.xyz.
+extern "C" int emu_curve_test(const float* ray8, const float* v0, const float* v1, int hasL, const float* vL, int hasR, const float* vR, float* out5) {
+  CurveHit h;
+  const CurveVtx a{v0[0], v0[1], v0[2], v0[3]}, b{v1[0], v1[1], v1[2], v1[3]}, l{vL[0], vL[1], vL[2], vL[3]}, r{vR[0], vR[1], vR[2], vR[3]};
+  if (!curve_test(ray8[0], ray8[1], ray8[2], ray8[4], ray8[5], ray8[6], ray8[3], ray8[7], a, b, hasL != 0, l, hasR != 0, r, h)) return 0;
+  out5[0] = h.t; out5[1] = h.u; out5[2] = h.ngx; out5[3] = h.ngy; out5[4] = h.ngz;
+  return 1;
+}

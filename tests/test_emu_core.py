@@ -132,3 +132,45 @@ def test_op_log_matches_traversal_counters(emu):
     emu.emu_trace_sorted(h, got.ctypes.data, len(got), s2.ctypes.data)
     assert (base["primID"] == got["primID"]).mean() > 0.9999 and s2[0] <= st[0]
     emu.emu_free(h)
+
+
+def test_curve_segment_test_equals_oracle(emu, oracle):
+    """rt_core.cuh curve_test (the routine the device runs per round-linear-curve record, here compiled for the host) finds,
+    by brute force over all segments, bit-identical t / u / Ng to the C oracle's BVH traversal on the golden curve rays --
+    every operation is explicitly rounded, so device, host instantiation and oracle evaluate the same expressions."""
+    import ctypes as C
+    from tests.conftest import load_golden_curves
+    g = load_golden_curves()
+    cv, ci, cf, gid, mask = g["curves"][0]
+    sc = oracle.scene([], curves=[(cv, ci, cf, gid, 0xFFFFFFFF)])
+    rays = g["rays_in"][::6].copy()
+    rays["mask"] = 0xFFFFFFFF
+    want = sc.trace(rays.copy())
+    n = len(ci)
+    right = np.zeros(n, bool)
+    right[:-1] = ci[1:] == ci[:-1] + 1
+    left = np.zeros(n, bool)
+    left[1:] = right[:-1]
+    P = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(C.c_void_p)   # noqa: E731
+    out = (C.c_float * 5)()
+    hits = 0
+    for k in range(len(rays)):
+        r = rays[k]
+        ray = np.array([r["org_x"], r["org_y"], r["org_z"], r["tnear"], r["dir_x"], r["dir_y"], r["dir_z"], r["tfar"]], np.float32)
+        best = None
+        for i in range(n):
+            v = int(ci[i])
+            vL, vR = (cv[v - 1] if left[i] else cv[v]), (cv[v + 2] if right[i] else cv[v + 1])
+            if emu.emu_curve_test(P(ray), P(cv[v]), P(cv[v + 1]), int(left[i]), P(vL), int(right[i]), P(vR), out):
+                best = (out[0], out[1], out[2], out[3], out[4], i)
+                ray[7] = out[0]                     # an accepted hit shrinks tfar for the following segments
+        w = want[k]
+        if best is None:
+            assert w["geomID"] == 0xFFFFFFFF, k
+            continue
+        hits += 1
+        got = np.array(best[:5], np.float32).view(np.uint32)
+        exp = np.array([w["tfar"], w["u"], w["Ng_x"], w["Ng_y"], w["Ng_z"]], np.float32).view(np.uint32)
+        assert (got == exp).all(), (k, best, w)
+    assert hits > 100
+    sc.free()
