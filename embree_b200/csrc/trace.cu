@@ -152,6 +152,9 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 #ifndef RTK_TOP_SMEM
 #define RTK_TOP_SMEM 0     // EXPERIMENT: this many nodes from the top of the (breadth-first) node array are staged in shared memory
 #endif                     // with one TMA bulk copy per CTA (cp.async.bulk + mbarrier); 73 = root + 8 + 64.  Measured: see DESIGN.md
+#ifndef RTK_SPREAD_PER_LANE
+#define RTK_SPREAD_PER_LANE 4   // triangles one lane may queue per SPREAD step (0 = round-2 first version: a divergent loop over all of them)
+#endif
 #ifndef RTK_TRI2
 #define RTK_TRI2 1   // a lane with two or more pending triangles tests two per triangle step (both records fetched together)
 #endif
@@ -512,20 +515,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         __shared__ unsigned long long s_best[TRACE_WARPS][32];
         const int wi = threadIdx.x >> 5;
         const bool isT = tracing && tgy != 0;
-        const int cnt = isT ? __popc(tgy) : 0;
+        const int cnt = isT ? min(__popc(tgy), RTK_SPREAD_PER_LANE) : 0;   // items this lane queues now; the rest waits for the next step
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-        int slot = incl - cnt;                                  // first queue slot of this lane's items
+        const int slot = incl - cnt;                            // first queue slot of this lane's items
         const int total = min(__shfl_sync(FULL, incl, 31), 32);
         s_best[wi][lane] = ~0ull;
-        while (isT && tgy != 0 && slot < 32) {                  // highest bit first = the sequential test order
-          const int tb = 31 - __clz((int)tgy);
-          tgy &= ~(1u << tb);
-          s_tri[wi][slot] = tgx + (uint32_t)tb;
-          s_owner[wi][slot] = (uint32_t)lane;
-          ++slot;
-        }
+#pragma unroll
+        for (int k = 0; k < RTK_SPREAD_PER_LANE; ++k)           // highest bit first = the sequential test order (predicated, no divergent loop)
+          if (k < cnt && slot + k < 32) {
+            const int tb = 31 - __clz((int)tgy);
+            tgy &= ~(1u << tb);
+            s_tri[wi][slot + k] = tgx + (uint32_t)tb;
+            s_owner[wi][slot + k] = (uint32_t)lane;
+          }
         __syncwarp();
         const bool work = lane < total;
         const uint32_t ti = work ? s_tri[wi][lane] : 0u;
