@@ -527,8 +527,8 @@ void trace_device(SceneImpl* s, void* d_rays, const int* d_valid, int K, size_t 
 // ---- multi-GPU hit gather into another GPU's memory ------------------------------------------------------------------
 // rtcb200Intersect1MGatherDevice: the trace kernel itself delivers one compact 32-byte hit record per ray into
 // `compact_out` -- local memory or a peer's memory over NVLink -- so the transfer is spread over the whole launch and no
-// separate collective moves hit data.  rtcb200SetTuning("gather_mode", m): 1 (default) stages each 32-ray block's
-// records in shared memory and stores complete blocks as 1 KB (eight full lines); 0 stores every record on its own as
+// separate collective moves hit data.  rtcb200SetTuning("gather_mode", m): 1 (default) writes each record to a local staging
+// buffer first and sends complete 32-ray blocks as 1 KB (eight full lines); 0 stores every record on its own as
 // one 256-bit sector when its ray terminates (round 1: 99 % / 98 % of linear at 2 / 4 GPUs but only ~225 GB/s into
 // rank 0 at 8 GPUs).  The copy-engine pipeline round 1 carried as an unvalidated option is gone.
 void trace_gather(SceneImpl* s, void* d_rays, size_t M, uint32_t instID, uint32_t instPrimID, cudaStream_t st, void* compact_out) {
@@ -540,6 +540,16 @@ void trace_gather(SceneImpl* s, void* d_rays, size_t M, uint32_t instID, uint32_
   cudaEventRecord(s->ev0, st);
   rtk::TraceParams p = make_params(s, d_rays, nullptr, (unsigned long long)M, instID, instPrimID);
   p.compact_out = compact_out;
+  if (rtk::tuning().gather_mode == 1) {   // local staging buffer of the blocked delivery, kept per calling thread and device
+    static thread_local struct Stage { int gpu = -1; void* p = nullptr; size_t cap = 0; ~Stage() { if (p) cudaFree(p); } } t_stage;
+    if (t_stage.gpu != s->dev->gpu || t_stage.cap < M * 32) {
+      if (t_stage.p) { cudaSetDevice(t_stage.gpu); cudaFree(t_stage.p); cudaSetDevice(s->dev->gpu); }
+      t_stage.p = nullptr; t_stage.cap = 0; t_stage.gpu = s->dev->gpu;
+      cuda_check(cudaMalloc(&t_stage.p, M * 32), "cudaMalloc(gather staging)");
+      t_stage.cap = M * 32;
+    }
+    p.stage = t_stage.p;
+  }
   cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, st), "trace launch");   // empty scene: every ray stores its miss record
   cudaEventRecord(s->ev1, st);
 }

@@ -79,6 +79,7 @@ struct TraceParams {
   // written when the ray terminates.  May point into a PEER GPU's memory (NVLink): this is how the multi-GPU
   // hit gather is fused into the trace kernel instead of being a separate collective.
   void* compact_out = nullptr;
+  void* stage = nullptr;   // gather mode 1: local staging buffer with the same indexing (n x 32 B)
   int tri_batch_min = 8, tri_wait_max = 4, refill_min = 4, use_prefetch = 1;  // filled by launch_trace from tuning()
   const GeomDesc* descs = nullptr;  // non-NULL: instanced scene, record.geomID slot holds a descriptor index
   int curves = 0;                   // the scene holds round linear curve records (descs != NULL)

@@ -177,11 +177,13 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 // GATHER (K == 1 closest hit only) adds the fused multi-GPU hit gather: every ray also produces one compact 32-byte
 // record {tfar, Ng, u, v, primID, geomID} in `compact_out`, which may be a PEER GPU's memory (NVLink).
 //   GATHER 1: the lane stores its record when the ray is written back -- one 256-bit store (STG.E.256), one sector.
-//   GATHER 2: records are staged per 32-ray block in shared memory (two 1 KB slots per warp) and a complete block leaves
-//             as ONE warp-wide store of 1 KB = eight full 128-byte lines.  At 8 GPUs seven peers store into rank 0; with
+//   GATHER 2: records are first stored to a LOCAL staging buffer (p.stage, same indexing); the warp tracks which records of
+//             its two newest 32-ray blocks have arrived and, when a block is complete, re-reads its 1 KB (L2 hits) and sends
+//             it as ONE warp-wide store of eight full 128-byte lines.  At 8 GPUs seven peers store into rank 0; with
 //             single-sector stores rank 0 ingested only ~225 GB/s (request-rate bound), which held the 8-GPU step at 67 ms
-//             instead of 50 ms.  A block whose slot is needed before all its rays have finished is flushed partially
-//             (masked lanes) and its stragglers fall back to the direct store.
+//             instead of 50 ms.  A block that stops being tracked before all its rays have finished is sent partially
+//             (masked lanes) and its stragglers fall back to the direct store.  (Staging in shared memory -- two 1 KB slots
+//             per warp -- cost 20 % of the kernel at 2 GPUs, profiles/r2_bench_n2.json gather_ab: 8 KB less L1 per CTA.)
 template <int K, bool OCCLUDED, bool STATS, bool ROBUST, int GENERAL, int GATHER = 0, bool SPREAD = false>
 __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(const TraceParams p) {
   const bool USE_TMA = p.use_prefetch != 0;
@@ -230,9 +232,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   bool warp_done = false;
   int tri_wait = 0;
   unsigned long long st_rays = 0, st_nodes = 0, st_tris = 0;
-  // GATHER 2: two staging slots per warp; slot_blk = index (in this warp's block sequence) of the block a slot holds,
-  // slot_have = which of its 32 record positions are filled (warp-uniform values)
-  __shared__ float4 s_rec[GATHER == 2 ? TRACE_WARPS * 2 * 32 * 2 : 1];
+  // GATHER 2: the two newest blocks of this warp are tracked; slot_blk = index (in this warp's block sequence), slot_have =
+  // which of its 32 records have been written to the local staging buffer (warp-uniform values)
   int slot_blk0 = -1, slot_blk1 = -1, ray_blk = -1;
   unsigned slot_have0 = 0, slot_have1 = 0;
 
@@ -323,15 +324,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
       rec[6] = __uint_as_float(cprim); rec[7] = __uint_as_float(cgeom);
     }
   };
-  // GATHER 2: write the filled positions of a staging slot to the gather buffer, lane i = record i of the block
+  // GATHER 2: send the arrived records of a tracked block from the staging buffer to the gather buffer, lane i = record i
   auto flush_slot = [&](int slot, int b, unsigned have) {
-    __syncwarp();
+    (void)slot;
+    __syncwarp();                    // the records were stored by other lanes of this warp: order them before the re-read
+    __threadfence_block();
     if (have & (1u << lane)) {
-      const float4* src = &s_rec[(((threadIdx.x >> 5) * 2 + slot) * 32 + lane) * 2];
-      const float4 x = src[0], y = src[1];
-      store_256(static_cast<char*>(p.compact_out) + (size_t)(block_first(b) + lane) * 32, x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w);
+      const size_t off = (size_t)(block_first(b) + lane) * 32;
+      const float4* src = reinterpret_cast<const float4*>(static_cast<const char*>(p.stage) + off);
+      const float4 x = __ldcg(src), y = __ldcg(src + 1);       // L2 (the stores went through L1 write-through)
+      store_256(static_cast<char*>(p.compact_out) + off, x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w);
     }
-    __syncwarp();
   };
 
   // one triangle record against this lane's ray (closest hit: shrinks tfar_tri; any hit: terminates the ray)
@@ -408,11 +411,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         const int slot = !has_rec ? -1 : (ray_blk == slot_blk0 ? 0 : (ray_blk == slot_blk1 ? 1 : -1));
         if (has_rec && slot < 0)   // straggler of a block that already lost its slot
           store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
-        if (slot >= 0) {
-          float4* dst = &s_rec[(((threadIdx.x >> 5) * 2 + slot) * 32 + (ray_index & 31u)) * 2];
-          dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-          dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-        }
+        if (slot >= 0) store_256(static_cast<char*>(p.stage) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
         slot_have0 |= __reduce_or_sync(FULL, slot == 0 ? 1u << (ray_index & 31u) : 0u);
         slot_have1 |= __reduce_or_sync(FULL, slot == 1 ? 1u << (ray_index & 31u) : 0u);
         if (slot_blk0 >= 0 && slot_have0 == full_mask(slot_blk0)) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
@@ -644,6 +643,7 @@ static int launch_k(TraceParams p, cudaStream_t st) {
       q.rays = static_cast<char*>(p.rays) + first * RayIO<K, OCCLUDED>::kRayBytes;
       if (p.valid) q.valid = p.valid + first;
       if (p.compact_out) q.compact_out = static_cast<char*>(p.compact_out) + first * 32;
+      if (p.stage) q.stage = static_cast<char*>(p.stage) + first * 32;
       const int r = launch_k<K, OCCLUDED>(q, st);
       if (r != 0) return r;
     }
@@ -670,7 +670,7 @@ static int launch_k(TraceParams p, cudaStream_t st) {
   constexpr bool CAN_GATHER = (K == 1 && CLOSEST);
   const int variant = (p.stat ? 4 : 0) | (p.robust ? 2 : 0) | (p.descs ? 1 : 0);
   if (p.descs && p.curves) {   // scenes with round linear curves: the GENERAL = 2 instantiations (kept apart: the curve test costs registers)
-    const int gmode = (CAN_GATHER && p.compact_out) ? (g_tuning.gather_mode == 0 ? 1 : 2) : 0;
+    const int gmode = (CAN_GATHER && p.compact_out) ? ((g_tuning.gather_mode == 0 || !p.stage) ? 1 : 2) : 0;
     switch ((variant >> 1) + 4 * gmode) {
 #define RTK_CURVE(ST, RB, GA) trace_kernel<K, OCCLUDED, ST, RB, 2, (CAN_GATHER ? GA : 0), false><<<blocks, TRACE_THREADS, 0, st>>>(p); break
 #define RTK_CURVE4(GA)                         \
@@ -687,7 +687,7 @@ static int launch_k(TraceParams p, cudaStream_t st) {
     count_launch();
     return (int)cudaGetLastError();
   }
-  const int gather = (CAN_GATHER && p.compact_out) ? (g_tuning.gather_mode == 0 ? 1 : 2) : 0;
+  const int gather = (CAN_GATHER && p.compact_out) ? ((g_tuning.gather_mode == 0 || !p.stage) ? 1 : 2) : 0;
   const bool spread = CLOSEST && g_tuning.tri_spread && !p.robust && !p.descs;
   switch (variant + 8 * gather + (spread ? 32 : 0)) {
 #define RTK_LAUNCH(ST, RB, IN, GA, SP) trace_kernel<K, OCCLUDED, ST, RB, (IN ? 1 : 0), (CAN_GATHER ? GA : 0), (CLOSEST && SP)><<<blocks, TRACE_THREADS, 0, st>>>(p); break

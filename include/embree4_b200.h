@@ -312,7 +312,7 @@ RTCB200_API void rtcb200Intersect1MDevice(RTCScene scene, struct RTCRayHit* d_ra
 /* as rtcb200Intersect1MDevice, and additionally writes one compact 32-byte record {tfar, Ng.xyz, u, v, primID, geomID} per
  * ray (primID = geomID = -1 on a miss) to compact_out[i] (32-byte aligned).  compact_out may be memory of ANOTHER GPU imported with
  * rtcb200PeerImport (the multi-GPU hit gather): the trace kernel stores the records itself, straight over NVLink when
- * the buffer is a peer's -- by default staged per 32-ray block in shared memory and stored as 1 KB (eight full lines) when
+ * the buffer is a peer's -- by default staged per 32-ray block in a local buffer and sent as 1 KB (eight full lines) when
  * the block is complete; rtcb200SetTuning("gather_mode", 0) selects one 256-bit store per record as its ray terminates.
  * Either way, work enqueued on cuda_stream after this call sees the complete buffer. */
 RTCB200_API void rtcb200Intersect1MGatherDevice(RTCScene scene, struct RTCRayHit* d_rayhits, size_t M, struct RTCIntersectArguments* args, void* cuda_stream, void* compact_out);
@@ -348,7 +348,7 @@ RTCB200_API void rtcb200ResetSceneStatCounters(RTCScene scene);
 RTCB200_API unsigned long long rtcb200GetLaunchCount(void);
 /* experiment knobs (process-wide): kernels "collapse_policy", "c_node", "c_tri", "sah_small", "tri_batch_min",
  * "tri_wait_max", "refill_min", "blocks_per_sm", "use_tma"; host-pointer pipeline "host_chunk_log2", "host_streams";
- * hit gather "gather_mode" (0 one store per record, 1 blocks staged in shared memory); EXPERIMENTAL: "tri_spread"
+ * hit gather "gather_mode" (0 one store per record, 1 complete 32-ray blocks as 1 KB stores); EXPERIMENTAL: "tri_spread"
  * (warp-wide triangle redistribution).  The defaults are the shipped, measured configuration.
  * Returns 0, or -1 for an unknown key or an out-of-range value. */
 RTCB200_API int rtcb200SetTuning(const char* key, int value);
