@@ -536,13 +536,19 @@ int build_sah_tree(const PrimRef* prims, uint32_t* idsA, uint32_t* idsB, uint32_
 // Build temporaries come from the device's stream-ordered memory pool (cudaMallocAsync): after the first commit the
 // pool serves every later build without touching the driver allocator, which is what keeps per-frame rebuilds of
 // dynamic scenes at kernel time (a plain cudaMalloc/cudaFree pair per buffer cost 10-300 ms at 10 M triangles).
+// The pool is the device's default one, which other users of cudaMallocAsync in the process share: the amount it may keep
+// cached after a commit is bounded (device config key "pool_keep_mb", default 8192 MB -- enough for the temporaries of a
+// 10 M-triangle build; memory above that goes back to the driver at the next synchronisation).
+static unsigned long long g_pool_keep_bytes = 8192ull << 20;
+void set_pool_keep_bytes(unsigned long long bytes) { g_pool_keep_bytes = bytes; }
 static void ensure_pool(int device) {
   static bool done[64] = {};
   if (device < 0 || device >= 64 || done[device]) return;
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    unsigned long long keep = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    unsigned long long keep = 0;
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (keep < g_pool_keep_bytes) { keep = g_pool_keep_bytes; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
   }
   cudaGetLastError();
   done[device] = true;

@@ -252,6 +252,7 @@ void parse_config(DeviceImpl* d, const char* cfg) {
       const std::string k = tok.substr(0, eq), v = tok.substr(eq + 1);
       if (k == "verbose") d->verbose = atoi(v.c_str());
       else if (k == "gpu") d->gpu = atoi(v.c_str());
+      else if (k == "pool_keep_mb") rtk::set_pool_keep_bytes((unsigned long long)atoll(v.c_str()) << 20);
     }
     pos = end + 1;
   }

@@ -104,6 +104,7 @@ struct Tuning {
 };
 Tuning& tuning();
 
+void set_pool_keep_bytes(unsigned long long bytes);   // release threshold of the stream-ordered pool the builds allocate from
 unsigned long long launch_count();
 void count_launch(unsigned n = 1);
 
