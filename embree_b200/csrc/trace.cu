@@ -152,9 +152,6 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 #ifndef RTK_TOP_SMEM
 #define RTK_TOP_SMEM 0     // EXPERIMENT: this many nodes from the top of the (breadth-first) node array are staged in shared memory
 #endif                     // with one TMA bulk copy per CTA (cp.async.bulk + mbarrier); 73 = root + 8 + 64.  Measured: see DESIGN.md
-#ifndef RTK_SPREAD_PER_LANE
-#define RTK_SPREAD_PER_LANE 4   // triangles one lane may queue per SPREAD step (0 = round-2 first version: a divergent loop over all of them)
-#endif
 #ifndef RTK_TRI2
 #define RTK_TRI2 1   // a lane with two or more pending triangles tests two per triangle step (both records fetched together)
 #endif
@@ -234,8 +231,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   unsigned long long st_rays = 0, st_nodes = 0, st_tris = 0;
   // GATHER 2: the two newest blocks of this warp are tracked; slot_blk = index (in this warp's block sequence), slot_have =
   // which of its 32 records have been written to the local staging buffer (warp-uniform values)
-  int slot_blk0 = -1, slot_blk1 = -1, ray_blk = -1;
-  unsigned slot_have0 = 0, slot_have1 = 0;
+  // The state lives in shared memory (16 B per warp: first ray index and arrival mask of the two tracked blocks), not in
+  // registers: it is only touched in the write-back phase, and four more live registers in the traversal loop cost 19 % of
+  // the kernel (first version of this mode, r2_bench_n2_smem_staging.json).
+  __shared__ uint32_t s_slot[GATHER == 2 ? TRACE_WARPS : 1][4];   // first0, have0, first1, have1; first == ~0u: free
+  constexpr uint32_t kNoBlock = 0xFFFFFFFFu;
+  if (GATHER == 2) {
+    if (lane < 4) s_slot[threadIdx.x >> 5][lane] = (lane & 1) ? 0u : kNoBlock;
+    __syncwarp();
+  }
 
   auto block_first = [&](int b) -> unsigned long long { return ((unsigned long long)b * num_warps + warp_id) * 32ull; };
   auto prefetch = [&](int b) {   // lane 0 only
@@ -325,12 +329,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     }
   };
   // GATHER 2: send the arrived records of a tracked block from the staging buffer to the gather buffer, lane i = record i
-  auto flush_slot = [&](int slot, int b, unsigned have) {
-    (void)slot;
+  auto flush_block = [&](uint32_t first, unsigned have) {
     __syncwarp();                    // the records were stored by other lanes of this warp: order them before the re-read
     __threadfence_block();
     if (have & (1u << lane)) {
-      const size_t off = (size_t)(block_first(b) + lane) * 32;
+      const size_t off = (size_t)(first + lane) * 32;
       const float4* src = reinterpret_cast<const float4*>(static_cast<const char*>(p.stage) + off);
       const float4 x = __ldcg(src), y = __ldcg(src + 1);       // L2 (the stores went through L1 write-through)
       store_256(static_cast<char*>(p.compact_out) + off, x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w);
@@ -404,18 +407,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         if (has_rec) store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
       }
       if (GATHER == 2) {
-        auto full_mask = [&](int b) -> unsigned {
-          const unsigned long long first = block_first(b);
-          return (n - first) >= 32ull ? 0xFFFFFFFFu : ((1u << (unsigned)(n - first)) - 1u);
-        };
-        const int slot = !has_rec ? -1 : (ray_blk == slot_blk0 ? 0 : (ray_blk == slot_blk1 ? 1 : -1));
-        if (has_rec && slot < 0)   // straggler of a block that already lost its slot
-          store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
-        if (slot >= 0) store_256(static_cast<char*>(p.stage) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
-        slot_have0 |= __reduce_or_sync(FULL, slot == 0 ? 1u << (ray_index & 31u) : 0u);
-        slot_have1 |= __reduce_or_sync(FULL, slot == 1 ? 1u << (ray_index & 31u) : 0u);
-        if (slot_blk0 >= 0 && slot_have0 == full_mask(slot_blk0)) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
-        if (slot_blk1 >= 0 && slot_have1 == full_mask(slot_blk1)) { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
+        uint32_t* ss = s_slot[threadIdx.x >> 5];
+        const uint32_t first0 = ss[0], first1 = ss[2];
+        const uint32_t my_first = ray_index & ~31u;
+        const int slot = !has_rec ? -1 : (my_first == first0 ? 0 : (my_first == first1 ? 1 : -1));
+        if (has_rec) {   // tracked block: local staging buffer; straggler of a block that is no longer tracked: straight to the gather buffer
+          char* dst = static_cast<char*>(slot >= 0 ? p.stage : p.compact_out) + (size_t)ray_index * 32;
+          store_256(dst, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
+        }
+        const unsigned have0 = ss[1] | __reduce_or_sync(FULL, slot == 0 ? 1u << (ray_index & 31u) : 0u);
+        const unsigned have1 = ss[3] | __reduce_or_sync(FULL, slot == 1 ? 1u << (ray_index & 31u) : 0u);
+        auto full_mask = [&](uint32_t first) -> unsigned { return (n - first) >= 32u ? 0xFFFFFFFFu : ((1u << (n - first)) - 1u); };
+        const bool done0 = first0 != kNoBlock && have0 == full_mask(first0), done1 = first1 != kNoBlock && have1 == full_mask(first1);
+        if (done0) flush_block(first0, have0);
+        if (done1) flush_block(first1, have1);
+        __syncwarp();
+        if (lane == 0) { ss[0] = done0 ? kNoBlock : first0; ss[1] = done0 ? 0u : have0; ss[2] = done1 ? kNoBlock : first1; ss[3] = done1 ? 0u : have1; }
+        __syncwarp();
       }
       if (!warp_done) {
         if (consumed == blk_count) {       // resident block used up (or nothing loaded yet): move to the next one
@@ -427,12 +435,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
             blk_first = (uint32_t)first;
             blk_count = (n - blk_first) < 32u ? (n - blk_first) : 32u;
             consumed = 0;
-            if (GATHER == 2) {   // the new block needs a staging slot: a free one, else the older block is flushed as far as it got
-              if (slot_blk0 >= 0 && slot_blk1 >= 0) {
-                if (slot_blk0 < slot_blk1) { flush_slot(0, slot_blk0, slot_have0); slot_blk0 = -1; slot_have0 = 0; }
-                else { flush_slot(1, slot_blk1, slot_have1); slot_blk1 = -1; slot_have1 = 0; }
-              }
-              if (slot_blk0 < 0) slot_blk0 = blk; else slot_blk1 = blk;
+            if (GATHER == 2) {   // the new block becomes tracked: in a free slot, else the older block is sent as far as it got
+              uint32_t* ss = s_slot[threadIdx.x >> 5];
+              const uint32_t f0 = ss[0], h0 = ss[1], f1 = ss[2], h1 = ss[3];
+              int use = f0 == kNoBlock ? 0 : (f1 == kNoBlock ? 1 : (f0 < f1 ? 0 : 1));
+              if (f0 != kNoBlock && f1 != kNoBlock) flush_block(use == 0 ? f0 : f1, use == 0 ? h0 : h1);
+              __syncwarp();
+              if (lane == 0) { ss[2 * use] = blk_first; ss[2 * use + 1] = 0u; }
+              __syncwarp();
             }
           }
         }
@@ -441,7 +451,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
           const uint32_t rank = __popc(idle & lt_mask);
           if (state == EMPTY && rank < avail) {
             ray_index = blk_first + consumed + rank;
-            ray_blk = blk;
             bool valid = true;
             if (K > 1) valid = (p.valid == nullptr) || (p.valid[ray_index] == -1);   // inactive lanes stay untouched
             if (valid) {
@@ -514,21 +523,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         __shared__ unsigned long long s_best[TRACE_WARPS][32];
         const int wi = threadIdx.x >> 5;
         const bool isT = tracing && tgy != 0;
-        const int cnt = isT ? min(__popc(tgy), RTK_SPREAD_PER_LANE) : 0;   // items this lane queues now; the rest waits for the next step
+        const int cnt = isT ? __popc(tgy) : 0;
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-        const int slot = incl - cnt;                            // first queue slot of this lane's items
+        int slot = incl - cnt;                                  // first queue slot of this lane's items
         const int total = min(__shfl_sync(FULL, incl, 31), 32);
         s_best[wi][lane] = ~0ull;
-#pragma unroll
-        for (int k = 0; k < RTK_SPREAD_PER_LANE; ++k)           // highest bit first = the sequential test order (predicated, no divergent loop)
-          if (k < cnt && slot + k < 32) {
-            const int tb = 31 - __clz((int)tgy);
-            tgy &= ~(1u << tb);
-            s_tri[wi][slot + k] = tgx + (uint32_t)tb;
-            s_owner[wi][slot + k] = (uint32_t)lane;
-          }
+        // (a predicated, unrolled version of this loop -- 3, 4 or 6 items per lane -- measured 1-5 % slower, r2_ab_runs.txt run 7)
+        while (isT && tgy != 0 && slot < 32) {                  // highest bit first = the sequential test order
+          const int tb = 31 - __clz((int)tgy);
+          tgy &= ~(1u << tb);
+          s_tri[wi][slot] = tgx + (uint32_t)tb;
+          s_owner[wi][slot] = (uint32_t)lane;
+          ++slot;
+        }
         __syncwarp();
         const bool work = lane < total;
         const uint32_t ti = work ? s_tri[wi][lane] : 0u;
@@ -613,9 +622,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
       else state = DONE;
     }
   }
-  if (GATHER == 2) {   // every block is complete by now and has left; this only covers a slot that never filled (n == 0 tail)
-    if (slot_blk0 >= 0 && slot_have0) flush_slot(0, slot_blk0, slot_have0);
-    if (slot_blk1 >= 0 && slot_have1) flush_slot(1, slot_blk1, slot_have1);
+  if (GATHER == 2) {   // every block is complete by now and has left; this only covers a block that never filled
+    const uint32_t* ss = s_slot[threadIdx.x >> 5];
+    if (ss[0] != kNoBlock && ss[1]) flush_block(ss[0], ss[1]);
+    if (ss[2] != kNoBlock && ss[3]) flush_block(ss[2], ss[3]);
   }
   if (STATS) {
 #pragma unroll
