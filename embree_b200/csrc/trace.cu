@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
 #endif
 
   // hit epilogue of one terminated ray (intersector_epilog.h:285-299; occluded: bvh_intersector1.cpp:186-188)
-  auto write_back = [&](float* rec) {
+  // `rec_dst`: where the compact 32-byte record goes (GATHER), chosen by the caller
+  auto write_back = [&](void* rec_dst) {
     float cngx = 0.0f, cngy = 0.0f, cngz = 0.0f;
     uint32_t cprim = kInvalidID, cgeom = kInvalidID;
     if (found) {
@@ -323,10 +324,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         cngx = hit.ngx; cngy = hit.ngy; cngz = hit.ngz; cprim = hit.primID; cgeom = hit.geomID;
       }
     }
-    if (GATHER) {   // a miss (also: empty scene) yields {tfar, 0.., -1, -1}
-      rec[0] = tfar_tri; rec[1] = cngx; rec[2] = cngy; rec[3] = cngz; rec[4] = found ? hit_u : 0.0f; rec[5] = found ? hit_v : 0.0f;
-      rec[6] = __uint_as_float(cprim); rec[7] = __uint_as_float(cgeom);
-    }
+    if (GATHER)   // one 256-bit store (STG.256, new on sm_100): a full 32-byte sector; a miss (also: empty scene) yields {tfar, 0.., -1, -1}
+      store_256(rec_dst, tfar_tri, cngx, cngy, cngz, found ? hit_u : 0.0f, found ? hit_v : 0.0f, __uint_as_float(cprim), __uint_as_float(cgeom));
   };
   // GATHER 2: send the arrived records of a tracked block from the staging buffer to the gather buffer, lane i = record i
   auto flush_block = [&](uint32_t first, unsigned have) {
@@ -399,22 +398,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     if (idle && (__popc(idle) >= refill_min || idle == FULL)) {
       // (Issuing the record fetches of the write-back together with the ray fetches of the refill -- one latency instead
       // of two -- was measured 10 % SLOWER, profiles/r2_ab_runs.txt run 3: the extra live registers spill in the node step.)
-      float rec[8];
       const bool has_rec = state == DONE;
-      if (has_rec) { write_back(rec); state = EMPTY; }
-      if (GATHER == 1) {
-        // one 256-bit store per record (STG.256, new on sm_100): over NVLink the record travels as ONE full 32-byte sector
-        if (has_rec) store_256(static_cast<char*>(p.compact_out) + (size_t)ray_index * 32, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
+      int slot = -1;
+      uint32_t first0 = 0, first1 = 0;
+      uint32_t* ss = s_slot[GATHER == 2 ? (threadIdx.x >> 5) : 0];
+      if (GATHER == 2) {
+        first0 = ss[0]; first1 = ss[2];
+        const uint32_t my_first = ray_index & ~31u;
+        slot = !has_rec ? -1 : (my_first == first0 ? 0 : (my_first == first1 ? 1 : -1));
+      }
+      if (has_rec) {
+        // GATHER 1: straight to the gather buffer.  GATHER 2: records of a tracked block go to the local staging buffer,
+        // stragglers of a block that is no longer tracked straight to the gather buffer.
+        char* dst = GATHER ? static_cast<char*>((GATHER == 2 && slot >= 0) ? p.stage : p.compact_out) + (size_t)ray_index * 32 : nullptr;
+        write_back(dst);
+        state = EMPTY;
       }
       if (GATHER == 2) {
-        uint32_t* ss = s_slot[threadIdx.x >> 5];
-        const uint32_t first0 = ss[0], first1 = ss[2];
-        const uint32_t my_first = ray_index & ~31u;
-        const int slot = !has_rec ? -1 : (my_first == first0 ? 0 : (my_first == first1 ? 1 : -1));
-        if (has_rec) {   // tracked block: local staging buffer; straggler of a block that is no longer tracked: straight to the gather buffer
-          char* dst = static_cast<char*>(slot >= 0 ? p.stage : p.compact_out) + (size_t)ray_index * 32;
-          store_256(dst, rec[0], rec[1], rec[2], rec[3], rec[4], rec[5], rec[6], rec[7]);
-        }
         const unsigned have0 = ss[1] | __reduce_or_sync(FULL, slot == 0 ? 1u << (ray_index & 31u) : 0u);
         const unsigned have1 = ss[3] | __reduce_or_sync(FULL, slot == 1 ? 1u << (ray_index & 31u) : 0u);
         auto full_mask = [&](uint32_t first) -> unsigned { return (n - first) >= 32u ? 0xFFFFFFFFu : ((1u << (n - first)) - 1u); };
