@@ -13,3 +13,25 @@ ln -sf ../../../embree_b200/csrc/libembree4_b200.so _bin/libembree4.so
 g++ -O1 -std=c++11 -I"$REF/include" -I"$GEN" -o _bin/embree_minimal "$REF/tutorials/minimal/minimal.cpp" \
     -L_bin -lembree4 -Wl,-rpath,'$ORIGIN/../../../embree_b200/csrc'
 echo built tests/link_compat/_bin/embree_minimal
+
+# BASELINE configs[0]: the reference's tutorial device code tutorials/triangle_geometry/triangle_geometry_device.cpp (cube +
+# ground plane, rtcTraversableIntersect1 + rtcTraversableOccluded1 per pixel in its own tile loop), compiled untouched
+# together with the reference's sys / tasking sources it needs and OUR small host driver (tutorial_host.cpp: what
+# tutorial.cpp would provide), linked (a) against libembree4_b200.so -> _bin/embree_triangle_geometry (runs on the GPU
+# box) and (b) against the unmodified reference library -> the golden frame tests/golden/triangle_geometry_160x120.raw.
+GENR=../../oracle/_ref/gen_rel
+INC="-I$REF -I$REF/include -I$GENR/include -I$GENR/include/embree4 -I$GENR -DTASKING_INTERNAL"
+SYS="$REF/common/sys/sysinfo.cpp $REF/common/sys/alloc.cpp $REF/common/sys/thread.cpp $REF/common/sys/mutex.cpp $REF/common/sys/condition.cpp
+     $REF/common/sys/barrier.cpp $REF/common/sys/estring.cpp $REF/common/sys/regression.cpp $REF/common/tasking/taskschedulerinternal.cpp
+     $REF/common/math/constants.cpp $REF/tutorials/common/alloc/alloc.cpp"
+if [ ! -x _bin/embree_triangle_geometry ] || [ tutorial_host.cpp -nt _bin/embree_triangle_geometry ]; then
+  g++ -O1 -std=c++17 -w $INC -o _bin/embree_triangle_geometry tutorial_host.cpp "$REF/tutorials/triangle_geometry/triangle_geometry_device.cpp" $SYS \
+      -L_bin -lembree4 -lpthread -Wl,-rpath,'$ORIGIN/../../../embree_b200/csrc'
+  echo built tests/link_compat/_bin/embree_triangle_geometry
+fi
+if [ -f ../../oracle/_ref/libembree4.so.4 ] && [ ! -f ../golden/triangle_geometry_160x120.raw ]; then
+  g++ -O1 -std=c++17 -w $INC -o _bin/ref_triangle_geometry tutorial_host.cpp "$REF/tutorials/triangle_geometry/triangle_geometry_device.cpp" $SYS \
+      -L../../oracle/_ref -l:libembree4.so.4 -lpthread -Wl,-rpath,'$ORIGIN/../../../oracle/_ref'
+  _bin/ref_triangle_geometry ../golden/triangle_geometry_160x120.raw 160 120 4
+  rm -f _bin/ref_triangle_geometry
+fi

@@ -35,3 +35,25 @@ def test_reference_tutorial_runs_on_the_gpu():
     out = subprocess.run([EXE], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120).stdout
     assert "Found intersection on geometry 0, primitive 0 at tfar=1.000000" in out, out
     assert "Did not find any intersection." in out, out
+
+
+TUT = os.path.join(ROOT, "tests", "link_compat", "_bin", "embree_triangle_geometry")
+GOLDEN_FRAME = os.path.join(ROOT, "tests", "golden", "triangle_geometry_160x120.raw")
+
+
+@pytest.mark.gpu
+def test_triangle_geometry_tutorial_renders_the_reference_frame(tmp_path):
+    """BASELINE configs[0]: the reference's tutorials/triangle_geometry device code (its own multi-threaded tile loop of
+    rtcTraversableIntersect1 + rtcTraversableOccluded1 per pixel), compiled untouched and linked against libembree4_b200.so,
+    renders the frame the same code produces with the unmodified reference library -- pixel for pixel."""
+    import numpy as np
+    _ensure_built()
+    if not os.path.exists(TUT):
+        pytest.skip("tutorial binary not built")
+    out = str(tmp_path / "frame.raw")
+    r = subprocess.run([TUT, out, "160", "120", "4"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "device error 0" in r.stdout, r.stdout
+    got = np.fromfile(out, np.int32)
+    want = np.fromfile(GOLDEN_FRAME, np.int32)
+    assert got.shape == want.shape and len(np.unique(want)) >= 5
+    assert (got != want).sum() == 0, f"{(got != want).sum()} of {got.size} pixels differ"
