@@ -724,39 +724,6 @@ struct u32x4 { uint32_t x, y, z, w; };
 struct NodeW { uint32_t w[24]; };   // one node in registers (three 256-bit loads)
 struct TravStats { uint32_t nodes, tris; };
 
-// two independent fp32 FMAs / multiplies with a shared scalar factor in ONE instruction on sm_100a (fma.rn.f32x2 -> FFMA2,
-// mul.rn.f32x2 -> FMUL2; same IEEE results as the scalar forms): half the issue slots for the 48 plane evaluations of a node
-#ifndef RTK_FFMA2
-#define RTK_FFMA2 3   // A/B switch: bit 0 = packed FMAs for the entry planes, bit 1 = for the exit planes, bit 2 = packed pad multiply
-#endif
-template <bool PACKED>
-RT_HD void fma2_bcast(float& d0, float& d1, float a0, float a1, float b, float c) {
-#if defined(__CUDA_ARCH__)
-  if (!PACKED) { d0 = fma_rn(a0, b, c); d1 = fma_rn(a1, b, c); return; }
-  unsigned long long A, B, C, D;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(C) : "f"(c));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(C));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
-#else
-  d0 = fma_rn(a0, b, c); d1 = fma_rn(a1, b, c);
-#endif
-}
-template <bool PACKED>
-RT_HD void mul2_bcast(float& d0, float& d1, float a0, float a1, float b) {
-#if defined(__CUDA_ARCH__)
-  if (!PACKED) { d0 = mul_rn(a0, b); d1 = mul_rn(a1, b); return; }
-  unsigned long long A, B, D;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
-#else
-  d0 = mul_rn(a0, b); d1 = mul_rn(a1, b);
-#endif
-}
-
 // Slab test of the 8 quantised children of one node; returns the hit mask in the layout
 // [31:24] internal children ordered by traversal priority (slot s at bit 24 + (s ^ oct_inv), oct_inv = 7 - ray octant),
 // [23:0] one bit per triangle of the node's leaf slots.
@@ -780,25 +747,23 @@ RT_HD uint32_t node_hitmask(const uint32_t* w, float ox, float oy, float oz, flo
     const uint32_t ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
     const uint32_t nz = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
 #pragma unroll
-    for (int j = 0; j < 4; j += 2) {   // children j, j+1: the six plane evaluations of both go through packed fp32 FMAs
+    for (int j = 0; j < 4; ++j) {
       const int sh = 8 * j;
-      float tnx[2], tny[2], tnz[2], tfx[2], tfy[2], tfz[2], tmax[2];
-      fma2_bcast<(RTK_FFMA2 & 1) != 0>(tnx[0], tnx[1], (float)((nx >> sh) & 0xFFu), (float)((nx >> (sh + 8)) & 0xFFu), sx, bx);
-      fma2_bcast<(RTK_FFMA2 & 1) != 0>(tny[0], tny[1], (float)((ny >> sh) & 0xFFu), (float)((ny >> (sh + 8)) & 0xFFu), sy, by);
-      fma2_bcast<(RTK_FFMA2 & 1) != 0>(tnz[0], tnz[1], (float)((nz >> sh) & 0xFFu), (float)((nz >> (sh + 8)) & 0xFFu), sz, bz);
-      fma2_bcast<(RTK_FFMA2 & 2) != 0>(tfx[0], tfx[1], (float)((fx >> sh) & 0xFFu), (float)((fx >> (sh + 8)) & 0xFFu), sx, bx);
-      fma2_bcast<(RTK_FFMA2 & 2) != 0>(tfy[0], tfy[1], (float)((fy >> sh) & 0xFFu), (float)((fy >> (sh + 8)) & 0xFFu), sy, by);
-      fma2_bcast<(RTK_FFMA2 & 2) != 0>(tfz[0], tfz[1], (float)((fz >> sh) & 0xFFu), (float)((fz >> (sh + 8)) & 0xFFu), sz, bz);
+      // (packed fp32 FMAs -- fma.rn.f32x2 / FFMA2 on sm_100a, two children per instruction -- were measured 3-8 % SLOWER:
+      // the aligned register pairs they need add spills in this loop, profiles/r2_ab_runs.txt run 10)
+      const float tnx = fma_rn((float)((nx >> sh) & 0xFFu), sx, bx);
+      const float tny = fma_rn((float)((ny >> sh) & 0xFFu), sy, by);
+      const float tnz = fma_rn((float)((nz >> sh) & 0xFFu), sz, bz);
+      const float tfx = fma_rn((float)((fx >> sh) & 0xFFu), sx, bx);
+      const float tfy = fma_rn((float)((fy >> sh) & 0xFFu), sy, by);
+      const float tfz = fma_rn((float)((fz >> sh) & 0xFFu), sz, bz);
+      const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tnear));
       // pad the exit distance by 2 ulp so rounding in the FMAs can never cull a box that exact arithmetic
       // accepts (the reference's robust mode pads by 3 ulp, node_intersector1.h:106-110)
-      mul2_bcast<(RTK_FFMA2 & 4) != 0>(tmax[0], tmax[1], fminf(fminf(tfx[0], tfy[0]), fminf(tfz[0], tfar)), fminf(fminf(tfx[1], tfy[1]), fminf(tfz[1], tfar)), 1.0000003f);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const float tmin = fmaxf(fmaxf(tnx[c], tny[c]), fmaxf(tnz[c], tnear));
-        if (tmin <= tmax[c]) {
-          leaf |= node_leafmask_raw(w, 4 * half + j + c);
-          slots |= 1u << (4 * half + j + c);
-        }
+      const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar)) * 1.0000003f;
+      if (tmin <= tmax) {
+        leaf |= node_leafmask_raw(w, 4 * half + j);
+        slots |= 1u << (4 * half + j);
       }
     }
   }

@@ -152,6 +152,9 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 #ifndef RTK_TOP_SMEM
 #define RTK_TOP_SMEM 0     // EXPERIMENT: this many nodes from the top of the (breadth-first) node array are staged in shared memory
 #endif                     // with one TMA bulk copy per CTA (cp.async.bulk + mbarrier); 73 = root + 8 + 64.  Measured: see DESIGN.md
+#ifndef RTK_LANE_SMEM
+#define RTK_LANE_SMEM 1    // per-lane state that only the hit update and the write-back touch (u, v, winning record, ray index)
+#endif                     // lives in shared memory instead of registers
 #ifndef RTK_TRI2
 #define RTK_TRI2 1   // a lane with two or more pending triangles tests two per triangle step (both records fetched together)
 #endif
@@ -201,10 +204,22 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   Ray r;
   float idx = 0, idy = 0, idz = 0, tfar_tri = 0;
   uint32_t oct = 0;
-  float hit_u = 0, hit_v = 0;            // closest hit so far: t = tfar_tri, barycentrics, triangle record index
+  // closest hit so far: t = tfar_tri (register), barycentrics and the winning record's index; the ray's index in the stream.
+  // These four are written on a hit / at refill and read at write-back only: with 64 registers per thread they are
+  // better placed in shared memory ([field][thread], conflict-free) than left to the register allocator, which spills
+  // other values inside the node step otherwise.
+#if RTK_LANE_SMEM
+  __shared__ uint32_t s_lane[4][TRACE_THREADS];
+#define hit_u (reinterpret_cast<float*>(s_lane[0])[threadIdx.x])
+#define hit_v (reinterpret_cast<float*>(s_lane[1])[threadIdx.x])
+#define hit_tri (s_lane[2][threadIdx.x])
+#define ray_index (s_lane[3][threadIdx.x])
+#else
+  float hit_u = 0, hit_v = 0;
   uint32_t hit_tri = 0;
-  bool found = false;
   uint32_t ray_index = 0;
+#endif
+  bool found = false;
   uint32_t ngx = 0, ngy = 0, tgx = 0, tgy = 0;
   uint32_t top_x = 0, top_y = 0;          // register copy of the newest stack entry (top_y == 0: none)
   // older entries: the first RTK_SMEM_STACK per lane in shared memory ([entry][thread]: conflict-free 8-byte accesses),
@@ -637,6 +652,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
     if (lane == 0) { atomicAdd(&p.stat[0], st_rays); atomicAdd(&p.stat[1], st_nodes); atomicAdd(&p.stat[2], st_tris); }
   }
 }
+
+#if RTK_LANE_SMEM
+#undef hit_u
+#undef hit_v
+#undef hit_tri
+#undef ray_index
+#endif
 
 static int g_num_sms = 0;
 static Tuning g_tuning;
