@@ -209,16 +209,32 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   // better placed in shared memory ([field][thread], conflict-free) than left to the register allocator, which spills
   // other values inside the node step otherwise.
 #if RTK_LANE_SMEM
-  __shared__ uint32_t s_lane[4][TRACE_THREADS];
+  __shared__ uint32_t s_lane[9][TRACE_THREADS];   // 0 u, 1 v, 2 winning record, 3 ray index, 4-6 ray direction, 7 ray mask, 8 the ray's own tfar
 #define hit_u (reinterpret_cast<float*>(s_lane[0])[threadIdx.x])
 #define hit_v (reinterpret_cast<float*>(s_lane[1])[threadIdx.x])
 #define hit_tri (s_lane[2][threadIdx.x])
 #define ray_index (s_lane[3][threadIdx.x])
+  // The ray's direction, mask and original tfar are only needed by triangle / curve tests: the node step works with
+  // org, 1/dir, tnear and the current hit distance.  They are parked in shared memory too (read by the SPREAD workers by
+  // owner index -- instead of five shuffles -- and by the non-SPREAD test of the lane itself).
+#define RAY_DX(t) (reinterpret_cast<float*>(s_lane[4])[t])
+#define RAY_DY(t) (reinterpret_cast<float*>(s_lane[5])[t])
+#define RAY_DZ(t) (reinterpret_cast<float*>(s_lane[6])[t])
+#define RAY_MASK(t) (s_lane[7][t])
+#define RAY_TFAR(t) (reinterpret_cast<float*>(s_lane[8])[t])
 #else
   float hit_u = 0, hit_v = 0;
   uint32_t hit_tri = 0;
   uint32_t ray_index = 0;
+#error "RTK_LANE_SMEM=0 is no longer supported (kept only in the history of profiles/r2_ab_runs.txt)"
 #endif
+  // this lane's ray with the parked fields filled in (non-SPREAD triangle / curve tests, ROBUST write-back)
+  auto full_ray = [&]() -> Ray {
+    Ray q = r;
+    q.dx = RAY_DX(threadIdx.x); q.dy = RAY_DY(threadIdx.x); q.dz = RAY_DZ(threadIdx.x);
+    q.mask = RAY_MASK(threadIdx.x); q.tfar = RAY_TFAR(threadIdx.x);
+    return q;
+  };
   bool found = false;
   uint32_t ngx = 0, ngy = 0, tgx = 0, tgy = 0;
   uint32_t top_x = 0, top_y = 0;          // register copy of the newest stack entry (top_y == 0: none)
@@ -308,13 +324,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
           hit.geomID = d.geomID;
           if (GENERAL == 2 && d.is_curve) {   // the normal of a curve hit depends on which surface was hit: re-run the (deterministic) test at the hit distance
             CurveHit ch;
-            curve_record_test(d, r, tfar_tri, a, b, c, ch);
+            curve_record_test(d, full_ray(), tfar_tri, a, b, c, ch);
             hit.ngx = ch.ngx; hit.ngy = ch.ngy; hit.ngz = ch.ngz;
             is_curve = true;
           }
           if (d.has_xfm) {
             instID = d.instID; instPrimID = 0u;   // instance_id_stack::push(context, instID, 0)
-            if (ROBUST) { Ray lr = r; to_object_space(d, lr); lox = lr.ox; loy = lr.oy; loz = lr.oz; }
+            if (ROBUST) { Ray lr = full_ray(); to_object_space(d, lr); lox = lr.ox; loy = lr.oy; loz = lr.oz; }
           }
         }
         if (is_curve) {
@@ -356,20 +372,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
 
   // one triangle record against this lane's ray (closest hit: shrinks tfar_tri; any hit: terminates the ray)
   auto test_tri = [&](uint32_t ti, const uint4& a, const uint4& b, const uint4& c) {
-    Ray lr = r;
-    bool visible = (c.w & r.mask) != 0;              // ray mask (intersector_epilog.h:256-262)
+    Ray lr = full_ray();
+    const Ray wr = lr;                               // world-space ray (curves are not instanced)
+    bool visible = (c.w & lr.mask) != 0;             // ray mask (intersector_epilog.h:256-262)
     if (GENERAL) {   // b.w = descriptor index: instance mask (instance_intersector.cpp:19-22) + object-space ray
       const GeomDesc& d = p.descs[b.w];
       if (GENERAL == 2 && d.is_curve) {   // RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE: cone-sphere test, u along the segment, v = 0
         CurveHit ch;
-        if (visible && curve_record_test(d, r, tfar_tri, a, b, c, ch)) {
+        if (visible && curve_record_test(d, wr, tfar_tri, a, b, c, ch)) {
           found = true;
           if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
           else { tfar_tri = ch.t; hit_u = ch.u; hit_v = 0.0f; hit_tri = ti; }
         }
         return;
       }
-      visible = visible && (d.inst_mask & r.mask) != 0;
+      visible = visible && (d.inst_mask & lr.mask) != 0;
       if (d.has_xfm) to_object_space(d, lr);
     }
     if (ROBUST) {   // RTC_SCENE_FLAG_ROBUST: the record holds v0, v1, v2; watertight Pluecker test
@@ -476,6 +493,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
               // empty scene / already occluded rays terminate at once (bvh_intersector1.cpp:39,128-129); they still
               // pass through DONE so that a gather buffer receives their miss record
               const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
+              RAY_DX(threadIdx.x) = r.dx; RAY_DY(threadIdx.x) = r.dy; RAY_DZ(threadIdx.x) = r.dz;
+              RAY_MASK(threadIdx.x) = r.mask; RAY_TFAR(threadIdx.x) = r.tfar;
               idx = rcp_safe_fast(r.dx); idy = rcp_safe_fast(r.dy); idz = rcp_safe_fast(r.dz);
               oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
               tfar_tri = r.tfar;
@@ -559,16 +578,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         const int owner = work ? (int)s_owner[wi][lane] : lane;
         Ray lr;
         lr.ox = __shfl_sync(FULL, r.ox, owner); lr.oy = __shfl_sync(FULL, r.oy, owner); lr.oz = __shfl_sync(FULL, r.oz, owner);
-        lr.dx = __shfl_sync(FULL, r.dx, owner); lr.dy = __shfl_sync(FULL, r.dy, owner); lr.dz = __shfl_sync(FULL, r.dz, owner);
+        const int ot = (threadIdx.x & ~31) + owner;             // the owner's slot of the parked ray fields
+        lr.dx = RAY_DX(ot); lr.dy = RAY_DY(ot); lr.dz = RAY_DZ(ot);
         lr.tnear = __shfl_sync(FULL, r.tnear, owner);
         // The winner must not depend on which other rays share the warp (an owner's items may be split over two steps
         // when the queue is full): a triangle is a candidate when it passes the test against the ray's ORIGINAL tfar and
         // its final t is <= the owner's current hit distance; among candidates the smallest t wins, the later item on
         // equal t.  This is the minimum over all tested triangles whatever the batching, so the batched entry points,
         // the packet entry points and the host-pointer pipeline return bit-identical hits for the same ray.
-        const float o_tfar = __shfl_sync(FULL, r.tfar, owner);
+        const float o_tfar = RAY_TFAR(ot);
         const float o_best = __shfl_sync(FULL, tfar_tri, owner);
-        const uint32_t o_mask = __shfl_sync(FULL, r.mask, owner);
+        const uint32_t o_mask = RAY_MASK(ot);
         float w_u = 0.0f, w_v = 0.0f;
         unsigned long long key = ~0ull;
         if (work) {
@@ -658,6 +678,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
 #undef hit_v
 #undef hit_tri
 #undef ray_index
+#undef RAY_DX
+#undef RAY_DY
+#undef RAY_DZ
+#undef RAY_MASK
+#undef RAY_TFAR
 #endif
 
 static int g_num_sms = 0;
