@@ -377,6 +377,40 @@ RT_HD bool curve_test(float ox, float oy, float oz, float dx, float dy, float dz
   return true;
 }
 
+// flat linear curve segment (RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE): FlatLinearCurveIntersector1::intersect
+// (kernels/geometry/line_intersector.h:38-89) with CurvePrecalculations1 (curve_intersector_precalculations.h:15-28) restated
+// for one segment -- a ray-facing ribbon: the end points go to ray space (frame of the normalised direction, z = ray
+// parameter), the closest point of the projected segment to the origin decides.  Explicitly rounded like curve_test.
+RT_HD bool flat_curve_test(float ox, float oy, float oz, float dx_, float dy_, float dz_, float tnear, float tfar, const CurveVtx& v0,
+                           const CurveVtx& v1, CurveHit& h) {
+  const float depth_scale = rcp_rn(sqrtf(dot3(dx_, dy_, dz_, dx_, dy_, dz_)));
+  const float Nx = mul_rn(depth_scale, dx_), Ny = mul_rn(depth_scale, dy_), Nz = mul_rn(depth_scale, dz_);
+  // frame(N) (linearspace3.h:117-124): dx0 = (0, N.z, -N.y), dx1 = (-N.z, 0, N.x)
+  const bool first = dot3(0.0f, Nz, -Ny, 0.0f, Nz, -Ny) > dot3(-Nz, 0.0f, Nx, -Nz, 0.0f, Nx);
+  const float sx = first ? 0.0f : -Nz, sy = first ? Nz : 0.0f, sz = first ? -Ny : Nx;
+  const float il = rcp_rn(sqrtf(dot3(sx, sy, sz, sx, sy, sz)));
+  const float ax = mul_rn(sx, il), ay = mul_rn(sy, il), az = mul_rn(sz, il);                                  // dx
+  float bx = msub(Ny, az, mul_rn(Nz, ay)), by = msub(Nz, ax, mul_rn(Nx, az)), bz = msub(Nx, ay, mul_rn(Ny, ax));   // cross(N, dx)
+  const float jl = rcp_rn(sqrtf(dot3(bx, by, bz, bx, by, bz)));
+  bx = mul_rn(bx, jl); by = mul_rn(by, jl); bz = mul_rn(bz, jl);                                              // dy
+  const float zx = mul_rn(Nx, depth_scale), zy = mul_rn(Ny, depth_scale), zz = mul_rn(Nz, depth_scale);      // vz
+  const float a0 = sub_rn(v0.x, ox), a1 = sub_rn(v0.y, oy), a2 = sub_rn(v0.z, oz);
+  const float c0 = sub_rn(v1.x, ox), c1 = sub_rn(v1.y, oy), c2 = sub_rn(v1.z, oz);
+  const float p0x = dot3(a0, a1, a2, ax, ay, az), p0y = dot3(a0, a1, a2, bx, by, bz), p0z = dot3(a0, a1, a2, zx, zy, zz);
+  const float p1x = dot3(c0, c1, c2, ax, ay, az), p1y = dot3(c0, c1, c2, bx, by, bz), p1z = dot3(c0, c1, c2, zx, zy, zz);
+  const float vx = sub_rn(p1x, p0x), vy = sub_rn(p1y, p0y), vz = sub_rn(p1z, p0z), vw = sub_rn(v1.r, v0.r);
+  const float d0 = fma_rn(-p0x, vx, mul_rn(-p0y, vy)), d1 = fma_rn(vx, vx, mul_rn(vy, vy));
+  const float u = fminf(fmaxf(mul_rn(d0, rcp_rn(d1)), 0.0f), 1.0f);
+  const float px = fma_rn(u, vx, p0x), py = fma_rn(u, vy, p0y), t = fma_rn(u, vz, p0z), rr = fma_rn(u, vw, v0.r);
+  const float d2 = fma_rn(px, px, mul_rn(py, py));
+  if (!((d2 <= mul_rn(rr, rr)) & (tnear <= t) & (t <= tfar))) return false;
+  if (!(t > mul_rn(mul_rn(2.0f, rr), depth_scale))) return false;      // EMBREE_CURVE_SELF_INTERSECTION_AVOIDANCE_FACTOR = 2.0
+  const float Tx = sub_rn(v1.x, v0.x), Ty = sub_rn(v1.y, v0.y), Tz = sub_rn(v1.z, v0.z);
+  if (!((Tx != 0.0f) | (Ty != 0.0f) | (Tz != 0.0f))) return false;     // denormalised segment
+  h.t = t; h.u = u; h.ngx = Tx; h.ngy = Ty; h.ngz = Tz;
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Node8 encoding (build side)
 // ------------------------------------------------------------------------------------------------

@@ -314,11 +314,11 @@ void commit_scene(SceneImpl* s) {
     d.verts = static_cast<const uint8_t*>(dv); d.idx = static_cast<const uint8_t*>(di); d.flags = static_cast<const uint8_t*>(df);
     d.vstride = g->vertices.stride; d.istride = g->indices.stride;
     d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)nsegs;
-    d.geomID = geomID; d.mask = g->mask; d.is_curve = 1;
+    d.geomID = geomID; d.mask = g->mask; d.is_curve = g->type == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE ? 2 : 1;
     descs.push_back(d);
   };
   auto add_mesh = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
-    if (g->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE) {
+    if (g->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE || g->type == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE) {
       if (xfm) fail(RTC_ERROR_INVALID_OPERATION, "instanced curve geometries are not supported by the B200 back-end");
       add_curves(g, geomID);
       return;
@@ -739,8 +739,9 @@ void rtcReleaseBuffer(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; AP
 RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
   API_BEGIN
   VERIFY_HANDLE(h);
-  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE && type != RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE)
-    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD, _ROUND_LINEAR_CURVE and _INSTANCE are supported by the B200 back-end");
+  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE && type != RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE &&
+      type != RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE)
+    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD, _ROUND_LINEAR_CURVE, _FLAT_LINEAR_CURVE and _INSTANCE are supported by the B200 back-end");
   GeometryImpl* g = new GeometryImpl(D(h));
   g->type = type;
   return reinterpret_cast<RTCGeometry>(g);
@@ -768,7 +769,7 @@ void rtcSetGeometryBuildQuality(RTCGeometry g, enum RTCBuildQuality q) {
 static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFormat format, BufferImpl* buf, size_t off, size_t stride, size_t num) {
   // scene_triangle_mesh.cpp:35-80, scene_quad_mesh.cpp:35-80
   if (g->type == RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
-  const bool curve = g->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE;   // scene_line_segments.cpp:35-100
+  const bool curve = g->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE || g->type == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE;   // scene_line_segments.cpp:35-100
   if (curve && type == RTC_BUFFER_TYPE_FLAGS) {
     if (format != RTC_FORMAT_UCHAR) fail(RTC_ERROR_INVALID_OPERATION, "invalid flag buffer format");
     if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot");
@@ -835,7 +836,7 @@ void* rtcGetGeometryBufferData(RTCGeometry g, enum RTCBufferType type, unsigned 
   if (type == RTC_BUFFER_TYPE_INDEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->indices; }
   else if (type == RTC_BUFFER_TYPE_VERTEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->vertices; }
   else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) { if (slot >= G(g)->attribs.size()) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->attribs[slot]; }
-  else if (type == RTC_BUFFER_TYPE_FLAGS && G(g)->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->flags; }
+  else if (type == RTC_BUFFER_TYPE_FLAGS && (G(g)->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE || G(g)->type == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE)) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->flags; }
   else fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
   return const_cast<char*>(v->data());
   GEOM_END

@@ -29,7 +29,7 @@ struct GeomDesc {
   // round linear curves (RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE): verts = float4 (xyz, radius), idx = first vertex of each
   // segment, ntris = segments; `flags` = one neighbour-flag byte per segment (device).  The vertex buffer stays resident
   // after the build: the trace kernel fetches the neighbour vertices from it.
-  uint32_t is_curve = 0;
+  uint32_t is_curve = 0;   // 1 round linear (cone-sphere), 2 flat linear (ray-facing ribbon)
   const uint8_t* flags = nullptr;
   float xfm[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
   float w2l[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};

@@ -116,6 +116,8 @@ __device__ __forceinline__ void to_object_space(const GeomDesc& d, Ray& r) {
 __device__ __noinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h) {
   const CurveVtx v0{__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(c.x)};
   const CurveVtx v1{__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.y)};
+  if (d.is_curve == 2)   // RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE: ray-facing ribbon, no neighbours involved
+    return flat_curve_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, v0, v1, h);
   const uint32_t vid = c.z & 0x3FFFFFFFu;
   const bool hasL = (c.z >> 30) & 1u, hasR = (c.z >> 31) & 1u;
   CurveVtx vL = v0, vR = v1;

@@ -21,6 +21,7 @@ RTC_BUFFER_TYPE_VERTEX = 1
 RTC_GEOMETRY_TYPE_TRIANGLE = 0
 RTC_GEOMETRY_TYPE_QUAD = 1
 RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE = 16
+RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE = 17
 RTC_GEOMETRY_TYPE_INSTANCE = 121
 RTC_FORMAT_UCHAR = 0x1001
 RTC_FORMAT_UINT = 0x5001
@@ -281,12 +282,13 @@ class RTCLib:
         self.rtcReleaseGeometry(g)
         return gid, (vpad, idx)
 
-    def add_round_linear_curves(self, device, scene, vertices4, indices, flags=None, mask=None, geom_id=None):
-        """RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE with shared FLOAT4 (xyz, radius) vertex / UINT first-vertex index buffers and
-        an optional UCHAR neighbour-flags buffer (tutorials/hair_geometry, curve_geometry).  The arrays must stay alive."""
+    def add_round_linear_curves(self, device, scene, vertices4, indices, flags=None, mask=None, geom_id=None, flat=False):
+        """RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE (flat=True: RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE) with shared FLOAT4 (xyz, radius)
+        vertex / UINT first-vertex index buffers and an optional UCHAR neighbour-flags buffer (tutorials/hair_geometry,
+        curve_geometry).  The arrays must stay alive."""
         v = np.ascontiguousarray(vertices4, np.float32).reshape(-1, 4)
         idx = np.ascontiguousarray(indices, np.uint32).reshape(-1)
-        g = self.rtcNewGeometry(device, RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE)
+        g = self.rtcNewGeometry(device, RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE if flat else RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE)
         self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT4, _ptr(v), 0, 16, v.shape[0])
         self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT, _ptr(idx), 0, 4, idx.shape[0])
         keep = [v, idx]

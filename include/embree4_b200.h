@@ -84,6 +84,7 @@ enum RTCFeatureFlags {
   RTC_FEATURE_FLAG_TRIANGLE = 1 << 1,
   RTC_FEATURE_FLAG_QUAD = 1 << 2,
   RTC_FEATURE_FLAG_ROUND_LINEAR_CURVE = 1 << 6,
+  RTC_FEATURE_FLAG_FLAT_LINEAR_CURVE = 1 << 7,
   RTC_FEATURE_FLAG_INSTANCE = 1 << 23,
   RTC_FEATURE_FLAG_ALL = 0xffffffff
 };
@@ -92,6 +93,7 @@ enum RTCGeometryType {
   RTC_GEOMETRY_TYPE_QUAD = 1,      /* index buffer RTC_FORMAT_UINT4; intersected as the halves (v0,v1,v3), (v2,v1,v3) */
   RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE = 16, /* vertex buffer RTC_FORMAT_FLOAT4 (xyz, radius), index buffer RTC_FORMAT_UINT = first vertex
                                                 of a segment, optional RTC_BUFFER_TYPE_FLAGS (rtcore_geometry.h:27; roundline_intersector.h) */
+  RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE = 17,  /* same buffers, ray-facing ribbons (line_intersector.h) */
   RTC_GEOMETRY_TYPE_INSTANCE = 121 /* single-level instances of triangle scenes (rtcore_geometry.h:51) */
 };
 enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2, RTC_BUFFER_TYPE_FLAGS = 32 };

@@ -59,8 +59,8 @@ def load_golden_curves(name="curves"):
         out.view(np.uint8).reshape(a.shape)[:] = a
         return out
     meshes = [(z[f"v{i}"], z[f"t{i}"], int(z[f"gid{i}"]), int(z[f"mask{i}"])) for i in range(int(z["n_meshes"]))]
-    curves = [(z[f"cv{i}"], z[f"ci{i}"], z[f"cf{i}"] if z[f"cf{i}"].size else None, int(z[f"cgid{i}"]), int(z[f"cmask{i}"]))
-              for i in range(int(z["n_curves"]))]
+    curves = [(z[f"cv{i}"], z[f"ci{i}"], z[f"cf{i}"] if z[f"cf{i}"].size else None, int(z[f"cgid{i}"]), int(z[f"cmask{i}"]),
+               bool(int(z[f"cflat{i}"])) if f"cflat{i}" in z else False) for i in range(int(z["n_curves"]))]
     return dict(meshes=meshes, curves=curves, rays_in=rec(z["rays_in"], RAYHIT_DTYPE), intersect_out=rec(z["intersect_out"], RAYHIT_DTYPE),
                 occluded_out=rec(z["occluded_out"], RAY_DTYPE), bounds=z["bounds"])
 

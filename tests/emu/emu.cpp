@@ -350,3 +350,11 @@ extern "C" int emu_curve_test(const float* ray8, const float* v0, const float* v
   out5[0] = h.t; out5[1] = h.u; out5[2] = h.ngx; out5[3] = h.ngy; out5[4] = h.ngz;
   return 1;
 }
+
+extern "C" int emu_flat_curve_test(const float* ray8, const float* v0, const float* v1, float* out5) {
+  CurveHit h;
+  const CurveVtx a{v0[0], v0[1], v0[2], v0[3]}, b{v1[0], v1[1], v1[2], v1[3]};
+  if (!flat_curve_test(ray8[0], ray8[1], ray8[2], ray8[4], ray8[5], ray8[6], ray8[3], ray8[7], a, b, h)) return 0;
+  out5[0] = h.t; out5[1] = h.u; out5[2] = h.ngx; out5[3] = h.ngy; out5[4] = h.ngz;
+  return 1;
+}

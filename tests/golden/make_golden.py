@@ -128,7 +128,7 @@ def run_curves(name, meshes, curves, rayhits):
     dev = R.new_device(None)
     sc = R.rtcNewScene(dev)
     keep = [R.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in meshes]
-    keep += [R.add_round_linear_curves(dev, sc, cv, ci, cf, mask=mask, geom_id=gid)[1] for (cv, ci, cf, gid, mask) in curves]
+    keep += [R.add_round_linear_curves(dev, sc, c[0], c[1], c[2], mask=c[4], geom_id=c[3], flat=len(c) > 5 and c[5])[1] for c in curves]
     R.rtcCommitScene(sc)
     R.check(dev)
     b = RTCBounds()
@@ -144,9 +144,11 @@ def run_curves(name, meshes, curves, rayhits):
              n_meshes=np.array(len(meshes)), n_curves=np.array(len(curves)))
     for i, (v, t, gid, mask) in enumerate(meshes):
         d[f"v{i}"], d[f"t{i}"], d[f"gid{i}"], d[f"mask{i}"] = v, t, np.array(gid, np.uint32), np.array(mask, np.uint32)
-    for i, (cv, ci, cf, gid, mask) in enumerate(curves):
+    for i, c in enumerate(curves):
+        cv, ci, cf, gid, mask = c[:5]
         d[f"cv{i}"], d[f"ci{i}"], d[f"cgid{i}"], d[f"cmask{i}"] = cv, ci, np.array(gid, np.uint32), np.array(mask, np.uint32)
         d[f"cf{i}"] = np.zeros(0, np.uint8) if cf is None else np.asarray(cf, np.uint8)
+        d[f"cflat{i}"] = np.array(1 if (len(c) > 5 and c[5]) else 0)
     print(f"{name}: {len(rayhits)} rays, hit rate {(out_i['geomID'] != 0xFFFFFFFF).mean():.3f}, curve hits "
           f"{np.isin(out_i['geomID'], [c[3] for c in curves]).mean():.3f}, occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
@@ -171,6 +173,16 @@ def main_curves():
     rays["mask"][::3] = 0x2
     rays["id"] = np.arange(len(rays))
     run_curves("curves", [(v, t, 0, 0xFFFFFFFF)], [(cv, ci, None, 1, 0x3), (cv2, ci2, fl2, 2, 0xFFFFFFFD)], rays)
+    # the same kind of scene with RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE sets (ray-facing ribbons), un-normalised ray directions
+    cv3, ci3, _ = scenes.hair_ball(200, 5, seed=13, width=0.03)
+    rays2 = rays.copy()
+    scale = rng.uniform(0.3, 4.0, len(rays2)).astype(np.float32)
+    for f in ("dir_x", "dir_y", "dir_z"):
+        rays2[f] *= scale
+    rays2["tnear"] = 0.0
+    rays2["tfar"] = np.inf
+    rays2["tfar"][::5] = 1.2 / scale[::5]
+    run_curves("curves_flat", [(v, t, 0, 0xFFFFFFFF)], [(cv3, ci3, None, 1, 0x3, True), (cv2, ci2, None, 2, 0xFFFFFFFD, True)], rays2)
 
 
 def main():

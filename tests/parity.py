@@ -24,6 +24,7 @@ class Oracle:
         d.orc_commit.argtypes = [C.c_void_p]
         d.orc_add_quad_mesh.argtypes = d.orc_add_mesh.argtypes
         d.orc_add_curves.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_uint, C.c_uint]
+        d.orc_add_curves_typed.argtypes = d.orc_add_curves.argtypes + [C.c_int]
         d.orc_add_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
         d.orc_set_robust.argtypes = [C.c_void_p, C.c_int]
         d.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
@@ -60,13 +61,15 @@ class OracleScene:
             self.keep += [v, t]
             (o.d.orc_add_quad_mesh if quad else o.d.orc_add_mesh)(self.h, v.ctypes.data, 12, v.shape[0], t.ctypes.data,
                                                                    16 if quad else 12, t.shape[0], gid, mask)
-        for (cv, ci, cf, gid, mask) in curves:
+        for entry in curves:      # (vertices4, indices, flags or None, geomID, mask[, flat]); flat: RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE
+            cv, ci, cf, gid, mask = entry[:5]
+            flat = len(entry) > 5 and bool(entry[5])
             cv = np.ascontiguousarray(cv, np.float32).reshape(-1, 4)
             ci = np.ascontiguousarray(ci, np.uint32).reshape(-1)
             cf = None if cf is None else np.ascontiguousarray(cf, np.uint8).reshape(-1)
             self.keep += [cv, ci, cf]
-            o.d.orc_add_curves(self.h, cv.ctypes.data, 16, cv.shape[0], ci.ctypes.data, 4, ci.shape[0],
-                               None if cf is None else cf.ctypes.data, gid, mask)
+            o.d.orc_add_curves_typed(self.h, cv.ctypes.data, 16, cv.shape[0], ci.ctypes.data, 4, ci.shape[0],
+                                     None if cf is None else cf.ctypes.data, gid, mask, 1 if flat else 0)
         for (child, xfm, gid, mask) in instances:
             m = np.ascontiguousarray(xfm, np.float32).reshape(12)
             self.keep += [child, m]

@@ -141,7 +141,7 @@ def test_curve_segment_test_equals_oracle(emu, oracle):
     import ctypes as C
     from tests.conftest import load_golden_curves
     g = load_golden_curves()
-    cv, ci, cf, gid, mask = g["curves"][0]
+    cv, ci, cf, gid, mask = g["curves"][0][:5]
     sc = oracle.scene([], curves=[(cv, ci, cf, gid, 0xFFFFFFFF)])
     rays = g["rays_in"][::6].copy()
     rays["mask"] = 0xFFFFFFFF
@@ -172,5 +172,42 @@ def test_curve_segment_test_equals_oracle(emu, oracle):
         got = np.array(best[:5], np.float32).view(np.uint32)
         exp = np.array([w["tfar"], w["u"], w["Ng_x"], w["Ng_y"], w["Ng_z"]], np.float32).view(np.uint32)
         assert (got == exp).all(), (k, best, w)
+    assert hits > 100
+    sc.free()
+
+
+def test_flat_curve_segment_test_equals_oracle(emu, oracle):
+    """rt_core.cuh flat_curve_test (RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE), host instantiation, by brute force over all segments:
+    bit-identical t / u / Ng to the C oracle on the golden rays."""
+    import ctypes as C
+    from tests.conftest import load_golden_curves
+    g = load_golden_curves("curves_flat")
+    cv, ci, cf, gid, mask, flat = g["curves"][0]
+    sc = oracle.scene([], curves=[(cv, ci, cf, gid, 0xFFFFFFFF, True)])
+    rays = g["rays_in"][::5].copy()
+    rays["mask"] = 0xFFFFFFFF
+    want = sc.trace(rays.copy())
+    P = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(C.c_void_p)   # noqa: E731
+    out = (C.c_float * 5)()
+    hits = 0
+    for k in range(len(rays)):
+        r = rays[k]
+        ray = np.array([r["org_x"], r["org_y"], r["org_z"], r["tnear"], r["dir_x"], r["dir_y"], r["dir_z"], r["tfar"]], np.float32)
+        best = None
+        for i in range(len(ci)):
+            v = int(ci[i])
+            if emu.emu_flat_curve_test(P(ray), P(cv[v]), P(cv[v + 1]), out):
+                best = (out[0], out[1], out[2], out[3], out[4])
+                ray[7] = out[0]
+        w = want[k]
+        if best is None:
+            assert w["geomID"] == 0xFFFFFFFF, k
+            continue
+        hits += 1
+        got = np.array(best, np.float32).view(np.uint32)
+        exp = np.array([w["tfar"], w["u"], w["Ng_x"], w["Ng_y"], w["Ng_z"]], np.float32).view(np.uint32)
+        assert got[0] == exp[0], (k, best, w)          # same distance; on an exact tie at a joint u / Ng name the other segment
+        if not (got == exp).all():
+            assert best[1] in (0.0, 1.0) and w["u"] in (0.0, 1.0), (k, best, w)
     assert hits > 100
     sc.free()

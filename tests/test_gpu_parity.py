@@ -527,19 +527,21 @@ def build_curve_scene(lib, dev, meshes, curves, quality=RTC_BUILD_QUALITY_MEDIUM
     sc = lib.rtcNewScene(dev)
     lib.rtcSetSceneBuildQuality(sc, quality)
     keep = [lib.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in meshes]
-    keep += [lib.add_round_linear_curves(dev, sc, cv, ci, cf, mask=mask, geom_id=gid)[1] for (cv, ci, cf, gid, mask) in curves]
+    keep += [lib.add_round_linear_curves(dev, sc, c[0], c[1], c[2], mask=c[4], geom_id=c[3], flat=len(c) > 5 and c[5])[1] for c in curves]
     lib.rtcCommitScene(sc)
     lib.check(dev)
     return sc, keep
 
 
+@pytest.mark.parametrize("name", ["curves", "curves_flat"])
 @pytest.mark.parametrize("quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
-def test_curves_golden_all_entry_points(b200, quality):
-    """RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE (tutorials/hair_geometry's shipped model; roundline_intersector.h) against the
-    reference's own outputs through every entry point: ids exact, t within 1e-4, u along the segment, v = 0, any-hit equal."""
+def test_curves_golden_all_entry_points(b200, quality, name):
+    """RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE (tutorials/hair_geometry's shipped model; roundline_intersector.h) and
+    RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE (line_intersector.h) against the reference's own outputs through every entry point:
+    ids exact, t within 1e-4, u along the segment, v = 0, any-hit equal."""
     from tests.conftest import load_golden_curves
     lib, dev = b200
-    g = load_golden_curves()
+    g = load_golden_curves(name)
     sc, keep = build_curve_scene(lib, dev, g["meshes"], g["curves"], quality)
     b = RTCBounds()
     lib.rtcGetSceneBounds(sc, C.byref(b))
@@ -549,7 +551,7 @@ def test_curves_golden_all_entry_points(b200, quality):
     for mode in MODES:
         got = lib.intersect(sc, g["rays_in"].copy(), mode)
         rep = compare_hits(want, got, TOL)
-        assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 10, (mode, rep)   # ties: joints of two segments
+        assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 40, (mode, rep)   # ties: joints of two segments
         assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= TOL and rep["miss_untouched"], (mode, rep)
         ok = (got["geomID"] == want["geomID"]) & (got["primID"] == want["primID"]) & (got["geomID"] != 0xFFFFFFFF)
         for f in ("Ng_x", "Ng_y", "Ng_z"):

@@ -177,15 +177,17 @@ def test_oracle_quads_and_instances_vs_reference_live(oracle, robust):
     R.rtcReleaseDevice(dev)
 
 
-def test_oracle_curves_vs_golden(oracle):
-    """Round linear curves (roundline_intersector.h restated in oracle/embree_oracle.c) against the reference's own outputs:
-    two curve sets (library-derived and application neighbour flags, geometry masks) around a triangle sphere."""
+@pytest.mark.parametrize("name", ["curves", "curves_flat"])
+def test_oracle_curves_vs_golden(oracle, name):
+    """Round linear curves (roundline_intersector.h) and flat linear curves (line_intersector.h) restated in
+    oracle/embree_oracle.c against the reference's own outputs: two curve sets (library-derived and application neighbour
+    flags, geometry masks) around a triangle sphere."""
     from tests.conftest import load_golden_curves
-    g = load_golden_curves()
+    g = load_golden_curves(name)
     sc = oracle.scene(g["meshes"], curves=g["curves"])
     got = sc.trace(g["rays_in"].copy())
     rep = compare_hits(g["intersect_out"], got)
-    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 10, rep    # ties: the joint of two segments
+    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 40, rep    # ties: the joint of two segments
     assert rep["max_rel_t"] <= 1e-4 and rep["max_abs_uv"] <= 1e-4 and rep["miss_untouched"], rep
     ok = (got["geomID"] == g["intersect_out"]["geomID"]) & (got["primID"] == g["intersect_out"]["primID"]) & (got["geomID"] != 0xFFFFFFFF)
     for f in ("Ng_x", "Ng_y", "Ng_z"):
