@@ -126,6 +126,9 @@ struct BufferView {
 };
 
 enum class GeomState { MODIFIED, COMMITTED };
+// number of live geometries that have a filter callback or accept the arguments' filter: while it is zero (and the
+// query carries no filter) no query looks at the geometries at all
+std::atomic<long> g_filterGeoms{0};
 
 struct SceneImpl;
 void release_scene_ref(SceneImpl* s);
@@ -143,10 +146,20 @@ struct GeometryImpl : RefCounted {
   bool enabled = true;
   RTCBuildQuality quality = RTC_BUILD_QUALITY_MEDIUM;
   void* userPtr = nullptr;
+  // filter callbacks (geometry.h:269-270,481-482; geometry.cpp:142-156): host functions, run by trace_filtered()
+  RTCFilterFunctionN intersectFilter = nullptr, occludedFilter = nullptr;
+  bool argFilterEnabled = false;
   GeomState state = GeomState::MODIFIED;
   unsigned modCounter = 1;
   explicit GeometryImpl(DeviceImpl* d) : dev(d) { dev->retain(); }
-  ~GeometryImpl() override { if (instScene) release_scene_ref(instScene); dev->release(); }
+  ~GeometryImpl() override { if (has_filter()) g_filterGeoms.fetch_sub(1); if (instScene) release_scene_ref(instScene); dev->release(); }
+  bool has_filter() const { return intersectFilter || occludedFilter || argFilterEnabled; }
+  template <typename F> void set_filter(F&& change) {
+    const bool before = has_filter();
+    change();
+    const bool after = has_filter();
+    if (after != before) g_filterGeoms.fetch_add(after ? 1 : -1);
+  }
   void update() { ++modCounter; state = GeomState::MODIFIED; }  // geometry.cpp:97-101
 };
 
@@ -465,16 +478,45 @@ thread_local ThreadCtx t_ctx;
 // RTCIntersectArguments / RTCOccludedArguments (rtcore_common.h:335-361, context.h:14-62).  `context->instID` seeds the
 // hit's instance ids.  `flags`: RTC_RAY_QUERY_FLAG_COHERENT only selects the reference's coherent packet traverser
 // (context.h:41-45) -- a performance hint with identical results, so every value is accepted; a warp here always traces 32
-// rays together.  `feature_mask`: "should get used in SYCL" (doc/src/api/rtcInitIntersectArguments.md:48); the reference's
-// CPU entry points never read it (kernels/common/rtcore.cpp), neither do we.  `filter` / `intersect` are host function
-// pointers that cannot run inside a device traversal: a non-NULL callback is an error instead of being silently skipped.
+// rays together; RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER makes `filter` apply to every geometry (context.h:48-50).
+// `feature_mask`: "should get used in SYCL" (doc/src/api/rtcInitIntersectArguments.md:48); the reference's CPU entry
+// points never read it (kernels/common/rtcore.cpp), neither do we.  `filter` is a host function: the host-pointer entry
+// points run it through trace_filtered() below, the Device entry points refuse it.  `intersect` / `occluded` belong to
+// user geometries, which this back-end does not have.
+struct QueryArgs {
+  uint32_t instID = RTC_INVALID_GEOMETRY_ID, instPrimID = RTC_INVALID_GEOMETRY_ID;
+  RTCFilterFunctionN filter = nullptr;
+  bool enforce = false;                  // RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER
+  RTCRayQueryContext* ctx = nullptr;     // the caller's context (NULL: a default one is made for the callbacks)
+};
 template <typename Args>
-void check_args(SceneImpl* s, const Args* a, uint32_t& instID, uint32_t& instPrimID) {
-  instID = instPrimID = RTC_INVALID_GEOMETRY_ID;
-  if (!a) return;
-  if (a->filter) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the device");
-  if (a->context) { instID = a->context->instID[0]; instPrimID = a->context->instPrimID[0]; }
-  (void)s;
+QueryArgs read_args(const Args* a) {
+  QueryArgs q;
+  if (!a) return q;
+  q.filter = a->filter;
+  q.enforce = (a->flags & RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER) != 0;
+  q.ctx = a->context;
+  if (a->context) { q.instID = a->context->instID[0]; q.instPrimID = a->context->instPrimID[0]; }
+  return q;
+}
+
+// Does a filter callback apply to some geometry of this scene for this query (filter.h:15-36, :51-71)?
+bool filters_apply(SceneImpl* s, const QueryArgs& q, int occluded) {
+  if (!q.filter && g_filterGeoms.load(std::memory_order_relaxed) == 0) return false;
+  auto applies = [&](const GeometryImpl* g) {
+    if (occluded ? g->occludedFilter != nullptr : g->intersectFilter != nullptr) return true;
+    return q.filter && (q.enforce || g->argFilterEnabled);
+  };
+  std::lock_guard<std::mutex> lg(s->geomMutex);
+  for (GeometryImpl* g : s->geoms) {
+    if (!g || !g->enabled) continue;
+    if (g->type != RTC_GEOMETRY_TYPE_INSTANCE) { if (applies(g)) return true; continue; }
+    if (!g->instScene) continue;
+    std::lock_guard<std::mutex> lc(g->instScene->geomMutex);
+    for (GeometryImpl* cg : g->instScene->geoms)
+      if (cg && cg->enabled && cg->type != RTC_GEOMETRY_TYPE_INSTANCE && applies(cg)) return true;
+  }
+  return false;
 }
 
 rtk::TraceParams make_params(SceneImpl* s, void* rays, const int* valid, unsigned long long n, uint32_t instID,
@@ -622,6 +664,168 @@ void trace_host(SceneImpl* s, void* rays, const int* valid, int K, size_t M, siz
   for (int i = 0; i < HostPipe::kStreams; ++i) cuda_check(cudaStreamSynchronize(t_pipe.st[i]), "trace");
 }
 
+// ---- filter callbacks (kernels/geometry/filter.h:15-84, intersector_epilog.h:264-280, :347-361) ----------------------
+// The reference calls the geometry's filter (and / or the arguments' filter) on the host thread for every candidate hit
+// it meets during traversal; a rejected candidate (valid[0] = 0) does not shorten the ray and the traversal goes on.  A
+// device traversal cannot call into the host, so the same semantics are produced in passes: the FILTER instantiation of
+// the trace kernel returns each ray's CLOSEST candidate that no callback has rejected yet, together with the index of
+// its leaf record; the callbacks run here with N == 1 (ray.tfar = candidate distance, a separate RTCHit, the context's
+// instance ids as during an instanced traversal); an accepted hit is final, a rejected one is appended to the ray's
+// exclusion list and the ray is traced again.  Closest hit: the first accepted candidate in distance order is the
+// closest accepted hit, which is what the reference's traversal converges to.  Occluded: the ray is occluded iff some
+// candidate in [tnear, tfar] is accepted, whatever the order.  Callbacks see every candidate at most once, front to back
+// (the reference's order is its traversal order and it may also call them on candidates behind the final hit).
+// Packets are processed lane by lane with N == 1, which the callback contract allows (rtcore_common.h:311-324: N is an
+// argument precisely because it varies).
+struct LaneIO {
+  char* base; int K; int occluded;
+  size_t packet() const { return (size_t)(occluded ? 12 : 21) * 4 * K + (K == 1 && !occluded ? 12 : 0); }
+  uint32_t* field(size_t i, int f) const { return reinterpret_cast<uint32_t*>(base + (i / K) * packet() + ((size_t)f * K + (i % K)) * 4); }
+  void load(size_t i, RTCRayHit& r) const {
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+    for (int f = 0; f < 12; ++f) d[f] = *field(i, f);
+    r.hit.Ng_x = r.hit.Ng_y = r.hit.Ng_z = r.hit.u = r.hit.v = 0.0f;
+    r.hit.primID = r.hit.geomID = r.hit.instID[0] = RTC_INVALID_GEOMETRY_ID;
+    r.hit.instPrimID[0] = RTC_INVALID_GEOMETRY_ID;
+  }
+  void store_hit(size_t i, const RTCRayHit& r) const {   // copyHitToRay + the distance the callback left in ray.tfar
+    const uint32_t* d = reinterpret_cast<const uint32_t*>(&r);
+    *field(i, 8) = d[8];
+    for (int f = 12; f < 21; ++f) *field(i, f) = d[f];
+  }
+  void store_tfar(size_t i, float t) const { memcpy(field(i, 8), &t, 4); }
+};
+
+GeometryImpl* hit_geometry(SceneImpl* s, const RTCHit& h) {
+  std::lock_guard<std::mutex> lg(s->geomMutex);
+  const unsigned inst = h.instID[0];
+  if (inst != RTC_INVALID_GEOMETRY_ID && inst < s->geoms.size() && s->geoms[inst] && s->geoms[inst]->type == RTC_GEOMETRY_TYPE_INSTANCE &&
+      s->geoms[inst]->instScene) {
+    SceneImpl* c = s->geoms[inst]->instScene;
+    std::lock_guard<std::mutex> lc(c->geomMutex);
+    return h.geomID < c->geoms.size() ? c->geoms[h.geomID] : nullptr;
+  }
+  return h.geomID < s->geoms.size() ? s->geoms[h.geomID] : nullptr;
+}
+
+// runIntersectionFilter1 / runOcclusionFilter1 (filter.h:15-84) for one candidate; true = accepted
+bool run_filters(GeometryImpl* g, RTCRayHit& r, const QueryArgs& q, int occluded) {
+  if (!g) return true;
+  RTCFilterFunctionN gfn = occluded ? g->occludedFilter : g->intersectFilter;
+  RTCFilterFunctionN afn = (q.filter && (q.enforce || g->argFilterEnabled)) ? q.filter : nullptr;
+  if (!gfn && !afn) return true;
+  RTCRayQueryContext fallback;
+  rtcInitRayQueryContext(&fallback);
+  RTCRayQueryContext* ctx = q.ctx ? q.ctx : &fallback;
+  const unsigned saveI = ctx->instID[0], saveP = ctx->instPrimID[0];
+  ctx->instID[0] = r.hit.instID[0]; ctx->instPrimID[0] = r.hit.instPrimID[0];   // instance_id_stack::push during an instanced traversal
+  RTCHit h = r.hit;
+  int mask = -1;
+  RTCFilterFunctionNArguments fa;
+  fa.valid = &mask; fa.geometryUserPtr = g->userPtr; fa.context = ctx;
+  fa.ray = reinterpret_cast<RTCRayN*>(&r.ray); fa.hit = reinterpret_cast<RTCHitN*>(&h); fa.N = 1;
+  bool ok = true;
+  if (gfn) { gfn(&fa); ok = mask != 0; }
+  if (ok && afn) { afn(&fa); ok = mask != 0; }
+  ctx->instID[0] = saveI; ctx->instPrimID[0] = saveP;
+  if (ok) r.hit = h;   // copyHitToRay: what the callback left in the hit is what the caller gets
+  return ok;
+}
+
+void trace_filtered(SceneImpl* s, void* recs, const int* valid, int K, size_t M, int occluded, const QueryArgs& q) {
+  require_committed(s);
+  if (!s->gpu.root_valid || M == 0) return;
+  t_ctx.ensure(s->dev->gpu);
+  cudaSetDevice(s->dev->gpu);
+  cudaStream_t st = t_ctx.stream;
+  const LaneIO io{static_cast<char*>(recs), K, occluded};
+  const size_t total = M * (size_t)K, chunk = size_t(1) << 21;
+  struct DevBuf {
+    void* p = nullptr; size_t cap = 0; cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    void* need(size_t bytes) {
+      if (bytes > cap) { if (p) cudaFreeAsync(p, st); p = nullptr; cap = 0; cuda_check(cudaMallocAsync(&p, bytes, st), "cudaMallocAsync(filter pass)"); cap = bytes; }
+      return p;
+    }
+  } dRays(st), dOff(st), dIdx(st), dWin(st);
+  for (size_t first = 0; first < total; first += chunk) {
+    const size_t cnt = std::min(chunk, total - first);
+    std::vector<RTCRayHit> work;       // the chunk's active rays as the caller passed them
+    std::vector<size_t> src;           // their lane index in the caller's records
+    work.reserve(cnt); src.reserve(cnt);
+    for (size_t i = first; i < first + cnt; ++i) {
+      if (K > 1 && valid && valid[i] != -1) continue;           // inactive lanes stay untouched
+      RTCRayHit r;
+      io.load(i, r);
+      if (occluded && r.ray.tfar < 0.0f) continue;               // already occluded (bvh_intersector1.cpp:128-129)
+      work.push_back(r); src.push_back(i);
+    }
+    std::vector<std::vector<uint32_t>> excl(work.size());
+    std::vector<uint32_t> active(work.size()), next;
+    for (size_t j = 0; j < active.size(); ++j) active[j] = (uint32_t)j;
+    std::vector<RTCRayHit> pass;
+    std::vector<uint32_t> off, idx, win;
+    while (!active.empty()) {
+      const size_t n = active.size();
+      pass.resize(n); off.assign(n + 1, 0u); idx.clear(); win.resize(n);
+      for (size_t j = 0; j < n; ++j) {
+        pass[j] = work[active[j]];
+        off[j] = (uint32_t)idx.size();
+        idx.insert(idx.end(), excl[active[j]].begin(), excl[active[j]].end());
+      }
+      off[n] = (uint32_t)idx.size();
+      RTCRayHit* dr = static_cast<RTCRayHit*>(dRays.need(n * sizeof(RTCRayHit)));
+      uint32_t* dof = static_cast<uint32_t*>(dOff.need((n + 1) * 4));
+      uint32_t* dix = static_cast<uint32_t*>(dIdx.need(std::max<size_t>(idx.size(), 1) * 4));
+      uint32_t* dwn = static_cast<uint32_t*>(dWin.need(n * 4));
+      cuda_check(cudaMemcpyAsync(dr, pass.data(), n * sizeof(RTCRayHit), cudaMemcpyHostToDevice, st), "H2D rays");
+      cuda_check(cudaMemcpyAsync(dof, off.data(), (n + 1) * 4, cudaMemcpyHostToDevice, st), "H2D exclusion offsets");
+      if (!idx.empty()) cuda_check(cudaMemcpyAsync(dix, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st), "H2D exclusion lists");
+      rtk::TraceParams p = make_params(s, dr, nullptr, (unsigned long long)n, q.instID, q.instPrimID);
+      p.stat = nullptr;
+      p.excl_off = dof; p.excl_idx = dix; p.win = dwn;
+      cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, st), "trace launch");
+      cuda_check(cudaMemcpyAsync(pass.data(), dr, n * sizeof(RTCRayHit), cudaMemcpyDeviceToHost, st), "D2H rays");
+      cuda_check(cudaMemcpyAsync(win.data(), dwn, n * 4, cudaMemcpyDeviceToHost, st), "D2H winning records");
+      cuda_check(cudaStreamSynchronize(st), "trace");
+      next.clear();
+      for (size_t j = 0; j < n; ++j) {
+        RTCRayHit& r = pass[j];
+        if (r.hit.geomID == RTC_INVALID_GEOMETRY_ID) continue;   // no candidate left: the caller's record stays as it was
+        if (run_filters(hit_geometry(s, r.hit), r, q, occluded)) {
+          if (occluded) io.store_tfar(src[active[j]], -INFINITY);   // bvh_intersector1.cpp:186-188
+          else io.store_hit(src[active[j]], r);
+        } else {
+          excl[active[j]].push_back(win[j]);
+          next.push_back(active[j]);
+        }
+      }
+      active.swap(next);
+    }
+  }
+}
+
+// one record (single ray or one packet) / M records through host pointers: with or without filter callbacks
+template <typename Args>
+void query_one(SceneImpl* s, void* rec, size_t bytes, const int* valid, int K, int occluded, const Args* a) {
+  const QueryArgs q = read_args(a);
+  if (filters_apply(s, q, occluded)) trace_filtered(s, rec, valid, K, 1, occluded, q);
+  else trace_one(s, rec, bytes, valid, K, occluded, q.instID, q.instPrimID);
+}
+template <typename Args>
+void query_host(SceneImpl* s, void* recs, const int* valid, int K, size_t M, size_t bytes, int occluded, const Args* a) {
+  const QueryArgs q = read_args(a);
+  if (filters_apply(s, q, occluded)) trace_filtered(s, recs, valid, K, M, occluded, q);
+  else trace_host(s, recs, valid, K, M, bytes, occluded, q.instID, q.instPrimID);
+}
+template <typename Args>
+QueryArgs device_args(SceneImpl* s, const Args* a, int occluded) {
+  const QueryArgs q = read_args(a);
+  if (filters_apply(s, q, occluded)) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks are host functions: use the host-pointer entry points");
+  return q;
+}
+
 size_t rec_bytes(int K, int occluded) { return (size_t)(occluded ? 12 : 21) * 4 * K + (K == 1 && !occluded ? 12 : 0); }
 
 }  // namespace
@@ -689,7 +893,7 @@ ssize_t rtcGetDeviceProperty(RTCDevice h, enum RTCDeviceProperty prop) {
     case RTC_DEVICE_PROPERTY_BACKFACE_CULLING_CURVES_ENABLED: return 0;
     case RTC_DEVICE_PROPERTY_RAY_MASK_SUPPORTED: return 1;
     case RTC_DEVICE_PROPERTY_BACKFACE_CULLING_ENABLED: return 0;
-    case RTC_DEVICE_PROPERTY_FILTER_FUNCTION_SUPPORTED: return 0;  // host callbacks cannot run in a device traversal
+    case RTC_DEVICE_PROPERTY_FILTER_FUNCTION_SUPPORTED: return 1;  // host-pointer entry points (trace_filtered)
     case RTC_DEVICE_PROPERTY_IGNORE_INVALID_RAYS_ENABLED: return 0;
     case RTC_DEVICE_PROPERTY_COMPACT_POLYS_ENABLED: return 0;
     case RTC_DEVICE_PROPERTY_TRIANGLE_GEOMETRY_SUPPORTED: return 1;
@@ -852,9 +1056,11 @@ void rtcUpdateGeometryBuffer(RTCGeometry g, enum RTCBufferType type, unsigned in
 }
 void rtcSetGeometryUserData(RTCGeometry g, void* p) { GEOM_BEGIN(g) G(g)->userPtr = p; GEOM_END }
 void* rtcGetGeometryUserData(RTCGeometry g) { GEOM_BEGIN(g) return G(g)->userPtr; GEOM_END return nullptr; }
-void rtcSetGeometryEnableFilterFunctionFromArguments(RTCGeometry g, bool) { GEOM_BEGIN(g) G(g)->update(); GEOM_END }
-void rtcSetGeometryIntersectFilterFunction(RTCGeometry g, RTCFilterFunctionN f) { GEOM_BEGIN(g) if (f) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the device"); GEOM_END }
-void rtcSetGeometryOccludedFilterFunction(RTCGeometry g, RTCFilterFunctionN f) { GEOM_BEGIN(g) if (f) fail(RTC_ERROR_INVALID_OPERATION, "filter callbacks cannot run on the device"); GEOM_END }
+// filter callbacks (rtcore.cpp:2188-2216; geometry.cpp:142-156): stored on the geometry, no commit needed; instances take none
+static void check_filter_geometry(GeometryImpl* g) { if (g->type == RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "filter functions not supported for this geometry"); }
+void rtcSetGeometryEnableFilterFunctionFromArguments(RTCGeometry g, bool e) { GEOM_BEGIN(g) G(g)->set_filter([&] { G(g)->argFilterEnabled = e; }); GEOM_END }
+void rtcSetGeometryIntersectFilterFunction(RTCGeometry g, RTCFilterFunctionN f) { GEOM_BEGIN(g) check_filter_geometry(G(g)); G(g)->set_filter([&] { G(g)->intersectFilter = f; }); GEOM_END }
+void rtcSetGeometryOccludedFilterFunction(RTCGeometry g, RTCFilterFunctionN f) { GEOM_BEGIN(g) check_filter_geometry(G(g)); G(g)->set_filter([&] { G(g)->occludedFilter = f; }); GEOM_END }
 
 // ---- scene --------------------------------------------------------------------------------------------------------
 #define SCENE_BEGIN(s) DeviceImpl* dev_ = (s) ? S(s)->dev : nullptr; API_BEGIN VERIFY_HANDLE(s);
@@ -962,16 +1168,16 @@ void rtcGetSceneLinearBounds(RTCScene s, struct RTCLinearBounds* b) {
 #define QUERY(scene, body) \
   SceneImpl* s_ = S(scene); \
   DeviceImpl* dev_ = s_ ? s_->dev : nullptr; \
-  API_BEGIN uint32_t iid, ipid; body API_END(dev_)
+  API_BEGIN body API_END(dev_)
 
-void rtcIntersect1(RTCScene sc, struct RTCRayHit* rh, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, rh, 96, nullptr, 1, 0, iid, ipid);) }
-void rtcIntersect4(const int* v, RTCScene sc, struct RTCRayHit4* rh, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, rh, sizeof(RTCRayHit4), v, 4, 0, iid, ipid);) }
-void rtcIntersect8(const int* v, RTCScene sc, struct RTCRayHit8* rh, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, rh, sizeof(RTCRayHit8), v, 8, 0, iid, ipid);) }
-void rtcIntersect16(const int* v, RTCScene sc, struct RTCRayHit16* rh, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, rh, sizeof(RTCRayHit16), v, 16, 0, iid, ipid);) }
-void rtcOccluded1(RTCScene sc, struct RTCRay* r, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, r, 48, nullptr, 1, 1, iid, ipid);) }
-void rtcOccluded4(const int* v, RTCScene sc, struct RTCRay4* r, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, r, sizeof(RTCRay4), v, 4, 1, iid, ipid);) }
-void rtcOccluded8(const int* v, RTCScene sc, struct RTCRay8* r, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, r, sizeof(RTCRay8), v, 8, 1, iid, ipid);) }
-void rtcOccluded16(const int* v, RTCScene sc, struct RTCRay16* r, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_one(s_, r, sizeof(RTCRay16), v, 16, 1, iid, ipid);) }
+void rtcIntersect1(RTCScene sc, struct RTCRayHit* rh, struct RTCIntersectArguments* a) { QUERY(sc, query_one(s_, rh, 96, nullptr, 1, 0, a);) }
+void rtcIntersect4(const int* v, RTCScene sc, struct RTCRayHit4* rh, struct RTCIntersectArguments* a) { QUERY(sc, query_one(s_, rh, sizeof(RTCRayHit4), v, 4, 0, a);) }
+void rtcIntersect8(const int* v, RTCScene sc, struct RTCRayHit8* rh, struct RTCIntersectArguments* a) { QUERY(sc, query_one(s_, rh, sizeof(RTCRayHit8), v, 8, 0, a);) }
+void rtcIntersect16(const int* v, RTCScene sc, struct RTCRayHit16* rh, struct RTCIntersectArguments* a) { QUERY(sc, query_one(s_, rh, sizeof(RTCRayHit16), v, 16, 0, a);) }
+void rtcOccluded1(RTCScene sc, struct RTCRay* r, struct RTCOccludedArguments* a) { QUERY(sc, query_one(s_, r, 48, nullptr, 1, 1, a);) }
+void rtcOccluded4(const int* v, RTCScene sc, struct RTCRay4* r, struct RTCOccludedArguments* a) { QUERY(sc, query_one(s_, r, sizeof(RTCRay4), v, 4, 1, a);) }
+void rtcOccluded8(const int* v, RTCScene sc, struct RTCRay8* r, struct RTCOccludedArguments* a) { QUERY(sc, query_one(s_, r, sizeof(RTCRay8), v, 8, 1, a);) }
+void rtcOccluded16(const int* v, RTCScene sc, struct RTCRay16* r, struct RTCOccludedArguments* a) { QUERY(sc, query_one(s_, r, sizeof(RTCRay16), v, 16, 1, a);) }
 
 void rtcTraversableIntersect1(RTCTraversable t, struct RTCRayHit* rh, struct RTCIntersectArguments* a) { rtcIntersect1(reinterpret_cast<RTCScene>(t), rh, a); }
 void rtcTraversableIntersect4(const int* v, RTCTraversable t, struct RTCRayHit4* rh, struct RTCIntersectArguments* a) { rtcIntersect4(v, reinterpret_cast<RTCScene>(t), rh, a); }
@@ -984,15 +1190,15 @@ void rtcTraversableOccluded16(const int* v, RTCTraversable t, struct RTCRay16* r
 
 // ---- batched extension ---------------------------------------------------------------------------------------------
 static void check_K(unsigned K) { if (K != 4 && K != 8 && K != 16) fail(RTC_ERROR_INVALID_ARGUMENT, "packet width must be 4, 8 or 16"); }
-void rtcb200Intersect1M(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_host(s_, rh, nullptr, 1, M, 96, 0, iid, ipid);) }
-void rtcb200Occluded1M(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOccludedArguments* a) { QUERY(sc, check_args(s_, a, iid, ipid); trace_host(s_, r, nullptr, 1, M, 48, 1, iid, ipid);) }
-void rtcb200IntersectNM(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_host(s_, rh, v, (int)K, M, (size_t)84 * K, 0, iid, ipid);) }
-void rtcb200OccludedNM(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_host(s_, r, v, (int)K, M, (size_t)48 * K, 1, iid, ipid);) }
-void rtcb200Intersect1MDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, rh, nullptr, 1, M, 0, iid, ipid, (cudaStream_t)st, true);) }
-void rtcb200Intersect1MGatherDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st, void* compact_out) { QUERY(sc, check_args(s_, a, iid, ipid); VERIFY_HANDLE(compact_out); trace_gather(s_, rh, M, iid, ipid, (cudaStream_t)st, compact_out);) }
-void rtcb200Occluded1MDevice(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, check_args(s_, a, iid, ipid); trace_device(s_, r, nullptr, 1, M, 1, iid, ipid, (cudaStream_t)st, true);) }
-void rtcb200IntersectNMDevice(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_device(s_, rh, v, (int)K, M, 0, iid, ipid, (cudaStream_t)st, true);) }
-void rtcb200OccludedNMDevice(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, check_K(K); check_args(s_, a, iid, ipid); trace_device(s_, r, v, (int)K, M, 1, iid, ipid, (cudaStream_t)st, true);) }
+void rtcb200Intersect1M(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a) { QUERY(sc, query_host(s_, rh, nullptr, 1, M, 96, 0, a);) }
+void rtcb200Occluded1M(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOccludedArguments* a) { QUERY(sc, query_host(s_, r, nullptr, 1, M, 48, 1, a);) }
+void rtcb200IntersectNM(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a) { QUERY(sc, check_K(K); query_host(s_, rh, v, (int)K, M, (size_t)84 * K, 0, a);) }
+void rtcb200OccludedNM(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a) { QUERY(sc, check_K(K); query_host(s_, r, v, (int)K, M, (size_t)48 * K, 1, a);) }
+void rtcb200Intersect1MDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, const QueryArgs q = device_args(s_, a, 0); trace_device(s_, rh, nullptr, 1, M, 0, q.instID, q.instPrimID, (cudaStream_t)st, true);) }
+void rtcb200Intersect1MGatherDevice(RTCScene sc, struct RTCRayHit* rh, size_t M, struct RTCIntersectArguments* a, void* st, void* compact_out) { QUERY(sc, const QueryArgs q = device_args(s_, a, 0); VERIFY_HANDLE(compact_out); trace_gather(s_, rh, M, q.instID, q.instPrimID, (cudaStream_t)st, compact_out);) }
+void rtcb200Occluded1MDevice(RTCScene sc, struct RTCRay* r, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, const QueryArgs q = device_args(s_, a, 1); trace_device(s_, r, nullptr, 1, M, 1, q.instID, q.instPrimID, (cudaStream_t)st, true);) }
+void rtcb200IntersectNMDevice(const int* v, RTCScene sc, void* rh, unsigned int K, size_t M, struct RTCIntersectArguments* a, void* st) { QUERY(sc, check_K(K); const QueryArgs q = device_args(s_, a, 0); trace_device(s_, rh, v, (int)K, M, 0, q.instID, q.instPrimID, (cudaStream_t)st, true);) }
+void rtcb200OccludedNMDevice(const int* v, RTCScene sc, void* r, unsigned int K, size_t M, struct RTCOccludedArguments* a, void* st) { QUERY(sc, check_K(K); const QueryArgs q = device_args(s_, a, 1); trace_device(s_, r, v, (int)K, M, 1, q.instID, q.instPrimID, (cudaStream_t)st, true);) }
 
 void rtcb200GetSceneStats(RTCScene sc, struct RTCB200SceneStats* o) {
   SCENE_BEGIN(sc)

@@ -85,6 +85,11 @@ struct TraceParams {
   int curves = 0;                   // the scene holds round linear curve records (descs != NULL)
   uint32_t top_nodes = 0;           // nodes in the first three BVH8 levels (RTK_TOP_SMEM experiment)
   int robust = 0;  // scene built with RTC_SCENE_FLAG_ROBUST: triangle records hold v0,v1,v2, Pluecker test
+  // filter-callback passes (K == 1 closest hit): per-ray lists of rejected record indices (excl_off has n + 1 entries) and
+  // the per-ray output of the winning record index (0xFFFFFFFF on a miss)
+  const uint32_t* excl_off = nullptr;
+  const uint32_t* excl_idx = nullptr;
+  uint32_t* win = nullptr;
 };
 // occluded: 0 = closest hit (rtcIntersect*), 1 = any hit (rtcOccluded*); K in {1,4,8,16}
 int launch_trace(const TraceParams& p, int occluded, int K, cudaStream_t stream);

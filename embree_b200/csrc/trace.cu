@@ -186,7 +186,12 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 //             instead of 50 ms.  A block that stops being tracked before all its rays have finished is sent partially
 //             (masked lanes) and its stragglers fall back to the direct store.  (Staging in shared memory -- two 1 KB slots
 //             per warp -- cost 20 % of the kernel at 2 GPUs, profiles/r2_bench_n2.json gather_ab: 8 KB less L1 per CTA.)
-template <int K, bool OCCLUDED, bool STATS, bool ROBUST, int GENERAL, int GATHER = 0, bool SPREAD = false>
+//
+// FILTER (K == 1 closest hit, host-pointer entry points only): the host side of filter callbacks (rtcore_shim.cpp
+// trace_filtered).  Every ray carries a list of record indices that a callback has already rejected
+// (p.excl_idx[p.excl_off[i] .. p.excl_off[i+1])); those records are skipped, and the winning record's index goes to p.win[i]
+// so that the host can extend the list when the callback rejects this hit as well.
+template <int K, bool OCCLUDED, bool STATS, bool ROBUST, int GENERAL, int GATHER = 0, bool SPREAD = false, bool FILTER = false>
 __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(const TraceParams p) {
   const bool USE_TMA = p.use_prefetch != 0;
   using IO = RayIO<K, OCCLUDED>;
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         cngx = hit.ngx; cngy = hit.ngy; cngz = hit.ngz; cprim = hit.primID; cgeom = hit.geomID;
       }
     }
+    if (FILTER) p.win[ray_index] = found ? hit_tri : kInvalidID;
     if (GATHER)   // one 256-bit store (STG.256, new on sm_100): a full 32-byte sector; a miss (also: empty scene) yields {tfar, 0.., -1, -1}
       store_256(rec_dst, tfar_tri, cngx, cngy, cngz, found ? hit_u : 0.0f, found ? hit_v : 0.0f, __uint_as_float(cprim), __uint_as_float(cgeom));
   };
@@ -374,6 +380,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
 
   // one triangle record against this lane's ray (closest hit: shrinks tfar_tri; any hit: terminates the ray)
   auto test_tri = [&](uint32_t ti, const uint4& a, const uint4& b, const uint4& c) {
+    if (FILTER) {   // a record the filter callback has rejected for this ray is no candidate any more
+      const uint32_t e0 = p.excl_off[ray_index], e1 = p.excl_off[ray_index + 1];
+      for (uint32_t e = e0; e < e1; ++e)
+        if (p.excl_idx[e] == ti) return;
+    }
     Ray lr = full_ray();
     const Ray wr = lr;                               // world-space ray (curves are not instanced)
     bool visible = (c.w & lr.mask) != 0;             // ray mask (intersector_epilog.h:256-262)
@@ -728,6 +739,23 @@ static int launch_k(TraceParams p, cudaStream_t st) {
   constexpr bool CLOSEST = !OCCLUDED;
   constexpr bool CAN_GATHER = (K == 1 && CLOSEST);
   const int variant = (p.stat ? 4 : 0) | (p.robust ? 2 : 0) | (p.descs ? 1 : 0);
+  if (p.excl_off) {   // filter-callback passes (rtcore_shim.cpp trace_filtered): K == 1 closest hit, no gather, no statistics
+    if (!(K == 1 && CLOSEST) || !p.excl_idx || !p.win) return (int)cudaErrorInvalidValue;
+    constexpr bool FI = (K == 1 && CLOSEST);   // only these instantiations carry the exclusion code
+    const int g = !p.descs ? 0 : (p.curves ? 2 : 1);
+    switch (g * 2 + (p.robust ? 1 : 0)) {
+#define RTK_FILTER(RB, GE) trace_kernel<K, OCCLUDED, false, RB, GE, 0, false, FI><<<blocks, TRACE_THREADS, 0, st>>>(p); break
+      case 0: RTK_FILTER(false, 0);
+      case 1: RTK_FILTER(true, 0);
+      case 2: RTK_FILTER(false, 1);
+      case 3: RTK_FILTER(true, 1);
+      case 4: RTK_FILTER(false, 2);
+      case 5: RTK_FILTER(true, 2);
+#undef RTK_FILTER
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   if (p.descs && p.curves) {   // scenes with round linear curves: the GENERAL = 2 instantiations (kept apart: the curve test costs registers)
     const int gmode = (CAN_GATHER && p.compact_out) ? ((g_tuning.gather_mode == 0 || !p.stage) ? 1 : 2) : 0;
     switch ((variant >> 1) + 4 * gmode) {

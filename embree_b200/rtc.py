@@ -130,6 +130,37 @@ class _IntersectArguments(C.Structure):
                 ("filter", C.c_void_p), ("intersect", C.c_void_p)]
 
 
+class RayQueryContext(C.Structure):
+    _fields_ = [("instID", C.c_uint), ("instPrimID", C.c_uint)]
+
+
+class FilterFunctionNArguments(C.Structure):
+    """RTCFilterFunctionNArguments (rtcore_common.h:311-321); ray / hit are SoA blocks of N lanes."""
+    _fields_ = [("valid", C.POINTER(C.c_int)), ("geometryUserPtr", C.c_void_p), ("context", C.POINTER(RayQueryContext)),
+                ("ray", C.POINTER(C.c_uint)), ("hit", C.POINTER(C.c_uint)), ("N", C.c_uint)]
+
+
+FILTER_FUNCTION = C.CFUNCTYPE(None, C.POINTER(FilterFunctionNArguments))
+RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER = 1 << 1
+
+
+def filter_lane(args, lane):
+    """Python view of lane `lane` of a filter callback's arguments: dict of the ray / hit fields (u32 bit patterns for
+    ids, floats for the rest), as RTCRayN_* / RTCHitN_* (rtcore_ray.h:187-256) read them."""
+    a = args.contents
+    n = a.N
+    ray = np.ctypeslib.as_array(a.ray, shape=(12 * n,))
+    hit = np.ctypeslib.as_array(a.hit, shape=(9 * n,))
+    out = {}
+    for f, name in enumerate(_RAY_FIELDS):
+        w = ray[f * n + lane]
+        out[name] = int(w) if name in ("mask", "id", "flags") else float(np.uint32(w).view(np.float32))
+    for f, name in enumerate(_HIT_FIELDS):
+        w = hit[f * n + lane]
+        out[name] = int(w) if name in ("primID", "geomID", "instID", "instPrimID") else float(np.uint32(w).view(np.float32))
+    return out
+
+
 class RTCBounds(C.Structure):
     _fields_ = [(n, C.c_float) for n in
                 ("lower_x", "lower_y", "lower_z", "align0", "upper_x", "upper_y", "upper_z", "align1")]
@@ -180,6 +211,9 @@ class RTCLib:
         "rtcUpdateGeometryBuffer": (None, [C.c_void_p, C.c_int, C.c_uint]),
         "rtcSetGeometryUserData": (None, [C.c_void_p, C.c_void_p]),
         "rtcGetGeometryUserData": (C.c_void_p, [C.c_void_p]),
+        "rtcSetGeometryIntersectFilterFunction": (None, [C.c_void_p, C.c_void_p]),
+        "rtcSetGeometryOccludedFilterFunction": (None, [C.c_void_p, C.c_void_p]),
+        "rtcSetGeometryEnableFilterFunctionFromArguments": (None, [C.c_void_p, C.c_bool]),
         "rtcSetGeometryInstancedScene": (None, [C.c_void_p, C.c_void_p]),
         "rtcSetGeometryTransform": (None, [C.c_void_p, C.c_uint, C.c_int, C.c_void_p]),
         "rtcGetGeometryTransform": (None, [C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
@@ -346,19 +380,22 @@ class RTCLib:
         self.rtcReleaseGeometry(g)
         return gid
 
-    def args(self, coherent=False):
+    def args(self, coherent=False, filter=None, invoke_argument_filter=False, context=None):
+        """RTCIntersectArguments / RTCOccludedArguments (same layout).  `filter`: a FILTER_FUNCTION instance (keep it
+        alive); `context`: a RayQueryContext (or a structure that starts with one)."""
         a = _IntersectArguments()
-        a.flags = RTC_RAY_QUERY_FLAG_COHERENT if coherent else RTC_RAY_QUERY_FLAG_INCOHERENT
+        a.flags = (RTC_RAY_QUERY_FLAG_COHERENT if coherent else RTC_RAY_QUERY_FLAG_INCOHERENT) | \
+                  (RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER if invoke_argument_filter else 0)
         a.feature_mask = RTC_FEATURE_FLAG_ALL
-        a.context = None
-        a.filter = None
+        a.context = C.cast(C.pointer(context), C.c_void_p) if context is not None else None
+        a.filter = C.cast(filter, C.c_void_p) if filter is not None else None
         a.intersect = None
         return a
 
     # "IntersectWithMode": feed the same RTCRayHit[] through any entry point -------------------------
-    def intersect(self, scene, rayhits, mode="1", coherent=False):
+    def intersect(self, scene, rayhits, mode="1", coherent=False, args=None):
         """mode: '1' (loop of rtcIntersect1), '4'/'8'/'16' (loop of packets), '1M'/'4M'/'8M'/'16M' (batched ext)."""
-        a = self.args(coherent)
+        a = args if args is not None else self.args(coherent)
         n = len(rayhits)
         if mode == "1":
             base, st = rayhits.ctypes.data, rayhits.dtype.itemsize
@@ -379,8 +416,8 @@ class RTCLib:
         rayhits[:] = from_packets(p, n)
         return rayhits
 
-    def occluded(self, scene, rays, mode="1", coherent=False):
-        a = self.args(coherent)
+    def occluded(self, scene, rays, mode="1", coherent=False, args=None):
+        a = args if args is not None else self.args(coherent)
         n = len(rays)
         if mode == "1":
             base, st = rays.ctypes.data, rays.dtype.itemsize

@@ -153,14 +153,23 @@ struct RTCB200_ALIGN(16) RTCBounds { /* rtcore_common.h:163-167 */
 };
 struct RTCB200_ALIGN(16) RTCLinearBounds { struct RTCBounds bounds0, bounds1; };
 
-/* per-query context and arguments (rtcore_common.h:335-361, rtcore_scene.h:34-86).  Host callbacks cannot run
- * inside a device traversal: `filter`/`intersect`/`occluded` must be NULL, otherwise the call records
- * RTC_ERROR_INVALID_OPERATION on the device and returns without tracing. */
+/* per-query context and arguments (rtcore_common.h:335-361, rtcore_scene.h:34-86).  `filter` is honoured by the
+ * host-pointer entry points (see below); the Device entry points cannot call back into the host and record
+ * RTC_ERROR_INVALID_OPERATION when a filter applies.  `intersect`/`occluded` (user geometries) must be NULL. */
 struct RTCRayQueryContext {
   unsigned int instID[RTC_MAX_INSTANCE_LEVEL_COUNT];
   unsigned int instPrimID[RTC_MAX_INSTANCE_LEVEL_COUNT];
 };
-typedef void (*RTCFilterFunctionN)(const void* args);
+/* Filter callbacks (rtcore_common.h:311-324): called on the HOST for every candidate hit of a geometry that has a filter
+ * (or, with RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER / rtcSetGeometryEnableFilterFunctionFromArguments, for the
+ * arguments' filter), always with N == 1: `ray` is an RTCRay whose tfar is the candidate distance, `hit` an RTCHit.
+ * Setting valid[0] = 0 rejects the hit and the traversal goes on without it.  Host-pointer entry points only. */
+struct RTCRayN;
+struct RTCHitN;
+struct RTCFilterFunctionNArguments {
+  int* valid; void* geometryUserPtr; struct RTCRayQueryContext* context; struct RTCRayN* ray; struct RTCHitN* hit; unsigned int N;
+};
+typedef void (*RTCFilterFunctionN)(const struct RTCFilterFunctionNArguments* args);
 typedef void (*RTCIntersectFunctionN)(const void* args);
 typedef void (*RTCOccludedFunctionN)(const void* args);
 struct RTCIntersectArguments {

@@ -185,6 +185,34 @@ def main_curves():
     run_curves("curves_flat", [(v, t, 0, 0xFFFFFFFF)], [(cv3, ci3, None, 1, 0x3, True), (cv2, ci2, None, 2, 0xFFFFFFFD, True)], rays2)
 
 
+def main_filters():
+    """Filter callbacks (tests/filter_cases.py) on the cube_ground scene: the reference's results with a geometry filter,
+    the arguments' filter on every geometry, and the arguments' filter enabled on one geometry."""
+    from tests import filter_cases as fc
+    from tests.conftest import load_golden
+    meshes, rin, _wi, _wo, _b = load_golden("cube_ground")
+    R = load_reference()
+    dev = R.new_device(None)
+    d = {}
+    for cfg in fc.CONFIGS:
+        oi, oo, ri, ro = fc.run_config(R, dev, meshes, rin, cfg, "1")
+        o16, oo16, r16, _q = fc.run_config(R, dev, meshes, rin, cfg, "16")
+        if cfg == "argument_all":
+            # Reference quirk: its PACKET intersectors are picked at commit (accel.h:240-253, scene.cpp:801
+            # accels_select(hasFilterFunction())); when no geometry carries or enables a filter the "nofilter" variants
+            # run and RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER is ignored by rtcIntersect4/8/16.  The single-ray entry
+            # point honours the flag as documented (context.h:48-50, filter.h:25-28): that is the golden behaviour.
+            assert len(r16.calls) == 0
+        else:
+            assert (o16["primID"] == oi["primID"]).all() and (oo16["tfar"].view(np.uint32) == oo["tfar"].view(np.uint32)).all()
+        d[cfg + "_intersect"], d[cfg + "_occluded"] = oi.view(np.uint8).reshape(-1, 96), oo.view(np.uint8).reshape(-1, 48)
+        rej = sum(1 for c in ri.calls if fc.rejects(c[1], c[2], c[3]))
+        print(f"filters/{cfg}: {len(ri.calls)} intersect callbacks ({rej} rejected), {len(ro.calls)} occluded callbacks, "
+              f"hit rate {(oi['geomID'] != 0xFFFFFFFF).mean():.3f}, occluded {(oo['tfar'] == -np.inf).mean():.3f}")
+    R.rtcReleaseDevice(dev)
+    np.savez_compressed(os.path.join(HERE, "filters.npz"), **d)
+
+
 def main():
     # 1. the triangle_geometry tutorial scene: cube (geomID 0) + ground plane (geomID 1), camera-like + random rays
     (cv, ct), (gv, gt) = scenes.cube_and_ground()
@@ -246,11 +274,15 @@ def main():
     run_instances("instances", [(sv, st, 0, 0xFFFFFFFF), (sv2, st, 1, 0x3)], [(gv, gt, 0, 0xFFFFFFFF)], xf,
                   [0xFFFFFFFF if i % 3 else 0x5 for i in range(7)], r)
     main_curves()
+    main_filters()
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "curves":
         main_curves()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "filters":
+        main_filters()
         sys.exit(0)
     if load_reference() is None:
         sys.exit("oracle/_ref/libembree4.so.4 missing: run python oracle/build_ref.py first")
