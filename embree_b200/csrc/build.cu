@@ -126,6 +126,26 @@ __device__ __forceinline__ void load_curve(const GeomDesc& g, uint32_t lp, float
   ok &= fminf(p0.w, p1.w) >= 0.0f;
 }
 
+// flat cubic curve lp of geometry g (scene_curves.h:498-533 valid()): all four control points (Hermite: both vertices
+// and tangents) exist and are finite, radii included
+__device__ __forceinline__ void load_cubic(const GeomDesc& g, uint32_t lp, CurveVtx cp[4], uint32_t& vid, bool& ok) {
+  vid = *reinterpret_cast<const uint32_t*>(g.idx + (uint64_t)lp * g.istride);
+  ok = (uint64_t)vid + (g.hermite ? 1 : 3) < g.nverts;
+  if (!ok) return;
+  if (g.hermite) {   // validity is checked on the vertices and tangents themselves (scene_curves.h:661-676)
+    for (int k = 0; k < 2; ++k) {
+      const float* a = reinterpret_cast<const float*>(g.verts + (uint64_t)(vid + k) * g.vstride);
+      const float* t = reinterpret_cast<const float*>(g.tangents + (uint64_t)(vid + k) * g.tstride);
+      for (int c = 0; c < 4; ++c) ok &= (a[c] > -kFltLarge) & (a[c] < kFltLarge) & (t[c] > -kFltLarge) & (t[c] < kFltLarge);
+    }
+  }
+  load_cubic_cp(g, vid, cp);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    ok &= (cp[k].x > -kFltLarge) & (cp[k].x < kFltLarge) & (cp[k].y > -kFltLarge) & (cp[k].y < kFltLarge) & (cp[k].z > -kFltLarge) &
+          (cp[k].z < kFltLarge) & (cp[k].r > -kFltLarge) & (cp[k].r < kFltLarge);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // 1. PrimRef generation + scene / centroid bounds
 // ---------------------------------------------------------------------------------------------------
@@ -138,7 +158,44 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
   if (p < ntot) {
     const int g = find_geom(offs, ngeoms, p);
     float v[9], pad[3] = {0.0f, 0.0f, 0.0f};
-    if (geoms[g].is_curve) {   // merge(p0, p1) enlarged by the larger radius; two extra ulp of the magnitudes keep it conservative
+    if (geoms[g].is_curve == 3) {
+      // accurateFlatBounds (bezier_curve.h:631-664, bspline_curve.h:244-275) + enlarge_bounds (scene_curves.cpp:433-437): box of
+      // the tessellation points (and the last control point), enlarged by the largest |radius| and by 4 ulp of the largest
+      // magnitude.  The ribbon's quads are p +- r n with |n| = 1 evaluated in ray space, so the union of the spheres
+      // around the tessellation points holds them; directed rounding + 2 ulp cover the world / ray-space difference.
+      CurveVtx cp[4];
+      uint32_t vid;
+      load_cubic(geoms[g], p - offs[g], cp, vid, ok);
+      if (ok) {
+        const int n = (int)geoms[g].tess, st = n + 1;
+        const float* tab = geoms[g].basis_tab;
+        // the curve's end point: the last control point of a Bezier curve, the table's last column otherwise
+        const bool bez = geoms[g].basis == BASIS_BEZIER;
+        float rmax = bez ? fabsf(cp[3].r) : 0.0f;
+        float plo[3] = {bez ? cp[3].x : INFINITY, bez ? cp[3].y : INFINITY, bez ? cp[3].z : INFINITY};
+        float phi[3] = {bez ? cp[3].x : -INFINITY, bez ? cp[3].y : -INFINITY, bez ? cp[3].z : -INFINITY};
+        for (int j = 0; j <= n; ++j) {
+          const float q[3] = {curve_blend(tab + j, st, cp[0].x, cp[1].x, cp[2].x, cp[3].x), curve_blend(tab + j, st, cp[0].y, cp[1].y, cp[2].y, cp[3].y),
+                              curve_blend(tab + j, st, cp[0].z, cp[1].z, cp[2].z, cp[3].z)};
+          rmax = fmaxf(rmax, fabsf(curve_blend(tab + j, st, cp[0].r, cp[1].r, cp[2].r, cp[3].r)));
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { plo[a] = fminf(plo[a], q[a]); phi[a] = fmaxf(phi[a], q[a]); }
+        }
+        float size = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          lo[a] = __fsub_rd(plo[a], rmax); hi[a] = __fadd_ru(phi[a], rmax);
+          size = fmaxf(size, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+        }
+        const float e = 4.0f * 1.1920929e-07f * size;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          lo[a] = __fsub_rd(lo[a], e); hi[a] = __fadd_ru(hi[a], e);
+          lo[a] -= fabsf(lo[a]) * 2.4e-7f; hi[a] += fabsf(hi[a]) * 2.4e-7f;
+        }
+        ok &= (lo[0] > -kFltLarge) & (hi[0] < kFltLarge) & (lo[1] > -kFltLarge) & (hi[1] < kFltLarge) & (lo[2] > -kFltLarge) & (hi[2] < kFltLarge);
+      }
+    } else if (geoms[g].is_curve) {   // merge(p0, p1) enlarged by the larger radius; two extra ulp of the magnitudes keep it conservative
       float4 c0, c1;
       uint32_t vid;
       load_curve(geoms[g], p - offs[g], c0, c1, vid, ok);
@@ -485,6 +542,15 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
   const GeomDesc gd = geoms[g];
   float v[9];
   bool ok;
+  if (gd.is_curve == 3) {   // flat cubic curve record: a = (-, -, -, primID), b = (-, -, -, descriptor), c = (-, -, first vertex, mask)
+    const uint32_t lp = p - offs[g];
+    const uint32_t vid = *reinterpret_cast<const uint32_t*>(gd.idx + (uint64_t)lp * gd.istride);
+    float4* dst = reinterpret_cast<float4*>(&out[t]);
+    dst[0] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(lp));
+    dst[1] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float((uint32_t)g));
+    dst[2] = make_float4(0.0f, 0.0f, __uint_as_float(vid), __uint_as_float(gd.mask));
+    return;
+  }
   if (gd.is_curve) {   // curve record: a = (p0.xyz, primID), b = (p1.xyz, descriptor), c = (r0, r1, first vertex | flags << 30, mask)
     float4 c0, c1;
     uint32_t vid;

@@ -248,7 +248,7 @@ RT_HD void pluecker_uv(const PlueckerHit& h, float& u, float& v) {   // Pluecker
 // of curves is off in the reference's default build, so both the entry and the exit surface are candidates; a closest-hit
 // query takes the first candidate inside [tnear, tfar] exactly as the reference's epilog sequence does (:614-640).
 // ------------------------------------------------------------------------------------------------
-struct CurveHit { float t, u, ngx, ngy, ngz; };
+struct CurveHit { float t, u, ngx, ngy, ngz, v = 0.0f; };   // v: only the ribbons of cubic curves report one (linear curves: 0)
 struct CurveVtx { float x, y, z, r; };
 
 // Every product / sum below is an explicitly rounded fp32 operation (mul_rn / add_rn / sub_rn, dot products as the
@@ -408,6 +408,184 @@ RT_HD bool flat_curve_test(float ox, float oy, float oz, float dx_, float dy_, f
   const float Tx = sub_rn(v1.x, v0.x), Ty = sub_rn(v1.y, v0.y), Tz = sub_rn(v1.z, v0.z);
   if (!((Tx != 0.0f) | (Ty != 0.0f) | (Tz != 0.0f))) return false;     // denormalised segment
   h.t = t; h.u = u; h.ngx = Tx; h.ngy = Ty; h.ngz = Tz;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat cubic curves (RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE / _BSPLINE_ / _CATMULL_ROM_ / _HERMITE_): intersect_ribbon
+// (kernels/geometry/curve_intersector_ribbon.h:73-190) restated for one curve.  The curve is tessellated into N =
+// tessellation rate segments at u = j / N; the control points go to ray space (CurvePrecalculations1: frame of the
+// normalised direction, z = ray parameter), every segment becomes a ray-facing quad p +- r * n (n = normalised 2D normal of
+// the curve derivative at the segment ends) and is intersected with the z axis (intersect_quad_backface_culling,
+// quad_intersector.h:14-84, with O = 0, D = (0, 0, 1)).  Segments are processed in chunks of 8 as the reference's
+// 8-wide loop does: inside a chunk the smallest t wins (lowest segment on a tie, select_min), and a chunk's winner
+// shortens the ray for the next chunk (the epilog writes ray.tfar).  The basis weights come from a table built by the
+// host exactly as the reference builds its own at start-up (PrecomputedBezierBasis, subdiv/bezier_curve.cpp:8-27 and the
+// B-spline / Catmull-Rom twins): tab[k][j], k = 0..3 position weights, 4..7 derivative weights, j = 0..N.  Hermite curves
+// enter as the Bezier control points (p0, p0 + t0/3, p1 - t1/3, p1) the reference converts them to (hermite_curve.h).
+// Every operation is explicitly rounded, so the device and the C oracle evaluate the same expressions.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxTess = 16;                         // PrecomputedBezierBasis::N
+enum CurveBasis : uint32_t { BASIS_BEZIER = 0, BASIS_BSPLINE = 1, BASIS_CATMULL_ROM = 2 };
+
+// basis derivative weights at parameter u (BezierBasis / BSplineBasis / CatmullRomBasis ::derivative): the hit's Ng = dP/du
+RT_HD void curve_basis_derivative(uint32_t basis, float u, float b[4]) {
+  const float t = u, s = sub_rn(1.0f, u);
+  if (basis == BASIS_BEZIER) {
+    const float st = mul_rn(s, t), ss = mul_rn(s, s), tt = mul_rn(t, t);
+    b[0] = mul_rn(3.0f, -ss); b[1] = mul_rn(3.0f, fma_rn(-2.0f, st, ss)); b[2] = mul_rn(3.0f, msub(2.0f, st, tt)); b[3] = mul_rn(3.0f, tt);
+  } else if (basis == BASIS_BSPLINE) {
+    const float st = mul_rn(s, t), ss = mul_rn(s, s), tt = mul_rn(t, t);
+    b[0] = mul_rn(0.5f, -ss); b[1] = mul_rn(0.5f, sub_rn(-tt, mul_rn(4.0f, st)));
+    b[2] = mul_rn(0.5f, add_rn(ss, mul_rn(4.0f, st))); b[3] = mul_rn(0.5f, tt);
+  } else {
+    const float st = mul_rn(s, t), ss = mul_rn(s, s), tt = mul_rn(t, t);
+    b[0] = mul_rn(0.5f, add_rn(-ss, mul_rn(2.0f, st)));
+    b[1] = mul_rn(0.5f, add_rn(mul_rn(mul_rn(2.0f, t), sub_rn(mul_rn(3.0f, t), 5.0f)), mul_rn(3.0f, tt)));
+    b[2] = mul_rn(0.5f, sub_rn(mul_rn(mul_rn(2.0f, s), add_rn(mul_rn(3.0f, t), 2.0f)), mul_rn(3.0f, ss)));
+    b[3] = mul_rn(0.5f, add_rn(mul_rn(-2.0f, st), tt));
+  }
+}
+// basis position / derivative weights at u as the reference's start-up tables hold them (scalar code of the base library:
+// BezierBasis::eval etc. with unfused products; the derivative of the Bezier basis uses madd / msub)
+RT_HD void curve_basis_table_entry(uint32_t basis, float u, float c[4], float d[4]) {
+  const float t = u, s = sub_rn(1.0f, u);
+  if (basis == BASIS_BEZIER) {
+    c[0] = mul_rn(mul_rn(s, s), s); c[1] = mul_rn(mul_rn(3.0f, t), mul_rn(s, s));
+    c[2] = mul_rn(mul_rn(3.0f, mul_rn(t, t)), s); c[3] = mul_rn(mul_rn(t, t), t);
+    const float st = mul_rn(s, t), ss = mul_rn(s, s), tt = mul_rn(t, t);
+    d[0] = mul_rn(3.0f, -ss); d[1] = mul_rn(3.0f, add_rn(mul_rn(-2.0f, st), ss)); d[2] = mul_rn(3.0f, sub_rn(mul_rn(2.0f, st), tt)); d[3] = mul_rn(3.0f, tt);
+  } else if (basis == BASIS_BSPLINE) {
+    const float sss = mul_rn(mul_rn(s, s), s), ttt = mul_rn(mul_rn(t, t), t);
+    const float sts = mul_rn(mul_rn(s, t), s), tst = mul_rn(mul_rn(t, s), t);
+    const float k = 1.0f / 6.0f;
+    c[0] = mul_rn(k, sss);
+    c[1] = mul_rn(k, add_rn(add_rn(mul_rn(4.0f, sss), ttt), add_rn(mul_rn(12.0f, sts), mul_rn(6.0f, tst))));
+    c[2] = mul_rn(k, add_rn(add_rn(mul_rn(4.0f, ttt), sss), add_rn(mul_rn(12.0f, tst), mul_rn(6.0f, sts))));
+    c[3] = mul_rn(k, ttt);
+    curve_basis_derivative(basis, u, d);
+  } else {
+    c[0] = mul_rn(0.5f, mul_rn(mul_rn(-t, s), s));
+    c[1] = mul_rn(0.5f, add_rn(2.0f, mul_rn(mul_rn(t, t), sub_rn(mul_rn(3.0f, t), 5.0f))));
+    c[2] = mul_rn(0.5f, add_rn(2.0f, mul_rn(mul_rn(s, s), sub_rn(mul_rn(3.0f, s), 5.0f))));
+    c[3] = mul_rn(0.5f, mul_rn(mul_rn(-s, t), t));
+    curve_basis_derivative(basis, u, d);
+  }
+}
+// tab[8][n + 1] for tessellation rate n (u = j / n as float(j) / float(n), bezier_curve.cpp:14)
+RT_HD void curve_basis_table(uint32_t basis, int n, float* tab) {
+  for (int j = 0; j <= n; ++j) {
+    float c[4], d[4];
+    curve_basis_table_entry(basis, (float)j / (float)n, c, d);
+    for (int k = 0; k < 4; ++k) { tab[k * (n + 1) + j] = c[k]; tab[(4 + k) * (n + 1) + j] = d[k]; }
+  }
+}
+
+struct RaySpace { float ax, ay, az, bx, by, bz, zx, zy, zz, depth_scale; };
+// CurvePrecalculations1 (curve_intersector_precalculations.h:15-28); same operations as in flat_curve_test above
+RT_HD RaySpace curve_ray_space(float dx_, float dy_, float dz_) {
+  RaySpace q;
+  q.depth_scale = rcp_rn(sqrtf(dot3(dx_, dy_, dz_, dx_, dy_, dz_)));
+  const float Nx = mul_rn(q.depth_scale, dx_), Ny = mul_rn(q.depth_scale, dy_), Nz = mul_rn(q.depth_scale, dz_);
+  const bool first = dot3(0.0f, Nz, -Ny, 0.0f, Nz, -Ny) > dot3(-Nz, 0.0f, Nx, -Nz, 0.0f, Nx);
+  const float sx = first ? 0.0f : -Nz, sy = first ? Nz : 0.0f, sz = first ? -Ny : Nx;
+  const float il = rcp_rn(sqrtf(dot3(sx, sy, sz, sx, sy, sz)));
+  q.ax = mul_rn(sx, il); q.ay = mul_rn(sy, il); q.az = mul_rn(sz, il);
+  float bx = msub(Ny, q.az, mul_rn(Nz, q.ay)), by = msub(Nz, q.ax, mul_rn(Nx, q.az)), bz = msub(Nx, q.ay, mul_rn(Ny, q.ax));
+  const float jl = rcp_rn(sqrtf(dot3(bx, by, bz, bx, by, bz)));
+  q.bx = mul_rn(bx, jl); q.by = mul_rn(by, jl); q.bz = mul_rn(bz, jl);
+  q.zx = mul_rn(Nx, q.depth_scale); q.zy = mul_rn(Ny, q.depth_scale); q.zz = mul_rn(Nz, q.depth_scale);
+  return q;
+}
+
+// weighted sum of the four control values: madd(c0, v0, madd(c1, v1, madd(c2, v2, c3 * v3))) (bezier_curve.h:512-526)
+RT_HD float curve_blend(const float* w, int stride, float v0, float v1, float v2, float v3) {
+  return fma_rn(w[0], v0, fma_rn(w[stride], v1, fma_rn(w[2 * stride], v2, mul_rn(w[3 * stride], v3))));
+}
+
+RT_HD bool flat_cubic_test(float ox, float oy, float oz, float dx_, float dy_, float dz_, float tnear, float tfar, const CurveVtx cp[4],
+                           uint32_t basis, int N, const float* tab, CurveHit& h) {
+  const RaySpace rs = curve_ray_space(dx_, dy_, dz_);
+  // control points in ray space (xfm_pr, bezier_curve.h:216-223); w = radius
+  float qx[4], qy[4], qz[4], qw[4];
+  float amax = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a0 = sub_rn(cp[k].x, ox), a1 = sub_rn(cp[k].y, oy), a2 = sub_rn(cp[k].z, oz);
+    qx[k] = dot3(a0, a1, a2, rs.ax, rs.ay, rs.az); qy[k] = dot3(a0, a1, a2, rs.bx, rs.by, rs.bz); qz[k] = dot3(a0, a1, a2, rs.zx, rs.zy, rs.zz);
+    qw[k] = cp[k].r;
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(qx[k]), fabsf(qy[k])), fabsf(qz[k])));
+  }
+  const float eps = mul_rn(mul_rn(4.0f, 1.1920929e-07f), amax);
+  const int st = N + 1;
+  bool ishit = false;
+  float ray_tfar = tfar;
+  for (int i0 = 0; i0 < N; i0 += 8) {
+    bool any = false;
+    float bt = 0.0f, bu = 0.0f, bv = 0.0f;
+    int bj = 0;
+    const int i1 = (i0 + 8 < N) ? i0 + 8 : N;
+    for (int j = i0; j < i1; ++j) {
+      const float* c0 = tab + j;           // weights of the segment's first point, +1: of its second point
+      const float p0x = curve_blend(c0, st, qx[0], qx[1], qx[2], qx[3]), p0y = curve_blend(c0, st, qy[0], qy[1], qy[2], qy[3]);
+      const float p0z = curve_blend(c0, st, qz[0], qz[1], qz[2], qz[3]), p0w = curve_blend(c0, st, qw[0], qw[1], qw[2], qw[3]);
+      const float p1x = curve_blend(c0 + 1, st, qx[0], qx[1], qx[2], qx[3]), p1y = curve_blend(c0 + 1, st, qy[0], qy[1], qy[2], qy[3]);
+      const float p1z = curve_blend(c0 + 1, st, qz[0], qz[1], qz[2], qz[3]), p1w = curve_blend(c0 + 1, st, qw[0], qw[1], qw[2], qw[3]);
+      // cylinder culling (:56-70): squared distance of the origin to the line p0 -> p1 in the projection plane
+      const float ex = sub_rn(p1x, p0x), ey = sub_rn(p1y, p0y);
+      const float num = msub(ex, p0y, mul_rn(ey, p0x)), den2 = fma_rn(ex, ex, mul_rn(ey, ey));
+      const float rmax = fmaxf(p0w, p1w);
+      if (!(mul_rn(num, num) <= mul_rn(mul_rn(rmax, rmax), den2))) continue;
+      const float* d0 = tab + 4 * st + j;
+      float t0x = curve_blend(d0, st, qx[0], qx[1], qx[2], qx[3]), t0y = curve_blend(d0, st, qy[0], qy[1], qy[2], qy[3]);
+      const float t0z = curve_blend(d0, st, qz[0], qz[1], qz[2], qz[3]);
+      float t1x = curve_blend(d0 + 1, st, qx[0], qx[1], qx[2], qx[3]), t1y = curve_blend(d0 + 1, st, qy[0], qy[1], qy[2], qy[3]);
+      const float t1z = curve_blend(d0 + 1, st, qz[0], qz[1], qz[2], qz[3]);
+      if (fmaxf(fmaxf(fabsf(t0x), fabsf(t0y)), fabsf(t0z)) < eps) { t0x = ex; t0y = ey; }   // vanishing derivative: the chord (:100-101)
+      if (fmaxf(fmaxf(fabsf(t1x), fabsf(t1y)), fabsf(t1z)) < eps) { t1x = ex; t1y = ey; }
+      // unit normals of the projected tangents, n = (dy, -dx, 0)
+      const float l0 = rcp_rn(sqrtf(fma_rn(t0y, t0y, mul_rn(t0x, t0x)))), l1 = rcp_rn(sqrtf(fma_rn(t1y, t1y, mul_rn(t1x, t1x))));
+      const float n0x = mul_rn(t0y, l0), n0y = mul_rn(-t0x, l0), n1x = mul_rn(t1y, l1), n1y = mul_rn(-t1x, l1);
+      // quad corners: va = lp0, vb = lp1, vc = up1, vd = up0 (:106-112); z is untouched (n.z = 0)
+      const float vax = fma_rn(p0w, n0x, p0x), vay = fma_rn(p0w, n0y, p0y), vaz = p0z;
+      const float vbx = fma_rn(p1w, n1x, p1x), vby = fma_rn(p1w, n1y, p1y), vbz = p1z;
+      const float vcx = fma_rn(-p1w, n1x, p1x), vcy = fma_rn(-p1w, n1y, p1y), vcz = p1z;
+      const float vdx = fma_rn(-p0w, n0x, p0x), vdy = fma_rn(-p0w, n0y, p0y), vdz = p0z;
+      // intersect_quad_backface_culling with O = 0, D = (0,0,1): dot(x, D) = x.z
+      const float edbx = sub_rn(vbx, vdx), edby = sub_rn(vby, vdy);
+      const float WW = msub(vdx, edby, mul_rn(vdy, edbx));
+      const bool sel = WW <= 0.0f;
+      const float v0x = sel ? vax : vcx, v0y = sel ? vay : vcy, v0z = sel ? vaz : vcz;
+      const float v1x = sel ? vbx : vdx, v1y = sel ? vby : vdy, v1z = sel ? vbz : vdz;
+      const float v2x = sel ? vdx : vbx, v2y = sel ? vdy : vby, v2z = sel ? vdz : vbz;
+      const float e0x = sub_rn(v2x, v0x), e0y = sub_rn(v2y, v0y), e0z = sub_rn(v2z, v0z);
+      const float e1x = sub_rn(v0x, v1x), e1y = sub_rn(v0y, v1y), e1z = sub_rn(v0z, v1z);
+      const float U = msub(v0x, e0y, mul_rn(v0y, e0x)), V = msub(v1x, e1y, mul_rn(v1y, e1x));
+      if (!(fmaxf(U, V) <= 0.0f)) continue;
+      const float ngx = msub(e1y, e0z, mul_rn(e1z, e0y)), ngy = msub(e1z, e0x, mul_rn(e1x, e0z)), ngz = msub(e1x, e0y, mul_rn(e1y, e0x));
+      const float den = ngz, rcpDen = rcp_rn(den);
+      const float t = mul_rn(rcpDen, dot3(v0x, v0y, v0z, ngx, ngy, ngz));
+      if (!((tnear <= t) & (t <= ray_tfar) & (den != 0.0f))) continue;
+      float u = mul_rn(U, rcpDen), v = mul_rn(V, rcpDen);
+      if (!sel) { u = sub_rn(1.0f, u); v = sub_rn(1.0f, v); }
+      const float r = fma_rn(sub_rn(1.0f, u), p0w, mul_rn(u, p1w));            // lerp(p0.w, p1.w, u), math.h
+      if (!(t > mul_rn(mul_rn(2.0f, r), rs.depth_scale))) continue;        // EMBREE_CURVE_SELF_INTERSECTION_AVOIDANCE_FACTOR = 2.0
+      if (!any || t < bt) { any = true; bt = t; bu = u; bv = v; bj = j; }   // select_min: the first lane on equal t
+    }
+    if (any) {
+      ishit = true;
+      ray_tfar = bt;
+      h.t = bt;
+      h.u = mul_rn(add_rn(add_rn((float)(bj - i0), bu), (float)i0), 1.0f / (float)N);   // RibbonHit::finalize (:27-32)
+      h.v = fma_rn(2.0f, bv, -1.0f);
+    }
+  }
+  if (!ishit) return false;
+  float b[4];
+  curve_basis_derivative(basis, h.u, b);                                   // Ng = curve3D.eval_du(u): the tangent
+  h.ngx = fma_rn(b[0], cp[0].x, fma_rn(b[1], cp[1].x, fma_rn(b[2], cp[2].x, mul_rn(b[3], cp[3].x))));
+  h.ngy = fma_rn(b[0], cp[0].y, fma_rn(b[1], cp[1].y, fma_rn(b[2], cp[2].y, mul_rn(b[3], cp[3].y))));
+  h.ngz = fma_rn(b[0], cp[0].z, fma_rn(b[1], cp[1].z, fma_rn(b[2], cp[2].z, mul_rn(b[3], cp[3].z))));
   return true;
 }
 

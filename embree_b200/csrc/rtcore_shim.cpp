@@ -126,6 +126,11 @@ struct BufferView {
 };
 
 enum class GeomState { MODIFIED, COMMITTED };
+bool is_linear_curve(RTCGeometryType t) { return t == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE || t == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE; }
+bool is_cubic_curve(RTCGeometryType t) {
+  return t == RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE || t == RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE || t == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE ||
+         t == RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE;
+}
 // number of live geometries that have a filter callback or accept the arguments' filter: while it is zero (and the
 // query carries no filter) no query looks at the geometries at all
 std::atomic<long> g_filterGeoms{0};
@@ -141,6 +146,8 @@ struct GeometryImpl : RefCounted {
   float w2l[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};  // world2local0 = rcp(local2world) (scene_instance.cpp:153)
   void update_world2local();
   BufferView vertices, indices, flags;   // flags: RTC_BUFFER_TYPE_FLAGS of a curve geometry (optional)
+  BufferView tangents;                   // RTC_BUFFER_TYPE_TANGENT of a Hermite curve geometry
+  int tessellationRate = 4;              // flat cubic curves (scene_curves.cpp:27,247)
   std::vector<BufferView> attribs;
   unsigned mask = 1;  // reference default (geometry.cpp:48)
   bool enabled = true;
@@ -330,10 +337,53 @@ void commit_scene(SceneImpl* s) {
     d.geomID = geomID; d.mask = g->mask; d.is_curve = g->type == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE ? 2 : 1;
     descs.push_back(d);
   };
+  // flat cubic curves (scene_curves.cpp): float4 control vertices, one index per curve (first control vertex), Hermite
+  // adds float4 tangents; the basis weights at the tessellation points are tabulated here as the reference tabulates them
+  auto add_cubic = [&](GeometryImpl* g, uint32_t geomID) {
+    const size_t ncurves = g->indices.count, nverts = g->vertices.count;
+    if (ncurves == 0 || !g->indices.buf) return;
+    if (!g->vertices.buf) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer not set");
+    const bool hermite = g->type == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE;
+    if (hermite && !g->tangents.buf) fail(RTC_ERROR_INVALID_OPERATION, "tangent buffer not set");
+    if (hermite && g->tangents.count != nverts) fail(RTC_ERROR_INVALID_OPERATION, "number of tangents must match number of vertices");   // scene_curves.cpp commit
+    if (ncurves > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "curve geometry too large");
+    curves = true;
+    const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 16 : 16, ibytes = (ncurves - 1) * g->indices.stride + 4;
+    void *dv = nullptr, *di = nullptr, *dt = nullptr, *db = nullptr;
+    cuda_check(cudaMallocAsync(&dv, vbytes, 0), "cudaMallocAsync(curve vertices)");
+    s->residentBuffers.push_back(dv);
+    cuda_check(cudaMallocAsync(&di, ibytes, 0), "cudaMallocAsync(curve indices)");
+    s->deviceBuffers.push_back(di);
+    cuda_check(cudaMemcpyAsync(dv, g->vertices.data(), vbytes, cudaMemcpyHostToDevice, 0), "upload curve vertices");
+    cuda_check(cudaMemcpyAsync(di, g->indices.data(), ibytes, cudaMemcpyHostToDevice, 0), "upload curve indices");
+    rtk::GeomDesc d;
+    if (hermite) {
+      const size_t tbytes = nverts ? (nverts - 1) * g->tangents.stride + 16 : 16;
+      cuda_check(cudaMallocAsync(&dt, tbytes, 0), "cudaMallocAsync(curve tangents)");
+      s->residentBuffers.push_back(dt);
+      cuda_check(cudaMemcpyAsync(dt, g->tangents.data(), tbytes, cudaMemcpyHostToDevice, 0), "upload curve tangents");
+      d.tangents = static_cast<const uint8_t*>(dt); d.tstride = g->tangents.stride; d.hermite = 1;
+    }
+    d.basis = g->type == RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE ? rtk::BASIS_BSPLINE : g->type == RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE ? rtk::BASIS_CATMULL_ROM : rtk::BASIS_BEZIER;
+    d.tess = (uint32_t)g->tessellationRate;
+    float tab[8 * (rtk::kMaxTess + 1)];
+    rtk::curve_basis_table(d.basis, g->tessellationRate, tab);
+    const size_t tabBytes = sizeof(float) * 8 * (g->tessellationRate + 1);
+    cuda_check(cudaMallocAsync(&db, tabBytes, 0), "cudaMallocAsync(curve basis table)");
+    s->residentBuffers.push_back(db);
+    cuda_check(cudaMemcpyAsync(db, tab, tabBytes, cudaMemcpyHostToDevice, 0), "upload curve basis table");
+    cuda_check(cudaStreamSynchronize(0), "upload curve basis table");   // `tab` is on the stack
+    d.basis_tab = static_cast<const float*>(db);
+    d.verts = static_cast<const uint8_t*>(dv); d.idx = static_cast<const uint8_t*>(di);
+    d.vstride = g->vertices.stride; d.istride = g->indices.stride;
+    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)ncurves;
+    d.geomID = geomID; d.mask = g->mask; d.is_curve = 3;
+    descs.push_back(d);
+  };
   auto add_mesh = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
-    if (g->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE || g->type == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE) {
+    if (is_linear_curve(g->type) || is_cubic_curve(g->type)) {
       if (xfm) fail(RTC_ERROR_INVALID_OPERATION, "instanced curve geometries are not supported by the B200 back-end");
-      add_curves(g, geomID);
+      if (is_cubic_curve(g->type)) add_cubic(g, geomID); else add_curves(g, geomID);
       return;
     }
     const bool quad = g->type == RTC_GEOMETRY_TYPE_QUAD;
@@ -943,9 +993,8 @@ void rtcReleaseBuffer(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; AP
 RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
   API_BEGIN
   VERIFY_HANDLE(h);
-  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE && type != RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE &&
-      type != RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE)
-    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD, _ROUND_LINEAR_CURVE, _FLAT_LINEAR_CURVE and _INSTANCE are supported by the B200 back-end");
+  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE && !is_linear_curve(type) && !is_cubic_curve(type))
+    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD, _ROUND_LINEAR_CURVE, _FLAT_LINEAR_CURVE, _FLAT_BEZIER / _BSPLINE / _HERMITE / _CATMULL_ROM_CURVE and _INSTANCE are supported by the B200 back-end");
   GeometryImpl* g = new GeometryImpl(D(h));
   g->type = type;
   return reinterpret_cast<RTCGeometry>(g);
@@ -959,6 +1008,15 @@ void rtcReleaseGeometry(RTCGeometry g) { GEOM_BEGIN(g) G(g)->release(); GEOM_END
 void rtcCommitGeometry(RTCGeometry g) { GEOM_BEGIN(g) ++G(g)->modCounter; G(g)->state = GeomState::COMMITTED; GEOM_END }  // geometry.cpp:103-107
 void rtcEnableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (!G(g)->enabled) { G(g)->enabled = true; ++G(g)->modCounter; } GEOM_END }
 void rtcDisableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (G(g)->enabled) { G(g)->enabled = false; ++G(g)->modCounter; } GEOM_END }
+// scene_curves.cpp:244-249; every other geometry type: "operation not supported for this geometry" (geometry.h)
+void rtcSetGeometryTessellationRate(RTCGeometry g, float n) {
+  GEOM_BEGIN(g)
+  if (!is_cubic_curve(G(g)->type)) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+  const int r = (int)n;
+  G(g)->tessellationRate = r < 1 ? 1 : (r > 16 ? 16 : r);
+  G(g)->update();
+  GEOM_END
+}
 void rtcSetGeometryTimeStepCount(RTCGeometry g, unsigned int n) { GEOM_BEGIN(g) if (n != 1) fail(RTC_ERROR_INVALID_OPERATION, "motion blur is not supported by the B200 back-end"); GEOM_END }
 void rtcSetGeometryVertexAttributeCount(RTCGeometry g, unsigned int n) { GEOM_BEGIN(g) G(g)->attribs.resize(n); G(g)->update(); GEOM_END }
 void rtcSetGeometryMask(RTCGeometry g, unsigned int mask) { GEOM_BEGIN(g) G(g)->mask = mask; G(g)->update(); GEOM_END }
@@ -973,8 +1031,16 @@ void rtcSetGeometryBuildQuality(RTCGeometry g, enum RTCBuildQuality q) {
 static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFormat format, BufferImpl* buf, size_t off, size_t stride, size_t num) {
   // scene_triangle_mesh.cpp:35-80, scene_quad_mesh.cpp:35-80
   if (g->type == RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
-  const bool curve = g->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE || g->type == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE;   // scene_line_segments.cpp:35-100
-  if (curve && type == RTC_BUFFER_TYPE_FLAGS) {
+  const bool curve = is_linear_curve(g->type) || is_cubic_curve(g->type);   // scene_line_segments.cpp:35-100, scene_curves.cpp:50-140
+  if (g->type == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE && type == RTC_BUFFER_TYPE_TANGENT) {
+    if (((size_t)(buf->ptr) + off) & 3 || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
+    if (format != RTC_FORMAT_FLOAT4) fail(RTC_ERROR_INVALID_OPERATION, "invalid tangent buffer format");
+    if (slot != 0) fail(RTC_ERROR_INVALID_OPERATION, "invalid tangent buffer slot");
+    g->tangents.set(buf, off, stride, num, format);
+    g->update();
+    return;
+  }
+  if (is_linear_curve(g->type) && type == RTC_BUFFER_TYPE_FLAGS) {
     if (format != RTC_FORMAT_UCHAR) fail(RTC_ERROR_INVALID_OPERATION, "invalid flag buffer format");
     if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot");
     g->flags.set(buf, off, stride, num, format);
@@ -1414,7 +1480,6 @@ RTCB200_UNSUPPORTED(rtcSetGeometryIntersectFunction)
 RTCB200_UNSUPPORTED(rtcSetGeometryOccludedFunction)
 RTCB200_UNSUPPORTED(rtcSetGeometryPointQueryFunction)
 RTCB200_UNSUPPORTED(rtcSetGeometrySubdivisionMode)
-RTCB200_UNSUPPORTED(rtcSetGeometryTessellationRate)
 RTCB200_UNSUPPORTED(rtcSetGeometryTopologyCount)
 RTCB200_UNSUPPORTED(rtcSetGeometryTransformQuaternion)
 RTCB200_UNSUPPORTED(rtcSetGeometryUserPrimitiveCount)

@@ -29,11 +29,43 @@ struct GeomDesc {
   // round linear curves (RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE): verts = float4 (xyz, radius), idx = first vertex of each
   // segment, ntris = segments; `flags` = one neighbour-flag byte per segment (device).  The vertex buffer stays resident
   // after the build: the trace kernel fetches the neighbour vertices from it.
-  uint32_t is_curve = 0;   // 1 round linear (cone-sphere), 2 flat linear (ray-facing ribbon)
+  uint32_t is_curve = 0;   // 1 round linear (cone-sphere), 2 flat linear (ray-facing ribbon), 3 flat cubic (tessellated ribbon)
   const uint8_t* flags = nullptr;
+  // flat cubic curves (RTC_GEOMETRY_TYPE_FLAT_BEZIER / _BSPLINE / _CATMULL_ROM / _HERMITE_CURVE): idx = first of the four
+  // control vertices (Hermite: of the two vertex / tangent pairs), `basis` = rt_core.cuh CurveBasis of the control points,
+  // `tess` = tessellation rate N, `basis_tab` = device table [8][N + 1] of the basis / derivative weights at u = j / N,
+  // `tangents` = the resident float4 tangent buffer of a Hermite geometry (converted to Bezier control points on load).
+  uint32_t basis = 0, tess = 4, hermite = 0;
+  const float* basis_tab = nullptr;
+  const uint8_t* tangents = nullptr;
+  uint64_t tstride = 0;
   float xfm[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
   float w2l[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
 };
+
+#if defined(__CUDACC__)
+// the four control points of the flat cubic curve whose index-buffer entry is `vid` (CurveGeometry::gather,
+// scene_curves.h:107-113; Hermite: HermiteCurveT's conversion to Bezier control points, hermite_curve.h:19-20)
+__device__ __forceinline__ void load_cubic_cp(const GeomDesc& g, uint32_t vid, CurveVtx cp[4]) {
+  if (g.hermite) {
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(g.verts + (size_t)vid * g.vstride));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(g.verts + (size_t)(vid + 1) * g.vstride));
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(g.tangents + (size_t)vid * g.tstride));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(g.tangents + (size_t)(vid + 1) * g.tstride));
+    const float k = 1.0f / 3.0f;
+    cp[0] = CurveVtx{p0.x, p0.y, p0.z, p0.w};
+    cp[1] = CurveVtx{fma_rn(k, t0.x, p0.x), fma_rn(k, t0.y, p0.y), fma_rn(k, t0.z, p0.z), fma_rn(k, t0.w, p0.w)};
+    cp[2] = CurveVtx{fma_rn(-k, t1.x, p1.x), fma_rn(-k, t1.y, p1.y), fma_rn(-k, t1.z, p1.z), fma_rn(-k, t1.w, p1.w)};
+    cp[3] = CurveVtx{p1.x, p1.y, p1.z, p1.w};
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(g.verts + (size_t)(vid + k) * g.vstride));
+    cp[k] = CurveVtx{q.x, q.y, q.z, q.w};
+  }
+}
+#endif
 
 enum BuilderKind : uint32_t { BUILDER_LBVH = 0, BUILDER_SAH = 1 };
 

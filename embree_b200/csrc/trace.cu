@@ -114,6 +114,11 @@ __device__ __forceinline__ void to_object_space(const GeomDesc& d, Ray& r) {
 // mask).  The neighbour vertices -- needed to cut away what lies inside the adjacent segments -- come from the geometry's
 // resident float4 vertex buffer (LineSegments::gather, scene_line_segments.h:270-276).
 __device__ __noinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h) {
+  if (d.is_curve == 3) {   // flat cubic curve (Bezier / B-spline / Catmull-Rom / Hermite): control points from the resident vertex buffer
+    CurveVtx cp[4];
+    load_cubic_cp(d, c.z, cp);
+    return flat_cubic_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, cp, d.basis, (int)d.tess, d.basis_tab, h);
+  }
   const CurveVtx v0{__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(c.x)};
   const CurveVtx v1{__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.y)};
   if (d.is_curve == 2)   // RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE: ray-facing ribbon, no neighbours involved
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         if (visible && curve_record_test(d, wr, tfar_tri, a, b, c, ch)) {
           found = true;
           if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
-          else { tfar_tri = ch.t; hit_u = ch.u; hit_v = 0.0f; hit_tri = ti; }
+          else { tfar_tri = ch.t; hit_u = ch.u; hit_v = ch.v; hit_tri = ti; }
         }
         return;
       }

@@ -23,6 +23,10 @@ RTC_GEOMETRY_TYPE_QUAD = 1
 RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE = 16
 RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE = 17
 RTC_GEOMETRY_TYPE_INSTANCE = 121
+RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE, RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE = 25, 33
+RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE, RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE = 41, 59
+FLAT_CUBIC_TYPES = {"bezier": 25, "bspline": 33, "hermite": 41, "catmull_rom": 59}
+RTC_BUFFER_TYPE_TANGENT = 4
 RTC_FORMAT_UCHAR = 0x1001
 RTC_FORMAT_UINT = 0x5001
 RTC_FORMAT_FLOAT4 = 0x9004
@@ -209,6 +213,7 @@ class RTCLib:
         "rtcSetNewGeometryBuffer": (C.c_void_p, [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_size_t, C.c_size_t]),
         "rtcGetGeometryBufferData": (C.c_void_p, [C.c_void_p, C.c_int, C.c_uint]),
         "rtcUpdateGeometryBuffer": (None, [C.c_void_p, C.c_int, C.c_uint]),
+        "rtcSetGeometryTessellationRate": (None, [C.c_void_p, C.c_float]),
         "rtcSetGeometryUserData": (None, [C.c_void_p, C.c_void_p]),
         "rtcGetGeometryUserData": (C.c_void_p, [C.c_void_p]),
         "rtcSetGeometryIntersectFilterFunction": (None, [C.c_void_p, C.c_void_p]),
@@ -340,6 +345,33 @@ class RTCLib:
             gid = geom_id
         self.rtcReleaseGeometry(g)
         return gid, tuple(keep)
+
+    def add_flat_cubic_curves(self, device, scene, vertices4, indices, basis="bezier", tess=None, tangents=None, mask=None, geom_id=None):
+        """RTC_GEOMETRY_TYPE_FLAT_{BEZIER,BSPLINE,CATMULL_ROM,HERMITE}_CURVE: shared FLOAT4 control vertices (xyz, radius), UINT index
+        of each curve's first control vertex, FLOAT4 tangents for 'hermite', optional tessellation rate (tutorials/curve_geometry,
+        hair_geometry).  The arrays must stay alive."""
+        v = np.ascontiguousarray(vertices4, np.float32).reshape(-1, 4)
+        idx = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        g = self.rtcNewGeometry(device, FLAT_CUBIC_TYPES[basis])
+        self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT4, _ptr(v), 0, 16, v.shape[0])
+        self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT, _ptr(idx), 0, 4, idx.shape[0])
+        keep = [v, idx]
+        if basis == "hermite":
+            tg = np.ascontiguousarray(tangents, np.float32).reshape(-1, 4)
+            self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_TANGENT, 0, RTC_FORMAT_FLOAT4, _ptr(tg), 0, 16, tg.shape[0])
+            keep.append(tg)
+        if tess is not None:
+            self.rtcSetGeometryTessellationRate(g, float(tess))
+        if mask is not None:
+            self.rtcSetGeometryMask(g, mask)
+        self.rtcCommitGeometry(g)
+        if geom_id is None:
+            gid = self.rtcAttachGeometry(scene, g)
+        else:
+            self.rtcAttachGeometryByID(scene, g, geom_id)
+            gid = geom_id
+        self.rtcReleaseGeometry(g)
+        return gid, keep
 
     def add_quad_mesh(self, device, scene, vertices, indices, mask=None, geom_id=None):
         """RTC_GEOMETRY_TYPE_QUAD with shared FLOAT3 vertex / UINT4 index buffers (quad (v0,v1,v2,v3); a triangle is a

@@ -117,6 +117,39 @@ def hair_ball(strands, segments, seed=3, radius=1.0, length=0.35, width=0.004):
     return verts, idx, None
 
 
+def cubic_hair(strands, basis="bezier", knots=10, seed=7, radius=1.0, step=0.08, width=0.02):
+    """Strands of connected cubic curves growing out of a sphere (tutorials/hair_geometry with --convert-...-to-curves, curve_geometry):
+    `knots` float4 control points per strand from a random walk, tapering.  Index buffer = first control vertex of every
+    curve: Bezier curves share their end points (0, 3, 6, ...), B-spline / Catmull-Rom curves slide by one, Hermite curves
+    join consecutive vertices and come with a random tangent (xyz, d radius) per vertex.
+    Returns (vertices[nv,4], indices[nc] u32, tangents[nv,4] or None)."""
+    rng = np.random.RandomState(seed)
+    n = rng.normal(size=(strands, 3))
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    pts = np.zeros((strands, knots, 4), np.float32)
+    p, d = n * radius, n.copy()
+    for k in range(knots):
+        pts[:, k, :3] = p
+        pts[:, k, 3] = width * (1.0 - 0.7 * k / knots)
+        d = d + rng.normal(scale=0.5, size=d.shape)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        p = p + d * step
+    verts = pts.reshape(-1, 4)
+    if basis == "bezier":
+        starts = np.arange(0, knots - 3, 3)
+    elif basis == "hermite":
+        starts = np.arange(0, knots - 1)
+    else:
+        starts = np.arange(0, knots - 3)
+    idx = (np.arange(strands)[:, None] * knots + starts[None, :]).reshape(-1).astype(np.uint32)
+    tang = None
+    if basis == "hermite":
+        tang = np.zeros_like(verts)
+        tang[:, :3] = rng.normal(scale=1.2 * step, size=(len(verts), 3))
+        tang[:, 3] = rng.normal(scale=0.1 * width, size=len(verts))
+    return verts, idx, tang
+
+
 def cube_and_ground():
     """The triangle_geometry tutorial scene (triangle_geometry_device.cpp:31-97): unit cube (12 tris, geomID 0)
     and a ground plane (2 tris, geomID 1)."""

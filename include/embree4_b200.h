@@ -85,6 +85,8 @@ enum RTCFeatureFlags {
   RTC_FEATURE_FLAG_QUAD = 1 << 2,
   RTC_FEATURE_FLAG_ROUND_LINEAR_CURVE = 1 << 6,
   RTC_FEATURE_FLAG_FLAT_LINEAR_CURVE = 1 << 7,
+  RTC_FEATURE_FLAG_FLAT_BEZIER_CURVE = 1 << 9, RTC_FEATURE_FLAG_FLAT_BSPLINE_CURVE = 1 << 12,
+  RTC_FEATURE_FLAG_FLAT_HERMITE_CURVE = 1 << 15, RTC_FEATURE_FLAG_FLAT_CATMULL_ROM_CURVE = 1 << 18,
   RTC_FEATURE_FLAG_INSTANCE = 1 << 23,
   RTC_FEATURE_FLAG_ALL = 0xffffffff
 };
@@ -94,9 +96,17 @@ enum RTCGeometryType {
   RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE = 16, /* vertex buffer RTC_FORMAT_FLOAT4 (xyz, radius), index buffer RTC_FORMAT_UINT = first vertex
                                                 of a segment, optional RTC_BUFFER_TYPE_FLAGS (rtcore_geometry.h:27; roundline_intersector.h) */
   RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE = 17,  /* same buffers, ray-facing ribbons (line_intersector.h) */
+  /* flat cubic curves (rtcore_geometry.h:31,35,39,47; curve_intersector_ribbon.h): vertex buffer RTC_FORMAT_FLOAT4 (xyz, radius),
+   * index buffer RTC_FORMAT_UINT = first of the curve's four control vertices (Hermite: of its two vertex / tangent pairs,
+   * tangents in RTC_BUFFER_TYPE_TANGENT, RTC_FORMAT_FLOAT4); ray-facing ribbons of rtcSetGeometryTessellationRate (default 4,
+   * 1..16) segments; hits report u along the curve, v in [-1, 1] across the ribbon and Ng = dP/du */
+  RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE = 25,
+  RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE = 33,
+  RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE = 41,
+  RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE = 59,
   RTC_GEOMETRY_TYPE_INSTANCE = 121 /* single-level instances of triangle scenes (rtcore_geometry.h:51) */
 };
-enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2, RTC_BUFFER_TYPE_FLAGS = 32 };
+enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2, RTC_BUFFER_TYPE_TANGENT = 4, RTC_BUFFER_TYPE_FLAGS = 32 };
 enum RTCCurveFlags { RTC_CURVE_FLAG_NEIGHBOR_LEFT = 1 << 0, RTC_CURVE_FLAG_NEIGHBOR_RIGHT = 1 << 1 };   /* rtcore_geometry.h:66-70 */
 enum RTCError {
   RTC_ERROR_NONE = 0, RTC_ERROR_UNKNOWN = 1, RTC_ERROR_INVALID_ARGUMENT = 2, RTC_ERROR_INVALID_OPERATION = 3,
@@ -236,6 +246,7 @@ RTCB200_API void rtcCommitGeometry(RTCGeometry geometry);
 RTCB200_API void rtcEnableGeometry(RTCGeometry geometry);
 RTCB200_API void rtcDisableGeometry(RTCGeometry geometry);
 RTCB200_API void rtcSetGeometryTimeStepCount(RTCGeometry geometry, unsigned int timeStepCount); /* only 1 */
+RTCB200_API void rtcSetGeometryTessellationRate(RTCGeometry geometry, float tessellationRate); /* flat cubic curves: segments per curve, clamped to 1..16 (scene_curves.cpp:247) */
 RTCB200_API void rtcSetGeometryVertexAttributeCount(RTCGeometry geometry, unsigned int n);
 RTCB200_API void rtcSetGeometryMask(RTCGeometry geometry, unsigned int mask);
 RTCB200_API void rtcSetGeometryBuildQuality(RTCGeometry geometry, enum RTCBuildQuality quality);
@@ -424,7 +435,6 @@ RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryIntersectFunction)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryOccludedFunction)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryPointQueryFunction)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometrySubdivisionMode)
-RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTessellationRate)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTopologyCount)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryTransformQuaternion)
 RTCB200_DECLARE_UNSUPPORTED(rtcSetGeometryUserPrimitiveCount)

@@ -65,6 +65,28 @@ def load_golden_curves(name="curves"):
                 occluded_out=rec(z["occluded_out"], RAY_DTYPE), bounds=z["bounds"])
 
 
+def load_golden_cubic(name="curves_cubic"):
+    """tests/golden/curves_cubic.npz -> dict(meshes, cubics=[(verts4, idx, geomID, mask, basis, tess or None, tangents or None)],
+    rays_in, intersect_out, occluded_out, bounds): flat Bezier / B-spline / Catmull-Rom / Hermite curve sets around a triangle
+    sphere and the reference's outputs (make_golden.main_cubic_curves)."""
+    from embree_b200.rtc import RAYHIT_DTYPE, RAY_DTYPE, aligned_empty
+    from tests.golden.make_golden_sets import CUBIC_SETS
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+    def rec(a, dt):
+        out = aligned_empty(a.shape[0], dt)
+        out.view(np.uint8).reshape(a.shape)[:] = a
+        return out
+    cubics = []
+    for i in range(int(z["n_sets"])):
+        tess = int(z[f"ctess{i}"])
+        tg = z[f"ctang{i}"]
+        cubics.append((z[f"cv{i}"], z[f"ci{i}"], int(z[f"cgid{i}"]), int(z[f"cmask{i}"]), CUBIC_SETS[i][0], tess if tess else None,
+                       tg if tg.size else None))
+    return dict(meshes=[(z["v0"], z["t0"], 0, 0xFFFFFFFF)], cubics=cubics, rays_in=rec(z["rays_in"], RAYHIT_DTYPE),
+                intersect_out=rec(z["intersect_out"], RAYHIT_DTYPE), occluded_out=rec(z["occluded_out"], RAY_DTYPE), bounds=z["bounds"])
+
+
 GOLDEN = ["cube_ground", "sphere21", "terrain_masks"]
 GOLDEN_QUADS = ["quads"]   # meshes with [n,4] indices are RTC_GEOMETRY_TYPE_QUAD
 

@@ -358,3 +358,22 @@ extern "C" int emu_flat_curve_test(const float* ray8, const float* v0, const flo
   out5[0] = h.t; out5[1] = h.u; out5[2] = h.ngx; out5[3] = h.ngy; out5[4] = h.ngz;
   return 1;
 }
+
+// ---- flat cubic curves (rt_core.cuh flat_cubic_test + curve_basis_table), host instantiation.  cps = n curves x 4 control points
+// x float4 (Hermite input already converted); every curve is tested in order against the ray as shortened by the hits so far
+// (the sequential leaf loop); returns the winning curve or -1.  out6 = t, u, v, Ng.xyz.
+extern "C" int emu_flat_cubic_closest(const float* ray8, const float* cps, int n, unsigned basis, int N, float* out6) {
+  float tab[8 * (kMaxTess + 1)];
+  curve_basis_table(basis, N, tab);
+  float tfar = ray8[7];
+  int win = -1;
+  for (int i = 0; i < n; ++i) {
+    CurveVtx cp[4];
+    for (int k = 0; k < 4; ++k) cp[k] = CurveVtx{cps[i * 16 + k * 4], cps[i * 16 + k * 4 + 1], cps[i * 16 + k * 4 + 2], cps[i * 16 + k * 4 + 3]};
+    CurveHit h;
+    if (!flat_cubic_test(ray8[0], ray8[1], ray8[2], ray8[4], ray8[5], ray8[6], ray8[3], tfar, cp, basis, N, tab, h)) continue;
+    tfar = h.t; win = i;
+    out6[0] = h.t; out6[1] = h.u; out6[2] = h.v; out6[3] = h.ngx; out6[4] = h.ngy; out6[5] = h.ngz;
+  }
+  return win;
+}

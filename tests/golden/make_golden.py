@@ -185,6 +185,56 @@ def main_curves():
     run_curves("curves_flat", [(v, t, 0, 0xFFFFFFFF)], [(cv3, ci3, None, 1, 0x3, True), (cv2, ci2, None, 2, 0xFFFFFFFD, True)], rays2)
 
 
+from tests.golden.make_golden_sets import CUBIC_SETS  # noqa: E402
+
+
+def main_cubic_curves():
+    """Flat cubic curves (curve_intersector_ribbon.h): one curve set per basis, each with its own tessellation rate and
+    geometry mask, around a triangle sphere; rays from outside towards the ball, some with masks and tnear / tfar windows."""
+    R = load_reference()
+    v, t = scenes.triangle_sphere(12)
+    v = (v * np.float32(0.9)).astype(np.float32)
+    sets = []
+    for k, (basis, tess) in enumerate(CUBIC_SETS):
+        cv, ci, tg = scenes.cubic_hair(60, basis, seed=20 + k, radius=0.9, width=0.03)
+        sets.append((cv, ci, 1 + k, 0xFFFFFFFF if k != 2 else 0x6, basis, tess, tg))
+    rng = np.random.RandomState(31)
+    org = rng.normal(size=(6144, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * rng.uniform(1.5, 2.5, (6144, 1)).astype(np.float32)
+    d = (-org + rng.normal(scale=0.45, size=org.shape)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    rays["mask"][0::7] = 0x2
+    rays["mask"][1::7] = 0x1
+    rays["tnear"][2::9] = 1.2
+    rays["tfar"][3::11] = 1.6
+    rays["id"] = np.arange(len(rays))
+    dev = R.new_device(None)
+    sc = R.rtcNewScene(dev)
+    keep = [R.add_triangle_mesh(dev, sc, v, t, mask=0xFFFFFFFF, geom_id=0)[1]]
+    for (cv, ci, gid, mask, basis, tess, tg) in sets:
+        keep.append(R.add_flat_cubic_curves(dev, sc, cv, ci, basis, tess, tg, mask=mask, geom_id=gid)[1])
+    R.rtcCommitScene(sc)
+    R.check(dev)
+    b = RTCBounds()
+    R.rtcGetSceneBounds(sc, C.byref(b))
+    out_i = R.intersect(sc, rays.copy(), "1")
+    out_o = R.occluded(sc, rays_of(rays), "1")
+    R.check(dev)
+    dd = dict(rays_in=rays.view(np.uint8).reshape(-1, 96), intersect_out=out_i.view(np.uint8).reshape(-1, 96),
+              occluded_out=out_o.view(np.uint8).reshape(-1, 48),
+              bounds=np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32),
+              v0=v, t0=t, n_sets=np.array(len(sets)))
+    for i, (cv, ci, gid, mask, basis, tess, tg) in enumerate(sets):
+        dd[f"cv{i}"], dd[f"ci{i}"], dd[f"cgid{i}"], dd[f"cmask{i}"] = cv, ci, np.array(gid, np.uint32), np.array(mask, np.uint32)
+        dd[f"ctess{i}"] = np.array(0 if tess is None else tess)
+        dd[f"ctang{i}"] = tg if tg is not None else np.zeros((0, 4), np.float32)
+    np.savez_compressed(os.path.join(HERE, "curves_cubic.npz"), **dd)
+    per = {basis: int((out_i["geomID"] == 1 + k).sum()) for k, (basis, _t) in enumerate(CUBIC_SETS)}
+    print(f"curves_cubic: {len(rays)} rays, hits per basis {per}, triangles {(out_i['geomID'] == 0).sum()}, occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
+    R.rtcReleaseScene(sc)
+    R.rtcReleaseDevice(dev)
+
+
 def main_filters():
     """Filter callbacks (tests/filter_cases.py) on the cube_ground scene: the reference's results with a geometry filter,
     the arguments' filter on every geometry, and the arguments' filter enabled on one geometry."""
@@ -274,12 +324,16 @@ def main():
     run_instances("instances", [(sv, st, 0, 0xFFFFFFFF), (sv2, st, 1, 0x3)], [(gv, gt, 0, 0xFFFFFFFF)], xf,
                   [0xFFFFFFFF if i % 3 else 0x5 for i in range(7)], r)
     main_curves()
+    main_cubic_curves()
     main_filters()
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "curves":
         main_curves()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cubic":
+        main_cubic_curves()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "filters":
         main_filters()

@@ -13,6 +13,9 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libembree4.so.4")
 
 
+CUBIC_BASES = ["bezier", "bspline", "catmull_rom", "hermite"]
+
+
 class Oracle:
     def __init__(self, path=ORACLE_SO):
         if not os.path.exists(path):
@@ -25,6 +28,8 @@ class Oracle:
         d.orc_add_quad_mesh.argtypes = d.orc_add_mesh.argtypes
         d.orc_add_curves.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_uint, C.c_uint]
         d.orc_add_curves_typed.argtypes = d.orc_add_curves.argtypes + [C.c_int]
+        d.orc_add_cubic_curves.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint,
+                                           C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         d.orc_add_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
         d.orc_set_robust.argtypes = [C.c_void_p, C.c_int]
         d.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
@@ -34,11 +39,11 @@ class Oracle:
         d.orc_api_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_uint, C.c_int]
         self.d = d
 
-    def scene(self, meshes, robust=False, instances=(), curves=()):
+    def scene(self, meshes, robust=False, instances=(), curves=(), cubics=()):
         """meshes: list of (vertices[nv,3] f32, indices[nt,3] u32 (or [nq,4] for a quad mesh), geomID, mask); instances:
         list of (child OracleScene, xfm[12] column-major 3x4, geomID, mask); curves: list of (vertices[nv,4] f32 (xyz,
         radius), first-vertex indices[ns] u32, flags[ns] u8 or None, geomID, mask) round linear curve sets."""
-        return OracleScene(self, meshes, robust, instances, curves)
+        return OracleScene(self, meshes, robust, instances, curves, cubics)
 
     def trace(self, v, t, rayhits, occluded=False, mask=0xFFFFFFFF, nthreads=1):
         sc = self.scene([(v, t, 0, mask)])
@@ -48,7 +53,7 @@ class Oracle:
 
 
 class OracleScene:
-    def __init__(self, o, meshes, robust=False, instances=(), curves=()):
+    def __init__(self, o, meshes, robust=False, instances=(), curves=(), cubics=()):
         self.o = o
         self.h = o.d.orc_new()
         o.d.orc_set_robust(self.h, 1 if robust else 0)
@@ -70,6 +75,13 @@ class OracleScene:
             self.keep += [cv, ci, cf]
             o.d.orc_add_curves_typed(self.h, cv.ctypes.data, 16, cv.shape[0], ci.ctypes.data, 4, ci.shape[0],
                                      None if cf is None else cf.ctypes.data, gid, mask, 1 if flat else 0)
+        for (cv, ci, gid, mask, basis, tess, tang) in cubics:   # flat cubic curves: basis 'bezier' | 'bspline' | 'catmull_rom' | 'hermite'
+            cv = np.ascontiguousarray(cv, np.float32).reshape(-1, 4)
+            ci = np.ascontiguousarray(ci, np.uint32).reshape(-1)
+            tg = None if tang is None else np.ascontiguousarray(tang, np.float32).reshape(-1, 4)
+            self.keep += [cv, ci, tg]
+            o.d.orc_add_cubic_curves(self.h, cv.ctypes.data, 16, cv.shape[0], ci.ctypes.data, 4, ci.shape[0], gid, mask,
+                                     CUBIC_BASES.index(basis), int(tess), None if tg is None else tg.ctypes.data, 16)
         for (child, xfm, gid, mask) in instances:
             m = np.ascontiguousarray(xfm, np.float32).reshape(12)
             self.keep += [child, m]

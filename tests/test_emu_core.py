@@ -211,3 +211,47 @@ def test_flat_curve_segment_test_equals_oracle(emu, oracle):
             assert best[1] in (0.0, 1.0) and w["u"] in (0.0, 1.0), (k, best, w)
     assert hits > 100
     sc.free()
+
+
+@pytest.mark.parametrize("which", [0, 1, 2, 3])
+def test_flat_cubic_curve_test_equals_oracle(emu, oracle, which):
+    """rt_core.cuh flat_cubic_test + curve_basis_table (flat Bezier / B-spline / Catmull-Rom / Hermite curves), host instantiation,
+    brute force over all curves of one golden curve set: the same winner and bit-identical t / u / v / Ng as the C oracle's
+    BVH traversal (an exact tie between two curves may name either)."""
+    import ctypes as C
+    from tests.conftest import load_golden_cubic
+    from tests.parity import CUBIC_BASES
+    g = load_golden_cubic()
+    cv, ci, gid, mask, basis, tess, tang = g["cubics"][which]
+    tess = 4 if tess is None else tess
+    sc = oracle.scene([], cubics=[(cv, ci, gid, 0xFFFFFFFF, basis, tess, tang)])
+    rays = g["rays_in"][::2].copy()
+    rays["mask"] = 0xFFFFFFFF
+    want = sc.trace(rays.copy())
+    if basis == "hermite":    # the conversion HermiteCurveT does (hermite_curve.h:19-20), with the same fused operations
+        k = np.float32(1.0 / 3.0)
+        fma = lambda a, b, c: (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)   # noqa: E731
+        p0, p1, t0, t1 = cv[ci], cv[ci + 1], tang[ci], tang[ci + 1]
+        cps = np.stack([p0, fma(np.full_like(t0, k), t0, p0), fma(np.full_like(t1, -k), t1, p1), p1], 1)
+    else:
+        cps = np.stack([cv[ci + j] for j in range(4)], 1)
+    cps = np.ascontiguousarray(cps, np.float32)
+    emu.emu_flat_cubic_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p]
+    out = (C.c_float * 6)()
+    hits = 0
+    for k in range(len(rays)):
+        r = rays[k]
+        ray = np.array([r["org_x"], r["org_y"], r["org_z"], r["tnear"], r["dir_x"], r["dir_y"], r["dir_z"], r["tfar"]], np.float32)
+        win = emu.emu_flat_cubic_closest(ray.ctypes.data, cps.ctypes.data, len(ci), 0 if basis == "hermite" else CUBIC_BASES.index(basis), tess, out)
+        w = want[k]
+        if win < 0:
+            assert w["geomID"] == 0xFFFFFFFF, k
+            continue
+        hits += 1
+        got = np.array(list(out), np.float32).view(np.uint32)
+        exp = np.array([w["tfar"], w["u"], w["v"], w["Ng_x"], w["Ng_y"], w["Ng_z"]], np.float32).view(np.uint32)
+        assert got[0] == exp[0], (k, list(out), w)
+        if win == w["primID"]:
+            assert (got == exp).all(), (k, list(out), w)
+    assert hits > 50
+    sc.free()

@@ -604,6 +604,112 @@ def test_curves_large_vs_oracle_and_errors(b200, oracle):
     lib.rtcReleaseScene(sc)
 
 
+def build_cubic_scene(lib, dev, meshes, cubics, quality=RTC_BUILD_QUALITY_MEDIUM):
+    sc = lib.rtcNewScene(dev)
+    lib.rtcSetSceneBuildQuality(sc, quality)
+    keep = [lib.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in meshes]
+    keep += [lib.add_flat_cubic_curves(dev, sc, cv, ci, basis, tess, tg, mask=mask, geom_id=gid)[1] for (cv, ci, gid, mask, basis, tess, tg) in cubics]
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    return sc, keep
+
+
+@pytest.mark.parametrize("quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
+def test_cubic_curves_golden_all_entry_points(b200, quality):
+    """RTC_GEOMETRY_TYPE_FLAT_BEZIER / _BSPLINE / _CATMULL_ROM / _HERMITE_CURVE (curve_intersector_ribbon.h:73-190; tessellation
+    rates default / 7 / 4 / 12, one geometry mask) against the reference's own outputs through every entry point: ids exact,
+    t / u / v within tolerance, Ng = the curve tangent, any-hit equal, scene bounds as the reference reports them."""
+    from tests.conftest import load_golden_cubic
+    lib, dev = b200
+    g = load_golden_cubic()
+    sc, keep = build_cubic_scene(lib, dev, g["meshes"], g["cubics"], quality)
+    b = RTCBounds()
+    lib.rtcGetSceneBounds(sc, C.byref(b))
+    got_b = np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32)
+    assert np.allclose(got_b, g["bounds"], rtol=1e-6, atol=1e-6) and (got_b[:3] <= g["bounds"][:3]).all() and (got_b[3:] >= g["bounds"][3:]).all()
+    want = g["intersect_out"]
+    for mode in MODES:
+        got = lib.intersect(sc, g["rays_in"].copy(), mode)
+        rep = compare_hits(want, got, TOL)
+        assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 4, (mode, rep)
+        assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= 2e-4 and rep["miss_untouched"], (mode, rep)
+        ok = (got["geomID"] == want["geomID"]) & (got["primID"] == want["primID"]) & (got["geomID"] != 0xFFFFFFFF)
+        for f in ("Ng_x", "Ng_y", "Ng_z"):
+            assert np.allclose(got[f][ok], want[f][ok], rtol=1e-3, atol=1e-5), (mode, f)
+        occ = lib.occluded(sc, rays_of(g["rays_in"]), mode)
+        assert ((occ["tfar"] == -np.inf) == (g["occluded_out"]["tfar"] == -np.inf)).all(), mode
+    lib.rtcReleaseScene(sc)
+
+
+@pytest.mark.parametrize("basis,tess", [("bezier", None), ("bspline", 9), ("catmull_rom", 16), ("hermite", 1)])
+def test_cubic_curves_large_vs_oracle(b200, oracle, basis, tess):
+    """30 000 strands of cubic curves + a triangle mesh against the C oracle.  The device runs the oracle's arithmetic operation
+    for operation (tests/test_emu_core.py), so the hits must be bit-identical wherever the two name the same curve, the GPU
+    may lose no hit (conservative curve bounds in the BVH), and a different curve is only admissible at the same distance."""
+    lib, dev = b200
+    cv, ci, tg = scenes.cubic_hair(30000, basis, seed=11, width=0.004)
+    cv = cv.copy()
+    cv[25, 1] = np.inf                          # an invalid control point drops the curves that use it (scene_curves.h:498-533)
+    v, t = scenes.triangle_sphere(60)
+    sc, keep = build_cubic_scene(lib, dev, [(v, t, 0, 0xFFFFFFFF)], [(cv, ci, 1, 0xFFFFFFFF, basis, tess, tg)])
+    rng = np.random.RandomState(6)
+    org = rng.normal(size=(300000, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * rng.uniform(1.02, 2.0, (300000, 1)).astype(np.float32)
+    d = (-org + rng.normal(scale=0.7, size=org.shape)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    got = lib.intersect(sc, rays.copy(), "1M")
+    osc = oracle.scene([(v, t, 0, 0xFFFFFFFF)], cubics=[(cv, ci, 1, 0xFFFFFFFF, basis, 4 if tess is None else tess, tg)])
+    want = osc.trace(rays.copy(), nthreads=16)
+    rep = compare_hits(want, got, TOL)
+    assert (want["geomID"] == 1).sum() > 20000, rep
+    assert rep["hit_miss_disagree"] == 0 and rep["id_mismatch"] == 0 and rep["tie"] <= 20, rep
+    same = (got["geomID"] == want["geomID"]) & (got["primID"] == want["primID"]) & (want["geomID"] == 1)
+    for f in ("tfar", "u", "v", "Ng_x", "Ng_y", "Ng_z"):
+        assert (got[f][same].view(np.uint32) == want[f][same].view(np.uint32)).all(), f
+    occ = lib.occluded(sc, rays_of(rays), "1M")
+    wocc = osc.trace(rays_of(rays), occluded=True, nthreads=16)
+    assert ((occ["tfar"] == -np.inf) == (wocc["tfar"] == -np.inf)).all()
+    osc.free()
+    lib.rtcReleaseScene(sc)
+
+
+def test_cubic_curve_api_errors(b200):
+    """Curve-specific API behaviour: the tessellation rate exists for cubic curves only and is clamped to 1..16
+    (scene_curves.cpp:244-249), a Hermite geometry needs its tangent buffer, formats are FLOAT4 / UINT."""
+    lib, dev = b200
+    cv, ci, tg = scenes.cubic_hair(300, "hermite", seed=3, width=0.05)
+    g = lib.rtcNewGeometry(dev, 0)
+    lib.rtcSetGeometryTessellationRate(g, 8.0)
+    assert lib.rtcGetDeviceError(dev) == 3                      # triangle mesh: operation not supported
+    lib.rtcReleaseGeometry(g)
+    g = lib.rtcNewGeometry(dev, 25)                             # flat Bezier: no tangent buffer
+    lib.rtcSetSharedGeometryBuffer(g, 4, 0, 0x9004, _ptr(tg), 0, 16, len(tg))
+    assert lib.rtcGetDeviceError(dev) == 2
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(cv), 0, 16, len(cv))
+    assert lib.rtcGetDeviceError(dev) == 3
+    lib.rtcReleaseGeometry(g)
+    sc = lib.rtcNewScene(dev)
+    g = lib.rtcNewGeometry(dev, 41)                             # flat Hermite without tangents: the commit fails
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, 0x9004, _ptr(cv), 0, 16, len(cv))
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, 0x5001, _ptr(ci), 0, 4, len(ci))
+    lib.rtcSetGeometryTessellationRate(g, 100.0)                # clamped to 16
+    lib.rtcCommitGeometry(g)
+    lib.rtcAttachGeometry(sc, g)
+    lib.rtcCommitScene(sc)
+    assert lib.rtcGetDeviceError(dev) == 3
+    lib.rtcSetSharedGeometryBuffer(g, 4, 0, 0x9004, _ptr(tg), 0, 16, len(tg))
+    lib.rtcCommitGeometry(g)
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    rays = make_rayhits(np.array([[0, 0, 3]], np.float32).repeat(64, 0) + np.random.RandomState(1).normal(scale=0.2, size=(64, 3)).astype(np.float32),
+                        np.tile([[0, 0, -1]], (64, 1)))
+    out = lib.intersect(sc, rays.copy(), "1M")
+    hit = out["geomID"] != 0xFFFFFFFF
+    assert hit.any() and (np.abs(out["v"][hit]) <= 1.0 + 1e-5).all() and ((out["u"][hit] >= 0) & (out["u"][hit] <= 1)).all()
+    lib.rtcReleaseGeometry(g)
+    lib.rtcReleaseScene(sc)
+
+
 def test_update_and_recommit(b200):
     """UpdateTest (verify.cpp:1835) / dynamic_scene: move the vertices, rtcUpdateGeometryBuffer, re-commit."""
     lib, dev = b200
