@@ -294,6 +294,91 @@ def dynamic_leg(lib, dev, args):
     return out
 
 
+def hair_leg(lib, dev, devt, stream, args):
+    """configs[3]a: tutorials/hair_geometry with Bezier curves -- a fur ball of flat cubic Bezier curves
+    (RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE, what the tutorials' hair generators and loaders create, geometry_creation.cpp:340,
+    obj_loader.cpp:641) around a triangle sphere.  Two ray sets: 1920x1080 camera rays and as many incoherent rays aimed at
+    the ball; closest hit and any hit, device-resident, CUDA events; next to the unmodified reference's rtcIntersect1 on the
+    usable host threads, with parity of every ray."""
+    from tests.parity import api_trace_mt, compare_hits, load_reference
+    strands = 120000
+    cv, ci, _tg = scenes.cubic_hair(strands, "bezier", knots=10, seed=5, radius=1.0, step=0.05, width=0.0025)
+    v, t = scenes.triangle_sphere(201)
+
+    def build(L, d):
+        sc = L.rtcNewScene(d)
+        keep = [L.add_triangle_mesh(d, sc, v, t, mask=0xFFFFFFFF, geom_id=0)[1], L.add_flat_cubic_curves(d, sc, cv, ci, "bezier", None, None, mask=0xFFFFFFFF, geom_id=1)[1]]
+        t0 = time.perf_counter()
+        L.rtcCommitScene(sc)
+        dt = time.perf_counter() - t0
+        L.check(d)
+        return sc, keep, dt
+    sc, keep, commit_s = build(lib, dev)
+    st = lib.scene_stats(sc)
+    cam = scenes.primary_rays(PRIMARY_W, PRIMARY_H, eye=(0.0, 0.4, -2.6), look=(0.0, -0.15, 1.0), fov=60.0, device=devt)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    n = cam.shape[0]
+    o = torch.randn((n, 3), generator=g)
+    o = o / o.norm(dim=1, keepdim=True) * (1.3 + 1.2 * torch.rand((n, 1), generator=g))
+    d = -o + 0.45 * torch.randn((n, 3), generator=g)
+    inc = scenes.pack_rayhits(o.to(devt), d.to(devt), 0.0, float("inf"))
+    a = lib.args()
+    out = {"workload": f"fur ball: {strands} strands x 3 flat cubic Bezier curves = {len(ci)} curves (tessellation rate 4) + createTriangleSphere(numPhi=201) = {len(t)} triangles",
+           "curves": int(len(ci)), "triangles": int(len(t)), "commit_ms": commit_s * 1e3, "build_device_ms": st.build_ms, "nodes": int(st.num_nodes)}
+    cores, _detail = usable_cores()
+    R = load_reference() if not args.no_cpu else None
+    if R is not None:
+        rdev = R.new_device(None)
+        rsc, rkeep, rcommit = build(R, rdev)
+        out["reference_commit_ms"] = rcommit * 1e3
+    for name, rays in (("camera_1080p", cam), ("incoherent", inc)):
+        work = rays.clone()
+        best = 1e9
+        for it in range(4):
+            work.copy_(rays)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            lib.rtcb200Intersect1MDevice(sc, C.c_void_p(work.data_ptr()), n, C.byref(a), C.c_void_p(stream))
+            c1.record()
+            torch.cuda.synchronize()
+            if it:
+                best = min(best, c0.elapsed_time(c1))
+        occ = rays[:, :12].contiguous()
+        ow = occ.clone()
+        obest = 1e9
+        for it in range(3):
+            ow.copy_(occ)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            lib.rtcb200Occluded1MDevice(sc, C.c_void_p(ow.data_ptr()), n, C.byref(a), C.c_void_p(stream))
+            c1.record()
+            torch.cuda.synchronize()
+            if it:
+                obest = min(obest, c0.elapsed_time(c1))
+        gi = work.view(torch.int32)[:, 18]
+        row = {"rays": int(n), "Mrays_per_s": n / best * 1e-3, "ms": best, "occluded_Mrays_per_s": n / obest * 1e-3,
+               "curve_hit_fraction": float((gi == 1).float().mean().item()), "triangle_hit_fraction": float((gi == 0).float().mean().item())}
+        if R is not None:
+            got = scenes.as_numpy_rayhits(work.cpu())
+            rin = scenes.as_numpy_rayhits(rays.cpu())
+            rbest = 1e30
+            for _ in range(2):
+                w = rin.copy()
+                t0 = time.perf_counter()
+                api_trace_mt(R, rsc, w, cores)
+                rbest = min(rbest, time.perf_counter() - t0)
+            row["reference"] = {"Mrays_per_s": n / rbest * 1e-6, "cores": cores, "api": "rtcIntersect1 loop (FTZ|DAZ), best of 2"}
+            rep = compare_hits(w, got)
+            row["parity"] = {k: rep[k] for k in ("n", "hits", "id_mismatch", "tie", "hit_miss_disagree", "max_rel_t", "max_abs_uv")}
+        out[name] = row
+        del work, occ, ow
+    if R is not None:
+        R.rtcReleaseScene(rsc)
+        R.rtcReleaseDevice(rdev)
+    lib.rtcReleaseScene(sc)
+    return out
+
+
 def coherent_leg(lib, dev, devt, stream, workload, phi, rays, args):
     """One coherent configuration, measured like the headline: device-resident value (CUDA events, 3 warm-up + 5 timed
     passes over a packet stream larger than L2), e2e through the host-pointer entry point rtcb200IntersectNM with pinned
@@ -927,6 +1012,7 @@ def main():
         del T, Tw, cam, Rr, work
         lib.check(dev)
         extras["dynamic_scene_recommit"] = dynamic_leg(lib, dev, args)
+        extras["hair_bezier"] = hair_leg(lib, dev, devt, stream, args)
 
     # ---- parity sample + CPU baseline (rank 0, N == 1)
     cpu_baseline, parity, ref_counters = None, None, None
