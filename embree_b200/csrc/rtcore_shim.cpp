@@ -1008,10 +1008,11 @@ void rtcReleaseGeometry(RTCGeometry g) { GEOM_BEGIN(g) G(g)->release(); GEOM_END
 void rtcCommitGeometry(RTCGeometry g) { GEOM_BEGIN(g) ++G(g)->modCounter; G(g)->state = GeomState::COMMITTED; GEOM_END }  // geometry.cpp:103-107
 void rtcEnableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (!G(g)->enabled) { G(g)->enabled = true; ++G(g)->modCounter; } GEOM_END }
 void rtcDisableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (G(g)->enabled) { G(g)->enabled = false; ++G(g)->modCounter; } GEOM_END }
-// scene_curves.cpp:244-249; every other geometry type: "operation not supported for this geometry" (geometry.h)
+// scene_curves.cpp:244-249, scene_line_segments.cpp:182-184 (linear curves store the value and never use it: tutorials/hair_geometry
+// sets it on every hair set); every other geometry type: "operation not supported for this geometry" (geometry.h:382)
 void rtcSetGeometryTessellationRate(RTCGeometry g, float n) {
   GEOM_BEGIN(g)
-  if (!is_cubic_curve(G(g)->type)) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+  if (!is_cubic_curve(G(g)->type) && !is_linear_curve(G(g)->type)) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
   const int r = (int)n;
   G(g)->tessellationRate = r < 1 ? 1 : (r > 16 ? 16 : r);
   G(g)->update();

@@ -377,3 +377,66 @@ extern "C" int emu_flat_cubic_closest(const float* ray8, const float* cps, int n
   }
   return win;
 }
+
+// ---- experiment (test tool): the production traversal order (leaf slots inside the node step, children in octant order)
+// with the entry distance of the pending children remembered.  mode 0: production (every pending child is visited);
+// mode 1: a pending child whose entry distance lies behind the current hit is skipped (per-child culling at pop time, what
+// the reference's stack does with its per-entry distance); mode 2: a pending GROUP is dropped when the smallest entry
+// distance of all children hit in that node lies behind the current hit (16 spare bits of the 8-byte stack entry would do).
+// stats[0] += node visits, stats[1] += triangle tests.
+namespace {
+struct CullCtx { const Node8* nodes; const TriRec* tris; Ray r; float idx, idy, idz, tfar; uint32_t oct; int mode; uint64_t* stats; };
+void cull_visit(CullCtx& c, uint32_t node) {
+  const Node8& nd = c.nodes[node];
+  c.stats[0]++;
+  const uint32_t ex = nd.w[3];
+  const float sx = u2f((ex & 0xFF) << 23) * c.idx, sy = u2f(((ex >> 8) & 0xFF) << 23) * c.idy, sz = u2f(((ex >> 16) & 0xFF) << 23) * c.idz;
+  const float bx = (u2f(nd.w[0]) - c.r.ox) * c.idx, by = (u2f(nd.w[1]) - c.r.oy) * c.idy, bz = (u2f(nd.w[2]) - c.r.oz) * c.idz;
+  const uint8_t* q = reinterpret_cast<const uint8_t*>(&nd.w[kNodePlaneWord]);
+  const uint32_t imask = ex >> 24;
+  float tmin_s[8]; bool hit_s[8]; uint32_t leaf = 0;
+  float gmin = INFINITY;
+  for (int s = 0; s < 8; ++s) {
+    hit_s[s] = false;
+    const uint32_t lm = node_leafmask_raw(nd.w, s) & 0xFFFFFFu;
+    if (lm == 0 && !(imask & (1u << s))) continue;
+    const float lx = q[s], ly = q[8 + s], lz = q[16 + s], hx = q[24 + s], hy = q[32 + s], hz = q[40 + s];
+    const float tnx = (c.idx < 0 ? hx : lx) * sx + bx, tfx = (c.idx < 0 ? lx : hx) * sx + bx;
+    const float tny = (c.idy < 0 ? hy : ly) * sy + by, tfy = (c.idy < 0 ? ly : hy) * sy + by;
+    const float tnz = (c.idz < 0 ? hz : lz) * sz + bz, tfz = (c.idz < 0 ? lz : hz) * sz + bz;
+    const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, fmaxf(c.r.tnear, 0.0f)));
+    const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, fmaxf(c.tfar, 0.0f))) * 1.0000003f;
+    if (!(tmin <= tmax)) continue;
+    if (imask & (1u << s)) { hit_s[s] = true; tmin_s[s] = tmin; gmin = fminf(gmin, tmin); }
+    else leaf |= lm;
+  }
+  for (uint32_t m = leaf; m;) {
+    const int tb = 31 - clz32(m);
+    m &= ~(1u << tb);
+    const TriRec& t = c.tris[nd.w[5] + (uint32_t)tb];
+    c.stats[1]++;
+    TriHit th;
+    if (tri_test(c.r, c.tfar, t.v0x, t.v0y, t.v0z, t.e1x, t.e1y, t.e1z, t.e2x, t.e2y, t.e2z, th) && (t.mask & c.r.mask)) c.tfar = th.T * (1.0f / th.absDen);
+  }
+  for (int b = 7; b >= 0; --b) {
+    const int s = b ^ (int)(7u - c.oct);
+    if (!hit_s[s]) continue;
+    if (c.mode == 1 && tmin_s[s] > c.tfar) continue;
+    if (c.mode == 2 && gmin > c.tfar) break;
+    cull_visit(c, nd.w[4] + (uint32_t)popc32(imask & ((1u << s) - 1u)));
+  }
+}
+}  // namespace
+extern "C" void emu_trace_cull(void* h, void* rays, uint64_t n, int mode, uint64_t* stats) {
+  EmuScene* sc = static_cast<EmuScene*>(h);
+  if (!sc->root_valid) return;
+  for (uint64_t ri = 0; ri < n; ++ri) {
+    CullCtx c;
+    c.nodes = sc->nodes.data(); c.tris = sc->tris.data(); c.mode = mode; c.stats = stats;
+    memcpy(&c.r, static_cast<char*>(rays) + ri * 96, 48);
+    c.idx = rcp_safe(c.r.dx); c.idy = rcp_safe(c.r.dy); c.idz = rcp_safe(c.r.dz);
+    c.oct = (c.idx < 0 ? 1u : 0u) | (c.idy < 0 ? 2u : 0u) | (c.idz < 0 ? 4u : 0u);
+    c.tfar = c.r.tfar;
+    cull_visit(c, 0);
+  }
+}

@@ -90,3 +90,69 @@ def run_config(lib, dev, meshes, rayhits, config, mode="1"):
     lib.rtcReleaseScene(sc)
     assert not ri.errors and not ro.errors, (ri.errors, ro.errors)
     return out_i, out_o, ri, ro
+
+
+# ---- tutorials/hair_geometry: shadow rays through hair with a STATEFUL argument filter -------------------------------------
+import ctypes as C  # noqa: E402
+
+
+class HairShadowContext(C.Structure):
+    """RayQueryContext of tutorials/common/tutorial/tutorial_device.h: the RTCRayQueryContext first, then the tutorial's
+    own fields -- here the transparency the occlusion filter accumulates (hair_geometry_device.cpp:208-238)."""
+    _fields_ = [("context", RayQueryContext), ("T", C.c_float * 3)]
+
+
+HAIR_KT = (0.8 * 0.8, 0.8 * 0.57, 0.8 * 0.32)     # TutorialData: hair_Kt = 0.8 * hair_K
+
+
+def hair_shadow_filter():
+    """occlusionFilter of hair_geometry_device.cpp:208-238: every hair multiplies the ray's transparency by Kt and is rejected
+    (the ray goes on) until the transparency drops below 2 %."""
+    def cb(args):
+        a = args.contents
+        if a.valid[0] == 0:
+            return
+        ctx = C.cast(a.context, C.POINTER(HairShadowContext)).contents
+        for k in range(3):
+            ctx.T[k] = C.c_float(HAIR_KT[k] * ctx.T[k]).value
+        if max(ctx.T[0], ctx.T[1], ctx.T[2]) > 0.02:
+            a.valid[0] = 0
+    return FILTER_FUNCTION(cb)
+
+
+def hair_scene():
+    """A small fur ball of flat Bezier curves around an (unfiltered) triangle sphere + shadow rays from its surroundings."""
+    from embree_b200 import scenes
+    cv, ci, _tg = scenes.cubic_hair(600, "bezier", seed=41, radius=0.8, step=0.06, width=0.012)
+    v, t = scenes.triangle_sphere(12)
+    v = (v * np.float32(0.8)).astype(np.float32)
+    rng = np.random.RandomState(43)
+    org = rng.normal(size=(1536, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * rng.uniform(1.05, 1.6, (1536, 1)).astype(np.float32)
+    d = (-org + rng.normal(scale=0.55, size=org.shape)).astype(np.float32)      # towards the ball, many graze only its fur
+    return (v, t), (cv, ci), rtc.rays_of(rtc.make_rayhits(org, d, tnear=1e-4))
+
+
+def run_hair_shadows(lib, dev, single=True):
+    """occluded() of hair_geometry_device.cpp:240-262 for every ray: returns (transparency[n,3], occluded[n])."""
+    (v, t), (cv, ci), rays = hair_scene()
+    sc = lib.rtcNewScene(dev)
+    keep = [lib.add_triangle_mesh(dev, sc, v, t, geom_id=0)[1], lib.add_flat_cubic_curves(dev, sc, cv, ci, "bezier", geom_id=1)[1]]
+    lib.rtcSetGeometryEnableFilterFunctionFromArguments(lib.rtcGetGeometry(sc, 1), True)   # convertHairSet: hair only
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    fn = hair_shadow_filter()
+    T = np.ones((len(rays), 3), np.float32)
+    occ = np.zeros(len(rays), bool)
+    base, st = rays.ctypes.data, rays.dtype.itemsize
+    for i in range(len(rays)):
+        ctx = HairShadowContext()
+        ctx.context.instID = ctx.context.instPrimID = 0xFFFFFFFF
+        ctx.T[0] = ctx.T[1] = ctx.T[2] = 1.0
+        a = lib.args(filter=fn, context=ctx)
+        lib.rtcOccluded1(sc, C.c_void_p(base + i * st), C.byref(a))
+        occ[i] = rays["tfar"][i] < 0
+        T[i] = (0.0, 0.0, 0.0) if occ[i] else (ctx.T[0], ctx.T[1], ctx.T[2])
+    lib.check(dev)
+    lib.rtcReleaseScene(sc)
+    return T, occ

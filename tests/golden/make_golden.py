@@ -259,6 +259,9 @@ def main_filters():
         rej = sum(1 for c in ri.calls if fc.rejects(c[1], c[2], c[3]))
         print(f"filters/{cfg}: {len(ri.calls)} intersect callbacks ({rej} rejected), {len(ro.calls)} occluded callbacks, "
               f"hit rate {(oi['geomID'] != 0xFFFFFFFF).mean():.3f}, occluded {(oo['tfar'] == -np.inf).mean():.3f}")
+    T, occ = fc.run_hair_shadows(R, dev)
+    d["hair_T"], d["hair_occluded"] = T, occ
+    print(f"filters/hair shadows: {len(occ)} rays, occluded {occ.mean():.3f}, partially transparent {((T < 1).any(1) & ~occ).mean():.3f}")
     R.rtcReleaseDevice(dev)
     np.savez_compressed(os.path.join(HERE, "filters.npz"), **d)
 

@@ -173,3 +173,16 @@ def test_device_entry_points_refuse_filters(b200):
     want = [not fc.rejects(0, int(p)) for p in out["primID"][out["geomID"] != 0xFFFFFFFF]]
     assert all(want)
     lib.rtcReleaseScene(sc)
+
+
+def test_hair_shadow_rays_with_transparency_filter(b200):
+    """The shadow rays of tutorials/hair_geometry (hair_geometry_device.cpp:208-262): a stateful occlusion filter passed in the
+    arguments and enabled on the hair geometry accumulates the transparency of every hair along the ray and lets the ray
+    through until less than 2 % is left.  Transparency and occlusion per ray equal the reference's (golden; the product is
+    taken in a different order, hence the 1e-5)."""
+    lib, dev = b200
+    z = np.load(os.path.join(ROOT, "tests", "golden", "filters.npz"))
+    T, occ = fc.run_hair_shadows(lib, dev)
+    assert (occ == z["hair_occluded"]).all()
+    assert np.allclose(T, z["hair_T"], rtol=1e-5, atol=1e-7)
+    assert occ.mean() > 0.05 and ((T < 1).any(1) & ~occ).mean() > 0.1
