@@ -300,7 +300,7 @@ def hair_leg(lib, dev, devt, stream, args):
     obj_loader.cpp:641) around a triangle sphere.  Two ray sets: 1920x1080 camera rays and as many incoherent rays aimed at
     the ball; closest hit and any hit, device-resident, CUDA events; next to the unmodified reference's rtcIntersect1 on the
     usable host threads, with parity of every ray."""
-    from tests.parity import api_trace_mt, compare_hits, load_reference
+    from tests.parity import api_trace_mt, compare_hits, load_reference, unexplained_ribbon_disagreements
     strands = 120000
     cv, ci, _tg = scenes.cubic_hair(strands, "bezier", knots=10, seed=5, radius=1.0, step=0.05, width=0.0025)
     v, t = scenes.triangle_sphere(201)
@@ -370,6 +370,10 @@ def hair_leg(lib, dev, devt, stream, args):
             row["reference"] = {"Mrays_per_s": n / rbest * 1e-6, "cores": cores, "api": "rtcIntersect1 loop (FTZ|DAZ), best of 2"}
             rep = compare_hits(w, got)
             row["parity"] = {k: rep[k] for k in ("n", "hits", "id_mismatch", "tie", "hit_miss_disagree", "max_rel_t", "max_abs_uv")}
+            nd, bad = unexplained_ribbon_disagreements(w, got, {1})
+            row["parity"]["differing_rays"] = nd
+            row["parity"]["not_on_a_ribbon_edge"] = bad     # every difference must be a ray through the very edge (|v| >= 0.999) of the nearer ribbon
+            row["parity"]["checked_against"] = "reference, every ray"
         out[name] = row
         del work, occ, ow
     if R is not None:

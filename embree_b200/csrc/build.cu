@@ -159,25 +159,33 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
     const int g = find_geom(offs, ngeoms, p);
     float v[9], pad[3] = {0.0f, 0.0f, 0.0f};
     if (geoms[g].is_curve == 3) {
-      // accurateFlatBounds (bezier_curve.h:631-664, bspline_curve.h:244-275) + enlarge_bounds (scene_curves.cpp:433-437): box of
-      // the tessellation points (and the last control point), enlarged by the largest |radius| and by 4 ulp of the largest
-      // magnitude.  The ribbon's quads are p +- r n with |n| = 1 evaluated in ray space, so the union of the spheres
-      // around the tessellation points holds them; directed rounding + 2 ulp cover the world / ray-space difference.
+      // One primitive per tessellation SEGMENT of a flat cubic curve (local index = curve * tess + segment): box of the
+      // segment's two tessellation points (the last segment of a Bezier curve also holds the last control point, as
+      // accurateFlatBounds does, bezier_curve.h:631-664, bspline_curve.h:244-275), enlarged by the largest |radius| of the WHOLE
+      // curve and by 4 ulp of the largest magnitude (enlarge_bounds, scene_curves.cpp:433-437) -- so the union over a curve's
+      // segments is the box the reference reports for the curve.  The ribbon's quads are p +- r n with |n| = 1 evaluated in
+      // ray space, so the spheres around the two points hold the segment's quad; directed rounding + 2 ulp cover the
+      // world / ray-space difference.
       CurveVtx cp[4];
       uint32_t vid;
-      load_cubic(geoms[g], p - offs[g], cp, vid, ok);
+      const int n = (int)geoms[g].tess, st = n + 1;
+      const uint32_t lp = p - offs[g];
+      const int seg = (int)(lp % (uint32_t)n);
+      load_cubic(geoms[g], lp / (uint32_t)n, cp, vid, ok);
       if (ok) {
-        const int n = (int)geoms[g].tess, st = n + 1;
         const float* tab = geoms[g].basis_tab;
-        // the curve's end point: the last control point of a Bezier curve, the table's last column otherwise
         const bool bez = geoms[g].basis == BASIS_BEZIER;
         float rmax = bez ? fabsf(cp[3].r) : 0.0f;
-        float plo[3] = {bez ? cp[3].x : INFINITY, bez ? cp[3].y : INFINITY, bez ? cp[3].z : INFINITY};
-        float phi[3] = {bez ? cp[3].x : -INFINITY, bez ? cp[3].y : -INFINITY, bez ? cp[3].z : -INFINITY};
-        for (int j = 0; j <= n; ++j) {
+        for (int j = 0; j <= n; ++j) rmax = fmaxf(rmax, fabsf(curve_blend(tab + j, st, cp[0].r, cp[1].r, cp[2].r, cp[3].r)));
+        float plo[3] = {INFINITY, INFINITY, INFINITY}, phi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int j = seg; j <= seg + 1; ++j) {
           const float q[3] = {curve_blend(tab + j, st, cp[0].x, cp[1].x, cp[2].x, cp[3].x), curve_blend(tab + j, st, cp[0].y, cp[1].y, cp[2].y, cp[3].y),
                               curve_blend(tab + j, st, cp[0].z, cp[1].z, cp[2].z, cp[3].z)};
-          rmax = fmaxf(rmax, fabsf(curve_blend(tab + j, st, cp[0].r, cp[1].r, cp[2].r, cp[3].r)));
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { plo[a] = fminf(plo[a], q[a]); phi[a] = fmaxf(phi[a], q[a]); }
+        }
+        if (bez && seg == n - 1) {
+          const float q[3] = {cp[3].x, cp[3].y, cp[3].z};
 #pragma unroll
           for (int a = 0; a < 3; ++a) { plo[a] = fminf(plo[a], q[a]); phi[a] = fmaxf(phi[a], q[a]); }
         }
@@ -542,13 +550,13 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
   const GeomDesc gd = geoms[g];
   float v[9];
   bool ok;
-  if (gd.is_curve == 3) {   // flat cubic curve record: a = (-, -, -, primID), b = (-, -, -, descriptor), c = (-, -, first vertex, mask)
-    const uint32_t lp = p - offs[g];
-    const uint32_t vid = *reinterpret_cast<const uint32_t*>(gd.idx + (uint64_t)lp * gd.istride);
+  if (gd.is_curve == 3) {   // record of one SEGMENT of a flat cubic curve: a = (-, -, -, primID), b = (-, -, -, descriptor), c = (segment, -, first vertex, mask)
+    const uint32_t lp = p - offs[g], curve = lp / gd.tess, seg = lp % gd.tess;
+    const uint32_t vid = *reinterpret_cast<const uint32_t*>(gd.idx + (uint64_t)curve * gd.istride);
     float4* dst = reinterpret_cast<float4*>(&out[t]);
-    dst[0] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(lp));
+    dst[0] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(curve));
     dst[1] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float((uint32_t)g));
-    dst[2] = make_float4(0.0f, 0.0f, __uint_as_float(vid), __uint_as_float(gd.mask));
+    dst[2] = make_float4(__uint_as_float(seg), 0.0f, __uint_as_float(vid), __uint_as_float(gd.mask));
     return;
   }
   if (gd.is_curve) {   // curve record: a = (p0.xyz, primID), b = (p1.xyz, descriptor), c = (r0, r1, first vertex | flags << 30, mask)

@@ -503,8 +503,12 @@ RT_HD float curve_blend(const float* w, int stride, float v0, float v1, float v2
   return fma_rn(w[0], v0, fma_rn(w[stride], v1, fma_rn(w[2 * stride], v2, mul_rn(w[3 * stride], v3))));
 }
 
+// `seg` >= 0 restricts the test to that one tessellation segment: the BVH holds every segment of a curve as its own
+// primitive (tight boxes around thin diagonal ribbons instead of one box per curve -- the job the reference gives to its
+// oriented-bounds hair BVH), and the closest hit over the segments is the closest hit of the curve.  seg < 0: all of them
+// (the host instantiation the tests compare with the oracle).
 RT_HD bool flat_cubic_test(float ox, float oy, float oz, float dx_, float dy_, float dz_, float tnear, float tfar, const CurveVtx cp[4],
-                           uint32_t basis, int N, const float* tab, CurveHit& h) {
+                           uint32_t basis, int N, const float* tab, CurveHit& h, int seg = -1) {
   const RaySpace rs = curve_ray_space(dx_, dy_, dz_);
   // control points in ray space (xfm_pr, bezier_curve.h:216-223); w = radius
   float qx[4], qy[4], qz[4], qw[4];
@@ -520,12 +524,12 @@ RT_HD bool flat_cubic_test(float ox, float oy, float oz, float dx_, float dy_, f
   const int st = N + 1;
   bool ishit = false;
   float ray_tfar = tfar;
-  for (int i0 = 0; i0 < N; i0 += 8) {
+  for (int i0 = seg < 0 ? 0 : (seg & ~7); i0 < (seg < 0 ? N : seg + 1); i0 += 8) {
     bool any = false;
     float bt = 0.0f, bu = 0.0f, bv = 0.0f;
     int bj = 0;
-    const int i1 = (i0 + 8 < N) ? i0 + 8 : N;
-    for (int j = i0; j < i1; ++j) {
+    const int i1 = seg >= 0 ? seg + 1 : ((i0 + 8 < N) ? i0 + 8 : N);
+    for (int j = seg >= 0 ? seg : i0; j < i1; ++j) {
       const float* c0 = tab + j;           // weights of the segment's first point, +1: of its second point
       const float p0x = curve_blend(c0, st, qx[0], qx[1], qx[2], qx[3]), p0y = curve_blend(c0, st, qy[0], qy[1], qy[2], qy[3]);
       const float p0z = curve_blend(c0, st, qz[0], qz[1], qz[2], qz[3]), p0w = curve_blend(c0, st, qw[0], qw[1], qw[2], qw[3]);

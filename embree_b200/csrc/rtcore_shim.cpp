@@ -346,7 +346,7 @@ void commit_scene(SceneImpl* s) {
     const bool hermite = g->type == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE;
     if (hermite && !g->tangents.buf) fail(RTC_ERROR_INVALID_OPERATION, "tangent buffer not set");
     if (hermite && g->tangents.count != nverts) fail(RTC_ERROR_INVALID_OPERATION, "number of tangents must match number of vertices");   // scene_curves.cpp commit
-    if (ncurves > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "curve geometry too large");
+    if (ncurves * (size_t)g->tessellationRate > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "curve geometry too large");
     curves = true;
     const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 16 : 16, ibytes = (ncurves - 1) * g->indices.stride + 4;
     void *dv = nullptr, *di = nullptr, *dt = nullptr, *db = nullptr;
@@ -376,7 +376,7 @@ void commit_scene(SceneImpl* s) {
     d.basis_tab = static_cast<const float*>(db);
     d.verts = static_cast<const uint8_t*>(dv); d.idx = static_cast<const uint8_t*>(di);
     d.vstride = g->vertices.stride; d.istride = g->indices.stride;
-    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)ncurves;
+    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)(ncurves * (size_t)g->tessellationRate);   // one BVH primitive per tessellation segment
     d.geomID = geomID; d.mask = g->mask; d.is_curve = 3;
     descs.push_back(d);
   };

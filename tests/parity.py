@@ -263,3 +263,21 @@ def unexplained_curve_disagreements(rays, a, b, curve_sets):
         if not any(curve_grazing(curve_sets[g][0], curve_sets[g][1], p, rays[i]) for (g, p) in involved):
             bad += 1
     return int(differ.sum()), bad
+
+
+def unexplained_ribbon_disagreements(a, b, curve_geoms, vmin=0.999):
+    """Flat cubic curves: rays on which two implementations of the ribbon test disagree (hit vs miss, or different curves
+    at different distances), and how many of them are NOT explained by a graze: the nearer of the two hits must lie on the
+    very edge of its ribbon (|v| >= vmin; v runs from -1 to 1 across the ribbon), where the sign of the quad's edge
+    functions U, V (quad_intersector.h:52-56) is decided by rounding -- the reference evaluates them with approximate
+    reciprocal square roots, this library with exact ones.  Returns (differing rays, unexplained ones)."""
+    ah, bh = a["geomID"] != 0xFFFFFFFF, b["geomID"] != 0xFFFFFFFF
+    ulps = np.abs(a["tfar"].view(np.int32).astype(np.int64) - b["tfar"].view(np.int32).astype(np.int64))
+    differ = (ah != bh) | (ah & bh & ((a["primID"] != b["primID"]) | (a["geomID"] != b["geomID"])) & (ulps > TIE_ULPS))
+    bad = 0
+    for i in np.nonzero(differ)[0]:
+        cands = [x for x, h in ((a, ah[i]), (b, bh[i])) if h]
+        near = min(cands, key=lambda x: float(x["tfar"][i]))
+        if not (int(near["geomID"][i]) in curve_geoms and abs(float(near["v"][i])) >= vmin):
+            bad += 1
+    return int(differ.sum()), bad

@@ -279,8 +279,11 @@ def test_oracle_cubic_curves_vs_reference_live(oracle, basis, tess):
     R.check(dev)
     ref = api_trace_mt(R, rs, rays.copy(), 4)
     rep = compare_hits(ref, want)
-    # a ray through the very edge of a ribbon quad flips with the rounding of U / V: allow a handful, none seen at this seed
-    assert (ref["geomID"] == 1).sum() > 5000 and rep["id_mismatch"] <= 2 and rep["hit_miss_disagree"] <= 2 and rep["tie"] <= 4, rep
+    # a ray through the very edge of a ribbon quad flips with the rounding of U / V (none at this seed; 4e-6 of the rays of
+    # bench.py's fur ball): every difference must be such a graze
+    from tests.parity import unexplained_ribbon_disagreements
+    n_differ, unexplained = unexplained_ribbon_disagreements(ref, want, {1})
+    assert (ref["geomID"] == 1).sum() > 5000 and n_differ <= 2 and unexplained == 0 and rep["tie"] <= 4, (rep, n_differ, unexplained)
     assert rep["max_rel_t"] <= 1e-4 and rep["max_abs_uv"] <= 4e-4, rep
     ro = api_trace_mt(R, rs, rays_of(rays), 4, occluded=True)
     wo = sc.trace(rays_of(rays), occluded=True, nthreads=4)
