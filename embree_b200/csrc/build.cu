@@ -158,7 +158,42 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
   if (p < ntot) {
     const int g = find_geom(offs, ngeoms, p);
     float v[9], pad[3] = {0.0f, 0.0f, 0.0f};
-    if (geoms[g].is_curve == 3) {
+    if (geoms[g].is_curve == 4) {
+      // round cubic curve: accurateRoundBounds (bezier_curve.h:606-628 and twins) -- 8 points at u = i/7, each with p -+ dp/18 (the hull
+      // of the 7 cubic sub-segments), enlarged by the largest |radius| among them and by enlarge_bounds' 4 ulp; + our 2 ulp
+      CurveVtx cp[4];
+      uint32_t vid;
+      load_cubic(geoms[g], p - offs[g], cp, vid, ok);
+      if (ok) {
+        float pl[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, pu[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        const float c4[4][4] = {{cp[0].x, cp[1].x, cp[2].x, cp[3].x}, {cp[0].y, cp[1].y, cp[2].y, cp[3].y}, {cp[0].z, cp[1].z, cp[2].z, cp[3].z}, {cp[0].r, cp[1].r, cp[2].r, cp[3].r}};
+        const float scale = 1.0f / (3.0f * 6.0f);
+        for (int i = 0; i <= 7; ++i) {
+          float cc[4], dd[4];
+          curve_basis_table_entry(geoms[g].basis, (float)i / 7.0f, cc, dd);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float pp = curve_blend(cc, 1, c4[c][0], c4[c][1], c4[c][2], c4[c][3]), dp = curve_blend(dd, 1, c4[c][0], c4[c][1], c4[c][2], c4[c][3]);
+            const float pm = __fsub_rn(pp, __fmul_rn(scale, i != 0 ? dp : 0.0f)), pq = __fadd_rn(pp, __fmul_rn(scale, i != 7 ? dp : 0.0f));
+            pl[c] = fminf(pl[c], fminf(pp, fminf(pm, pq))); pu[c] = fmaxf(pu[c], fmaxf(pp, fmaxf(pm, pq)));
+          }
+        }
+        const float rmax = fmaxf(fabsf(pl[3]), fabsf(pu[3]));
+        float size = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          lo[a] = __fsub_rd(pl[a], rmax); hi[a] = __fadd_ru(pu[a], rmax);
+          size = fmaxf(size, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+        }
+        const float e = 4.0f * 1.1920929e-07f * size;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          lo[a] = __fsub_rd(lo[a], e); hi[a] = __fadd_ru(hi[a], e);
+          lo[a] -= fabsf(lo[a]) * 2.4e-7f; hi[a] += fabsf(hi[a]) * 2.4e-7f;
+        }
+        ok &= (lo[0] > -kFltLarge) & (hi[0] < kFltLarge) & (lo[1] > -kFltLarge) & (hi[1] < kFltLarge) & (lo[2] > -kFltLarge) & (hi[2] < kFltLarge);
+      }
+    } else if (geoms[g].is_curve == 3) {
       // One primitive per tessellation SEGMENT of a flat cubic curve (local index = curve * tess + segment): box of the
       // segment's two tessellation points (the last segment of a Bezier curve also holds the last control point, as
       // accurateFlatBounds does, bezier_curve.h:631-664, bspline_curve.h:244-275), enlarged by the largest |radius| of the WHOLE
@@ -550,8 +585,8 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
   const GeomDesc gd = geoms[g];
   float v[9];
   bool ok;
-  if (gd.is_curve == 3) {   // record of one SEGMENT of a flat cubic curve: a = (-, -, -, primID), b = (-, -, -, descriptor), c = (segment, -, first vertex, mask)
-    const uint32_t lp = p - offs[g], curve = lp / gd.tess, seg = lp % gd.tess;
+  if (gd.is_curve == 3 || gd.is_curve == 4) {   // record of one SEGMENT of a flat cubic curve (round: of the whole curve): a = (-, -, -, primID), b = (-, -, -, descriptor), c = (segment, -, first vertex, mask)
+    const uint32_t lp = p - offs[g], per = gd.is_curve == 4 ? 1u : gd.tess, curve = lp / per, seg = lp % per;
     const uint32_t vid = *reinterpret_cast<const uint32_t*>(gd.idx + (uint64_t)curve * gd.istride);
     float4* dst = reinterpret_cast<float4*>(&out[t]);
     dst[0] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(curve));

@@ -594,6 +594,283 @@ RT_HD bool flat_cubic_test(float ox, float oy, float oz, float dx_, float dy_, f
 }
 
 // ------------------------------------------------------------------------------------------------
+// round cubic curves (RTC_GEOMETRY_TYPE_ROUND_BEZIER_CURVE / _BSPLINE_ / _CATMULL_ROM_ / _HERMITE_): SweepCurve1Intersector1
+// (kernels/geometry/curve_intersector_sweep.h:446-470).  The curve is the sweep of a sphere of radius r(u) along P(u).
+// intersect_bezier_recursive_jacobian (:146-316, the 8-wide form of the AVX paths: 7 sub-segments per level, two levels, a third
+// where the inner cylinder is grazed) bounds every sub-segment by an outer and an inner cylinder (cylinder.h:119-195) cut by the
+// cap half-planes (plane.h:33-55) and starts a Newton iteration on (u, t) from the entry and the exit of the outer cylinder
+// (intersect_bezier_iterative_jacobian, :59-140: at most 5 steps, converged when |f| and |g| fall below their error
+// estimates).  Every accepted hit shortens the ray at once.  Explicitly rounded operations, operation for operation the C
+// oracle's round_cubic_intersect.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSweepW = 8;
+RT_HD float lerp_rn(float a, float b, float t) { return fma_rn(sub_rn(1.0f, t), a, mul_rn(t, b)); }   // math/emath.h lerp
+RT_HD void curve_basis_eval(uint32_t basis, float u, float b[4]) {    // BSplineBasis::eval / CatmullRomBasis::eval (live, not tabulated)
+  const float t = u, s = sub_rn(1.0f, u);
+  if (basis == BASIS_BSPLINE) {
+    const float sss = mul_rn(mul_rn(s, s), s), ttt = mul_rn(mul_rn(t, t), t), k = 1.0f / 6.0f;
+    const float sts = mul_rn(mul_rn(s, t), s), tst = mul_rn(mul_rn(t, s), t);
+    b[0] = mul_rn(k, sss);
+    b[1] = mul_rn(k, add_rn(add_rn(mul_rn(4.0f, sss), ttt), add_rn(mul_rn(12.0f, sts), mul_rn(6.0f, tst))));
+    b[2] = mul_rn(k, add_rn(add_rn(mul_rn(4.0f, ttt), sss), add_rn(mul_rn(12.0f, tst), mul_rn(6.0f, sts))));
+    b[3] = mul_rn(k, ttt);
+  } else {
+    b[0] = mul_rn(0.5f, mul_rn(mul_rn(-t, s), s));
+    b[1] = mul_rn(0.5f, add_rn(2.0f, mul_rn(mul_rn(t, t), sub_rn(mul_rn(3.0f, t), 5.0f))));
+    b[2] = mul_rn(0.5f, add_rn(2.0f, mul_rn(mul_rn(s, s), sub_rn(mul_rn(3.0f, s), 5.0f))));
+    b[3] = mul_rn(0.5f, mul_rn(mul_rn(-s, t), t));
+  }
+}
+RT_HD void curve_basis_derivative2(uint32_t basis, float u, float b[4]) {
+  const float t = u, s = sub_rn(1.0f, u);
+  if (basis == BASIS_BEZIER) { b[0] = mul_rn(6.0f, s); b[1] = mul_rn(6.0f, fma_rn(-2.0f, s, t)); b[2] = mul_rn(6.0f, fma_rn(-2.0f, t, s)); b[3] = mul_rn(6.0f, t); }
+  else if (basis == BASIS_BSPLINE) { b[0] = s; b[1] = sub_rn(t, mul_rn(2.0f, s)); b[2] = sub_rn(s, mul_rn(2.0f, t)); b[3] = t; }
+  else { b[0] = add_rn(mul_rn(-3.0f, t), 2.0f); b[1] = sub_rn(mul_rn(9.0f, t), 5.0f); b[2] = add_rn(mul_rn(-9.0f, t), 4.0f); b[3] = sub_rn(mul_rn(3.0f, t), 1.0f); }
+}
+// curve.eval(u, P, dPdu, ddPdu) on xyz + radius; ddP may be null
+RT_HD void cubic_eval(const float cp[4][4], uint32_t basis, float u, float P[4], float dP[4], float* ddP) {
+  if (basis == BASIS_BEZIER) {   // de Casteljau (bezier_curve.h:424-440)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float p10 = lerp_rn(cp[0][c], cp[1][c], u), p11 = lerp_rn(cp[1][c], cp[2][c], u), p12 = lerp_rn(cp[2][c], cp[3][c], u);
+      const float p20 = lerp_rn(p10, p11, u), p21 = lerp_rn(p11, p12, u);
+      P[c] = lerp_rn(p20, p21, u); dP[c] = mul_rn(3.0f, sub_rn(p21, p20));
+    }
+  } else {
+    float b[4], d[4];
+    curve_basis_eval(basis, u, b); curve_basis_derivative(basis, u, d);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      P[c] = fma_rn(b[0], cp[0][c], fma_rn(b[1], cp[1][c], fma_rn(b[2], cp[2][c], mul_rn(b[3], cp[3][c]))));
+      dP[c] = fma_rn(d[0], cp[0][c], fma_rn(d[1], cp[1][c], fma_rn(d[2], cp[2][c], mul_rn(d[3], cp[3][c]))));
+    }
+  }
+  if (ddP) {
+    float dd[4];
+    curve_basis_derivative2(basis, u, dd);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ddP[c] = fma_rn(dd[0], cp[0][c], fma_rn(dd[1], cp[1][c], fma_rn(dd[2], cp[2][c], mul_rn(dd[3], cp[3][c]))));
+  }
+}
+RT_HD float dot3v(const float* a, const float* b) { return dot3(a[0], a[1], a[2], b[0], b[1], b[2]); }
+RT_HD void cross3v(const float* a, const float* b, float* o) {
+  o[0] = msub(a[1], b[2], mul_rn(a[2], b[1])); o[1] = msub(a[2], b[0], mul_rn(a[0], b[2])); o[2] = msub(a[0], b[1], mul_rn(a[1], b[0]));
+}
+struct SweepState { const float* dir; float tnear, tfar, dt; const float (*cp)[4]; uint32_t basis; float P_err, upper_w; bool found; CurveHit hit; };
+RT_HD bool sweep_jacobian(SweepState& w, float u, float t) {
+  const float* dir = w.dir;
+  const float length_ray_dir = sqrtf(dot3v(dir, dir));
+  const float k16 = 16.0f * 1.1920929e-07f;
+  for (int it = 0; it < 5; ++it) {
+    const float Q[3] = {mul_rn(t, dir[0]), mul_rn(t, dir[1]), mul_rn(t, dir[2])};
+    const float Q_err = mul_rn(mul_rn(k16, length_ray_dir), t);
+    float P[4], dP[4], ddP[4];
+    cubic_eval(w.cp, w.basis, u, P, dP, ddP);
+    const float R[3] = {sub_rn(Q[0], P[0]), sub_rn(Q[1], P[1]), sub_rn(Q[2], P[2])};
+    const float RR = dot3v(R, R);
+    const float len_R = sqrtf(RR);
+    const float R_err = fmaxf(Q_err, w.P_err);
+    const float dRdu[3] = {-dP[0], -dP[1], -dP[2]};
+    const float dPdu2 = dot3v(dP, dP), rcp_len = rcp_rn(sqrtf(dPdu2));
+    const float T[3] = {mul_rn(dP[0], rcp_len), mul_rn(dP[1], rcp_len), mul_rn(dP[2], rcp_len)};
+    const float pdp = dot3v(dP, ddP), kk = mul_rn(rcp_rn(dPdu2), rcp_rn(sqrtf(dPdu2)));      // dnormalize (vec3fa.h:357-362)
+    const float dTdu[3] = {mul_rn(sub_rn(mul_rn(dPdu2, ddP[0]), mul_rn(pdp, dP[0])), kk), mul_rn(sub_rn(mul_rn(dPdu2, ddP[1]), mul_rn(pdp, dP[1])), kk),
+                           mul_rn(sub_rn(mul_rn(dPdu2, ddP[2]), mul_rn(pdp, dP[2])), kk)};
+    const float cos_err = mul_rn(w.P_err, rcp_len);
+    const float f = dot3v(R, T);
+    const float f_err = add_rn(add_rn(mul_rn(len_R, w.P_err), R_err), mul_rn(cos_err, add_rn(1.0f, len_R)));
+    const float dfdu = add_rn(dot3v(dRdu, T), dot3v(R, dTdu));
+    const float dfdt = dot3v(dir, T);
+    const float K = sub_rn(RR, mul_rn(f, f));
+    const float dKdu = sub_rn(dot3v(R, dRdu), mul_rn(f, dfdu));
+    const float dKdt = sub_rn(dot3v(R, dir), mul_rn(f, dfdt));
+    const float rsqrt_K = rcp_rn(sqrtf(K));
+    const float g = sub_rn(sqrtf(K), P[3]);
+    const float g_err = add_rn(add_rn(R_err, f_err), mul_rn(k16, w.upper_w));
+    const float dgdu = sub_rn(mul_rn(dKdu, rsqrt_K), dP[3]);
+    const float dgdt = mul_rn(dKdt, rsqrt_K);
+    const float rdet = rcp_rn(sub_rn(mul_rn(dfdu, dgdt), mul_rn(dfdt, dgdu)));
+    const float du = mul_rn(sub_rn(mul_rn(dgdt, f), mul_rn(dfdt, g)), rdet), dtt = mul_rn(sub_rn(mul_rn(dfdu, g), mul_rn(dgdu, f)), rdet);
+    u = sub_rn(u, du); t = sub_rn(t, dtt);
+    if (fabsf(f) < f_err && fabsf(g) < g_err) {
+      t = add_rn(t, w.dt);
+      if (!(w.tnear <= t && t <= w.tfar)) return false;
+      if (!(u >= 0.0f && u <= 1.0f)) return false;
+      const float rl = rcp_rn(sqrtf(RR));
+      const float Rn[3] = {mul_rn(R[0], rl), mul_rn(R[1], rl), mul_rn(R[2], rl)};
+      const float U[3] = {fma_rn(dP[3], Rn[0], dP[0]), fma_rn(dP[3], Rn[1], dP[1]), fma_rn(dP[3], Rn[2], dP[2])};
+      float V[3], Ng[3];
+      cross3v(dP, Rn, V);
+      cross3v(V, U, Ng);
+      w.hit.t = t; w.hit.u = u; w.hit.v = 0.0f; w.hit.ngx = Ng[0]; w.hit.ngy = Ng[1]; w.hit.ngz = Ng[2];
+      w.tfar = t; w.found = true;
+      return true;
+    }
+  }
+  return false;
+}
+// CylinderN::intersect for one lane, ray origin 0
+RT_HD bool sweep_cylinder(const float* p0, const float* p1, float r, const float* dir, float& tlo, float& thi, float& u0, float* Ng0, float& u1, float* Ng1) {
+  const float rr = mul_rn(r, r);
+  const float e[3] = {sub_rn(p1[0], p0[0]), sub_rn(p1[1], p0[1]), sub_rn(p1[2], p0[2])};
+  const float rl = rcp_rn(sqrtf(dot3v(e, e)));
+  const float dP[3] = {mul_rn(e[0], rl), mul_rn(e[1], rl), mul_rn(e[2], rl)};
+  const float O[3] = {-p0[0], -p0[1], -p0[2]};
+  const float dOdO = dot3v(dir, dir), OdO = dot3v(dir, O), OO = dot3v(O, O), dOz = dot3v(dP, dir), Oz = dot3v(dP, O);
+  const float A = sub_rn(dOdO, mul_rn(dOz, dOz)), B = mul_rn(2.0f, sub_rn(OdO, mul_rn(dOz, Oz))), C = sub_rn(sub_rn(OO, mul_rn(Oz, Oz)), rr);
+  const float D = sub_rn(mul_rn(B, B), mul_rn(mul_rn(4.0f, A), C));
+  bool valid = D >= 0.0f;
+  const float Q = sqrtf(D), rcp_2A = rcp_rn(mul_rn(2.0f, A));
+  const float t0 = mul_rn(sub_rn(-B, Q), rcp_2A), t1 = mul_rn(add_rn(-B, Q), rcp_2A);
+  u0 = mul_rn(fma_rn(t0, dOz, Oz), rl);
+  u1 = mul_rn(fma_rn(t1, dOz, Oz), rl);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    Ng0[k] = sub_rn(mul_rn(t0, dir[k]), fma_rn(u0, e[k], p0[k]));
+    Ng1[k] = sub_rn(mul_rn(t1, dir[k]), fma_rn(u1, e[k], p0[k]));
+  }
+  tlo = valid ? t0 : INFINITY; thi = valid ? t1 : -INFINITY;
+  const float eps = mul_rn(16.0f * 1.1920929e-07f, fmaxf(fabsf(dOdO), fabsf(mul_rn(dOz, dOz))));
+  if (valid && fabsf(A) < eps) {
+    const bool inside = C <= 0.0f;
+    tlo = inside ? -INFINITY : INFINITY; thi = inside ? INFINITY : -INFINITY;
+    valid = inside;
+  }
+  return valid;
+}
+RT_HD void sweep_halfplane(const float* P, const float* N, const float* dir, float& lo, float& hi) {
+  const float O[3] = {-P[0], -P[1], -P[2]};
+  const float ON = dot3v(O, N), DN = dot3v(dir, N);
+  const bool eps = fabsf(DN) < 1e-18f;
+  const float t = mul_rn(-ON, rcp_rn(DN));
+  lo = (eps || DN < 0.0f) ? -INFINITY : t;
+  hi = (eps || DN > 0.0f) ? INFINITY : t;
+}
+RT_HD int sweep_select_min(uint32_t valid, const float* v) {
+  int best = -1;
+  for (int i = 0; i < kSweepW; ++i) if ((valid >> i) & 1u) if (best < 0 || v[i] < v[best]) best = i;
+  return best;
+}
+RT_HD bool round_cubic_test(float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar, const CurveVtx cpv[4], uint32_t basis,
+                            CurveHit& h) {
+  const float org[3] = {ox, oy, oz}, dir[3] = {dx, dy, dz};
+  // move the ray origin next to the curve (:458-462); center(): bezier_curve.h:173, bspline_curve.h:94, catmullrom_curve.h:102
+  const float cin[4][3] = {{cpv[0].x, cpv[0].y, cpv[0].z}, {cpv[1].x, cpv[1].y, cpv[1].z}, {cpv[2].x, cpv[2].y, cpv[2].z}, {cpv[3].x, cpv[3].y, cpv[3].z}};
+  float co[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float c = basis == BASIS_CATMULL_ROM ? mul_rn(0.5f, add_rn(cin[0][k], cin[1][k])) : mul_rn(0.25f, add_rn(add_rn(add_rn(cin[0][k], cin[1][k]), cin[2][k]), cin[3][k]));
+    co[k] = sub_rn(c, org[k]);
+  }
+  const float dt = mul_rn(dot3v(co, dir), rcp_rn(dot3v(dir, dir)));
+  float cp[4][4];
+  float amax = 0.0f, upw = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { cp[k][a] = sub_rn(cin[k][a], fma_rn(dt, dir[a], org[a])); amax = fmaxf(amax, fabsf(cp[k][a])); }
+  }
+  cp[0][3] = cpv[0].r; cp[1][3] = cpv[1].r; cp[2][3] = cpv[2].r; cp[3][3] = cpv[3].r;
+  upw = fmaxf(fmaxf(cp[0][3], cp[1][3]), fmaxf(cp[2][3], cp[3][3]));
+  SweepState w;
+  w.dir = dir; w.tnear = tnear; w.tfar = tfar; w.dt = dt; w.cp = cp; w.basis = basis; w.found = false;
+  w.P_err = mul_rn(16.0f * 1.1920929e-07f, amax); w.upper_w = upw;
+  const uint32_t maxDepth = 2;
+  struct Entry { uint32_t valid; float tlower[kSweepW]; float u0, u1; uint32_t depth; } stack[3];
+  uint32_t sptr = 0, depth = 1;
+  float u0 = 0.0f, u1 = 1.0f;
+  bool first = true;
+  const float k7 = 1.0f / (kSweepW - 1);
+  while (first || sptr) {
+    if (!first) {
+      --sptr;
+      uint32_t valid = stack[sptr].valid;
+      for (int i = 0; i < kSweepW; ++i) if (!(add_rn(stack[sptr].tlower[i], dt) <= w.tfar)) valid &= ~(1u << i);
+      if (!valid) continue;
+      u0 = stack[sptr].u0; u1 = stack[sptr].u1; depth = stack[sptr].depth;
+      const int i = sweep_select_min(valid, stack[sptr].tlower);
+      valid &= ~(1u << i);
+      stack[sptr].valid = valid;
+      if (valid) ++sptr;
+      const float a0 = lerp_rn(u0, u1, mul_rn((float)i, k7)), a1 = lerp_rn(u0, u1, mul_rn((float)(i + 1), k7));
+      u0 = a0; u1 = a1;
+    }
+    first = false;
+    const float dscale = mul_rn(sub_rn(u1, u0), 1.0f / (3.0f * (kSweepW - 1)));
+    float P0[kSweepW][4], dP0[kSweepW][4];
+    for (int i = 0; i < kSweepW; ++i) {
+      cubic_eval(cp, basis, lerp_rn(u0, u1, mul_rn((float)i, k7)), P0[i], dP0[i], nullptr);
+      for (int a = 0; a < 4; ++a) dP0[i][a] = mul_rn(dP0[i][a], dscale);
+    }
+    uint32_t valid0 = 0, valid1 = 0, rec0 = 0, rec1 = 0;
+    float tp0lo[kSweepW], tp1lo[kSweepW], tp1hi[kSweepW], uo0[kSweepW], uo1[kSweepW];
+    for (int i = 0; i < kSweepW; ++i) { tp0lo[i] = tp1lo[i] = INFINITY; tp1hi[i] = -INFINITY; uo0[i] = uo1[i] = 0.0f; }
+    for (int i = 0; i < kSweepW - 1; ++i) {
+      const float *A0 = P0[i], *A3 = P0[i + 1], *dA0 = dP0[i], *dA3 = dP0[i + 1];
+      const float P1w = add_rn(A0[3], dA0[3]), P2w = sub_rn(A3[3], dA3[3]);
+      const float e[3] = {sub_rn(A3[0], A0[0]), sub_rn(A3[1], A0[1]), sub_rn(A3[2], A0[2])};
+      float n1[3], n2[3];
+      cross3v(dA0, e, n1); cross3v(dA3, e, n2);
+      const float rcp_ee = rcp_rn(dot3v(e, e));
+      const float rr1 = mul_rn(dot3v(n1, n1), rcp_ee), rr2 = mul_rn(dot3v(n2, n2), rcp_ee);
+      const float maxr12 = sqrtf(fmaxf(rr1, rr2));
+      float r_outer = add_rn(fmaxf(fmaxf(A0[3], P1w), fmaxf(P2w, A3[3])), maxr12);
+      float r_inner = sub_rn(fminf(fminf(A0[3], P1w), fminf(P2w, A3[3])), maxr12);
+      r_outer = mul_rn(1.0f + 2.0f * 1.1920929e-07f, r_outer);
+      r_inner = fmaxf(0.0f, mul_rn(1.0f - 2.0f * 1.1920929e-07f, r_inner));
+      float tlo, thi, u_o0, u_o1, Ng_o0[3], Ng_o1[3];
+      if (!sweep_cylinder(A0, A3, r_outer, dir, tlo, thi, u_o0, Ng_o0, u_o1, Ng_o1)) continue;
+      float lo = fmaxf(sub_rn(w.tnear, dt), tlo), hi = fminf(sub_rn(w.tfar, dt), thi), hl, hh;
+      sweep_halfplane(A0, dA0, dir, hl, hh);
+      lo = fmaxf(lo, hl); hi = fminf(hi, hh);
+      const float ndA3[3] = {-dA3[0], -dA3[1], -dA3[2]};
+      sweep_halfplane(A3, ndA3, dir, hl, hh);
+      lo = fmaxf(lo, hl); hi = fminf(hi, hh);
+      if (!(lo <= hi)) continue;
+      u_o0 = fminf(fmaxf(u_o0, 0.0f), 1.0f); u_o1 = fminf(fmaxf(u_o1, 0.0f), 1.0f);
+      uo0[i] = lerp_rn(u0, u1, mul_rn(add_rn((float)i, u_o0), 1.0f / (float)kSweepW));
+      uo1[i] = lerp_rn(u0, u1, mul_rn(add_rn((float)i, u_o1), 1.0f / (float)kSweepW));
+      float ilo, ihi, ui0 = 0.0f, ui1 = 0.0f, Ng_i0[3] = {0.0f, 0.0f, 0.0f}, Ng_i1[3] = {0.0f, 0.0f, 0.0f};
+      const bool valid_inner = sweep_cylinder(A0, A3, r_inner, dir, ilo, ihi, ui0, Ng_i0, ui1, Ng_i1);
+      const bool unstable0 = !valid_inner || fabsf(dot3v(dir, Ng_i0)) < 0.3f;
+      const bool unstable1 = !valid_inner || fabsf(dot3v(dir, Ng_i1)) < 0.3f;
+      tp0lo[i] = lo; const float tp0hi = fminf(hi, ilo);
+      tp1lo[i] = fmaxf(lo, ihi); tp1hi[i] = hi;
+      const bool v0 = tp0lo[i] <= tp0hi, v1 = tp1lo[i] <= tp1hi[i];
+      const uint32_t term0 = unstable0 ? maxDepth + 1 : maxDepth, term1 = unstable1 ? maxDepth + 1 : maxDepth;
+      if (v0) { if (depth < term0) rec0 |= 1u << i; else valid0 |= 1u << i; }
+      if (v1) { if (depth < term1) rec1 |= 1u << i; else valid1 |= 1u << i; }
+    }
+    if (!(valid0 | valid1 | rec0 | rec1)) continue;
+    while (valid0) {
+      const int i = sweep_select_min(valid0, tp0lo);
+      valid0 &= ~(1u << i);
+      sweep_jacobian(w, uo0[i], tp0lo[i]);
+      for (int j = 0; j < kSweepW; ++j) if (!(add_rn(tp0lo[j], dt) <= w.tfar)) valid0 &= ~(1u << j);
+    }
+    for (int j = 0; j < kSweepW; ++j) if (!(add_rn(tp1lo[j], dt) <= w.tfar)) { valid1 &= ~(1u << j); rec1 &= ~(1u << j); }
+    while (valid1) {
+      const int i = sweep_select_min(valid1, tp1lo);
+      valid1 &= ~(1u << i);
+      sweep_jacobian(w, uo1[i], tp1hi[i]);
+      for (int j = 0; j < kSweepW; ++j) if (!(add_rn(tp1lo[j], dt) <= w.tfar)) valid1 &= ~(1u << j);
+    }
+    for (int j = 0; j < kSweepW; ++j) {
+      if (!(add_rn(tp0lo[j], dt) <= w.tfar)) rec0 &= ~(1u << j);
+      if (!(add_rn(tp1lo[j], dt) <= w.tfar)) rec1 &= ~(1u << j);
+    }
+    if (rec0 | rec1) {
+      stack[sptr].valid = rec0 | rec1;
+      for (int j = 0; j < kSweepW; ++j) stack[sptr].tlower[j] = ((rec0 >> j) & 1u) ? tp0lo[j] : tp1lo[j];
+      stack[sptr].u0 = u0; stack[sptr].u1 = u1; stack[sptr].depth = depth + 1;
+      ++sptr;
+    }
+  }
+  if (w.found) h = w.hit;
+  return w.found;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Node8 encoding (build side)
 // ------------------------------------------------------------------------------------------------
 struct ChildBox { float lo[3], hi[3]; };

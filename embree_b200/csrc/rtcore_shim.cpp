@@ -127,10 +127,15 @@ struct BufferView {
 
 enum class GeomState { MODIFIED, COMMITTED };
 bool is_linear_curve(RTCGeometryType t) { return t == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE || t == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE; }
+bool is_round_cubic(RTCGeometryType t) {
+  return t == RTC_GEOMETRY_TYPE_ROUND_BEZIER_CURVE || t == RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE || t == RTC_GEOMETRY_TYPE_ROUND_HERMITE_CURVE ||
+         t == RTC_GEOMETRY_TYPE_ROUND_CATMULL_ROM_CURVE;
+}
 bool is_cubic_curve(RTCGeometryType t) {
   return t == RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE || t == RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE || t == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE ||
-         t == RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE;
+         t == RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE || is_round_cubic(t);
 }
+bool is_hermite(RTCGeometryType t) { return t == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE || t == RTC_GEOMETRY_TYPE_ROUND_HERMITE_CURVE; }
 // number of live geometries that have a filter callback or accept the arguments' filter: while it is zero (and the
 // query carries no filter) no query looks at the geometries at all
 std::atomic<long> g_filterGeoms{0};
@@ -343,10 +348,11 @@ void commit_scene(SceneImpl* s) {
     const size_t ncurves = g->indices.count, nverts = g->vertices.count;
     if (ncurves == 0 || !g->indices.buf) return;
     if (!g->vertices.buf) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer not set");
-    const bool hermite = g->type == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE;
+    const bool hermite = is_hermite(g->type), round = is_round_cubic(g->type);
     if (hermite && !g->tangents.buf) fail(RTC_ERROR_INVALID_OPERATION, "tangent buffer not set");
     if (hermite && g->tangents.count != nverts) fail(RTC_ERROR_INVALID_OPERATION, "number of tangents must match number of vertices");   // scene_curves.cpp commit
-    if (ncurves * (size_t)g->tessellationRate > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "curve geometry too large");
+    const size_t segs = round ? 1 : (size_t)g->tessellationRate;   // BVH primitives per curve
+    if (ncurves * segs > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "curve geometry too large");
     curves = true;
     const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 16 : 16, ibytes = (ncurves - 1) * g->indices.stride + 4;
     void *dv = nullptr, *di = nullptr, *dt = nullptr, *db = nullptr;
@@ -364,7 +370,8 @@ void commit_scene(SceneImpl* s) {
       cuda_check(cudaMemcpyAsync(dt, g->tangents.data(), tbytes, cudaMemcpyHostToDevice, 0), "upload curve tangents");
       d.tangents = static_cast<const uint8_t*>(dt); d.tstride = g->tangents.stride; d.hermite = 1;
     }
-    d.basis = g->type == RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE ? rtk::BASIS_BSPLINE : g->type == RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE ? rtk::BASIS_CATMULL_ROM : rtk::BASIS_BEZIER;
+    d.basis = (g->type == RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE || g->type == RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE) ? rtk::BASIS_BSPLINE
+            : (g->type == RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE || g->type == RTC_GEOMETRY_TYPE_ROUND_CATMULL_ROM_CURVE) ? rtk::BASIS_CATMULL_ROM : rtk::BASIS_BEZIER;
     d.tess = (uint32_t)g->tessellationRate;
     float tab[8 * (rtk::kMaxTess + 1)];
     rtk::curve_basis_table(d.basis, g->tessellationRate, tab);
@@ -376,8 +383,8 @@ void commit_scene(SceneImpl* s) {
     d.basis_tab = static_cast<const float*>(db);
     d.verts = static_cast<const uint8_t*>(dv); d.idx = static_cast<const uint8_t*>(di);
     d.vstride = g->vertices.stride; d.istride = g->indices.stride;
-    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)(ncurves * (size_t)g->tessellationRate);   // one BVH primitive per tessellation segment
-    d.geomID = geomID; d.mask = g->mask; d.is_curve = 3;
+    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)(ncurves * segs);   // flat: one BVH primitive per tessellation segment; round: per curve
+    d.geomID = geomID; d.mask = g->mask; d.is_curve = round ? 4 : 3;
     descs.push_back(d);
   };
   auto add_mesh = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
@@ -994,7 +1001,7 @@ RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
   API_BEGIN
   VERIFY_HANDLE(h);
   if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE && !is_linear_curve(type) && !is_cubic_curve(type))
-    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD, _ROUND_LINEAR_CURVE, _FLAT_LINEAR_CURVE, _FLAT_BEZIER / _BSPLINE / _HERMITE / _CATMULL_ROM_CURVE and _INSTANCE are supported by the B200 back-end");
+    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD, _ROUND / _FLAT_LINEAR_CURVE, _ROUND / _FLAT_BEZIER / _BSPLINE / _HERMITE / _CATMULL_ROM_CURVE and _INSTANCE are supported by the B200 back-end");
   GeometryImpl* g = new GeometryImpl(D(h));
   g->type = type;
   return reinterpret_cast<RTCGeometry>(g);
@@ -1033,7 +1040,7 @@ static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFo
   // scene_triangle_mesh.cpp:35-80, scene_quad_mesh.cpp:35-80
   if (g->type == RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
   const bool curve = is_linear_curve(g->type) || is_cubic_curve(g->type);   // scene_line_segments.cpp:35-100, scene_curves.cpp:50-140
-  if (g->type == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE && type == RTC_BUFFER_TYPE_TANGENT) {
+  if (is_hermite(g->type) && type == RTC_BUFFER_TYPE_TANGENT) {
     if (((size_t)(buf->ptr) + off) & 3 || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
     if (format != RTC_FORMAT_FLOAT4) fail(RTC_ERROR_INVALID_OPERATION, "invalid tangent buffer format");
     if (slot != 0) fail(RTC_ERROR_INVALID_OPERATION, "invalid tangent buffer slot");

@@ -113,7 +113,14 @@ __device__ __forceinline__ void to_object_space(const GeomDesc& d, Ray& r) {
 // round linear curve record (build.cu leaf_pack): a = (p0.xyz, primID), b = (p1.xyz, descriptor), c = (r0, r1, first vertex | flags << 30,
 // mask).  The neighbour vertices -- needed to cut away what lies inside the adjacent segments -- come from the geometry's
 // resident float4 vertex buffer (LineSegments::gather, scene_line_segments.h:270-276).
+// round cubic curve (sweep intersector): its own function, so that its arrays and register needs stay out of the other curve tests
+__device__ __noinline__ bool round_record_test(const GeomDesc& d, const Ray& r, float tfar, uint32_t vid, CurveHit& h) {
+  CurveVtx cp[4];
+  load_cubic_cp(d, vid, cp);
+  return round_cubic_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, cp, d.basis, h);
+}
 __device__ __noinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h) {
+  if (d.is_curve == 4) return round_record_test(d, r, tfar, c.z, h);
   if (d.is_curve == 3) {   // flat cubic curve (Bezier / B-spline / Catmull-Rom / Hermite): control points from the resident vertex buffer
     CurveVtx cp[4];
     load_cubic_cp(d, c.z, cp);
@@ -221,7 +228,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
   // better placed in shared memory ([field][thread], conflict-free) than left to the register allocator, which spills
   // other values inside the node step otherwise.
 #if RTK_LANE_SMEM
-  __shared__ uint32_t s_lane[9][TRACE_THREADS];   // 0 u, 1 v, 2 winning record, 3 ray index, 4-6 ray direction, 7 ray mask, 8 the ray's own tfar
+  // GENERAL == 2 (curve scenes): 9-11 the normal of a curve hit -- the round cubic test is an iteration whose result depends on
+  // the tfar it was started with, so the normal is kept from the winning test instead of re-running the test at write-back
+  __shared__ uint32_t s_lane[GENERAL == 2 ? 12 : 9][TRACE_THREADS];   // 0 u, 1 v, 2 winning record, 3 ray index, 4-6 ray direction, 7 ray mask, 8 the ray's own tfar
 #define hit_u (reinterpret_cast<float*>(s_lane[0])[threadIdx.x])
 #define hit_v (reinterpret_cast<float*>(s_lane[1])[threadIdx.x])
 #define hit_tri (s_lane[2][threadIdx.x])
@@ -334,10 +343,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         if (GENERAL) {   // ids through the descriptor; Ng stays in OBJECT space as in the reference
           const GeomDesc& d = p.descs[b.w];
           hit.geomID = d.geomID;
-          if (GENERAL == 2 && d.is_curve) {   // the normal of a curve hit depends on which surface was hit: re-run the (deterministic) test at the hit distance
-            CurveHit ch;
-            curve_record_test(d, full_ray(), tfar_tri, a, b, c, ch);
-            hit.ngx = ch.ngx; hit.ngy = ch.ngy; hit.ngz = ch.ngz;
+          if (GENERAL == 2 && d.is_curve) {   // the normal of a curve hit depends on which surface was hit: kept from the winning test
+            hit.ngx = __uint_as_float(s_lane[GENERAL == 2 ? 9 : 0][threadIdx.x]); hit.ngy = __uint_as_float(s_lane[GENERAL == 2 ? 10 : 0][threadIdx.x]);
+            hit.ngz = __uint_as_float(s_lane[GENERAL == 2 ? 11 : 0][threadIdx.x]);
             is_curve = true;
           }
           if (d.has_xfm) {
@@ -400,7 +408,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         if (visible && curve_record_test(d, wr, tfar_tri, a, b, c, ch)) {
           found = true;
           if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
-          else { tfar_tri = ch.t; hit_u = ch.u; hit_v = ch.v; hit_tri = ti; }
+          else {
+            tfar_tri = ch.t; hit_u = ch.u; hit_v = ch.v; hit_tri = ti;
+            s_lane[GENERAL == 2 ? 9 : 0][threadIdx.x] = __float_as_uint(ch.ngx); s_lane[GENERAL == 2 ? 10 : 0][threadIdx.x] = __float_as_uint(ch.ngy);
+            s_lane[GENERAL == 2 ? 11 : 0][threadIdx.x] = __float_as_uint(ch.ngz);
+          }
         }
         return;
       }

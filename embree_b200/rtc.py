@@ -26,6 +26,7 @@ RTC_GEOMETRY_TYPE_INSTANCE = 121
 RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE, RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE = 25, 33
 RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE, RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE = 41, 59
 FLAT_CUBIC_TYPES = {"bezier": 25, "bspline": 33, "hermite": 41, "catmull_rom": 59}
+ROUND_CUBIC_TYPES = {"bezier": 24, "bspline": 32, "hermite": 40, "catmull_rom": 58}
 RTC_BUFFER_TYPE_TANGENT = 4
 RTC_FORMAT_UCHAR = 0x1001
 RTC_FORMAT_UINT = 0x5001
@@ -346,13 +347,13 @@ class RTCLib:
         self.rtcReleaseGeometry(g)
         return gid, tuple(keep)
 
-    def add_flat_cubic_curves(self, device, scene, vertices4, indices, basis="bezier", tess=None, tangents=None, mask=None, geom_id=None):
+    def add_flat_cubic_curves(self, device, scene, vertices4, indices, basis="bezier", tess=None, tangents=None, mask=None, geom_id=None, round=False):
         """RTC_GEOMETRY_TYPE_FLAT_{BEZIER,BSPLINE,CATMULL_ROM,HERMITE}_CURVE: shared FLOAT4 control vertices (xyz, radius), UINT index
         of each curve's first control vertex, FLOAT4 tangents for 'hermite', optional tessellation rate (tutorials/curve_geometry,
         hair_geometry).  The arrays must stay alive."""
         v = np.ascontiguousarray(vertices4, np.float32).reshape(-1, 4)
         idx = np.ascontiguousarray(indices, np.uint32).reshape(-1)
-        g = self.rtcNewGeometry(device, FLAT_CUBIC_TYPES[basis])
+        g = self.rtcNewGeometry(device, (ROUND_CUBIC_TYPES if round else FLAT_CUBIC_TYPES)[basis])   # round=True: RTC_GEOMETRY_TYPE_ROUND_*_CURVE
         self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT4, _ptr(v), 0, 16, v.shape[0])
         self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT, _ptr(idx), 0, 4, idx.shape[0])
         keep = [v, idx]

@@ -121,16 +121,19 @@ def cubic_hair(strands, basis="bezier", knots=10, seed=7, radius=1.0, step=0.08,
     """Strands of connected cubic curves growing out of a sphere (tutorials/hair_geometry with --convert-...-to-curves, curve_geometry):
     `knots` float4 control points per strand from a random walk, tapering.  Index buffer = first control vertex of every
     curve: Bezier curves share their end points (0, 3, 6, ...), B-spline / Catmull-Rom curves slide by one, Hermite curves
-    join consecutive vertices and come with a random tangent (xyz, d radius) per vertex.
+    join consecutive vertices and come with a tangent per vertex (the strand's growth direction there, slightly perturbed, and the
+    radius derivative).
     Returns (vertices[nv,4], indices[nc] u32, tangents[nv,4] or None)."""
     rng = np.random.RandomState(seed)
     n = rng.normal(size=(strands, 3))
     n /= np.linalg.norm(n, axis=1, keepdims=True)
     pts = np.zeros((strands, knots, 4), np.float32)
+    dirs = np.zeros((strands, knots, 3), np.float32)
     p, d = n * radius, n.copy()
     for k in range(knots):
         pts[:, k, :3] = p
         pts[:, k, 3] = width * (1.0 - 0.7 * k / knots)
+        dirs[:, k] = d
         d = d + rng.normal(scale=0.5, size=d.shape)
         d /= np.linalg.norm(d, axis=1, keepdims=True)
         p = p + d * step
@@ -145,8 +148,8 @@ def cubic_hair(strands, basis="bezier", knots=10, seed=7, radius=1.0, step=0.08,
     tang = None
     if basis == "hermite":
         tang = np.zeros_like(verts)
-        tang[:, :3] = rng.normal(scale=1.2 * step, size=(len(verts), 3))
-        tang[:, 3] = rng.normal(scale=0.1 * width, size=len(verts))
+        tang[:, :3] = dirs.reshape(-1, 3) * (1.1 * step) + rng.normal(scale=0.15 * step, size=(len(verts), 3))
+        tang[:, 3] = -0.7 * width / knots + rng.normal(scale=0.02 * width, size=len(verts))
     return verts, idx, tang
 
 

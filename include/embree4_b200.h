@@ -85,6 +85,8 @@ enum RTCFeatureFlags {
   RTC_FEATURE_FLAG_QUAD = 1 << 2,
   RTC_FEATURE_FLAG_ROUND_LINEAR_CURVE = 1 << 6,
   RTC_FEATURE_FLAG_FLAT_LINEAR_CURVE = 1 << 7,
+  RTC_FEATURE_FLAG_ROUND_BEZIER_CURVE = 1 << 8, RTC_FEATURE_FLAG_ROUND_BSPLINE_CURVE = 1 << 11,
+  RTC_FEATURE_FLAG_ROUND_HERMITE_CURVE = 1 << 14, RTC_FEATURE_FLAG_ROUND_CATMULL_ROM_CURVE = 1 << 17,
   RTC_FEATURE_FLAG_FLAT_BEZIER_CURVE = 1 << 9, RTC_FEATURE_FLAG_FLAT_BSPLINE_CURVE = 1 << 12,
   RTC_FEATURE_FLAG_FLAT_HERMITE_CURVE = 1 << 15, RTC_FEATURE_FLAG_FLAT_CATMULL_ROM_CURVE = 1 << 18,
   RTC_FEATURE_FLAG_INSTANCE = 1 << 23,
@@ -104,6 +106,13 @@ enum RTCGeometryType {
   RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE = 33,
   RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE = 41,
   RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE = 59,
+  /* round cubic curves (rtcore_geometry.h:30,34,38,46; curve_intersector_sweep.h): the same buffers; the curve is the sweep of a
+   * sphere of radius r(u) along P(u), intersected by the reference's cylinder-bounded subdivision + Newton iteration; hits
+   * report u along the curve, v = 0 and the surface normal */
+  RTC_GEOMETRY_TYPE_ROUND_BEZIER_CURVE = 24,
+  RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE = 32,
+  RTC_GEOMETRY_TYPE_ROUND_HERMITE_CURVE = 40,
+  RTC_GEOMETRY_TYPE_ROUND_CATMULL_ROM_CURVE = 58,
   RTC_GEOMETRY_TYPE_INSTANCE = 121 /* single-level instances of triangle scenes (rtcore_geometry.h:51) */
 };
 enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2, RTC_BUFFER_TYPE_TANGENT = 4, RTC_BUFFER_TYPE_FLAGS = 32 };

@@ -82,7 +82,7 @@ def load_golden_cubic(name="curves_cubic"):
         tess = int(z[f"ctess{i}"])
         tg = z[f"ctang{i}"]
         cubics.append((z[f"cv{i}"], z[f"ci{i}"], int(z[f"cgid{i}"]), int(z[f"cmask{i}"]), CUBIC_SETS[i][0], tess if tess else None,
-                       tg if tg.size else None))
+                       tg if tg.size else None, bool(int(z["round"])) if "round" in z else False))
     return dict(meshes=[(z["v0"], z["t0"], 0, 0xFFFFFFFF)], cubics=cubics, rays_in=rec(z["rays_in"], RAYHIT_DTYPE),
                 intersect_out=rec(z["intersect_out"], RAYHIT_DTYPE), occluded_out=rec(z["occluded_out"], RAY_DTYPE), bounds=z["bounds"])
 

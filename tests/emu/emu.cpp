@@ -440,3 +440,18 @@ extern "C" void emu_trace_cull(void* h, void* rays, uint64_t n, int mode, uint64
     cull_visit(c, 0);
   }
 }
+
+// ---- round cubic curves (rt_core.cuh round_cubic_test), host instantiation; same calling convention as emu_flat_cubic_closest
+extern "C" int emu_round_cubic_closest(const float* ray8, const float* cps, int n, unsigned basis, float* out6) {
+  float tfar = ray8[7];
+  int win = -1;
+  for (int i = 0; i < n; ++i) {
+    CurveVtx cp[4];
+    for (int k = 0; k < 4; ++k) cp[k] = CurveVtx{cps[i * 16 + k * 4], cps[i * 16 + k * 4 + 1], cps[i * 16 + k * 4 + 2], cps[i * 16 + k * 4 + 3]};
+    CurveHit h;
+    if (!round_cubic_test(ray8[0], ray8[1], ray8[2], ray8[4], ray8[5], ray8[6], ray8[3], tfar, cp, basis, h)) continue;
+    tfar = h.t; win = i;
+    out6[0] = h.t; out6[1] = h.u; out6[2] = h.v; out6[3] = h.ngx; out6[4] = h.ngy; out6[5] = h.ngz;
+  }
+  return win;
+}

@@ -188,9 +188,10 @@ def main_curves():
 from tests.golden.make_golden_sets import CUBIC_SETS  # noqa: E402
 
 
-def main_cubic_curves():
-    """Flat cubic curves (curve_intersector_ribbon.h): one curve set per basis, each with its own tessellation rate and
-    geometry mask, around a triangle sphere; rays from outside towards the ball, some with masks and tnear / tfar windows."""
+def main_cubic_curves(name="curves_cubic", rnd=False):
+    """Flat cubic curves (curve_intersector_ribbon.h; rnd: ROUND cubic curves, curve_intersector_sweep.h): one curve set per basis,
+    each with its own tessellation rate and geometry mask, around a triangle sphere; rays from outside towards the ball, some
+    with masks and tnear / tfar windows."""
     R = load_reference()
     v, t = scenes.triangle_sphere(12)
     v = (v * np.float32(0.9)).astype(np.float32)
@@ -212,7 +213,7 @@ def main_cubic_curves():
     sc = R.rtcNewScene(dev)
     keep = [R.add_triangle_mesh(dev, sc, v, t, mask=0xFFFFFFFF, geom_id=0)[1]]
     for (cv, ci, gid, mask, basis, tess, tg) in sets:
-        keep.append(R.add_flat_cubic_curves(dev, sc, cv, ci, basis, tess, tg, mask=mask, geom_id=gid)[1])
+        keep.append(R.add_flat_cubic_curves(dev, sc, cv, ci, basis, tess, tg, mask=mask, geom_id=gid, round=rnd)[1])
     R.rtcCommitScene(sc)
     R.check(dev)
     b = RTCBounds()
@@ -223,14 +224,14 @@ def main_cubic_curves():
     dd = dict(rays_in=rays.view(np.uint8).reshape(-1, 96), intersect_out=out_i.view(np.uint8).reshape(-1, 96),
               occluded_out=out_o.view(np.uint8).reshape(-1, 48),
               bounds=np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32),
-              v0=v, t0=t, n_sets=np.array(len(sets)))
+              v0=v, t0=t, n_sets=np.array(len(sets)), round=np.array(1 if rnd else 0))
     for i, (cv, ci, gid, mask, basis, tess, tg) in enumerate(sets):
         dd[f"cv{i}"], dd[f"ci{i}"], dd[f"cgid{i}"], dd[f"cmask{i}"] = cv, ci, np.array(gid, np.uint32), np.array(mask, np.uint32)
         dd[f"ctess{i}"] = np.array(0 if tess is None else tess)
         dd[f"ctang{i}"] = tg if tg is not None else np.zeros((0, 4), np.float32)
-    np.savez_compressed(os.path.join(HERE, "curves_cubic.npz"), **dd)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **dd)
     per = {basis: int((out_i["geomID"] == 1 + k).sum()) for k, (basis, _t) in enumerate(CUBIC_SETS)}
-    print(f"curves_cubic: {len(rays)} rays, hits per basis {per}, triangles {(out_i['geomID'] == 0).sum()}, occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
+    print(f"{name}: {len(rays)} rays, hits per basis {per}, triangles {(out_i['geomID'] == 0).sum()}, occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
     R.rtcReleaseScene(sc)
     R.rtcReleaseDevice(dev)
 
@@ -328,6 +329,7 @@ def main():
                   [0xFFFFFFFF if i % 3 else 0x5 for i in range(7)], r)
     main_curves()
     main_cubic_curves()
+    main_cubic_curves("curves_cubic_round", True)
     main_filters()
 
 
@@ -337,6 +339,7 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cubic":
         main_cubic_curves()
+        main_cubic_curves("curves_cubic_round", True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "filters":
         main_filters()

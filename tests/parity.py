@@ -29,7 +29,7 @@ class Oracle:
         d.orc_add_curves.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_uint, C.c_uint]
         d.orc_add_curves_typed.argtypes = d.orc_add_curves.argtypes + [C.c_int]
         d.orc_add_cubic_curves.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint,
-                                           C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+                                           C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         d.orc_add_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
         d.orc_set_robust.argtypes = [C.c_void_p, C.c_int]
         d.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
@@ -75,13 +75,15 @@ class OracleScene:
             self.keep += [cv, ci, cf]
             o.d.orc_add_curves_typed(self.h, cv.ctypes.data, 16, cv.shape[0], ci.ctypes.data, 4, ci.shape[0],
                                      None if cf is None else cf.ctypes.data, gid, mask, 1 if flat else 0)
-        for (cv, ci, gid, mask, basis, tess, tang) in cubics:   # flat cubic curves: basis 'bezier' | 'bspline' | 'catmull_rom' | 'hermite'
+        for entry in cubics:   # cubic curves: basis 'bezier' | 'bspline' | 'catmull_rom' | 'hermite'; 8th element True: ROUND (swept) instead of flat
+            cv, ci, gid, mask, basis, tess, tang = entry[:7]
+            rnd = len(entry) > 7 and bool(entry[7])
             cv = np.ascontiguousarray(cv, np.float32).reshape(-1, 4)
             ci = np.ascontiguousarray(ci, np.uint32).reshape(-1)
             tg = None if tang is None else np.ascontiguousarray(tang, np.float32).reshape(-1, 4)
             self.keep += [cv, ci, tg]
             o.d.orc_add_cubic_curves(self.h, cv.ctypes.data, 16, cv.shape[0], ci.ctypes.data, 4, ci.shape[0], gid, mask,
-                                     CUBIC_BASES.index(basis), int(tess), None if tg is None else tg.ctypes.data, 16)
+                                     CUBIC_BASES.index(basis), int(tess), None if tg is None else tg.ctypes.data, 16, 1 if rnd else 0)
         for (child, xfm, gid, mask) in instances:
             m = np.ascontiguousarray(xfm, np.float32).reshape(12)
             self.keep += [child, m]
@@ -279,5 +281,28 @@ def unexplained_ribbon_disagreements(a, b, curve_geoms, vmin=0.999):
         cands = [x for x, h in ((a, ah[i]), (b, bh[i])) if h]
         near = min(cands, key=lambda x: float(x["tfar"][i]))
         if not (int(near["geomID"][i]) in curve_geoms and abs(float(near["v"][i])) >= vmin):
+            bad += 1
+    return int(differ.sum()), bad
+
+
+def sweep_disagreements(rays, a, b, curve_geoms, tol=1e-4, cos_max=0.1):
+    """Round (swept) cubic curves: the hit is the result of a Newton iteration started from bounding-cylinder estimates
+    (curve_intersector_sweep.h:59-140), so two implementations can converge to different roots, or one of them not at all,
+    where the problem is ill-conditioned: on the silhouette of the tube, where the ray is tangent to the surface.  Returns
+    (differing rays, unexplained ones): a ray differs when hit / miss, the curve or the distance (beyond `tol` relative)
+    differ; it is explained when the nearer of the two hits is a curve hit whose normal is perpendicular to the ray
+    (|cos(Ng, dir)| < cos_max)."""
+    ah, bh = a["geomID"] != 0xFFFFFFFF, b["geomID"] != 0xFFFFFFFF
+    with np.errstate(invalid="ignore"):
+        rel = np.abs(a["tfar"] - b["tfar"]) / np.maximum(np.abs(a["tfar"]), 1e-30)
+    differ = (ah != bh) | (ah & bh & ((a["primID"] != b["primID"]) | (a["geomID"] != b["geomID"]) | (rel > tol)))
+    bad = 0
+    for i in np.nonzero(differ)[0]:
+        cands = [x for x, h in ((a, ah[i]), (b, bh[i])) if h]
+        near = min(cands, key=lambda x: float(x["tfar"][i]))
+        ng = np.array([near["Ng_x"][i], near["Ng_y"][i], near["Ng_z"][i]], np.float64)
+        d = np.array([rays["dir_x"][i], rays["dir_y"][i], rays["dir_z"][i]], np.float64)
+        c = abs(ng @ d) / max(np.linalg.norm(ng) * np.linalg.norm(d), 1e-300)
+        if not (int(near["geomID"][i]) in curve_geoms and c < cos_max):
             bad += 1
     return int(differ.sum()), bad

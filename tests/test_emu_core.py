@@ -222,7 +222,7 @@ def test_flat_cubic_curve_test_equals_oracle(emu, oracle, which):
     from tests.conftest import load_golden_cubic
     from tests.parity import CUBIC_BASES
     g = load_golden_cubic()
-    cv, ci, gid, mask, basis, tess, tang = g["cubics"][which]
+    cv, ci, gid, mask, basis, tess, tang = g["cubics"][which][:7]
     tess = 4 if tess is None else tess
     sc = oracle.scene([], cubics=[(cv, ci, gid, 0xFFFFFFFF, basis, tess, tang)])
     rays = g["rays_in"][::2].copy()
@@ -254,4 +254,50 @@ def test_flat_cubic_curve_test_equals_oracle(emu, oracle, which):
         if win == w["primID"]:
             assert (got == exp).all(), (k, list(out), w)
     assert hits > 50
+    sc.free()
+
+
+@pytest.mark.parametrize("basis", ["bezier", "bspline", "catmull_rom", "hermite"])
+def test_round_cubic_curve_test_equals_oracle(emu, oracle, basis):
+    """rt_core.cuh round_cubic_test (RTC_GEOMETRY_TYPE_ROUND_*_CURVE: the sweep intersector with its Newton iteration), host
+    instantiation, brute force over all curves: the same winner and bit-identical t / u / Ng as the C oracle's BVH traversal."""
+    import ctypes as C
+    from embree_b200 import scenes
+    from embree_b200.rtc import make_rayhits
+    from tests.parity import CUBIC_BASES
+    cv, ci, tang = scenes.cubic_hair(90, basis, seed=13, width=0.03)
+    sc = oracle.scene([], cubics=[(cv, ci, 1, 0xFFFFFFFF, basis, 4, tang, True)])
+    rng = np.random.RandomState(5)
+    org = rng.normal(size=(1500, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * 2.0
+    d = (-org + rng.normal(scale=0.35, size=org.shape)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    rays["tnear"][::7] = 1.1
+    want = sc.trace(rays.copy())
+    if basis == "hermite":
+        k = np.float32(1.0 / 3.0)
+        fma = lambda a, b, c: (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)   # noqa: E731
+        p0, p1, t0, t1 = cv[ci], cv[ci + 1], tang[ci], tang[ci + 1]
+        cps = np.stack([p0, fma(np.full_like(t0, k), t0, p0), fma(np.full_like(t1, -k), t1, p1), p1], 1)
+    else:
+        cps = np.stack([cv[ci + j] for j in range(4)], 1)
+    cps = np.ascontiguousarray(cps, np.float32)
+    emu.emu_round_cubic_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_void_p]
+    out = (C.c_float * 6)()
+    hits = 0
+    for k in range(len(rays)):
+        r = rays[k]
+        ray = np.array([r["org_x"], r["org_y"], r["org_z"], r["tnear"], r["dir_x"], r["dir_y"], r["dir_z"], r["tfar"]], np.float32)
+        win = emu.emu_round_cubic_closest(ray.ctypes.data, cps.ctypes.data, len(ci), 0 if basis == "hermite" else CUBIC_BASES.index(basis), out)
+        w = want[k]
+        if win < 0:
+            assert w["geomID"] == 0xFFFFFFFF, k
+            continue
+        hits += 1
+        got = np.array(list(out), np.float32).view(np.uint32)
+        exp = np.array([w["tfar"], w["u"], w["v"], w["Ng_x"], w["Ng_y"], w["Ng_z"]], np.float32).view(np.uint32)
+        assert got[0] == exp[0], (k, list(out), w)
+        if win == w["primID"]:
+            assert (got == exp).all(), (k, list(out), w)
+    assert hits > 150
     sc.free()

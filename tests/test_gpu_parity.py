@@ -608,20 +608,22 @@ def build_cubic_scene(lib, dev, meshes, cubics, quality=RTC_BUILD_QUALITY_MEDIUM
     sc = lib.rtcNewScene(dev)
     lib.rtcSetSceneBuildQuality(sc, quality)
     keep = [lib.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in meshes]
-    keep += [lib.add_flat_cubic_curves(dev, sc, cv, ci, basis, tess, tg, mask=mask, geom_id=gid)[1] for (cv, ci, gid, mask, basis, tess, tg) in cubics]
+    keep += [lib.add_flat_cubic_curves(dev, sc, c[0], c[1], c[4], c[5], c[6], mask=c[3], geom_id=c[2], round=len(c) > 7 and c[7])[1] for c in cubics]
     lib.rtcCommitScene(sc)
     lib.check(dev)
     return sc, keep
 
 
+@pytest.mark.parametrize("name", ["curves_cubic", "curves_cubic_round"])
 @pytest.mark.parametrize("quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
-def test_cubic_curves_golden_all_entry_points(b200, quality):
+def test_cubic_curves_golden_all_entry_points(b200, quality, name):
     """RTC_GEOMETRY_TYPE_FLAT_BEZIER / _BSPLINE / _CATMULL_ROM / _HERMITE_CURVE (curve_intersector_ribbon.h:73-190; tessellation
-    rates default / 7 / 4 / 12, one geometry mask) against the reference's own outputs through every entry point: ids exact,
-    t / u / v within tolerance, Ng = the curve tangent, any-hit equal, scene bounds as the reference reports them."""
+    rates default / 7 / 4 / 12, one geometry mask) and their ROUND counterparts (curve_intersector_sweep.h) against the
+    reference's own outputs through every entry point: ids exact, t / u / v within tolerance, Ng = the curve tangent (flat) or
+    the surface normal (round), any-hit equal, scene bounds as the reference reports them."""
     from tests.conftest import load_golden_cubic
     lib, dev = b200
-    g = load_golden_cubic()
+    g = load_golden_cubic(name)
     sc, keep = build_cubic_scene(lib, dev, g["meshes"], g["cubics"], quality)
     b = RTCBounds()
     lib.rtcGetSceneBounds(sc, C.byref(b))
@@ -632,12 +634,43 @@ def test_cubic_curves_golden_all_entry_points(b200, quality):
         got = lib.intersect(sc, g["rays_in"].copy(), mode)
         rep = compare_hits(want, got, TOL)
         assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 4, (mode, rep)
-        assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= 2e-4 and rep["miss_untouched"], (mode, rep)
+        # u of a round curve is the root of a Newton iteration: ill-conditioned where the ray grazes the tube (seen: 2.5e-3)
+        assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= (5e-3 if name.endswith("round") else 2e-4) and rep["miss_untouched"], (mode, rep)
         ok = (got["geomID"] == want["geomID"]) & (got["primID"] == want["primID"]) & (got["geomID"] != 0xFFFFFFFF)
         for f in ("Ng_x", "Ng_y", "Ng_z"):
-            assert np.allclose(got[f][ok], want[f][ok], rtol=1e-3, atol=1e-5), (mode, f)
+            assert np.allclose(got[f][ok], want[f][ok], rtol=2e-2 if name.endswith("round") else 1e-3, atol=1e-4 if name.endswith("round") else 1e-5), (mode, f)
         occ = lib.occluded(sc, rays_of(g["rays_in"]), mode)
         assert ((occ["tfar"] == -np.inf) == (g["occluded_out"]["tfar"] == -np.inf)).all(), mode
+    lib.rtcReleaseScene(sc)
+
+
+@pytest.mark.parametrize("basis", ["bezier", "bspline", "catmull_rom", "hermite"])
+def test_round_cubic_curves_large_vs_oracle(b200, oracle, basis):
+    """20 000 strands of ROUND cubic curves + a triangle mesh against the C oracle: the device runs the oracle's arithmetic
+    operation for operation (tests/test_emu_core.py), so hits are bit-identical wherever the two name the same curve, the GPU
+    loses no hit (conservative bounds), and a different curve is only admissible at the same distance."""
+    lib, dev = b200
+    cv, ci, tg = scenes.cubic_hair(20000, basis, seed=12, width=0.006)
+    v, t = scenes.triangle_sphere(60)
+    sc, keep = build_cubic_scene(lib, dev, [(v, t, 0, 0xFFFFFFFF)], [(cv, ci, 1, 0xFFFFFFFF, basis, None, tg, True)])
+    rng = np.random.RandomState(8)
+    org = rng.normal(size=(200000, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * rng.uniform(1.02, 2.0, (200000, 1)).astype(np.float32)
+    d = (-org + rng.normal(scale=0.7, size=org.shape)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    got = lib.intersect(sc, rays.copy(), "1M")
+    osc = oracle.scene([(v, t, 0, 0xFFFFFFFF)], cubics=[(cv, ci, 1, 0xFFFFFFFF, basis, 4, tg, True)])
+    want = osc.trace(rays.copy(), nthreads=16)
+    rep = compare_hits(want, got, TOL)
+    assert (want["geomID"] == 1).sum() > 15000, rep
+    assert rep["hit_miss_disagree"] == 0 and rep["id_mismatch"] == 0 and rep["tie"] <= 20, rep
+    same = (got["geomID"] == want["geomID"]) & (got["primID"] == want["primID"]) & (want["geomID"] == 1)
+    for f in ("tfar", "u", "v", "Ng_x", "Ng_y", "Ng_z"):
+        assert (got[f][same].view(np.uint32) == want[f][same].view(np.uint32)).all(), f
+    occ = lib.occluded(sc, rays_of(rays), "1M")
+    wocc = osc.trace(rays_of(rays), occluded=True, nthreads=16)
+    assert ((occ["tfar"] == -np.inf) == (wocc["tfar"] == -np.inf)).all()
+    osc.free()
     lib.rtcReleaseScene(sc)
 
 

@@ -234,22 +234,24 @@ def test_oracle_curves_vs_reference_live(oracle):
     del keep
 
 
-def test_oracle_cubic_curves_vs_golden(oracle):
+@pytest.mark.parametrize("name", ["curves_cubic", "curves_cubic_round"])
+def test_oracle_cubic_curves_vs_golden(oracle, name):
     """Flat Bezier / B-spline / Catmull-Rom / Hermite curves (curve_intersector_ribbon.h:73-190, tessellation rates 4 / 7 / 4 / 12)
-    restated in oracle/embree_oracle.c against the reference's own outputs: ids exact, t / u / v and the tangent Ng within
-    tolerance, any-hit equal, scene bounds equal."""
+    and their ROUND counterparts (curve_intersector_sweep.h) restated in oracle/embree_oracle.c against the reference's own
+    outputs: ids exact, t / u / v and Ng within tolerance, any-hit equal, scene bounds equal."""
     from tests.conftest import load_golden_cubic
-    g = load_golden_cubic()
-    sc = oracle.scene(g["meshes"], cubics=[(cv, ci, gid, mask, basis, 4 if tess is None else tess, tg) for (cv, ci, gid, mask, basis, tess, tg) in g["cubics"]])
+    g = load_golden_cubic(name)
+    rnd = name.endswith("round")
+    sc = oracle.scene(g["meshes"], cubics=[(c[0], c[1], c[2], c[3], c[4], 4 if c[5] is None else c[5], c[6], c[7]) for c in g["cubics"]])
     got = sc.trace(g["rays_in"].copy())
     want = g["intersect_out"]
     rep = compare_hits(want, got)
     assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 4, rep
-    assert rep["max_rel_t"] <= 1e-4 and rep["max_abs_uv"] <= 2e-4 and rep["miss_untouched"], rep
+    assert rep["max_rel_t"] <= 1e-4 and rep["max_abs_uv"] <= (5e-3 if rnd else 2e-4) and rep["miss_untouched"], rep
     ok = (got["geomID"] == want["geomID"]) & (got["primID"] == want["primID"]) & (got["geomID"] != 0xFFFFFFFF)
     assert ((want["geomID"] >= 1) & ok).sum() > 1500
     for f in ("Ng_x", "Ng_y", "Ng_z"):
-        assert np.allclose(got[f][ok], want[f][ok], rtol=1e-3, atol=1e-5), f
+        assert np.allclose(got[f][ok], want[f][ok], rtol=2e-2 if rnd else 1e-3, atol=1e-4 if rnd else 1e-5), f
     occ = sc.trace(rays_of(g["rays_in"]), occluded=True)
     assert (occ["tfar"].view(np.uint32) == g["occluded_out"]["tfar"].view(np.uint32)).all()
     assert np.allclose(sc.bounds(), g["bounds"], rtol=2e-7, atol=0)
@@ -288,6 +290,40 @@ def test_oracle_cubic_curves_vs_reference_live(oracle, basis, tess):
     ro = api_trace_mt(R, rs, rays_of(rays), 4, occluded=True)
     wo = sc.trace(rays_of(rays), occluded=True, nthreads=4)
     assert ((ro["tfar"] < 0) != (wo["tfar"] < 0)).sum() <= 2
+    R.rtcReleaseScene(rs)
+    R.rtcReleaseDevice(dev)
+    sc.free()
+
+
+@pytest.mark.parametrize("basis", ["bezier", "bspline", "catmull_rom", "hermite"])
+def test_oracle_round_cubic_curves_vs_reference_live(oracle, basis):
+    """ROUND cubic curves (sweep intersector) while the reference library is present: 400 strands, 60 000 rays.  The hit is the
+    root of a Newton iteration, so the two implementations may part where the problem is ill-conditioned -- on the silhouette of
+    the tube; every differing ray must be such a graze (tests/parity.py sweep_disagreements; seen: 0-3 of 60 000)."""
+    R = load_reference()
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    from tests.parity import api_trace_mt, sweep_disagreements
+    cv, ci, tg = scenes.cubic_hair(400, basis, seed=8)
+    v, t = scenes.triangle_sphere(16)
+    rng = np.random.RandomState(10)
+    org = rng.normal(size=(60000, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * 2.5
+    d = (-org + rng.normal(scale=0.5, size=org.shape)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    sc = oracle.scene([(v, t, 0, 0xFFFFFFFF)], cubics=[(cv, ci, 1, 0xFFFFFFFF, basis, 4, tg, True)])
+    want = sc.trace(rays.copy(), nthreads=4)
+    dev = R.new_device(None)
+    rs = R.rtcNewScene(dev)
+    keep = [R.add_triangle_mesh(dev, rs, v, t, mask=0xFFFFFFFF, geom_id=0)[1], R.add_flat_cubic_curves(dev, rs, cv, ci, basis, None, tg, mask=0xFFFFFFFF, geom_id=1, round=True)[1]]
+    R.rtcCommitScene(rs)
+    R.check(dev)
+    ref = api_trace_mt(R, rs, rays.copy(), 4)
+    n_differ, unexplained = sweep_disagreements(rays, ref, want, {1})
+    assert (ref["geomID"] == 1).sum() > 5000 and n_differ <= 8 and unexplained == 0, (n_differ, unexplained)
+    ro = api_trace_mt(R, rs, rays_of(rays), 4, occluded=True)
+    wo = sc.trace(rays_of(rays), occluded=True, nthreads=4)
+    assert ((ro["tfar"] < 0) != (wo["tfar"] < 0)).sum() <= n_differ
     R.rtcReleaseScene(rs)
     R.rtcReleaseDevice(dev)
     sc.free()
