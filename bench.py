@@ -294,20 +294,21 @@ def dynamic_leg(lib, dev, args):
     return out
 
 
-def hair_leg(lib, dev, devt, stream, args):
-    """configs[3]a: tutorials/hair_geometry with Bezier curves -- a fur ball of flat cubic Bezier curves
+def hair_leg(lib, dev, devt, stream, args, rnd=False):
+    """configs[3]a (rnd: the same fur ball as RTC_GEOMETRY_TYPE_ROUND_BEZIER_CURVE, the xml loader's default hair type,
+    xml_loader.cpp:1322 -- the sweep intersector): tutorials/hair_geometry with Bezier curves -- a fur ball of flat cubic Bezier curves
     (RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE, what the tutorials' hair generators and loaders create, geometry_creation.cpp:340,
     obj_loader.cpp:641) around a triangle sphere.  Two ray sets: 1920x1080 camera rays and as many incoherent rays aimed at
     the ball; closest hit and any hit, device-resident, CUDA events; next to the unmodified reference's rtcIntersect1 on the
     usable host threads, with parity of every ray."""
-    from tests.parity import api_trace_mt, compare_hits, load_reference, unexplained_ribbon_disagreements
+    from tests.parity import api_trace_mt, compare_hits, load_reference, sweep_disagreements, unexplained_ribbon_disagreements
     strands = 120000
     cv, ci, _tg = scenes.cubic_hair(strands, "bezier", knots=10, seed=5, radius=1.0, step=0.05, width=0.0025)
     v, t = scenes.triangle_sphere(201)
 
     def build(L, d):
         sc = L.rtcNewScene(d)
-        keep = [L.add_triangle_mesh(d, sc, v, t, mask=0xFFFFFFFF, geom_id=0)[1], L.add_flat_cubic_curves(d, sc, cv, ci, "bezier", None, None, mask=0xFFFFFFFF, geom_id=1)[1]]
+        keep = [L.add_triangle_mesh(d, sc, v, t, mask=0xFFFFFFFF, geom_id=0)[1], L.add_flat_cubic_curves(d, sc, cv, ci, "bezier", None, None, mask=0xFFFFFFFF, geom_id=1, round=rnd)[1]]
         t0 = time.perf_counter()
         L.rtcCommitScene(sc)
         dt = time.perf_counter() - t0
@@ -323,7 +324,8 @@ def hair_leg(lib, dev, devt, stream, args):
     d = -o + 0.45 * torch.randn((n, 3), generator=g)
     inc = scenes.pack_rayhits(o.to(devt), d.to(devt), 0.0, float("inf"))
     a = lib.args()
-    out = {"workload": f"fur ball: {strands} strands x 3 flat cubic Bezier curves = {len(ci)} curves (tessellation rate 4) + createTriangleSphere(numPhi=201) = {len(t)} triangles",
+    kind = "round cubic Bezier curves (swept spheres)" if rnd else "flat cubic Bezier curves (tessellation rate 4)"
+    out = {"workload": f"fur ball: {strands} strands x 3 {kind} = {len(ci)} curves + createTriangleSphere(numPhi=201) = {len(t)} triangles",
            "curves": int(len(ci)), "triangles": int(len(t)), "commit_ms": commit_s * 1e3, "build_device_ms": st.build_ms, "nodes": int(st.num_nodes)}
     cores, _detail = usable_cores()
     R = load_reference() if not args.no_cpu else None
@@ -370,9 +372,14 @@ def hair_leg(lib, dev, devt, stream, args):
             row["reference"] = {"Mrays_per_s": n / rbest * 1e-6, "cores": cores, "api": "rtcIntersect1 loop (FTZ|DAZ), best of 2"}
             rep = compare_hits(w, got)
             row["parity"] = {k: rep[k] for k in ("n", "hits", "id_mismatch", "tie", "hit_miss_disagree", "max_rel_t", "max_abs_uv")}
-            nd, bad = unexplained_ribbon_disagreements(w, got, {1})
-            row["parity"]["differing_rays"] = nd
-            row["parity"]["not_on_a_ribbon_edge"] = bad     # every difference must be a ray through the very edge (|v| >= 0.999) of the nearer ribbon
+            if rnd:
+                nd, bad = sweep_disagreements(rin, w, got, {1})
+                row["parity"]["differing_rays"] = nd
+                row["parity"]["not_a_silhouette_graze"] = bad   # every difference must be a ray tangent to the tube (|cos(Ng, dir)| < 0.1 at the nearer hit)
+            else:
+                nd, bad = unexplained_ribbon_disagreements(w, got, {1})
+                row["parity"]["differing_rays"] = nd
+                row["parity"]["not_on_a_ribbon_edge"] = bad     # every difference must be a ray through the very edge (|v| >= 0.999) of the nearer ribbon
             row["parity"]["checked_against"] = "reference, every ray"
         out[name] = row
         del work, occ, ow
@@ -1017,6 +1024,7 @@ def main():
         lib.check(dev)
         extras["dynamic_scene_recommit"] = dynamic_leg(lib, dev, args)
         extras["hair_bezier"] = hair_leg(lib, dev, devt, stream, args)
+        extras["hair_bezier_round"] = hair_leg(lib, dev, devt, stream, args, rnd=True)
 
     # ---- parity sample + CPU baseline (rank 0, N == 1)
     cpu_baseline, parity, ref_counters = None, None, None
