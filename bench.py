@@ -329,10 +329,14 @@ def hair_leg(lib, dev, devt, stream, args, rnd=False):
            "curves": int(len(ci)), "triangles": int(len(t)), "commit_ms": commit_s * 1e3, "build_device_ms": st.build_ms, "nodes": int(st.num_nodes)}
     cores, _detail = usable_cores()
     R = load_reference() if not args.no_cpu else None
+    rsc2 = None
     if R is not None:
         rdev = R.new_device(None)
         rsc, rkeep, rcommit = build(R, rdev)
         out["reference_commit_ms"] = rcommit * 1e3
+        if rnd:
+            rdev2 = R.new_device("isa=avx2")
+            rsc2, rkeep2, _c2 = build(R, rdev2)
     for name, rays in (("camera_1080p", cam), ("incoherent", inc)):
         work = rays.clone()
         best = 1e9
@@ -373,9 +377,18 @@ def hair_leg(lib, dev, devt, stream, args, rnd=False):
             rep = compare_hits(w, got)
             row["parity"] = {k: rep[k] for k in ("n", "hits", "id_mismatch", "tie", "hit_miss_disagree", "max_rel_t", "max_abs_uv")}
             if rnd:
+                # The hit is the root of a Newton iteration (at most 5 steps from cylinder estimates): implementations part where it is
+                # ill-conditioned -- mostly on the silhouette of the tube (|cos(Ng, dir)| < 0.1 at the nearer hit), a few at the
+                # iteration limit.  The yardstick is the reference against ITSELF: its AVX2 and AVX-512 code paths (same algorithm,
+                # different reciprocal / rsqrt approximations) on the same rays.
                 nd, bad = sweep_disagreements(rin, w, got, {1})
                 row["parity"]["differing_rays"] = nd
-                row["parity"]["not_a_silhouette_graze"] = bad   # every difference must be a ray tangent to the tube (|cos(Ng, dir)| < 0.1 at the nearer hit)
+                row["parity"]["not_a_silhouette_graze"] = bad
+                if rsc2 is not None:
+                    w2 = rin.copy()
+                    api_trace_mt(R, rsc2, w2, cores)
+                    sd, sb = sweep_disagreements(rin, w, w2, {1})
+                    row["parity"]["reference_avx512_vs_its_own_avx2_path"] = {"differing_rays": sd, "not_a_silhouette_graze": sb}
             else:
                 nd, bad = unexplained_ribbon_disagreements(w, got, {1})
                 row["parity"]["differing_rays"] = nd
@@ -386,6 +399,9 @@ def hair_leg(lib, dev, devt, stream, args, rnd=False):
     if R is not None:
         R.rtcReleaseScene(rsc)
         R.rtcReleaseDevice(rdev)
+        if rsc2 is not None:
+            R.rtcReleaseScene(rsc2)
+            R.rtcReleaseDevice(rdev2)
     lib.rtcReleaseScene(sc)
     return out
 

@@ -154,20 +154,28 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
                                                    BuildInfo* __restrict__ info) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  bool ok = false, skipb = false;
+  float alo[3] = {INFINITY, INFINITY, INFINITY}, ahi[3] = {-INFINITY, -INFINITY, -INFINITY};   // API-visible box when it is not the primitive's own (own_api)
+  bool ok = false, skipb = false, own_api = false;
   if (p < ntot) {
     const int g = find_geom(offs, ngeoms, p);
     float v[9], pad[3] = {0.0f, 0.0f, 0.0f};
     if (geoms[g].is_curve == 4) {
-      // round cubic curve: accurateRoundBounds (bezier_curve.h:606-628 and twins) -- 8 points at u = i/7, each with p -+ dp/18 (the hull
-      // of the 7 cubic sub-segments), enlarged by the largest |radius| among them and by enlarge_bounds' 4 ulp; + our 2 ulp
+      // round cubic curve: one primitive per FIRST-LEVEL sub-segment of the sweep intersector (local index = curve * 7 + i, the
+      // curve between u = i/7 and (i+1)/7).  Box = hull of the sub-segment's Bezier control points p_i, p_i + dp_i/21,
+      // p_{i+1} - dp_{i+1}/21, p_{i+1} enlarged by the largest |radius| among them: the swept spheres of the sub-segment lie
+      // inside (convex hull property, radius included), and so do the bounding cylinders' hit points the iteration starts from
+      // only as start values.  The API bounds of the scene take the whole curve's accurateRoundBounds (bezier_curve.h:606-628: 8
+      // points at u = i/7, each with p -+ dp/18) + enlarge_bounds, as the reference reports them.
       CurveVtx cp[4];
       uint32_t vid;
-      load_cubic(geoms[g], p - offs[g], cp, vid, ok);
+      const uint32_t lp = p - offs[g];
+      const int seg = (int)(lp % 7u);
+      load_cubic(geoms[g], lp / 7u, cp, vid, ok);
       if (ok) {
-        float pl[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, pu[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float pl[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, pu[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // whole curve (API bounds)
+        float sl[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, su[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // this sub-segment
         const float c4[4][4] = {{cp[0].x, cp[1].x, cp[2].x, cp[3].x}, {cp[0].y, cp[1].y, cp[2].y, cp[3].y}, {cp[0].z, cp[1].z, cp[2].z, cp[3].z}, {cp[0].r, cp[1].r, cp[2].r, cp[3].r}};
-        const float scale = 1.0f / (3.0f * 6.0f);
+        const float scale = 1.0f / (3.0f * 6.0f), sub = 1.0f / (3.0f * 7.0f);
         for (int i = 0; i <= 7; ++i) {
           float cc[4], dd[4];
           curve_basis_table_entry(geoms[g].basis, (float)i / 7.0f, cc, dd);
@@ -176,21 +184,25 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
             const float pp = curve_blend(cc, 1, c4[c][0], c4[c][1], c4[c][2], c4[c][3]), dp = curve_blend(dd, 1, c4[c][0], c4[c][1], c4[c][2], c4[c][3]);
             const float pm = __fsub_rn(pp, __fmul_rn(scale, i != 0 ? dp : 0.0f)), pq = __fadd_rn(pp, __fmul_rn(scale, i != 7 ? dp : 0.0f));
             pl[c] = fminf(pl[c], fminf(pp, fminf(pm, pq))); pu[c] = fmaxf(pu[c], fmaxf(pp, fmaxf(pm, pq)));
+            if (i == seg) { const float q = __fmaf_rn(sub, dp, pp); sl[c] = fminf(sl[c], fminf(pp, q)); su[c] = fmaxf(su[c], fmaxf(pp, q)); }
+            if (i == seg + 1) { const float q = __fmaf_rn(-sub, dp, pp); sl[c] = fminf(sl[c], fminf(pp, q)); su[c] = fmaxf(su[c], fmaxf(pp, q)); }
           }
         }
-        const float rmax = fmaxf(fabsf(pl[3]), fabsf(pu[3]));
+        // the sub-segment's points come from the start-up-table formulas here and from de Casteljau / live basis evaluation in the
+        // test: a relative 1e-6 of the coordinates covers the difference
+        const float rseg = fmaxf(fabsf(sl[3]), fabsf(su[3])) * 1.000002f, rall = fmaxf(fabsf(pl[3]), fabsf(pu[3]));
         float size = 0.0f;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          lo[a] = __fsub_rd(pl[a], rmax); hi[a] = __fadd_ru(pu[a], rmax);
-          size = fmaxf(size, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+          lo[a] = __fsub_rd(sl[a], rseg); hi[a] = __fadd_ru(su[a], rseg);
+          lo[a] -= fabsf(lo[a]) * 1.2e-6f; hi[a] += fabsf(hi[a]) * 1.2e-6f;
+          alo[a] = __fsub_rd(pl[a], rall); ahi[a] = __fadd_ru(pu[a], rall);
+          size = fmaxf(size, fmaxf(fabsf(alo[a]), fabsf(ahi[a])));
         }
         const float e = 4.0f * 1.1920929e-07f * size;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          lo[a] = __fsub_rd(lo[a], e); hi[a] = __fadd_ru(hi[a], e);
-          lo[a] -= fabsf(lo[a]) * 2.4e-7f; hi[a] += fabsf(hi[a]) * 2.4e-7f;
-        }
+        for (int a = 0; a < 3; ++a) { alo[a] = __fsub_rd(alo[a], e); ahi[a] = __fadd_ru(ahi[a], e); }
+        own_api = true;
         ok &= (lo[0] > -kFltLarge) & (hi[0] < kFltLarge) & (lo[1] > -kFltLarge) & (hi[1] < kFltLarge) & (lo[2] > -kFltLarge) & (hi[2] < kFltLarge);
       }
     } else if (geoms[g].is_curve == 3) {
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
   for (int a = 0; a < 3; ++a) { c_lo[a] = ok ? lo[a] + hi[a] : INFINITY; c_hi[a] = ok ? lo[a] + hi[a] : -INFINITY; }
   float a_lo[3], a_hi[3];   // API-visible bounds: instanced triangles are represented by their instance box (host side)
 #pragma unroll
-  for (int a = 0; a < 3; ++a) { a_lo[a] = skipb ? INFINITY : lo[a]; a_hi[a] = skipb ? -INFINITY : hi[a]; }
+  for (int a = 0; a < 3; ++a) { a_lo[a] = skipb ? INFINITY : (own_api ? alo[a] : lo[a]); a_hi[a] = skipb ? -INFINITY : (own_api ? ahi[a] : hi[a]); }
   unsigned cnt = ok ? 1u : 0u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -586,7 +598,7 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
   float v[9];
   bool ok;
   if (gd.is_curve == 3 || gd.is_curve == 4) {   // record of one SEGMENT of a flat cubic curve (round: of the whole curve): a = (-, -, -, primID), b = (-, -, -, descriptor), c = (segment, -, first vertex, mask)
-    const uint32_t lp = p - offs[g], per = gd.is_curve == 4 ? 1u : gd.tess, curve = lp / per, seg = lp % per;
+    const uint32_t lp = p - offs[g], per = gd.is_curve == 4 ? 7u : gd.tess, curve = lp / per, seg = lp % per;
     const uint32_t vid = *reinterpret_cast<const uint32_t*>(gd.idx + (uint64_t)curve * gd.istride);
     float4* dst = reinterpret_cast<float4*>(&out[t]);
     dst[0] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(curve));

@@ -751,8 +751,11 @@ RT_HD int sweep_select_min(uint32_t valid, const float* v) {
   for (int i = 0; i < kSweepW; ++i) if ((valid >> i) & 1u) if (best < 0 || v[i] < v[best]) best = i;
   return best;
 }
+// `lane` >= 0 restricts the FIRST subdivision level to that one of its 7 sub-segments: the BVH holds every first-level
+// sub-segment of a round curve as its own primitive (tight boxes), and the closest hit over them is the closest hit of the curve
+// (the same converged roots; only the order in which candidates shorten the ray differs).  lane < 0: the whole curve.
 RT_HD bool round_cubic_test(float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar, const CurveVtx cpv[4], uint32_t basis,
-                            CurveHit& h) {
+                            CurveHit& h, int lane = -1) {
   const float org[3] = {ox, oy, oz}, dir[3] = {dx, dy, dz};
   // move the ray origin next to the curve (:458-462); center(): bezier_curve.h:173, bspline_curve.h:94, catmullrom_curve.h:102
   const float cin[4][3] = {{cpv[0].x, cpv[0].y, cpv[0].z}, {cpv[1].x, cpv[1].y, cpv[1].z}, {cpv[2].x, cpv[2].y, cpv[2].z}, {cpv[3].x, cpv[3].y, cpv[3].z}};
@@ -798,14 +801,15 @@ RT_HD bool round_cubic_test(float ox, float oy, float oz, float dx, float dy, fl
     first = false;
     const float dscale = mul_rn(sub_rn(u1, u0), 1.0f / (3.0f * (kSweepW - 1)));
     float P0[kSweepW][4], dP0[kSweepW][4];
-    for (int i = 0; i < kSweepW; ++i) {
+    const bool one = lane >= 0 && depth == 1;                       // first level of a per-sub-segment primitive
+    for (int i = one ? lane : 0; i < (one ? lane + 2 : kSweepW); ++i) {
       cubic_eval(cp, basis, lerp_rn(u0, u1, mul_rn((float)i, k7)), P0[i], dP0[i], nullptr);
       for (int a = 0; a < 4; ++a) dP0[i][a] = mul_rn(dP0[i][a], dscale);
     }
     uint32_t valid0 = 0, valid1 = 0, rec0 = 0, rec1 = 0;
     float tp0lo[kSweepW], tp1lo[kSweepW], tp1hi[kSweepW], uo0[kSweepW], uo1[kSweepW];
     for (int i = 0; i < kSweepW; ++i) { tp0lo[i] = tp1lo[i] = INFINITY; tp1hi[i] = -INFINITY; uo0[i] = uo1[i] = 0.0f; }
-    for (int i = 0; i < kSweepW - 1; ++i) {
+    for (int i = one ? lane : 0; i < (one ? lane + 1 : kSweepW - 1); ++i) {
       const float *A0 = P0[i], *A3 = P0[i + 1], *dA0 = dP0[i], *dA3 = dP0[i + 1];
       const float P1w = add_rn(A0[3], dA0[3]), P2w = sub_rn(A3[3], dA3[3]);
       const float e[3] = {sub_rn(A3[0], A0[0]), sub_rn(A3[1], A0[1]), sub_rn(A3[2], A0[2])};

@@ -351,7 +351,7 @@ void commit_scene(SceneImpl* s) {
     const bool hermite = is_hermite(g->type), round = is_round_cubic(g->type);
     if (hermite && !g->tangents.buf) fail(RTC_ERROR_INVALID_OPERATION, "tangent buffer not set");
     if (hermite && g->tangents.count != nverts) fail(RTC_ERROR_INVALID_OPERATION, "number of tangents must match number of vertices");   // scene_curves.cpp commit
-    const size_t segs = round ? 1 : (size_t)g->tessellationRate;   // BVH primitives per curve
+    const size_t segs = round ? 7 : (size_t)g->tessellationRate;   // BVH primitives per curve: the 7 first-level sub-segments of the sweep / the ribbon's segments
     if (ncurves * segs > 0x7FFFFFFFull || nverts > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "curve geometry too large");
     curves = true;
     const size_t vbytes = nverts ? (nverts - 1) * g->vertices.stride + 16 : 16, ibytes = (ncurves - 1) * g->indices.stride + 4;
@@ -383,7 +383,7 @@ void commit_scene(SceneImpl* s) {
     d.basis_tab = static_cast<const float*>(db);
     d.verts = static_cast<const uint8_t*>(dv); d.idx = static_cast<const uint8_t*>(di);
     d.vstride = g->vertices.stride; d.istride = g->indices.stride;
-    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)(ncurves * segs);   // flat: one BVH primitive per tessellation segment; round: per curve
+    d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)(ncurves * segs);   // flat: one BVH primitive per tessellation segment; round: per first-level sub-segment of the sweep intersector
     d.geomID = geomID; d.mask = g->mask; d.is_curve = round ? 4 : 3;
     descs.push_back(d);
   };

@@ -114,13 +114,13 @@ __device__ __forceinline__ void to_object_space(const GeomDesc& d, Ray& r) {
 // mask).  The neighbour vertices -- needed to cut away what lies inside the adjacent segments -- come from the geometry's
 // resident float4 vertex buffer (LineSegments::gather, scene_line_segments.h:270-276).
 // round cubic curve (sweep intersector): its own function, so that its arrays and register needs stay out of the other curve tests
-__device__ __noinline__ bool round_record_test(const GeomDesc& d, const Ray& r, float tfar, uint32_t vid, CurveHit& h) {
+__device__ __noinline__ bool round_record_test(const GeomDesc& d, const Ray& r, float tfar, uint32_t vid, int lane, CurveHit& h) {
   CurveVtx cp[4];
   load_cubic_cp(d, vid, cp);
-  return round_cubic_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, cp, d.basis, h);
+  return round_cubic_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, cp, d.basis, h, lane);
 }
 __device__ __noinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h) {
-  if (d.is_curve == 4) return round_record_test(d, r, tfar, c.z, h);
+  if (d.is_curve == 4) return round_record_test(d, r, tfar, c.z, (int)c.x, h);   // c.x: this record's first-level sub-segment
   if (d.is_curve == 3) {   // flat cubic curve (Bezier / B-spline / Catmull-Rom / Hermite): control points from the resident vertex buffer
     CurveVtx cp[4];
     load_cubic_cp(d, c.z, cp);

@@ -293,9 +293,11 @@ def sweep_disagreements(rays, a, b, curve_geoms, tol=1e-4, cos_max=0.1):
     differ; it is explained when the nearer of the two hits is a curve hit whose normal is perpendicular to the ray
     (|cos(Ng, dir)| < cos_max)."""
     ah, bh = a["geomID"] != 0xFFFFFFFF, b["geomID"] != 0xFFFFFFFF
-    with np.errstate(invalid="ignore"):
+    with np.errstate(invalid="ignore", divide="ignore"):
         rel = np.abs(a["tfar"] - b["tfar"]) / np.maximum(np.abs(a["tfar"]), 1e-30)
-    differ = (ah != bh) | (ah & bh & ((a["primID"] != b["primID"]) | (a["geomID"] != b["geomID"]) | (rel > tol)))
+    ulps = np.abs(a["tfar"].view(np.int32).astype(np.int64) - b["tfar"].view(np.int32).astype(np.int64))
+    # (two curves that meet at a joint and are hit at the same distance are a tie, not a difference)
+    differ = (ah != bh) | (ah & bh & ((((a["primID"] != b["primID"]) | (a["geomID"] != b["geomID"])) & (ulps > TIE_ULPS)) | (rel > tol)))
     bad = 0
     for i in np.nonzero(differ)[0]:
         cands = [x for x, h in ((a, ah[i]), (b, bh[i])) if h]
