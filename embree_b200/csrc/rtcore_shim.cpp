@@ -1345,6 +1345,8 @@ int rtcb200SetTuning(const char* key, int value) {
   else if (!strcmp(key, "c_tri")) t.c_tri = value;
   else if (!strcmp(key, "tri_batch_min")) t.tri_batch_min = value;
   else if (!strcmp(key, "tri_wait_max")) t.tri_wait_max = value;
+  else if (!strcmp(key, "curve_batch_min")) t.curve_batch_min = value;
+  else if (!strcmp(key, "curve_wait_max")) t.curve_wait_max = value;
   else if (!strcmp(key, "blocks_per_sm")) t.blocks_per_sm = value;
   else if (!strcmp(key, "use_tma")) t.use_tma = value;
   else if (!strcmp(key, "tri_spread")) t.tri_spread = value != 0;

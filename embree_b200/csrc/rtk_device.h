@@ -132,6 +132,9 @@ struct Tuning {
   int c_node = 100, c_tri = 50;  // DP cost of a BVH8 node visit / a triangle test, in 1/100
   int tri_batch_min = 8;     // triangle step when >= this many lanes have triangles pending (or no lane has a node, or after tri_wait_max deferrals)
   int tri_wait_max = 4;
+  // the same two keys for scenes with curve records: a curve test costs 10-100x a triangle test, so it pays to wait until more
+  // lanes have one pending (measured on the fur ball of bench.py: flat +13 / +20 %, round +43 / +56 % over 8 / 4; scripts/hair_tune.py)
+  int curve_batch_min = 24, curve_wait_max = 16;
   int blocks_per_sm = 8;
   int use_tma = 1;
   int refill_min = 4;

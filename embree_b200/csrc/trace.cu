@@ -742,8 +742,8 @@ static int launch_k(TraceParams p, cudaStream_t st) {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  p.tri_batch_min = g_tuning.tri_batch_min;
-  p.tri_wait_max = g_tuning.tri_wait_max;
+  p.tri_batch_min = p.curves ? g_tuning.curve_batch_min : g_tuning.tri_batch_min;
+  p.tri_wait_max = p.curves ? g_tuning.curve_wait_max : g_tuning.tri_wait_max;
   p.refill_min = g_tuning.refill_min;
   // persistent grid: a multiple of the SM count, capped by the work available
   const unsigned long long need = (p.n + TRACE_THREADS - 1) / TRACE_THREADS;

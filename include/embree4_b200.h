@@ -378,9 +378,10 @@ RTCB200_API void rtcb200ResetSceneStatCounters(RTCScene scene);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 RTCB200_API unsigned long long rtcb200GetLaunchCount(void);
 /* experiment knobs (process-wide): kernels "collapse_policy", "c_node", "c_tri", "sah_small", "tri_batch_min",
- * "tri_wait_max", "refill_min", "blocks_per_sm", "use_tma"; host-pointer pipeline "host_chunk_log2", "host_streams";
- * hit gather "gather_mode" (0 one store per record, 1 complete 32-ray blocks as 1 KB stores); EXPERIMENTAL: "tri_spread"
- * (warp-wide triangle redistribution).  The defaults are the shipped, measured configuration.
+ * "tri_wait_max" ("curve_batch_min", "curve_wait_max": the same two for scenes with curves), "refill_min", "blocks_per_sm",
+ * "use_tma"; host-pointer pipeline "host_chunk_log2", "host_streams"; hit gather "gather_mode" (0 one store per record,
+ * 1 complete 32-ray blocks as 1 KB stores); "tri_spread" (warp-wide triangle redistribution, on by default).
+ * The defaults are the shipped, measured configuration.
  * Returns 0, or -1 for an unknown key or an out-of-range value. */
 RTCB200_API int rtcb200SetTuning(const char* key, int value);
 /* device time (ms) of the most recent batched Device trace launch, measured with events on its stream; -1 if none */
