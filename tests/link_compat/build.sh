@@ -35,3 +35,20 @@ if [ -f ../../oracle/_ref/libembree4.so.4 ] && [ ! -f ../golden/triangle_geometr
   _bin/ref_triangle_geometry ../golden/triangle_geometry_160x120.raw 160 120 4
   rm -f _bin/ref_triangle_geometry
 fi
+
+# BASELINE configs[3]a: the reference's tutorial device code tutorials/hair_geometry/hair_geometry_device.cpp (hair sets converted with
+# rtcSetGeometryTessellationRate / rtcSetGeometryEnableFilterFunctionFromArguments, per pixel a path of rtcTraversableIntersect1 and
+# rtcTraversableOccluded1 with its transparency-accumulating occlusion filter), compiled untouched with OUR host driver hair_host.cpp
+# (procedural fur ball: round linear / flat Bezier / round Bezier hair), linked (a) against libembree4_b200.so ->
+# _bin/embree_hair_geometry and (b) against the unmodified reference -> golden frames tests/golden/hair_geometry_<type>_96x72.raw.
+if [ ! -x _bin/embree_hair_geometry ] || [ hair_host.cpp -nt _bin/embree_hair_geometry ]; then
+  g++ -O1 -std=c++17 -w $INC -o _bin/embree_hair_geometry hair_host.cpp "$REF/tutorials/hair_geometry/hair_geometry_device.cpp" $SYS \
+      -L_bin -lembree4 -lpthread -Wl,-rpath,'$ORIGIN/../../../embree_b200/csrc'
+  echo built tests/link_compat/_bin/embree_hair_geometry
+fi
+if [ -f ../../oracle/_ref/libembree4.so.4 ] && [ ! -f ../golden/hair_geometry_2_96x72.raw ]; then
+  g++ -O1 -std=c++17 -w $INC -o _bin/ref_hair_geometry hair_host.cpp "$REF/tutorials/hair_geometry/hair_geometry_device.cpp" $SYS \
+      -L../../oracle/_ref -l:libembree4.so.4 -lpthread -Wl,-rpath,'$ORIGIN/../../../oracle/_ref'
+  for t in 0 1 2; do _bin/ref_hair_geometry ../golden/hair_geometry_${t}_96x72.raw 96 72 4 $t 3000; done
+  rm -f _bin/ref_hair_geometry
+fi
