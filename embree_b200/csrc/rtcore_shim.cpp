@@ -1015,6 +1015,67 @@ void rtcReleaseGeometry(RTCGeometry g) { GEOM_BEGIN(g) G(g)->release(); GEOM_END
 void rtcCommitGeometry(RTCGeometry g) { GEOM_BEGIN(g) ++G(g)->modCounter; G(g)->state = GeomState::COMMITTED; GEOM_END }  // geometry.cpp:103-107
 void rtcEnableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (!G(g)->enabled) { G(g)->enabled = true; ++G(g)->modCounter; } GEOM_END }
 void rtcDisableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (G(g)->enabled) { G(g)->enabled = false; ++G(g)->modCounter; } GEOM_END }
+// ---- rtcInterpolate / rtcInterpolateN (scene_triangle_mesh.h:49-105, scene_quad_mesh.h interpolate_impl, geometry.cpp:163-235): host arithmetic
+// on the caller's vertex / attribute buffers; P = w p0 + u p1 + v p2 with the reference's madd order, first derivatives the edge
+// vectors, second derivatives zero; a quad interpolates in the half (v0,v1,v3) or, for u + v > 1, (v2,v3,v1) with (1-u, 1-v).
+static void interpolate1(GeometryImpl* g, const RTCInterpolateArguments* a) {
+  const bool quad = g->type == RTC_GEOMETRY_TYPE_QUAD;
+  if (g->type != RTC_GEOMETRY_TYPE_TRIANGLE && !quad) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
+  const BufferView* bv = nullptr;
+  if (a->bufferType == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) { if (a->bufferSlot < g->attribs.size()) bv = &g->attribs[a->bufferSlot]; }
+  else if (a->bufferType == RTC_BUFFER_TYPE_VERTEX && a->bufferSlot == 0) bv = &g->vertices;
+  if (!bv || !bv->buf || !g->indices.buf) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer");
+  if (a->primID >= g->indices.count) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid primitive ID");
+  const unsigned* idx = reinterpret_cast<const unsigned*>(g->indices.data() + (size_t)a->primID * g->indices.stride);
+  const char* src = bv->data();
+  const size_t st = bv->stride;
+  float u = a->u, v = a->v;
+  unsigned i0 = idx[0], i1 = idx[1], i2 = idx[2];
+  bool left = true;
+  if (quad) {
+    left = u + v <= 1.0f;
+    i0 = left ? idx[0] : idx[2]; i1 = left ? idx[1] : idx[3]; i2 = left ? idx[3] : idx[1];
+    if (!left) { u = 1.0f - u; v = 1.0f - v; }
+  }
+  const float w = 1.0f - u - v;
+  for (unsigned k = 0; k < a->valueCount; ++k) {
+    const float p0 = reinterpret_cast<const float*>(src + (size_t)i0 * st)[k], p1 = reinterpret_cast<const float*>(src + (size_t)i1 * st)[k],
+                p2 = reinterpret_cast<const float*>(src + (size_t)i2 * st)[k];
+    if (a->P) a->P[k] = fmaf(w, p0, fmaf(u, p1, v * p2));
+    if (a->dPdu) { a->dPdu[k] = left ? p1 - p0 : p0 - p1; a->dPdv[k] = left ? p2 - p0 : p0 - p2; }
+    if (a->ddPdudu) { a->ddPdudu[k] = 0.0f; a->ddPdvdv[k] = 0.0f; a->ddPdudv[k] = 0.0f; }
+  }
+}
+void rtcInterpolate(const RTCInterpolateArguments* a) {
+  GeometryImpl* g_ = a ? G(a->geometry) : nullptr;
+  DeviceImpl* dev_ = g_ ? g_->dev : nullptr;
+  API_BEGIN VERIFY_HANDLE(a); VERIFY_HANDLE(a->geometry); interpolate1(g_, a); API_END(dev_)
+}
+void rtcInterpolateN(const RTCInterpolateNArguments* a) {
+  GeometryImpl* g_ = a ? G(a->geometry) : nullptr;
+  DeviceImpl* dev_ = g_ ? g_->dev : nullptr;
+  API_BEGIN
+  VERIFY_HANDLE(a); VERIFY_HANDLE(a->geometry);
+  if (a->valueCount > 256) fail(RTC_ERROR_INVALID_OPERATION, "maximally 256 floating point values can be interpolated per vertex");
+  const int* valid = static_cast<const int*>(a->valid);
+  float P[256], dPdu[256], dPdv[256], d2uu[256], d2vv[256], d2uv[256];
+  for (unsigned i = 0; i < a->N; ++i) {
+    if (valid && !valid[i]) continue;
+    RTCInterpolateArguments ia;
+    ia.geometry = a->geometry; ia.primID = a->primIDs[i]; ia.u = a->u[i]; ia.v = a->v[i]; ia.bufferType = a->bufferType; ia.bufferSlot = a->bufferSlot;
+    ia.P = a->P ? P : nullptr; ia.dPdu = a->dPdu ? dPdu : nullptr; ia.dPdv = a->dPdu ? dPdv : nullptr;
+    ia.ddPdudu = a->ddPdudu ? d2uu : nullptr; ia.ddPdvdv = a->ddPdudu ? d2vv : nullptr; ia.ddPdudv = a->ddPdudu ? d2uv : nullptr;
+    ia.valueCount = a->valueCount;
+    interpolate1(g_, &ia);
+    for (unsigned j = 0; j < a->valueCount; ++j) {   // SoA outputs: value j of lane i at [j * N + i]
+      if (a->P) a->P[j * a->N + i] = P[j];
+      if (a->dPdu) { a->dPdu[j * a->N + i] = dPdu[j]; a->dPdv[j * a->N + i] = dPdv[j]; }
+      if (a->ddPdudu) { a->ddPdudu[j * a->N + i] = d2uu[j]; a->ddPdvdv[j * a->N + i] = d2vv[j]; a->ddPdudv[j * a->N + i] = d2uv[j]; }
+    }
+  }
+  API_END(dev_)
+}
+
 // scene_curves.cpp:244-249, scene_line_segments.cpp:182-184 (linear curves store the value and never use it: tutorials/hair_geometry
 // sets it on every hair set); every other geometry type: "operation not supported for this geometry" (geometry.h:382)
 void rtcSetGeometryTessellationRate(RTCGeometry g, float n) {
@@ -1471,8 +1532,6 @@ RTCB200_UNSUPPORTED(rtcGetGeometryFirstHalfEdge)
 RTCB200_UNSUPPORTED(rtcGetGeometryNextHalfEdge)
 RTCB200_UNSUPPORTED(rtcGetGeometryOppositeHalfEdge)
 RTCB200_UNSUPPORTED(rtcGetGeometryPreviousHalfEdge)
-RTCB200_UNSUPPORTED(rtcInterpolate)
-RTCB200_UNSUPPORTED(rtcInterpolateN)
 RTCB200_UNSUPPORTED(rtcInvokeIntersectFilterFromGeometry)
 RTCB200_UNSUPPORTED(rtcInvokeOccludedFilterFromGeometry)
 RTCB200_UNSUPPORTED(rtcMakeStaticBVH)

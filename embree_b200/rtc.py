@@ -166,6 +166,13 @@ def filter_lane(args, lane):
     return out
 
 
+class InterpolateArguments(C.Structure):
+    """RTCInterpolateArguments (rtcore_geometry.h:284-299)."""
+    _fields_ = [("geometry", C.c_void_p), ("primID", C.c_uint), ("u", C.c_float), ("v", C.c_float), ("bufferType", C.c_int), ("bufferSlot", C.c_uint),
+                ("P", C.c_void_p), ("dPdu", C.c_void_p), ("dPdv", C.c_void_p), ("ddPdudu", C.c_void_p), ("ddPdvdv", C.c_void_p), ("ddPdudv", C.c_void_p),
+                ("valueCount", C.c_uint)]
+
+
 class RTCBounds(C.Structure):
     _fields_ = [(n, C.c_float) for n in
                 ("lower_x", "lower_y", "lower_z", "align0", "upper_x", "upper_y", "upper_z", "align1")]
@@ -215,6 +222,7 @@ class RTCLib:
         "rtcGetGeometryBufferData": (C.c_void_p, [C.c_void_p, C.c_int, C.c_uint]),
         "rtcUpdateGeometryBuffer": (None, [C.c_void_p, C.c_int, C.c_uint]),
         "rtcSetGeometryTessellationRate": (None, [C.c_void_p, C.c_float]),
+        "rtcInterpolate": (None, [C.c_void_p]),
         "rtcSetGeometryUserData": (None, [C.c_void_p, C.c_void_p]),
         "rtcGetGeometryUserData": (C.c_void_p, [C.c_void_p]),
         "rtcSetGeometryIntersectFilterFunction": (None, [C.c_void_p, C.c_void_p]),

@@ -402,6 +402,20 @@ RTCB200_API void rtcSetNewGeometryBufferHostDevice(RTCGeometry geometry, enum RT
 RTCB200_API void* rtcGetGeometryUserDataFromTraversable(RTCTraversable traversable, unsigned int geomID);
 RTCB200_API void rtcSetGeometryTimeRange(RTCGeometry geometry, float startTime, float endTime);
 RTCB200_API void rtcSetGeometryMaxRadiusScale(RTCGeometry geometry, float maxRadiusScale);
+/* Vertex-data interpolation (rtcore_geometry.h:284-387; scene_triangle_mesh.h:49-105, scene_quad_mesh.h, geometry.cpp:163-235): host-side
+ * arithmetic on the geometry's vertex / vertex-attribute buffers at (primID, u, v) for triangle and quad meshes -- what the tutorials'
+ * shading code calls after a hit (rtcInterpolate0/1/2 are inline wrappers in the reference header).  Other geometry types:
+ * RTC_ERROR_INVALID_OPERATION. */
+struct RTCInterpolateArguments {
+  RTCGeometry geometry; unsigned int primID; float u, v; enum RTCBufferType bufferType; unsigned int bufferSlot;
+  float *P, *dPdu, *dPdv, *ddPdudu, *ddPdvdv, *ddPdudv; unsigned int valueCount;
+};
+struct RTCInterpolateNArguments {
+  RTCGeometry geometry; const void* valid; const unsigned int* primIDs; const float *u, *v; unsigned int N;
+  enum RTCBufferType bufferType; unsigned int bufferSlot; float *P, *dPdu, *dPdv, *ddPdudu, *ddPdvdv, *ddPdudv; unsigned int valueCount;
+};
+RTCB200_API void rtcInterpolate(const struct RTCInterpolateArguments* args);
+RTCB200_API void rtcInterpolateN(const struct RTCInterpolateNArguments* args);
 #define RTCB200_DECLARE_UNSUPPORTED(name) RTCB200_API void* name(void);
 RTCB200_DECLARE_UNSUPPORTED(rtcBuildBVH)
 RTCB200_DECLARE_UNSUPPORTED(rtcCollide)
@@ -426,8 +440,6 @@ RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryFirstHalfEdge)
 RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryNextHalfEdge)
 RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryOppositeHalfEdge)
 RTCB200_DECLARE_UNSUPPORTED(rtcGetGeometryPreviousHalfEdge)
-RTCB200_DECLARE_UNSUPPORTED(rtcInterpolate)
-RTCB200_DECLARE_UNSUPPORTED(rtcInterpolateN)
 RTCB200_DECLARE_UNSUPPORTED(rtcInvokeIntersectFilterFromGeometry)
 RTCB200_DECLARE_UNSUPPORTED(rtcInvokeOccludedFilterFromGeometry)
 RTCB200_DECLARE_UNSUPPORTED(rtcMakeStaticBVH)

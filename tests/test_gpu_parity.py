@@ -750,6 +750,43 @@ def test_cubic_curve_api_errors(b200):
     lib.rtcReleaseScene(sc)
 
 
+def test_interpolate_matches_the_reference(b200):
+    """rtcInterpolate on triangle and quad meshes (scene_triangle_mesh.h:49-105, scene_quad_mesh.h): P, dPdu, dPdv of the vertex
+    buffer at (primID, u, v) -- what shading code calls with the u, v of a hit -- bit-equal to the reference's when it is present,
+    and equal to the hit point org + t dir of a traced ray."""
+    from embree_b200.rtc import InterpolateArguments
+    lib, dev = b200
+    meshes, rin, want_i, _o, _b = load_golden("quads")
+    sc, keep = build_scene(lib, dev, meshes)
+    got = lib.intersect(sc, rin.copy(), "1M")
+    ref = load_reference()
+    rsc = rdev = None
+    if ref is not None:
+        rdev = ref.new_device(None)
+        rsc, rkeep = build_scene(ref, rdev, meshes)
+
+    def interp(L, scn, gid, prim, u, v):
+        P, du, dv = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+        a = InterpolateArguments(L.rtcGetGeometry(scn, gid), prim, u, v, RTC_BUFFER_TYPE_VERTEX, 0, C.cast(P, C.c_void_p), C.cast(du, C.c_void_p),
+                                 C.cast(dv, C.c_void_p), None, None, None, 3)
+        L.rtcInterpolate(C.byref(a))
+        return np.array([list(P), list(du), list(dv)], np.float32)
+    hits = np.nonzero(got["geomID"] != 0xFFFFFFFF)[0][:400]
+    assert len(hits) > 200 and len(set(got["geomID"][hits])) >= 2          # quad meshes and the triangle mesh
+    for i in hits:
+        r = got[i]
+        mine = interp(lib, sc, int(r["geomID"]), int(r["primID"]), float(r["u"]), float(r["v"]))
+        hitp = np.array([r["org_x"] + r["tfar"] * r["dir_x"], r["org_y"] + r["tfar"] * r["dir_y"], r["org_z"] + r["tfar"] * r["dir_z"]], np.float64)
+        assert np.abs(mine[0] - hitp).max() <= 2e-5 * max(1.0, np.abs(hitp).max()), (i, mine[0], hitp)
+        if rsc is not None:
+            assert (interp(ref, rsc, int(r["geomID"]), int(r["primID"]), float(r["u"]), float(r["v"])).view(np.uint32) == mine.view(np.uint32)).all(), i
+    lib.check(dev)
+    if ref is not None:
+        ref.rtcReleaseScene(rsc)
+        ref.rtcReleaseDevice(rdev)
+    lib.rtcReleaseScene(sc)
+
+
 def test_update_and_recommit(b200):
     """UpdateTest (verify.cpp:1835) / dynamic_scene: move the vertices, rtcUpdateGeometryBuffer, re-commit."""
     lib, dev = b200
