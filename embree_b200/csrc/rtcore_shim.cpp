@@ -1016,7 +1016,7 @@ void rtcCommitGeometry(RTCGeometry g) { GEOM_BEGIN(g) ++G(g)->modCounter; G(g)->
 void rtcEnableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (!G(g)->enabled) { G(g)->enabled = true; ++G(g)->modCounter; } GEOM_END }
 void rtcDisableGeometry(RTCGeometry g) { GEOM_BEGIN(g) if (G(g)->enabled) { G(g)->enabled = false; ++G(g)->modCounter; } GEOM_END }
 // ---- rtcInterpolate / rtcInterpolateN (scene_triangle_mesh.h:49-105, scene_quad_mesh.h interpolate_impl, geometry.cpp:163-235): host arithmetic
-// on the caller's vertex / attribute buffers; P = w p0 + u p1 + v p2 with the reference's madd order, first derivatives the edge
+// on the caller's vertex / attribute buffers; P = w p0 + (u p1 + v p2) in the reference's (unfused) order, first derivatives the edge
 // vectors, second derivatives zero; a quad interpolates in the half (v0,v1,v3) or, for u + v > 1, (v2,v3,v1) with (1-u, 1-v).
 static void interpolate1(GeometryImpl* g, const RTCInterpolateArguments* a) {
   const bool quad = g->type == RTC_GEOMETRY_TYPE_QUAD;
@@ -1041,7 +1041,11 @@ static void interpolate1(GeometryImpl* g, const RTCInterpolateArguments* a) {
   for (unsigned k = 0; k < a->valueCount; ++k) {
     const float p0 = reinterpret_cast<const float*>(src + (size_t)i0 * st)[k], p1 = reinterpret_cast<const float*>(src + (size_t)i1 * st)[k],
                 p2 = reinterpret_cast<const float*>(src + (size_t)i2 * st)[k];
-    if (a->P) a->P[k] = fmaf(w, p0, fmaf(u, p1, v * p2));
+    if (a->P) {   // madd(w, p0, madd(u, p1, v * p2)) of the mesh classes' highest ISA, AVX without FMA (SELECT_SYMBOL_DEFAULT_AVX): unfused
+      volatile float m2 = v * p2, m1 = u * p1, m0 = w * p0;
+      volatile float s12 = m1 + m2;
+      a->P[k] = m0 + s12;
+    }
     if (a->dPdu) { a->dPdu[k] = left ? p1 - p0 : p0 - p1; a->dPdv[k] = left ? p2 - p0 : p0 - p2; }
     if (a->ddPdudu) { a->ddPdudu[k] = 0.0f; a->ddPdvdv[k] = 0.0f; a->ddPdudv[k] = 0.0f; }
   }
