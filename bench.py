@@ -286,11 +286,75 @@ def dynamic_leg(lib, dev, args):
                 if who == "b200":
                     st = L.scene_stats(sc)
                     row[who]["device_ms"] = st.build_ms
-                    row[who]["path"] = ["lbvh build", "sah build", "refit"][st.builder]
+                    row[who]["path"] = ["lbvh build", "sah build", "refit", "two-level"][st.builder]
                 L.rtcReleaseScene(sc)
             out.append(row)
     if R is not None:
         R.rtcReleaseDevice(rdev)
+    return out
+
+
+def two_level_leg(lib, dev, args):
+    """configs[3]b, the tutorial's case proper (tutorials/dynamic_scene: many meshes, a few of them move every frame): one static terrain of
+    4 M triangles + 200 spheres of 5 000 triangles each in an RTC_SCENE_FLAG_DYNAMIC scene; per frame 10 spheres move and the scene is
+    committed.  Wall time of rtcCommitGeometry x 10 + rtcCommitScene: the two-level path (one kept BVH per mesh, only the moved meshes are
+    uploaded and rebuilt), the same library forced to rebuild one BVH over everything (RTCB200_NO_TWOLEVEL), and the reference's
+    two-level builder (scene build quality LOW, as the tutorial sets it)."""
+    from tests.parity import load_reference
+    tv, tt = scenes.terrain(1414, seed=3)
+    rng = np.random.RandomState(1)
+    sv, st_ = scenes.triangle_sphere(36)
+    balls = []
+    for i in range(200):
+        c = np.array([rng.uniform(-0.9, 0.9), rng.uniform(0.2, 0.6), rng.uniform(-0.9, 0.9)], np.float32)
+        balls.append((sv * np.float32(0.03) + c).astype(np.float32))
+    R = load_reference() if not args.no_cpu else None
+    out = {"workload": f"terrain {len(tt)} triangles (static) + 200 spheres x {len(st_)} triangles, 10 spheres move per frame, RTC_SCENE_FLAG_DYNAMIC, scene quality LOW",
+           "triangles": int(len(tt) + 200 * len(st_))}
+    runs = [("b200_two_level", lib, dev, None), ("b200_single_bvh_rebuild", lib, dev, "1")]
+    if R is not None:
+        runs.append(("reference", R, R.new_device(None), None))
+    for name, L, d, env in runs:
+        if env:
+            os.environ["RTCB200_NO_TWOLEVEL"] = env
+        sc = L.rtcNewScene(d)
+        L.rtcSetSceneFlags(sc, 1)
+        L.rtcSetSceneBuildQuality(sc, 0)
+        keep = [L.add_triangle_mesh(d, sc, tv, tt, mask=0xFFFFFFFF, geom_id=0)[1]]
+        for i, bv in enumerate(balls):
+            keep.append(L.add_triangle_mesh(d, sc, bv, st_, mask=0xFFFFFFFF, geom_id=1 + i)[1])
+        t0 = time.perf_counter()
+        L.rtcCommitScene(sc)
+        first = time.perf_counter() - t0
+        L.check(d)
+        ts = []
+        for it in range(8):
+            moved = [1 + (it * 10 + k) % 200 for k in range(10)]
+            for m in moved:
+                keep[m][0][: sv.size] += np.float32(0.001)
+                g = L.rtcGetGeometry(sc, m)
+                L.rtcUpdateGeometryBuffer(g, 1, 0)
+            t0 = time.perf_counter()
+            for m in moved:
+                L.rtcCommitGeometry(L.rtcGetGeometry(sc, m))
+            L.rtcCommitScene(sc)
+            dt = time.perf_counter() - t0
+            if it >= 2:
+                ts.append(dt)
+        L.check(d)
+        row = {"first_commit_ms": first * 1e3, "recommit_ms": float(np.mean(ts)) * 1e3}
+        if L is lib:
+            row["path"] = ["lbvh build", "sah build", "refit", "two-level"][L.scene_stats(sc).builder]
+            rays = scenes.as_numpy_rayhits(scenes.primary_rays(480, 270, eye=(0.0, 0.9, -0.2), look=(0.0, -1.0, 0.25)))
+            hit = L.intersect(sc, rays, "1M")
+            row["camera_hit_fraction"] = float((hit["geomID"] != 0xFFFFFFFF).mean())
+            row["camera_hit_checksum"] = int(hit["primID"][hit["geomID"] != 0xFFFFFFFF].astype(np.uint64).sum())
+        L.rtcReleaseScene(sc)
+        if env:
+            del os.environ["RTCB200_NO_TWOLEVEL"]
+        out[name] = row
+    if R is not None:
+        R.rtcReleaseDevice(runs[-1][2])
     return out
 
 
@@ -1039,6 +1103,7 @@ def main():
         del T, Tw, cam, Rr, work
         lib.check(dev)
         extras["dynamic_scene_recommit"] = dynamic_leg(lib, dev, args)
+        extras["dynamic_scene_two_level"] = two_level_leg(lib, dev, args)
         extras["hair_bezier"] = hair_leg(lib, dev, devt, stream, args)
         extras["hair_bezier_round"] = hair_leg(lib, dev, devt, stream, args, rnd=True)
 

@@ -927,4 +927,145 @@ int refit_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, cudaStream_t st,
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// two-level scenes: relocation of a sub-BVH into the scene's arrays + host-built top level (see rtk_device.h)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relocate_nodes(const Node8* __restrict__ src, uint32_t n, Node8* __restrict__ dst, uint32_t node_off, uint32_t tri_off) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Node8 nd = src[i];
+  nd.w[4] += node_off;     // child_base (unused when the node has no internal child)
+  nd.w[5] += tri_off;      // tri_base   (unused when it has no leaf slot)
+  dst[i] = nd;
+}
+
+namespace {
+struct TopItem { float lo[3], hi[3]; int sub; };
+// emits the top-level node for items[0..n) at out[q]; n >= 2.  Groups of <= 8 items become one node whose children are the items' root
+// copies; larger sets are cut into <= 8 groups by repeated median splits of the largest group along the longest axis of its centres.
+void top_emit(std::vector<Node8>& out, uint32_t q, std::vector<TopItem> items, const std::vector<Node8>& roots) {
+  std::vector<std::vector<TopItem>> groups;
+  if (items.size() <= 8) for (auto& it : items) groups.push_back({it});
+  else {
+    groups.push_back(std::move(items));
+    while (groups.size() < 8) {
+      size_t big = 0;
+      for (size_t g = 1; g < groups.size(); ++g) if (groups[g].size() > groups[big].size()) big = g;
+      if (groups[big].size() < 2) break;
+      std::vector<TopItem> src = std::move(groups[big]);
+      float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+      for (auto& it : src) for (int a = 0; a < 3; ++a) { const float c = it.lo[a] + it.hi[a]; clo[a] = fminf(clo[a], c); chi[a] = fmaxf(chi[a], c); }
+      int ax = 0;
+      for (int a = 1; a < 3; ++a) if (chi[a] - clo[a] > chi[ax] - clo[ax]) ax = a;
+      const size_t mid = src.size() / 2;
+      std::nth_element(src.begin(), src.begin() + mid, src.end(), [ax](const TopItem& x, const TopItem& y) { return x.lo[ax] + x.hi[ax] < y.lo[ax] + y.hi[ax]; });
+      groups[big] = std::vector<TopItem>(src.begin(), src.begin() + mid);
+      groups.push_back(std::vector<TopItem>(src.begin() + mid, src.end()));
+    }
+  }
+  const int n = (int)groups.size();
+  ChildBox cb[8];
+  float plo[3] = {INFINITY, INFINITY, INFINITY}, phi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int c = 0; c < n; ++c) {
+    for (int a = 0; a < 3; ++a) { cb[c].lo[a] = INFINITY; cb[c].hi[a] = -INFINITY; }
+    for (auto& it : groups[c]) for (int a = 0; a < 3; ++a) { cb[c].lo[a] = fminf(cb[c].lo[a], it.lo[a]); cb[c].hi[a] = fmaxf(cb[c].hi[a], it.hi[a]); }
+    for (int a = 0; a < 3; ++a) { plo[a] = fminf(plo[a], cb[c].lo[a]); phi[a] = fmaxf(phi[a], cb[c].hi[a]); }
+  }
+  uint8_t slot_of[8];
+  assign_slots(cb, n, plo, phi, slot_of);
+  int child_at[8];
+  for (int s = 0; s < 8; ++s) child_at[s] = -1;
+  for (int c = 0; c < n; ++c) child_at[slot_of[c]] = c;
+  const uint32_t child_base = (uint32_t)out.size();
+  out.resize(out.size() + n);                       // every child is an internal node: n consecutive nodes in slot order
+  Node8 nd;
+  for (int k = 0; k < 24; ++k) nd.w[k] = 0;
+  encode_node_boxes(nd, plo, phi, cb, slot_of, n);
+  uint32_t imask = 0;
+  for (int s = 0; s < 8; ++s) if (child_at[s] >= 0) imask |= 1u << s;
+  nd.w[3] = (nd.w[3] & 0x00FFFFFFu) | (imask << 24);
+  nd.w[4] = child_base; nd.w[5] = 0;
+  out[q] = nd;
+  uint32_t rank = 0;
+  for (int s = 0; s < 8; ++s) {
+    const int c = child_at[s];
+    if (c < 0) continue;
+    if (groups[c].size() == 1) out[child_base + rank] = roots[groups[c][0].sub];
+    else top_emit(out, child_base + rank, std::move(groups[c]), roots);
+    ++rank;
+  }
+}
+}  // namespace
+
+int assemble_scene(SceneGPU& s, SceneGPU* const* subs, int nsubs, const uint8_t* dirty, cudaStream_t st, char* errmsg) {
+  errmsg[0] = 0;
+  ensure_pool(s.device);
+  if (!s.d_stat) { CK(cudaMalloc(&s.d_stat, 3 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s.d_stat, 0, 24, st)); }
+  struct Events { cudaEvent_t a = nullptr, b = nullptr; ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evs;
+  CK(cudaEventCreate(&evs.a)); CK(cudaEventCreate(&evs.b));
+  CK(cudaEventRecord(evs.a, st));
+  // same layout as last time?  (same number of subs, each with unchanged node / record counts)
+  bool same = s.nodes && s.tris && (int)s.sub_nodes.size() == nsubs;
+  for (int i = 0; same && i < nsubs; ++i)
+    same = s.sub_nodes[i] == (subs[i]->root_valid ? subs[i]->num_nodes : 0u) && s.sub_tris[i] == (subs[i]->root_valid ? subs[i]->num_tris : 0u);
+  if (!same) {
+    if (s.nodes) { cudaFreeAsync(s.nodes, st); s.nodes = nullptr; }
+    if (s.tris) { cudaFreeAsync(s.tris, st); s.tris = nullptr; }
+    s.sub_node_off.assign(nsubs, 0); s.sub_tri_off.assign(nsubs, 0); s.sub_nodes.assign(nsubs, 0); s.sub_tris.assign(nsubs, 0);
+    s.sub_root.assign(nsubs, Node8{});
+    s.top_cap = (uint32_t)(2 * nsubs + 8);
+    uint64_t nn = s.top_cap, nt = 0;
+    for (int i = 0; i < nsubs; ++i) {
+      s.sub_node_off[i] = (uint32_t)nn; s.sub_tri_off[i] = (uint32_t)nt;
+      if (!subs[i]->root_valid) continue;
+      s.sub_nodes[i] = subs[i]->num_nodes; s.sub_tris[i] = subs[i]->num_tris;
+      nn += subs[i]->num_nodes; nt += subs[i]->num_tris;
+    }
+    if (nn >= 0x7FFFFFFFull || nt >= 0x7FFFFFFFull) { snprintf(errmsg, 256, "two-level scene too large"); return -1; }
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&s.nodes), std::max<uint64_t>(nn, 1) * sizeof(Node8), st));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&s.tris), std::max<uint64_t>(nt, 1) * sizeof(TriRec), st));
+    s.num_nodes = (uint32_t)nn; s.num_tris = (uint32_t)nt;
+  }
+  for (int i = 0; i < nsubs; ++i) {
+    const SceneGPU& b = *subs[i];
+    if (!b.root_valid || (same && !dirty[i])) continue;
+    relocate_nodes<<<(b.num_nodes + 255) / 256, 256, 0, st>>>(b.nodes, b.num_nodes, s.nodes + s.sub_node_off[i], s.sub_node_off[i], s.sub_tri_off[i]);
+    count_launch();
+    CK(cudaMemcpyAsync(s.tris + s.sub_tri_off[i], b.tris, (size_t)b.num_tris * sizeof(TriRec), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(&s.sub_root[i], s.nodes + s.sub_node_off[i], sizeof(Node8), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));   // the relocated root nodes are on the host now
+  CK(cudaGetLastError());
+  // top level on the host: a few hundred meshes at most cost microseconds here
+  std::vector<TopItem> items;
+  for (int a = 0; a < 3; ++a) { s.bounds[a] = s.api_bounds[a] = INFINITY; s.bounds[3 + a] = s.api_bounds[3 + a] = -INFINITY; }
+  for (int i = 0; i < nsubs; ++i) {
+    if (!subs[i]->root_valid) continue;
+    TopItem it;
+    for (int a = 0; a < 3; ++a) {
+      it.lo[a] = subs[i]->bounds[a]; it.hi[a] = subs[i]->bounds[3 + a];
+      s.bounds[a] = s.api_bounds[a] = fminf(s.bounds[a], it.lo[a]); s.bounds[3 + a] = s.api_bounds[3 + a] = fmaxf(s.bounds[3 + a], it.hi[a]);
+    }
+    it.sub = i;
+    items.push_back(it);
+  }
+  s.root_valid = items.empty() ? 0u : 1u;
+  s.levels.clear();
+  if (!items.empty()) {
+    std::vector<Node8> top(1);
+    if (items.size() == 1) top[0] = s.sub_root[items[0].sub];
+    else top_emit(top, 0, items, s.sub_root);
+    if (top.size() > s.top_cap) { snprintf(errmsg, 256, "internal: top level needs %zu of %u nodes", top.size(), s.top_cap); return -1; }
+    CK(cudaMemcpyAsync(s.nodes, top.data(), top.size() * sizeof(Node8), cudaMemcpyHostToDevice, st));
+    s.levels = {0u, s.num_nodes};
+  }
+  CK(cudaEventRecord(evs.b, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, evs.a, evs.b);
+  s.build_ms = ms; s.builder = 3; s.max_depth = 0; s.sah_cost = 0;
+  return 0;
+}
+
 }  // namespace rtk

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <stdexcept>
@@ -202,6 +203,14 @@ struct SceneImpl : RefCounted {
   float apiBounds[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};  // what rtcGetSceneBounds reports
   std::vector<void*> deviceBuffers;  // uploaded vertex/index bytes of the current commit
   std::vector<void*> residentBuffers;  // curve vertex buffers: read by the trace kernel, live until the next commit
+  // two-level scenes (RTC_SCENE_FLAG_DYNAMIC with several triangle meshes; bvh_builder_twolevel.cpp:35-240): one kept BVH per mesh,
+  // rebuilt or refitted only when that mesh's modCounter moved (scene.cpp:878-884, bvh_builder_twolevel.h:174-177)
+  struct SubEntry {
+    unsigned modCounter = 0; RTCBuildQuality sceneQuality = RTC_BUILD_QUALITY_MEDIUM; int robust = 0; size_t nprims = 0, nverts = 0;
+    rtk::SceneGPU gpu;
+  };
+  std::unordered_map<GeometryImpl*, SubEntry*> subs;
+  void free_subs() { for (auto& kv : subs) { rtk::free_scene(kv.second->gpu); delete kv.second; } subs.clear(); }
   bool statCounters = false;
   double lastTraceMs = -1.0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -211,6 +220,7 @@ struct SceneImpl : RefCounted {
     for (GeometryImpl* g : geoms) if (g) g->release();
     for (void* p : deviceBuffers) cudaFreeAsync(p, 0);
     for (void* p : residentBuffers) cudaFreeAsync(p, 0);
+    free_subs();
     rtk::free_scene(gpu);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -425,6 +435,88 @@ void commit_scene(SceneImpl* s) {
     }
     descs.push_back(d);
   };
+  // ---- two-level path: a DYNAMIC scene of several plain triangle meshes keeps one BVH per mesh (the reference's two-level builder for
+  // dynamic scenes) -- a commit rebuilds / refits only the meshes that changed and re-assembles the top level
+  {
+    size_t ntri_geoms = 0;
+    bool plain = true;
+    for (GeometryImpl* g : geoms) if (g && g->enabled) { plain = plain && g->type == RTC_GEOMETRY_TYPE_TRIANGLE; ++ntri_geoms; }
+    if (plain && ntri_geoms >= 2 && (s->flags & RTC_SCENE_FLAG_DYNAMIC) && !getenv("RTCB200_NO_TWOLEVEL")) {
+      const int robust = (s->flags & RTC_SCENE_FLAG_ROBUST) ? 1 : 0;
+      rtk::BuilderKind kind2 = (s->quality == RTC_BUILD_QUALITY_LOW) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
+      if (const char* e = getenv("RTCB200_BUILDER")) kind2 = (strcmp(e, "lbvh") == 0) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
+      std::vector<rtk::SceneGPU*> order;
+      std::vector<uint8_t> dirty;
+      std::unordered_map<GeometryImpl*, SceneImpl::SubEntry*> keep;
+      char err2[256];
+      for (size_t id = 0; id < geoms.size(); ++id) {
+        GeometryImpl* g = geoms[id];
+        if (!g || !g->enabled) continue;
+        SceneImpl::SubEntry* e = nullptr;
+        auto it = s->subs.find(g);
+        if (it != s->subs.end()) { e = it->second; s->subs.erase(it); }
+        const bool fresh = e == nullptr;
+        if (fresh) { e = new SceneImpl::SubEntry(); e->gpu.device = s->dev->gpu; }
+        keep[g] = e;
+        const bool changed = fresh || e->modCounter != g->modCounter || e->sceneQuality != s->quality || e->robust != robust || e->gpu.device != s->dev->gpu;
+        if (changed) {   // only a changed mesh is uploaded and built again
+          e->gpu.robust = robust; e->gpu.general = 0; e->gpu.curves = 0;
+          const size_t before = descs.size();
+          add_mesh(g, (uint32_t)id, nullptr, nullptr, RTC_INVALID_GEOMETRY_ID, 0xFFFFFFFFu);
+          int r2 = 0;
+          if (descs.size() == before) {   // no triangles: an empty sub-BVH
+            const int dv = e->gpu.device;
+            rtk::free_scene(e->gpu);
+            e->gpu.device = dv;
+            for (int a = 0; a < 3; ++a) { e->gpu.bounds[a] = INFINITY; e->gpu.bounds[3 + a] = -INFINITY; }
+          } else {
+          const rtk::GeomDesc& d = descs.back();
+          if (!fresh && g->quality == RTC_BUILD_QUALITY_REFIT && e->gpu.root_valid && e->nprims == g->indices.count && e->nverts == g->vertices.count &&
+              e->sceneQuality == s->quality && e->robust == robust && !getenv("RTCB200_NO_REFIT"))
+            r2 = rtk::refit_scene(e->gpu, &d, 1, 0, err2);
+          else
+            r2 = rtk::build_scene(e->gpu, &d, 1, kind2, 0, err2);
+          }
+          if (r2 != 0) {
+            for (auto& kv : keep) s->subs[kv.first] = kv.second;
+            fail(r2 == (int)cudaErrorMemoryAllocation ? RTC_ERROR_OUT_OF_MEMORY : RTC_ERROR_UNKNOWN, err2);
+          }
+          e->modCounter = g->modCounter; e->sceneQuality = s->quality; e->robust = robust; e->nprims = g->indices.count; e->nverts = g->vertices.count;
+        }
+        order.push_back(&e->gpu);
+        dirty.push_back(changed ? 1 : 0);
+      }
+      s->free_subs();            // meshes that are no longer attached or enabled
+      s->subs.swap(keep);
+      s->gpu.general = 0; s->gpu.curves = 0; s->gpu.robust = robust;
+      if (s->gpu.d_descs) { cudaFreeAsync(s->gpu.d_descs, 0); s->gpu.d_descs = nullptr; }
+      if (s->gpu.tri_src) { cudaFreeAsync(s->gpu.tri_src, 0); s->gpu.tri_src = nullptr; }
+      const int r3 = rtk::assemble_scene(s->gpu, order.data(), (int)order.size(), dirty.data(), 0, err2);
+      for (void* p : s->deviceBuffers) cudaFreeAsync(p, 0);
+      s->deviceBuffers.clear();
+      if (r3 != 0) { rtk::free_scene(s->gpu); fail(r3 == (int)cudaErrorMemoryAllocation ? RTC_ERROR_OUT_OF_MEMORY : RTC_ERROR_UNKNOWN, err2); }
+      s->builtTopology.clear();
+      for (int a = 0; a < 6; ++a) s->apiBounds[a] = s->gpu.api_bounds[a];
+      if (s->dev->verbose >= 2)
+        fprintf(stderr, "[b200] commit (two-level): %zu meshes, %zu rebuilt or refitted, %u nodes, %u tris, assembly %.3f ms\n", order.size(),
+                (size_t)std::count(dirty.begin(), dirty.end(), 1), s->gpu.num_nodes, s->gpu.num_tris, s->gpu.build_ms);
+      {
+        std::lock_guard<std::mutex> lg(s->geomMutex);
+        s->committedCounter.assign(geoms.size(), 0u);
+        for (size_t i = 0; i < geoms.size(); ++i) s->committedCounter[i] = geoms[i] ? geoms[i]->modCounter : 0u;
+        s->committedChildGen = childGen;
+        s->generation.fetch_add(1);
+        s->flagsModified = false;
+        s->everCommitted = true;
+      }
+      if (s->progFn) s->progFn(s->progPtr, 1.0);
+      return;
+    }
+    if (!s->subs.empty()) {   // the scene left the two-level regime: drop the kept sub-BVHs and the assembly's layout
+      s->free_subs();
+      s->gpu.sub_nodes.clear(); s->gpu.sub_tris.clear(); s->gpu.sub_node_off.clear(); s->gpu.sub_tri_off.clear(); s->gpu.sub_root.clear();
+    }
+  }
   for (size_t id = 0; id < geoms.size(); ++id) {
     GeometryImpl* g = geoms[id];
     if (!g || !g->enabled) continue;
@@ -496,7 +588,7 @@ void commit_scene(SceneImpl* s) {
   if (s->dev->verbose >= 2)
     fprintf(stderr, "[b200] commit: %u tris, %u nodes (%.1f MB) + %.1f MB tris, builder=%s, %.3f ms (%.1f Mprim/s), SAH %.2f, depth %u\n",
             s->gpu.num_tris, s->gpu.num_nodes, s->gpu.num_nodes * 80e-6, s->gpu.num_tris * 48e-6,
-            s->gpu.builder == 2 ? "refit" : s->gpu.builder ? "sah" : "lbvh", s->gpu.build_ms, s->gpu.build_ms > 0 ? s->gpu.num_tris / s->gpu.build_ms * 1e-3 : 0.0,
+            s->gpu.builder == 3 ? "two-level" : s->gpu.builder == 2 ? "refit" : s->gpu.builder ? "sah" : "lbvh", s->gpu.build_ms, s->gpu.build_ms > 0 ? s->gpu.num_tris / s->gpu.build_ms * 1e-3 : 0.0,
             s->gpu.sah_cost, s->gpu.max_depth);
   {
     std::lock_guard<std::mutex> lg(s->geomMutex);

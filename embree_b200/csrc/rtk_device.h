@@ -90,7 +90,19 @@ struct SceneGPU {
   uint32_t* tri_src = nullptr;
   uint32_t total_prims = 0;
   std::vector<uint32_t> levels;
+  // two-level assembly (assemble_scene): where each sub-BVH lives in the arrays, its counts at layout time, its (relocated) root node
+  std::vector<uint32_t> sub_node_off, sub_tri_off, sub_nodes, sub_tris;
+  std::vector<Node8> sub_root;
+  uint32_t top_cap = 0;                 // nodes reserved at the start of the array for the top level
 };
+
+// ---- two-level scenes (kernels/bvh/bvh_builder_twolevel.cpp:35-240: dynamic scenes keep one BVH per mesh and rebuild only what
+// changed).  Every mesh is built on its own (build_scene / refit_scene on a one-mesh SceneGPU, kept by the host shim); assemble_scene
+// places the sub-BVHs in ONE node / record array -- node and record indices relocated by the mesh's offsets -- under a small top-level
+// BVH8 built on the host over the mesh boxes, whose lowest nodes hold COPIES of the meshes' root nodes (children of a node must be
+// consecutive), so the trace kernel runs unchanged.  `dirty[i]`: sub i was rebuilt / refitted since the last assembly.  The layout
+// is reused while every sub keeps its node and record counts (then only dirty subs are copied again); otherwise everything is laid out anew.
+int assemble_scene(SceneGPU& top, SceneGPU* const* subs, int nsubs, const uint8_t* dirty, cudaStream_t stream, char* errmsg);
 
 // Build the BVH8 over `ngeoms` meshes.  Returns cudaSuccess (0) or a CUDA error code; `errmsg` (>=256 B) gets text.
 int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind, cudaStream_t stream, char* errmsg);

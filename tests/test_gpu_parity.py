@@ -973,3 +973,95 @@ def test_full_size_properties_1m(b200, oracle):
         lib.rtcReleaseScene(sc)
     rep = compare_hits(results[0], results[1], TOL)
     assert rep["id_mismatch"] == 0 and rep["tie"] <= 8 and rep["max_rel_t"] <= TOL, rep
+
+
+def _dynamic_meshes(n, seed=4):
+    """n triangle spheres of different sizes scattered in a box, as tutorials/dynamic_scene places its spheres."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for i in range(n):
+        v, t = scenes.triangle_sphere(int(rng.randint(6, 24)))
+        c = rng.uniform(-3, 3, 3).astype(np.float32)
+        r = np.float32(rng.uniform(0.2, 0.9))
+        out.append(((v * r + c).astype(np.float32), t.copy()))
+    return out
+
+
+@pytest.mark.parametrize("robust", [False, True])
+@pytest.mark.parametrize("scene_quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
+def test_two_level_dynamic_scene(b200, oracle, scene_quality, robust):
+    """a25: an RTC_SCENE_FLAG_DYNAMIC scene of several triangle meshes keeps one BVH per mesh (bvh_builder_twolevel.cpp:35-240); a commit
+    rebuilds / refits only the meshes whose modCounter moved (scene.cpp:878-884) and re-assembles the top level.  Hits equal the
+    oracle's single BVH over the same triangles at every stage: first commit, one mesh moved, one mesh refitted, a mesh disabled, a
+    mesh with a new triangle count (new layout), and after leaving the two-level regime."""
+    lib, dev = b200
+    meshes = _dynamic_meshes(24)
+    sc = lib.rtcNewScene(dev)
+    lib.rtcSetSceneFlags(sc, 1 | (4 if robust else 0))   # DYNAMIC (| ROBUST)
+    lib.rtcSetSceneBuildQuality(sc, scene_quality)
+    geoms, bufs = [], []
+    for i, (v, t) in enumerate(meshes):
+        vpad = np.zeros(v.size + 4, np.float32)
+        vpad[:v.size] = v.ravel()
+        g = lib.rtcNewGeometry(dev, RTC_GEOMETRY_TYPE_TRIANGLE)
+        lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(vpad), 0, 12, len(v))
+        lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT3, _ptr(t), 0, 12, len(t))
+        lib.rtcSetGeometryMask(g, 0xFFFFFFFF)
+        if i == 5:
+            lib.rtcSetGeometryBuildQuality(g, 3)          # RTC_BUILD_QUALITY_REFIT for this one
+        lib.rtcCommitGeometry(g)
+        lib.rtcAttachGeometryByID(sc, g, i)
+        geoms.append(g)
+        bufs.append((vpad, v.shape[0], t))
+    rng = np.random.RandomState(9)
+    org = rng.uniform(-5, 5, (40000, 3)).astype(np.float32)
+    d = rng.normal(size=(40000, 3)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    enabled = [True] * len(meshes)
+
+    def check(stage):
+        lib.rtcCommitScene(sc)
+        lib.check(dev)
+        cur = [(bufs[i][0][:bufs[i][1] * 3].reshape(-1, 3).copy(), bufs[i][2], i, 0xFFFFFFFF) for i in range(len(bufs)) if enabled[i]]
+        want = oracle.scene(cur, robust=robust).trace(rays.copy(), nthreads=8)
+        got = lib.intersect(sc, rays.copy(), "1M")
+        rep = compare_hits(want, got, TOL, meshes=cur)
+        assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 12, (stage, rep)
+        assert rep["max_rel_t"] <= TOL and rep["hits"] > 5000, (stage, rep)
+        occ = lib.occluded(sc, rays_of(rays), "1M")
+        assert ((occ["tfar"] == -np.inf) == (want["geomID"] != 0xFFFFFFFF)).all(), stage
+        return lib.scene_stats(sc)
+    l0 = lib.rtcb200GetLaunchCount()
+    st = check("first commit")
+    first_launches = lib.rtcb200GetLaunchCount() - l0
+    assert st.builder == 3 and st.num_triangles == sum(len(t) for (_v, t) in meshes)
+    # one mesh moves: only that mesh is rebuilt (far fewer kernel launches than the first commit of 24 meshes)
+    bufs[2][0][:bufs[2][1] * 3] += np.float32(0.35)
+    lib.rtcUpdateGeometryBuffer(geoms[2], RTC_BUFFER_TYPE_VERTEX, 0)
+    lib.rtcCommitGeometry(geoms[2])
+    l0 = lib.rtcb200GetLaunchCount()
+    check("one mesh moved")
+    assert lib.rtcb200GetLaunchCount() - l0 < first_launches / 5 + 40   # (the traces of check() are part of both counts)
+    # the REFIT mesh deforms
+    bufs[5][0][:bufs[5][1] * 3] *= np.float32(1.1)
+    lib.rtcUpdateGeometryBuffer(geoms[5], RTC_BUFFER_TYPE_VERTEX, 0)
+    lib.rtcCommitGeometry(geoms[5])
+    check("refit mesh deformed")
+    # a mesh is disabled, another one gets a different triangle count (fewer triangles through a shorter index buffer)
+    lib.rtcDisableGeometry(geoms[7])
+    enabled[7] = False
+    t9 = bufs[9][2][: len(bufs[9][2]) // 2].copy()
+    lib.rtcSetSharedGeometryBuffer(geoms[9], RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT3, _ptr(t9), 0, 12, len(t9))
+    lib.rtcCommitGeometry(geoms[9])
+    bufs[9] = (bufs[9][0], bufs[9][1], t9)
+    check("disabled + new triangle count")
+    # leaving the two-level regime: all but one mesh disabled -> the ordinary single BVH
+    for i in range(1, len(geoms)):
+        if enabled[i]:
+            lib.rtcDisableGeometry(geoms[i])
+            enabled[i] = False
+    st = check("single mesh left")
+    assert st.builder != 3
+    for g in geoms:
+        lib.rtcReleaseGeometry(g)
+    lib.rtcReleaseScene(sc)
