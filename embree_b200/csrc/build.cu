@@ -1014,6 +1014,7 @@ int assemble_scene(SceneGPU& s, SceneGPU* const* subs, int nsubs, const uint8_t*
     if (s.tris) { cudaFreeAsync(s.tris, st); s.tris = nullptr; }
     s.sub_node_off.assign(nsubs, 0); s.sub_tri_off.assign(nsubs, 0); s.sub_nodes.assign(nsubs, 0); s.sub_tris.assign(nsubs, 0);
     s.sub_root.assign(nsubs, Node8{});
+    s.sub_id.assign(nsubs, nullptr);
     s.top_cap = (uint32_t)(2 * nsubs + 8);
     uint64_t nn = s.top_cap, nt = 0;
     for (int i = 0; i < nsubs; ++i) {
@@ -1029,7 +1030,9 @@ int assemble_scene(SceneGPU& s, SceneGPU* const* subs, int nsubs, const uint8_t*
   }
   for (int i = 0; i < nsubs; ++i) {
     const SceneGPU& b = *subs[i];
-    if (!b.root_valid || (same && !dirty[i])) continue;
+    const bool other = s.sub_id[i] != static_cast<const void*>(subs[i]);   // another mesh took this slot
+    s.sub_id[i] = subs[i];
+    if (!b.root_valid || (same && !dirty[i] && !other)) continue;
     relocate_nodes<<<(b.num_nodes + 255) / 256, 256, 0, st>>>(b.nodes, b.num_nodes, s.nodes + s.sub_node_off[i], s.sub_node_off[i], s.sub_tri_off[i]);
     count_launch();
     CK(cudaMemcpyAsync(s.tris + s.sub_tri_off[i], b.tris, (size_t)b.num_tris * sizeof(TriRec), cudaMemcpyDeviceToDevice, st));

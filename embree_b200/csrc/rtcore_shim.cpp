@@ -514,7 +514,7 @@ void commit_scene(SceneImpl* s) {
     }
     if (!s->subs.empty()) {   // the scene left the two-level regime: drop the kept sub-BVHs and the assembly's layout
       s->free_subs();
-      s->gpu.sub_nodes.clear(); s->gpu.sub_tris.clear(); s->gpu.sub_node_off.clear(); s->gpu.sub_tri_off.clear(); s->gpu.sub_root.clear();
+      s->gpu.sub_nodes.clear(); s->gpu.sub_tris.clear(); s->gpu.sub_node_off.clear(); s->gpu.sub_tri_off.clear(); s->gpu.sub_root.clear(); s->gpu.sub_id.clear();
     }
   }
   for (size_t id = 0; id < geoms.size(); ++id) {

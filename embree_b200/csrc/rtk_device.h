@@ -93,6 +93,7 @@ struct SceneGPU {
   // two-level assembly (assemble_scene): where each sub-BVH lives in the arrays, its counts at layout time, its (relocated) root node
   std::vector<uint32_t> sub_node_off, sub_tri_off, sub_nodes, sub_tris;
   std::vector<Node8> sub_root;
+  std::vector<const void*> sub_id;      // which sub-BVH object occupies each slot (a different one there is copied even if the counts match)
   uint32_t top_cap = 0;                 // nodes reserved at the start of the array for the top level
 };
 

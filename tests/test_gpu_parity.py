@@ -1055,6 +1055,24 @@ def test_two_level_dynamic_scene(b200, oracle, scene_quality, robust):
     lib.rtcCommitGeometry(geoms[9])
     bufs[9] = (bufs[9][0], bufs[9][1], t9)
     check("disabled + new triangle count")
+    # a slot changes hands between two meshes of identical size in ONE commit (same node / record counts: the layout is reused)
+    vtw, ttw = scenes.triangle_sphere(12)
+    for i, c in ((20, (-2.0, 2.0, 1.0)), (21, (2.5, -1.0, -2.0))):
+        vv = (vtw * np.float32(0.5) + np.float32(c)).astype(np.float32)
+        vpad = np.zeros(vv.size + 4, np.float32)
+        vpad[:vv.size] = vv.ravel()
+        tcp = ttw.copy()
+        lib.rtcSetSharedGeometryBuffer(geoms[i], RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(vpad), 0, 12, len(vv))
+        lib.rtcSetSharedGeometryBuffer(geoms[i], RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT3, _ptr(tcp), 0, 12, len(tcp))
+        lib.rtcCommitGeometry(geoms[i])
+        bufs[i] = (vpad, len(vv), tcp)
+    lib.rtcDisableGeometry(geoms[21])
+    enabled[21] = False
+    check("two equal meshes, one disabled")
+    lib.rtcDisableGeometry(geoms[20])
+    lib.rtcEnableGeometry(geoms[21])
+    enabled[20], enabled[21] = False, True
+    check("slot handed to the other equal mesh")
     # leaving the two-level regime: all but one mesh disabled -> the ordinary single BVH
     for i in range(1, len(geoms)):
         if enabled[i]:
