@@ -455,3 +455,46 @@ extern "C" int emu_round_cubic_closest(const float* ray8, const float* cps, int 
   }
   return win;
 }
+
+// ---- two-level assembly on the host (embree_b200/csrc/two_level.h + the relocation of build.cu relocate_nodes): `n` emulated scenes
+// become ONE scene -- [top level | scene 0 nodes | scene 1 nodes ...], node / record indices relocated, root-node copies under a
+// top-level BVH8 -- exactly what assemble_scene does on the device.  Returns a new handle (free with emu_free).
+#include "../../embree_b200/csrc/two_level.h"
+extern "C" void* emu_assemble(void** handles, int n) {
+  EmuScene* out = new EmuScene();
+  std::vector<TopItem> items;
+  std::vector<Node8> roots(n);
+  const uint32_t top_cap = (uint32_t)(2 * n + 8);
+  uint32_t nn = top_cap, nt = 0;
+  std::vector<uint32_t> noff(n), toff(n);
+  for (int i = 0; i < n; ++i) {
+    EmuScene* s = static_cast<EmuScene*>(handles[i]);
+    noff[i] = nn; toff[i] = nt;
+    if (!s->root_valid) continue;
+    nn += (uint32_t)s->nodes.size(); nt += (uint32_t)s->tris.size();
+  }
+  out->nodes.resize(nn); out->tris.resize(nt);
+  for (int i = 0; i < n; ++i) {
+    EmuScene* s = static_cast<EmuScene*>(handles[i]);
+    if (!s->root_valid) continue;
+    out->robust = s->robust;
+    for (size_t k = 0; k < s->nodes.size(); ++k) { Node8 nd = s->nodes[k]; nd.w[4] += noff[i]; nd.w[5] += toff[i]; out->nodes[noff[i] + k] = nd; }
+    for (size_t k = 0; k < s->tris.size(); ++k) out->tris[toff[i] + k] = s->tris[k];
+    roots[i] = out->nodes[noff[i]];
+    TopItem it;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    // the mesh box: decoded from its root node's grid (conservative) -- p + [0, 255] * 2^e per axis covers all children
+    const Node8& r = s->nodes[0];
+    for (int a = 0; a < 3; ++a) { lo[a] = u2f(r.w[a]); hi[a] = lo[a] + 255.0f * u2f(((r.w[3] >> (8 * a)) & 0xFFu) << 23); }
+    for (int a = 0; a < 3; ++a) { it.lo[a] = lo[a]; it.hi[a] = hi[a]; }
+    it.sub = i;
+    items.push_back(it);
+  }
+  if (!items.empty()) {
+    const std::vector<Node8> top = build_top_level(items, roots);
+    if (top.size() > top_cap) { delete out; return nullptr; }
+    for (size_t k = 0; k < top.size(); ++k) out->nodes[k] = top[k];
+    out->root_valid = 1;
+  }
+  return out;
+}

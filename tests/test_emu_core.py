@@ -301,3 +301,41 @@ def test_round_cubic_curve_test_equals_oracle(emu, oracle, basis):
             assert (got == exp).all(), (k, list(out), w)
     assert hits > 150
     sc.free()
+
+
+@pytest.mark.parametrize("n_meshes", [1, 2, 8, 9, 40])
+def test_two_level_assembly_equals_single_bvh(emu, oracle, n_meshes):
+    """embree_b200/csrc/two_level.h (the host-built top level of two-level dynamic scenes) + the node / record relocation of
+    build.cu assemble_scene, on the CPU emulation: `n_meshes` separately built BVH8s assembled under a top level return the hits of
+    the oracle's single BVH over all triangles (1 mesh: the root is the mesh's root; <= 8: one top node; more: nested top nodes)."""
+    import ctypes as C
+    from embree_b200 import scenes
+    from embree_b200.rtc import make_rayhits
+    rng = np.random.RandomState(3 + n_meshes)
+    emu.emu_assemble.restype = C.c_void_p
+    emu.emu_assemble.argtypes = [C.c_void_p, C.c_int]
+    handles, meshes, keep = [], [], []
+    for i in range(n_meshes):
+        v, t = scenes.triangle_sphere(int(rng.randint(4, 12)))
+        v = (v * np.float32(rng.uniform(0.3, 0.9)) + rng.uniform(-3, 3, 3).astype(np.float32)).astype(np.float32)
+        v = np.ascontiguousarray(v); t = np.ascontiguousarray(t, np.uint32)
+        keep += [v, t]
+        handles.append(emu.emu_build(v.ctypes.data, len(v), t.ctypes.data, len(t), i, 0xFFFFFFFF, 3))
+        meshes.append((v, t, i, 0xFFFFFFFF))
+    arr = (C.c_void_p * n_meshes)(*handles)
+    top = emu.emu_assemble(arr, n_meshes)
+    assert top
+    org = rng.uniform(-5, 5, (6000, 3)).astype(np.float32)
+    d = rng.normal(size=(6000, 3)).astype(np.float32)
+    rays = make_rayhits(org, d)
+    got = rays.copy()
+    emu.emu_trace(top, got.ctypes.data, len(got), 0, None)
+    want = oracle.scene(meshes).trace(rays.copy())
+    rep = compare_hits(want, got, meshes=meshes)
+    assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 4 and rep["hits"] > 20, rep
+    occ = rays_of(rays)
+    emu.emu_trace(top, occ.ctypes.data, len(occ), 1, None)
+    assert ((occ["tfar"] == -np.inf) == (want["geomID"] != 0xFFFFFFFF)).all()
+    emu.emu_free(top)
+    for h in handles:
+        emu.emu_free(h)
