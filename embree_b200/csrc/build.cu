@@ -706,7 +706,7 @@ int build_scene(SceneGPU& s, const GeomDesc* geoms, int ngeoms, BuilderKind kind
   s.levels.clear();
   s.num_nodes = s.num_tris = 0; s.root_valid = 0; s.max_depth = 0; s.sah_cost = 0; s.builder = kind;
   for (int a = 0; a < 3; ++a) { s.bounds[a] = s.api_bounds[a] = INFINITY; s.bounds[3 + a] = s.api_bounds[3 + a] = -INFINITY; }
-  if (!s.d_stat) { CK(cudaMalloc(&s.d_stat, 3 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s.d_stat, 0, 24, st)); }
+  if (!s.d_stat && !s.is_sub) { CK(cudaMalloc(&s.d_stat, 3 * sizeof(unsigned long long))); CK(cudaMemsetAsync(s.d_stat, 0, 24, st)); }
 
   std::vector<uint32_t> offs(ngeoms + 1, 0);
   uint64_t tot64 = 0;

@@ -456,7 +456,7 @@ void commit_scene(SceneImpl* s) {
         auto it = s->subs.find(g);
         if (it != s->subs.end()) { e = it->second; s->subs.erase(it); }
         const bool fresh = e == nullptr;
-        if (fresh) { e = new SceneImpl::SubEntry(); e->gpu.device = s->dev->gpu; }
+        if (fresh) { e = new SceneImpl::SubEntry(); e->gpu.device = s->dev->gpu; e->gpu.is_sub = true; }
         keep[g] = e;
         const bool changed = fresh || e->modCounter != g->modCounter || e->sceneQuality != s->quality || e->robust != robust || e->gpu.device != s->dev->gpu;
         if (changed) {   // only a changed mesh is uploaded and built again

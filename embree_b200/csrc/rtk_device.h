@@ -95,6 +95,7 @@ struct SceneGPU {
   std::vector<Node8> sub_root;
   std::vector<const void*> sub_id;      // which sub-BVH object occupies each slot (a different one there is copied even if the counts match)
   uint32_t top_cap = 0;                 // nodes reserved at the start of the array for the top level
+  bool is_sub = false;                  // a per-mesh BVH of a two-level scene: never traced on its own (no stat counters)
 };
 
 // ---- two-level scenes (kernels/bvh/bvh_builder_twolevel.cpp:35-240: dynamic scenes keep one BVH per mesh and rebuild only what

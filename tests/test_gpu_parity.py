@@ -1027,7 +1027,7 @@ def test_two_level_dynamic_scene(b200, oracle, scene_quality, robust):
         got = lib.intersect(sc, rays.copy(), "1M")
         rep = compare_hits(want, got, TOL, meshes=cur)
         assert rep["id_mismatch"] == 0 and rep["hit_miss_disagree"] == 0 and rep["tie"] <= 12, (stage, rep)
-        assert rep["max_rel_t"] <= TOL and rep["hits"] > 5000, (stage, rep)
+        assert rep["max_rel_t"] <= TOL and rep["hits"] > (2500 if sum(enabled) > 1 else 30), (stage, rep)
         occ = lib.occluded(sc, rays_of(rays), "1M")
         assert ((occ["tfar"] == -np.inf) == (want["geomID"] != 0xFFFFFFFF)).all(), stage
         return lib.scene_stats(sc)
