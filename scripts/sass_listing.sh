@@ -5,11 +5,11 @@ set -e
 cd "$(dirname "$0")/.."
 OBJ=embree_b200/csrc/trace.o
 OUT=profiles/${1:-r2}_trace_sass.txt
-K='_ZN3rtk12trace_kernelILi1ELb0ELb0ELb0ELb0ELi0ELb1EEEvNS_11TraceParamsE'
-G='_ZN3rtk12trace_kernelILi1ELb0ELb0ELb0ELb0ELi2ELb1EEEvNS_11TraceParamsE'
+K='_ZN3rtk12trace_kernelILi1ELb0ELb0ELb0ELi0ELi0ELb1ELb0EEEvNS_11TraceParamsE'
+G='_ZN3rtk12trace_kernelILi1ELb0ELb0ELb0ELi0ELi2ELb1ELb0EEEvNS_11TraceParamsE'
 {
   echo "# cuobjdump -sass of embree_b200/csrc/trace.o (nvcc 12.9, -gencode arch=compute_100a,code=sm_100a -O3), $(date -u +%Y-%m-%d)"
-  echo "# headline kernel: rtk::trace_kernel<K=1, OCCLUDED=false, STATS=false, ROBUST=false, GENERAL=false, GATHER=0, SPREAD=true>"
+  echo "# headline kernel: rtk::trace_kernel<K=1, OCCLUDED=false, STATS=false, ROBUST=false, GENERAL=0, GATHER=0, SPREAD=true, FILTER=false>"
   grep -A3 "$K" embree_b200/csrc/trace.o.ptxas.log | sed 's/^/# /'
   cuobjdump -sass -fun "$K" $OBJ | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's/^\s+\/\*([0-9a-f]{4})\*\/\s+/\1  /; s/\s*\/\*.*$//' > /tmp/sass_k.txt
   echo "# instructions: $(wc -l < /tmp/sass_k.txt)"
