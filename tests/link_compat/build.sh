@@ -52,3 +52,19 @@ if [ -f ../../oracle/_ref/libembree4.so.4 ] && [ ! -f ../golden/hair_geometry_2_
   for t in 0 1 2; do _bin/ref_hair_geometry ../golden/hair_geometry_${t}_96x72.raw 96 72 4 $t 3000; done
   rm -f _bin/ref_hair_geometry
 fi
+
+# BASELINE configs[3]b: the reference's tutorial device code tutorials/dynamic_scene/dynamic_scene_device.cpp (DYNAMIC | ROBUST scene of a plane
+# and 20 spheres with per-geometry build qualities, all vertices rewritten and re-committed every frame), compiled untouched with OUR host
+# driver dynamic_host.cpp, linked (a) against libembree4_b200.so -> _bin/embree_dynamic_scene and (b) against the unmodified reference ->
+# golden frames tests/golden/dynamic_scene_160x120_<frame>.raw.
+if [ ! -x _bin/embree_dynamic_scene ] || [ dynamic_host.cpp -nt _bin/embree_dynamic_scene ]; then
+  g++ -O1 -std=c++17 -w $INC -o _bin/embree_dynamic_scene dynamic_host.cpp "$REF/tutorials/dynamic_scene/dynamic_scene_device.cpp" $SYS \
+      -L_bin -lembree4 -lpthread -Wl,-rpath,'$ORIGIN/../../../embree_b200/csrc'
+  echo built tests/link_compat/_bin/embree_dynamic_scene
+fi
+if [ -f ../../oracle/_ref/libembree4.so.4 ] && [ ! -f ../golden/dynamic_scene_160x120_2.raw ]; then
+  g++ -O1 -std=c++17 -w $INC -o _bin/ref_dynamic_scene dynamic_host.cpp "$REF/tutorials/dynamic_scene/dynamic_scene_device.cpp" $SYS \
+      -L../../oracle/_ref -l:libembree4.so.4 -lpthread -Wl,-rpath,'$ORIGIN/../../../oracle/_ref'
+  _bin/ref_dynamic_scene ../golden/dynamic_scene_160x120 160 120 4 3
+  rm -f _bin/ref_dynamic_scene
+fi
