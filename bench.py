@@ -345,10 +345,12 @@ def two_level_leg(lib, dev, args):
                 L.rtcCommitGeometry(L.rtcGetGeometry(sc, m))
             L.rtcCommitScene(sc)
             dt = time.perf_counter() - t0
+            if it == 0:
+                frame0 = dt
             if it >= 2:
                 ts.append(dt)
         L.check(d)
-        row = {"first_commit_ms": first * 1e3, "recommit_ms": float(np.mean(ts)) * 1e3}
+        row = {"first_commit_ms": first * 1e3, "second_commit_ms": frame0 * 1e3, "recommit_ms": float(np.mean(ts)) * 1e3}   # second commit: the kept per-mesh BVHs are built here (two-level path)
         if L is lib:
             row["path"] = ["lbvh build", "sah build", "refit", "two-level"][L.scene_stats(sc).builder]
             rays = scenes.as_numpy_rayhits(scenes.primary_rays(480, 270, eye=(0.0, 0.9, -0.2), look=(0.0, -1.0, 0.25)))

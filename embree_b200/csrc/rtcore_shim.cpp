@@ -441,7 +441,25 @@ void commit_scene(SceneImpl* s) {
     size_t ntri_geoms = 0;
     bool plain = true;
     for (GeometryImpl* g : geoms) if (g && g->enabled) { plain = plain && g->type == RTC_GEOMETRY_TYPE_TRIANGLE; ++ntri_geoms; }
-    if (plain && ntri_geoms >= 2 && (s->flags & RTC_SCENE_FLAG_DYNAMIC) && !getenv("RTCB200_NO_TWOLEVEL")) {
+    bool eligible = plain && ntri_geoms >= 2 && (s->flags & RTC_SCENE_FLAG_DYNAMIC) && !getenv("RTCB200_NO_TWOLEVEL");
+    if (eligible && !getenv("RTCB200_FORCE_TWOLEVEL")) {
+      // Which regime is cheaper for THIS commit?  A device build runs at ~400 Mprims/s plus ~0.5 ms of launches and round trips per
+      // build, the vertex upload at PCIe speed: rebuilding one BVH over everything costs ~1.5 ms + 2.5 ns per triangle, the two-level
+      // commit ~1 ms + (0.5 ms + 2.5 ns per triangle) per mesh modified since the last commit (measured, bench.py
+      // extras.dynamic_scene_two_level).  When most meshes move every frame (tutorials/dynamic_scene) one rebuild wins; when a few of
+      // many move, the two-level path does -- meshes that have no kept BVH yet are built then, a one-time investment.
+      double total = 0.0, two = 1.0;
+      for (size_t id = 0; id < geoms.size(); ++id) {
+        GeometryImpl* g = geoms[id];
+        if (!g || !g->enabled) continue;
+        const double tris = (double)g->indices.count;
+        total += tris;
+        const bool modified = !s->everCommitted || id >= s->committedCounter.size() || s->committedCounter[id] != g->modCounter;
+        if (modified) two += 0.5 + tris * 2.5e-6;
+      }
+      eligible = two < 1.5 + total * 2.5e-6;
+    }
+    if (eligible) {
       const int robust = (s->flags & RTC_SCENE_FLAG_ROBUST) ? 1 : 0;
       rtk::BuilderKind kind2 = (s->quality == RTC_BUILD_QUALITY_LOW) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
       if (const char* e = getenv("RTCB200_BUILDER")) kind2 = (strcmp(e, "lbvh") == 0) ? rtk::BUILDER_LBVH : rtk::BUILDER_SAH;
@@ -449,6 +467,16 @@ void commit_scene(SceneImpl* s) {
       std::vector<uint8_t> dirty;
       std::unordered_map<GeometryImpl*, SceneImpl::SubEntry*> keep;
       char err2[256];
+      {   // many fresh per-mesh BVHs keep their memory: grow the stream-ordered pool once instead of once per mesh (~ms each)
+        size_t fresh_tris = 0, fresh_n = 0;
+        for (GeometryImpl* g : geoms) if (g && g->enabled && !s->subs.count(g)) { fresh_tris += g->indices.count; ++fresh_n; }
+        if (fresh_n >= 8) {
+          void* prime = nullptr;
+          const size_t bytes = fresh_tris * 400 + (size_t)fresh_n * (1u << 16);     // nodes + records + the build's temporaries, generously
+          if (cudaMallocAsync(&prime, bytes, 0) == cudaSuccess) cudaFreeAsync(prime, 0);
+          else cudaGetLastError();
+        }
+      }
       for (size_t id = 0; id < geoms.size(); ++id) {
         GeometryImpl* g = geoms[id];
         if (!g || !g->enabled) continue;
@@ -512,8 +540,9 @@ void commit_scene(SceneImpl* s) {
       if (s->progFn) s->progFn(s->progPtr, 1.0);
       return;
     }
-    if (!s->subs.empty()) {   // the scene left the two-level regime: drop the kept sub-BVHs and the assembly's layout
-      s->free_subs();
+    if (!s->subs.empty()) {   // one BVH over everything this time: the assembly's layout is gone; the kept per-mesh BVHs stay only while the
+      // scene could return to the two-level path (they are compared by modCounter then)
+      if (!(plain && ntri_geoms >= 2 && (s->flags & RTC_SCENE_FLAG_DYNAMIC))) s->free_subs();
       s->gpu.sub_nodes.clear(); s->gpu.sub_tris.clear(); s->gpu.sub_node_off.clear(); s->gpu.sub_tri_off.clear(); s->gpu.sub_root.clear(); s->gpu.sub_id.clear();
     }
   }

@@ -3,8 +3,8 @@
 // LOW) of a ground plane and 20 spheres with per-geometry build qualities, whose vertices the tutorial rewrites every frame through
 // rtcGetGeometryBufferData / rtcUpdateGeometryBuffer / rtcCommitGeometry before rtcCommitScene.  This file supplies what tutorial.cpp would
 // (g_device, g_stats, the camera of dynamic_scene.cpp:23-24) and renders a few frames of the animation to files, so the same tutorial code
-// can be linked against the reference library (golden frames) and against libembree4_b200.so, where every frame goes through the
-// two-level commit (one kept BVH per mesh; here every sphere moves, so every frame rebuilds / refits all of them).
+// can be linked against the reference library (golden frames) and against libembree4_b200.so (every sphere moves every frame, so the
+// library rebuilds one BVH over everything per commit rather than taking its two-level path).
 #include <cstdio>
 #include <cstdlib>
 #include <string>

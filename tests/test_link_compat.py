@@ -114,8 +114,8 @@ def test_dynamic_scene_tutorial_renders_the_reference_frames(tmp_path):
     """BASELINE configs[3]b: the reference's tutorials/dynamic_scene device code -- an RTC_SCENE_FLAG_DYNAMIC | RTC_SCENE_FLAG_ROBUST scene of a
     plane and 20 spheres with per-geometry build qualities whose vertices it rewrites (rtcGetGeometryBufferData, rtcUpdateGeometryBuffer,
     rtcCommitGeometry) and re-commits every frame -- compiled untouched and linked against libembree4_b200.so, renders three frames of the
-    animation like the same code does with the unmodified reference library.  Every commit goes through the two-level path (one kept BVH
-    per mesh).  Pixels may differ only ON an edge of the picture (silhouettes, shadow boundaries), at most 0.5 % of a frame."""
+    animation like the same code does with the unmodified reference library (every sphere moves every frame, so each commit rebuilds one
+    BVH over everything -- the library's own choice between that and the two-level path).  Pixels may differ only ON an edge of the picture (silhouettes, shadow boundaries), at most 0.5 % of a frame."""
     import numpy as np
     _ensure_built()
     if not os.path.exists(DYN):
