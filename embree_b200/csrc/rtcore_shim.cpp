@@ -778,6 +778,12 @@ void trace_gather(SceneImpl* s, void* d_rays, size_t M, uint32_t instID, uint32_
 // batched, host pointers: chunked H2D -> trace -> D2H pipeline over three streams
 // host-buffer pipeline shape (rtcb200SetTuning "host_chunk_log2" / "host_streams"): rays per chunk and chunks in flight
 static int g_host_chunk_log2 = 20, g_host_streams = 3;   // measured: 2^20 -> 492 Mrays/s, 2^22 -> 474 (scripts/e2e_sweep.py)
+// rtcb200SetTuning("host_d2h_partial", 1): the copy back to the host skips the bytes of a record that a query never changes -- org, tnear,
+// dir, time of an RTCRayHit (the first 32 of its 96 bytes), the first eight fields of an RTCRayHitK -- with a pitched copy of the rest.
+// Fewer bytes cross PCIe and, with several GPUs per socket, the host's memory controllers (the limit of the 8-GPU e2e number) -- but the
+// copy engine moves 64-byte rows of a pitched copy slower than one contiguous block: measured at one GPU 431 vs 490 Mrays/s
+// (scripts/e2e_partial_ab.py, identical records), so it is OFF by default; not measured at 8 GPUs.
+static int g_host_d2h_partial = 0;
 
 struct HostPipe {
   int gpu = -1;
@@ -837,7 +843,12 @@ void trace_host(SceneImpl* s, void* rays, const int* valid, int K, size_t M, siz
     }
     rtk::TraceParams p = make_params(s, t_pipe.buf[b], dvalid, (unsigned long long)cnt * K, instID, instPrimID);
     cuda_check((cudaError_t)rtk::launch_trace(p, occluded, K, st), "trace launch");
-    cuda_check(cudaMemcpyAsync(h, t_pipe.buf[b], cnt * recBytes, cudaMemcpyDeviceToHost, st), "D2H rays");
+    // closest hit: only tfar .. end of the record can have changed (K == 1: bytes 32..95; packets: fields 8..20 = the last 52 K bytes)
+    const size_t skip = (!occluded && g_host_d2h_partial) ? (K == 1 ? 32 : (size_t)8 * 4 * K) : 0;
+    if (skip)
+      cuda_check(cudaMemcpy2DAsync(h + skip, recBytes, t_pipe.buf[b] + skip, recBytes, recBytes - skip, cnt, cudaMemcpyDeviceToHost, st), "D2H rays");
+    else
+      cuda_check(cudaMemcpyAsync(h, t_pipe.buf[b], cnt * recBytes, cudaMemcpyDeviceToHost, st), "D2H rays");
   }
   for (int i = 0; i < HostPipe::kStreams; ++i) cuda_check(cudaStreamSynchronize(t_pipe.st[i]), "trace");
 }
@@ -1537,6 +1548,7 @@ int rtcb200SetTuning(const char* key, int value) {
   else if (!strcmp(key, "use_tma")) t.use_tma = value;
   else if (!strcmp(key, "tri_spread")) t.tri_spread = value != 0;
   else if (!strcmp(key, "gather_mode") && value >= 0 && value <= 1) t.gather_mode = value;
+  else if (!strcmp(key, "host_d2h_partial")) g_host_d2h_partial = value != 0;
   else if (!strcmp(key, "host_chunk_log2") && value >= 10 && value <= 26) g_host_chunk_log2 = value;
   else if (!strcmp(key, "host_streams") && value >= 1 && value <= HostPipe::kStreams) g_host_streams = value;
   else return -1;
