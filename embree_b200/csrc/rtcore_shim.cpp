@@ -636,7 +636,8 @@ void commit_scene(SceneImpl* s) {
 struct ThreadCtx {  // per calling thread: a stream and a mapped pinned staging record for the single-call path
   int gpu = -1;
   cudaStream_t stream = nullptr;
-  char* staging = nullptr;  // 1344 B packet + 64 B valid
+  static constexpr size_t kStagingBytes = 16384;
+  char* staging = nullptr;  // mapped pinned: 1344 B packet + 64 B valid for the single-call path; [2048, 16384) = the filter passes of small queries
   ~ThreadCtx() {
     if (staging) cudaFreeHost(staging);
     if (stream) cudaStreamDestroy(stream);
@@ -647,7 +648,7 @@ struct ThreadCtx {  // per calling thread: a stream and a mapped pinned staging 
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     cudaSetDevice(g);
     cuda_check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
-    cuda_check(cudaHostAlloc(reinterpret_cast<void**>(&staging), 2048, cudaHostAllocMapped), "cudaHostAlloc");
+    cuda_check(cudaHostAlloc(reinterpret_cast<void**>(&staging), kStagingBytes, cudaHostAllocMapped), "cudaHostAlloc");
     gpu = g;
   }
 };
@@ -964,6 +965,23 @@ void trace_filtered(SceneImpl* s, void* recs, const int* valid, int K, size_t M,
         idx.insert(idx.end(), excl[active[j]].begin(), excl[active[j]].end());
       }
       off[n] = (uint32_t)idx.size();
+      // a single ray or one packet (what a per-pixel caller such as tutorials/hair_geometry issues): the pass runs out of the calling
+      // thread's mapped pinned staging block -- no allocation, no copy calls, one launch and one synchronisation, like trace_one
+      constexpr size_t kSmallRays = 16, kRaysAt = 2048, kOffAt = kRaysAt + kSmallRays * sizeof(RTCRayHit), kWinAt = kOffAt + 128, kIdxAt = kWinAt + 64;
+      if (n <= kSmallRays && kIdxAt + idx.size() * 4 <= ThreadCtx::kStagingBytes) {
+        char* sg = t_ctx.staging;
+        memcpy(sg + kRaysAt, pass.data(), n * sizeof(RTCRayHit));
+        memcpy(sg + kOffAt, off.data(), (n + 1) * 4);
+        if (!idx.empty()) memcpy(sg + kIdxAt, idx.data(), idx.size() * 4);
+        rtk::TraceParams p = make_params(s, sg + kRaysAt, nullptr, (unsigned long long)n, q.instID, q.instPrimID);
+        p.stat = nullptr;
+        p.excl_off = reinterpret_cast<const uint32_t*>(sg + kOffAt); p.excl_idx = reinterpret_cast<const uint32_t*>(sg + kIdxAt);
+        p.win = reinterpret_cast<uint32_t*>(sg + kWinAt);
+        cuda_check((cudaError_t)rtk::launch_trace(p, 0, 1, st), "trace launch");
+        cuda_check(cudaStreamSynchronize(st), "trace");
+        memcpy(pass.data(), sg + kRaysAt, n * sizeof(RTCRayHit));
+        memcpy(win.data(), sg + kWinAt, n * 4);
+      } else {
       RTCRayHit* dr = static_cast<RTCRayHit*>(dRays.need(n * sizeof(RTCRayHit)));
       uint32_t* dof = static_cast<uint32_t*>(dOff.need((n + 1) * 4));
       uint32_t* dix = static_cast<uint32_t*>(dIdx.need(std::max<size_t>(idx.size(), 1) * 4));
@@ -978,6 +996,7 @@ void trace_filtered(SceneImpl* s, void* recs, const int* valid, int K, size_t M,
       cuda_check(cudaMemcpyAsync(pass.data(), dr, n * sizeof(RTCRayHit), cudaMemcpyDeviceToHost, st), "D2H rays");
       cuda_check(cudaMemcpyAsync(win.data(), dwn, n * 4, cudaMemcpyDeviceToHost, st), "D2H winning records");
       cuda_check(cudaStreamSynchronize(st), "trace");
+      }
       next.clear();
       for (size_t j = 0; j < n; ++j) {
         RTCRayHit& r = pass[j];
