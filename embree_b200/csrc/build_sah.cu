@@ -389,11 +389,10 @@ __global__ void __launch_bounds__(NT* GROUPS) sah_group_kernel(const SahTask* __
 __global__ void sah_large_setup(const SahTask* __restrict__ tasks, uint32_t ntasks, LargeScratch* scr, uint32_t* chunk_task,
                                 SahCounters* ctr) {
   // single CTA: clear scratch, assign chunk ranges
-  __shared__ uint32_t total;
   if (threadIdx.x == 0) {
     uint32_t run = 0;
     for (uint32_t t = 0; t < ntasks; ++t) { scr[t].chunk0 = run; run += (tasks[t].end - tasks[t].begin + kChunk - 1) / kChunk; }
-    total = run; ctr->n_chunks = run;
+    ctr->n_chunks = run;
   }
   __syncthreads();
   for (uint32_t t = 0; t < ntasks; ++t) {

@@ -1034,7 +1034,6 @@ QueryArgs device_args(SceneImpl* s, const Args* a, int occluded) {
   return q;
 }
 
-size_t rec_bytes(int K, int occluded) { return (size_t)(occluded ? 12 : 21) * 4 * K + (K == 1 && !occluded ? 12 : 0); }
 
 }  // namespace
 
