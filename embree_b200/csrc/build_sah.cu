@@ -409,7 +409,6 @@ __global__ void sah_large_setup(const SahTask* __restrict__ tasks, uint32_t ntas
     const uint32_t nch = (tasks[t].end - tasks[t].begin + kChunk - 1) / kChunk;
     for (uint32_t c = threadIdx.x; c < nch; c += blockDim.x) chunk_task[s.chunk0 + c] = t;
   }
-  (void)total;
 }
 
 __global__ void __launch_bounds__(256) sah_large_bin(const SahTask* __restrict__ tasks, const uint32_t* __restrict__ chunk_task,
