@@ -169,6 +169,9 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
 #ifndef RTK_LANE_SMEM
 #define RTK_LANE_SMEM 1    // per-lane state that only the hit update and the write-back touch (u, v, winning record, ray index)
 #endif                     // lives in shared memory instead of registers
+#ifndef RTK_CHILD_PREFETCH
+#define RTK_CHILD_PREFETCH 0   // EXPERIMENT: when a node step leaves two or more internal children pending, prefetch them into L2 (they will all be
+#endif                         // fetched: there is no pop-time culling).  1 = one TMA bulk prefetch of the node's child block, 2 = prefetch.global.L2 of the next sibling
 #ifndef RTK_TRI2
 #define RTK_TRI2 1   // a lane with two or more pending triangles tests two per triangle step (both records fetched together)
 #endif
@@ -569,6 +572,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
       ngy = (hm & 0xFF000000u) | (nw.w[3] >> 24);
       tgx = nw.w[5];
       tgy = hm & 0x00FFFFFFu;
+#if RTK_CHILD_PREFETCH == 1
+      {
+        const uint32_t pend = ngy >> 24;
+        if (pend & (pend - 1u)) tma_prefetch_l2(reinterpret_cast<const char*>(nodes) + (size_t)ngx * sizeof(Node8), (uint32_t)__popc(ngy & 0xFFu) * (uint32_t)sizeof(Node8));
+      }
+#elif RTK_CHILD_PREFETCH == 2
+      {
+        const uint32_t pend = ngy >> 24;
+        if (pend & (pend - 1u)) {   // the sibling that will be popped after the first child's subtree
+          const int b2 = 31 - __clz((int)(ngy & ~(1u << (31 - __clz((int)ngy)))));
+          const uint32_t slot2 = ((uint32_t)(b2 - 24)) ^ (7u - oct);
+          const char* a2 = reinterpret_cast<const char*>(nodes) + (size_t)(ngx + (uint32_t)__popc(ngy & 0xFFu & ((1u << slot2) - 1u))) * sizeof(Node8);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a2));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a2 + 64));
+        }
+      }
+#endif
     }
     // ---- 3. triangle step, batched across the warp
     const unsigned tri_lanes = __ballot_sync(FULL, tracing && tgy != 0);
