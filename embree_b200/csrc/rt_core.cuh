@@ -377,31 +377,23 @@ RT_HD bool curve_test(float ox, float oy, float oz, float dx, float dy, float dz
   return true;
 }
 
-struct RaySpace { float ax, ay, az, bx, by, bz, zx, zy, zz, depth_scale; };
-// CurvePrecalculations1 (curve_intersector_precalculations.h:15-28): per RAY, so the trace kernel computes it once when it loads a ray
-// (three IEEE square roots and divisions) and the flat curve tests take it as an argument
-RT_HD RaySpace curve_ray_space(float dx_, float dy_, float dz_) {
-  RaySpace q;
-  q.depth_scale = rcp_rn(sqrtf(dot3(dx_, dy_, dz_, dx_, dy_, dz_)));
-  const float Nx = mul_rn(q.depth_scale, dx_), Ny = mul_rn(q.depth_scale, dy_), Nz = mul_rn(q.depth_scale, dz_);
-  const bool first = dot3(0.0f, Nz, -Ny, 0.0f, Nz, -Ny) > dot3(-Nz, 0.0f, Nx, -Nz, 0.0f, Nx);
-  const float sx = first ? 0.0f : -Nz, sy = first ? Nz : 0.0f, sz = first ? -Ny : Nx;
-  const float il = rcp_rn(sqrtf(dot3(sx, sy, sz, sx, sy, sz)));
-  q.ax = mul_rn(sx, il); q.ay = mul_rn(sy, il); q.az = mul_rn(sz, il);
-  float bx = msub(Ny, q.az, mul_rn(Nz, q.ay)), by = msub(Nz, q.ax, mul_rn(Nx, q.az)), bz = msub(Nx, q.ay, mul_rn(Ny, q.ax));
-  const float jl = rcp_rn(sqrtf(dot3(bx, by, bz, bx, by, bz)));
-  q.bx = mul_rn(bx, jl); q.by = mul_rn(by, jl); q.bz = mul_rn(bz, jl);
-  q.zx = mul_rn(Nx, q.depth_scale); q.zy = mul_rn(Ny, q.depth_scale); q.zz = mul_rn(Nz, q.depth_scale);
-  return q;
-}
-
 // flat linear curve segment (RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE): FlatLinearCurveIntersector1::intersect
 // (kernels/geometry/line_intersector.h:38-89) with CurvePrecalculations1 (curve_intersector_precalculations.h:15-28) restated
 // for one segment -- a ray-facing ribbon: the end points go to ray space (frame of the normalised direction, z = ray
 // parameter), the closest point of the projected segment to the origin decides.  Explicitly rounded like curve_test.
-RT_HD bool flat_curve_test_rs(const RaySpace& rs, float ox, float oy, float oz, float tnear, float tfar, const CurveVtx& v0, const CurveVtx& v1, CurveHit& h) {
-  const float depth_scale = rs.depth_scale;
-  const float ax = rs.ax, ay = rs.ay, az = rs.az, bx = rs.bx, by = rs.by, bz = rs.bz, zx = rs.zx, zy = rs.zy, zz = rs.zz;   // frame(N) rows dx, dy, vz
+RT_HD bool flat_curve_test(float ox, float oy, float oz, float dx_, float dy_, float dz_, float tnear, float tfar, const CurveVtx& v0,
+                           const CurveVtx& v1, CurveHit& h) {
+  const float depth_scale = rcp_rn(sqrtf(dot3(dx_, dy_, dz_, dx_, dy_, dz_)));
+  const float Nx = mul_rn(depth_scale, dx_), Ny = mul_rn(depth_scale, dy_), Nz = mul_rn(depth_scale, dz_);
+  // frame(N) (linearspace3.h:117-124): dx0 = (0, N.z, -N.y), dx1 = (-N.z, 0, N.x)
+  const bool first = dot3(0.0f, Nz, -Ny, 0.0f, Nz, -Ny) > dot3(-Nz, 0.0f, Nx, -Nz, 0.0f, Nx);
+  const float sx = first ? 0.0f : -Nz, sy = first ? Nz : 0.0f, sz = first ? -Ny : Nx;
+  const float il = rcp_rn(sqrtf(dot3(sx, sy, sz, sx, sy, sz)));
+  const float ax = mul_rn(sx, il), ay = mul_rn(sy, il), az = mul_rn(sz, il);                                  // dx
+  float bx = msub(Ny, az, mul_rn(Nz, ay)), by = msub(Nz, ax, mul_rn(Nx, az)), bz = msub(Nx, ay, mul_rn(Ny, ax));   // cross(N, dx)
+  const float jl = rcp_rn(sqrtf(dot3(bx, by, bz, bx, by, bz)));
+  bx = mul_rn(bx, jl); by = mul_rn(by, jl); bz = mul_rn(bz, jl);                                              // dy
+  const float zx = mul_rn(Nx, depth_scale), zy = mul_rn(Ny, depth_scale), zz = mul_rn(Nz, depth_scale);      // vz
   const float a0 = sub_rn(v0.x, ox), a1 = sub_rn(v0.y, oy), a2 = sub_rn(v0.z, oz);
   const float c0 = sub_rn(v1.x, ox), c1 = sub_rn(v1.y, oy), c2 = sub_rn(v1.z, oz);
   const float p0x = dot3(a0, a1, a2, ax, ay, az), p0y = dot3(a0, a1, a2, bx, by, bz), p0z = dot3(a0, a1, a2, zx, zy, zz);
@@ -417,10 +409,6 @@ RT_HD bool flat_curve_test_rs(const RaySpace& rs, float ox, float oy, float oz, 
   if (!((Tx != 0.0f) | (Ty != 0.0f) | (Tz != 0.0f))) return false;     // denormalised segment
   h.t = t; h.u = u; h.ngx = Tx; h.ngy = Ty; h.ngz = Tz;
   return true;
-}
-RT_HD bool flat_curve_test(float ox, float oy, float oz, float dx_, float dy_, float dz_, float tnear, float tfar, const CurveVtx& v0,
-                           const CurveVtx& v1, CurveHit& h) {
-  return flat_curve_test_rs(curve_ray_space(dx_, dy_, dz_), ox, oy, oz, tnear, tfar, v0, v1, h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -493,6 +481,23 @@ RT_HD void curve_basis_table(uint32_t basis, int n, float* tab) {
   }
 }
 
+struct RaySpace { float ax, ay, az, bx, by, bz, zx, zy, zz, depth_scale; };
+// CurvePrecalculations1 (curve_intersector_precalculations.h:15-28); same operations as in flat_curve_test above
+RT_HD RaySpace curve_ray_space(float dx_, float dy_, float dz_) {
+  RaySpace q;
+  q.depth_scale = rcp_rn(sqrtf(dot3(dx_, dy_, dz_, dx_, dy_, dz_)));
+  const float Nx = mul_rn(q.depth_scale, dx_), Ny = mul_rn(q.depth_scale, dy_), Nz = mul_rn(q.depth_scale, dz_);
+  const bool first = dot3(0.0f, Nz, -Ny, 0.0f, Nz, -Ny) > dot3(-Nz, 0.0f, Nx, -Nz, 0.0f, Nx);
+  const float sx = first ? 0.0f : -Nz, sy = first ? Nz : 0.0f, sz = first ? -Ny : Nx;
+  const float il = rcp_rn(sqrtf(dot3(sx, sy, sz, sx, sy, sz)));
+  q.ax = mul_rn(sx, il); q.ay = mul_rn(sy, il); q.az = mul_rn(sz, il);
+  float bx = msub(Ny, q.az, mul_rn(Nz, q.ay)), by = msub(Nz, q.ax, mul_rn(Nx, q.az)), bz = msub(Nx, q.ay, mul_rn(Ny, q.ax));
+  const float jl = rcp_rn(sqrtf(dot3(bx, by, bz, bx, by, bz)));
+  q.bx = mul_rn(bx, jl); q.by = mul_rn(by, jl); q.bz = mul_rn(bz, jl);
+  q.zx = mul_rn(Nx, q.depth_scale); q.zy = mul_rn(Ny, q.depth_scale); q.zz = mul_rn(Nz, q.depth_scale);
+  return q;
+}
+
 // weighted sum of the four control values: madd(c0, v0, madd(c1, v1, madd(c2, v2, c3 * v3))) (bezier_curve.h:512-526)
 RT_HD float curve_blend(const float* w, int stride, float v0, float v1, float v2, float v3) {
   return fma_rn(w[0], v0, fma_rn(w[stride], v1, fma_rn(w[2 * stride], v2, mul_rn(w[3 * stride], v3))));
@@ -502,8 +507,9 @@ RT_HD float curve_blend(const float* w, int stride, float v0, float v1, float v2
 // primitive (tight boxes around thin diagonal ribbons instead of one box per curve -- the job the reference gives to its
 // oriented-bounds hair BVH), and the closest hit over the segments is the closest hit of the curve.  seg < 0: all of them
 // (the host instantiation the tests compare with the oracle).
-RT_HD bool flat_cubic_test_rs(const RaySpace& rs, float ox, float oy, float oz, float tnear, float tfar, const CurveVtx cp[4],
-                              uint32_t basis, int N, const float* tab, CurveHit& h, int seg = -1) {
+RT_HD bool flat_cubic_test(float ox, float oy, float oz, float dx_, float dy_, float dz_, float tnear, float tfar, const CurveVtx cp[4],
+                           uint32_t basis, int N, const float* tab, CurveHit& h, int seg = -1) {
+  const RaySpace rs = curve_ray_space(dx_, dy_, dz_);
   // control points in ray space (xfm_pr, bezier_curve.h:216-223); w = radius
   float qx[4], qy[4], qz[4], qw[4];
   float amax = 0.0f;
@@ -585,10 +591,6 @@ RT_HD bool flat_cubic_test_rs(const RaySpace& rs, float ox, float oy, float oz, 
   h.ngy = fma_rn(b[0], cp[0].y, fma_rn(b[1], cp[1].y, fma_rn(b[2], cp[2].y, mul_rn(b[3], cp[3].y))));
   h.ngz = fma_rn(b[0], cp[0].z, fma_rn(b[1], cp[1].z, fma_rn(b[2], cp[2].z, mul_rn(b[3], cp[3].z))));
   return true;
-}
-RT_HD bool flat_cubic_test(float ox, float oy, float oz, float dx_, float dy_, float dz_, float tnear, float tfar, const CurveVtx cp[4],
-                           uint32_t basis, int N, const float* tab, CurveHit& h, int seg = -1) {
-  return flat_cubic_test_rs(curve_ray_space(dx_, dy_, dz_), ox, oy, oz, tnear, tfar, cp, basis, N, tab, h, seg);
 }
 
 // ------------------------------------------------------------------------------------------------

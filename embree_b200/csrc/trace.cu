@@ -119,24 +119,17 @@ __device__ __noinline__ bool round_record_test(const GeomDesc& d, const Ray& r, 
   load_cubic_cp(d, vid, cp);
   return round_cubic_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, cp, d.basis, h, lane);
 }
-// `rsp`: this lane's ray-space frame (CurvePrecalculations1), ten floats kept in shared memory since the ray was loaded ([k * TRACE_THREADS])
-__device__ __noinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h,
-                                               const float* rsp) {
+__device__ __noinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h) {
   if (d.is_curve == 4) return round_record_test(d, r, tfar, c.z, (int)c.x, h);   // c.x: this record's first-level sub-segment
-  RaySpace rs;
-  if (d.is_curve >= 2) {
-    rs.ax = rsp[0]; rs.ay = rsp[128]; rs.az = rsp[256]; rs.bx = rsp[384]; rs.by = rsp[512]; rs.bz = rsp[640];
-    rs.zx = rsp[768]; rs.zy = rsp[896]; rs.zz = rsp[1024]; rs.depth_scale = rsp[1152];
-  }
   if (d.is_curve == 3) {   // flat cubic curve (Bezier / B-spline / Catmull-Rom / Hermite): control points from the resident vertex buffer
     CurveVtx cp[4];
     load_cubic_cp(d, c.z, cp);
-    return flat_cubic_test_rs(rs, r.ox, r.oy, r.oz, r.tnear, tfar, cp, d.basis, (int)d.tess, d.basis_tab, h, (int)c.x);   // c.x: this record's segment
+    return flat_cubic_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, cp, d.basis, (int)d.tess, d.basis_tab, h, (int)c.x);   // c.x: this record's segment
   }
   const CurveVtx v0{__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(c.x)};
   const CurveVtx v1{__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.y)};
   if (d.is_curve == 2)   // RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE: ray-facing ribbon, no neighbours involved
-    return flat_curve_test_rs(rs, r.ox, r.oy, r.oz, r.tnear, tfar, v0, v1, h);
+    return flat_curve_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, v0, v1, h);
   const uint32_t vid = c.z & 0x3FFFFFFFu;
   const bool hasL = (c.z >> 30) & 1u, hasR = (c.z >> 31) & 1u;
   CurveVtx vL = v0, vR = v1;
@@ -154,7 +147,6 @@ __device__ __forceinline__ void store_256(void* dst, float a0, float a1, float a
 
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_WARPS = TRACE_THREADS / 32;
-static_assert(TRACE_THREADS == 128, "curve_record_test reads the per-lane ray-space frame with a stride of 128 floats");
 
 // ---- TMA bulk prefetch of one 32-ray block (1.5 .. 3 KB contiguous) into L2 ------------------------------------------
 // Staging the blocks in shared memory (cp.async.bulk.shared + mbarrier) was measured SLOWER (1012 vs 1380 Mrays/s):
@@ -241,9 +233,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
 #if RTK_LANE_SMEM
   // GENERAL == 2 (curve scenes): 9-11 the normal of a curve hit -- the round cubic test is an iteration whose result depends on
   // the tfar it was started with, so the normal is kept from the winning test instead of re-running the test at write-back
-  // 12-21 (GENERAL == 2): the ray-space frame of the flat curve tests (CurvePrecalculations1: three IEEE square roots and divisions), computed
-  // once when the ray is loaded instead of once per curve test
-  __shared__ uint32_t s_lane[GENERAL == 2 ? 22 : 9][TRACE_THREADS];   // 0 u, 1 v, 2 winning record, 3 ray index, 4-6 ray direction, 7 ray mask, 8 the ray's own tfar
+  __shared__ uint32_t s_lane[GENERAL == 2 ? 12 : 9][TRACE_THREADS];   // 0 u, 1 v, 2 winning record, 3 ray index, 4-6 ray direction, 7 ray mask, 8 the ray's own tfar
 #define hit_u (reinterpret_cast<float*>(s_lane[0])[threadIdx.x])
 #define hit_v (reinterpret_cast<float*>(s_lane[1])[threadIdx.x])
 #define hit_tri (s_lane[2][threadIdx.x])
@@ -418,7 +408,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
       const GeomDesc& d = p.descs[b.w];
       if (GENERAL == 2 && d.is_curve) {   // RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE: cone-sphere test, u along the segment, v = 0
         CurveHit ch;
-        if (visible && curve_record_test(d, wr, tfar_tri, a, b, c, ch, reinterpret_cast<const float*>(&s_lane[GENERAL == 2 ? 12 : 0][threadIdx.x]))) {
+        if (visible && curve_record_test(d, wr, tfar_tri, a, b, c, ch)) {
           found = true;
           if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
           else {
@@ -538,12 +528,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
               const bool go = p.root_valid && !(OCCLUDED && r.tfar < 0.0f);
               RAY_DX(threadIdx.x) = r.dx; RAY_DY(threadIdx.x) = r.dy; RAY_DZ(threadIdx.x) = r.dz;
               RAY_MASK(threadIdx.x) = r.mask; RAY_TFAR(threadIdx.x) = r.tfar;
-              if (GENERAL == 2) {
-                const RaySpace rs = curve_ray_space(r.dx, r.dy, r.dz);
-                float* q = reinterpret_cast<float*>(&s_lane[GENERAL == 2 ? 12 : 0][threadIdx.x]);
-                q[0] = rs.ax; q[128] = rs.ay; q[256] = rs.az; q[384] = rs.bx; q[512] = rs.by; q[640] = rs.bz;
-                q[768] = rs.zx; q[896] = rs.zy; q[1024] = rs.zz; q[1152] = rs.depth_scale;
-              }
               idx = rcp_safe_fast(r.dx); idy = rcp_safe_fast(r.dy); idz = rcp_safe_fast(r.dz);
               oct = (idx < 0.0f ? 1u : 0u) | (idy < 0.0f ? 2u : 0u) | (idz < 0.0f ? 4u : 0u);
               tfar_tri = r.tfar;
