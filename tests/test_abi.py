@@ -26,6 +26,15 @@ int main(void) {
     sizeof(struct RTCBounds), sizeof(struct RTCIntersectArguments), sizeof(struct RTCRayQueryContext));
   printf("%d %d %d %d %d %d\n", (int)RTC_FORMAT_FLOAT3, (int)RTC_FORMAT_UINT3, (int)RTC_BUFFER_TYPE_VERTEX,
     (int)RTC_ERROR_INVALID_OPERATION, (int)RTC_RAY_QUERY_FLAG_COHERENT, (int)RTC_DEVICE_PROPERTY_RAY_MASK_SUPPORTED);
+  /* callback / interpolation argument blocks and the curve, filter and tangent enumerators added in round 2 */
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(struct RTCFilterFunctionNArguments), offsetof(struct RTCFilterFunctionNArguments, hit),
+    offsetof(struct RTCFilterFunctionNArguments, N), sizeof(struct RTCInterpolateArguments), offsetof(struct RTCInterpolateArguments, P),
+    sizeof(struct RTCInterpolateNArguments), offsetof(struct RTCInterpolateNArguments, valueCount));
+  printf("%d %d %d %d %d %d %d %d %d %d %d %d\n", (int)RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE, (int)RTC_GEOMETRY_TYPE_ROUND_BEZIER_CURVE,
+    (int)RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE, (int)RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE, (int)RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE,
+    (int)RTC_GEOMETRY_TYPE_ROUND_HERMITE_CURVE, (int)RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE, (int)RTC_GEOMETRY_TYPE_ROUND_CATMULL_ROM_CURVE,
+    (int)RTC_BUFFER_TYPE_TANGENT, (int)RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER, (int)RTC_FEATURE_FLAG_FLAT_BEZIER_CURVE,
+    (int)RTC_FEATURE_FLAG_ROUND_CATMULL_ROM_CURVE);
   return 0;
 }
 """
