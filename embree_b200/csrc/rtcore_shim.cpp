@@ -1565,6 +1565,7 @@ int rtcb200SetTuning(const char* key, int value) {
   else if (!strcmp(key, "blocks_per_sm")) t.blocks_per_sm = value;
   else if (!strcmp(key, "use_tma")) t.use_tma = value;
   else if (!strcmp(key, "tri_spread")) t.tri_spread = value != 0;
+  else if (!strcmp(key, "tri_spread_occluded")) t.tri_spread_occluded = value != 0;
   else if (!strcmp(key, "gather_mode") && value >= 0 && value <= 1) t.gather_mode = value;
   else if (!strcmp(key, "host_d2h_partial")) g_host_d2h_partial = value != 0;
   else if (!strcmp(key, "host_chunk_log2") && value >= 10 && value <= 26) g_host_chunk_log2 = value;

@@ -154,6 +154,7 @@ struct Tuning {
   int refill_min = 4;
   int gather_mode = 1;       // fused hit gather: 0 = one 256-bit store per record, 1 = blocks staged in shared memory, 1 KB stores
   int tri_spread = 1;        // warp-wide triangle redistribution in the trace kernel (trace.cu SPREAD; closest-hit triangle scenes)
+  int tri_spread_occluded = 1;   // the same redistribution in the any-hit kernels (a hit ends the owner's ray)
   int sah_small = 4;         // SAH builder: segments of <= this many primitives are split in the middle (no binning)
 };
 Tuning& tuning();

@@ -649,6 +649,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
           if ((c.w & o_mask) != 0 &&
               tri_test(lr, o_tfar, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(b.x),
                        __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z), th)) {
+            if (OCCLUDED) {   // any hit: one accepted triangle terminates the owner's ray (bvh_intersector1.cpp:186-188)
+              s_best[wi][owner] = 0ull;
+            } else {
             const float rcpAbsDen = 1.0f / th.absDen;
             const float t = th.T * rcpAbsDen;
             if (t <= o_best) {
@@ -658,6 +661,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
               key = ((unsigned long long)tb32 << 32) | (uint32_t)(31 - lane);
               atomicMin(&s_best[wi][owner], key);
             }
+            }
           }
         }
         __syncwarp();
@@ -665,7 +669,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         const bool got = isT && best != ~0ull;
         const int win = got ? 31 - (int)(best & 31ull) : lane;  // worker lane that holds the winning item
         const float b_u = __shfl_sync(FULL, w_u, win), b_v = __shfl_sync(FULL, w_v, win);
-        if (got) {
+        if (got && OCCLUDED) { found = true; ngy = 0; tgy = 0; sp = 0; top_y = 0; }
+        else if (got) {
           uint32_t tb32 = (uint32_t)(best >> 32);
           tb32 ^= (tb32 >> 31) ? 0x80000000u : 0xFFFFFFFFu;     // inverse of the transform above
           tfar_tri = __uint_as_float(tb32);
@@ -812,9 +817,9 @@ static int launch_k(TraceParams p, cudaStream_t st) {
     return (int)cudaGetLastError();
   }
   const int gather = (CAN_GATHER && p.compact_out) ? ((g_tuning.gather_mode == 0 || !p.stage) ? 1 : 2) : 0;
-  const bool spread = CLOSEST && g_tuning.tri_spread && !p.robust && !p.descs;
+  const bool spread = (CLOSEST ? g_tuning.tri_spread : g_tuning.tri_spread_occluded) && !p.robust && !p.descs;
   switch (variant + 8 * gather + (spread ? 32 : 0)) {
-#define RTK_LAUNCH(ST, RB, IN, GA, SP) trace_kernel<K, OCCLUDED, ST, RB, (IN ? 1 : 0), (CAN_GATHER ? GA : 0), (CLOSEST && SP)><<<blocks, TRACE_THREADS, 0, st>>>(p); break
+#define RTK_LAUNCH(ST, RB, IN, GA, SP) trace_kernel<K, OCCLUDED, ST, RB, (IN ? 1 : 0), (CAN_GATHER ? GA : 0), SP><<<blocks, TRACE_THREADS, 0, st>>>(p); break
 #define RTK_LAUNCH8(GA)                                          \
     case 8 * GA + 0: RTK_LAUNCH(false, false, false, GA, false); \
     case 8 * GA + 1: RTK_LAUNCH(false, false, true, GA, false);  \
