@@ -251,6 +251,22 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
         }
         ok &= (lo[0] > -kFltLarge) & (hi[0] < kFltLarge) & (lo[1] > -kFltLarge) & (hi[1] < kFltLarge) & (lo[2] > -kFltLarge) & (hi[2] < kFltLarge);
       }
+    } else if (geoms[g].is_curve >= 5) {   // point primitives (Points::valid + bounds, scene_points.h:146-199): centre -+ radius
+      const uint32_t lp = p - offs[g];
+      const float* q = reinterpret_cast<const float*>(geoms[g].verts + (uint64_t)lp * geoms[g].vstride);
+      const float c[4] = {q[0], q[1], q[2], q[3]};
+      ok = lp < geoms[g].nverts;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ok &= (c[k] > -kFltLarge) & (c[k] < kFltLarge);
+      ok &= c[3] >= 0.0f;
+      if (ok) {
+        const float rp = __fmul_ru(c[3], 1.000001f);   // the test's own rounding can accept a point a few ulp of the radius outside the exact sphere
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          lo[a] = __fsub_rd(c[a], rp); hi[a] = __fadd_ru(c[a], rp);
+          lo[a] -= fabsf(lo[a]) * 2.4e-7f; hi[a] += fabsf(hi[a]) * 2.4e-7f;
+        }
+      }
     } else if (geoms[g].is_curve) {   // merge(p0, p1) enlarged by the larger radius; two extra ulp of the magnitudes keep it conservative
       float4 c0, c1;
       uint32_t vid;
@@ -605,6 +621,20 @@ __global__ void __launch_bounds__(256) leaf_pack(const GeomDesc* __restrict__ ge
     dst[0] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(curve));
     dst[1] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float((uint32_t)g));
     dst[2] = make_float4(__uint_as_float(seg), 0.0f, __uint_as_float(vid), __uint_as_float(gd.mask));
+    return;
+  }
+  if (gd.is_curve >= 5) {   // point record: a = (centre, primID), b = (normal of an oriented disc, descriptor), c = (radius, -, -, mask)
+    const uint32_t lp = p - offs[g];
+    const float* q = reinterpret_cast<const float*>(gd.verts + (uint64_t)lp * gd.vstride);
+    float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+    if (gd.is_curve == 7) {
+      const float* n = reinterpret_cast<const float*>(gd.tangents + (uint64_t)lp * gd.tstride);
+      nx = n[0]; ny = n[1]; nz = n[2];
+    }
+    float4* dst = reinterpret_cast<float4*>(&out[t]);
+    dst[0] = make_float4(q[0], q[1], q[2], __uint_as_float(lp));
+    dst[1] = make_float4(nx, ny, nz, __uint_as_float((uint32_t)g));
+    dst[2] = make_float4(q[3], 0.0f, 0.0f, __uint_as_float(gd.mask));
     return;
   }
   if (gd.is_curve) {   // curve record: a = (p0.xyz, primID), b = (p1.xyz, descriptor), c = (r0, r1, first vertex | flags << 30, mask)

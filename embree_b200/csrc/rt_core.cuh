@@ -412,6 +412,45 @@ RT_HD bool flat_curve_test(float ox, float oy, float oz, float dx_, float dy_, f
 }
 
 // ------------------------------------------------------------------------------------------------
+// point primitives (RTC_GEOMETRY_TYPE_SPHERE_POINT / _DISC_POINT / _ORIENTED_DISC_POINT): SphereIntersector1
+// (kernels/geometry/sphere_intersector.h:76-140), DiscIntersector1 ray-facing (disc_intersector.h:85-131) and oriented
+// (:133-170) restated for one point.  kind: 0 sphere, 1 ray-facing disc, 2 oriented disc (n = its normal).  u = v = 0.
+// Without a filter callback the sphere's back hit is only ever offered when it does not lie behind the accepted front hit,
+// so the first valid hit is the result.  Explicitly rounded like the curve tests: bit-identical to oracle point_intersect.
+RT_HD bool point_test(float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar, float cx, float cy, float cz,
+                      float radius, float nx, float ny, float nz, int kind, CurveHit& h) {
+  h.u = 0.0f; h.v = 0.0f;
+  const float c0x = sub_rn(cx, ox), c0y = sub_rn(cy, oy), c0z = sub_rn(cz, oz);
+  if (kind == 2) {
+    const float divisor = dot3(dx, dy, dz, nx, ny, nz);
+    if (divisor == 0.0f) return false;
+    const float t = dot3(c0x, c0y, c0z, nx, ny, nz) / divisor;
+    if (!((tnear <= t) & (t <= tfar))) return false;
+    const float qx = sub_rn(fma_rn(dx, t, ox), cx), qy = sub_rn(fma_rn(dy, t, oy), cy), qz = sub_rn(fma_rn(dz, t, oz), cz);
+    if (!(dot3(qx, qy, qz, qx, qy, qz) < mul_rn(radius, radius))) return false;
+    h.t = t; h.ngx = nx; h.ngy = ny; h.ngz = nz;
+    return true;
+  }
+  const float rd2 = rcp_rn(dot3(dx, dy, dz, dx, dy, dz));
+  const float projC0 = mul_rn(dot3(c0x, c0y, c0z, dx, dy, dz), rd2);
+  if (kind == 1 && !((tnear <= projC0) & (projC0 <= tfar))) return false;
+  const float px = fma_rn(-projC0, dx, c0x), py = fma_rn(-projC0, dy, c0y), pz = fma_rn(-projC0, dz, c0z);
+  const float l2 = dot3(px, py, pz, px, py, pz), r2 = mul_rn(radius, radius);
+  if (!(l2 <= r2)) return false;
+  if (kind == 1) {
+    h.t = projC0; h.ngx = -dx; h.ngy = -dy; h.ngz = -dz;
+    return true;
+  }
+  const float td = sqrtf(mul_rn(sub_rn(r2, l2), rd2)), t_front = sub_rn(projC0, td), t_back = add_rn(projC0, td);
+  const bool front = (tnear <= t_front) & (t_front <= tfar), back = (tnear <= t_back) & (t_back <= tfar);
+  if (!(front | back)) return false;
+  const float s = front ? -td : td;
+  h.t = front ? t_front : t_back;
+  h.ngx = fma_rn(s, dx, -px); h.ngy = fma_rn(s, dy, -py); h.ngz = fma_rn(s, dz, -pz);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // flat cubic curves (RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE / _BSPLINE_ / _CATMULL_ROM_ / _HERMITE_): intersect_ribbon
 // (kernels/geometry/curve_intersector_ribbon.h:73-190) restated for one curve.  The curve is tessellated into N =
 // tessellation rate segments at u = j / N; the control points go to ray space (CurvePrecalculations1: frame of the

@@ -136,6 +136,7 @@ bool is_cubic_curve(RTCGeometryType t) {
   return t == RTC_GEOMETRY_TYPE_FLAT_BEZIER_CURVE || t == RTC_GEOMETRY_TYPE_FLAT_BSPLINE_CURVE || t == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE ||
          t == RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE || is_round_cubic(t);
 }
+bool is_point(RTCGeometryType t) { return t == RTC_GEOMETRY_TYPE_SPHERE_POINT || t == RTC_GEOMETRY_TYPE_DISC_POINT || t == RTC_GEOMETRY_TYPE_ORIENTED_DISC_POINT; }
 bool is_hermite(RTCGeometryType t) { return t == RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE || t == RTC_GEOMETRY_TYPE_ROUND_HERMITE_CURVE; }
 // number of live geometries that have a filter callback or accept the arguments' filter: while it is zero (and the
 // query carries no filter) no query looks at the geometries at all
@@ -397,7 +398,41 @@ void commit_scene(SceneImpl* s) {
     d.geomID = geomID; d.mask = g->mask; d.is_curve = round ? 4 : 3;
     descs.push_back(d);
   };
+  // point primitives (scene_points.cpp): float4 vertices (centre, radius), one primitive per vertex; oriented discs carry one
+  // float3 normal per vertex (GeomDesc.tangents / tstride hold that buffer).  They share the curve kernels (GENERAL == 2).
+  auto add_points = [&](GeometryImpl* g, uint32_t geomID) {
+    const size_t n = g->vertices.count;
+    if (n == 0 || !g->vertices.buf) return;
+    const bool oriented = g->type == RTC_GEOMETRY_TYPE_ORIENTED_DISC_POINT;
+    if (oriented && !g->tangents.buf) fail(RTC_ERROR_INVALID_OPERATION, "normal buffer not set");
+    if (oriented && g->tangents.count != n) fail(RTC_ERROR_INVALID_OPERATION, "number of normals must match number of vertices");
+    if (n > 0x7FFFFFFFull) fail(RTC_ERROR_INVALID_OPERATION, "point geometry too large");
+    curves = true;
+    const size_t vbytes = (n - 1) * g->vertices.stride + 16;
+    void *dv = nullptr, *dn = nullptr;
+    cuda_check(cudaMallocAsync(&dv, vbytes, 0), "cudaMallocAsync(point vertices)");
+    s->deviceBuffers.push_back(dv);
+    cuda_check(cudaMemcpyAsync(dv, g->vertices.data(), vbytes, cudaMemcpyHostToDevice, 0), "upload point vertices");
+    rtk::GeomDesc d;
+    if (oriented) {
+      const size_t nbytes = (n - 1) * g->tangents.stride + 12;
+      cuda_check(cudaMallocAsync(&dn, nbytes, 0), "cudaMallocAsync(point normals)");
+      s->deviceBuffers.push_back(dn);
+      cuda_check(cudaMemcpyAsync(dn, g->tangents.data(), nbytes, cudaMemcpyHostToDevice, 0), "upload point normals");
+      d.tangents = static_cast<const uint8_t*>(dn); d.tstride = g->tangents.stride;
+    }
+    d.verts = static_cast<const uint8_t*>(dv); d.vstride = g->vertices.stride;
+    d.nverts = (uint32_t)n; d.ntris = (uint32_t)n;
+    d.geomID = geomID; d.mask = g->mask;
+    d.is_curve = g->type == RTC_GEOMETRY_TYPE_SPHERE_POINT ? 5 : g->type == RTC_GEOMETRY_TYPE_DISC_POINT ? 6 : 7;
+    descs.push_back(d);
+  };
   auto add_mesh = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
+    if (is_point(g->type)) {
+      if (xfm) fail(RTC_ERROR_INVALID_OPERATION, "instanced point geometries are not supported by the B200 back-end");
+      add_points(g, geomID);
+      return;
+    }
     if (is_linear_curve(g->type) || is_cubic_curve(g->type)) {
       if (xfm) fail(RTC_ERROR_INVALID_OPERATION, "instanced curve geometries are not supported by the B200 back-end");
       if (is_cubic_curve(g->type)) add_cubic(g, geomID); else add_curves(g, geomID);
@@ -1108,7 +1143,7 @@ ssize_t rtcGetDeviceProperty(RTCDevice h, enum RTCDeviceProperty prop) {
     case RTC_DEVICE_PROPERTY_CURVE_GEOMETRY_SUPPORTED: return 1;   // round linear curves
     case RTC_DEVICE_PROPERTY_SUBDIVISION_GEOMETRY_SUPPORTED:
     case RTC_DEVICE_PROPERTY_USER_GEOMETRY_SUPPORTED:
-    case RTC_DEVICE_PROPERTY_POINT_GEOMETRY_SUPPORTED: return 0;
+    case RTC_DEVICE_PROPERTY_POINT_GEOMETRY_SUPPORTED: return 1;   // sphere / disc / oriented disc points
     case RTC_DEVICE_PROPERTY_TASKING_SYSTEM: return 0;
     case RTC_DEVICE_PROPERTY_JOIN_COMMIT_SUPPORTED: return 1;
     case RTC_DEVICE_PROPERTY_PARALLEL_COMMIT_SUPPORTED: return 0;
@@ -1150,8 +1185,8 @@ void rtcReleaseBuffer(RTCBuffer b) { DeviceImpl* d = b ? B(b)->dev : nullptr; AP
 RTCGeometry rtcNewGeometry(RTCDevice h, enum RTCGeometryType type) {
   API_BEGIN
   VERIFY_HANDLE(h);
-  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE && !is_linear_curve(type) && !is_cubic_curve(type))
-    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD, _ROUND / _FLAT_LINEAR_CURVE, _ROUND / _FLAT_BEZIER / _BSPLINE / _HERMITE / _CATMULL_ROM_CURVE and _INSTANCE are supported by the B200 back-end");
+  if (type != RTC_GEOMETRY_TYPE_TRIANGLE && type != RTC_GEOMETRY_TYPE_QUAD && type != RTC_GEOMETRY_TYPE_INSTANCE && !is_linear_curve(type) && !is_cubic_curve(type) && !is_point(type))
+    fail(RTC_ERROR_INVALID_OPERATION, "only RTC_GEOMETRY_TYPE_TRIANGLE, _QUAD, _ROUND / _FLAT_LINEAR_CURVE, _ROUND / _FLAT_BEZIER / _BSPLINE / _HERMITE / _CATMULL_ROM_CURVE, _SPHERE / _DISC / _ORIENTED_DISC_POINT and _INSTANCE are supported by the B200 back-end");
   GeometryImpl* g = new GeometryImpl(D(h));
   g->type = type;
   return reinterpret_cast<RTCGeometry>(g);
@@ -1255,6 +1290,16 @@ static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFo
   // scene_triangle_mesh.cpp:35-80, scene_quad_mesh.cpp:35-80
   if (g->type == RTC_GEOMETRY_TYPE_INSTANCE) fail(RTC_ERROR_INVALID_OPERATION, "operation not supported for this geometry");
   const bool curve = is_linear_curve(g->type) || is_cubic_curve(g->type);   // scene_line_segments.cpp:35-100, scene_curves.cpp:50-140
+  if (type == RTC_BUFFER_TYPE_NORMAL) {   // scene_points.cpp:60-71: oriented discs only
+    if (g->type != RTC_GEOMETRY_TYPE_ORIENTED_DISC_POINT) fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
+    if (((size_t)(buf->ptr) + off) & 3 || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
+    if (format != RTC_FORMAT_FLOAT3) fail(RTC_ERROR_INVALID_OPERATION, "invalid normal buffer format");
+    if (slot != 0) fail(RTC_ERROR_INVALID_OPERATION, "invalid normal buffer slot");
+    g->tangents.set(buf, off, stride, num, format);
+    g->update();
+    return;
+  }
+  if (is_point(g->type) && type == RTC_BUFFER_TYPE_INDEX) fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");   // scene_points.cpp:82
   if (is_hermite(g->type) && type == RTC_BUFFER_TYPE_TANGENT) {
     if (((size_t)(buf->ptr) + off) & 3 || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
     if (format != RTC_FORMAT_FLOAT4) fail(RTC_ERROR_INVALID_OPERATION, "invalid tangent buffer format");
@@ -1273,7 +1318,7 @@ static void set_buffer(GeometryImpl* g, RTCBufferType type, unsigned slot, RTCFo
   if (((size_t)(buf->ptr) + off) & 3 || (stride & 3)) fail(RTC_ERROR_INVALID_OPERATION, "data must be 4 bytes aligned");
   if (num > 0xFFFFFFFFull) fail(RTC_ERROR_INVALID_ARGUMENT, "buffer too large");
   if (type == RTC_BUFFER_TYPE_VERTEX) {
-    if (format != (curve ? RTC_FORMAT_FLOAT4 : RTC_FORMAT_FLOAT3)) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex buffer format");
+    if (format != ((curve || is_point(g->type)) ? RTC_FORMAT_FLOAT4 : RTC_FORMAT_FLOAT3)) fail(RTC_ERROR_INVALID_OPERATION, "invalid vertex buffer format");
     if (stride * num > 16ull * 1024 * 1024 * 1024) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer can be at most 16GB large");
     if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid vertex buffer slot");
     g->vertices.set(buf, off, stride, num, format);
@@ -1330,6 +1375,7 @@ void* rtcGetGeometryBufferData(RTCGeometry g, enum RTCBufferType type, unsigned 
   else if (type == RTC_BUFFER_TYPE_VERTEX) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->vertices; }
   else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) { if (slot >= G(g)->attribs.size()) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->attribs[slot]; }
   else if (type == RTC_BUFFER_TYPE_FLAGS && (G(g)->type == RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE || G(g)->type == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE)) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->flags; }
+  else if ((type == RTC_BUFFER_TYPE_TANGENT && is_hermite(G(g)->type)) || (type == RTC_BUFFER_TYPE_NORMAL && G(g)->type == RTC_GEOMETRY_TYPE_ORIENTED_DISC_POINT)) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); v = &G(g)->tangents; }
   else fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
   return const_cast<char*>(v->data());
   GEOM_END
@@ -1337,7 +1383,7 @@ void* rtcGetGeometryBufferData(RTCGeometry g, enum RTCBufferType type, unsigned 
 }
 void rtcUpdateGeometryBuffer(RTCGeometry g, enum RTCBufferType type, unsigned int slot) {
   GEOM_BEGIN(g)
-  if (type == RTC_BUFFER_TYPE_INDEX || type == RTC_BUFFER_TYPE_VERTEX || type == RTC_BUFFER_TYPE_FLAGS) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); }
+  if (type == RTC_BUFFER_TYPE_INDEX || type == RTC_BUFFER_TYPE_VERTEX || type == RTC_BUFFER_TYPE_FLAGS || type == RTC_BUFFER_TYPE_TANGENT || type == RTC_BUFFER_TYPE_NORMAL) { if (slot != 0) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); }
   else if (type == RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE) { if (slot >= G(g)->attribs.size()) fail(RTC_ERROR_INVALID_ARGUMENT, "invalid buffer slot"); }
   else fail(RTC_ERROR_INVALID_ARGUMENT, "unknown buffer type");
   G(g)->update();

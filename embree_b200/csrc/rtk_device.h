@@ -29,7 +29,8 @@ struct GeomDesc {
   // round linear curves (RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE): verts = float4 (xyz, radius), idx = first vertex of each
   // segment, ntris = segments; `flags` = one neighbour-flag byte per segment (device).  The vertex buffer stays resident
   // after the build: the trace kernel fetches the neighbour vertices from it.
-  uint32_t is_curve = 0;   // 1 round linear (cone-sphere), 2 flat linear (ray-facing ribbon), 3 flat cubic (tessellated ribbon), 4 round cubic (sweep)
+  uint32_t is_curve = 0;   // 1 round linear (cone-sphere), 2 flat linear (ray-facing ribbon), 3 flat cubic (tessellated ribbon), 4 round cubic (sweep),
+                           // 5 sphere point, 6 ray-facing disc point, 7 oriented disc point (normals in `tangents`, stride `tstride`)
   const uint8_t* flags = nullptr;
   // flat cubic curves (RTC_GEOMETRY_TYPE_FLAT_BEZIER / _BSPLINE / _CATMULL_ROM / _HERMITE_CURVE): idx = first of the four
   // control vertices (Hermite: of the two vertex / tangent pairs), `basis` = rt_core.cuh CurveBasis of the control points,

@@ -120,6 +120,9 @@ __device__ __noinline__ bool round_record_test(const GeomDesc& d, const Ray& r, 
   return round_cubic_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, cp, d.basis, h, lane);
 }
 __device__ __noinline__ bool curve_record_test(const GeomDesc& d, const Ray& r, float tfar, const uint4& a, const uint4& b, const uint4& c, CurveHit& h) {
+  if (d.is_curve >= 5)   // point primitives (sphere / ray-facing disc / oriented disc): the record holds everything (build.cu leaf_pack)
+    return point_test(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tnear, tfar, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z),
+                      __uint_as_float(c.x), __uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), (int)d.is_curve - 5, h);
   if (d.is_curve == 4) return round_record_test(d, r, tfar, c.z, (int)c.x, h);   // c.x: this record's first-level sub-segment
   if (d.is_curve == 3) {   // flat cubic curve (Bezier / B-spline / Catmull-Rom / Hermite): control points from the resident vertex buffer
     CurveVtx cp[4];

@@ -28,6 +28,8 @@ RTC_GEOMETRY_TYPE_FLAT_HERMITE_CURVE, RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE =
 FLAT_CUBIC_TYPES = {"bezier": 25, "bspline": 33, "hermite": 41, "catmull_rom": 59}
 ROUND_CUBIC_TYPES = {"bezier": 24, "bspline": 32, "hermite": 40, "catmull_rom": 58}
 RTC_BUFFER_TYPE_TANGENT = 4
+RTC_BUFFER_TYPE_NORMAL = 3
+POINT_TYPES = {"sphere": 50, "disc": 51, "oriented_disc": 52}   # RTC_GEOMETRY_TYPE_SPHERE_POINT / _DISC_POINT / _ORIENTED_DISC_POINT
 RTC_FORMAT_UCHAR = 0x1001
 RTC_FORMAT_UINT = 0x5001
 RTC_FORMAT_FLOAT4 = 0x9004
@@ -371,6 +373,30 @@ class RTCLib:
             keep.append(tg)
         if tess is not None:
             self.rtcSetGeometryTessellationRate(g, float(tess))
+        if mask is not None:
+            self.rtcSetGeometryMask(g, mask)
+        self.rtcCommitGeometry(g)
+        if geom_id is None:
+            gid = self.rtcAttachGeometry(scene, g)
+        else:
+            self.rtcAttachGeometryByID(scene, g, geom_id)
+            gid = geom_id
+        self.rtcReleaseGeometry(g)
+        return gid, keep
+
+    def add_points(self, device, scene, vertices4, kind="sphere", normals=None, mask=None, geom_id=None):
+        """RTC_GEOMETRY_TYPE_SPHERE_POINT / _DISC_POINT / _ORIENTED_DISC_POINT: shared FLOAT4 vertices (centre, radius), one
+        primitive per vertex; 'oriented_disc' adds FLOAT3 normals (tutorials/point_geometry).  The arrays must stay alive."""
+        v = np.ascontiguousarray(vertices4, np.float32).reshape(-1, 4)
+        g = self.rtcNewGeometry(device, POINT_TYPES[kind])
+        self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT4, _ptr(v), 0, 16, v.shape[0])
+        keep = [v]
+        if kind == "oriented_disc":
+            n = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+            npad = np.zeros(n.size + 4, np.float32)
+            npad[:n.size] = n.reshape(-1)
+            self.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_NORMAL, 0, RTC_FORMAT_FLOAT3, _ptr(npad), 0, 12, n.shape[0])
+            keep.append(npad)
         if mask is not None:
             self.rtcSetGeometryMask(g, mask)
         self.rtcCommitGeometry(g)

@@ -89,6 +89,7 @@ enum RTCFeatureFlags {
   RTC_FEATURE_FLAG_ROUND_HERMITE_CURVE = 1 << 14, RTC_FEATURE_FLAG_ROUND_CATMULL_ROM_CURVE = 1 << 17,
   RTC_FEATURE_FLAG_FLAT_BEZIER_CURVE = 1 << 9, RTC_FEATURE_FLAG_FLAT_BSPLINE_CURVE = 1 << 12,
   RTC_FEATURE_FLAG_FLAT_HERMITE_CURVE = 1 << 15, RTC_FEATURE_FLAG_FLAT_CATMULL_ROM_CURVE = 1 << 18,
+  RTC_FEATURE_FLAG_SPHERE_POINT = 1 << 20, RTC_FEATURE_FLAG_DISC_POINT = 1 << 21, RTC_FEATURE_FLAG_ORIENTED_DISC_POINT = 1 << 22,
   RTC_FEATURE_FLAG_INSTANCE = 1 << 23,
   RTC_FEATURE_FLAG_ALL = 0xffffffff
 };
@@ -113,9 +114,15 @@ enum RTCGeometryType {
   RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE = 32,
   RTC_GEOMETRY_TYPE_ROUND_HERMITE_CURVE = 40,
   RTC_GEOMETRY_TYPE_ROUND_CATMULL_ROM_CURVE = 58,
+  /* point primitives (rtcore_geometry.h:42-44; sphere_intersector.h, disc_intersector.h): vertex buffer RTC_FORMAT_FLOAT4 (centre,
+   * radius), one primitive per vertex, no index buffer; oriented discs add RTC_BUFFER_TYPE_NORMAL (RTC_FORMAT_FLOAT3), one
+   * normal per vertex.  Hits report u = v = 0; Ng = the sphere normal, -ray direction (ray-facing disc) or the disc normal */
+  RTC_GEOMETRY_TYPE_SPHERE_POINT = 50,
+  RTC_GEOMETRY_TYPE_DISC_POINT = 51,
+  RTC_GEOMETRY_TYPE_ORIENTED_DISC_POINT = 52,
   RTC_GEOMETRY_TYPE_INSTANCE = 121 /* single-level instances of triangle scenes (rtcore_geometry.h:51) */
 };
-enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2, RTC_BUFFER_TYPE_TANGENT = 4, RTC_BUFFER_TYPE_FLAGS = 32 };
+enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1, RTC_BUFFER_TYPE_VERTEX_ATTRIBUTE = 2, RTC_BUFFER_TYPE_NORMAL = 3, RTC_BUFFER_TYPE_TANGENT = 4, RTC_BUFFER_TYPE_FLAGS = 32 };
 enum RTCCurveFlags { RTC_CURVE_FLAG_NEIGHBOR_LEFT = 1 << 0, RTC_CURVE_FLAG_NEIGHBOR_RIGHT = 1 << 1 };   /* rtcore_geometry.h:66-70 */
 enum RTCError {
   RTC_ERROR_NONE = 0, RTC_ERROR_UNKNOWN = 1, RTC_ERROR_INVALID_ARGUMENT = 2, RTC_ERROR_INVALID_OPERATION = 3,

@@ -18,7 +18,7 @@ and written under oracle/_ref/gen/ (git-ignored).
 Configuration (all are supported reference build options, CMakeLists.txt:185-214):
   tasking   = INTERNAL        (no TBB in this image)
   ISAs      = SSE2 (base) + AVX + AVX2 + AVX512   (runtime-selected by cpuid)
-  geometry  = triangles + quads + curves + instances (EMBREE_GEOMETRY_TRIANGLE / QUAD / CURVE / INSTANCE), ray packets ON,
+  geometry  = triangles + quads + curves + points + instances (EMBREE_GEOMETRY_TRIANGLE / QUAD / CURVE / POINT / INSTANCE), ray packets ON,
               ray masks ON, filter functions ON, backface culling OFF  -- the
               reference defaults for every switch that reaches the hot path.
 
@@ -128,7 +128,7 @@ def gen_headers(gen, stat):
     # --- config.h from kernels/config.h.in
     t = open(f"{REF}/kernels/config.h.in").read()
     cfg_on = {"EMBREE_RAY_MASK", "EMBREE_FILTER_FUNCTION", "EMBREE_GEOMETRY_TRIANGLE", "EMBREE_GEOMETRY_QUAD", "EMBREE_GEOMETRY_CURVE",
-              "EMBREE_GEOMETRY_INSTANCE", "EMBREE_RAY_PACKETS"}
+              "EMBREE_GEOMETRY_INSTANCE", "EMBREE_GEOMETRY_POINT", "EMBREE_RAY_PACKETS"}
     if stat:
         cfg_on.add("EMBREE_STAT_COUNTERS")
     t = re.sub(r"#cmakedefine (\w+)",

@@ -87,6 +87,25 @@ def load_golden_cubic(name="curves_cubic"):
                 intersect_out=rec(z["intersect_out"], RAYHIT_DTYPE), occluded_out=rec(z["occluded_out"], RAY_DTYPE), bounds=z["bounds"])
 
 
+def load_golden_points(name="points"):
+    """tests/golden/points.npz -> dict(meshes, points=[(verts4, kind, normals or None, geomID, mask)], rays_in, intersect_out,
+    occluded_out, bounds): sphere / disc / oriented-disc point sets around a triangle sphere (the scene is rebuilt from its seed by
+    make_golden.point_scene, the file holds the rays and the reference's outputs)."""
+    from embree_b200.rtc import RAYHIT_DTYPE, RAY_DTYPE, aligned_empty
+    from tests.golden.make_golden_sets import point_scene
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+    def rec(a, dt):
+        out = aligned_empty(a.shape[0], dt)
+        out.view(np.uint8).reshape(a.shape)[:] = a
+        return out
+    meshes, sets, rays = point_scene()
+    rays_in = rec(z["rays_in"], RAYHIT_DTYPE)
+    assert rays_in.tobytes() == rays.tobytes(), "point_scene() no longer reproduces the rays of the committed fixture"
+    return dict(meshes=meshes, points=sets, rays_in=rays_in, intersect_out=rec(z["intersect_out"], RAYHIT_DTYPE),
+                occluded_out=rec(z["occluded_out"], RAY_DTYPE), bounds=z["bounds"])
+
+
 GOLDEN = ["cube_ground", "sphere21", "terrain_masks"]
 GOLDEN_QUADS = ["quads"]   # meshes with [n,4] indices are RTC_GEOMETRY_TYPE_QUAD
 

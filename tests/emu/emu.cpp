@@ -359,6 +359,24 @@ extern "C" int emu_flat_curve_test(const float* ray8, const float* v0, const flo
   return 1;
 }
 
+// ---- point primitives (rt_core.cuh point_test), host instantiation.  verts = n x (centre, radius), normals = n x float3 (oriented
+// discs) or NULL; kind 0 sphere, 1 ray-facing disc, 2 oriented disc.  Every point is tested in order against the ray as shortened
+// by the hits so far (the sequential leaf loop); returns the winning point or -1.  out6 = t, u, v, Ng.xyz.
+extern "C" int emu_point_closest(const float* ray8, const float* verts, const float* normals, int n, int kind, float* out6) {
+  int best = -1;
+  float tfar = ray8[7];
+  for (int i = 0; i < n; ++i) {
+    CurveHit h;
+    const float* v = verts + 4 * (size_t)i;
+    const float zero[3] = {0.0f, 0.0f, 0.0f};
+    const float* nn = normals ? normals + 3 * (size_t)i : zero;
+    if (!point_test(ray8[0], ray8[1], ray8[2], ray8[4], ray8[5], ray8[6], ray8[3], tfar, v[0], v[1], v[2], v[3], nn[0], nn[1], nn[2], kind, h)) continue;
+    best = i; tfar = h.t;
+    out6[0] = h.t; out6[1] = h.u; out6[2] = h.v; out6[3] = h.ngx; out6[4] = h.ngy; out6[5] = h.ngz;
+  }
+  return best;
+}
+
 // ---- flat cubic curves (rt_core.cuh flat_cubic_test + curve_basis_table), host instantiation.  cps = n curves x 4 control points
 // x float4 (Hermite input already converted); every curve is tested in order against the ray as shortened by the hits so far
 // (the sequential leaf loop); returns the winning curve or -1.  out6 = t, u, v, Ng.xyz.

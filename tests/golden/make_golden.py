@@ -267,6 +267,36 @@ def main_filters():
     np.savez_compressed(os.path.join(HERE, "filters.npz"), **d)
 
 
+from tests.golden.make_golden_sets import point_scene  # noqa: E402
+
+
+def main_points(name="points"):
+    """Point primitives (RTC_GEOMETRY_TYPE_SPHERE_POINT / _DISC_POINT / _ORIENTED_DISC_POINT: sphere_intersector.h, disc_intersector.h)."""
+    R = load_reference()
+    dev = R.new_device(None)
+    meshes, sets, rayhits = point_scene()
+    sc = R.rtcNewScene(dev)
+    keep = [R.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in meshes]
+    keep += [R.add_points(dev, sc, pv, kind, normals=pn, mask=mask, geom_id=gid)[1] for (pv, kind, pn, gid, mask) in sets]
+    R.rtcCommitScene(sc)
+    R.check(dev)
+    b = RTCBounds()
+    R.rtcGetSceneBounds(sc, C.byref(b))
+    out_i = R.intersect(sc, rayhits.copy(), "1")
+    out_o = R.occluded(sc, rays_of(rayhits), "1")
+    out_8 = R.intersect(sc, rayhits.copy(), "8")
+    assert (out_8["primID"] == out_i["primID"]).all() and (out_8["geomID"] == out_i["geomID"]).all()
+    R.check(dev)
+    d = dict(rays_in=rayhits.view(np.uint8).reshape(-1, 96), intersect_out=out_i.view(np.uint8).reshape(-1, 96),
+             occluded_out=out_o.view(np.uint8).reshape(-1, 48),
+             bounds=np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32))
+    print(f"{name}: {len(rayhits)} rays, hits per geometry {[int((out_i['geomID'] == g).sum()) for g in range(4)]}, "
+          f"occluded {(out_o['tfar'] == -np.inf).mean():.3f}")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    R.rtcReleaseScene(sc)
+    R.rtcReleaseDevice(dev)
+
+
 def main():
     # 1. the triangle_geometry tutorial scene: cube (geomID 0) + ground plane (geomID 1), camera-like + random rays
     (cv, ct), (gv, gt) = scenes.cube_and_ground()
@@ -330,6 +360,7 @@ def main():
     main_curves()
     main_cubic_curves()
     main_cubic_curves("curves_cubic_round", True)
+    main_points()
     main_filters()
 
 
@@ -340,6 +371,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cubic":
         main_cubic_curves()
         main_cubic_curves("curves_cubic_round", True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "points":
+        main_points()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "filters":
         main_filters()

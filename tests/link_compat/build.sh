@@ -68,3 +68,20 @@ if [ -f ../../oracle/_ref/libembree4.so.4 ] && [ ! -f ../golden/dynamic_scene_16
   _bin/ref_dynamic_scene ../golden/dynamic_scene_160x120 160 120 4 3
   rm -f _bin/ref_dynamic_scene
 fi
+
+# Point primitives: the reference's tutorial device code tutorials/point_geometry/point_geometry_device.cpp (three sets of 512 sphere /
+# disc / oriented-disc points over a ground plane, closest hit + shadow ray per pixel), compiled untouched with tutorial_host.cpp (camera of
+# point_geometry.cpp:23-24), linked (a) against libembree4_b200.so -> _bin/embree_point_geometry and (b) against the unmodified reference ->
+# the golden frame tests/golden/point_geometry_160x120.raw.
+PCAM="-DCAMERA_FROM=0.0f,2.0f,7.0f"
+if [ ! -x _bin/embree_point_geometry ] || [ tutorial_host.cpp -nt _bin/embree_point_geometry ]; then
+  g++ -O1 -std=c++17 -w $INC $PCAM -o _bin/embree_point_geometry tutorial_host.cpp "$REF/tutorials/point_geometry/point_geometry_device.cpp" $SYS \
+      -L_bin -lembree4 -lpthread -Wl,-rpath,'$ORIGIN/../../../embree_b200/csrc'
+  echo built tests/link_compat/_bin/embree_point_geometry
+fi
+if [ -f ../../oracle/_ref/libembree4.so.4 ] && [ ! -f ../golden/point_geometry_160x120.raw ]; then
+  g++ -O1 -std=c++17 -w $INC $PCAM -o _bin/ref_point_geometry tutorial_host.cpp "$REF/tutorials/point_geometry/point_geometry_device.cpp" $SYS \
+      -L../../oracle/_ref -l:libembree4.so.4 -lpthread -Wl,-rpath,'$ORIGIN/../../../oracle/_ref'
+  _bin/ref_point_geometry ../golden/point_geometry_160x120.raw 160 120 4
+  rm -f _bin/ref_point_geometry
+fi

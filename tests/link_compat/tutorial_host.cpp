@@ -11,6 +11,10 @@
 #include <tutorials/common/tutorial/camera.h>
 #include <common/tasking/taskscheduler.h>
 
+#ifndef CAMERA_FROM
+#define CAMERA_FROM 1.5f, 1.5f, -1.5f
+#endif
+
 namespace embree {
 RTCDevice g_device = nullptr;
 extern "C" RayStats* g_stats = nullptr;
@@ -30,7 +34,7 @@ int main(int argc, char** argv) {
   g_stats = (RayStats*)alignedMalloc(TaskScheduler::threadCount() * sizeof(RayStats), 64);
   for (size_t i = 0; i < TaskScheduler::threadCount(); ++i) g_stats[i].numRays = 0;
   Camera camera;
-  camera.from = Vec3fa(1.5f, 1.5f, -1.5f);   // triangle_geometry.cpp:23-24
+  camera.from = Vec3fa(CAMERA_FROM);         // triangle_geometry.cpp:23-24 (point_geometry.cpp:23-24 through -DCAMERA_FROM)
   camera.to = Vec3fa(0.0f, 0.0f, 0.0f);
   std::vector<int> pixels((size_t)width * height, 0);
   device_init(nullptr);

@@ -14,6 +14,7 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "libembree4.so.4")
 
 
 CUBIC_BASES = ["bezier", "bspline", "catmull_rom", "hermite"]
+POINT_KINDS = ["sphere", "disc", "oriented_disc"]
 
 
 class Oracle:
@@ -31,6 +32,7 @@ class Oracle:
         d.orc_add_cubic_curves.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint,
                                            C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         d.orc_add_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
+        d.orc_add_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_uint]
         d.orc_set_robust.argtypes = [C.c_void_p, C.c_int]
         d.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
         d.orc_get_bounds.argtypes = [C.c_void_p, C.c_void_p]
@@ -39,11 +41,11 @@ class Oracle:
         d.orc_api_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_uint, C.c_int]
         self.d = d
 
-    def scene(self, meshes, robust=False, instances=(), curves=(), cubics=()):
+    def scene(self, meshes, robust=False, instances=(), curves=(), cubics=(), points=()):
         """meshes: list of (vertices[nv,3] f32, indices[nt,3] u32 (or [nq,4] for a quad mesh), geomID, mask); instances:
         list of (child OracleScene, xfm[12] column-major 3x4, geomID, mask); curves: list of (vertices[nv,4] f32 (xyz,
         radius), first-vertex indices[ns] u32, flags[ns] u8 or None, geomID, mask) round linear curve sets."""
-        return OracleScene(self, meshes, robust, instances, curves, cubics)
+        return OracleScene(self, meshes, robust, instances, curves, cubics, points)
 
     def trace(self, v, t, rayhits, occluded=False, mask=0xFFFFFFFF, nthreads=1):
         sc = self.scene([(v, t, 0, mask)])
@@ -53,7 +55,7 @@ class Oracle:
 
 
 class OracleScene:
-    def __init__(self, o, meshes, robust=False, instances=(), curves=(), cubics=()):
+    def __init__(self, o, meshes, robust=False, instances=(), curves=(), cubics=(), points=()):
         self.o = o
         self.h = o.d.orc_new()
         o.d.orc_set_robust(self.h, 1 if robust else 0)
@@ -84,6 +86,11 @@ class OracleScene:
             self.keep += [cv, ci, tg]
             o.d.orc_add_cubic_curves(self.h, cv.ctypes.data, 16, cv.shape[0], ci.ctypes.data, 4, ci.shape[0], gid, mask,
                                      CUBIC_BASES.index(basis), int(tess), None if tg is None else tg.ctypes.data, 16, 1 if rnd else 0)
+        for (pv, kind, normals, gid, mask) in points:   # point primitives: vertices4 (centre, radius), kind 'sphere' | 'disc' | 'oriented_disc', normals[n,3] or None
+            pv = np.ascontiguousarray(pv, np.float32).reshape(-1, 4)
+            pn = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+            self.keep += [pv, pn]
+            o.d.orc_add_points(self.h, pv.ctypes.data, 16, pv.shape[0], None if pn is None else pn.ctypes.data, 12, POINT_KINDS.index(kind), gid, mask)
         for (child, xfm, gid, mask) in instances:
             m = np.ascontiguousarray(xfm, np.float32).reshape(12)
             self.keep += [child, m]
@@ -307,4 +314,44 @@ def sweep_disagreements(rays, a, b, curve_geoms, tol=1e-4, cos_max=0.1):
         c = abs(ng @ d) / max(np.linalg.norm(ng) * np.linalg.norm(d), 1e-300)
         if not (int(near["geomID"][i]) in curve_geoms and c < cos_max):
             bad += 1
+    return int(differ.sum()), bad
+
+
+def point_disagreements(rays, a, b, point_sets, margin=1e-4):
+    """Point primitives: rays on which two implementations disagree (hit vs miss, or different primitives at different
+    distances), and how many of them are NOT explained by a graze.  point_sets: {geomID: (vertices[n,4], kind, normals or None)}.
+    A disagreement is explained when, for a point one side reports and the other does not, the exact (float64) test sits on a
+    decision boundary within `margin` relative: the ray is tangent to the sphere / passes through the rim of the disc, or the hit
+    distance coincides with tnear / tfar (the reference evaluates 1 / dir^2 with a refined hardware approximation, this library
+    with the exact reciprocal).  Returns (differing rays, unexplained ones)."""
+    ah, bh = a["geomID"] != 0xFFFFFFFF, b["geomID"] != 0xFFFFFFFF
+    ulps = np.abs(a["tfar"].view(np.int32).astype(np.int64) - b["tfar"].view(np.int32).astype(np.int64))
+    differ = (ah != bh) | (ah & bh & ((a["primID"] != b["primID"]) | (a["geomID"] != b["geomID"])) & (ulps > TIE_ULPS))
+    bad = 0
+    for i in np.nonzero(differ)[0]:
+        o = np.array([rays["org_x"][i], rays["org_y"][i], rays["org_z"][i]], np.float64)
+        d = np.array([rays["dir_x"][i], rays["dir_y"][i], rays["dir_z"][i]], np.float64)
+        tn, tf = float(rays["tnear"][i]), float(rays["tfar"][i])
+        explained = False
+        for x, h in ((a, ah[i]), (b, bh[i])):
+            g = int(x["geomID"][i])
+            if not h or g not in point_sets:
+                continue
+            pv, kind, pn = point_sets[g]
+            c, r = pv[int(x["primID"][i]), :3].astype(np.float64), float(pv[int(x["primID"][i]), 3])
+            c0 = c - o
+            if kind == "oriented_disc":
+                n = pn[int(x["primID"][i])].astype(np.float64)
+                t = float(c0 @ n) / float(d @ n)
+                ts = [t]
+                rim = abs(np.linalg.norm(o + t * d - c) - r) / r
+            else:
+                proj = float(c0 @ d) / float(d @ d)
+                l = np.linalg.norm(c0 - proj * d)
+                rim = abs(l - r) / r
+                td = np.sqrt(max(r * r - l * l, 0.0) / float(d @ d))
+                ts = [proj] if kind == "disc" else [proj - td, proj + td]
+            edge = min(min(abs(t - tn), abs(t - tf)) / max(abs(t), 1e-30) for t in ts) if np.isfinite(tf) else min(abs(t - tn) / max(abs(t), 1e-30) for t in ts)
+            explained |= (rim < margin) or (edge < margin)
+        bad += 0 if explained else 1
     return int(differ.sum()), bad

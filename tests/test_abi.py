@@ -35,6 +35,9 @@ int main(void) {
     (int)RTC_GEOMETRY_TYPE_ROUND_HERMITE_CURVE, (int)RTC_GEOMETRY_TYPE_FLAT_CATMULL_ROM_CURVE, (int)RTC_GEOMETRY_TYPE_ROUND_CATMULL_ROM_CURVE,
     (int)RTC_BUFFER_TYPE_TANGENT, (int)RTC_RAY_QUERY_FLAG_INVOKE_ARGUMENT_FILTER, (int)RTC_FEATURE_FLAG_FLAT_BEZIER_CURVE,
     (int)RTC_FEATURE_FLAG_ROUND_CATMULL_ROM_CURVE);
+  printf("%d %d %d %d %d %d %d %d\n", (int)RTC_GEOMETRY_TYPE_SPHERE_POINT, (int)RTC_GEOMETRY_TYPE_DISC_POINT, (int)RTC_GEOMETRY_TYPE_ORIENTED_DISC_POINT,
+    (int)RTC_BUFFER_TYPE_NORMAL, (int)RTC_FEATURE_FLAG_SPHERE_POINT, (int)RTC_FEATURE_FLAG_DISC_POINT, (int)RTC_FEATURE_FLAG_ORIENTED_DISC_POINT,
+    (int)RTC_DEVICE_PROPERTY_POINT_GEOMETRY_SUPPORTED);
   return 0;
 }
 """

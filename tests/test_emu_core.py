@@ -339,3 +339,48 @@ def test_two_level_assembly_equals_single_bvh(emu, oracle, n_meshes):
     emu.emu_free(top)
     for h in handles:
         emu.emu_free(h)
+
+
+def point_cloud(n=1500, seed=5):
+    """Random point primitives inside the unit cube (centre, radius) + normals, and rays through them: some start inside a
+    sphere (back hit), some end before the cloud."""
+    rng = np.random.RandomState(seed)
+    pv = np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.uniform(0.01, 0.12, (n, 1))], 1).astype(np.float32)
+    pn = rng.normal(size=(n, 3)).astype(np.float32)
+    m = 4000
+    org = rng.normal(size=(m, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * rng.uniform(0.0, 2.5, (m, 1)).astype(np.float32)
+    org[::11] = pv[rng.randint(0, n, len(org[::11])), :3] + np.float32(0.004)     # inside a sphere: only its back side is hit
+    d = (rng.uniform(-1, 1, (m, 3)) - org).astype(np.float32) * rng.uniform(0.3, 3, (m, 1)).astype(np.float32)
+    rays = make_rayhits(org, d, tnear=1e-3)
+    rays["tfar"][::7] = 0.9
+    return pv, pn, rays
+
+
+@pytest.mark.parametrize("kind", ["sphere", "disc", "oriented_disc"])
+def test_point_test_equals_oracle(emu, oracle, kind):
+    """rt_core.cuh point_test (RTC_GEOMETRY_TYPE_SPHERE_POINT / _DISC_POINT / _ORIENTED_DISC_POINT), host instantiation, brute force
+    over all points: the same winner and bit-identical t / Ng as the C oracle's BVH traversal."""
+    from tests.parity import POINT_KINDS
+    pv, pn, rays = point_cloud()
+    sc = oracle.scene([], points=[(pv, kind, pn if kind == "oriented_disc" else None, 2, 0xFFFFFFFF)])
+    want = sc.trace(rays.copy())
+    emu.emu_point_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    out = np.zeros(6, np.float32)
+    hits = 0
+    for k in range(len(rays)):
+        r = rays[k]
+        ray = np.array([r["org_x"], r["org_y"], r["org_z"], r["tnear"], r["dir_x"], r["dir_y"], r["dir_z"], r["tfar"]], np.float32)
+        best = emu.emu_point_closest(ray.ctypes.data, pv.ctypes.data, pn.ctypes.data if kind == "oriented_disc" else None, len(pv),
+                                     POINT_KINDS.index(kind), out.ctypes.data)
+        w = want[k]
+        if best < 0:
+            assert w["geomID"] == 0xFFFFFFFF, k
+            continue
+        hits += 1
+        assert w["geomID"] == 2 and w["primID"] == best, (k, best, w)
+        exp = np.array([w["tfar"], w["u"], w["v"], w["Ng_x"], w["Ng_y"], w["Ng_z"]], np.float32)
+        assert (out.view(np.uint32) == exp.view(np.uint32)).all(), (k, out, w)
+    assert hits > 1000
+    assert np.allclose(sc.bounds(), np.concatenate([(pv[:, :3] - pv[:, 3:]).min(0), (pv[:, :3] + pv[:, 3:]).max(0)]))
+    sc.free()

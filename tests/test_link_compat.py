@@ -68,6 +68,37 @@ def test_triangle_geometry_tutorial_renders_the_reference_frame(tmp_path):
     assert diff.sum() <= 0.003 * w.size and not (diff & ~edge).any(), f"{diff.sum()} pixels differ, {(diff & ~edge).sum()} of them off an edge"
 
 
+POINTS = os.path.join(ROOT, "tests", "link_compat", "_bin", "embree_point_geometry")
+
+
+@pytest.mark.gpu
+def test_point_geometry_tutorial_renders_the_reference_frame(tmp_path):
+    """The reference's tutorials/point_geometry device code (512 sphere points, 512 ray-facing discs and 512 oriented discs over a ground
+    plane; closest hit + shadow ray per pixel), compiled untouched and linked against libembree4_b200.so, renders the frame the same
+    code produces with the unmodified reference library; pixels may differ only on an edge of the picture (a silhouette or a shadow
+    boundary, where the reference's own approximate reciprocal decides), at most 0.5 % of the frame; one step of one 8-bit colour channel
+    (the quantised shading of a normal that differs in its last bits) is tolerated anywhere, on at most 3 % of the frame."""
+    import numpy as np
+    _ensure_built()
+    if not os.path.exists(POINTS):
+        pytest.skip("tutorial binary not built")
+    out = str(tmp_path / "frame.raw")
+    r = subprocess.run([POINTS, out, "160", "120", "4"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "device error 0" in r.stdout, r.stdout
+    got = np.fromfile(out, np.int32)
+    want = np.fromfile(os.path.join(ROOT, "tests", "golden", "point_geometry_160x120.raw"), np.int32)
+    assert got.shape == want.shape and len(np.unique(want)) >= 100
+    g, w = got.reshape(120, 160), want.reshape(120, 160)
+    edge = np.zeros_like(w, bool)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            edge |= np.roll(np.roll(w, dy, 0), dx, 1) != w
+    ch = lambda a: np.stack([(a >> sh) & 0xFF for sh in (0, 8, 16)], -1).astype(np.int32)      # noqa: E731
+    big = (np.abs(ch(g) - ch(w)) > 1).any(-1)      # more than one step of one 8-bit channel (the shading quantises dot(light, normalize(Ng)))
+    diff = g != w
+    assert big.sum() <= 0.005 * w.size and diff.sum() <= 0.03 * w.size and not (big & ~edge).any(), f"{diff.sum()} pixels differ, {big.sum()} by more than one step, {(big & ~edge).sum()} of them off an edge"
+
+
 HAIR = os.path.join(ROOT, "tests", "link_compat", "_bin", "embree_hair_geometry")
 
 

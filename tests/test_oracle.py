@@ -327,3 +327,65 @@ def test_oracle_round_cubic_curves_vs_reference_live(oracle, basis):
     R.rtcReleaseScene(rs)
     R.rtcReleaseDevice(dev)
     sc.free()
+
+
+def test_oracle_points_vs_golden(oracle):
+    """Point primitives (sphere_intersector.h, disc_intersector.h) restated in oracle/embree_oracle.c against the reference's own
+    outputs: sphere / ray-facing disc / oriented disc sets (geometry masks, an invalid centre, a negative radius, ray origins
+    inside spheres) around a triangle sphere."""
+    from tests.conftest import load_golden_points
+    from tests.parity import point_disagreements
+    g = load_golden_points()
+    sc = oracle.scene(g["meshes"], points=g["points"])
+    got = sc.trace(g["rays_in"].copy())
+    want = g["intersect_out"]
+    rep = compare_hits(want, got)
+    n_differ, unexplained = point_disagreements(g["rays_in"], want, got, {s[3]: (s[0], s[1], s[2]) for s in g["points"]})
+    assert n_differ <= 2 and unexplained == 0, (rep, n_differ, unexplained)
+    assert all((want["geomID"] == k).sum() > 150 for k in (1, 2, 3)), rep
+    assert rep["max_rel_t"] <= 1e-4 and rep["max_abs_uv"] <= 1e-6 and rep["miss_untouched"], rep
+    pt = np.isin(got["geomID"], [1, 2, 3])
+    assert (got["u"][pt] == 0).all() and (got["v"][pt] == 0).all() and (want["u"][pt] == 0).all()
+    ok = (got["geomID"] == want["geomID"]) & (got["primID"] == want["primID"]) & (got["geomID"] != 0xFFFFFFFF)
+    for f in ("Ng_x", "Ng_y", "Ng_z"):
+        assert np.allclose(got[f][ok], want[f][ok], rtol=1e-3, atol=2e-5), f
+    occ = sc.trace(rays_of(g["rays_in"]), occluded=True)
+    assert ((occ["tfar"] == -np.inf) != (g["occluded_out"]["tfar"] == -np.inf)).sum() <= n_differ
+    assert np.array_equal(sc.bounds(), g["bounds"])
+    sc.free()
+
+
+@pytest.mark.parametrize("kind", ["sphere", "disc", "oriented_disc"])
+def test_oracle_points_vs_live_reference(oracle, kind):
+    """60 000 rays against 4 000 points of one kind, oracle next to the live reference (when oracle/_ref is present)."""
+    from tests.parity import load_reference, point_disagreements
+    R = load_reference()
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.RandomState(5)
+    n, m = 4000, 60000
+    pv = np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.uniform(0.01, 0.08, (n, 1))], 1).astype(np.float32)
+    pn = rng.normal(size=(n, 3)).astype(np.float32)
+    org = rng.normal(size=(m, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * rng.uniform(0.0, 2.5, (m, 1)).astype(np.float32)
+    d = ((rng.uniform(-1, 1, (m, 3)) - org) * rng.uniform(0.3, 3, (m, 1))).astype(np.float32)
+    rays = make_rayhits(org, d, tnear=1e-3)
+    rays["tfar"][::7] = 0.9
+    dev = R.new_device(None)
+    sc = R.rtcNewScene(dev)
+    _, keep = R.add_points(dev, sc, pv, kind, normals=pn, geom_id=3)
+    R.rtcCommitScene(sc)
+    R.check(dev)
+    want = R.intersect(sc, rays.copy(), "1")
+    wocc = R.occluded(sc, rays_of(rays), "1")
+    R.rtcReleaseScene(sc)
+    R.rtcReleaseDevice(dev)
+    o = oracle.scene([], points=[(pv, kind, pn if kind == "oriented_disc" else None, 3, 0xFFFFFFFF)])
+    got = o.trace(rays.copy(), nthreads=8)
+    gocc = o.trace(rays_of(rays), occluded=True, nthreads=8)
+    rep = compare_hits(want, got, 1e-4)
+    n_differ, unexplained = point_disagreements(rays, want, got, {3: (pv, kind, pn)})
+    assert rep["hits"] > 10000 and n_differ <= 4 and unexplained == 0, (rep, n_differ, unexplained)
+    assert rep["max_rel_t"] <= 1e-4 and rep["max_abs_uv"] == 0.0, rep
+    assert ((wocc["tfar"] == -np.inf) != (gocc["tfar"] == -np.inf)).sum() <= n_differ
+    o.free()

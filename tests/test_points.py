@@ -1,0 +1,146 @@
+"""Point primitives on the GPU (RTC_GEOMETRY_TYPE_SPHERE_POINT / _DISC_POINT / _ORIENTED_DISC_POINT; reference:
+kernels/geometry/sphere_intersector.h:76-140, disc_intersector.h:85-170, kernels/common/scene_points.h/.cpp; caller
+tutorials/point_geometry): golden outputs of the unmodified reference through every entry point, a large cloud against the C
+oracle (the device function is bit-identical to it: tests/test_emu_core.py test_point_test_equals_oracle), error paths."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from embree_b200.rtc import (RTCBounds, RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM, RTC_BUFFER_TYPE_INDEX, RTC_BUFFER_TYPE_NORMAL,
+                             RTC_BUFFER_TYPE_VERTEX, RTC_FORMAT_FLOAT3, RTC_FORMAT_FLOAT4, RTC_FORMAT_UINT, _ptr, make_rayhits, rays_of)
+from tests.conftest import load_golden_points
+from tests.parity import compare_hits, point_disagreements
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+MODES = ["1", "4", "8", "16", "1M", "4M", "8M", "16M"]
+
+
+def build_point_scene(lib, dev, meshes, sets, quality=RTC_BUILD_QUALITY_MEDIUM):
+    sc = lib.rtcNewScene(dev)
+    lib.rtcSetSceneBuildQuality(sc, quality)
+    keep = [lib.add_triangle_mesh(dev, sc, v, t, mask=mask, geom_id=gid)[1] for (v, t, gid, mask) in meshes]
+    keep += [lib.add_points(dev, sc, pv, kind, normals=pn, mask=mask, geom_id=gid)[1] for (pv, kind, pn, gid, mask) in sets]
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    return sc, keep
+
+
+@pytest.mark.parametrize("quality", [RTC_BUILD_QUALITY_LOW, RTC_BUILD_QUALITY_MEDIUM])
+def test_points_golden_all_entry_points(b200, quality):
+    """Ids exact (up to rays on a decision boundary of the reference's own arithmetic, each one shown to be one), t within 1e-4,
+    u = v = 0, Ng of the reference, any-hit equal, bounds equal -- through all eight entry points."""
+    lib, dev = b200
+    g = load_golden_points()
+    sc, keep = build_point_scene(lib, dev, g["meshes"], g["points"], quality)
+    b = RTCBounds()
+    lib.rtcGetSceneBounds(sc, C.byref(b))
+    got_b = np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32)
+    assert np.allclose(got_b, g["bounds"], rtol=1e-6, atol=1e-6) and (got_b[:3] <= g["bounds"][:3]).all() and (got_b[3:] >= g["bounds"][3:]).all()
+    want = g["intersect_out"]
+    sets = {s[3]: (s[0], s[1], s[2]) for s in g["points"]}
+    first = None
+    for mode in MODES:
+        got = lib.intersect(sc, g["rays_in"].copy(), mode)
+        rep = compare_hits(want, got, TOL)
+        n_differ, unexplained = point_disagreements(g["rays_in"], want, got, sets)
+        assert n_differ <= 2 and unexplained == 0, (mode, rep, n_differ, unexplained)
+        assert rep["max_rel_t"] <= TOL and rep["max_abs_uv"] <= TOL and rep["miss_untouched"], (mode, rep)
+        pt = np.isin(got["geomID"], [1, 2, 3])
+        assert (got["u"][pt] == 0).all() and (got["v"][pt] == 0).all(), mode
+        ok = (got["geomID"] == want["geomID"]) & (got["primID"] == want["primID"]) & (got["geomID"] != 0xFFFFFFFF)
+        for f in ("Ng_x", "Ng_y", "Ng_z"):
+            assert np.allclose(got[f][ok], want[f][ok], rtol=1e-3, atol=2e-5), (mode, f)
+        if first is None:
+            first = got
+        else:   # every entry point runs the same kernel: identical records
+            assert all((got[f].view(np.uint32) == first[f].view(np.uint32)).all() for f in ("tfar", "primID", "geomID", "Ng_x", "Ng_y", "Ng_z")), mode
+        occ = lib.occluded(sc, rays_of(g["rays_in"]), mode)
+        assert ((occ["tfar"] == -np.inf) != (g["occluded_out"]["tfar"] == -np.inf)).sum() <= n_differ, mode
+    lib.rtcReleaseScene(sc)
+
+
+@pytest.mark.parametrize("kind", ["sphere", "disc", "oriented_disc"])
+def test_points_large_equal_the_oracle(b200, oracle, kind):
+    """200 000 points + 400 000 rays: the GPU result equals the C oracle's bit for bit (closest hit: ids, t, Ng; any hit)."""
+    lib, dev = b200
+    rng = np.random.RandomState(23)
+    n, m = 200000, 400000
+    pv = np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.uniform(0.002, 0.012, (n, 1))], 1).astype(np.float32)
+    pn = rng.normal(size=(n, 3)).astype(np.float32)
+    org = rng.normal(size=(m, 3)).astype(np.float32)
+    org = org / np.linalg.norm(org, axis=1, keepdims=True) * rng.uniform(0.0, 2.5, (m, 1)).astype(np.float32)
+    d = ((rng.uniform(-1, 1, (m, 3)) - org) * rng.uniform(0.3, 3, (m, 1))).astype(np.float32)
+    rays = make_rayhits(org, d, tnear=1e-3)
+    rays["tfar"][::7] = 0.9
+    sets = [(pv, kind, pn if kind == "oriented_disc" else None, 4, 0xFFFFFFFF)]
+    sc, keep = build_point_scene(lib, dev, [], sets)
+    got = lib.intersect(sc, rays.copy(), "1M")
+    occ = lib.occluded(sc, rays_of(rays), "1M")
+    osc = oracle.scene([], points=sets)
+    want = osc.trace(rays.copy(), nthreads=16)
+    wocc = osc.trace(rays_of(rays), occluded=True, nthreads=16)
+    osc.free()
+    rep = compare_hits(want, got, TOL)
+    assert rep["hits"] > 100000, rep
+    fields = ("tfar", "u", "v", "Ng_x", "Ng_y", "Ng_z", "primID", "geomID", "instID")
+    differs = np.zeros(len(rays), bool)
+    for f in fields:
+        differs |= got[f].view(np.uint32) != want[f].view(np.uint32)
+    differs = np.nonzero(differs)[0]   # two points at exactly the same distance may be named in either order; nothing else may differ
+    assert len(differs) <= 4 and (got["tfar"][differs].view(np.uint32) == want["tfar"][differs].view(np.uint32)).all(), (rep, differs[:8])
+    assert (occ["tfar"].view(np.uint32) == wocc["tfar"].view(np.uint32)).all()
+    lib.rtcReleaseScene(sc)
+
+
+def test_point_api_errors_and_updates(b200):
+    """Buffer formats / slots of scene_points.cpp:38-85, a missing normal buffer, instancing refused; moving the points and
+    re-committing gives the new hits."""
+    lib, dev = b200
+    pv = np.array([[0, 0, 5, 1], [3, 0, 5, 0.5]], np.float32)
+    pad = np.zeros((3, 4), np.float32)
+    pad[:2] = pv
+    g = lib.rtcNewGeometry(dev, 50)
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(pad), 0, 16, 2)
+    assert lib.rtcGetDeviceError(dev) == 3                      # points take FLOAT4 vertices
+    idx = np.zeros(4, np.uint32)
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT, _ptr(idx), 0, 4, 2)
+    assert lib.rtcGetDeviceError(dev) == 2                      # no index buffer: unknown buffer type -> INVALID_ARGUMENT
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_NORMAL, 0, RTC_FORMAT_FLOAT3, _ptr(pad), 0, 12, 2)
+    assert lib.rtcGetDeviceError(dev) == 2                      # normals belong to oriented discs only
+    lib.rtcReleaseGeometry(g)
+    g = lib.rtcNewGeometry(dev, 52)
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT4, _ptr(pad), 0, 16, 2)
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_NORMAL, 0, RTC_FORMAT_FLOAT4, _ptr(pad), 0, 16, 2)
+    assert lib.rtcGetDeviceError(dev) == 3                      # FLOAT3 normals
+    lib.rtcCommitGeometry(g)
+    sc = lib.rtcNewScene(dev)
+    lib.rtcAttachGeometry(sc, g)
+    lib.rtcReleaseGeometry(g)
+    lib.rtcCommitScene(sc)
+    assert lib.rtcGetDeviceError(dev) == 3                      # oriented discs without normals
+    lib.rtcReleaseScene(sc)
+    # a sphere set: hit, move, re-commit, hit again; a ray from inside reports the back side
+    sc = lib.rtcNewScene(dev)
+    gid, keep = lib.add_points(dev, sc, pad[:2], "sphere")
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    rays = make_rayhits(np.array([[0, 0, 0], [0, 0, 5], [3, 0, 0]], np.float32), np.array([[0, 0, 1]] * 3, np.float32))
+    out = lib.intersect(sc, rays.copy(), "1")
+    assert out["primID"].tolist() == [0, 0, 1] and np.allclose(out["tfar"], [4.0, 1.0, 4.5]) and (out["geomID"] == gid).all()
+    assert np.allclose(out["Ng_z"], [-1.0, 1.0, -0.5]) and (out["u"] == 0).all() and (out["v"] == 0).all()
+    keep[0][0, 2] = 9.0
+    geo = lib.rtcGetGeometry(sc, gid)
+    lib.rtcUpdateGeometryBuffer(geo, RTC_BUFFER_TYPE_VERTEX, 0)
+    lib.rtcCommitGeometry(geo)
+    lib.rtcCommitScene(sc)
+    lib.check(dev)
+    out = lib.intersect(sc, rays.copy(), "1")
+    assert np.allclose(out["tfar"], [8.0, 3.0, 4.5]) and out["primID"].tolist() == [0, 0, 1]
+    top = lib.rtcNewScene(dev)
+    lib.add_instance(dev, top, sc, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32))
+    lib.rtcCommitScene(top)
+    assert lib.rtcGetDeviceError(dev) == 3                      # point geometries cannot be instanced on this back-end
+    lib.rtcReleaseScene(top)
+    lib.rtcReleaseScene(sc)
