@@ -478,6 +478,80 @@ def hair_leg(lib, dev, devt, stream, args, rnd=False):
     return out
 
 
+def point_leg(lib, dev, devt, stream, args):
+    """Point primitives (tutorials/point_geometry's geometry types at scale): 2 M sphere points / ray-facing discs / oriented discs in a
+    ball, 1920x1080 camera rays; closest hit and any hit, device-resident, CUDA events; next to the unmodified reference's rtcIntersect1
+    on the usable host threads with parity of every ray (differences must be rays on a decision boundary of the test)."""
+    from tests.parity import api_trace_mt, compare_hits, load_reference, point_disagreements
+    rng = np.random.RandomState(31)
+    npts = 2000000
+    c = rng.normal(size=(npts, 3)).astype(np.float32)
+    c = c / np.linalg.norm(c, axis=1, keepdims=True) * (rng.uniform(0.0, 1.0, (npts, 1)) ** (1.0 / 3.0)).astype(np.float32)
+    pv = np.concatenate([c, rng.uniform(0.001, 0.004, (npts, 1)).astype(np.float32)], 1).astype(np.float32)
+    pn = rng.normal(size=(npts, 3)).astype(np.float32)
+    cam = scenes.primary_rays(PRIMARY_W, PRIMARY_H, eye=(0.0, 0.4, -2.6), look=(0.0, -0.15, 1.0), fov=60.0, device=devt)
+    n = cam.shape[0]
+    a = lib.args()
+    cores, _detail = usable_cores()
+    R = load_reference() if not args.no_cpu else None
+    out = {"workload": f"{npts} points of radius 0.001-0.004 in the unit ball, {PRIMARY_W}x{PRIMARY_H} camera rays", "points": npts}
+    for kind in ("sphere", "disc", "oriented_disc"):
+        def build(L, d):
+            sc = L.rtcNewScene(d)
+            keep = L.add_points(d, sc, pv, kind, normals=pn, mask=0xFFFFFFFF, geom_id=0)[1]
+            t0 = time.perf_counter()
+            L.rtcCommitScene(sc)
+            dt = time.perf_counter() - t0
+            L.check(d)
+            return sc, keep, dt
+        sc, keep, commit_s = build(lib, dev)
+        work = cam.clone()
+        best = 1e9
+        for it in range(4):
+            work.copy_(cam)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            lib.rtcb200Intersect1MDevice(sc, C.c_void_p(work.data_ptr()), n, C.byref(a), C.c_void_p(stream))
+            c1.record()
+            torch.cuda.synchronize()
+            if it:
+                best = min(best, c0.elapsed_time(c1))
+        occ = cam[:, :12].contiguous()
+        ow = occ.clone()
+        obest = 1e9
+        for it in range(3):
+            ow.copy_(occ)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            lib.rtcb200Occluded1MDevice(sc, C.c_void_p(ow.data_ptr()), n, C.byref(a), C.c_void_p(stream))
+            c1.record()
+            torch.cuda.synchronize()
+            if it:
+                obest = min(obest, c0.elapsed_time(c1))
+        row = {"commit_ms": commit_s * 1e3, "rays": int(n), "Mrays_per_s": n / best * 1e-3, "ms": best, "occluded_Mrays_per_s": n / obest * 1e-3,
+               "hit_fraction": float((work.view(torch.int32)[:, 18] == 0).float().mean().item())}
+        if R is not None:
+            rdev = R.new_device(None)
+            rsc, rkeep, rcommit = build(R, rdev)
+            row["reference_commit_ms"] = rcommit * 1e3
+            got = scenes.as_numpy_rayhits(work.cpu())
+            rin = scenes.as_numpy_rayhits(cam.cpu())
+            w = rin.copy()
+            t0 = time.perf_counter()
+            api_trace_mt(R, rsc, w, cores)
+            row["reference"] = {"Mrays_per_s": n / (time.perf_counter() - t0) * 1e-6, "cores": cores, "api": "rtcIntersect1 loop (FTZ|DAZ)"}
+            rep = compare_hits(w, got)
+            nd, bad = point_disagreements(rin, w, got, {0: (pv, kind, pn)})
+            row["parity"] = {k: rep[k] for k in ("n", "hits", "max_rel_t", "max_abs_uv")}
+            row["parity"].update({"differing_rays": nd, "not_on_a_decision_boundary": bad, "checked_against": "reference, every ray"})
+            R.rtcReleaseScene(rsc)
+            R.rtcReleaseDevice(rdev)
+        out[kind] = row
+        lib.rtcReleaseScene(sc)
+        del work, occ, ow
+    return out
+
+
 def coherent_leg(lib, dev, devt, stream, workload, phi, rays, args):
     """One coherent configuration, measured like the headline: device-resident value (CUDA events, 3 warm-up + 5 timed
     passes over a packet stream larger than L2), e2e through the host-pointer entry point rtcb200IntersectNM with pinned
@@ -1114,6 +1188,10 @@ def main():
         extras["dynamic_scene_two_level"] = two_level_leg(lib, dev, args)
         extras["hair_bezier"] = hair_leg(lib, dev, devt, stream, args)
         extras["hair_bezier_round"] = hair_leg(lib, dev, devt, stream, args, rnd=True)
+        try:   # added at the very end of round 2: a failure here must not cost the line its other numbers
+            extras["points"] = point_leg(lib, dev, devt, stream, args)
+        except Exception as e:   # noqa: BLE001
+            extras["points"] = {"error": repr(e)}
 
     # ---- parity sample + CPU baseline (rank 0, N == 1)
     cpu_baseline, parity, ref_counters = None, None, None

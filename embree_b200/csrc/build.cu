@@ -281,6 +281,25 @@ __global__ void __launch_bounds__(256) primref_gen(const GeomDesc* __restrict__ 
         }
       }
     } else load_tri_verts(geoms[g], p - offs[g], v, ok, true, pad);
+    if (ok && geoms[g].is_curve && geoms[g].has_xfm) {
+      // instanced curve / point: the box above is in OBJECT space (where the record is tested); the BVH needs the world box of its eight
+      // corners (xfmBounds, affinespace.h:106-118), widened by the rounding of the transform and of the ray's way back (trace.cu
+      // to_object_space), as for instanced triangles
+      const GeomDesc& gd = geoms[g];
+      float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY}, wpad[3] = {0.0f, 0.0f, 0.0f};
+      for (int cnr = 0; cnr < 8; ++cnr) {
+        const float x = (cnr & 4) ? hi[0] : lo[0], y = (cnr & 2) ? hi[1] : lo[1], z = (cnr & 1) ? hi[2] : lo[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float w = __fmaf_rn(x, gd.xfm[a], __fmaf_rn(y, gd.xfm[3 + a], __fmaf_rn(z, gd.xfm[6 + a], gd.xfm[9 + a])));
+          wlo[a] = fminf(wlo[a], w); whi[a] = fmaxf(whi[a], w);
+          wpad[a] = fmaxf(wpad[a], 9.6e-7f * (fabsf(x * gd.xfm[a]) + fabsf(y * gd.xfm[3 + a]) + fabsf(z * gd.xfm[6 + a]) + fabsf(gd.xfm[9 + a])));
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { lo[a] = wlo[a] - wpad[a]; hi[a] = whi[a] + wpad[a]; }
+      ok &= (lo[0] > -kFltLarge) & (hi[0] < kFltLarge) & (lo[1] > -kFltLarge) & (hi[1] < kFltLarge) & (lo[2] > -kFltLarge) & (hi[2] < kFltLarge);
+    }
     skipb = geoms[g].skip_bounds != 0;
     if (ok && !geoms[g].is_curve) {
 #pragma unroll

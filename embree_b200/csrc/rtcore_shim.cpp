@@ -165,6 +165,10 @@ struct GeometryImpl : RefCounted {
   bool argFilterEnabled = false;
   GeomState state = GeomState::MODIFIED;
   unsigned modCounter = 1;
+  // identity that survives address reuse: caches keyed by the GeometryImpl* (kept per-mesh BVHs, the refit topology) compare it, because a
+  // geometry released and another one allocated at the same address with the same modCounter must not be taken for the old one
+  static std::atomic<unsigned long long>& serial_source() { static std::atomic<unsigned long long> n{0}; return n; }
+  const unsigned long long serial = serial_source().fetch_add(1) + 1;
   explicit GeometryImpl(DeviceImpl* d) : dev(d) { dev->retain(); }
   ~GeometryImpl() override { if (has_filter()) g_filterGeoms.fetch_sub(1); if (instScene) release_scene_ref(instScene); dev->release(); }
   bool has_filter() const { return intersectFilter || occludedFilter || argFilterEnabled; }
@@ -190,7 +194,7 @@ struct SceneImpl : RefCounted {
   std::vector<unsigned long long> committedChildGen;
   // topology signature of the last full build (geometry, type, primitive / vertex counts): a later commit whose enabled
   // geometries all ask for RTC_BUILD_QUALITY_REFIT and match it refits the BVH instead of rebuilding (bvh_refit.cpp)
-  struct TopoEntry { GeometryImpl* g; size_t nprims, nverts; bool operator==(const TopoEntry& o) const { return g == o.g && nprims == o.nprims && nverts == o.nverts; } };
+  struct TopoEntry { GeometryImpl* g; size_t nprims, nverts; unsigned long long serial; bool operator==(const TopoEntry& o) const { return g == o.g && nprims == o.nprims && nverts == o.nverts && serial == o.serial; } };
   std::vector<TopoEntry> builtTopology;
   RTCBuildQuality builtQuality = RTC_BUILD_QUALITY_MEDIUM;
   RTCSceneFlags builtFlags = RTC_SCENE_FLAG_NONE;
@@ -208,6 +212,7 @@ struct SceneImpl : RefCounted {
   // rebuilt or refitted only when that mesh's modCounter moved (scene.cpp:878-884, bvh_builder_twolevel.h:174-177)
   struct SubEntry {
     unsigned modCounter = 0; RTCBuildQuality sceneQuality = RTC_BUILD_QUALITY_MEDIUM; int robust = 0; size_t nprims = 0, nverts = 0;
+    unsigned long long serial = 0;   // GeometryImpl::serial of the mesh this BVH was built from
     rtk::SceneGPU gpu;
   };
   std::unordered_map<GeometryImpl*, SubEntry*> subs;
@@ -318,7 +323,17 @@ void commit_scene(SceneImpl* s) {
   float instBounds[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
   // round linear curves (scene_line_segments.cpp): float4 vertices, one index per segment, neighbour flags from the
   // application or derived from the index buffer as LineSegments::commit does (:209-232)
-  auto add_curves = [&](GeometryImpl* g, uint32_t geomID) {
+  // an instanced curve / point geometry: the records stay in OBJECT space (the trace kernel takes the ray there, as for instanced
+  // triangles), the builder boxes them in world space, the API bounds come from the instance box
+  auto as_instance = [](rtk::GeomDesc& d, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
+    if (!xfm) return;
+    d.has_xfm = 1; d.instID = instID; d.inst_mask = instMask; d.skip_bounds = 1;
+    memcpy(d.xfm, xfm, sizeof d.xfm);
+    memcpy(d.w2l, w2l, sizeof d.w2l);
+  };
+  std::unordered_map<GeometryImpl*, rtk::GeomDesc> uploadedCurves;   // a curve / point geometry instanced many times is uploaded once
+  auto add_curves = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
+    { auto it = uploadedCurves.find(g); if (it != uploadedCurves.end()) { rtk::GeomDesc d = it->second; d.geomID = geomID; as_instance(d, xfm, w2l, instID, instMask); descs.push_back(d); curves = true; return; } }
     const size_t nsegs = g->indices.count, nverts = g->vertices.count;
     if (nsegs == 0 || !g->indices.buf) return;
     if (!g->vertices.buf) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer not set");
@@ -351,11 +366,14 @@ void commit_scene(SceneImpl* s) {
     d.vstride = g->vertices.stride; d.istride = g->indices.stride;
     d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)nsegs;
     d.geomID = geomID; d.mask = g->mask; d.is_curve = g->type == RTC_GEOMETRY_TYPE_FLAT_LINEAR_CURVE ? 2 : 1;
+    uploadedCurves[g] = d;
+    as_instance(d, xfm, w2l, instID, instMask);
     descs.push_back(d);
   };
   // flat cubic curves (scene_curves.cpp): float4 control vertices, one index per curve (first control vertex), Hermite
   // adds float4 tangents; the basis weights at the tessellation points are tabulated here as the reference tabulates them
-  auto add_cubic = [&](GeometryImpl* g, uint32_t geomID) {
+  auto add_cubic = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
+    { auto it = uploadedCurves.find(g); if (it != uploadedCurves.end()) { rtk::GeomDesc d = it->second; d.geomID = geomID; as_instance(d, xfm, w2l, instID, instMask); descs.push_back(d); curves = true; return; } }
     const size_t ncurves = g->indices.count, nverts = g->vertices.count;
     if (ncurves == 0 || !g->indices.buf) return;
     if (!g->vertices.buf) fail(RTC_ERROR_INVALID_OPERATION, "vertex buffer not set");
@@ -396,11 +414,14 @@ void commit_scene(SceneImpl* s) {
     d.vstride = g->vertices.stride; d.istride = g->indices.stride;
     d.nverts = (uint32_t)nverts; d.ntris = (uint32_t)(ncurves * segs);   // flat: one BVH primitive per tessellation segment; round: per first-level sub-segment of the sweep intersector
     d.geomID = geomID; d.mask = g->mask; d.is_curve = round ? 4 : 3;
+    uploadedCurves[g] = d;
+    as_instance(d, xfm, w2l, instID, instMask);
     descs.push_back(d);
   };
   // point primitives (scene_points.cpp): float4 vertices (centre, radius), one primitive per vertex; oriented discs carry one
   // float3 normal per vertex (GeomDesc.tangents / tstride hold that buffer).  They share the curve kernels (GENERAL == 2).
-  auto add_points = [&](GeometryImpl* g, uint32_t geomID) {
+  auto add_points = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
+    { auto it = uploadedCurves.find(g); if (it != uploadedCurves.end()) { rtk::GeomDesc d = it->second; d.geomID = geomID; as_instance(d, xfm, w2l, instID, instMask); descs.push_back(d); curves = true; return; } }
     const size_t n = g->vertices.count;
     if (n == 0 || !g->vertices.buf) return;
     const bool oriented = g->type == RTC_GEOMETRY_TYPE_ORIENTED_DISC_POINT;
@@ -425,17 +446,14 @@ void commit_scene(SceneImpl* s) {
     d.nverts = (uint32_t)n; d.ntris = (uint32_t)n;
     d.geomID = geomID; d.mask = g->mask;
     d.is_curve = g->type == RTC_GEOMETRY_TYPE_SPHERE_POINT ? 5 : g->type == RTC_GEOMETRY_TYPE_DISC_POINT ? 6 : 7;
+    uploadedCurves[g] = d;
+    as_instance(d, xfm, w2l, instID, instMask);
     descs.push_back(d);
   };
   auto add_mesh = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
-    if (is_point(g->type)) {
-      if (xfm) fail(RTC_ERROR_INVALID_OPERATION, "instanced point geometries are not supported by the B200 back-end");
-      add_points(g, geomID);
-      return;
-    }
+    if (is_point(g->type)) { add_points(g, geomID, xfm, w2l, instID, instMask); return; }
     if (is_linear_curve(g->type) || is_cubic_curve(g->type)) {
-      if (xfm) fail(RTC_ERROR_INVALID_OPERATION, "instanced curve geometries are not supported by the B200 back-end");
-      if (is_cubic_curve(g->type)) add_cubic(g, geomID); else add_curves(g, geomID);
+      if (is_cubic_curve(g->type)) add_cubic(g, geomID, xfm, w2l, instID, instMask); else add_curves(g, geomID, xfm, w2l, instID, instMask);
       return;
     }
     const bool quad = g->type == RTC_GEOMETRY_TYPE_QUAD;
@@ -521,7 +539,7 @@ void commit_scene(SceneImpl* s) {
         const bool fresh = e == nullptr;
         if (fresh) { e = new SceneImpl::SubEntry(); e->gpu.device = s->dev->gpu; e->gpu.is_sub = true; }
         keep[g] = e;
-        const bool changed = fresh || e->modCounter != g->modCounter || e->sceneQuality != s->quality || e->robust != robust || e->gpu.device != s->dev->gpu;
+        const bool changed = fresh || e->serial != g->serial || e->modCounter != g->modCounter || e->sceneQuality != s->quality || e->robust != robust || e->gpu.device != s->dev->gpu;
         if (changed) {   // only a changed mesh is uploaded and built again
           e->gpu.robust = robust; e->gpu.general = 0; e->gpu.curves = 0;
           const size_t before = descs.size();
@@ -534,7 +552,7 @@ void commit_scene(SceneImpl* s) {
             for (int a = 0; a < 3; ++a) { e->gpu.bounds[a] = INFINITY; e->gpu.bounds[3 + a] = -INFINITY; }
           } else {
           const rtk::GeomDesc& d = descs.back();
-          if (!fresh && g->quality == RTC_BUILD_QUALITY_REFIT && e->gpu.root_valid && e->nprims == g->indices.count && e->nverts == g->vertices.count &&
+          if (!fresh && e->serial == g->serial && g->quality == RTC_BUILD_QUALITY_REFIT && e->gpu.root_valid && e->nprims == g->indices.count && e->nverts == g->vertices.count &&
               e->sceneQuality == s->quality && e->robust == robust && !getenv("RTCB200_NO_REFIT"))
             r2 = rtk::refit_scene(e->gpu, &d, 1, 0, err2);
           else
@@ -544,7 +562,7 @@ void commit_scene(SceneImpl* s) {
             for (auto& kv : keep) s->subs[kv.first] = kv.second;
             fail(r2 == (int)cudaErrorMemoryAllocation ? RTC_ERROR_OUT_OF_MEMORY : RTC_ERROR_UNKNOWN, err2);
           }
-          e->modCounter = g->modCounter; e->sceneQuality = s->quality; e->robust = robust; e->nprims = g->indices.count; e->nverts = g->vertices.count;
+          e->serial = g->serial; e->modCounter = g->modCounter; e->sceneQuality = s->quality; e->robust = robust; e->nprims = g->indices.count; e->nverts = g->vertices.count;
         }
         order.push_back(&e->gpu);
         dirty.push_back(changed ? 1 : 0);
@@ -627,7 +645,7 @@ void commit_scene(SceneImpl* s) {
   for (size_t id = 0; id < geoms.size(); ++id) {
     GeometryImpl* g = geoms[id];
     if (!g || !g->enabled) continue;
-    topo.push_back({g, g->indices.count, g->vertices.count});
+    topo.push_back({g, g->indices.count, g->vertices.count, g->serial});
     wantRefit = wantRefit && g->quality == RTC_BUILD_QUALITY_REFIT;
   }
   const bool canRefit = wantRefit && s->gpu.root_valid && s->everCommitted && topo == s->builtTopology && s->builtQuality == s->quality &&

@@ -405,13 +405,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, RTK_MIN_BLOCKS) trace_kernel(co
         if (p.excl_idx[e] == ti) return;
     }
     Ray lr = full_ray();
-    const Ray wr = lr;                               // world-space ray (curves are not instanced)
     bool visible = (c.w & lr.mask) != 0;             // ray mask (intersector_epilog.h:256-262)
     if (GENERAL) {   // b.w = descriptor index: instance mask (instance_intersector.cpp:19-22) + object-space ray
       const GeomDesc& d = p.descs[b.w];
       if (GENERAL == 2 && d.is_curve) {   // RTC_GEOMETRY_TYPE_ROUND_LINEAR_CURVE: cone-sphere test, u along the segment, v = 0
         CurveHit ch;
-        if (visible && curve_record_test(d, wr, tfar_tri, a, b, c, ch)) {
+        visible = visible && (d.inst_mask & lr.mask) != 0;   // an instanced curve / point geometry: the instance's mask as well,
+        if (d.has_xfm) to_object_space(d, lr);               // and the test runs on the object-space ray (t is unchanged)
+        if (visible && curve_record_test(d, lr, tfar_tri, a, b, c, ch)) {
           found = true;
           if (OCCLUDED) { ngy = 0; tgy = 0; sp = 0; top_y = 0; }
           else {

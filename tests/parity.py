@@ -355,3 +355,63 @@ def point_disagreements(rays, a, b, point_sets, margin=1e-4):
             explained |= (rim < margin) or (edge < margin)
         bad += 0 if explained else 1
     return int(differ.sum()), bad
+
+
+def instanced_hair_scene(seed=3, n_inst=6):
+    """A child scene of every curve / point kind around a triangle sphere + `n_inst` instances of it under random affine transforms
+    (rotation x non-uniform scale + translation) with instance masks, and rays through the lot.  Returns dict(mesh, curves, cubics,
+    points, xfms, masks, rays) in the formats OracleScene / the rtc.py helpers take."""
+    from embree_b200 import scenes
+    from embree_b200.rtc import make_rayhits
+    rng = np.random.RandomState(seed)
+    v, t = scenes.triangle_sphere(10)
+    v = (v * np.float32(0.5)).astype(np.float32)
+    cv, ci, _ = scenes.hair_ball(150, 4, seed=seed + 1, radius=0.5, length=0.5, width=0.03)
+    bv, bi, _tg = scenes.cubic_hair(120, "bezier", knots=7, seed=seed + 2, radius=0.5, step=0.08, width=0.02)
+    cv2, ci2, _ = scenes.hair_ball(150, 4, seed=seed + 5, radius=0.5, length=0.5, width=0.03)
+    bv2, bi2, _tg2 = scenes.cubic_hair(120, "bezier", knots=7, seed=seed + 6, radius=0.5, step=0.08, width=0.02)
+    def cloud():
+        pc = rng.normal(size=(300, 3)).astype(np.float32)
+        pc = pc / np.linalg.norm(pc, axis=1, keepdims=True) * rng.uniform(0.6, 1.1, (300, 1)).astype(np.float32)
+        return np.concatenate([pc, rng.uniform(0.02, 0.07, (300, 1)).astype(np.float32)], 1).astype(np.float32)
+    pv, pv2, pv3 = cloud(), cloud(), cloud()
+    pn = rng.normal(size=(300, 3)).astype(np.float32)
+    xfms, masks = [], []
+    for i in range(n_inst):
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        m = (q * rng.uniform(0.6, 1.4, 3)[None, :]).astype(np.float32)            # columns vx | vy | vz
+        p = (rng.uniform(-2.5, 2.5, 3)).astype(np.float32)
+        xfms.append(np.concatenate([m[:, 0], m[:, 1], m[:, 2], p]).astype(np.float32))
+        masks.append([0xFFFFFFFF, 0x1, 0x2, 0xFFFFFFFF, 0x3, 0xFFFFFFFF][i % 6])
+    m = 30000
+    org = rng.uniform(-4, 4, (m, 3)).astype(np.float32)
+    tgt = np.stack([x[9:12] for x in xfms])[rng.randint(0, n_inst, m)] + rng.normal(scale=0.5, size=(m, 3)).astype(np.float32)
+    d = ((tgt - org) * rng.uniform(0.3, 2.0, (m, 1))).astype(np.float32)
+    rays = make_rayhits(org, d)
+    rays["mask"][1::3] = 0x1
+    rays["mask"][2::3] = 0x2
+    rays["tfar"][::9] = 1.0
+    return dict(mesh=(v, t), curves=[(cv, ci, None, 1, 0xFFFFFFFF, False), (cv2, ci2, None, 2, 0x5, True)],
+                cubics=[(bv, bi, 3, 0xFFFFFFFF, "bezier", 4, None, False), (bv2, bi2, 4, 0xFFFFFFFF, "bezier", 4, None, True)],
+                points=[(pv, "sphere", None, 5, 0xFFFFFFFF), (pv2, "disc", None, 6, 0x6), (pv3, "oriented_disc", pn, 7, 0xFFFFFFFF)],
+                xfms=xfms, masks=masks, rays=rays)
+
+
+def build_instanced_hair(L, d, S):
+    """The scene of instanced_hair_scene() on a library behind the rtc.py binding: returns (top scene, child scene, keep-alive list)."""
+    child = L.rtcNewScene(d)
+    keep = [L.add_triangle_mesh(d, child, S["mesh"][0], S["mesh"][1], mask=0xFFFFFFFF, geom_id=0)[1]]
+    for (cv, ci, cf, gid, mask, flat) in S["curves"]:
+        keep.append(L.add_round_linear_curves(d, child, cv, ci, cf, mask=mask, geom_id=gid, flat=flat)[1])
+    for (bv, bi, gid, mask, basis, tess, tang, rnd) in S["cubics"]:
+        keep.append(L.add_flat_cubic_curves(d, child, bv, bi, basis, tess, tang, mask=mask, geom_id=gid, round=rnd)[1])
+    for (pv, kind, pn, gid, mask) in S["points"]:
+        keep.append(L.add_points(d, child, pv, kind, normals=pn if pn is not None else None, mask=mask, geom_id=gid)[1])
+    L.rtcCommitScene(child)
+    L.check(d)
+    top = L.rtcNewScene(d)
+    for i, m in enumerate(S["xfms"]):
+        L.add_instance(d, top, child, m, mask=S["masks"][i], geom_id=i)
+    L.rtcCommitScene(top)
+    L.check(d)
+    return top, child, keep

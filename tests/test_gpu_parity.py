@@ -589,11 +589,17 @@ def test_curves_large_vs_oracle_and_errors(b200, oracle):
     wocc = osc.trace(rays_of(rays), occluded=True, nthreads=16)
     assert ((occ["tfar"] == -np.inf) != (wocc["tfar"] == -np.inf)).sum() <= n_differ
     osc.free()
-    # a curve geometry cannot be instanced on this back-end, and its buffers have their own formats
+    # an identity instance of the curve scene reports the same hits with instID set; curve buffers have their own formats
     top = lib.rtcNewScene(dev)
     lib.add_instance(dev, top, sc, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32))
     lib.rtcCommitScene(top)
-    assert lib.rtcGetDeviceError(dev) == 3
+    lib.check(dev)
+    sub = rays[:50000].copy()
+    inst = lib.intersect(top, sub.copy(), "1M")
+    hit = got["geomID"][:50000] != 0xFFFFFFFF
+    irep = compare_hits(got[:50000], inst, TOL)      # (two segments hit at the same distance at a joint may swap: a tie)
+    assert irep["id_mismatch"] == 0 and irep["hit_miss_disagree"] == 0 and irep["tie"] <= 40, irep
+    assert (inst["tfar"].view(np.uint32) == got["tfar"][:50000].view(np.uint32)).all() and (inst["instID"][hit] == 0).all()
     g = lib.rtcNewGeometry(dev, 16)
     lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(cv), 0, 16, len(cv))
     assert lib.rtcGetDeviceError(dev) == 3                      # curves take FLOAT4 vertices
@@ -1090,6 +1096,22 @@ def test_two_level_dynamic_scene(b200, oracle, scene_quality, robust):
     lib.rtcEnableGeometry(geoms[21])
     enabled[20], enabled[21] = False, True
     check("slot handed to the other equal mesh")
+    # a mesh is REPLACED by a new geometry object of the same size, set up by the same sequence of calls (same modification counter)
+    # and very likely allocated where the released one lived: the kept BVH of the old object must not be taken for the new one's
+    v11 = (bufs[11][0][:bufs[11][1] * 3].reshape(-1, 3) + np.float32(0.6)).astype(np.float32)
+    lib.rtcDetachGeometry(sc, 11)
+    lib.rtcReleaseGeometry(geoms[11])
+    vpad = np.zeros(v11.size + 4, np.float32)
+    vpad[:v11.size] = v11.ravel()
+    g = lib.rtcNewGeometry(dev, RTC_GEOMETRY_TYPE_TRIANGLE)
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(vpad), 0, 12, len(v11))
+    lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_INDEX, 0, RTC_FORMAT_UINT3, _ptr(bufs[11][2]), 0, 12, len(bufs[11][2]))
+    lib.rtcSetGeometryMask(g, 0xFFFFFFFF)
+    lib.rtcCommitGeometry(g)
+    lib.rtcAttachGeometryByID(sc, g, 11)
+    geoms[11] = g
+    bufs[11] = (vpad, len(v11), bufs[11][2])
+    assert check("mesh replaced by a new geometry object").builder == 3
     # leaving the two-level regime: all but one mesh disabled -> the ordinary single BVH
     for i in range(1, len(geoms)):
         if enabled[i]:

@@ -95,8 +95,8 @@ def test_points_large_equal_the_oracle(b200, oracle, kind):
 
 
 def test_point_api_errors_and_updates(b200):
-    """Buffer formats / slots of scene_points.cpp:38-85, a missing normal buffer, instancing refused; moving the points and
-    re-committing gives the new hits."""
+    """Buffer formats / slots of scene_points.cpp:38-85, a missing normal buffer; moving the points and re-committing gives the new
+    hits; an instance of the point scene."""
     lib, dev = b200
     pv = np.array([[0, 0, 5, 1], [3, 0, 5, 0.5]], np.float32)
     pad = np.zeros((3, 4), np.float32)
@@ -139,8 +139,56 @@ def test_point_api_errors_and_updates(b200):
     out = lib.intersect(sc, rays.copy(), "1")
     assert np.allclose(out["tfar"], [8.0, 3.0, 4.5]) and out["primID"].tolist() == [0, 0, 1]
     top = lib.rtcNewScene(dev)
-    lib.add_instance(dev, top, sc, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32))
+    lib.add_instance(dev, top, sc, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 2], np.float32))     # the same spheres, 2 further along z
     lib.rtcCommitScene(top)
-    assert lib.rtcGetDeviceError(dev) == 3                      # point geometries cannot be instanced on this back-end
+    lib.check(dev)
+    out = lib.intersect(top, rays.copy(), "1")
+    assert np.allclose(out["tfar"], [10.0, 5.0, 6.5]) and (out["instID"] == 0).all() and out["primID"].tolist() == [0, 0, 1]
     lib.rtcReleaseScene(top)
     lib.rtcReleaseScene(sc)
+
+
+def test_instanced_curves_and_points(b200, oracle):
+    """Instances of a scene holding every curve and point kind (round / flat linear, flat / round Bezier, sphere / disc / oriented disc
+    points) under rotation, non-uniform scale and translation, with instance and geometry masks: hits (ids, instID, t, u, v, Ng in
+    object space) equal the C oracle's -- which tests/test_oracle.py pins to the live reference on the same scene -- and, when
+    oracle/_ref travelled to the box, the live reference's too."""
+    from tests.parity import build_instanced_hair, instanced_hair_scene, load_reference
+    lib, dev = b200
+    S = instanced_hair_scene()
+    top, child, keep = build_instanced_hair(lib, dev, S)
+    oc = oracle.scene([(S["mesh"][0], S["mesh"][1], 0, 0xFFFFFFFF)], curves=S["curves"], cubics=S["cubics"], points=S["points"])
+    ot = oracle.scene([], instances=[(oc, m, i, S["masks"][i]) for i, m in enumerate(S["xfms"])])
+    want = ot.trace(S["rays"].copy(), nthreads=8)
+    wocc = ot.trace(rays_of(S["rays"]), occluded=True, nthreads=8)
+    b = RTCBounds()
+    lib.rtcGetSceneBounds(top, C.byref(b))
+    got_b = np.array([b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], np.float32)
+    assert np.allclose(got_b, ot.bounds(), rtol=1e-5, atol=1e-5)
+    refs = [("oracle", want, wocc)]
+    R = load_reference()
+    if R is not None:
+        rdev = R.new_device(None)
+        rtop, rchild, rkeep = build_instanced_hair(R, rdev, S)
+        refs.append(("reference", R.intersect(rtop, S["rays"].copy(), "1"), R.occluded(rtop, rays_of(S["rays"]), "1")))
+        R.rtcReleaseScene(rtop)
+        R.rtcReleaseScene(rchild)
+        R.rtcReleaseDevice(rdev)
+    for mode in ("1M", "8", "16M"):
+        got = lib.intersect(top, S["rays"].copy(), mode)
+        occ = lib.occluded(top, rays_of(S["rays"]), mode)
+        for name, w, wo in refs:
+            rep = compare_hits(w, got, TOL)
+            per_geom = [int((got["geomID"] == g).sum()) for g in range(8)]
+            assert min(per_geom) > 40, (mode, per_geom)
+            # grazing rays of the curve kinds may flip (see the per-kind tests); nothing systematic
+            assert rep["id_mismatch"] + rep["hit_miss_disagree"] <= 6 and rep["max_rel_t"] <= 2e-4, (mode, name, rep)
+            same = (w["geomID"] == got["geomID"]) & (w["primID"] == got["primID"]) & (w["geomID"] != 0xFFFFFFFF)
+            assert (w["instID"][same] == got["instID"][same]).all() and (got["instID"][same] < len(S["xfms"])).all(), (mode, name)
+            for f in ("Ng_x", "Ng_y", "Ng_z", "u", "v"):
+                assert np.allclose(got[f][same], w[f][same], rtol=2e-3, atol=2e-4), (mode, name, f)
+            assert ((wo["tfar"] == -np.inf) != (occ["tfar"] == -np.inf)).sum() <= 6, (mode, name)
+    ot.free()
+    oc.free()
+    lib.rtcReleaseScene(top)
+    lib.rtcReleaseScene(child)
