@@ -597,9 +597,11 @@ def test_curves_large_vs_oracle_and_errors(b200, oracle):
     sub = rays[:50000].copy()
     inst = lib.intersect(top, sub.copy(), "1M")
     hit = got["geomID"][:50000] != 0xFFFFFFFF
-    irep = compare_hits(got[:50000], inst, TOL)      # (two segments hit at the same distance at a joint may swap: a tie)
-    assert irep["id_mismatch"] == 0 and irep["hit_miss_disagree"] == 0 and irep["tie"] <= 40, irep
-    assert (inst["tfar"].view(np.uint32) == got["tfar"][:50000].view(np.uint32)).all() and (inst["instID"][hit] == 0).all()
+    assert (inst["instID"][hit] == 0).all() and (inst["instID"][~hit] == 0xFFFFFFFF).all()
+    flat = inst.copy()
+    flat["instID"] = got["instID"][:50000]            # everything but the instance id must agree with the un-instanced scene
+    irep = compare_hits(got[:50000], flat, TOL)       # (the two segments that share a joint are hit at the same distance there and may swap: ties)
+    assert irep["id_mismatch"] == 0 and irep["hit_miss_disagree"] == 0 and irep["tie"] <= 0.02 * irep["hits"] and irep["max_rel_t"] <= 1e-6, irep
     g = lib.rtcNewGeometry(dev, 16)
     lib.rtcSetSharedGeometryBuffer(g, RTC_BUFFER_TYPE_VERTEX, 0, RTC_FORMAT_FLOAT3, _ptr(cv), 0, 16, len(cv))
     assert lib.rtcGetDeviceError(dev) == 3                      # curves take FLOAT4 vertices
