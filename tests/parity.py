@@ -317,16 +317,28 @@ def sweep_disagreements(rays, a, b, curve_geoms, tol=1e-4, cos_max=0.1):
     return int(differ.sum()), bad
 
 
-def point_disagreements(rays, a, b, point_sets, margin=1e-4):
+def point_disagreements(rays, a, b, point_sets, margin=1e-4, t_tol=None):
     """Point primitives: rays on which two implementations disagree (hit vs miss, or different primitives at different
     distances), and how many of them are NOT explained by a graze.  point_sets: {geomID: (vertices[n,4], kind, normals or None)}.
     A disagreement is explained when, for a point one side reports and the other does not, the exact (float64) test sits on a
     decision boundary within `margin` relative: the ray is tangent to the sphere / passes through the rim of the disc, or the hit
     distance coincides with tnear / tfar (the reference evaluates 1 / dir^2 with a refined hardware approximation, this library
-    with the exact reciprocal).  Returns (differing rays, unexplained ones)."""
+    with the exact reciprocal).  `t_tol`: also count the same point reported at distances that differ by more than t_tol relative to the
+    size of the problem in units of t (front hit on one side, back hit on the other).  Returns (differing rays, unexplained ones)."""
     ah, bh = a["geomID"] != 0xFFFFFFFF, b["geomID"] != 0xFFFFFFFF
     ulps = np.abs(a["tfar"].view(np.int32).astype(np.int64) - b["tfar"].view(np.int32).astype(np.int64))
     differ = (ah != bh) | (ah & bh & ((a["primID"] != b["primID"]) | (a["geomID"] != b["geomID"])) & (ulps > TIE_ULPS))
+    if t_tol is not None:   # the same point at different distances (front hit on one side, back hit on the other) is a difference too
+        k = np.nonzero(ah & bh & (a["primID"] == b["primID"]) & (a["geomID"] == b["geomID"]) & np.isin(a["geomID"], list(point_sets)))[0]
+        for g in point_sets:
+            kg = k[a["geomID"][k] == g]
+            pvg = point_sets[g][0]
+            o3 = np.stack([rays["org_x"][kg], rays["org_y"][kg], rays["org_z"][kg]], 1).astype(np.float64)
+            d3 = np.stack([rays["dir_x"][kg], rays["dir_y"][kg], rays["dir_z"][kg]], 1).astype(np.float64)
+            c3, r3 = pvg[a["primID"][kg], :3].astype(np.float64), pvg[a["primID"][kg], 3].astype(np.float64)
+            tscale = (np.linalg.norm(c3 - o3, axis=1) + r3) / np.maximum(np.linalg.norm(d3, axis=1), 1e-30)
+            err = np.abs(a["tfar"][kg].astype(np.float64) - b["tfar"][kg]) / np.maximum(np.maximum(np.abs(a["tfar"][kg]), tscale), 1e-30)
+            differ[kg[err > t_tol]] = True
     bad = 0
     for i in np.nonzero(differ)[0]:
         o = np.array([rays["org_x"][i], rays["org_y"][i], rays["org_z"][i]], np.float64)
@@ -344,14 +356,15 @@ def point_disagreements(rays, a, b, point_sets, margin=1e-4):
                 n = pn[int(x["primID"][i])].astype(np.float64)
                 t = float(c0 @ n) / float(d @ n)
                 ts = [t]
-                rim = abs(np.linalg.norm(o + t * d - c) - r) / r
+                rim = abs(np.linalg.norm(o + t * d - c) - r) / max(r, 1e-30)
             else:
                 proj = float(c0 @ d) / float(d @ d)
                 l = np.linalg.norm(c0 - proj * d)
-                rim = abs(l - r) / r
+                rim = abs(l - r) / max(r, 1e-30)
                 td = np.sqrt(max(r * r - l * l, 0.0) / float(d @ d))
                 ts = [proj] if kind == "disc" else [proj - td, proj + td]
-            edge = min(min(abs(t - tn), abs(t - tf)) / max(abs(t), 1e-30) for t in ts) if np.isfinite(tf) else min(abs(t - tn) / max(abs(t), 1e-30) for t in ts)
+            tscale = (np.linalg.norm(c0) + r) / max(np.linalg.norm(d), 1e-30)      # the size of the problem in units of t: a hit at t ~ 0 with tnear = 0 is a boundary case too
+            edge = min(min(abs(t - tn), abs(t - tf) if np.isfinite(tf) else np.inf) / max(abs(t), tscale, 1e-30) for t in ts)
             explained |= (rim < margin) or (edge < margin)
         bad += 0 if explained else 1
     return int(differ.sum()), bad
@@ -415,3 +428,60 @@ def build_instanced_hair(L, d, S):
     L.rtcCommitScene(top)
     L.check(d)
     return top, child, keep
+
+
+def point_edge_cases(seed=77):
+    """Point primitives and rays at the corners of the test's domain: zero and large radii, far-away centres, ray origins at the centre /
+    inside / on the surface, tnear / tfar windows that cut between the front and the back hit, direction lengths from 1e-3 to 1e3,
+    rays parallel to an oriented disc, non-unit normals.  Returns (vertices4, normals, rays)."""
+    from embree_b200.rtc import make_rayhits
+    rng = np.random.RandomState(seed)
+    n = 96
+    c = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    c[::8] *= np.float32(3000.0)                                   # far from the origin
+    r = rng.uniform(0.05, 0.3, n).astype(np.float32)
+    r[1::8] = 0.0                                                  # degenerate but valid (radius >= 0)
+    r[2::8] = 2.5                                                  # contains many ray origins
+    r[::8] *= np.float32(300.0)
+    pv = np.concatenate([c, r[:, None]], 1).astype(np.float32)
+    pn = (rng.normal(size=(n, 3)) * rng.uniform(0.1, 10.0, (n, 1))).astype(np.float32)
+    org, d, tn, tf = [], [], [], []
+    for i in range(n):
+        for k in range(40):
+            ci, ri = pv[i, :3].astype(np.float64), max(float(pv[i, 3]), 1e-3)
+            u = rng.normal(size=3)
+            u /= np.linalg.norm(u)
+            mode = k % 8
+            if mode == 0:      # from outside, through the point with some offset
+                o = ci + u * ri * rng.uniform(1.5, 6.0)
+                t = ci + rng.normal(size=3) * ri * 0.7 - o
+            elif mode == 1:    # origin at the centre
+                o, t = ci.copy(), u
+            elif mode == 2:    # origin inside
+                o = ci + u * ri * rng.uniform(0.0, 0.95)
+                t = rng.normal(size=3)
+            elif mode == 3:    # origin (nearly) on the surface, pointing in or out
+                o = ci + u * ri
+                t = -u + rng.normal(size=3) * 0.8
+            elif mode == 4:    # grazing
+                w = np.cross(u, rng.normal(size=3))
+                w /= np.linalg.norm(w)
+                o = ci + u * ri * rng.uniform(0.98, 1.02) - w * ri * 4.0
+                t = w
+            elif mode == 5:    # parallel to the oriented disc's plane
+                nn = pn[i].astype(np.float64)
+                w = np.cross(nn, rng.normal(size=3))
+                o = ci - w / np.linalg.norm(w) * ri * 3.0 + nn / np.linalg.norm(nn) * ri * rng.uniform(-0.2, 0.2)
+                t = w
+            else:
+                o = rng.uniform(-1.5, 1.5, 3)
+                t = ci - o + rng.normal(size=3) * ri
+            t = t / max(np.linalg.norm(t), 1e-30) * (10.0 ** rng.uniform(-3, 3))
+            org.append(o); d.append(t)
+            dist = np.linalg.norm(ci - o) / np.linalg.norm(t)
+            tn.append(0.0 if k % 3 else dist * rng.uniform(0.5, 1.2))
+            tf.append(np.inf if k % 5 else dist * rng.uniform(0.8, 1.5))
+    rays = make_rayhits(np.array(org, np.float32), np.array(d, np.float32))
+    rays["tnear"] = np.array(tn, np.float32)
+    rays["tfar"] = np.maximum(np.array(tf, np.float32), rays["tnear"])
+    return pv, pn, rays

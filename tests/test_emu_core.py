@@ -384,3 +384,35 @@ def test_point_test_equals_oracle(emu, oracle, kind):
     assert hits > 1000
     assert np.allclose(sc.bounds(), np.concatenate([(pv[:, :3] - pv[:, 3:]).min(0), (pv[:, :3] + pv[:, 3:]).max(0)]))
     sc.free()
+
+
+@pytest.mark.parametrize("kind", ["sphere", "disc", "oriented_disc"])
+def test_point_test_edge_cases_equal_oracle(emu, oracle, kind):
+    """The corners of the point tests' domain (tests/parity.py point_edge_cases): host instantiation of rt_core.cuh point_test, brute
+    force, against the C oracle's BVH traversal -- the same winner and bit-identical t / Ng (zero radii, far centres, origins at the
+    centre / inside / on the surface, tnear / tfar windows, |dir| from 1e-3 to 1e3, rays parallel to a disc, non-unit normals)."""
+    from tests.parity import POINT_KINDS, point_edge_cases
+    pv, pn, rays = point_edge_cases()
+    sc = oracle.scene([], points=[(pv, kind, pn if kind == "oriented_disc" else None, 2, 0xFFFFFFFF)])
+    want = sc.trace(rays.copy())
+    sc.free()
+    emu.emu_point_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    out = np.zeros(6, np.float32)
+    hits = ties = 0
+    for k in range(len(rays)):
+        r = rays[k]
+        ray = np.array([r["org_x"], r["org_y"], r["org_z"], r["tnear"], r["dir_x"], r["dir_y"], r["dir_z"], r["tfar"]], np.float32)
+        best = emu.emu_point_closest(ray.ctypes.data, pv.ctypes.data, pn.ctypes.data if kind == "oriented_disc" else None, len(pv),
+                                     POINT_KINDS.index(kind), out.ctypes.data)
+        w = want[k]
+        if best < 0:
+            assert w["geomID"] == 0xFFFFFFFF, k
+            continue
+        hits += 1
+        assert w["geomID"] == 2 and np.float32(out[0]).view(np.uint32) == w["tfar"].view(np.uint32), (k, best, out, w)
+        if w["primID"] != best:      # two points at exactly the same distance (t = 0 from inside two large spheres): order dependent
+            ties += 1
+            continue
+        exp = np.array([w["tfar"], w["u"], w["v"], w["Ng_x"], w["Ng_y"], w["Ng_z"]], np.float32)
+        assert (out.view(np.uint32) == exp.view(np.uint32)).all(), (k, out, w)
+    assert hits > 1000 and ties <= 0.02 * hits, (hits, ties)

@@ -426,3 +426,34 @@ def test_oracle_instanced_curves_and_points_vs_live_reference(oracle):
     assert np.allclose(ot.bounds(), [b.lower_x, b.lower_y, b.lower_z, b.upper_x, b.upper_y, b.upper_z], rtol=1e-5, atol=1e-5)
     ot.free()
     oc.free()
+
+
+@pytest.mark.parametrize("kind", ["sphere", "disc", "oriented_disc"])
+def test_oracle_point_edge_cases_vs_live_reference(oracle, kind):
+    """The corners of the point tests' domain (tests/parity.py point_edge_cases: zero / huge radii, far centres, origins at the centre,
+    inside and on the surface, tnear / tfar cutting between front and back hit, |dir| from 1e-3 to 1e3, rays parallel to a disc,
+    non-unit normals): oracle next to the live reference; a difference must sit on a decision boundary of the test."""
+    from tests.parity import load_reference, point_disagreements, point_edge_cases
+    R = load_reference()
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    pv, pn, rays = point_edge_cases()
+    dev = R.new_device(None)
+    sc = R.rtcNewScene(dev)
+    _, keep = R.add_points(dev, sc, pv, kind, normals=pn, geom_id=0)
+    R.rtcCommitScene(sc)
+    R.check(dev)
+    want = R.intersect(sc, rays.copy(), "1")
+    wocc = R.occluded(sc, rays_of(rays), "1")
+    R.rtcReleaseScene(sc)
+    R.rtcReleaseDevice(dev)
+    o = oracle.scene([], points=[(pv, kind, pn if kind == "oriented_disc" else None, 0, 0xFFFFFFFF)])
+    got = o.trace(rays.copy())
+    gocc = o.trace(rays_of(rays), occluded=True)
+    o.free()
+    rep = compare_hits(want, got, 1e-4)
+    # (t_tol: the same point at different distances counts as a difference as well, measured against the size of the problem in units of t --
+    # a hit at t ~ 1e-10 from an origin on the surface has no relative accuracy)
+    n_differ, unexplained = point_disagreements(rays, want, got, {0: (pv, kind, pn)}, margin=2e-4, t_tol=1e-4)
+    assert rep["hits"] > 1000 and unexplained == 0 and n_differ <= 0.01 * len(rays), (rep, n_differ, unexplained)
+    assert ((wocc["tfar"] == -np.inf) != (gocc["tfar"] == -np.inf)).sum() <= n_differ
