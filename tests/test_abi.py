@@ -136,3 +136,48 @@ def test_error_strings():
     lib = embree_b200.load()
     assert lib.rtcGetErrorString(0) == b"No error"
     assert lib.rtcGetErrorString(3) == b"Invalid operation"
+
+
+def _prototypes(text):
+    """{function name: (return type, [parameter types])} of every rtc* declaration in a header; types are compared modulo
+    struct / enum / const keywords, parameter names and export macros."""
+    import re
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    text = re.sub(r"\s+", " ", text)
+    macros = r"\b(RTC_API|RTC_API_EXTERN_C|RTC_SYCL_API|RTCB200_API|RTC_SYCL_INDIRECTLY_CALLABLE|RTC_FORCEINLINE|RTC_OPTIONAL_ARGUMENT|extern|struct|enum|const)\b"
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(rtc[A-Z][A-Za-z0-9]*)\s*\(([^;{]*?)\)\s*;", text):
+        ret = re.sub(macros, "", m.group(1)).replace(" ", "")
+        params = []
+        for a in (m.group(3).split(",") if m.group(3).strip() else []):
+            a = re.sub(r"\s+", " ", re.sub(macros, "", a)).strip()
+            named = re.match(r"^(.*?)([A-Za-z_][A-Za-z0-9_]*)$", a)
+            if named and named.group(1).strip():
+                a = named.group(1)
+            params.append(a.replace(" ", ""))
+        out[m.group(2)] = (ret, params)
+    return out
+
+
+def test_prototypes_match_the_reference_headers():
+    """Every rtc* function include/embree4_b200.h declares has the reference's signature (return type, parameter types and order,
+    include/embree4/rtcore_*.h); the reference functions the header does not declare are exactly the stubs outside the path."""
+    import glob
+    ref_dir = "/root/reference/include/embree4"
+    if not os.path.isdir(ref_dir):
+        pytest.skip("reference headers not present")
+    ref = {}
+    for f in glob.glob(os.path.join(ref_dir, "*.h")):
+        ref.update(_prototypes(open(f).read()))
+    mine = _prototypes(open(HEADER).read())
+    shared = [n for n in mine if n in ref]
+    assert len(shared) >= 85
+    wrong = {n: (ref[n], mine[n]) for n in shared if ref[n] != mine[n]}
+    assert not wrong, wrong
+    undeclared = set(ref) - set(mine)
+    unsupported = ("Forward", "PointQuery", "BVH", "Collide", "HalfEdge", "GeometryFace", "SYCL", "WithQueue", "InvokeIntersectFilter",
+                   "InvokeOccludedFilter", "BoundsFunction", "DisplacementFunction", "InstancedScenes", "IntersectFunction", "OccludedFunction",
+                   "PointQueryFunction", "Subdivision", "Topology", "TransformQuaternion", "UserPrimitiveCount", "ThreadLocalAlloc")
+    assert all(any(u in n for u in unsupported) for n in undeclared), sorted(n for n in undeclared if not any(u in n for u in unsupported))
