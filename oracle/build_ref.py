@@ -101,6 +101,13 @@ def isa_files(isa, lowest=SSE2, lowest_avx=AVX):
     return f
 
 
+def write_if_changed(path, text):
+    """Generated headers keep their time stamp when their content is unchanged, so that a second run rebuilds nothing."""
+    if os.path.exists(path) and open(path).read() == text:
+        return
+    open(path, "w").write(text)
+
+
 def gen_headers(gen, stat):
     os.makedirs(f"{gen}/include/embree4", exist_ok=True)
     os.makedirs(f"{gen}/kernels/common", exist_ok=True)  # so that "../config.h" resolves via -I
@@ -124,7 +131,7 @@ def gen_headers(gen, stat):
     t = re.sub(r"#cmakedefine01 (\w+)", cmdef01, t)
     t = re.sub(r"#cmakedefine (\w+)", cmdef, t)
     t = re.sub(r"@(\w+)@", lambda m: subst[m.group(1)], t)
-    open(f"{gen}/include/embree4/rtcore_config.h", "w").write(t)
+    write_if_changed(f"{gen}/include/embree4/rtcore_config.h", t)
     # --- config.h from kernels/config.h.in
     t = open(f"{REF}/kernels/config.h.in").read()
     cfg_on = {"EMBREE_RAY_MASK", "EMBREE_FILTER_FUNCTION", "EMBREE_GEOMETRY_TRIANGLE", "EMBREE_GEOMETRY_QUAD", "EMBREE_GEOMETRY_CURVE",
@@ -136,8 +143,8 @@ def gen_headers(gen, stat):
     t = t.replace("@EMBREE_CURVE_SELF_INTERSECTION_AVOIDANCE_FACTOR@", "2.0")
     t = t.replace('#include "../include/embree4/rtcore_config.h"',
                   f'#include "{gen}/include/embree4/rtcore_config.h"')
-    open(f"{gen}/kernels/config.h", "w").write(t)
-    open(f"{gen}/kernels/hash.h", "w").write('#define RTC_HASH "0"\n')
+    write_if_changed(f"{gen}/kernels/config.h", t)
+    write_if_changed(f"{gen}/kernels/hash.h", '#define RTC_HASH "0"\n')
 
 
 def main():
