@@ -321,8 +321,6 @@ void commit_scene(SceneImpl* s) {
   std::unordered_map<GeometryImpl*, std::pair<void*, void*>> uploaded;   // a mesh instanced many times is uploaded once
   bool instanced = false, quads = false, curves = false;
   float instBounds[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  // round linear curves (scene_line_segments.cpp): float4 vertices, one index per segment, neighbour flags from the
-  // application or derived from the index buffer as LineSegments::commit does (:209-232)
   // an instanced curve / point geometry: the records stay in OBJECT space (the trace kernel takes the ray there, as for instanced
   // triangles), the builder boxes them in world space, the API bounds come from the instance box
   auto as_instance = [](rtk::GeomDesc& d, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
@@ -332,6 +330,8 @@ void commit_scene(SceneImpl* s) {
     memcpy(d.w2l, w2l, sizeof d.w2l);
   };
   std::unordered_map<GeometryImpl*, rtk::GeomDesc> uploadedCurves;   // a curve / point geometry instanced many times is uploaded once
+  // round linear curves (scene_line_segments.cpp): float4 vertices, one index per segment, neighbour flags from the
+  // application or derived from the index buffer as LineSegments::commit does (:209-232)
   auto add_curves = [&](GeometryImpl* g, uint32_t geomID, const float* xfm, const float* w2l, uint32_t instID, uint32_t instMask) {
     { auto it = uploadedCurves.find(g); if (it != uploadedCurves.end()) { rtk::GeomDesc d = it->second; d.geomID = geomID; as_instance(d, xfm, w2l, instID, instMask); descs.push_back(d); curves = true; return; } }
     const size_t nsegs = g->indices.count, nverts = g->vertices.count;
